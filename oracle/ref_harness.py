@@ -1,0 +1,431 @@
+"""Runs the reference's OWN source for the HideAndSeek step on CPU (build container only).
+
+TEST INFRASTRUCTURE.  This module needs /root/reference and therefore only runs in
+the build container; it is used by ``oracle/gen_golden.py`` to (a) validate the
+restatement in ``oracle/hs_oracle.py`` and (b) write the fixtures under
+``tests/golden/``.  Nothing here is copied from the reference: the reference files
+are parsed with ``ast`` where they lie and the wanted function bodies are exec'd
+against a fake ``self`` (recipe: SURVEY.md Appendix C).
+
+The one piece the reference does not contain -- the PhysX step -- is supplied by
+``hs_oracle.rigid_body_step`` (parity unpinned, see that module's header).
+"""
+from __future__ import annotations
+
+import ast
+import collections
+import importlib.util
+import math
+import sys
+import textwrap
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+import yaml
+
+from . import hs_oracle as O
+
+REF = Path("/root/reference")
+
+
+# ----------------------------------------------------------------------------
+# a dict that behaves enough like tensordict.TensorDict for the extracted methods
+# ----------------------------------------------------------------------------
+class TD(dict):
+    def __init__(self, source=None, batch_size=None, device=None):
+        super().__init__()
+        self.batch_size = list(batch_size) if batch_size is not None else []
+        for k, v in (source or {}).items():
+            self[k] = v
+
+    def __setitem__(self, key, value):
+        if isinstance(key, tuple) and all(isinstance(k, str) for k in key):
+            if len(key) == 1:
+                return self.__setitem__(key[0], value)
+            if key[0] not in self:
+                dict.__setitem__(self, key[0], TD({}, self.batch_size))
+            self[key[0]][key[1:]] = value
+            return
+        if isinstance(key, str):
+            if isinstance(value, dict) and not isinstance(value, TD):
+                value = TD(value, self.batch_size)
+            dict.__setitem__(self, key, value)
+            return
+        # index assignment: td[env_ids] = scalar
+        for v in self.values():
+            if isinstance(v, TD):
+                v[key] = value
+            else:
+                v[key] = value
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and all(isinstance(k, str) for k in key):
+            out = self
+            for k in key:
+                out = dict.__getitem__(out, k)
+            return out
+        return dict.__getitem__(self, key)
+
+    def set(self, key, value):
+        self[key] = value
+        return self
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def update(self, other):
+        for k, v in other.items():
+            if isinstance(v, dict) and k in self and isinstance(self[k], TD):
+                self[k].update(v)
+            else:
+                self[k] = v
+        return self
+
+    def clone(self):
+        return TD({k: v.clone() for k, v in self.items()}, self.batch_size)
+
+    def flat(self, prefix=()):
+        out = {}
+        for k, v in self.items():
+            if isinstance(v, TD):
+                out.update(v.flat(prefix + (k,)))
+            else:
+                out[prefix + (k,)] = v
+        return out
+
+
+# ----------------------------------------------------------------------------
+# module loading / AST extraction
+# ----------------------------------------------------------------------------
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__path__ = []
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _load(modname, relpath):
+    spec = importlib.util.spec_from_file_location(modname, REF / relpath)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_LOADED = {}
+
+
+def load_reference():
+    """Path-loads the importable reference modules and extracts the hot methods."""
+    if _LOADED:
+        return _LOADED
+    _stub("omni_drones")
+    _stub("omni_drones.utils")
+    _stub("omni_drones.controllers")
+    _stub("omni_drones.actuators")
+    _stub("tensordict", TensorDict=TD)
+    ut = _load("omni_drones.utils.torch", "omni_drones/utils/torch.py")
+    rg = _load("omni_drones.actuators.rotor_group", "omni_drones/actuators/rotor_group.py")
+    lc = _load("omni_drones.controllers.lee_position_controller",
+               "omni_drones/controllers/lee_position_controller.py")
+
+    ns = dict(torch=torch, np=np, math=math, collections=collections, vmap=torch.vmap,
+              TensorDict=TD, TensorDictBase=TD, D=torch.distributions,
+              cpos=ut.cpos, off_diag=ut.off_diag, quat_axis=ut.quat_axis, others=ut.others,
+              quat_rotate=ut.quat_rotate, quat_rotate_inverse=ut.quat_rotate_inverse,
+              normalize=ut.normalize, euler_to_quaternion=ut.euler_to_quaternion,
+              symlog=ut.symlog, Optional=None)
+
+    def extract(relpath, names, cls=None, strip_decorators=True):
+        src = (REF / relpath).read_text()
+        tree = ast.parse(src)
+        body = tree.body
+        if cls is not None:
+            body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+        out = {}
+        for node in body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                if strip_decorators:
+                    node.decorator_list = []
+                mod = ast.Module(body=[node], type_ignores=[])
+                code = compile(ast.fix_missing_locations(mod), f"<ref:{relpath}:{node.name}>", "exec")
+                local = {}
+                exec(code, ns, local)
+                out[node.name] = local[node.name]
+        missing = set(names) - set(out)
+        assert not missing, f"not found in {relpath}: {missing}"
+        return out
+
+    hs = "omni_drones/envs/hide_and_seek/hideandseek.py"
+    free = extract(hs, ["is_perpendicular_line_intersecting_segment", "is_line_blocked_by_cylinder",
+                        "select_unoccupied_positions", "grid_to_continuous", "continuous_to_grid",
+                        "set_outside_circle_to_one"])
+    ns.update(free)
+    env_m = extract(hs, ["_pre_sim_step", "_compute_state_and_obs", "_compute_reward_and_done",
+                         "_get_dummy_policy_prey", "_reset_idx", "rejection_sampling_random_cylinder"],
+                    cls="HideAndSeek")
+    mr = "omni_drones/robots/drone/multirotor.py"
+    ns.update(extract(mr, ["separation"]))
+    drone_m = extract(mr, ["apply_action", "get_state", "_reset_idx", "downwash"], cls="MultirotorBase")
+    tr = extract("omni_drones/utils/torchrl/transforms.py", ["_inv_call"], cls="PIDRateController")
+    ie = extract("omni_drones/envs/isaac_env.py", ["_reset", "_step", "get_env_poses"], cls="IsaacEnv")
+    tp = ast.parse((REF / "omni_drones/learning/mappo.py").read_text())
+    node = next(n for n in tp.body if isinstance(n, ast.ClassDef) and n.name == "TP_net")
+    tp_ns = dict(torch=torch, nn=torch.nn)
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "<ref:TP_net>", "exec"), tp_ns)
+    _LOADED.update(ut=ut, rg=rg, lc=lc, env=env_m, drone=drone_m, transform=tr, isaac=ie,
+                   TP_net=tp_ns["TP_net"], ns=ns)
+    return _LOADED
+
+
+# ----------------------------------------------------------------------------
+# fakes for the simulator views
+# ----------------------------------------------------------------------------
+class _View:
+    """pos/rot/vel accessors over tensors held in a dict (stands in for omni_drones/views/*)."""
+
+    def __init__(self, store, pos, rot=None, vel=None):
+        self.s, self.kp, self.kr, self.kv = store, pos, rot, vel
+
+    def get_world_poses(self, clone=False):
+        p = self.s[self.kp]
+        r = self.s[self.kr] if self.kr else torch.zeros(*p.shape[:-1], 4)
+        return (p.clone(), r.clone()) if clone else (p, r)
+
+    def set_world_poses(self, positions=None, orientations=None, env_indices=None):
+        if positions is not None:
+            self.s[self.kp][env_indices] = positions
+        if orientations is not None and self.kr:
+            self.s[self.kr][env_indices] = orientations
+
+    def get_velocities(self, clone=False):
+        v = self.s[self.kv]
+        return v.clone() if clone else v
+
+    def set_velocities(self, velocities, env_indices=None):
+        full = self.s[self.kv]
+        if env_indices is None:
+            full[:] = velocities
+        elif velocities.shape[0] == full.shape[0]:
+            full[env_indices] = velocities[env_indices]
+        else:
+            full[env_indices] = velocities
+
+
+class _Wrench:
+    def __init__(self):
+        self.forces = None
+        self.torques = None
+
+    def apply_forces_and_torques_at_pos(self, forces=None, torques=None, positions=None, is_global=True):
+        self.forces = None if forces is None else forces.clone()
+        self.torques = None if torques is None else torques.clone()
+
+
+class _Obj:
+    pass
+
+
+class RefEnv:
+    """The reference's HideAndSeek step, driven from its extracted source."""
+
+    def __init__(self, P: O.HSParams, E: int, use_random_cylinder=True, scenario_flag="empty",
+                 min_cylinders=4, tp_state_dict=None):
+        R = load_reference()
+        self.R, self.P, self.E = R, P, E
+        A, C = P.num_agents, P.num_cylinders
+        dev = torch.device("cpu")
+        store = dict(dpos=torch.zeros(E, A, 3), drot=torch.zeros(E, A, 4), dvel=torch.zeros(E, A, 6),
+                     tpos=torch.zeros(E, 1, 3), tvel=torch.zeros(E, 1, 6), cpos=torch.zeros(E, C, 3))
+        store["drot"][..., 0] = 1.0
+        store["cpos"][..., 2] = -20.0
+        self.store = store
+
+        params = yaml.safe_load((REF / "omni_drones/robots/assets/usd/crazyflie.yaml").read_text())
+        # ---- drone (MultirotorBase stand-in, attributes as multirotor.py:159-263 sets them)
+        d = _Obj()
+        d.shape, d.n, d.num_rotors, d.device, d.dt = (E, A), A, 4, dev, P.dt
+        d.params, d.is_articulation, d.rotor_joint_indices = params, True, None
+        d.use_force_sensor, d.randomization = False, {}
+        rotors_mod = R["rg"].RotorGroup(params["rotor_configuration"], dt=P.dt)
+        d.rotors_module = rotors_mod
+        d.rotors = lambda cmds, prm: torch.func.functional_call(rotors_mod, prm, (cmds,))
+        d.rotors.f_inv = torch.sqrt
+        d.rotor_params = {k: v.detach().expand(E, A, *v.shape).clone() for k, v in rotors_mod.named_parameters()}
+        d.throttle = d.rotor_params["throttle"]
+        d.directions, d.KF, d.KM = d.rotor_params["directions"], d.rotor_params["KF"], d.rotor_params["KM"]
+        d.MAX_ROT_VEL = torch.as_tensor(params["rotor_configuration"]["max_rotation_velocities"]).float()
+        d.thrusts, d.torques, d.forces = torch.zeros(E, A, 4, 3), torch.zeros(E, A, 3), torch.zeros(E, A, 3)
+        d.pos, d.rot = store["dpos"].clone(), store["drot"].clone()
+        d.throttle_difference = torch.zeros(E, A)
+        d.heading, d.up = torch.zeros(E, A, 3), torch.zeros(E, A, 3)
+        d.vel = d.vel_w = torch.zeros(E, A, 6)
+        d.vel_b = torch.zeros(E, A, 6)
+        d.acc = d.acc_w = torch.zeros(E, A, 6)
+        d.jerk = torch.zeros(E, A, 6)
+        d.masses = torch.ones(E, A, 1) * torch.tensor(params["mass"])
+        d.gravity = torch.ones(E, A, 1) * torch.tensor(P.total_mass) * 9.81       # sum of body masses
+        d.drag_coef = torch.zeros(E, A, 1) * torch.tensor(params["drag_coef"])
+        d.rotor_pos_offset = torch.zeros(E, A, 4, 3)
+        d._envs_positions = torch.zeros(E, 1, 3)
+        dv = _View(store, "dpos", "drot", "dvel")
+        d.get_world_poses, d.set_world_poses = dv.get_world_poses, dv.set_world_poses
+        d.get_velocities, d.set_velocities = dv.get_velocities, dv.set_velocities
+        d.rotors_view = _Obj()
+        d.rotors_view.get_world_poses = lambda clone=False: (
+            store["dpos"].unsqueeze(2).expand(E, A, 4, 3), store["drot"].unsqueeze(2).expand(E, A, 4, 4))
+        self.rotor_wrench, self.base_wrench = _Wrench(), _Wrench()
+        d.rotors_view.apply_forces_and_torques_at_pos = self.rotor_wrench.apply_forces_and_torques_at_pos
+        d.base_link = self.base_wrench
+        d.downwash = R["drone"]["downwash"]
+        for name in ("apply_action", "get_state", "_reset_idx"):
+            setattr(d, name, types.MethodType(R["drone"][name], d))
+        d.rotors_f_inv = torch.sqrt
+        # MultirotorBase._reset_idx uses self.rotors.f_inv
+        self.drone = d
+
+        # ---- env (HideAndSeek stand-in; attribute list: SURVEY.md Appendix C item 5)
+        e = _Obj()
+        e.num_envs, e.num_agents, e.num_cylinders, e.device, e.batch_size = E, A, C, dev, [E]
+        e.drone = d
+        e.target = _View(store, "tpos", None, "tvel")
+        e.cylinders = _View(store, "cpos")
+        e.envs_positions = torch.zeros(E, 3)
+        e.cylinder_height, e.cylinder_size = P.max_height, P.cylinder_size
+        e.obs_max_cylinder, e.mask_value = P.obs_max_cylinder, P.mask_value
+        e.drone_detect_radius, e.target_detect_radius = P.drone_detect_radius, P.target_detect_radius
+        e.progress_buf = torch.zeros(E)
+        e.max_episode_length = P.max_episode_length
+        e.use_TP_net, e.use_obstacles = P.use_tp_net, 0
+        e.history_step = P.history_step
+        e.history_data = collections.deque(maxlen=P.history_step)
+        e.future_predcition_step, e.arena_size, e.max_height = P.future_step, P.arena_size, P.max_height
+        e.time_encoding_dim = 4
+        e._should_render = lambda substep: False
+        e.use_eval = 0
+        e.catch_radius, e.collision_radius = P.catch_radius, P.collision_radius
+        e.dist_reward_coef, e.detect_reward_coef = P.dist_reward_coef, P.detect_reward_coef
+        e.catch_reward_coef, e.speed_coef, e.collision_coef = P.catch_reward_coef, P.speed_coef, P.collision_coef
+        e.init_smoothness_coef, e.smooth_lr, e.update_epoch, e.max_smoothness_coef = P.smoothness_coef, 0.0, 0, 5.0
+        e.use_deployment = P.use_deployment
+        e.cfg = _Obj()
+        e.cfg.task = _Obj()
+        e.cfg.task.v_drone = P.v_drone
+        e.v_prey = P.v_prey
+        e.env_ids = torch.arange(E)
+        e.stats = TD({k: torch.zeros(E, 1) for k in O.STAT_KEYS}, [E])
+        e.info = TD({"drone_state": torch.zeros(E, A, 13), "prev_action": torch.zeros(E, A, 4)}, [E])
+        e.prev_actions = torch.zeros(E, A, 4)
+        e.use_random_cylinder, e.scenario_flag = use_random_cylinder, scenario_flag
+        e.max_cylinders, e.min_cylinders = C, min_cylinders
+        e.use_fixed_num, e.fixed_num = False, None
+        e.invalid_z, e.boundary = -20.0, P.arena_size - 0.1
+        a = P.arena_size / math.sqrt(2.0)
+        U = torch.distributions.Uniform
+        e.init_drone_pos_dist = U(torch.tensor([0.1, -a + 0.1]), torch.tensor([a - 0.1, a - 0.1]))
+        e.init_target_pos_dist = U(torch.tensor([-a + 0.1, -a + 0.1]), torch.tensor([-0.1, a - 0.1]))
+        e.init_drone_pos_dist_z = U(torch.tensor([P.max_height / 2 - 0.1]), torch.tensor([P.max_height / 2 + 0.1]))
+        e.init_target_pos_dist_z = U(torch.tensor([P.max_height / 2 - 0.1]), torch.tensor([P.max_height / 2 + 0.1]))
+        e.init_rpy_dist = U(torch.tensor([-0.2, -0.2, 0.0]) * torch.pi, torch.tensor([0.2, 0.2, 0.2]) * torch.pi)
+        e.active_cylinders = torch.zeros(E, 1)
+        if P.use_tp_net:
+            e.TP = R["TP_net"](input_dim=7 + 3 * A, output_dim=3 * P.future_step,
+                               future_predcition_step=P.future_step, window_step=1)
+            if tp_state_dict is not None:
+                e.TP.load_state_dict(tp_state_dict)
+            e.TP.requires_grad_(False)
+        e.sim = _Obj()
+        e.sim.step = self._sim_step
+        e.sim._physics_sim_view = _Obj()
+        e.sim._physics_sim_view.flush = lambda: None
+        e._post_sim_step = lambda td: None
+        for name, fn in R["env"].items():
+            setattr(e, name, types.MethodType(fn, e))
+        for name, fn in R["isaac"].items():
+            setattr(e, name, types.MethodType(fn, e))
+        self.env = e
+
+        # ---- the PIDrate transform (transforms.py:404-459)
+        t = _Obj()
+        t.controller = R["lc"].PIDRateController(P.dt, 9.81, params)
+        t.controller.requires_grad_(False)
+        t.action_key = ("agents", "action")
+        t.target_clip, t.max_thrust_ratio, t.fixed_yaw = params["target_clip"], params["max_thrust_ratio"], params["fixed_yaw"]
+        t._inv_call = types.MethodType(R["transform"]["_inv_call"], t)
+        self.transform = t
+        self.td = None
+
+    # PhysX stand-in: consumes the wrench recorded by apply_action, then clears it
+    def _sim_step(self, render=False):
+        P, s = self.P, self.store
+        q = s["drot"]
+        if self.rotor_wrench.forces is not None:
+            thrusts = self.rotor_wrench.forces.reshape(self.E, P.num_agents, 4, 3)[..., 2]
+            tau_w = self.base_wrench.torques.reshape(self.E, P.num_agents, 3)
+            yaw = O.quat_apply_inverse(q, tau_w)[..., 2]
+            ext = self.base_wrench.forces.reshape(self.E, P.num_agents, 3)
+        else:
+            thrusts = yaw = ext = None
+        p, q2, v, w = O.rigid_body_step(P, s["dpos"], q, s["dvel"][..., :3], s["dvel"][..., 3:], thrusts, yaw, ext)
+        s["dpos"][:], s["drot"][:] = p, q2
+        s["dvel"][..., :3], s["dvel"][..., 3:] = v, w
+        s["tpos"][:] = s["tpos"] + P.dt * s["tvel"][..., :3]
+        self.rotor_wrench.forces = self.base_wrench.forces = self.base_wrench.torques = None
+
+    # -- driving ---------------------------------------------------------------
+    def reset_with(self, mask, init):
+        """Reset through IsaacEnv._reset, but with the initial poses injected instead of sampled."""
+        e = self.env
+        orig = e._reset_idx
+
+        def injected(env_ids):
+            # run the reference _reset_idx for its bookkeeping, then overwrite the sampled poses
+            orig(env_ids)
+        # Patch the pose setters so that the *sampled* poses are replaced by `init`
+        d = self.drone
+        real_set = d.set_world_poses
+        real_tset = e.target.set_world_poses
+        real_cset = e.cylinders.set_world_poses
+
+        def dset(positions=None, orientations=None, env_indices=None):
+            real_set(init["drone_pos"][env_indices], init["drone_rot"][env_indices], env_indices)
+
+        def tset(positions=None, orientations=None, env_indices=None):
+            real_tset(positions=init["target_pos"][env_indices].unsqueeze(1), env_indices=env_indices)
+
+        def cset(positions=None, orientations=None, env_indices=None):
+            real_cset(positions=init["cyl_pos"][env_indices], env_indices=env_indices)
+
+        d.set_world_poses, e.target.set_world_poses, e.cylinders.set_world_poses = dset, tset, cset
+        if not e.use_random_cylinder:
+            # fixed scenarios never call cylinders.set_world_poses in _reset_idx
+            ids = mask.nonzero().squeeze(-1)
+            real_cset(positions=init["cyl_pos"][ids], env_indices=ids)
+            e.active_cylinders = (init["cyl_pos"][..., 2] > 0).sum(-1, keepdim=True).float()
+        try:
+            td_in = TD({"_reset": mask.clone()}, [self.E])
+            out = e._reset(td_in)
+        finally:
+            d.set_world_poses, e.target.set_world_poses, e.cylinders.set_world_poses = real_set, real_tset, real_cset
+        self.td = out
+        return out
+
+    def step(self, raw_action, done_prev):
+        e = self.env
+        td = TD({"agents": {"action": raw_action.clone()},
+                 "info": {"drone_state": e.info["drone_state"].clone(), "prev_action": e.info["prev_action"].clone()},
+                 "stats": TD({}, [self.E]),
+                 "done": done_prev.reshape(self.E, 1).clone()}, [self.E])
+        td = self.transform._inv_call(td)
+        aux = dict(cmds=td[("agents", "action")].clone(), ctbr=td["ctbr"].clone(),
+                   target_rate=td["target_rate"].clone(),
+                   action_error=td[("stats", "action_error_order1")].clone())
+        out = e._step(td)
+        return out["next"], aux
