@@ -1,0 +1,222 @@
+/*
+ * hs_b200.h -- C ABI of the B200-native HideAndSeek environment step.
+ *
+ * This library replaces, for ONE path, what the reference reaches through Isaac Sim /
+ * PhysX plus ~300 eager torch launches per tick (all paths relative to the reference
+ * tree thu-uav/Multi-UAV-pursuit-evasion @ ba29682):
+ *
+ *   hs_step_pre   <- PIDRateController._inv_call      omni_drones/utils/torchrl/transforms.py:425-459
+ *                    PIDRateController.forward        omni_drones/controllers/lee_position_controller.py:476-550
+ *                    HideAndSeek._pre_sim_step        omni_drones/envs/hide_and_seek/hideandseek.py:725-744
+ *                    MultirotorBase.apply_action      omni_drones/robots/drone/multirotor.py:466-508
+ *                    RotorGroup.forward               omni_drones/actuators/rotor_group.py:55-71
+ *                    _get_dummy_policy_prey           omni_drones/envs/hide_and_seek/hideandseek.py:1067-1141
+ *                    SimulationContext.step (PhysX)   omni_drones/envs/isaac_env.py:233-234
+ *                    _compute_state_and_obs           omni_drones/envs/hide_and_seek/hideandseek.py:746-917
+ *                    _compute_reward_and_done         omni_drones/envs/hide_and_seek/hideandseek.py:919-1065
+ *   hs_step_post  <- the part of _compute_state_and_obs that depends on the trajectory
+ *                    predictor output                 omni_drones/envs/hide_and_seek/hideandseek.py:834-887
+ *   hs_reset      <- IsaacEnv._reset + _reset_idx     omni_drones/envs/isaac_env.py:210-225,
+ *                                                     omni_drones/envs/hide_and_seek/hideandseek.py:698-723,
+ *                                                     omni_drones/robots/drone/multirotor.py:635-650
+ *   views         <- omni.physics.tensors get/set     omni_drones/views/articulation_view.py:211-251,
+ *   (hs_state_*)                                      omni_drones/views/rigid_prim_view.py:61-198
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types.
+ *   - every `float*` / `uint8_t*` below is a DEVICE pointer unless the name ends in `_host`.
+ *     The library never allocates or frees them; the caller (PyTorch on the Python side)
+ *     owns all buffers and keeps them alive while the handle uses them.
+ *   - every entry point returns 0 on success or a negative hs_status; hs_last_error()
+ *     gives a message for the calling thread.  Nothing throws across the boundary.
+ *   - kernels are launched asynchronously on the `stream` argument (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream).  No entry point synchronises the device
+ *     except hs_step_host (which must, it returns host data).
+ *   - one host thread per handle; a handle is bound to the CUDA device current at create.
+ *   - there is NO CPU fallback: without a CUDA device hs_create fails with HS_ERR_NO_DEVICE.
+ *
+ * Layouts (E envs, A pursuers, C cylinders, K observed cylinders, F predicted steps,
+ * H history frames, D = 20 + 3F if use_tp_net else 20).  "AoS" tensors are exactly the
+ * reference's tensordict entries, row-major, contiguous.
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1
+#define HS_NUM_STATS 24
+#define HS_MAX_AGENTS 3
+#define HS_MAX_CYLINDERS 8
+#define HS_MAX_OBS_CYLINDERS 4
+#define HS_MAX_FUTURE 8
+
+typedef enum hs_status {
+    HS_OK = 0,
+    HS_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    HS_ERR_NO_DEVICE = -2,   /* no CUDA device: this library has no CPU path */
+    HS_ERR_CUDA = -3,        /* a CUDA runtime call failed; see hs_last_error() */
+    HS_ERR_UNBOUND = -4      /* hs_bind_buffers has not been called */
+} hs_status;
+
+/* Stats slot order = declaration order of the reference's stats spec
+ * (hideandseek.py:400-425).  stats buffer layout is [HS_NUM_STATS][E] so that each key
+ * is a contiguous [E] vector (viewed as [E,1] by the host). */
+enum {
+    HS_STAT_SUCCESS = 0, HS_STAT_COLLISION, HS_STAT_BLOCKED, HS_STAT_DISTANCE_REWARD,
+    HS_STAT_DISTANCE_PREDICTED_REWARD, HS_STAT_SPEED_REWARD, HS_STAT_COLLISION_REWARD,
+    HS_STAT_COLLISION_WALL, HS_STAT_COLLISION_CYLINDER, HS_STAT_COLLISION_DRONE,
+    HS_STAT_DETECT_REWARD, HS_STAT_CATCH_REWARD, HS_STAT_SMOOTHNESS_REWARD,
+    HS_STAT_SMOOTHNESS_MEAN, HS_STAT_SMOOTHNESS_MAX, HS_STAT_FIRST_CAPTURE_STEP,
+    HS_STAT_SUM_DETECT_STEP, HS_STAT_RETURN, HS_STAT_ACTION_ERROR_MEAN,
+    HS_STAT_ACTION_ERROR_MAX, HS_STAT_TARGET_PREDICTED_ERROR, HS_STAT_DISTANCE_THRESHOLD_L,
+    HS_STAT_OUT_OF_ARENA, HS_STAT_SMOOTHNESS_COEF
+};
+
+/* Task + vehicle constants.  Defaults (hs_default_config) = cfg/task/HideAndSeek.yaml,
+ * omni_drones/robots/assets/usd/crazyflie.yaml and the USD rigid-body constants. */
+typedef struct hs_config {
+    int32_t abi_version;        /* must be HS_ABI_VERSION */
+    int32_t num_envs;           /* E */
+    int32_t num_agents;         /* A, 1..HS_MAX_AGENTS */
+    int32_t num_cylinders;      /* C = cylinder.max_num, 0..HS_MAX_CYLINDERS */
+    int32_t obs_max_cylinder;   /* K <= min(C, HS_MAX_OBS_CYLINDERS) */
+    int32_t future_step;        /* F */
+    int32_t history_step;       /* H */
+    int32_t max_episode_length;
+    int32_t use_tp_net;         /* 1: state_self/state_drones carry 3F prediction slots, written by hs_step_post */
+    int32_t smoothness_gated;   /* 1: smoothness reward zeroed (HideAndSeek with use_deployment=0) */
+    int32_t write_smoothness_coef_stat; /* 1 for HideAndSeek, 0 for the envgen variant */
+    int32_t fixed_yaw;
+    int32_t ground_clamp;
+    int32_t reserved_i[3];
+    float dt;
+    float arena_size, max_height, cylinder_size, catch_radius, collision_radius;
+    float drone_detect_radius, target_detect_radius, v_drone, mask_value;
+    float dist_reward_coef, catch_reward_coef, detect_reward_coef, collision_coef, speed_coef;
+    float smoothness_coef;
+    float target_clip, max_thrust_ratio;
+    float pid_kp[3], pid_ki[3], pid_kd[3], pid_ilimit[3], pid_out_limit;
+    float kf, km, rotor_alpha;  /* KF, KM per rotor; alpha = dt / clamp(tau,0,1) */
+    float rotor_dirs[4];
+    float rotor_x[4], rotor_y[4];
+    float drag_coef_times_mass; /* drag_coef * base-link mass (multirotor.py:495) */
+    float downwash_kr, downwash_kz;
+    float total_mass, inertia[3], gravity;
+    float lin_damp_factor, ang_damp_factor;   /* max(0, 1 - dt*c) */
+    float max_linear_velocity, max_angular_velocity;
+    float ground_z;
+    float hover_throttle;       /* sqrt(total_mass*9.81 / (4 KF)), multirotor.py:647-648 */
+    /* Derived constants.  The reference forms these from Python doubles and only then
+     * rounds to fp32 (e.g. `self.arena_size**2`), so the host computes them in double. */
+    float arena_size_sq;        /* arena_size^2            hideandseek.py:980,1096 */
+    float half_arena;           /* 0.5*arena_size          hideandseek.py:835,841 */
+    float coll_radius_x2;       /* 2*collision_radius      hideandseek.py:975 */
+    float vmax_clamped;         /* max_linear_velocity*(1-1e-6): see DESIGN.md "Integrator" */
+    float reserved_f[4];
+} hs_config;
+
+/* Device buffers.  All owned by the caller.
+ * State arena (private to the library; SoA so that consecutive envs are consecutive
+ * addresses): `arena` holds hs_arena_floats(cfg) floats.  Everything else is a
+ * reference-facing tensor in the reference's own AoS layout. */
+typedef struct hs_buffers {
+    float* arena;               /* state arena, see hs_arena_floats / hs_state_get */
+    float* stats;               /* [HS_NUM_STATS][E] */
+    /* outputs of hs_step_pre / hs_reset (observation side) */
+    float* state_self;          /* [E,A,1,D]  ("agents","observation","state_self") */
+    float* state_others;        /* [E,A,A-1,3] (may be NULL when A == 1) */
+    float* obs_cylinders;       /* [E,A,K,5]  (also ("agents","state","cylinders")) */
+    float* state_drones;        /* [E,A,D]    ("agents","state","state_drones") */
+    float* tp_input;            /* [E,H,7+3A] written: previous frames shifted + new frame */
+    const float* tp_input_prev; /* [E,H,7+3A] read; may equal tp_input (in-place shift) */
+    float* tp_groundtruth;      /* [E,3] */
+    uint8_t* tp_done;           /* [E,1] bool */
+    float* reward;              /* [E,A,1] */
+    uint8_t* done;              /* [E,1] bool */
+    uint8_t* truncated;         /* [E,1] bool, written by hs_reset only (may be NULL) */
+    float* drone_state;         /* [E,A,13] ("info","drone_state") */
+    float* prev_action;         /* [E,A,4]  ("info","prev_action"); also the PID transform's memory */
+    /* by-products of the fused action transform (keys the reference's transform writes) */
+    float* rotor_cmds;          /* [E,A,4]  post-transform ("agents","action") */
+    float* ctbr;                /* [E,A,4]  'ctbr' */
+    float* target_rate;         /* [E,A,3]  'target_rate' */
+    float* action_error;        /* [E,A]    ("stats","action_error_order1") */
+    const float* v_prey;        /* device scalar: current evader speed (curriculum, hideandseek.py:1012-1015) */
+} hs_buffers;
+
+typedef struct hs_handle hs_handle;
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+int hs_abi_version(void);
+const char* hs_last_error(void);
+/* Fill `cfg` with the reference defaults for E envs. */
+int hs_default_config(hs_config* cfg, int32_t num_envs);
+/* Number of floats the state arena needs for this config. */
+int64_t hs_arena_floats(const hs_config* cfg);
+int hs_create(const hs_config* cfg, hs_handle** out);
+int hs_destroy(hs_handle* h);
+/* (Re)bind device buffers.  Cheap: may be called before every step to rotate output sets. */
+int hs_bind_buffers(hs_handle* h, const hs_buffers* bufs);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+/* One control tick for every env.
+ *   action        [E,A,4]  device.  action_is_raw != 0: policy output before tanh; the CTBR
+ *                 transform + rate PID run inside the kernel (reference path with
+ *                 action_transform: PIDrate).  action_is_raw == 0: rotor commands in [-1,1]
+ *                 applied directly (base env stepped without the transform); then
+ *                 action_error must be supplied by the caller in bufs.action_error.
+ *   reset_pid     [E] bool device or NULL: the `done` entry of the tensordict handed to
+ *                 step (transforms.py:453); true rows zero the PID memory first. */
+int hs_step_pre(hs_handle* h, const float* action, int action_is_raw,
+                const uint8_t* reset_pid, void* stream);
+/* Second half, only when use_tp_net: tp_pred [E,3F] is TP_net's tanh output for
+ * bufs.tp_input; writes state_self / state_drones (hideandseek.py:834-887). */
+int hs_step_post(hs_handle* h, const float* tp_pred, void* stream);
+/* Partial reset.  env_mask [E] bool (NULL = all).  Initial poses are injected (sampling
+ * stays on the host side so that it can follow the reference's RNG streams):
+ *   drone_pos [E,A,3], drone_rot [E,A,4] (wxyz), target_pos [E,3], cyl_pos [E,C,3];
+ *   rows outside the mask are ignored.  Performs the reference's extra unforced physics
+ *   tick for ALL envs (hideandseek.py:722-723), zeroes progress/stats of the masked
+ *   envs and writes the observation tensors (state_self/state_drones too when
+ *   use_tp_net == 0; otherwise call hs_step_post afterwards). */
+int hs_reset(hs_handle* h, const uint8_t* env_mask, const float* drone_pos,
+             const float* drone_rot, const float* target_pos, const float* cyl_pos,
+             void* stream);
+
+/* ---- convenience: host-buffer tick (the e2e path) ------------------------------------ */
+/* action_host [E,A,4] host (pinned for full speed) -> H2D -> hs_step_pre -> D2H of
+ * reward [E,A] and done [E].  Only valid when use_tp_net == 0 (otherwise the predictor
+ * runs between the halves on the caller's side).  Synchronises `stream`. */
+int hs_step_host(hs_handle* h, const float* action_host, int action_is_raw,
+                 float* reward_host, uint8_t* done_host, float* staging_dev, void* stream);
+
+/* ---- state views (what omni_drones/views/* get/set did) ------------------------------ */
+enum {
+    HS_FIELD_DRONE_POS = 0,   /* [E,A,3] */
+    HS_FIELD_DRONE_ROT,       /* [E,A,4] wxyz */
+    HS_FIELD_DRONE_LINVEL,    /* [E,A,3] world */
+    HS_FIELD_DRONE_ANGVEL,    /* [E,A,3] world */
+    HS_FIELD_THROTTLE,        /* [E,A,4] */
+    HS_FIELD_PID_INTEG,       /* [E,A,3] */
+    HS_FIELD_PID_LAST_RATE,   /* [E,A,3] */
+    HS_FIELD_TARGET_POS,      /* [E,3] */
+    HS_FIELD_TARGET_VEL,      /* [E,3] */
+    HS_FIELD_CYL_POS,         /* [E,C,3] */
+    HS_FIELD_PROGRESS,        /* [E] */
+    HS_FIELD_COUNT
+};
+/* Gather an arena field into a contiguous AoS device buffer / scatter it back. */
+int hs_state_get(hs_handle* h, int field, float* dst, void* stream);
+int hs_state_set(hs_handle* h, int field, const float* src, void* stream);
+/* Number of kernels this handle has launched so far (bench `gpu_launches`). */
+int64_t hs_launch_count(const hs_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */

@@ -1,0 +1,12 @@
+"""B200-native HideAndSeek environment step (drop-in for the reference's IsaacEnv path).
+
+Importing this package loads ``libhs_b200.so`` (the sm_100a kernels behind the C ABI of
+``include/hs_b200.h``).  There is no CPU implementation: a missing library is an
+ImportError, a missing GPU is an ``HsError`` at environment construction.
+"""
+from . import _lib
+from ._lib import HsError
+from .config import Cfg, build_hs_config, compose, load_drone_params
+from .engine import HsEngine
+
+__all__ = ["HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params"]

@@ -1,0 +1,120 @@
+"""ctypes binding of include/hs_b200.h.
+
+There is deliberately no fallback: if ``libhs_b200.so`` is missing or an entry point is
+absent, import raises; if no CUDA device is visible, ``hs_create`` fails with
+HS_ERR_NO_DEVICE and :class:`HsError` is raised.
+"""
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
+
+HS_ABI_VERSION = 1
+HS_NUM_STATS = 24
+
+# field ids, include/hs_b200.h
+(FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,
+ FIELD_PID_INTEG, FIELD_PID_LAST_RATE, FIELD_TARGET_POS, FIELD_TARGET_VEL, FIELD_CYL_POS,
+ FIELD_PROGRESS) = range(11)
+
+
+class HsError(RuntimeError):
+    pass
+
+
+class hs_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("num_agents", C.c_int32),
+        ("num_cylinders", C.c_int32), ("obs_max_cylinder", C.c_int32), ("future_step", C.c_int32),
+        ("history_step", C.c_int32), ("max_episode_length", C.c_int32), ("use_tp_net", C.c_int32),
+        ("smoothness_gated", C.c_int32), ("write_smoothness_coef_stat", C.c_int32),
+        ("fixed_yaw", C.c_int32), ("ground_clamp", C.c_int32), ("reserved_i", C.c_int32 * 3),
+        ("dt", C.c_float),
+        ("arena_size", C.c_float), ("max_height", C.c_float), ("cylinder_size", C.c_float),
+        ("catch_radius", C.c_float), ("collision_radius", C.c_float),
+        ("drone_detect_radius", C.c_float), ("target_detect_radius", C.c_float),
+        ("v_drone", C.c_float), ("mask_value", C.c_float),
+        ("dist_reward_coef", C.c_float), ("catch_reward_coef", C.c_float),
+        ("detect_reward_coef", C.c_float), ("collision_coef", C.c_float), ("speed_coef", C.c_float),
+        ("smoothness_coef", C.c_float),
+        ("target_clip", C.c_float), ("max_thrust_ratio", C.c_float),
+        ("pid_kp", C.c_float * 3), ("pid_ki", C.c_float * 3), ("pid_kd", C.c_float * 3),
+        ("pid_ilimit", C.c_float * 3), ("pid_out_limit", C.c_float),
+        ("kf", C.c_float), ("km", C.c_float), ("rotor_alpha", C.c_float),
+        ("rotor_dirs", C.c_float * 4), ("rotor_x", C.c_float * 4), ("rotor_y", C.c_float * 4),
+        ("drag_coef_times_mass", C.c_float),
+        ("downwash_kr", C.c_float), ("downwash_kz", C.c_float),
+        ("total_mass", C.c_float), ("inertia", C.c_float * 3), ("gravity", C.c_float),
+        ("lin_damp_factor", C.c_float), ("ang_damp_factor", C.c_float),
+        ("max_linear_velocity", C.c_float), ("max_angular_velocity", C.c_float),
+        ("ground_z", C.c_float), ("hover_throttle", C.c_float),
+        ("arena_size_sq", C.c_float), ("half_arena", C.c_float), ("coll_radius_x2", C.c_float),
+        ("vmax_clamped", C.c_float), ("reserved_f", C.c_float * 4),
+    ]
+
+
+_BUF_FIELDS = [
+    "arena", "stats", "state_self", "state_others", "obs_cylinders", "state_drones", "tp_input",
+    "tp_input_prev", "tp_groundtruth", "tp_done", "reward", "done", "truncated", "drone_state",
+    "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey",
+]
+
+
+class hs_buffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _BUF_FIELDS]
+
+
+_EXPORTS = {
+    "hs_abi_version": (C.c_int, []),
+    "hs_last_error": (C.c_char_p, []),
+    "hs_default_config": (C.c_int, [C.POINTER(hs_config), C.c_int32]),
+    "hs_arena_floats": (C.c_int64, [C.POINTER(hs_config)]),
+    "hs_create": (C.c_int, [C.POINTER(hs_config), C.POINTER(C.c_void_p)]),
+    "hs_destroy": (C.c_int, [C.c_void_p]),
+    "hs_bind_buffers": (C.c_int, [C.c_void_p, C.POINTER(hs_buffers)]),
+    "hs_step_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hs_step_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_state_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hs_state_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "hs_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_EXPORTS)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(nvcc, sm_100a).  There is no CPU/eager fallback for the environment step.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _EXPORTS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hs_abi_version() != HS_ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.hs_abi_version()} != {HS_ABI_VERSION}; rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib.hs_last_error()
+        raise HsError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def default_config(num_envs: int) -> hs_config:
+    cfg = hs_config()
+    check(lib.hs_default_config(C.byref(cfg), int(num_envs)), "hs_default_config")
+    return cfg

@@ -1,0 +1,1158 @@
+// hs_kernels.cu -- sm_100a kernels + C ABI for the HideAndSeek environment tick.
+//
+// One fused kernel per control tick (hs_tick_kernel) covers what the reference does with
+// ~300 eager torch launches plus a PhysX step (see include/hs_b200.h for the file:line map).
+//
+// Work decomposition (B200: 148 SMs, 32-wide warps):
+//   * a GROUP of G=4 adjacent lanes owns one environment: lanes 0..A-1 are the pursuers,
+//     lane A is the evader.  A warp therefore advances 8 environments; all cross-agent
+//     terms (downwash all-pairs, evader repulsion sum, capture/detect "any", per-env
+//     means for the stats) are warp-shuffle exchanges inside the group -- no shared
+//     memory round trip and no atomics.
+//   * state lives in a private SoA arena [row][E] so that the 8 envs of a warp are 8
+//     consecutive floats (one 32 B sector) per row and slot.
+//   * reference-facing outputs are AoS ([E,A,W] row-major).  A warp's 8 envs are ONE
+//     contiguous span of every such tensor, so wide rows (W >= 6) are staged in shared
+//     memory and leave through a single TMA bulk store (cp.async.bulk.global.shared::cta,
+//     SASS UBLKCP) per tensor per warp; narrow rows (W <= 4) are written directly
+//     (float4 / scalar), which is already sector-exact.
+//   * no tensor cores: there is no dense contraction on this path.
+//
+// Numerics: fp32 throughout, compiled with -fmad=false so that every product and sum is
+// rounded like the eager torch reference (which never fuses across ops); IEEE div/sqrt.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "hs_b200.h"
+
+#ifndef HS_USE_BULK_STORE
+#define HS_USE_BULK_STORE 1
+#endif
+
+namespace {
+
+constexpr int G = 4;                 // lanes per environment
+constexpr int ENVS_PER_WARP = 32 / G;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CMAX = HS_MAX_CYLINDERS;
+constexpr int KMAX = HS_MAX_OBS_CYLINDERS;
+constexpr int FMAX = HS_MAX_FUTURE;
+constexpr int ND = 23;               // per-drone arena scalars
+// per-drone scalar ids
+enum { D_POS = 0, D_ROT = 3, D_LIN = 7, D_ANG = 10, D_THR = 13, D_INT = 17, D_LAST = 20 };
+// per-env rows that follow the 23*A drone rows
+enum { E_TPOS = 0, E_TVEL = 3, E_PROGRESS = 6, E_BDETECT = 7, E_CYL = 8 };
+
+struct KParams {
+    hs_config c;
+    hs_buffers b;
+    int64_t Ep;                      // arena row pitch (E rounded up to 32)
+    const float* action;
+    const uint8_t* reset_pid;
+    const uint8_t* env_mask;
+    const float* init_drone_pos;
+    const float* init_drone_rot;
+    const float* init_target_pos;
+    const float* init_cyl_pos;
+    const float* tp_pred;
+    int action_is_raw;
+    int tp_init;                     // 1: first frame ever -> fill all H history rows
+};
+
+struct V3 { float x, y, z; };
+struct Q4 { float w, x, y, z; };
+
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ float norm3(V3 a) { return sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z); }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// torch.clamp semantics (NaN propagates)
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// omni_drones/utils/torch.py:182-201 -- a (+/-) b + c with the same grouping
+template <bool INV>
+__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+    const V3 u = mk(q.x, q.y, q.z);
+    const float s = 2.0f * (q.w * q.w) - 1.0f;
+    const V3 a = v * s;
+    const V3 b = (cross3(u, v) * q.w) * 2.0f;
+    const V3 c = (u * dot3(u, v)) * 2.0f;
+    return INV ? ((a - b) + c) : ((a + b) + c);
+}
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+    Q4 r;
+    r.w = ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z;
+    r.x = ((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y;
+    r.y = ((a.w * b.y - a.x * b.z) + a.y * b.w) + a.z * b.x;
+    r.z = ((a.w * b.z + a.x * b.y) - a.y * b.x) + a.z * b.w;
+    return r;
+}
+
+__device__ __forceinline__ float gshfl(float v, int src_lane) { return __shfl_sync(FULL, v, src_lane); }
+__device__ __forceinline__ V3 gshfl3(V3 v, int src_lane) {
+    return mk(gshfl(v.x, src_lane), gshfl(v.y, src_lane), gshfl(v.z, src_lane));
+}
+
+// ---- shared-memory staging + TMA bulk store --------------------------------------------
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+
+// Per-warp staging: two buffers used alternately so that filling tile n+1 overlaps the
+// bulk store of tile n.
+struct Stager {
+    float* buf[2];
+    int cur;
+    int lane;
+    __device__ __forceinline__ float* begin() {
+        // the store issued two flushes ago read from buf[cur]; wait until it has
+        if (HS_USE_BULK_STORE) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+        }
+        return buf[cur];
+    }
+    // all lanes have written their part of buf[cur]; send nwords to gdst
+    __device__ __forceinline__ void flush(float* gdst, int nwords, bool full_tile) {
+        float* s = buf[cur];
+        const bool bulk = HS_USE_BULK_STORE && full_tile && ((nwords & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+        if (bulk) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(gdst, s, static_cast<uint32_t>(nwords) * 4u);
+                bulk_commit();
+            }
+        } else {
+            __syncwarp();
+            for (int i = lane; i < nwords; i += 32) gdst[i] = s[i];
+            __syncwarp();
+            if (HS_USE_BULK_STORE && lane == 0) bulk_commit();   // keep group parity
+        }
+        cur ^= 1;
+    }
+    __device__ __forceinline__ void finish() {
+        if (HS_USE_BULK_STORE) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
+    }
+};
+
+constexpr int FILL_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * (20 + 3 * FMAX);   // 8*3*44 = 1056
+constexpr int TICK_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * 20;                // widest tick tile: [24][20]
+
+// ---- line of sight, hideandseek.py:47-103 ------------------------------------------------
+__device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float (&cx)[CMAX],
+                                            const float (&cy)[CMAX], const float (&cz)[CMAX],
+                                            int C, float size) {
+    const float ddx = p.x - t.x, ddy = p.y - t.y;
+    const float seg = sqrtf(ddx * ddx + ddy * ddy);
+    const float dx = t.x - p.x, dy = t.y - p.y;
+    const float den = dx * dx + dy * dy;
+    bool blocked = false;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            const float ccx = cx[c] - t.x, ccy = cy[c] - t.y;
+            const float cr = fabsf(ddx * ccy - ddy * ccx);
+            const bool near = (cr / (seg + 1e-5f)) <= size;
+            const float num = (cx[c] - p.x) * dx + (cy[c] - p.y) * dy;
+            const float tt = num / (den + 1e-5f);
+            const bool between = (tt >= 0.0f) && (tt <= 1.0f);
+            blocked = blocked || (near && between && (cz[c] > 0.0f));
+        }
+    }
+    return blocked;
+}
+
+// heading = R x, up = R z (utils/torch.py:221-225 evaluated on a basis vector)
+__device__ __forceinline__ void heading_up(Q4 q, V3& heading, V3& up) {
+    heading = qrot<false>(q, mk(1.0f, 0.0f, 0.0f));
+    up = qrot<false>(q, mk(0.0f, 0.0f, 1.0f));
+}
+
+// Writes one [*, D] row: [head3, (p - pred_f) x F, quat4, linvel3, heading3, up3, t x4]
+__device__ __forceinline__ void write_self_row(float* row, V3 head, int F3, const float* rp,
+                                               Q4 q, V3 v, V3 heading, V3 up, float t) {
+    row[0] = head.x; row[1] = head.y; row[2] = head.z;
+    int o = 3;
+    for (int i = 0; i < F3; ++i) row[o + i] = rp[i];
+    o += F3;
+    row[o + 0] = q.w; row[o + 1] = q.x; row[o + 2] = q.y; row[o + 3] = q.z;
+    row[o + 4] = v.x; row[o + 5] = v.y; row[o + 6] = v.z;
+    row[o + 7] = heading.x; row[o + 8] = heading.y; row[o + 9] = heading.z;
+    row[o + 10] = up.x; row[o + 11] = up.y; row[o + 12] = up.z;
+    row[o + 13] = t; row[o + 14] = t; row[o + 15] = t; row[o + 16] = t;
+}
+
+#define AROW(r) (P.b.arena + (int64_t)(r) * P.Ep + e)
+#define DROW(k) AROW((k) * A + slot)
+#define EROW(k) AROW(ND * A + (k))
+
+// =========================================================================================
+// The tick.  RESET=false: full control tick.  RESET=true: the unforced physics tick + obs
+// that closes a reset (hideandseek.py:722-723, isaac_env.py:220-224).
+// =========================================================================================
+template <int A, bool RESET>
+__global__ void __launch_bounds__(128)
+hs_tick_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
+    __shared__ __align__(16) float frame_mem[4][ENVS_PER_WARP][7 + 3 * HS_MAX_AGENTS];
+
+    const hs_config& c = P.c;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = lane & (G - 1);
+    const int gbase = lane & ~(G - 1);
+    const int64_t e0 = warp_g * ENVS_PER_WARP;           // first env of this warp
+    const int E = c.num_envs;
+    if (e0 >= E) return;                                 // whole warp out of range
+    const int64_t e_raw = e0 + (lane >> 2);
+    const bool valid = e_raw < E;
+    const int64_t e = valid ? e_raw : (E - 1);           // clamp: idle lanes shadow the last env (no stores)
+    const bool is_drone = slot < A;
+    const bool is_ev = slot == A;
+    const int nenv = (int)min((int64_t)ENVS_PER_WARP, E - e0);
+    const bool full_tile = nenv == ENVS_PER_WARP;
+    const int C = c.num_cylinders, K = c.obs_max_cylinder;
+    const int FD = 7 + 3 * A;
+    const int H = c.history_step;
+    const float dt = c.dt;
+
+    Stager st;
+    st.buf[0] = stage_mem[wib][0];
+    st.buf[1] = stage_mem[wib][1];
+    st.cur = 0;
+    st.lane = lane;
+
+    // ---- history shift of TP_input: rows 1..H-1 of the previous tensor become rows 0..H-2.
+    // Pure streaming copy, issued first so it overlaps the arithmetic below.
+    if (c.use_tp_net && !P.tp_init) {
+        const int per_env = H * FD, keep = (H - 1) * FD;
+        const float* src = P.b.tp_input_prev + e0 * per_env;
+        float* dst = P.b.tp_input + e0 * per_env;
+        if ((FD & 3) == 0) {
+            const int pe4 = per_env >> 2, keep4 = keep >> 2, fd4 = FD >> 2;
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            const int total = nenv * pe4;
+            for (int i = lane; i < ((total + 31) & ~31); i += 32) {
+                const int env = i / pe4, j = i - env * pe4;
+                const bool act = (i < total) && (j < keep4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act) v = s4[i + fd4];
+                __syncwarp();                            // in-place safe: all loads precede the stores
+                if (act) d4[i] = v;
+            }
+        } else {
+            const int total = nenv * per_env;
+            for (int i = lane; i < ((total + 31) & ~31); i += 32) {
+                const int env = i / per_env, j = i - env * per_env;
+                const bool act = (i < total) && (j < keep);
+                float v = 0.f;
+                if (act) v = src[i + FD];
+                __syncwarp();
+                if (act) dst[i] = v;
+            }
+        }
+    }
+
+    // ---- load state ------------------------------------------------------------------
+    V3 p = mk(0, 0, 0), lv = mk(0, 0, 0), av = mk(0, 0, 0);
+    Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
+    float thr[4] = {0, 0, 0, 0};
+    V3 integ = mk(0, 0, 0), last = mk(0, 0, 0);
+    if (is_drone) {
+        p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+        lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+        av = mk(*DROW(D_ANG), *DROW(D_ANG + 1), *DROW(D_ANG + 2));
+        if (!RESET) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) thr[k] = *DROW(D_THR + k);
+            integ = mk(*DROW(D_INT), *DROW(D_INT + 1), *DROW(D_INT + 2));
+            last = mk(*DROW(D_LAST), *DROW(D_LAST + 1), *DROW(D_LAST + 2));
+        }
+    }
+    // per-env scalars: every lane of the group reads the same address (one broadcast sector)
+    V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+    V3 tv = mk(*EROW(E_TVEL), *EROW(E_TVEL + 1), *EROW(E_TVEL + 2));
+    float progress = *EROW(E_PROGRESS);
+    float cx[CMAX], cy[CMAX], cz[CMAX];
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k) {
+        if (k < C) {
+            cx[k] = __ldg(EROW(E_CYL + 3 * k));
+            cy[k] = __ldg(EROW(E_CYL + 3 * k + 1));
+            cz[k] = __ldg(EROW(E_CYL + 3 * k + 2));
+        } else { cx[k] = 0.f; cy[k] = 0.f; cz[k] = -20.f; }
+    }
+
+    float action_err = 0.f, throttle_diff = 0.f;
+    float T[4] = {0, 0, 0, 0};
+    float yaw_torque = 0.f;
+    V3 ext = mk(0, 0, 0);
+    bool out_of_arena = false;
+
+    if (!RESET) {
+        // ---- CTBR transform + body-rate PID (transforms.py:425-459, lee_position_controller.py:476-550)
+        float cmd[4] = {0, 0, 0, 0};
+        if (is_drone) {
+            const int64_t row = e * A + slot;
+            const float4 act = __ldg(reinterpret_cast<const float4*>(P.action) + row);
+            if (P.action_is_raw) {
+                const float4 prev = *(reinterpret_cast<const float4*>(P.b.prev_action) + row);
+                const float a0 = tanhf(act.x), a1 = tanhf(act.y), a3 = tanhf(act.w);
+                float a2 = tanhf(act.z);
+                const float thrust = clampf((a3 + 1.0f) / 2.0f, 0.0f, c.max_thrust_ratio);
+                if (c.fixed_yaw) a2 = 0.0f;
+                const float d0 = a0 - prev.x, d1 = a1 - prev.y, d2 = a2 - prev.z, d3 = thrust - prev.w;
+                action_err = sqrtf(((d0 * d0 + d1 * d1) + d2 * d2) + d3 * d3);
+                if (valid) *(reinterpret_cast<float4*>(P.b.prev_action) + row) = make_float4(a0, a1, a2, thrust);
+                const V3 trate = mk((a0 * 180.0f) * c.target_clip, (a1 * 180.0f) * c.target_clip,
+                                    (a2 * 180.0f) * c.target_clip);
+                const float tthrust = thrust * 65536.0f;
+                if (P.reset_pid != nullptr && P.reset_pid[e]) { integ = mk(0, 0, 0); last = mk(0, 0, 0); }
+                const V3 br0 = qrot<true>(q, av);
+                const float pi_f = 3.14159265358979323846f;
+                const V3 br = mk((br0.x * 180.0f) / pi_f, (br0.y * 180.0f) / pi_f, (br0.z * 180.0f) / pi_f);
+                const V3 err = trate - br;
+                float o[3];
+                const float errv[3] = {err.x, err.y, err.z};
+                const float brv[3] = {br.x, br.y, br.z};
+                const float lastv[3] = {last.x, last.y, last.z};
+                float integv[3] = {integ.x, integ.y, integ.z};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float outP = errv[k] * c.pid_kp[k];
+                    float deriv = -(brv[k] - lastv[k]) / dt;
+                    if (isnan(deriv)) deriv = 0.0f;
+                    const float outD = deriv * c.pid_kd[k];
+                    integv[k] = clampf(integv[k] + errv[k] * dt, -c.pid_ilimit[k], c.pid_ilimit[k]);
+                    const float outI = integv[k] * c.pid_ki[k];
+                    float out = (outP + outD) + outI;
+                    if (isnan(out)) out = 0.0f;
+                    o[k] = clampf(out, -c.pid_out_limit, c.pid_out_limit);
+                }
+                integ = mk(integv[0], integv[1], integv[2]);
+                last = br;
+                const float r = o[0] / 2.0f, pp = o[1] / 2.0f, y = o[2];
+                const float m[4] = {((tthrust + r) - pp) + y, ((tthrust + r) + pp) - y,
+                                    ((tthrust - r) + pp) + y, ((tthrust - r) - pp) - y};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float v = (m[k] / 65536.0f) * 2.0f - c.max_thrust_ratio;
+                    if (isnan(v)) v = 0.0f;                       // torch.nan_to_num_(cmds, 0.)
+                    else if (isinf(v)) v = v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+                    cmd[k] = v;
+                }
+                if (valid) {
+                    *(reinterpret_cast<float4*>(P.b.rotor_cmds) + row) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
+                    *(reinterpret_cast<float4*>(P.b.ctbr) + row) = make_float4(r, pp, y, tthrust);
+                    P.b.target_rate[row * 3 + 0] = trate.x;
+                    P.b.target_rate[row * 3 + 1] = trate.y;
+                    P.b.target_rate[row * 3 + 2] = trate.z;
+                    P.b.action_error[row] = action_err;
+                }
+            } else {
+                cmd[0] = act.x; cmd[1] = act.y; cmd[2] = act.z; cmd[3] = act.w;
+                action_err = P.b.action_error[row];
+            }
+            // ---- rotor model, rotor_group.py:55-71
+            float dsq = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float target = sqrtf(clampf((cmd[k] + 1.0f) / 2.0f, 0.0f, 1.0f));
+                const float nt = thr[k] + c.rotor_alpha * (target - thr[k]);
+                const float dth = nt - thr[k];
+                dsq = (k == 0) ? dth * dth : dsq + dth * dth;
+                thr[k] = nt;
+                const float t = clampf(nt * nt + 0.0f, 0.0f, 1.0f);
+                T[k] = t * c.kf;
+                const float mom = (t * c.km) * (-c.rotor_dirs[k]);
+                yaw_torque = (k == 0) ? mom : yaw_torque + mom;
+            }
+            throttle_diff = sqrtf(dsq);
+        }
+        // ---- downwash all-pairs, multirotor.py:488-494, 724-753
+        const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
+        const V3 Fw = qrot<false>(q, mk(0.f, 0.f, total_thrust));
+        V3 dw = mk(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const V3 Fj = gshfl3(Fw, gbase + j);
+            const V3 pj = gshfl3(p, gbase + j);
+            if (is_drone && j != slot) {
+                const V3 d = Fj / (norm3(Fj) + 1e-6f);
+                const V3 rel = pj - p;
+                const float zd = dot3(rel, d);
+                const float rr = norm3(rel - d * zd);
+                const float z = zd < 0.0f ? 0.0f : zd;
+                const float qq = (c.downwash_kr * rr) / z;
+                const float den = 1.0f + c.downwash_kz * z;
+                const float v = expf(-0.5f * (qq * qq)) / (den * den);
+                dw = dw + neg(Fj) * v;
+            }
+        }
+        ext = dw + lv * c.drag_coef_times_mass;
+
+        // ---- evader, hideandseek.py:1067-1141 + 737-744
+        V3 fp = mk(0.f, 0.f, 0.f);
+        if (is_drone) {
+            const V3 rel = p - tp;
+            const float dist = norm3(rel);
+            const bool blocked = los_blocked(p, tp, cx, cy, cz, C, c.cylinder_size);
+            const float active = ((dist < c.target_detect_radius) && !blocked) ? 1.0f : 0.0f;
+            const V3 away = neg(rel) / (dist + 1e-5f);
+            fp = (away * (1.0f / (dist + 1e-5f))) * active;
+        }
+        V3 force = gshfl3(fp, gbase);
+#pragma unroll
+        for (int j = 1; j < A; ++j) force = force + gshfl3(fp, gbase + j);
+        if (is_ev) {
+            force = mk(0.f, 0.f, 0.f) + force;
+            const float rho = sqrtf(tp.x * tp.x + tp.y * tp.y);
+            const float inx = -tp.x / (rho + 1e-5f), iny = -tp.y / (rho + 1e-5f);
+            out_of_arena = (tp.x * tp.x + tp.y * tp.y) > c.arena_size_sq;
+            const float o = out_of_arena ? 1.0f : 0.0f, no = out_of_arena ? 0.0f : 1.0f;
+            const float wall = 1.0f / ((c.arena_size - rho) + 1e-5f);
+            V3 fr;
+            fr.x = (o * inx) * 1e5f + (no * inx) * wall;
+            fr.y = (o * iny) * 1e5f + (no * iny) * wall;
+            const bool hi = tp.z > c.max_height;
+            const float hz = c.max_height - tp.z;
+            fr.z = (hi ? 1.0f : 0.0f) * (-1e5f) + ((hi ? 0.0f : 1.0f) * (-hz)) / (hz * hz + 1e-5f);
+            const bool lo = tp.z < 0.0f;
+            const float lz = 0.0f - tp.z;
+            fr.z = fr.z + ((lo ? 1.0f : 0.0f) * 1e5f + ((lo ? 0.0f : 1.0f) * (-lz)) / (lz * lz + 1e-5f));
+            force = force + fr;
+            float fcx = 0.f, fcy = 0.f;
+#pragma unroll
+            for (int k = 0; k < CMAX; ++k) {
+                if (k < C) {
+                    const float tx = tp.x - cx[k], ty = tp.y - cy[k];
+                    const float dxy = sqrtf(tx * tx + ty * ty);
+                    const float gap = dxy - c.cylinder_size;
+                    const float act = (!(cz[k] < 0.0f) && (dxy < c.target_detect_radius)) ? 1.0f : 0.0f;
+                    const float inv = 1.0f / (gap + 1e-5f);
+                    const float tx_n = (act * (tx / (dxy + 1e-5f))) * inv;
+                    const float ty_n = (act * (ty / (dxy + 1e-5f))) * inv;
+                    fcx = (k == 0) ? tx_n : fcx + tx_n;
+                    fcy = (k == 0) ? ty_n : fcy + ty_n;
+                }
+            }
+            force = force + mk(fcx, fcy, 0.f);
+            const float vp = *P.b.v_prey;
+            tv = mk((vp * force.x) / (fabsf(force.x) + 1e-5f), (vp * force.y) / (fabsf(force.y) + 1e-5f),
+                    (vp * force.z) / (fabsf(force.z) + 1e-5f));
+        }
+    }
+
+    // ---- rigid-body integration (PhysX stand-in; oracle/hs_oracle.py rigid_body_step) ----
+    if (is_drone) {
+        V3 force = mk(0.f, 0.f, 0.f), tau = mk(0.f, 0.f, 0.f);
+        if (!RESET) {
+            const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
+            force = qrot<false>(q, mk(0.f, 0.f, total_thrust));
+            tau.x = ((c.rotor_y[0] * T[0] + c.rotor_y[1] * T[1]) + c.rotor_y[2] * T[2]) + c.rotor_y[3] * T[3];
+            tau.y = (((-c.rotor_x[0]) * T[0] + (-c.rotor_x[1]) * T[1]) + (-c.rotor_x[2]) * T[2]) + (-c.rotor_x[3]) * T[3];
+            tau.z = yaw_torque;
+            force = force + ext;
+        }
+        V3 acc = force / c.total_mass;
+        acc.z = acc.z - c.gravity;
+        V3 v = lv + acc * dt;
+        const V3 I = mk(c.inertia[0], c.inertia[1], c.inertia[2]);
+        V3 wb = qrot<true>(q, av);
+        const V3 gyro = cross3(wb, mk(I.x * wb.x, I.y * wb.y, I.z * wb.z));
+        const V3 tg = tau - gyro;
+        wb = wb + mk(tg.x / I.x, tg.y / I.y, tg.z / I.z) * dt;
+        V3 w = qrot<false>(q, wb);
+        v = v * c.lin_damp_factor;
+        w = w * c.ang_damp_factor;
+        const float vn = norm3(v);
+        if (vn > c.max_linear_velocity) v = v * (c.vmax_clamped / vn);
+        float wn = norm3(w);
+        if (wn > c.max_angular_velocity) w = w * (c.max_angular_velocity / wn);
+        p = p + v * dt;
+        wn = norm3(w);
+        const float half = (0.5f * dt) * wn;
+        const bool small = wn < 1e-6f;
+        const float kk = small ? (0.5f * dt) : (sinf(half) / fmaxf(wn, 1e-6f));
+        Q4 dq; dq.w = small ? 1.0f : cosf(half); dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk;
+        Q4 qn = qmul(dq, q);
+        const float qnorm = sqrtf(((qn.w * qn.w + qn.x * qn.x) + qn.y * qn.y) + qn.z * qn.z);
+        q.w = qn.w / qnorm; q.x = qn.x / qnorm; q.y = qn.y / qnorm; q.z = qn.z / qnorm;
+        if (c.ground_clamp && p.z < c.ground_z) {
+            p.z = c.ground_z;
+            if (v.z < 0.0f) v.z = 0.0f;
+        }
+        lv = v; av = w;
+    }
+    if (is_ev) tp = tp + tv * dt;
+    // everyone needs the evader's new position/velocity
+    tp = gshfl3(tp, gbase + A);
+    tv = gshfl3(tv, gbase + A);
+    if (!RESET) progress = progress + 1.0f;
+    else if (P.env_mask == nullptr || P.env_mask[e]) progress = 0.0f;
+
+    // ---- write back state ------------------------------------------------------------
+    if (valid && is_drone) {
+        *DROW(D_POS) = p.x; *DROW(D_POS + 1) = p.y; *DROW(D_POS + 2) = p.z;
+        *DROW(D_ROT) = q.w; *DROW(D_ROT + 1) = q.x; *DROW(D_ROT + 2) = q.y; *DROW(D_ROT + 3) = q.z;
+        *DROW(D_LIN) = lv.x; *DROW(D_LIN + 1) = lv.y; *DROW(D_LIN + 2) = lv.z;
+        *DROW(D_ANG) = av.x; *DROW(D_ANG + 1) = av.y; *DROW(D_ANG + 2) = av.z;
+        if (!RESET) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *DROW(D_THR + k) = thr[k];
+            if (P.action_is_raw) {
+                *DROW(D_INT) = integ.x; *DROW(D_INT + 1) = integ.y; *DROW(D_INT + 2) = integ.z;
+                *DROW(D_LAST) = last.x; *DROW(D_LAST + 1) = last.y; *DROW(D_LAST + 2) = last.z;
+            }
+        }
+    }
+    if (valid && is_ev) {
+        *EROW(E_TPOS) = tp.x; *EROW(E_TPOS + 1) = tp.y; *EROW(E_TPOS + 2) = tp.z;
+        if (!RESET) { *EROW(E_TVEL) = tv.x; *EROW(E_TVEL + 1) = tv.y; *EROW(E_TVEL + 2) = tv.z; }
+        *EROW(E_PROGRESS) = progress;
+    }
+
+    // ---- observation, hideandseek.py:746-917 ------------------------------------------
+    const int row_l = (lane >> 2) * A + slot;            // row of this lane inside the warp tile
+    const int64_t tile_row0 = e0 * A;                    // first [E*A] row of the warp
+    V3 heading, up;
+    heading_up(q, heading, up);
+
+    // info.drone_state [E,A,13]
+    {
+        float* s = st.begin();
+        if (is_drone) {
+            float* r = s + row_l * 13;
+            r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = q.w; r[4] = q.x; r[5] = q.y; r[6] = q.z;
+            r[7] = lv.x; r[8] = lv.y; r[9] = lv.z; r[10] = av.x; r[11] = av.y; r[12] = av.z;
+        }
+        st.flush(P.b.drone_state + tile_row0 * 13, nenv * A * 13, full_tile);
+    }
+    // state_others [E,A,A-1,3] = p_a - p_j, j != a ascending; also drone-drone collisions
+    float hit_drone = 0.f;
+    if (A > 1) {
+        float* s = st.begin();
+        int o = 0;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const V3 pj = gshfl3(p, gbase + j);
+            if (is_drone && j != slot) {
+                const V3 d = p - pj;
+                float* r = s + row_l * ((A - 1) * 3) + o * 3;
+                r[0] = d.x; r[1] = d.y; r[2] = d.z;
+                hit_drone = hit_drone + ((norm3(d) < c.coll_radius_x2) ? 1.0f : 0.0f);
+                ++o;
+            }
+        }
+        st.flush(P.b.state_others + tile_row0 * ((A - 1) * 3), nenv * A * (A - 1) * 3, full_tile);
+    }
+    // k nearest cylinders [E,A,K,5]; lowest index wins ties
+    float hit_cyl = 0.f;
+    {
+        float* s = st.begin();
+        if (is_drone) {
+            float key[CMAX];
+#pragma unroll
+            for (int k = 0; k < CMAX; ++k)
+                key[k] = (k < C) ? (norm3(mk(p.x - cx[k], p.y - cy[k], p.z - cz[k])) - c.cylinder_size) : INFINITY;
+            unsigned taken = 0u;
+            float* r = s + row_l * (K * 5);
+#pragma unroll
+            for (int n = 0; n < KMAX; ++n) {
+                if (n < K) {
+                    int best = 0; float bk = INFINITY; bool found = false;
+#pragma unroll
+                    for (int k = 0; k < CMAX; ++k) {
+                        const bool cand = (k < C) && !((taken >> k) & 1u);
+                        if (cand && (!found || key[k] < bk)) { best = k; bk = key[k]; found = true; }
+                    }
+                    taken |= 1u << best;
+                    float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CMAX; ++k) if (k == best) { bx = cx[k]; by = cy[k]; bz = cz[k]; }
+                    const bool inactive = bz < 0.0f;
+                    const float rx = p.x - bx, ry = p.y - by, rz = p.z - bz;
+                    const float mv = c.mask_value;
+                    r[n * 5 + 0] = inactive ? mv : rx;
+                    r[n * 5 + 1] = inactive ? mv : ry;
+                    r[n * 5 + 2] = inactive ? mv : rz;
+                    r[n * 5 + 3] = inactive ? mv : c.max_height;
+                    r[n * 5 + 4] = inactive ? mv : c.cylinder_size;
+                    const float dxy = sqrtf(rx * rx + ry * ry);
+                    const float hit = ((dxy - c.cylinder_size) < c.collision_radius) ? 1.0f : 0.0f;
+                    hit_cyl = hit_cyl + (inactive ? 0.0f : hit);
+                }
+            }
+        }
+        st.flush(P.b.obs_cylinders + tile_row0 * (K * 5), nenv * A * K * 5, full_tile);
+    }
+    // target visibility
+    const V3 t_rpos = p - tp;
+    bool blocked = false, detect = false;
+    if (is_drone) {
+        blocked = los_blocked(p, tp, cx, cy, cz, C, c.cylinder_size);
+        detect = (norm3(t_rpos) < c.drone_detect_radius) && !blocked;
+    }
+    const unsigned gmask = ((1u << A) - 1u) << gbase;
+    const unsigned det_ballot = __ballot_sync(FULL, detect);
+    const bool bdetect = (det_ballot & gmask) != 0u;
+    const float mv = c.mask_value;
+    const float tfrac = progress / (float)c.max_episode_length;
+
+    if (c.use_tp_net) {
+        // new TP frame [progress, tpos_masked3, tvel_masked3, p_0..p_{A-1}] -> last history row
+        float* fr = frame_mem[wib][lane >> 2];
+        if (is_drone) { fr[7 + 3 * slot] = p.x; fr[8 + 3 * slot] = p.y; fr[9 + 3 * slot] = p.z; }
+        if (is_ev) {
+            fr[0] = progress;
+            fr[1] = bdetect ? tp.x : mv; fr[2] = bdetect ? tp.y : mv; fr[3] = bdetect ? tp.z : mv;
+            fr[4] = bdetect ? tv.x : mv; fr[5] = bdetect ? tv.y : mv; fr[6] = bdetect ? tv.z : mv;
+        }
+        __syncwarp();
+        if (valid) {
+            float* dst = P.b.tp_input + e * (int64_t)(H * FD);
+            if (P.tp_init) {
+                for (int i = slot; i < H * FD; i += G) dst[i] = fr[i % FD];
+            } else {
+                for (int i = slot; i < FD; i += G) dst[(H - 1) * FD + i] = fr[i];
+            }
+        }
+        if (valid && is_ev) {
+            P.b.tp_groundtruth[e * 3 + 0] = tp.x / c.half_arena;
+            P.b.tp_groundtruth[e * 3 + 1] = tp.y / c.half_arena;
+            P.b.tp_groundtruth[e * 3 + 2] = (tp.z / c.max_height) * 2.0f - 1.0f;
+            P.b.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;
+            *EROW(E_BDETECT) = bdetect ? 1.0f : 0.0f;
+        }
+    } else {
+        // no predictor: the rows are complete now (width 20)
+        const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+        float* s = st.begin();
+        if (is_drone) write_self_row(s + row_l * 20, head_m, 0, nullptr, q, lv, heading, up, tfrac);
+        st.flush(P.b.state_self + tile_row0 * 20, nenv * A * 20, full_tile);
+        s = st.begin();
+        if (is_drone) write_self_row(s + row_l * 20, t_rpos, 0, nullptr, q, lv, heading, up, tfrac);
+        st.flush(P.b.state_drones + tile_row0 * 20, nenv * A * 20, full_tile);
+    }
+
+    if (RESET) {
+        if (valid && is_ev && P.b.truncated != nullptr)
+            P.b.truncated[e] = (progress > (float)c.max_episode_length) ? 1 : 0;
+        st.finish();
+        return;
+    }
+
+    // ---- reward / done / stats, hideandseek.py:919-1065 --------------------------------
+    float r_dist = 0.f, r_speed = 0.f, r_coll = 0.f, r_smooth = 0.f, hit_wall = 0.f;
+    bool seen_capture = false;
+    if (is_drone) {
+        const float dist = norm3(tp - p);
+        r_dist = (-c.dist_reward_coef * dist) * ((dist > c.catch_radius) ? 1.0f : 0.0f);
+        seen_capture = (dist < c.catch_radius) && !blocked;
+        r_speed = -c.speed_coef * ((norm3(lv) > c.v_drone) ? 1.0f : 0.0f);
+        r_coll = -c.collision_coef * hit_cyl;
+        r_coll = r_coll + (-c.collision_coef * hit_drone);
+        hit_wall = ((p.z > c.max_height) ? 1.0f : 0.0f) +
+                   (((p.x * p.x + p.y * p.y) > c.arena_size_sq) ? 1.0f : 0.0f);
+        r_coll = r_coll + (-c.collision_coef * hit_wall);
+        r_smooth = c.smoothness_gated ? 0.0f : c.smoothness_coef * expf(-action_err);
+    }
+    const bool any_capture = (__ballot_sync(FULL, seen_capture) & gmask) != 0u;
+    const bool all_blocked = (__ballot_sync(FULL, blocked) & gmask) == gmask;
+    const bool any_coll = (__ballot_sync(FULL, is_drone && (r_coll < 0.0f)) & gmask) != 0u;
+    const float r_detect = c.detect_reward_coef * (bdetect ? 1.0f : 0.0f);
+    const float r_catch = c.catch_reward_coef * (any_capture ? 1.0f : 0.0f);
+    const float reward = ((((r_dist + r_detect) + r_catch) + r_coll) + r_speed) + r_smooth;
+    if (valid && is_drone) P.b.reward[e * A + slot] = reward;
+
+    // per-env means over the A pursuers (sum in agent order, then / A like torch.mean)
+    auto gmean = [&](float x) {
+        float s = gshfl(x, gbase);
+#pragma unroll
+        for (int j = 1; j < A; ++j) s = s + gshfl(x, gbase + j);
+        return s / (float)A;
+    };
+    auto gmax = [&](float x) {
+        float s = gshfl(x, gbase);
+#pragma unroll
+        for (int j = 1; j < A; ++j) s = fmaxf(s, gshfl(x, gbase + j));
+        return s;
+    };
+    const float m_ae = gmean(action_err), m_dist = gmean(r_dist), m_detect = gmean(r_detect),
+                m_catch = gmean(r_catch), m_speed = gmean(r_speed), m_hcyl = gmean(hit_cyl),
+                m_hdrone = gmean(hit_drone), m_hwall = gmean(hit_wall), m_coll = gmean(r_coll),
+                m_smooth = gmean(r_smooth), m_tdiff = gmean(throttle_diff), m_reward = gmean(reward),
+                x_tdiff = gmax(throttle_diff);
+
+    if (valid && is_ev) {
+        const bool done = progress >= (float)c.max_episode_length;
+        P.b.done[e] = done ? 1 : 0;
+        const float ep_len = done ? progress : 1.0f;
+        float* S = P.b.stats + e;
+        const int64_t Es = E;
+#define ST(k) S[(int64_t)(k) * Es]
+        // accumulators that are divided by the episode length on the done tick
+        ST(HS_STAT_ACTION_ERROR_MEAN) = (ST(HS_STAT_ACTION_ERROR_MEAN) + m_ae) / ep_len;
+        ST(HS_STAT_ACTION_ERROR_MAX) = fmaxf(ST(HS_STAT_ACTION_ERROR_MAX), m_ae);
+        ST(HS_STAT_OUT_OF_ARENA) = ((ST(HS_STAT_OUT_OF_ARENA) != 0.0f) || out_of_arena) ? 1.0f : 0.0f;
+        ST(HS_STAT_DISTANCE_REWARD) = (ST(HS_STAT_DISTANCE_REWARD) + m_dist) / ep_len;
+        ST(HS_STAT_SUM_DETECT_STEP) = ST(HS_STAT_SUM_DETECT_STEP) + 1.0f * (bdetect ? 1.0f : 0.0f);
+        ST(HS_STAT_DETECT_REWARD) = (ST(HS_STAT_DETECT_REWARD) + m_detect) / ep_len;
+        ST(HS_STAT_BLOCKED) = ST(HS_STAT_BLOCKED) + (all_blocked ? 1.0f : 0.0f);
+        const bool capture_flag = r_catch != 0.0f;
+        ST(HS_STAT_SUCCESS) = (capture_flag || (ST(HS_STAT_SUCCESS) != 0.0f)) ? 1.0f : 0.0f;
+        const float step_now = (capture_flag ? 1.0f : 0.0f) * progress +
+                               (capture_flag ? 0.0f : 1.0f) * (float)c.max_episode_length;
+        ST(HS_STAT_FIRST_CAPTURE_STEP) = fminf(ST(HS_STAT_FIRST_CAPTURE_STEP), step_now);
+        ST(HS_STAT_CATCH_REWARD) = (ST(HS_STAT_CATCH_REWARD) + m_catch) / ep_len;
+        ST(HS_STAT_SPEED_REWARD) = (ST(HS_STAT_SPEED_REWARD) + m_speed) / ep_len;
+        ST(HS_STAT_COLLISION_CYLINDER) = (ST(HS_STAT_COLLISION_CYLINDER) + m_hcyl) / ep_len;
+        ST(HS_STAT_COLLISION_DRONE) = (ST(HS_STAT_COLLISION_DRONE) + m_hdrone) / ep_len;
+        ST(HS_STAT_COLLISION) = (ST(HS_STAT_COLLISION) + (any_coll ? 1.0f : 0.0f)) / ep_len;
+        ST(HS_STAT_COLLISION_WALL) = (ST(HS_STAT_COLLISION_WALL) + m_hwall) / ep_len;
+        ST(HS_STAT_COLLISION_REWARD) = (ST(HS_STAT_COLLISION_REWARD) + m_coll) / ep_len;
+        if (c.write_smoothness_coef_stat) ST(HS_STAT_SMOOTHNESS_COEF) = c.smoothness_coef;
+        ST(HS_STAT_SMOOTHNESS_REWARD) = (ST(HS_STAT_SMOOTHNESS_REWARD) + m_smooth) / ep_len;
+        ST(HS_STAT_SMOOTHNESS_MEAN) = (ST(HS_STAT_SMOOTHNESS_MEAN) + m_tdiff) / ep_len;
+        ST(HS_STAT_SMOOTHNESS_MAX) = fmaxf(x_tdiff, ST(HS_STAT_SMOOTHNESS_MAX));
+        ST(HS_STAT_RETURN) = ST(HS_STAT_RETURN) + m_reward;
+        // target_predicted_error is only ever divided (stays 0); distance_predicted_reward and
+        // distance_threshold_L are never written (hideandseek.py:1023-1025).
+#undef ST
+    }
+    st.finish();
+}
+
+// =========================================================================================
+// Second half with the trajectory predictor: state_self / state_drones rows (width 20+3F).
+// hideandseek.py:834-887
+// =========================================================================================
+template <int A>
+__global__ void __launch_bounds__(128)
+hs_fill_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) float stage_mem[4][2][FILL_STAGE_WORDS];
+    const hs_config& c = P.c;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = lane & (G - 1);
+    const int64_t e0 = warp_g * ENVS_PER_WARP;
+    const int E = c.num_envs;
+    if (e0 >= E) return;
+    const int64_t e_raw = e0 + (lane >> 2);
+    const bool valid = e_raw < E;
+    const int64_t e = valid ? e_raw : (E - 1);
+    const bool is_drone = slot < A;
+    const int nenv = (int)min((int64_t)ENVS_PER_WARP, E - e0);
+    const bool full_tile = nenv == ENVS_PER_WARP;
+    const int F = c.future_step, F3 = 3 * F, D = 20 + F3;
+
+    Stager st;
+    st.buf[0] = stage_mem[wib][0];
+    st.buf[1] = stage_mem[wib][1];
+    st.cur = 0;
+    st.lane = lane;
+
+    V3 p = mk(0, 0, 0), lv = mk(0, 0, 0);
+    Q4 q; q.w = 1.f; q.x = q.y = q.z = 0.f;
+    if (is_drone) {
+        p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+        lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+    }
+    const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+    const float progress = *EROW(E_PROGRESS);
+    const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+    float rp[3 * FMAX];
+    const float* pr = P.tp_pred + e * F3;
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+        if (f < F) {
+            const float px = (__ldg(pr + 3 * f) * 0.5f) * c.arena_size;
+            const float py = (__ldg(pr + 3 * f + 1) * 0.5f) * c.arena_size;
+            const float pz = ((__ldg(pr + 3 * f + 2) + 1.0f) / 2.0f) * c.max_height;
+            rp[3 * f] = p.x - px; rp[3 * f + 1] = p.y - py; rp[3 * f + 2] = p.z - pz;
+        } else { rp[3 * f] = rp[3 * f + 1] = rp[3 * f + 2] = 0.f; }
+    }
+    V3 heading, up;
+    heading_up(q, heading, up);
+    const float tfrac = progress / (float)c.max_episode_length;
+    const V3 t_rpos = p - tp;
+    const float mv = c.mask_value;
+    const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+    const int row_l = (lane >> 2) * A + slot;
+    const int64_t tile_row0 = e0 * A;
+
+    float* s = st.begin();
+    if (is_drone) write_self_row(s + row_l * D, head_m, F3, rp, q, lv, heading, up, tfrac);
+    st.flush(P.b.state_self + tile_row0 * D, nenv * A * D, full_tile);
+    s = st.begin();
+    if (is_drone) write_self_row(s + row_l * D, t_rpos, F3, rp, q, lv, heading, up, tfrac);
+    st.flush(P.b.state_drones + tile_row0 * D, nenv * A * D, full_tile);
+    st.finish();
+}
+
+// =========================================================================================
+// Reset scatter: hideandseek.py:698-717, multirotor.py:635-650
+// =========================================================================================
+template <int A>
+__global__ void __launch_bounds__(128)
+hs_reset_scatter_kernel(const __grid_constant__ KParams P) {
+    const hs_config& c = P.c;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (int)(gt & (G - 1));
+    const int64_t e = gt >> 2;
+    const int E = c.num_envs;
+    if (e >= E) return;
+    const bool masked = (P.env_mask == nullptr) || (P.env_mask[e] != 0);
+    const int C = c.num_cylinders;
+    if (slot < A && masked) {
+        const int64_t row = e * A + slot;
+        for (int k = 0; k < 3; ++k) *DROW(D_POS + k) = P.init_drone_pos[row * 3 + k];
+        for (int k = 0; k < 4; ++k) *DROW(D_ROT + k) = P.init_drone_rot[row * 4 + k];
+        for (int k = 0; k < 3; ++k) { *DROW(D_LIN + k) = 0.f; *DROW(D_ANG + k) = 0.f; }
+        const float h = c.hover_throttle;
+        for (int k = 0; k < 4; ++k) *DROW(D_THR + k) = h;
+        const float cmd_init = 2.0f * (h * h) - 1.0f;
+        P.b.prev_action[row * 4 + 3] = 0.5f * (c.max_thrust_ratio + cmd_init);
+    }
+    if (slot == A) {
+        if (masked) {
+            for (int k = 0; k < 3; ++k) *EROW(E_TPOS + k) = P.init_target_pos[e * 3 + k];
+            for (int k = 0; k < 3 * C; ++k) *EROW(E_CYL + k) = P.init_cyl_pos[e * 3 * C + k];
+            for (int k = 0; k < HS_NUM_STATS; ++k) P.b.stats[(int64_t)k * E + e] = 0.f;
+        }
+        // every env, not just the masked ones (hideandseek.py:712)
+        P.b.stats[(int64_t)HS_STAT_FIRST_CAPTURE_STEP * E + e] = (float)c.max_episode_length;
+    }
+}
+
+// ---- AoS <-> arena field copies (views/* replacement, used by tests and tools) -----------
+__global__ void hs_field_copy_kernel(float* arena, int64_t Ep, int row0, int n_slots, int width,
+                                     int row_stride_slot, int row_stride_comp, int E, float* aos, int to_aos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_env = (int64_t)n_slots * width;
+    if (i >= per_env * E) return;
+    const int64_t e = i / per_env;
+    const int r = (int)(i - e * per_env);
+    const int a = r / width, k = r - a * width;
+    float* ap = arena + ((int64_t)row0 + (int64_t)k * row_stride_comp + (int64_t)a * row_stride_slot) * Ep + e;
+    if (to_aos) aos[i] = *ap; else *ap = aos[i];
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+struct hs_handle {
+    hs_config cfg;
+    hs_buffers bufs;
+    bool bound;
+    int device;
+    int64_t Ep;
+    int64_t launches;
+    int tp_frames;               // number of TP frames written so far (0 -> next one initialises history)
+    int block;                   // threads per block for the tick kernels
+};
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CUDA_OK(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return set_err(HS_ERR_CUDA, #call ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+template <bool RESET>
+static cudaError_t launch_tick(const hs_handle* h, const KParams& P, cudaStream_t s) {
+    const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
+    const int wpb = h->block / 32;
+    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    switch (h->cfg.num_agents) {
+        case 1: hs_tick_kernel<1, RESET><<<grid, h->block, 0, s>>>(P); break;
+        case 2: hs_tick_kernel<2, RESET><<<grid, h->block, 0, s>>>(P); break;
+        default: hs_tick_kernel<3, RESET><<<grid, h->block, 0, s>>>(P); break;
+    }
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+int hs_abi_version(void) { return HS_ABI_VERSION; }
+const char* hs_last_error(void) { return g_err; }
+
+int hs_default_config(hs_config* c, int32_t num_envs) {
+    if (!c) return set_err(HS_ERR_INVALID, "hs_default_config: null cfg%s");
+    memset(c, 0, sizeof(*c));
+    c->abi_version = HS_ABI_VERSION;
+    c->num_envs = num_envs;
+    c->num_agents = 3; c->num_cylinders = 5; c->obs_max_cylinder = 3;
+    c->future_step = 5; c->history_step = 10; c->max_episode_length = 800;
+    c->use_tp_net = 1; c->smoothness_gated = 1; c->write_smoothness_coef_stat = 1;
+    c->fixed_yaw = 0; c->ground_clamp = 1;
+    c->dt = 0.01f;
+    c->arena_size = 0.9f; c->max_height = 1.2f; c->cylinder_size = 0.1f;
+    c->catch_radius = 0.3f; c->collision_radius = 0.07f;
+    c->drone_detect_radius = 100.0f; c->target_detect_radius = 100.0f;
+    c->v_drone = 1.0f; c->mask_value = -5.0f;
+    c->dist_reward_coef = 1.0f; c->catch_reward_coef = 20.0f; c->detect_reward_coef = 0.0f;
+    c->collision_coef = 100.0f; c->speed_coef = 10.0f; c->smoothness_coef = 0.0f;
+    c->target_clip = 1.0f; c->max_thrust_ratio = 0.9f;
+    const float kp[3] = {250.f, 250.f, 120.f}, ki[3] = {500.f, 500.f, 16.7f}, kd[3] = {2.5f, 2.5f, 0.f},
+                il[3] = {33.3f, 33.3f, 166.7f};
+    for (int i = 0; i < 3; ++i) { c->pid_kp[i] = kp[i]; c->pid_ki[i] = ki[i]; c->pid_kd[i] = kd[i]; c->pid_ilimit[i] = il[i]; }
+    c->pid_out_limit = 32767.0f;
+    const float wmax = 2315.0f;
+    c->kf = (wmax * wmax) * 2.350347298350041e-08f;
+    c->km = (wmax * wmax) * 7.24e-10f;
+    c->rotor_alpha = 0.01f / 0.025f;
+    const float dirs[4] = {-1.f, 1.f, -1.f, 1.f};
+    const float rx[4] = {0.028f, -0.028f, -0.028f, 0.028f}, ry[4] = {0.028f, 0.028f, -0.028f, -0.028f};
+    for (int i = 0; i < 4; ++i) { c->rotor_dirs[i] = dirs[i]; c->rotor_x[i] = rx[i]; c->rotor_y[i] = ry[i]; }
+    c->drag_coef_times_mass = 0.0f;
+    c->downwash_kr = 2.0f; c->downwash_kz = 0.3f;
+    const double m = 0.0321 + 4 * 1.0e-4;
+    c->total_mass = (float)m;
+    const double s = 4 * 1.0e-4 * 0.028 * 0.028;
+    c->inertia[0] = (float)(1.4e-5 + s); c->inertia[1] = (float)(1.4e-5 + s); c->inertia[2] = (float)(2.17e-5 + 2 * s);
+    c->gravity = 9.81f;
+    c->lin_damp_factor = (float)(1.0 - 0.01 * 0.2); c->ang_damp_factor = (float)(1.0 - 0.01 * 0.2);
+    c->max_linear_velocity = 1.0f; c->max_angular_velocity = 1000.0f;
+    c->ground_z = 0.0125f;
+    c->hover_throttle = sqrtf((c->total_mass * 9.81f) / (4.0f * c->kf));
+    c->arena_size_sq = (float)(0.9 * 0.9);
+    c->half_arena = (float)(0.5 * 0.9);
+    c->coll_radius_x2 = (float)(2.0 * 0.07);
+    c->vmax_clamped = (float)(1.0 * (1.0 - 1e-6));
+    return HS_OK;
+}
+
+static int check_cfg(const hs_config* c) {
+    if (!c) return set_err(HS_ERR_INVALID, "null config%s");
+    if (c->abi_version != HS_ABI_VERSION) return set_err(HS_ERR_INVALID, "config abi_version mismatch%s");
+    if (c->num_envs <= 0) return set_err(HS_ERR_INVALID, "num_envs must be > 0%s");
+    if (c->num_agents < 1 || c->num_agents > HS_MAX_AGENTS) return set_err(HS_ERR_INVALID, "num_agents must be 1..3%s");
+    if (c->num_cylinders < 0 || c->num_cylinders > HS_MAX_CYLINDERS) return set_err(HS_ERR_INVALID, "num_cylinders must be 0..8%s");
+    if (c->obs_max_cylinder < 0 || c->obs_max_cylinder > HS_MAX_OBS_CYLINDERS || c->obs_max_cylinder > c->num_cylinders)
+        return set_err(HS_ERR_INVALID, "obs_max_cylinder must be <= min(num_cylinders, 4)%s");
+    if (c->future_step < 0 || c->future_step > HS_MAX_FUTURE) return set_err(HS_ERR_INVALID, "future_step must be 0..8%s");
+    if (c->history_step < 1) return set_err(HS_ERR_INVALID, "history_step must be >= 1%s");
+    return HS_OK;
+}
+
+int64_t hs_arena_floats(const hs_config* c) {
+    if (check_cfg(c) != HS_OK) return -1;
+    const int64_t Ep = ((int64_t)c->num_envs + 31) & ~(int64_t)31;
+    return ((int64_t)ND * c->num_agents + E_CYL + 3 * (int64_t)c->num_cylinders) * Ep;
+}
+
+int hs_create(const hs_config* cfg, hs_handle** out) {
+    if (!out) return set_err(HS_ERR_INVALID, "hs_create: null out%s");
+    *out = nullptr;
+    int rc = check_cfg(cfg);
+    if (rc != HS_OK) return rc;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_err(HS_ERR_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU path",
+                       ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    }
+    hs_handle* h = new (std::nothrow) hs_handle();
+    if (!h) return set_err(HS_ERR_INVALID, "out of host memory%s");
+    h->cfg = *cfg;
+    memset(&h->bufs, 0, sizeof(h->bufs));
+    h->bound = false;
+    CUDA_OK(cudaGetDevice(&h->device));
+    h->Ep = ((int64_t)cfg->num_envs + 31) & ~(int64_t)31;
+    h->launches = 0;
+    h->tp_frames = 0;
+    // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
+    const int64_t warps = ((int64_t)cfg->num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
+    h->block = (warps >= 4 * 148 * 4) ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
+    *out = h;
+    return HS_OK;
+}
+
+int hs_destroy(hs_handle* h) {
+    delete h;
+    return HS_OK;
+}
+
+int hs_bind_buffers(hs_handle* h, const hs_buffers* b) {
+    if (!h || !b) return set_err(HS_ERR_INVALID, "hs_bind_buffers: null argument%s");
+    const hs_config& c = h->cfg;
+    if (!b->arena || !b->stats || !b->obs_cylinders || !b->state_self || !b->state_drones || !b->reward ||
+        !b->done || !b->drone_state || !b->prev_action || !b->rotor_cmds || !b->ctbr || !b->target_rate ||
+        !b->action_error || !b->v_prey)
+        return set_err(HS_ERR_INVALID, "hs_bind_buffers: a required buffer is NULL%s");
+    if (c.num_agents > 1 && !b->state_others) return set_err(HS_ERR_INVALID, "state_others is NULL%s");
+    if (c.use_tp_net && (!b->tp_input || !b->tp_input_prev || !b->tp_groundtruth || !b->tp_done))
+        return set_err(HS_ERR_INVALID, "use_tp_net needs tp_input/tp_input_prev/tp_groundtruth/tp_done%s");
+    h->bufs = *b;
+    h->bound = true;
+    return HS_OK;
+}
+
+static KParams make_params(const hs_handle* h) {
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    P.c = h->cfg;
+    P.b = h->bufs;
+    P.Ep = h->Ep;
+    return P;
+}
+
+int hs_step_pre(hs_handle* h, const float* action, int action_is_raw, const uint8_t* reset_pid, void* stream) {
+    if (!h || !action) return set_err(HS_ERR_INVALID, "hs_step_pre: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_pre: call hs_bind_buffers first%s");
+    KParams P = make_params(h);
+    P.action = action;
+    P.action_is_raw = action_is_raw;
+    P.reset_pid = reset_pid;
+    P.tp_init = (h->cfg.use_tp_net && h->tp_frames == 0) ? 1 : 0;
+    CUDA_OK(launch_tick<false>(h, P, (cudaStream_t)stream));
+    h->launches += 1;
+    if (h->cfg.use_tp_net) h->tp_frames += 1;
+    return HS_OK;
+}
+
+int hs_step_post(hs_handle* h, const float* tp_pred, void* stream) {
+    if (!h || !tp_pred) return set_err(HS_ERR_INVALID, "hs_step_post: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_post: call hs_bind_buffers first%s");
+    if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_post: config has use_tp_net == 0%s");
+    KParams P = make_params(h);
+    P.tp_pred = tp_pred;
+    const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
+    const int wpb = h->block / 32;
+    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (h->cfg.num_agents) {
+        case 1: hs_fill_kernel<1><<<grid, h->block, 0, s>>>(P); break;
+        case 2: hs_fill_kernel<2><<<grid, h->block, 0, s>>>(P); break;
+        default: hs_fill_kernel<3><<<grid, h->block, 0, s>>>(P); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return HS_OK;
+}
+
+int hs_reset(hs_handle* h, const uint8_t* env_mask, const float* drone_pos, const float* drone_rot,
+             const float* target_pos, const float* cyl_pos, void* stream) {
+    if (!h || !drone_pos || !drone_rot || !target_pos) return set_err(HS_ERR_INVALID, "hs_reset: null argument%s");
+    if (h->cfg.num_cylinders > 0 && !cyl_pos) return set_err(HS_ERR_INVALID, "hs_reset: cyl_pos is NULL%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_reset: call hs_bind_buffers first%s");
+    KParams P = make_params(h);
+    P.env_mask = env_mask;
+    P.init_drone_pos = drone_pos; P.init_drone_rot = drone_rot;
+    P.init_target_pos = target_pos; P.init_cyl_pos = cyl_pos;
+    P.tp_init = (h->cfg.use_tp_net && h->tp_frames == 0) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t threads = (int64_t)h->cfg.num_envs * G;
+    const unsigned grid = (unsigned)((threads + 127) / 128);
+    switch (h->cfg.num_agents) {
+        case 1: hs_reset_scatter_kernel<1><<<grid, 128, 0, s>>>(P); break;
+        case 2: hs_reset_scatter_kernel<2><<<grid, 128, 0, s>>>(P); break;
+        default: hs_reset_scatter_kernel<3><<<grid, 128, 0, s>>>(P); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(launch_tick<true>(h, P, s));
+    h->launches += 2;
+    if (h->cfg.use_tp_net) h->tp_frames += 1;
+    return HS_OK;
+}
+
+int hs_step_host(hs_handle* h, const float* action_host, int action_is_raw, float* reward_host,
+                 uint8_t* done_host, float* staging_dev, void* stream) {
+    if (!h || !action_host || !reward_host || !done_host || !staging_dev)
+        return set_err(HS_ERR_INVALID, "hs_step_host: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_host: call hs_bind_buffers first%s");
+    if (h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_host: only for use_tp_net == 0%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.num_envs * h->cfg.num_agents;
+    CUDA_OK(cudaMemcpyAsync(staging_dev, action_host, n * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = hs_step_pre(h, staging_dev, action_is_raw, nullptr, stream);
+    if (rc != HS_OK) return rc;
+    CUDA_OK(cudaMemcpyAsync(reward_host, h->bufs.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(done_host, h->bufs.done, (size_t)h->cfg.num_envs, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return HS_OK;
+}
+
+static int field_desc(const hs_handle* h, int field, int* row0, int* n_slots, int* width, int* stride_slot,
+                      int* stride_comp) {
+    const int A = h->cfg.num_agents, C = h->cfg.num_cylinders;
+    const int ebase = ND * A;
+    switch (field) {
+        case HS_FIELD_DRONE_POS:     *row0 = D_POS * A;  *n_slots = A; *width = 3; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_DRONE_ROT:     *row0 = D_ROT * A;  *n_slots = A; *width = 4; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_DRONE_LINVEL:  *row0 = D_LIN * A;  *n_slots = A; *width = 3; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_DRONE_ANGVEL:  *row0 = D_ANG * A;  *n_slots = A; *width = 3; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_THROTTLE:      *row0 = D_THR * A;  *n_slots = A; *width = 4; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_PID_INTEG:     *row0 = D_INT * A;  *n_slots = A; *width = 3; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_PID_LAST_RATE: *row0 = D_LAST * A; *n_slots = A; *width = 3; *stride_slot = 1; *stride_comp = A; break;
+        case HS_FIELD_TARGET_POS:    *row0 = ebase + E_TPOS; *n_slots = 1; *width = 3; *stride_slot = 0; *stride_comp = 1; break;
+        case HS_FIELD_TARGET_VEL:    *row0 = ebase + E_TVEL; *n_slots = 1; *width = 3; *stride_slot = 0; *stride_comp = 1; break;
+        case HS_FIELD_CYL_POS:       *row0 = ebase + E_CYL;  *n_slots = C; *width = 3; *stride_slot = 3; *stride_comp = 1; break;
+        case HS_FIELD_PROGRESS:      *row0 = ebase + E_PROGRESS; *n_slots = 1; *width = 1; *stride_slot = 0; *stride_comp = 1; break;
+        default: return set_err(HS_ERR_INVALID, "unknown field id%s");
+    }
+    return HS_OK;
+}
+
+static int field_copy(hs_handle* h, int field, float* aos, int to_aos, void* stream) {
+    if (!h || !aos) return set_err(HS_ERR_INVALID, "hs_state_get/set: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_state_get/set: call hs_bind_buffers first%s");
+    int row0, n_slots, width, ss, sc;
+    int rc = field_desc(h, field, &row0, &n_slots, &width, &ss, &sc);
+    if (rc != HS_OK) return rc;
+    const int64_t n = (int64_t)h->cfg.num_envs * n_slots * width;
+    if (n == 0) return HS_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    hs_field_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->bufs.arena, h->Ep, row0, n_slots, width, ss, sc,
+                                                                 h->cfg.num_envs, aos, to_aos);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return HS_OK;
+}
+
+int hs_state_get(hs_handle* h, int field, float* dst, void* stream) { return field_copy(h, field, dst, 1, stream); }
+int hs_state_set(hs_handle* h, int field, const float* src, void* stream) {
+    return field_copy(h, field, const_cast<float*>(src), 0, stream);
+}
+int64_t hs_launch_count(const hs_handle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Device-memory plumbing around the C ABI: allocates the arena and the reference-facing
+output tensors with PyTorch, binds them, and launches the kernels on torch's current stream.
+
+PyTorch is used here for memory, streams and (elsewhere) torch.distributed only; all
+arithmetic of the environment tick happens in libhs_b200.so.
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, hs_buffers, hs_config
+
+_ALIGN_WORDS = 32            # 128 B: keeps every output tensor TMA-bulk-store aligned
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class OutputSet:
+    """One set of reference-facing tensors carved out of a single float32 slab (+ a byte slab)."""
+
+    def __init__(self, cfg: hs_config, device):
+        E, A = cfg.num_envs, cfg.num_agents
+        K, F, H = cfg.obs_max_cylinder, cfg.future_step, cfg.history_step
+        D = 20 + (3 * F if cfg.use_tp_net else 0)
+        FD = 7 + 3 * A
+        shapes = {
+            "state_self": (E, A, 1, D), "state_others": (E, A, max(A - 1, 0), 3),
+            "obs_cylinders": (E, A, K, 5), "state_drones": (E, A, D),
+            "reward": (E, A, 1), "drone_state": (E, A, 13), "rotor_cmds": (E, A, 4),
+            "ctbr": (E, A, 4), "target_rate": (E, A, 3), "action_error": (E, A),
+        }
+        if cfg.use_tp_net:
+            shapes.update({"tp_input": (E, H, FD), "tp_groundtruth": (E, 3)})
+        offs, total = {}, 0
+        for k, s in shapes.items():
+            n = 1
+            for d in s:
+                n *= d
+            offs[k] = (total, n)
+            total += (n + _ALIGN_WORDS - 1) // _ALIGN_WORDS * _ALIGN_WORDS
+        self.slab = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        self.t: Dict[str, torch.Tensor] = {}
+        for k, s in shapes.items():
+            o, n = offs[k]
+            self.t[k] = self.slab[o:o + n].view(*s)
+        self.bytes = torch.zeros(3, E, 1, dtype=torch.uint8, device=device)
+        self.t["done"] = self.bytes[0].view(torch.bool)
+        self.t["tp_done"] = self.bytes[1].view(torch.bool)
+        self.t["truncated"] = self.bytes[2].view(torch.bool)
+        self.result_words = total
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+
+class HsEngine:
+    """Owns the buffers of one environment batch on one GPU and drives the kernels."""
+
+    def __init__(self, cfg: hs_config, device="cuda:0", num_output_sets: int = 2):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.HsError("HsEngine needs a CUDA device: the environment step has no CPU path")
+        self.cfg = cfg
+        self.device = device
+        self.E, self.A, self.C = cfg.num_envs, cfg.num_agents, cfg.num_cylinders
+        with torch.cuda.device(device):
+            h = C.c_void_p()
+            check(lib.hs_create(C.byref(cfg), C.byref(h)), "hs_create")
+        self._h = h
+        n = lib.hs_arena_floats(C.byref(cfg))
+        self.arena = torch.zeros(n, dtype=torch.float32, device=device)
+        self.stats = torch.zeros(_lib.HS_NUM_STATS, self.E, dtype=torch.float32, device=device)
+        self.prev_action = torch.zeros(self.E, self.A, 4, dtype=torch.float32, device=device)
+        self.v_prey = torch.full((1,), 1.3, dtype=torch.float32, device=device)
+        self.sets = [OutputSet(cfg, device) for _ in range(max(1, num_output_sets))]
+        self._bufs = [self._make_bufs(i) for i in range(len(self.sets))]
+        self.cur = len(self.sets) - 1          # index of the set holding the latest outputs
+        self._keep = []                        # keeps caller tensors alive across async launches
+        # identity quaternions so that an un-reset arena is still well formed
+        ident = torch.zeros(self.E, self.A, 4, device=device)
+        ident[..., 0] = 1.0
+        self._bind(self.cur)
+        self.set_state(_lib.FIELD_DRONE_ROT, ident)
+
+    # ------------------------------------------------------------------ plumbing
+    def _make_bufs(self, i: int) -> hs_buffers:
+        s = self.sets[i]
+        prev = self.sets[(i - 1) % len(self.sets)]
+        b = hs_buffers()
+        b.arena, b.stats = _ptr(self.arena), _ptr(self.stats)
+        for k in ("state_self", "obs_cylinders", "state_drones", "reward", "drone_state",
+                  "rotor_cmds", "ctbr", "target_rate", "action_error"):
+            setattr(b, k, _ptr(s[k]))
+        b.state_others = _ptr(s["state_others"]) if self.A > 1 else None
+        if self.cfg.use_tp_net:
+            b.tp_input, b.tp_input_prev = _ptr(s["tp_input"]), _ptr(prev["tp_input"])
+            b.tp_groundtruth = _ptr(s["tp_groundtruth"])
+        b.tp_done, b.done, b.truncated = _ptr(s["tp_done"]), _ptr(s["done"]), _ptr(s["truncated"])
+        b.prev_action, b.v_prey = _ptr(self.prev_action), _ptr(self.v_prey)
+        return b
+
+    def _bind(self, i: int):
+        check(lib.hs_bind_buffers(self._h, C.byref(self._bufs[i])), "hs_bind_buffers")
+        self.cur = i
+
+    def _advance(self):
+        self._bind((self.cur + 1) % len(self.sets))
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def out(self) -> OutputSet:
+        return self.sets[self.cur]
+
+    # ------------------------------------------------------------------ hot path
+    def step_pre(self, action: torch.Tensor, raw: bool = True, reset_pid: Optional[torch.Tensor] = None) -> OutputSet:
+        E, A = self.E, self.A
+        if action.shape != (E, A, 4) or action.dtype != torch.float32 or not action.is_contiguous() \
+                or action.device != self.device:
+            raise _lib.HsError(f"action must be a contiguous float32 [{E},{A},4] tensor on {self.device}")
+        rp = None
+        if reset_pid is not None:
+            rp = reset_pid.reshape(E)
+            if rp.dtype == torch.bool:
+                rp = rp.view(torch.uint8)
+            if rp.dtype != torch.uint8 or not rp.is_contiguous():
+                rp = rp.to(torch.uint8).contiguous()
+        self._advance()
+        self._keep = [action, rp]
+        check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if raw else 0, _ptr(rp), self._stream()), "hs_step_pre")
+        return self.out
+
+    def step_post(self, tp_pred: torch.Tensor) -> OutputSet:
+        F3 = 3 * self.cfg.future_step
+        tp_pred = tp_pred.reshape(self.E, F3)
+        if tp_pred.dtype != torch.float32 or not tp_pred.is_contiguous():
+            tp_pred = tp_pred.float().contiguous()
+        self._keep.append(tp_pred)
+        check(lib.hs_step_post(self._h, tp_pred.data_ptr(), self._stream()), "hs_step_post")
+        return self.out
+
+    def reset(self, mask: Optional[torch.Tensor], drone_pos, drone_rot, target_pos, cyl_pos) -> OutputSet:
+        E, A, Cc = self.E, self.A, self.C
+        f = lambda t, shape: t.to(self.device, torch.float32).reshape(shape).contiguous()
+        drone_pos, drone_rot = f(drone_pos, (E, A, 3)), f(drone_rot, (E, A, 4))
+        target_pos = f(target_pos, (E, 3))
+        cyl_pos = f(cyl_pos, (E, Cc, 3)) if Cc > 0 else None
+        m = None
+        if mask is not None:
+            m = mask.to(self.device).reshape(E)
+            m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+            m = m.contiguous()
+        self._advance()
+        self._keep = [m, drone_pos, drone_rot, target_pos, cyl_pos]
+        check(lib.hs_reset(self._h, _ptr(m), drone_pos.data_ptr(), drone_rot.data_ptr(), target_pos.data_ptr(),
+                           _ptr(cyl_pos), self._stream()), "hs_reset")
+        return self.out
+
+    # ------------------------------------------------------------------ state views
+    _SHAPES = {
+        _lib.FIELD_DRONE_POS: lambda s: (s.E, s.A, 3), _lib.FIELD_DRONE_ROT: lambda s: (s.E, s.A, 4),
+        _lib.FIELD_DRONE_LINVEL: lambda s: (s.E, s.A, 3), _lib.FIELD_DRONE_ANGVEL: lambda s: (s.E, s.A, 3),
+        _lib.FIELD_THROTTLE: lambda s: (s.E, s.A, 4), _lib.FIELD_PID_INTEG: lambda s: (s.E, s.A, 3),
+        _lib.FIELD_PID_LAST_RATE: lambda s: (s.E, s.A, 3), _lib.FIELD_TARGET_POS: lambda s: (s.E, 3),
+        _lib.FIELD_TARGET_VEL: lambda s: (s.E, 3), _lib.FIELD_CYL_POS: lambda s: (s.E, s.C, 3),
+        _lib.FIELD_PROGRESS: lambda s: (s.E,),
+    }
+
+    def get_state(self, field: int) -> torch.Tensor:
+        out = torch.empty(self._SHAPES[field](self), dtype=torch.float32, device=self.device)
+        if out.numel():
+            check(lib.hs_state_get(self._h, field, out.data_ptr(), self._stream()), "hs_state_get")
+        return out
+
+    def set_state(self, field: int, value: torch.Tensor):
+        v = value.to(self.device, torch.float32).reshape(self._SHAPES[field](self)).contiguous()
+        if v.numel():
+            check(lib.hs_state_set(self._h, field, v.data_ptr(), self._stream()), "hs_state_set")
+            self._keep.append(v)
+
+    @property
+    def launches(self) -> int:
+        return int(lib.hs_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            lib.hs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
