@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the HideAndSeek 3v1 tick on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one control tick (dt = 0.01 s) of one batch of E environments through the hot
+path: hs_step_pre (fused CTBR/PID/rotor/physics/evader/obs/reward kernel) -> TP_net
+forward (torch LSTM, the reference calls it inside the env) -> hs_step_post.
+Workload at every N: BASELINE.json configs[1] -- HideAndSeek, 3 pursuers + 1 evader,
+'empty' scenario (0 active cylinders, C=5 buffers), E=4096 envs per GPU, use_TP_net=1.
+
+Timing hygiene: the per-GPU working set of one batch (~12 MB) is smaller than the 126 MB L2,
+so the timed loop ROTATES over R=16 independent env batches (R x 12 MB > L2): every step
+finds its state cold in L2 without a flush kernel inside the timed region.  Device time
+comes from CUDA events on the launching stream, bracketed by barrier + synchronize, max
+over ranks.
+
+`--impl reference` times the CPU arm instead: the oracle port of the reference's torch code
+(oracle/hs_oracle.py, Isaac Sim / PhysX cannot run here) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+E_PER_GPU = 4096
+ROTATE = 16
+ROLLOUT = 64                      # steps per rollout (cfg/algo/mappo.yaml train_every)
+METRIC = "env-steps/sec (3v1 HideAndSeek)"
+WORKLOAD = "HideAndSeek 3 pursuers + 1 evader, 'empty' scenario (0 active cylinders, C=5), 4096 envs per GPU, use_TP_net=1"
+
+
+def algorithmic_bytes(A=3, C=5, K=3, F=5, H=10, tp=True):
+    """Bytes one env-step must move (SURVEY.md section 8d formula), split per kernel."""
+    D = 20 + (3 * F if tp else 0)
+    state_rw = 2 * (27 * A + 31)
+    words_total = state_rw + 4 * A + 3 * C + (3 * F if tp else 0) + (A * D + 3 * A * (A - 1) + 5 * A * K) \
+        + A * D + (H * (7 + 3 * A) + 4 if tp else 0) + A + 13 * A + A + 7 * A
+    total = 4 * words_total + 1
+    fill = 4 * (2 * A * D + 3 * F) if tp else 0          # state_self + state_drones + prediction
+    return {"total": total, "tick": total - fill, "fill": fill}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
+def make_tp_net(torch, A, F, device, seed=0):
+    torch.manual_seed(seed)
+    lstm = torch.nn.LSTM(7 + 3 * A, 64, 1, batch_first=True).to(device)
+    fc = torch.nn.Linear(64, 3 * F).to(device)
+    lstm.requires_grad_(False); fc.requires_grad_(False)
+
+    def fwd(x):
+        with torch.no_grad():
+            out, _ = lstm(x)
+            return torch.tanh(fc(out[:, -1, :]))
+    return fwd
+
+
+def params():
+    from oracle import hs_oracle as O
+    return O, O.HSParams(num_cylinders=5, obs_max_cylinder=3, use_tp_net=True)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference), also used for the cpu_baseline leg of the GPU arm
+# ------------------------------------------------------------------------------------------
+def time_cpu_oracle(steps, warmup, E=E_PER_GPU, budget_s=25.0):
+    import torch
+    O, P = params()
+    cores = usable_cores()
+    torch.set_num_threads(cores)
+    tp = make_tp_net(torch, P.num_agents, P.future_step, "cpu")
+    orc = O.HideAndSeekOracle(P, E)
+    g = torch.Generator().manual_seed(0)
+    init = O.sample_reset(P, E, g, "empty")
+    orc.reset(torch.ones(E, dtype=torch.bool), init, tp)
+    done = torch.zeros(E, dtype=torch.bool)
+    acts = [torch.randn(E, P.num_agents, 4, generator=g) for _ in range(8)]
+    for i in range(warmup):
+        done = orc.step(acts[i % 8], done, tp)["done"].reshape(-1)
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(steps):
+        done = orc.step(acts[i % 8], done, tp)["done"].reshape(-1)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": E * n / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} ticks of the same {E}-env batch (oracle/hs_oracle.py, torch CPU fp32, {cores} threads)",
+            "ms_per_step": 1e3 * dt / n, "steps": n}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu_oracle(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference's torch code for the tick (oracle port) + CPU integrator "
+                   "stand-in for PhysX; Isaac Sim cannot run on this box"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def make_env(mupe_b200, E, device):
+    """BASELINE.json configs[1] through the public API (cfg tree -> registry class -> transforms)."""
+    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides={
+        "task.env.num_envs": E, "task.use_random_cylinder": 0, "task.scenario_flag": "empty",
+        "task.cylinder.max_num": 5, "task.sim.device": str(device), "algo.use_TP_net": 1})
+    base = mupe_b200.IsaacEnv.REGISTRY[cfg.task.name](cfg, headless=True)
+    return mupe_b200.TransformedEnv(base, mupe_b200.Compose(mupe_b200.InitTracker(), mupe_b200.PIDRateController()))
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import mupe_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1000 + rank)
+    E, A = E_PER_GPU, 3
+
+    # R independent env batches per GPU (weak scaling: E per GPU fixed); all share one TP_net
+    envs = [make_env(mupe_b200, E, dev) for _ in range(ROTATE)]
+    tp_net = envs[0].base_env.TP
+    for env in envs:
+        env.base_env.TP = tp_net
+        env.reset()
+    engines = [env.base_env.engine for env in envs]
+    actions = [torch.randn(E, A, 4, device=dev) for _ in range(ROTATE)]
+    F, C, K, H = 5, 5, 3, 10
+    gather_buf = [torch.empty(E, device=dev) for _ in range(world)] if world > 1 else None
+
+    def tick(i):
+        """The hot path with inputs resident in HBM: fused tick kernel -> TP_net -> fill kernel."""
+        eng = engines[i % ROTATE]
+        out = eng.step_pre(actions[(i + 3) % ROTATE], raw=True, reset_pid=None)
+        with torch.no_grad():
+            eng.step_post(tp_net(out["tp_input"]))
+        return eng
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        tick(i)
+    barrier()
+    launches0 = sum(e.launches for e in engines)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        eng = tick(i)
+        if world > 1 and (i + 1) % ROLLOUT == 0:
+            # the one collective of the path: episode returns of the rollout, all ranks
+            dist.all_gather(gather_buf, eng.stats[17].contiguous())
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(e.launches for e in engines) - launches0
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    extra = {}
+    if rank == 0:
+        # ---- kernel-only roofline: the tick kernel alone over the rotating (L2-cold) batches
+        nk = max(64, min(args.steps, 512))
+        for e in engines:
+            e.step_pre(actions[0], True, None)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(nk):
+            engines[i % ROTATE].step_pre(actions[(i + 5) % ROTATE], True, None)
+        k1.record()
+        torch.cuda.synchronize()
+        tick_us = 1e3 * k0.elapsed_time(k1) / nk
+        ab = algorithmic_bytes(A, C, K, F, H, True)
+        peaks = {}
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = ab["tick"] * E / (tick_us * 1e-6) / 1e9
+        extra["roofline"] = {"bound": "hbm", "kernel": "hs_tick_kernel<3,false>", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
+                             "algorithmic_bytes_per_launch": ab["tick"] * E, "launch_us": tick_us,
+                             "note": "launch_us is the back-to-back launch period of 4096-env launches "
+                                     "(launch-latency bound at this E); large-E sweep in profiles/"}
+        # ---- end to end through env.step(): pinned host actions in; observation, reward, done out
+        h_act = torch.randn(E, A, 4).pin_memory()
+        d_act = torch.empty(E, A, 4, device=dev)
+        slab0 = engines[0].out
+        h_res = torch.empty(slab0.slab.numel(), dtype=torch.float32).pin_memory()
+        h_bytes = torch.empty(slab0.bytes.numel(), dtype=torch.uint8).pin_memory()
+        tds = [env.reset() for env in envs]
+        ne = max(32, min(args.steps, 256))
+
+        def e2e_step(i):
+            r = i % ROTATE
+            td = tds[r]
+            d_act.copy_(h_act, non_blocking=True)
+            td.set(("agents", "action"), d_act)
+            td = envs[r].step(td)
+            out = engines[r].out                  # the tensors env.step() returned live in this slab
+            h_res.copy_(out.slab, non_blocking=True)
+            h_bytes.copy_(out.bytes.reshape(-1), non_blocking=True)
+            torch.cuda.synchronize()              # the caller needs the result before it can act again
+            tds[r] = mupe_b200.step_mdp(td)
+        for i in range(ROTATE):
+            e2e_step(i)
+        t0 = time.perf_counter()
+        for i in range(ne):
+            e2e_step(i)
+        e2e_s = time.perf_counter() - t0
+        extra["e2e"] = {"value": E * ne / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4,
+                        "d2h_bytes_per_step": h_res.numel() * 4 + h_bytes.numel(), "steps": ne, "n_gpus": 1,
+                        "api": "TransformedEnv(HideAndSeek).step(td): pinned host action -> H2D -> tick -> "
+                               "D2H of the whole observation/reward/done slab, host sync every step"}
+        extra["cpu_baseline"] = {k: v for k, v in time_cpu_oracle(40, 3, budget_s=20.0).items()
+                                 if k in ("value", "unit", "cores", "kind", "sample")}
+        value = world * E * args.steps / (ms_total * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "parallelism": f"env-sharded x{world}",
+                       "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
+                       "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
+            "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    for env in envs:
+        env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 512:
+            args.steps = 60
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,11 @@ ImportError, a missing GPU is an ``HsError`` at environment construction.
 """
 from . import _lib
 from ._lib import HsError
+from .compat import (Compose, InitTracker, SyncDataCollector, TensorDict, TransformedEnv, step_mdp)
 from .config import Cfg, build_hs_config, compose, load_drone_params
 from .engine import HsEngine
+from .envs import AgentSpec, HideAndSeek, IsaacEnv, PIDRateController, TP_net
 
-__all__ = ["HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params"]
+__all__ = ["HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+           "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
+           "HideAndSeek", "IsaacEnv", "PIDRateController", "TP_net"]

@@ -77,9 +77,10 @@ def compose(task: str = "HideAndSeek", algo: str = "mappo", overrides: Optional[
         for k in keys[:-1]:
             node = node.setdefault(k, {})
         node[keys[-1]] = v
-    root["sim"] = root["task"].get("sim", {})            # sim: ${task.sim}
-    root["env"] = root["task"].get("env", {})            # env: ${task.env}
-    return Cfg.wrap(root)
+    cfg = Cfg.wrap(root)
+    cfg["sim"] = cfg.task.setdefault("sim", Cfg())        # sim: ${task.sim}
+    cfg["env"] = cfg.task.setdefault("env", Cfg())        # env: ${task.env}
+    return cfg
 
 
 def load_drone_params(path: str = CRAZYFLIE_YAML) -> dict:

@@ -62,8 +62,9 @@ class HsEngine:
 
     def __init__(self, cfg: hs_config, device="cuda:0", num_output_sets: int = 2):
         device = torch.device(device)
-        if device.type != "cuda":
-            raise _lib.HsError("HsEngine needs a CUDA device: the environment step has no CPU path")
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.HsError("HsEngine needs a CUDA device: the environment step has no CPU path "
+                               f"(requested {device}, torch.cuda.is_available()={torch.cuda.is_available()})")
         self.cfg = cfg
         self.device = device
         self.E, self.A, self.C = cfg.num_envs, cfg.num_agents, cfg.num_cylinders

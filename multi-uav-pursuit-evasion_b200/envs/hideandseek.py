@@ -1,0 +1,346 @@
+"""HideAndSeek: 3-pursuer / 1-evader task behind the reference's IsaacEnv surface.
+
+Reference class: omni_drones/envs/hide_and_seek/hideandseek.py:183 (HideAndSeek).
+Every per-tick computation of that class (_pre_sim_step, the PhysX step, _compute_state_and_obs,
+_compute_reward_and_done) and of the PIDrate action transform runs inside libhs_b200.so; this
+module owns what stays on the host side: specs, the tensordict assembly (zero-copy views of the
+engine's buffers), reset *sampling* (kept in torch so it can follow the reference's draw order)
+and the call of the trajectory predictor between the two halves of a tick.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from ..compat import (BoundedTensorSpec, CompositeSpec, TensorDict, Transform, UnboundedContinuousTensorSpec)
+from ..config import Cfg, build_hs_config, load_drone_params
+from ..engine import HsEngine
+from .agent_spec import AgentSpec
+from .isaac_env import IsaacEnv
+from .tp_net import TP_net
+
+STAT_KEYS = (
+    "success", "collision", "blocked", "distance_reward", "distance_predicted_reward", "speed_reward",
+    "collision_reward", "collision_wall", "collision_cylinder", "collision_drone", "detect_reward",
+    "catch_reward", "smoothness_reward", "smoothness_mean", "smoothness_max", "first_capture_step",
+    "sum_detect_step", "return", "action_error_order1_mean", "action_error_order1_max",
+    "target_predicted_error", "distance_threshold_L", "out_of_arena", "smoothness_coef",
+)
+
+# fixed scenarios: cylinder xy in units of cylinder.size (hideandseek.py:480-531) and start
+# poses of up to four pursuers + the evader (hideandseek.py:633-682)
+_LAYOUTS = {
+    "empty": [],
+    "wall": [(0.0, 1.5), (0.0, -1.5), (0.0, 4.5), (0.0, -4.5)],
+    "narrow_gap": [(3, -3), (3, 3), (-3, 3), (-3, -3), (0, 3)],
+    "random": [(6, 4), (-6, 4), (-2, 4), (0, 2), (-2, -4), (0, -2)],
+    "passage": [(0, 3), (-2, 3), (2, 3), (2, -2), (-2, -2), (0, -2)],
+}
+_STARTS = {
+    "empty": ([(0.6, 0.0, 0.5), (0.8, 0.0, 0.5), (0.8, -0.2, 0.5), (0.8, 0.2, 0.5)], (-0.8, 0.0, 0.5)),
+    "wall": ([(0.6, 0.4, 0.5), (0.6, 0.0, 0.5), (0.6, -0.4, 0.5), (0.8, 0.2, 0.5)], (-0.8, 0.0, 0.5)),
+    "narrow_gap": ([(0.0, 0.7, 0.5), (0.2, 0.7, 0.5), (-0.2, 0.7, 0.5), (0.8, 0.2, 0.5)], (-0.5, 0.2, 0.5)),
+    "random": ([(0.6, 0.0, 0.5), (0.8, 0.0, 0.5), (0.8, -0.2, 0.5), (0.8, 0.2, 0.5)], (-0.8, 0.0, 0.5)),
+    "passage": ([(0.6, 0.0, 0.5), (0.8, 0.2, 0.5), (0.8, -0.2, 0.5), (0.8, 0.2, 0.5)], (0.0, 0.6, 0.5)),
+}
+
+
+class DroneView:
+    """What scripts and transforms read from ``env.drone`` (MultirotorBase, multirotor.py:55-263):
+    ``params`` (the vehicle yaml), ``n``, ``action_spec``/``state_spec`` and tensor accessors that
+    gather from the engine's arena (they replace the omni.physics.tensors views)."""
+
+    def __init__(self, engine: HsEngine, params: dict, n: int, device):
+        self._e, self.params, self.n, self.device = engine, params, n, device
+        self.num_rotors = params["rotor_configuration"]["num_rotors"]
+        self.action_spec = BoundedTensorSpec(-1, 1, self.num_rotors, device=device)
+        self.state_spec = UnboundedContinuousTensorSpec(19 + self.num_rotors, device=device)
+
+    def get_world_poses(self, clone=True):
+        return self._e.get_state(_lib.FIELD_DRONE_POS), self._e.get_state(_lib.FIELD_DRONE_ROT)
+
+    def get_velocities(self, clone=True):
+        return torch.cat([self._e.get_state(_lib.FIELD_DRONE_LINVEL), self._e.get_state(_lib.FIELD_DRONE_ANGVEL)], -1)
+
+    @property
+    def throttle(self):
+        return self._e.get_state(_lib.FIELD_THROTTLE)
+
+
+class HideAndSeek(IsaacEnv):
+    VARIANT_ENVGEN = False
+
+    # ------------------------------------------------------------------ construction
+    def _design_scene(self):
+        t = self.cfg.task
+        self.num_agents = int(t.num_agents)
+        self.max_cylinders = int(t.cylinder.max_num)
+        self.min_cylinders = int(t.cylinder.min_num)
+        self.num_cylinders = self.max_cylinders
+        self.drone_detect_radius, self.target_detect_radius = t.drone_detect_radius, t.target_detect_radius
+        self.catch_radius, self.arena_size, self.max_height = t.catch_radius, t.arena_size, t.max_height
+        self.cylinder_size, self.cylinder_height = t.cylinder.size, t.max_height
+        self.scenario_flag, self.use_random_cylinder = t.scenario_flag, bool(t.use_random_cylinder)
+        self.fixed_num = t.cylinder.fixed_num
+        self.use_fixed_num = self.fixed_num is not None
+        self.invalid_z, self.boundary = -20.0, t.arena_size - 0.1
+        algo = self.cfg.algo
+        self.use_TP_net = bool(algo.use_TP_net) if algo is not None and algo.use_TP_net is not None else True
+        self.use_eval, self.use_deployment = bool(t.use_eval), bool(t.use_deployment)
+        self.obs_max_cylinder = int(t.cylinder.obs_max_cylinder)
+        self.future_predcition_step, self.history_step = int(t.future_predcition_step), int(t.history_step)
+        self.window_step = int(t.window_step or 1)
+        if t.use_obstacles:
+            raise NotImplementedError("use_obstacles=1 (cylinders in the TP frame) is not built; the task YAMLs use 0")
+        self.time_encoding_dim = 4
+        self.collision_radius = t.collision_radius
+        self.mask_value = -5
+        self.update_epoch = 0
+        self.init_smoothness_coef = t.init_smoothness_coef if t.init_smoothness_coef is not None else (t.smoothness_coef or 0.0)
+        self.smooth_lr = t.smooth_lr or 0.0
+        self.max_smoothness_coef = t.max_smoothness_coef if t.max_smoothness_coef is not None else 5.0
+        self.smoothness_coef = min(self.max_smoothness_coef, self.init_smoothness_coef + self.smooth_lr * self.update_epoch)
+        if not self.use_random_cylinder and self.scenario_flag not in _LAYOUTS:
+            raise ValueError(f"unknown scenario_flag {self.scenario_flag!r}")
+        if not self.use_random_cylinder and len(_LAYOUTS[self.scenario_flag]) > self.num_cylinders:
+            raise ValueError(f"scenario {self.scenario_flag!r} needs cylinder.max_num >= {len(_LAYOUTS[self.scenario_flag])}")
+
+        params = load_drone_params()
+        self._hs_cfg = build_hs_config(
+            self.num_envs, num_agents=self.num_agents, num_cylinders=self.num_cylinders,
+            obs_max_cylinder=self.obs_max_cylinder, future_step=self.future_predcition_step,
+            history_step=self.history_step, max_episode_length=self.max_episode_length,
+            use_tp_net=self.use_TP_net, dt=self.dt, arena_size=t.arena_size, max_height=t.max_height,
+            cylinder_size=t.cylinder.size, catch_radius=t.catch_radius, collision_radius=t.collision_radius,
+            drone_detect_radius=t.drone_detect_radius, target_detect_radius=t.target_detect_radius,
+            v_drone=t.v_drone, mask_value=float(self.mask_value), dist_reward_coef=t.dist_reward_coef,
+            catch_reward_coef=t.catch_reward_coef, detect_reward_coef=t.detect_reward_coef,
+            collision_coef=t.collision_coef, speed_coef=t.speed_coef, smoothness_coef=self.smoothness_coef,
+            smoothness_gated=(not self.VARIANT_ENVGEN) and (not self.use_deployment),
+            write_smoothness_coef_stat=not self.VARIANT_ENVGEN,
+            ground_clamp=True if self.cfg.sim is None or self.cfg.sim.ground_clamp is None else bool(self.cfg.sim.ground_clamp),
+            max_linear_velocity=t.v_drone, drone_params=params)
+        self.engine = HsEngine(self._hs_cfg, self.device, num_output_sets=int(self.cfg.env.output_sets or 2))
+        self.v_prey = t.v_drone * t.v_prey                      # hideandseek.py:263
+        self.engine.v_prey.fill_(self.v_prey)
+        self._curriculum = self.v_prey < 1.3 and not self.VARIANT_ENVGEN
+        self.drone = DroneView(self.engine, params, self.num_agents, self.device)
+        self.action_is_raw = False      # set by the PIDRateController transform (fused in-kernel)
+        self._active_fixed = float(len(_LAYOUTS.get(self.scenario_flag, [])))
+
+        frame = 7 + 3 * self.num_agents
+        self.TP = TP_net(input_dim=frame, output_dim=3 * self.future_predcition_step,
+                         future_predcition_step=self.future_predcition_step, window_step=self.window_step).to(self.device)
+
+    def _set_specs(self):
+        n, dev = self.num_agents, self.device
+        F, K = self.future_predcition_step, self.obs_max_cylinder
+        U = UnboundedContinuousTensorSpec
+        D = 3 + (3 * F if self.use_TP_net else 0) + self.time_encoding_dim + 13
+        observation_spec = CompositeSpec({"state_self": U((1, D)), "state_others": U((n - 1, 3)), "cylinders": U((K, 5))}).to(dev)
+        state_spec = CompositeSpec({"state_drones": U((n, D)), "cylinders": U((K, 5))}).to(dev)
+        TP_spec = CompositeSpec({"TP_input": U((self.history_step, 7 + 3 * n)), "TP_groundtruth": U((1, 3)),
+                                 "TP_done": U((1, 3))}).to(dev)
+        E = self.num_envs
+        self.observation_spec = CompositeSpec({"agents": CompositeSpec({
+            "observation": observation_spec.expand(n), "state": state_spec, "TP": TP_spec})}).expand(E).to(dev)
+        self.action_spec = CompositeSpec({"agents": CompositeSpec({
+            "action": torch.stack([self.drone.action_spec] * n, dim=0)})}).expand(E).to(dev)
+        self.reward_spec = CompositeSpec({"agents": CompositeSpec({"reward": U((n, 1))})}).expand(E).to(dev)
+        self.agent_spec["drone"] = AgentSpec("drone", n, observation_key=("agents", "observation"),
+                                             action_key=("agents", "action"), reward_key=("agents", "reward"),
+                                             state_key=("agents", "state"))
+        stats_spec = CompositeSpec({k: U(1) for k in self._stat_keys()}).expand(E).to(dev)
+        info_spec = CompositeSpec({"drone_state": U((n, 13), device=dev),
+                                   "prev_action": torch.stack([self.drone.action_spec] * n, 0)}).expand(E).to(dev)
+        self.observation_spec["stats"] = stats_spec
+        self.observation_spec["info"] = info_spec
+        # live views of the engine's buffers (the reference also hands out live references)
+        self.stats = TensorDict({k: self.engine.stats[i].unsqueeze(-1) for i, k in enumerate(STAT_KEYS)}, [E], dev)
+        self._extra_stats = {}
+        self.info = TensorDict({"drone_state": self.engine.out["drone_state"], "prev_action": self.engine.prev_action}, [E], dev)
+
+    def _stat_keys(self):
+        return STAT_KEYS
+
+    # ------------------------------------------------------------------ views
+    @property
+    def progress_buf(self) -> torch.Tensor:
+        return self.engine.get_state(_lib.FIELD_PROGRESS)
+
+    # ------------------------------------------------------------------ reset sampling
+    def _uniform(self, lo, hi, *shape):
+        return lo + (hi - lo) * torch.rand(*shape, device=self.device)
+
+    def _sample_cylinders(self, n, drone_xy, target_xy):
+        """Vectorised version of rejection_sampling_random_cylinder + select_unoccupied_positions
+        (hideandseek.py:576-607, 106-119): a 9x9 grid of cell size 2*cylinder.size, cells at
+        integer distance >= 4 from the centre and the pursuers'/evader's cells are occupied,
+        `max_num` distinct free cells drawn without replacement per env (argsort of iid keys
+        instead of the reference's per-env CPU randperm loop)."""
+        C, cs = self.num_cylinders, self.cylinder_size
+        grid_size = 2 * cs
+        ng = int(self.arena_size * 2 / grid_size)
+        half = int(ng / 2)
+        dev = self.device
+        ii, jj = torch.meshgrid(torch.arange(ng, device=dev), torch.arange(ng, device=dev), indexing="ij")
+        occ = (torch.sqrt(((ii - half) ** 2 + (jj - half) ** 2).float()) >= (ng // 2)).unsqueeze(0).repeat(n, 1, 1)
+        cell = lambda xy: torch.clamp(torch.round(xy / grid_size).int() + half, 0, ng - 1).long()
+        dc, tc = cell(drone_xy), cell(target_xy)
+        ar = torch.arange(n, device=dev)
+        for k in range(dc.shape[1]):
+            occ[ar, dc[:, k, 0], dc[:, k, 1]] = True
+        occ[ar, tc[:, 0, 0], tc[:, 0, 1]] = True
+        if self.use_fixed_num:
+            n_active = torch.full((n, 1), int(self.fixed_num), device=dev)
+        else:
+            n_active = torch.randint(self.min_cylinders, C + 1, (n, 1), device=dev)
+        keys = torch.rand(n, ng * ng, device=dev)
+        keys = torch.where(occ.reshape(n, -1), torch.full_like(keys, 2.0), keys)
+        pick = torch.argsort(keys, dim=-1)[:, :C]
+        xy = torch.stack([pick // ng, pick % ng], dim=-1).float()
+        xy = torch.clamp((xy - half) * grid_size, -self.boundary, self.boundary)
+        inactive = torch.arange(C, device=dev).unsqueeze(0) >= n_active
+        z = torch.where(inactive, torch.tensor(self.invalid_z, device=dev), torch.tensor(0.5 * self.cylinder_height, device=dev))
+        return torch.cat([xy, z.unsqueeze(-1)], dim=-1), n_active.float()
+
+    def _sample_reset(self, n: int):
+        """Initial poses for n envs (draw order follows hideandseek.py:609-697)."""
+        A, C, dev = self.num_agents, self.num_cylinders, self.device
+        a = self.arena_size / math.sqrt(2.0)
+        zlo, zhi = self.max_height / 2 - 0.1, self.max_height / 2 + 0.1
+        if self.use_random_cylinder:
+            if not self.use_eval:
+                dxy = torch.stack([self._uniform(0.1, a - 0.1, n, A), self._uniform(-a + 0.1, a - 0.1, n, A)], -1)
+                txy = torch.stack([self._uniform(-a + 0.1, -0.1, n, 1), self._uniform(-a + 0.1, a - 0.1, n, 1)], -1)
+            else:
+                dxy = torch.tensor([p[:2] for p in _STARTS["empty"][0][:A]], device=dev).unsqueeze(0).expand(n, -1, -1)
+                txy = torch.tensor([_STARTS["empty"][1][:2]], device=dev).unsqueeze(0).expand(n, -1, -1)
+            dpos = torch.cat([dxy, self._uniform(zlo, zhi, n, A, 1)], -1)
+            tpos = torch.cat([txy, self._uniform(zlo, zhi, n, 1, 1)], -1)
+            cyl, n_active = self._sample_cylinders(n, dxy, txy)
+        else:
+            d, t = _STARTS[self.scenario_flag]
+            dpos = torch.tensor(d[:A], device=dev).unsqueeze(0).repeat(n, 1, 1)
+            tpos = torch.tensor([t], device=dev).unsqueeze(0).repeat(n, 1, 1)
+            cyl = torch.zeros(n, C, 3, device=dev)
+            cyl[..., 0] = torch.arange(C, device=dev) * 2 * self.cylinder_size
+            cyl[..., 2] = self.invalid_z
+            for k, (x, y) in enumerate(_LAYOUTS[self.scenario_flag]):
+                cyl[:, k] = torch.tensor([x * self.cylinder_size, y * self.cylinder_size, 0.5 * self.cylinder_height], device=dev)
+            n_active = torch.full((n, 1), self._active_fixed, device=dev)
+        if self.use_eval:
+            rpy = torch.zeros(n, A, 3, device=dev)
+        else:
+            lo = torch.tensor([-0.2, -0.2, 0.0], device=dev) * torch.pi
+            hi = torch.tensor([0.2, 0.2, 0.2], device=dev) * torch.pi
+            rpy = lo + (hi - lo) * torch.rand(n, A, 3, device=dev)
+        r, p, y = rpy.unbind(-1)
+        cy, sy, cp, sp, cr, sr = torch.cos(y * 0.5), torch.sin(y * 0.5), torch.cos(p * 0.5), torch.sin(p * 0.5), \
+            torch.cos(r * 0.5), torch.sin(r * 0.5)
+        rot = torch.stack([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                           cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy], dim=-1)
+        return dict(drone_pos=dpos, drone_rot=rot, target_pos=tpos.squeeze(1), cyl_pos=cyl, active_cylinders=n_active)
+
+    # ------------------------------------------------------------------ tensordict assembly
+    def _obs_td(self, out) -> TensorDict:
+        E, dev = self.num_envs, self.device
+        obs = TensorDict({"state_self": out["state_self"], "cylinders": out["obs_cylinders"]}, [E, self.num_agents], dev)
+        if self.num_agents > 1:
+            obs.set("state_others", out["state_others"])
+        state = TensorDict({"state_drones": out["state_drones"], "cylinders": out["obs_cylinders"]}, [E], dev)
+        agents = {"observation": obs, "state": state}
+        if self.use_TP_net:
+            agents["TP"] = TensorDict({"TP_input": out["tp_input"], "TP_groundtruth": out["tp_groundtruth"],
+                                       "TP_done": out["tp_done"]}, [E], dev)
+        self.info.set("drone_state", out["drone_state"])
+        return TensorDict({"agents": agents, "stats": self.stats, "info": self.info}, [E], dev)
+
+    def _predict(self, out):
+        if self.use_TP_net:
+            with torch.no_grad():
+                pred = self.TP(out["tp_input"])
+            self.engine.step_post(pred)
+
+    # ------------------------------------------------------------------ EnvBase protocol
+    def _reset(self, tensordict: Optional[TensorDict] = None, init: Optional[dict] = None, **kwargs) -> TensorDict:
+        E, dev = self.num_envs, self.device
+        if tensordict is not None and "_reset" in tensordict:
+            mask = tensordict.get("_reset").reshape(E)
+        else:
+            mask = None
+        last_stats = self.stats.clone()
+        if init is None:
+            init = self._sample_reset(E)          # rows outside the mask are ignored by the kernel
+        if "active_cylinders" in init:
+            ac = init["active_cylinders"]
+            self.active_cylinders = ac if mask is None or not hasattr(self, "active_cylinders") \
+                else torch.where(mask.unsqueeze(-1), ac, self.active_cylinders)
+        out = self.engine.reset(mask, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        self._predict(out)
+        td = TensorDict({}, self.batch_size, dev)
+        td.update(self._obs_td(out))
+        td.set("stats", last_stats)
+        td.set("truncated", out["truncated"])
+        return td
+
+    def _step(self, tensordict: TensorDict) -> TensorDict:
+        action = tensordict.get(("agents", "action"))
+        eng = self.engine
+        if self.action_is_raw:
+            done_prev = tensordict.get("done", None)
+            out = eng.step_pre(action.contiguous(), raw=True, reset_pid=done_prev)
+            # keys the reference's transform writes on the input tensordict (transforms.py:441-458)
+            tensordict.set(("stats", "action_error_order1"), out["action_error"])
+            tensordict.set(("info", "prev_action"), eng.prev_action)
+            tensordict.set(("agents", "action"), out["rotor_cmds"])
+            tensordict.set("ctbr", out["ctbr"])
+            tensordict.set("target_rate", out["target_rate"])
+        else:
+            ae = tensordict.get(("stats", "action_error_order1"), None)
+            if ae is None:
+                ae = torch.zeros(self.num_envs, self.num_agents, device=self.device)
+            eng.sets[(eng.cur + 1) % len(eng.sets)]["action_error"].copy_(ae)
+            out = eng.step_pre(action.contiguous(), raw=False, reset_pid=None)
+        self._predict(out)
+        nxt = self._obs_td(out)
+        nxt.set(("agents", "reward"), out["reward"])
+        nxt.set("done", out["done"])
+        if self._curriculum:
+            self._update_v_prey(out["done"])
+        return TensorDict({"next": nxt}, self.batch_size, self.device)
+
+    def _update_v_prey(self, done):
+        """hideandseek.py:1012-1015 without a host sync: v_prey lives in device memory."""
+        ok = done.any() & (self.engine.stats[0].mean() >= 0.98)
+        v = self.engine.v_prey
+        v.copy_(torch.where(ok, torch.clamp(v + 0.05, max=1.3), v))
+
+    def close(self):
+        if not self._is_closed:
+            self.engine.close()
+        super().close()
+
+
+class PIDRateController(Transform):
+    """Stand-in for the reference's PIDrate action transform
+    (omni_drones/utils/torchrl/transforms.py:404-459).  The arithmetic of that transform and of
+    the rate PID it wraps (lee_position_controller.py:476-550) is fused into hs_tick_kernel;
+    this object only switches the base env to raw-action mode and re-declares the action spec
+    the way the reference's ``transform_input_spec`` does."""
+
+    def __init__(self, controller=None, action_key=("agents", "action")):
+        super().__init__([], in_keys_inv=[("info", "drone_state")])
+        self.controller, self.action_key = controller, action_key
+
+    def set_parent(self, env):
+        super().set_parent(env)
+        base = env.base_env if hasattr(env, "base_env") else env
+        base.action_is_raw = True
+
+    def transform_input_spec(self, input_spec):
+        spec = input_spec[("_action_spec", *self.action_key)]
+        input_spec[("_action_spec", *self.action_key)] = UnboundedContinuousTensorSpec(
+            tuple(spec.shape[:-1]) + (4,), device=spec.device)
+        return input_spec

@@ -1,0 +1,154 @@
+"""GPU tests of the reference-facing surface: IsaacEnv.REGISTRY -> HideAndSeek(cfg, headless)
+-> TransformedEnv(..., PIDRateController) -> reset()/step()/collector, checked against the
+CPU oracle driven with the same injected initial state and the same actions.
+(Reference call sites: scripts/train.py:110-205, omni_drones/envs/isaac_env.py:210-240.)
+"""
+import pytest
+import torch
+
+from oracle import hs_oracle as O
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _fp32_lstm():
+    # torch lets cuDNN run the LSTM in TF32 by default; the parity bar is fp32
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def make(E, **over):
+    import mupe_b200
+    o = {"task.env.num_envs": E, "task.sim.device": DEV}
+    o.update(over)
+    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides=o)
+    base = mupe_b200.IsaacEnv.REGISTRY[cfg.task.name.lower()](cfg, headless=True)
+    env = mupe_b200.TransformedEnv(base, mupe_b200.Compose(mupe_b200.InitTracker(), mupe_b200.PIDRateController()))
+    return mupe_b200, cfg, base, env
+
+
+def oracle_for(base, E, **kw):
+    P = O.HSParams(num_agents=base.num_agents, num_cylinders=base.num_cylinders,
+                   obs_max_cylinder=base.obs_max_cylinder, use_tp_net=base.use_TP_net,
+                   max_episode_length=base.max_episode_length, **kw)
+    return P, O.HideAndSeekOracle(P, E)
+
+
+def test_specs_and_registry():
+    m, cfg, base, env = make(32)
+    assert m.IsaacEnv.REGISTRY["HideAndSeek"] is m.IsaacEnv.REGISTRY["hideandseek"] is m.HideAndSeek
+    spec = base.agent_spec["drone"]
+    assert spec.n == 3
+    assert tuple(spec.observation_spec["state_self"].shape) == (32, 3, 1, 35)
+    assert tuple(spec.observation_spec["state_others"].shape) == (32, 3, 2, 3)
+    assert tuple(spec.observation_spec["cylinders"].shape) == (32, 3, 3, 5)
+    assert tuple(spec.state_spec["state_drones"].shape) == (32, 3, 35)
+    assert tuple(spec.action_spec.shape) == (32, 3, 4)
+    assert tuple(spec.reward_spec.shape) == (32, 3, 1)
+    stats = [k for k in base.observation_spec.keys(True, True) if isinstance(k, tuple) and k[0] == "stats"]
+    assert len(stats) == 24
+    assert base.drone.params["max_thrust_ratio"] == 0.9 and base.drone.n == 3
+    assert isinstance(base.TP, torch.nn.Module)
+    with pytest.raises(RuntimeError):
+        base.to("cpu")
+    env.close()
+
+
+def test_env_matches_oracle_through_public_api():
+    E = 96
+    m, cfg, base, env = make(E)
+    P, orc = oracle_for(base, E)
+    tp_cpu = m.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step)
+    tp_cpu.load_state_dict({k: v.cpu() for k, v in base.TP.state_dict().items()})
+    tp_fn = lambda x: tp_cpu(x).detach()
+    torch.manual_seed(5)
+    init = base._sample_reset(E)
+    cinit = {k: v.cpu() for k, v in init.items()}
+    td = env.reset(init=init)
+    want = orc.reset(torch.ones(E, dtype=torch.bool), cinit, tp_fn)
+    assert td.get("is_init").all() and not td.get("done").any()
+    # cuDNN LSTM vs CPU LSTM differ by ~1e-6 in the prediction -> compare at 2e-4
+    assert_close("reset/state_self", td[("agents", "observation", "state_self")], want["state_self"], rtol=2e-4, atol=2e-5)
+    assert_close("reset/TP_input", td[("agents", "TP", "TP_input")], want["tp_input"])
+    g = torch.Generator().manual_seed(11)
+    for t in range(12):
+        act = torch.randn(E, 3, 4, generator=g)
+        td.set(("agents", "action"), act.to(DEV))
+        done_prev = td.get("done").reshape(-1).cpu()
+        td = env.step(td)
+        want = orc.step(act, done_prev, tp_fn)
+        nxt = td.get("next")
+        flip = 0.02      # free-running: a few envs may sit on a discontinuity
+        assert_close(f"t{t}/state_self", nxt[("agents", "observation", "state_self")], want["state_self"], rtol=2e-4, atol=2e-5, max_bad_frac=flip)
+        assert_close(f"t{t}/state_others", nxt[("agents", "observation", "state_others")], want["others"], max_bad_frac=flip)
+        assert_close(f"t{t}/cylinders", nxt[("agents", "observation", "cylinders")], want["cylinders"], max_bad_frac=flip)
+        assert nxt[("agents", "state", "cylinders")] is nxt[("agents", "observation", "cylinders")]
+        assert_close(f"t{t}/state_drones", nxt[("agents", "state", "state_drones")], want["state_drones"], rtol=2e-4, atol=2e-5, max_bad_frac=flip)
+        assert_close(f"t{t}/TP_input", nxt[("agents", "TP", "TP_input")], want["tp_input"], max_bad_frac=flip)
+        assert_close(f"t{t}/reward", nxt[("agents", "reward")], want["reward"], max_bad_frac=flip)
+        assert_close(f"t{t}/drone_state", nxt[("info", "drone_state")], want["drone_state"], max_bad_frac=flip)
+        assert_close(f"t{t}/return", nxt[("stats", "return")], want["stats"][:, O.S["return"]], atol=1e-3, max_bad_frac=flip)
+        # keys the reference's PIDrate transform leaves on the input tensordict
+        assert_close(f"t{t}/ctbr", td["ctbr"], want["ctbr"], max_bad_frac=flip)
+        assert_close(f"t{t}/target_rate", td["target_rate"], want["target_rate"], max_bad_frac=flip)
+        assert_close(f"t{t}/action", td[("agents", "action")], want["cmds"], max_bad_frac=flip)
+        assert_close(f"t{t}/action_error", td[("stats", "action_error_order1")], want["action_error"], max_bad_frac=flip)
+        assert not nxt.get("is_init").any()
+        td = m.step_mdp(td)
+    env.close()
+
+
+def test_collector_rollout_and_episode_boundary():
+    E, T = 64, 8
+    m, cfg, base, env = make(E, **{"task.env.max_episode_length": 5})
+    frames = []
+
+    def policy(td):
+        td.set(("agents", "action"), torch.randn(E, 3, 4, device=DEV))
+        return td
+    col = m.SyncDataCollector(env, policy=policy, frames_per_batch=E * T, total_frames=E * T * 2, return_same_td=True)
+    for data in col:
+        frames.append(data)
+    assert len(frames) == 2
+    d = frames[0]
+    assert tuple(d.batch_size) == (E, T)
+    assert tuple(d[("next", "agents", "reward")].shape) == (E, T, 3, 1)
+    done = d[("next", "done")].reshape(E, T)
+    # progress reaches max_episode_length=5 on the 5th tick, every env resets together
+    assert done[:, 4].all() and not done[:, :4].any()
+    prog = d[("next", "agents", "TP", "TP_input")][:, :, -1, 0]     # newest frame carries raw progress
+    assert torch.equal(prog[0].cpu(), torch.tensor([1., 2., 3., 4., 5., 1., 2., 3.]))
+    assert d[("is_init")].reshape(E, T)[:, 0].all() and d[("is_init")].reshape(E, T)[:, 5].all()
+    # stats returned by reset are the pre-reset values (isaac_env.py:216,223)
+    ret_done = d[("next", "stats", "return")].reshape(E, T)[:, 4]
+    ret_after_reset = d[("stats", "return")].reshape(E, T)[:, 5]
+    assert torch.allclose(ret_done, ret_after_reset)
+    assert col._fps > 0
+    env.close()
+
+
+def test_partial_reset_mask_and_direct_rotor_commands():
+    E = 32
+    import mupe_b200 as m
+    cfg = m.compose("HideAndSeek", "mappo", overrides={"task.env.num_envs": E, "task.sim.device": DEV,
+                                                        "algo.use_TP_net": 0})
+    base = m.HideAndSeek(cfg, headless=True)          # no transform: rotor commands go straight in
+    td = base.reset()
+    assert tuple(td[("agents", "observation", "state_self")].shape) == (E, 3, 1, 20)
+    for _ in range(3):
+        td.set(("agents", "action"), torch.rand(E, 3, 4, device=DEV) * 2 - 1)
+        td = m.step_mdp(base.step(td))
+    prog = base.progress_buf
+    assert torch.all(prog == 3)
+    mask = torch.zeros(E, 1, dtype=torch.bool, device=DEV)
+    mask[::2] = True
+    td.set("_reset", mask)
+    td = base.reset(td)
+    prog = base.progress_buf
+    assert torch.all(prog[::2] == 0) and torch.all(prog[1::2] == 3)
+    base.close()

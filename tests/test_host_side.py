@@ -1,0 +1,122 @@
+"""CPU tests of everything that does not need a GPU: the C-ABI library loads and exports every
+symbol the header declares, refuses to run without a device (no CPU fallback), the config
+composer reproduces the hydra tree, and the tensordict/torchrl stand-ins behave."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    import mupe_b200
+    from mupe_b200 import _lib
+    header = open(os.path.join(REPO, "include", "hs_b200.h")).read()
+    declared = set(re.findall(r"\b(hs_[a-z_]+)\s*\(", header)) - {"hs_default_config"} | {"hs_default_config"}
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/hs_b200.h but not exported"
+    assert set(_lib.exported_symbols()) == declared
+    assert _lib.lib.hs_abi_version() == _lib.HS_ABI_VERSION
+
+
+def test_config_struct_layout_matches_c_defaults(built_lib):
+    import mupe_b200
+    from mupe_b200 import _lib
+    c = _lib.default_config(128)            # filled by the C side
+    p = mupe_b200.build_hs_config(128)      # filled by the Python side from the YAML/vehicle file
+    for name, _ in _lib.hs_config._fields_:
+        a, b = getattr(c, name), getattr(p, name)
+        if hasattr(a, "__len__"):
+            assert list(a) == pytest.approx(list(b), rel=1e-6), name
+        else:
+            assert a == pytest.approx(b, rel=1e-6), name
+    assert c.kf == pytest.approx(0.1259604, rel=1e-6) and c.km == pytest.approx(3.8800789e-3, rel=1e-6)
+    assert c.hover_throttle == pytest.approx(0.79548, rel=1e-4) and c.rotor_alpha == pytest.approx(0.4, rel=1e-6)
+    n = _lib.lib.hs_arena_floats(ctypes.byref(c))
+    assert n == (23 * 3 + 8 + 15) * 128
+
+
+def test_invalid_configs_are_rejected(built_lib):
+    from mupe_b200 import _lib
+    for field, bad in (("num_agents", 4), ("num_cylinders", 9), ("obs_max_cylinder", 6), ("num_envs", 0), ("abi_version", 99)):
+        c = _lib.default_config(64)
+        setattr(c, field, bad)
+        assert _lib.lib.hs_arena_floats(ctypes.byref(c)) == -1, field
+        assert _lib.lib.hs_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(built_lib):
+    import mupe_b200
+    from mupe_b200 import _lib
+    c = _lib.default_config(64)
+    h = ctypes.c_void_p()
+    assert _lib.lib.hs_create(ctypes.byref(c), ctypes.byref(h)) == -2        # HS_ERR_NO_DEVICE
+    assert b"no CPU path" in _lib.lib.hs_last_error()
+    with pytest.raises(mupe_b200.HsError):
+        mupe_b200.HsEngine(c, "cuda:0")
+    cfg = mupe_b200.compose("HideAndSeek", overrides={"task.env.num_envs": 8})
+    with pytest.raises(mupe_b200.HsError):
+        mupe_b200.HideAndSeek(cfg, headless=True)
+
+
+def test_compose_reproduces_the_hydra_tree():
+    import mupe_b200
+    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides={"task.env.num_envs": 4096, "task.cylinder.max_num": 8})
+    assert cfg.task.name == "HideAndSeek" and cfg.env.num_envs == 4096 and cfg.env is cfg.task.env
+    assert cfg.env.env_spacing == 5                     # from base/env_base merged @_here_
+    assert cfg.sim.dt == 0.01 and cfg.sim.substeps == 1
+    assert cfg.task.cylinder.max_num == 8 and cfg.task.cylinder.obs_max_cylinder == 3
+    assert cfg.algo.use_TP_net == 1 and cfg.seed == 0
+    assert cfg.task.does_not_exist is None              # struct-less OmegaConf behaviour
+    g = mupe_b200.compose("HideAndSeek_envgen")
+    assert g.task.ratio_unif == 0.3 and g.task.eval_iter == 3
+    p = mupe_b200.load_drone_params()
+    assert p["mass"] == 0.0321 and p["rotor_configuration"]["time_constant"] == 0.025
+
+
+def test_tensordict_standin():
+    from mupe_b200.compat import TensorDict
+    td = TensorDict({"a": torch.zeros(4, 3), "n": {"x": torch.ones(4, 2, 5)}}, [4])
+    td[("n", "y")] = torch.arange(4)
+    assert td.keys(True, True) == ["a", ("n", "x"), ("n", "y")]
+    assert td[("n", "x")].shape == (4, 2, 5) and td.get("zz", None) is None
+    sub = td[1:3]
+    assert tuple(sub.batch_size) == (2,) and sub[("n", "y")].tolist() == [1, 2]
+    td[torch.tensor([0, 2])] = 7.0
+    assert td["a"][0, 0] == 7 and td["a"][1, 0] == 0 and td[("n", "x")][2, 0, 0] == 7
+    st = torch.stack([td, td], dim=1)
+    assert tuple(st.batch_size) == (4, 2) and st["a"].shape == (4, 2, 3) and st.numel() == 8
+    c = td.clone()
+    c["a"] += 1
+    assert td["a"][1, 0] == 0
+    sel = td.select("a", ("n", "x"))
+    assert sel.keys(True, True) == ["a", ("n", "x")]
+    assert td.exclude("a").keys() == ["n"]
+    td.update({"n": {"z": torch.zeros(4)}})
+    assert ("n", "z") in td and ("n", "x") in td
+
+
+def test_spec_standins():
+    from mupe_b200.compat import BoundedTensorSpec, CompositeSpec, UnboundedContinuousTensorSpec as U
+    obs = CompositeSpec({"state_self": U((1, 35)), "state_others": U((2, 3))})
+    top = CompositeSpec({"agents": CompositeSpec({"observation": obs.expand(3)})}).expand(16)
+    assert tuple(top[("agents", "observation", "state_self")].shape) == (16, 3, 1, 35)
+    z = top.zero()
+    assert z[("agents", "observation", "state_others")].shape == (16, 3, 2, 3) and tuple(z.batch_size) == (16,)
+    act = torch.stack([BoundedTensorSpec(-1, 1, 4)] * 3, dim=0)
+    assert tuple(act.shape) == (3, 4)
+    top["stats"] = CompositeSpec({"return": U(1)}).expand(16)
+    assert ("stats", "return") in top.keys(True, True)
+
+
+def test_algorithmic_bytes_formula_matches_survey():
+    import bench
+    ab = bench.algorithmic_bytes(3, 5, 3, 5, 10, True)
+    assert ab["total"] == 3077                      # SURVEY.md section 8d / BASELINE.md section 3
+    assert ab["tick"] + ab["fill"] == ab["total"]
+    assert bench.algorithmic_bytes(3, 8, 3, 5, 10, True)["total"] == 3077 + 36
