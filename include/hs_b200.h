@@ -177,6 +177,23 @@ int hs_step_pre(hs_handle* h, const float* action, int action_is_raw,
 /* Second half, only when use_tp_net: tp_pred [E,3F] is TP_net's tanh output for
  * bufs.tp_input; writes state_self / state_drones (hideandseek.py:834-887). */
 int hs_step_post(hs_handle* h, const float* tp_pred, void* stream);
+/* Same second half, but with the trajectory predictor fused in: the kernel evaluates
+ * TP_net (one-layer LSTM, hidden 64, zero initial state, last step -> Linear -> tanh;
+ * omni_drones/learning/mappo.py:572-589) on bufs.tp_input straight from the module's live
+ * parameter tensors and writes state_self / state_drones.  Replaces the cuDNN LSTM call the
+ * reference makes inside _compute_state_and_obs (hideandseek.py:834).  tp_pred_out [E,3F]
+ * receives the raw prediction when non-NULL. */
+typedef struct hs_tp_weights {
+    const float* weight_ih;     /* [4*64, 7+3A]  lstm.weight_ih_l0, gate order i,f,g,o */
+    const float* weight_hh;     /* [4*64, 64]    lstm.weight_hh_l0 */
+    const float* bias_ih;       /* [4*64]        lstm.bias_ih_l0 */
+    const float* bias_hh;       /* [4*64]        lstm.bias_hh_l0 */
+    const float* fc_weight;     /* [3F, 64]      fc.weight */
+    const float* fc_bias;       /* [3F]          fc.bias */
+    int32_t input_size, hidden_size, output_size;
+    int32_t reserved;
+} hs_tp_weights;
+int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, void* stream);
 /* Partial reset.  env_mask [E] bool (NULL = all).  Initial poses are injected (sampling
  * stays on the host side so that it can follow the reference's RNG streams):
  *   drone_pos [E,A,3], drone_rot [E,A,4] (wxyz), target_pos [E,3], cyl_pos [E,C,3];

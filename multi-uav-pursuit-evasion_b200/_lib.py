@@ -65,6 +65,13 @@ class hs_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _BUF_FIELDS]
 
 
+class hs_tp_weights(C.Structure):
+    _fields_ = [("weight_ih", C.c_void_p), ("weight_hh", C.c_void_p), ("bias_ih", C.c_void_p),
+                ("bias_hh", C.c_void_p), ("fc_weight", C.c_void_p), ("fc_bias", C.c_void_p),
+                ("input_size", C.c_int32), ("hidden_size", C.c_int32), ("output_size", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 _EXPORTS = {
     "hs_abi_version": (C.c_int, []),
     "hs_last_error": (C.c_char_p, []),
@@ -75,6 +82,7 @@ _EXPORTS = {
     "hs_bind_buffers": (C.c_int, [C.c_void_p, C.POINTER(hs_buffers)]),
     "hs_step_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_step_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_step_post_tp": (C.c_int, [C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
     "hs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_state_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -822,6 +822,230 @@ hs_fill_kernel(const __grid_constant__ KParams P) {
 }
 
 // =========================================================================================
+// Fused trajectory predictor + second half of the observation.
+//   pred = tanh(FC(LSTM_64(TP_input)))           omni_drones/learning/mappo.py:572-589
+//   state_self / state_drones rows                omni_drones/envs/hide_and_seek/hideandseek.py:834-887
+// The reference runs the predictor through cuDNN between two groups of eager ops; here one
+// kernel keeps the whole recurrence on chip: a CTA owns TPB_E environments, the 80x256 gate
+// matrix [W_ih | W_hh]^T lives in shared memory (80 KB, permuted so that a thread owns the
+// i,f,g,o columns of two hidden units), x_t / h_t are broadcast reads, and each thread keeps
+// a 4-env x 8-column fp32 accumulator tile in registers (SIMT FFMA; the 1e-4 fp32 parity bar
+// rules out the TF32/BF16 tensor-core paths).  The epilogue applies the FC + tanh, forms the
+// 35-wide rows and sends both row tiles out with TMA bulk stores.
+// =========================================================================================
+constexpr int TPB_E = 32;            // envs per CTA
+constexpr int TP_THREADS = 256;
+constexpr int TP_NE = TPB_E / 8;     // envs per thread (8 warps, one env group per warp)
+constexpr int TP_HID = 64;
+
+struct TPParams {
+    const float* w_ih;   // [256, FD]   gate order i,f,g,o (torch.nn.LSTM)
+    const float* w_hh;   // [256, 64]
+    const float* b_ih;   // [256]
+    const float* b_hh;   // [256]
+    const float* fc_w;   // [3F, 64]
+    const float* fc_b;   // [3F]
+    float* pred_out;     // [E, 3F] or null
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int A>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+    extern __shared__ __align__(128) float smem[];
+    const hs_config& c = P.c;
+    constexpr int FD = 7 + 3 * A;
+    constexpr int KTOT = FD + TP_HID;
+    const int H = c.history_step;
+    const int F3 = 3 * c.future_step;
+    const int D = 20 + F3;
+    const int E = c.num_envs;
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * TPB_E;
+    const int nenv = (int)min((int64_t)TPB_E, E - e0);
+
+    float* Wp = smem;                               // [KTOT][256]
+    float* bias = Wp + KTOT * 256;                  // [256]
+    float* fcw = bias + 256;                        // [F3][64]
+    float* fcb = fcw + F3 * TP_HID;                 // [F3] (padded to 32)
+    float* xs = fcb + 32;                           // [H][FD][TPB_E]
+    float* hs = xs + H * FD * TPB_E;                // [2][64][TPB_E]
+    float* preds = hs + 2 * TP_HID * TPB_E;         // [TPB_E][F3]
+
+    // ---- stage weights (permuted) and the input tile ------------------------------------
+    // column of (gate g, hidden unit j): thread-group t = j/2 owns columns t*8 + g*2 + (j&1)
+    for (int i = tid; i < 256 * FD; i += TP_THREADS) {
+        const int row = i / FD, k = i - row * FD;
+        const int g = row >> 6, j = row & 63;
+        Wp[k * 256 + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_ih + i);
+    }
+    for (int i = tid; i < 256 * TP_HID; i += TP_THREADS) {
+        const int row = i >> 6, k = i & 63;
+        const int g = row >> 6, j = row & 63;
+        Wp[(FD + k) * 256 + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_hh + i);
+    }
+    {
+        const int row = tid, g = row >> 6, j = row & 63;
+        bias[(j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
+    }
+    for (int i = tid; i < F3 * TP_HID; i += TP_THREADS) fcw[i] = __ldg(W.fc_w + i);
+    if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
+    {
+        const float* src = P.b.tp_input + e0 * (int64_t)(H * FD);
+        const int per_env = H * FD;
+        for (int i = tid; i < TPB_E * per_env; i += TP_THREADS) {
+            const int e = i / per_env, r = i - e * per_env;       // r = s*FD + k
+            xs[r * TPB_E + e] = (e < nenv) ? __ldg(src + i) : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    // ---- recurrence ------------------------------------------------------------------------
+    const int t = tid & 31;              // column group: hidden units 2t, 2t+1
+    const int eg = tid >> 5;             // env group (= warp): envs eg*TP_NE .. +TP_NE-1
+    float cst[TP_NE][2];
+#pragma unroll
+    for (int e = 0; e < TP_NE; ++e) { cst[e][0] = 0.f; cst[e][1] = 0.f; }
+    float bv[8];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + t * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + t * 8 + 4);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    }
+    int cur = 0;
+    for (int s = 0; s < H; ++s) {
+        float acc[TP_NE][8];
+#pragma unroll
+        for (int e = 0; e < TP_NE; ++e)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[e][q] = bv[q];
+        const float* xrow = xs + (s * FD) * TPB_E + eg * TP_NE;
+#pragma unroll 4
+        for (int k = 0; k < FD; ++k) {
+            const float4 xv = *reinterpret_cast<const float4*>(xrow + k * TPB_E);
+            const float4 w0 = *reinterpret_cast<const float4*>(Wp + k * 256 + t * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(Wp + k * 256 + t * 8 + 4);
+            const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int e = 0; e < TP_NE; ++e)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(xe[e], wq[q], acc[e][q]);
+        }
+        if (s > 0) {                      // h_0 = 0
+            const float* hrow = hs + cur * TP_HID * TPB_E + eg * TP_NE;
+#pragma unroll 4
+            for (int k = 0; k < TP_HID; ++k) {
+                const float4 hv = *reinterpret_cast<const float4*>(hrow + k * TPB_E);
+                const float4 w0 = *reinterpret_cast<const float4*>(Wp + (FD + k) * 256 + t * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(Wp + (FD + k) * 256 + t * 8 + 4);
+                const float he[4] = {hv.x, hv.y, hv.z, hv.w};
+                const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int e = 0; e < TP_NE; ++e)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(he[e], wq[q], acc[e][q]);
+            }
+        }
+        float* hnext = hs + (cur ^ 1) * TP_HID * TPB_E + eg * TP_NE;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float hv[TP_NE];
+#pragma unroll
+            for (int e = 0; e < TP_NE; ++e) {
+                const float ig = sigmoidf_(acc[e][0 + u]), fg = sigmoidf_(acc[e][2 + u]);
+                const float gg = tanhf(acc[e][4 + u]), og = sigmoidf_(acc[e][6 + u]);
+                cst[e][u] = fmaf(fg, cst[e][u], ig * gg);
+                hv[e] = og * tanhf(cst[e][u]);
+            }
+            *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    // ---- FC + tanh -------------------------------------------------------------------------
+    {
+        const float* hfin = hs + cur * TP_HID * TPB_E;
+        for (int i = tid; i < TPB_E * F3; i += TP_THREADS) {
+            const int o = i / TPB_E, e = i - o * TPB_E;
+            float a = fcb[o];
+#pragma unroll 8
+            for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[j * TPB_E + e], a);
+            const float pv = tanhf(a);
+            preds[e * F3 + o] = pv;
+            if (W.pred_out != nullptr && e < nenv) W.pred_out[(e0 + e) * F3 + o] = pv;
+        }
+    }
+    __syncthreads();
+
+    // ---- rows: thread (a, e) with e fastest -> coalesced arena reads ----------------------------
+    float* tile_self = Wp;                                  // weights are dead: reuse as staging
+    float* tile_all = Wp + TPB_E * A * (20 + 3 * FMAX);
+    if (tid < TPB_E * A) {
+        const int slot = tid / TPB_E, el = tid - slot * TPB_E;
+        const bool valid = el < nenv;
+        const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
+        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+        const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+        const float progress = *EROW(E_PROGRESS);
+        const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+        V3 heading, up;
+        heading_up(q, heading, up);
+        const float tfrac = progress / (float)c.max_episode_length;
+        const V3 t_rpos = p - tp;
+        const float mv = c.mask_value;
+        const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+        float* r1 = tile_self + (el * A + slot) * D;
+        float* r2 = tile_all + (el * A + slot) * D;
+        r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+        r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z;
+        const float* pr = preds + el * F3;
+        for (int f = 0; f < c.future_step; ++f) {
+            const float px = (pr[3 * f] * 0.5f) * c.arena_size;
+            const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
+            const float pz = ((pr[3 * f + 2] + 1.0f) / 2.0f) * c.max_height;
+            const float dx = p.x - px, dy = p.y - py, dz = p.z - pz;
+            r1[3 + 3 * f] = dx; r1[4 + 3 * f] = dy; r1[5 + 3 * f] = dz;
+            r2[3 + 3 * f] = dx; r2[4 + 3 * f] = dy; r2[5 + 3 * f] = dz;
+        }
+        const int o = 3 + F3;
+        const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+#pragma unroll
+        for (int i = 0; i < 17; ++i) { r1[o + i] = tail[i]; r2[o + i] = tail[i]; }
+    }
+    const int nwords = nenv * A * D;
+    float* g1 = P.b.state_self + e0 * A * D;
+    float* g2 = P.b.state_drones + e0 * A * D;
+    const bool bulk = HS_USE_BULK_STORE && (nenv == TPB_E) && ((nwords & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
+    if (bulk) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(g1, tile_self, (uint32_t)nwords * 4u);
+            bulk_store(g2, tile_all, (uint32_t)nwords * 4u);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else {
+        __syncthreads();
+        for (int i = tid; i < nwords; i += TP_THREADS) { g1[i] = tile_self[i]; g2[i] = tile_all[i]; }
+    }
+}
+
+static size_t tp_smem_bytes(const hs_config& c) {
+    const int FD = 7 + 3 * c.num_agents, KT = FD + TP_HID, F3 = 3 * c.future_step;
+    size_t words = (size_t)KT * 256 + 256 + (size_t)F3 * TP_HID + 32 + (size_t)c.history_step * FD * TPB_E +
+                   2 * TP_HID * TPB_E + (size_t)TPB_E * F3;
+    return words * sizeof(float);
+}
+
+// =========================================================================================
 // Reset scatter: hideandseek.py:698-717, multirotor.py:635-650
 // =========================================================================================
 template <int A>
@@ -1003,6 +1227,18 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
     // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
     const int64_t warps = ((int64_t)cfg->num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
     h->block = (warps >= 4 * 148 * 4) ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
+    if (cfg->use_tp_net) {
+        // opt in to > 48 KB dynamic shared memory once (not a stream operation: keeps the
+        // step entry points legal inside CUDA-graph capture)
+        const int smem = (int)tp_smem_bytes(*cfg);
+        cudaError_t e = cudaSuccess;
+        switch (cfg->num_agents) {
+            case 1: e = cudaFuncSetAttribute(hs_tp_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+            case 2: e = cudaFuncSetAttribute(hs_tp_fill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+            default: e = cudaFuncSetAttribute(hs_tp_fill_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+        }
+        if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
+    }
     *out = h;
     return HS_OK;
 }
@@ -1064,6 +1300,31 @@ int hs_step_post(hs_handle* h, const float* tp_pred, void* stream) {
         case 1: hs_fill_kernel<1><<<grid, h->block, 0, s>>>(P); break;
         case 2: hs_fill_kernel<2><<<grid, h->block, 0, s>>>(P); break;
         default: hs_fill_kernel<3><<<grid, h->block, 0, s>>>(P); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return HS_OK;
+}
+
+int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, void* stream) {
+    if (!h || !w) return set_err(HS_ERR_INVALID, "hs_step_post_tp: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_post_tp: call hs_bind_buffers first%s");
+    if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_post_tp: config has use_tp_net == 0%s");
+    if (!w->weight_ih || !w->weight_hh || !w->bias_ih || !w->bias_hh || !w->fc_weight || !w->fc_bias)
+        return set_err(HS_ERR_INVALID, "hs_step_post_tp: a weight pointer is NULL%s");
+    if (w->hidden_size != TP_HID || w->input_size != 7 + 3 * h->cfg.num_agents || w->output_size != 3 * h->cfg.future_step)
+        return set_err(HS_ERR_INVALID, "hs_step_post_tp: predictor shape must be LSTM(7+3A -> 64) + Linear(64 -> 3F)%s");
+    KParams P = make_params(h);
+    TPParams W;
+    W.w_ih = w->weight_ih; W.w_hh = w->weight_hh; W.b_ih = w->bias_ih; W.b_hh = w->bias_hh;
+    W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = tp_pred_out;
+    const size_t smem = tp_smem_bytes(h->cfg);
+    const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + TPB_E - 1) / TPB_E);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (h->cfg.num_agents) {
+        case 1: hs_tp_fill_kernel<1><<<grid, TP_THREADS, smem, s>>>(P, W); break;
+        case 2: hs_tp_fill_kernel<2><<<grid, TP_THREADS, smem, s>>>(P, W); break;
+        default: hs_tp_fill_kernel<3><<<grid, TP_THREADS, smem, s>>>(P, W); break;
     }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;

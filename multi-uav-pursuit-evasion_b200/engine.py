@@ -145,6 +145,72 @@ class HsEngine:
         check(lib.hs_step_post(self._h, tp_pred.data_ptr(), self._stream()), "hs_step_post")
         return self.out
 
+    def tp_weights(self, module) -> Optional["_lib.hs_tp_weights"]:
+        """hs_tp_weights for a TP_net-shaped module (``lstm``: 1-layer LSTM hidden 64, ``fc``:
+        Linear), or None when the module does not have that shape.  Pointers are taken from the
+        live parameters, so in-place optimiser updates are seen by the next tick."""
+        lstm, fc = getattr(module, "lstm", None), getattr(module, "fc", None)
+        if not isinstance(lstm, torch.nn.LSTM) or not isinstance(fc, torch.nn.Linear):
+            return None
+        if lstm.num_layers != 1 or lstm.bidirectional or lstm.hidden_size != 64 or not lstm.batch_first \
+                or lstm.proj_size != 0 or not lstm.bias:
+            return None
+        ps = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, fc.weight, fc.bias]
+        if any(p.dtype != torch.float32 or p.device != self.device or not p.is_contiguous() for p in ps):
+            return None
+        w = _lib.hs_tp_weights()
+        w.weight_ih, w.weight_hh, w.bias_ih, w.bias_hh, w.fc_weight, w.fc_bias = [p.data_ptr() for p in ps]
+        w.input_size, w.hidden_size, w.output_size = lstm.input_size, lstm.hidden_size, fc.out_features
+        if w.input_size != 7 + 3 * self.A or w.output_size != 3 * self.cfg.future_step:
+            return None
+        return w
+
+    def step_post_tp(self, weights: "_lib.hs_tp_weights", pred_out: Optional[torch.Tensor] = None) -> OutputSet:
+        """Second half with the predictor fused into the kernel (no cuDNN call)."""
+        if pred_out is not None:
+            assert pred_out.shape == (self.E, 3 * self.cfg.future_step) and pred_out.is_contiguous()
+            self._keep.append(pred_out)
+        check(lib.hs_step_post_tp(self._h, C.byref(weights), _ptr(pred_out), self._stream()), "hs_step_post_tp")
+        return self.out
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def capture_tick_graphs(self, tp_weights=None, raw: bool = True):
+        """Captures one CUDA graph per output set holding a whole tick (hs_step_pre and, with the
+        predictor, hs_step_post_tp).  Inputs are read from the static buffers ``graph_action``
+        [E,A,4] and ``graph_reset_pid`` [E] uint8; replay with :meth:`replay_tick`.  Must be
+        called after the first reset (the history-initialising first frame is not captured)."""
+        if self.cfg.use_tp_net and tp_weights is None:
+            raise _lib.HsError("capture_tick_graphs: use_tp_net needs tp_weights (fused predictor)")
+        dev = self.device
+        self.graph_action = torch.zeros(self.E, self.A, 4, dtype=torch.float32, device=dev)
+        self.graph_reset_pid = torch.zeros(self.E, dtype=torch.uint8, device=dev)
+        self._graph_weights = tp_weights
+        self._graphs = []
+        self._graph_kernels = 2 if self.cfg.use_tp_net else 1
+        keep = self.cur
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        for i in range(len(self.sets)):
+            self._bind(i)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                st = torch.cuda.current_stream(dev).cuda_stream
+                check(lib.hs_step_pre(self._h, self.graph_action.data_ptr(), 1 if raw else 0,
+                                      self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
+                if self.cfg.use_tp_net:
+                    check(lib.hs_step_post_tp(self._h, C.byref(tp_weights), None, st), "hs_step_post_tp (capture)")
+            self._graphs.append(g)
+        self._bind(keep)
+        self._graph_replays = 0
+        return self
+
+    def replay_tick(self) -> OutputSet:
+        """One tick from ``graph_action`` / ``graph_reset_pid`` with a single graph launch."""
+        self._advance()
+        self._graphs[self.cur].replay()
+        self._graph_replays += 1
+        return self.out
+
     def reset(self, mask: Optional[torch.Tensor], drone_pos, drone_rot, target_pos, cyl_pos) -> OutputSet:
         E, A, Cc = self.E, self.A, self.C
         f = lambda t, shape: t.to(self.device, torch.float32).reshape(shape).contiguous()
@@ -186,7 +252,11 @@ class HsEngine:
 
     @property
     def launches(self) -> int:
-        return int(lib.hs_launch_count(self._h))
+        """Kernels of libhs_b200.so launched so far (graph replays counted per captured kernel)."""
+        n = int(lib.hs_launch_count(self._h))
+        if getattr(self, "_graphs", None):
+            n += (self._graph_replays - len(self._graphs)) * self._graph_kernels   # capture calls counted once each
+        return n
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -127,6 +127,8 @@ class HideAndSeek(IsaacEnv):
         self._curriculum = self.v_prey < 1.3 and not self.VARIANT_ENVGEN
         self.drone = DroneView(self.engine, params, self.num_agents, self.device)
         self.action_is_raw = False      # set by the PIDRateController transform (fused in-kernel)
+        self.fused_predictor = True if self.cfg.env.fused_predictor is None else bool(self.cfg.env.fused_predictor)
+        self.use_cuda_graph = True if self.cfg.env.cuda_graph is None else bool(self.cfg.env.cuda_graph)
         self._active_fixed = float(len(_LAYOUTS.get(self.scenario_flag, [])))
 
         frame = 7 + 3 * self.num_agents
@@ -258,7 +260,15 @@ class HideAndSeek(IsaacEnv):
         return TensorDict({"agents": agents, "stats": self.stats, "info": self.info}, [E], dev)
 
     def _predict(self, out):
-        if self.use_TP_net:
+        """Second half of the tick.  A TP_net-shaped predictor is evaluated inside the fused
+        kernel from its live parameters; any other module goes through torch and hs_step_post
+        (same arithmetic downstream, the module's own forward upstream)."""
+        if not self.use_TP_net:
+            return
+        w = self.engine.tp_weights(self.TP) if self.fused_predictor else None
+        if w is not None:
+            self.engine.step_post_tp(w)
+        else:
             with torch.no_grad():
                 pred = self.TP(out["tp_input"])
             self.engine.step_post(pred)
@@ -285,12 +295,39 @@ class HideAndSeek(IsaacEnv):
         td.set("truncated", out["truncated"])
         return td
 
+    def _graph_ready(self) -> bool:
+        """(Re)captures the per-tick CUDA graphs when the fast path applies: raw actions through
+        the fused PID, and either no predictor or a TP_net-shaped one whose parameters still
+        live where they did at capture time."""
+        if not (self.use_cuda_graph and self.action_is_raw):
+            return False
+        eng = self.engine
+        w = None
+        if self.use_TP_net:
+            w = eng.tp_weights(self.TP) if self.fused_predictor else None
+            if w is None:
+                return False
+        key = None if w is None else (w.weight_ih, w.weight_hh, w.bias_ih, w.bias_hh, w.fc_weight, w.fc_bias)
+        if getattr(self, "_graph_key", ...) != key or not getattr(eng, "_graphs", None):
+            eng.capture_tick_graphs(w, raw=True)
+            self._graph_key = key
+        return True
+
     def _step(self, tensordict: TensorDict) -> TensorDict:
         action = tensordict.get(("agents", "action"))
         eng = self.engine
         if self.action_is_raw:
             done_prev = tensordict.get("done", None)
-            out = eng.step_pre(action.contiguous(), raw=True, reset_pid=done_prev)
+            if self._graph_ready():
+                eng.graph_action.copy_(action.reshape(eng.graph_action.shape))
+                if done_prev is None:
+                    eng.graph_reset_pid.zero_()
+                else:
+                    eng.graph_reset_pid.copy_(done_prev.reshape(-1))
+                out = eng.replay_tick()
+            else:
+                out = eng.step_pre(action.contiguous(), raw=True, reset_pid=done_prev)
+                self._predict(out)
             # keys the reference's transform writes on the input tensordict (transforms.py:441-458)
             tensordict.set(("stats", "action_error_order1"), out["action_error"])
             tensordict.set(("info", "prev_action"), eng.prev_action)
@@ -303,7 +340,7 @@ class HideAndSeek(IsaacEnv):
                 ae = torch.zeros(self.num_envs, self.num_agents, device=self.device)
             eng.sets[(eng.cur + 1) % len(eng.sets)]["action_error"].copy_(ae)
             out = eng.step_pre(action.contiguous(), raw=False, reset_pid=None)
-        self._predict(out)
+            self._predict(out)
         nxt = self._obs_td(out)
         nxt.set(("agents", "reward"), out["reward"])
         nxt.set("done", out["done"])

@@ -166,3 +166,73 @@ def test_partial_reset_keeps_other_envs():
     assert_close("prev_action", eng.prev_action, orc.prev_action)
     assert_close("throttle", st["throttle"], orc.throttle)
     eng.close()
+
+
+@pytest.mark.parametrize("A,E", [(3, 200), (3, 32), (2, 45), (1, 64)])
+def test_fused_predictor_matches_torch_lstm(A, E):
+    """hs_step_post_tp (LSTM+FC+tanh+rows in one kernel, fp32 FFMA) against torch's CPU LSTM
+    and against the two-kernel path fed with the same prediction."""
+    import mupe_b200
+    P = O.HSParams(num_agents=A)
+    dev = torch.device("cuda:0")
+    eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    orc = O.HideAndSeekOracle(P, E)
+    torch.manual_seed(A)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step)
+    with torch.no_grad():                       # non-trivial weights
+        for p_ in tp.parameters():
+            p_.mul_(3.0)
+    tp_gpu = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    tp_gpu.load_state_dict(tp.state_dict())
+    tp_fn = lambda x: tp(x).detach()
+    g = torch.Generator().manual_seed(7)
+    init = O.sample_reset(P, E, g)
+    mask = torch.ones(E, dtype=torch.bool)
+    orc.reset(mask, init, tp_fn)
+    eng.reset(mask.to(dev), init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    w = eng.tp_weights(tp_gpu)
+    assert w is not None
+    done_prev = torch.zeros(E, dtype=torch.bool)
+    for t in range(12):                          # > history_step so that the window is full of distinct frames
+        act = torch.randn(E, A, 4, generator=g)
+        push_state(eng, orc)
+        want = orc.step(act, done_prev, tp_fn)
+        eng.step_pre(act.to(dev), True, None)
+        pred = torch.empty(E, 3 * P.future_step, device=dev)
+        got = eng.step_post_tp(w, pred)
+        FLIP_TP = 0.02      # a flipped evader-velocity sign in one frame changes that env's whole prediction
+        # the predictor itself: against torch's LSTM evaluated on the very same input window
+        assert_close(f"t{t}/pred", pred, tp_fn(got["tp_input"].cpu()), rtol=1e-4, atol=2e-6)
+        assert_close(f"t{t}/pred-vs-oracle", pred, want["tp_pred"], rtol=1e-4, atol=2e-6, max_bad_frac=0.02)
+        assert_close(f"t{t}/state_self", got["state_self"], want["state_self"], max_bad_frac=FLIP_TP)
+        assert_close(f"t{t}/state_drones", got["state_drones"], want["state_drones"], max_bad_frac=FLIP_TP)
+    eng.close()
+
+
+def test_cuda_graph_replay_equals_direct_launches():
+    import mupe_b200
+    P, E = O.HSParams(), 256
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(1)
+    init = O.sample_reset(P, E, g)
+    engs = [mupe_b200.HsEngine(cfg, dev) for _ in range(2)]
+    for e in engs:
+        e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        e.step_post_tp(e.tp_weights(tp))
+    engs[1].capture_tick_graphs(engs[1].tp_weights(tp), raw=True)
+    n0 = engs[1].launches
+    for t in range(7):
+        act = torch.randn(E, 3, 4, generator=g).to(dev)
+        a = engs[0].step_pre(act, True, None)
+        engs[0].step_post_tp(engs[0].tp_weights(tp))
+        engs[1].graph_action.copy_(act)
+        b = engs[1].replay_tick()
+        for k in ("state_self", "state_drones", "obs_cylinders", "tp_input", "reward", "drone_state"):
+            assert torch.equal(a[k], b[k]), (t, k)
+    assert torch.equal(engs[0].stats, engs[1].stats)
+    assert engs[1].launches - n0 == 14
+    for e in engs:
+        e.close()
