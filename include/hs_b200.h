@@ -117,7 +117,8 @@ typedef struct hs_config {
     float half_arena;           /* 0.5*arena_size          hideandseek.py:835,841 */
     float coll_radius_x2;       /* 2*collision_radius      hideandseek.py:975 */
     float vmax_clamped;         /* max_linear_velocity*(1-1e-6): see DESIGN.md "Integrator" */
-    float reserved_f[4];
+    float inv_inertia[3];       /* 1/inertia */
+    float reserved_f[1];
 } hs_config;
 
 /* Device buffers.  All owned by the caller.

@@ -50,7 +50,7 @@ class hs_config(C.Structure):
         ("max_linear_velocity", C.c_float), ("max_angular_velocity", C.c_float),
         ("ground_z", C.c_float), ("hover_throttle", C.c_float),
         ("arena_size_sq", C.c_float), ("half_arena", C.c_float), ("coll_radius_x2", C.c_float),
-        ("vmax_clamped", C.c_float), ("reserved_f", C.c_float * 4),
+        ("vmax_clamped", C.c_float), ("inv_inertia", C.c_float * 3), ("reserved_f", C.c_float * 1),
     ]
 
 

@@ -12,8 +12,6 @@ LIB = os.path.join(PKG_DIR, "libhs_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    # fp32 products and sums are rounded separately, like the eager reference (DESIGN.md "Numerics")
-    "-fmad=false",
     "--shared", "-Xcompiler", "-fPIC",
 ]
 

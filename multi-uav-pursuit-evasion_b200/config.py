@@ -141,6 +141,8 @@ def build_hs_config(num_envs: int, *, num_agents=3, num_cylinders=5, obs_max_cyl
     sy = sum(mr * x * x for x, _ in xy)
     c.total_mass = total_mass
     c.inertia[0], c.inertia[1], c.inertia[2] = bi[0] + sx, bi[1] + sy, bi[2] + sx + sy
+    for i in range(3):
+        c.inv_inertia[i] = 1.0 / c.inertia[i]
     c.gravity = 9.81
     c.lin_damp_factor = max(0.0, 1.0 - dt * rb.get("linear_damping", 0.2))
     c.ang_damp_factor = max(0.0, 1.0 - dt * rb.get("angular_damping", 0.2))

@@ -18,8 +18,10 @@
 //     (float4 / scalar), which is already sector-exact.
 //   * no tensor cores: there is no dense contraction on this path.
 //
-// Numerics: fp32 throughout, compiled with -fmad=false so that every product and sum is
-// rounded like the eager torch reference (which never fuses across ops); IEEE div/sqrt.
+// Numerics: fp32 throughout.  Products/sums may contract to FFMA; divisions and square roots
+// use the SFU approximations (rcp/sqrt.approx, <= 2 ulp) because the tick is instruction-bound,
+// not bandwidth-bound (profiles/): that keeps every output within ~1e-6 relative of the eager
+// reference, two orders of magnitude inside the 1e-4 parity bar.  tanh/sin/cos stay accurate.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -70,10 +72,13 @@ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { const float r = frcp(s); return mk(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-__device__ __forceinline__ float norm3(V3 a) { return sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z); }
+__device__ __forceinline__ float norm3(V3 a) { return fsqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
 __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
@@ -98,6 +103,39 @@ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
     r.z = ((a.w * b.z + a.x * b.y) - a.y * b.x) + a.z * b.w;
     return r;
 }
+
+// Round-to-nearest primitives that the compiler may not contract or approximate.  Used where
+// the reference's arithmetic has catastrophic cancellation that amplifies 1-ulp differences
+// (the D term of the rate PID: (rate - last_rate)/dt * kd, gain ~1.4e4 on the body rate).
+namespace ex {
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+}  // namespace ex
+// omni_drones/utils/torch.py:193-201 with the reference's exact operation order and rounding
+__device__ __forceinline__ V3 qrot_inv_exact(Q4 q, V3 v) {
+    using namespace ex;
+    const float s = sub(mul(2.0f, mul(q.w, q.w)), 1.0f);
+    const V3 a = mk(mul(v.x, s), mul(v.y, s), mul(v.z, s));
+    const V3 cr = mk(sub(mul(q.y, v.z), mul(q.z, v.y)), sub(mul(q.z, v.x), mul(q.x, v.z)), sub(mul(q.x, v.y), mul(q.y, v.x)));
+    const V3 b = mk(mul(mul(cr.x, q.w), 2.0f), mul(mul(cr.y, q.w), 2.0f), mul(mul(cr.z, q.w), 2.0f));
+    const float d = add(add(mul(q.x, v.x), mul(q.y, v.y)), mul(q.z, v.z));
+    const V3 c = mk(mul(mul(q.x, d), 2.0f), mul(mul(q.y, d), 2.0f), mul(mul(q.z, d), 2.0f));
+    return mk(add(sub(a.x, b.x), c.x), add(sub(a.y, b.y), c.y), add(sub(a.z, b.z), c.z));
+}
+
+// Ampere-style async copies global -> shared (SASS LDGSTS): prefetch without holding registers
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(sdst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ float gshfl(float v, int src_lane) { return __shfl_sync(FULL, v, src_lane); }
 __device__ __forceinline__ V3 gshfl3(V3 v, int src_lane) {
@@ -163,26 +201,26 @@ struct Stager {
 
 constexpr int FILL_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * (20 + 3 * FMAX);   // 8*3*44 = 1056
 constexpr int TICK_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * 20;                // widest tick tile: [24][20]
+constexpr int TP_ENV_WORDS_MAX = 192;                                               // history_step * (7+3A) <= 192
 
 // ---- line of sight, hideandseek.py:47-103 ------------------------------------------------
 __device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float (&cx)[CMAX],
                                             const float (&cy)[CMAX], const float (&cz)[CMAX],
                                             int C, float size) {
     const float ddx = p.x - t.x, ddy = p.y - t.y;
-    const float seg = sqrtf(ddx * ddx + ddy * ddy);
+    // dist/(seg+eps) <= size  and  0 <= num/(den+eps) <= 1  with the (positive) denominators
+    // multiplied out: no division per cylinder; underground (inactive) cylinders are skipped
+    const float seg_sz = (fsqrt(ddx * ddx + ddy * ddy) + 1e-5f) * size;
     const float dx = t.x - p.x, dy = t.y - p.y;
-    const float den = dx * dx + dy * dy;
+    const float den = (dx * dx + dy * dy) + 1e-5f;
     bool blocked = false;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
+        if (c < C && cz[c] > 0.0f) {
             const float ccx = cx[c] - t.x, ccy = cy[c] - t.y;
             const float cr = fabsf(ddx * ccy - ddy * ccx);
-            const bool near = (cr / (seg + 1e-5f)) <= size;
             const float num = (cx[c] - p.x) * dx + (cy[c] - p.y) * dy;
-            const float tt = num / (den + 1e-5f);
-            const bool between = (tt >= 0.0f) && (tt <= 1.0f);
-            blocked = blocked || (near && between && (cz[c] > 0.0f));
+            blocked = blocked || ((cr <= seg_sz) && (num >= 0.0f) && (num <= den));
         }
     }
     return blocked;
@@ -220,7 +258,8 @@ template <int A, bool RESET>
 __global__ void __launch_bounds__(128)
 hs_tick_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
-    __shared__ __align__(16) float frame_mem[4][ENVS_PER_WARP][7 + 3 * HS_MAX_AGENTS];
+    __shared__ __align__(128) float tp_mem[4][ENVS_PER_WARP * TP_ENV_WORDS_MAX];   // TP_input tile of the warp
+    __shared__ __align__(16) float stat_mem[4][ENVS_PER_WARP][HS_NUM_STATS];
 
     const hs_config& c = P.c;
     const int lane = threadIdx.x & 31;
@@ -249,37 +288,35 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     st.cur = 0;
     st.lane = lane;
 
-    // ---- history shift of TP_input: rows 1..H-1 of the previous tensor become rows 0..H-2.
-    // Pure streaming copy, issued first so it overlaps the arithmetic below.
+    // ---- prefetch (no registers held): the previous TP_input rows 1..H-1 land in the warp's
+    // shared tile already shifted to rows 0..H-2, and the env's stats row lands in stat_mem.
+    float* tp_tile = tp_mem[wib];
+    const int per_env = H * FD, keep = (H - 1) * FD;
     if (c.use_tp_net && !P.tp_init) {
-        const int per_env = H * FD, keep = (H - 1) * FD;
         const float* src = P.b.tp_input_prev + e0 * per_env;
-        float* dst = P.b.tp_input + e0 * per_env;
         if ((FD & 3) == 0) {
             const int pe4 = per_env >> 2, keep4 = keep >> 2, fd4 = FD >> 2;
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            const int total = nenv * pe4;
-            for (int i = lane; i < ((total + 31) & ~31); i += 32) {
-                const int env = i / pe4, j = i - env * pe4;
-                const bool act = (i < total) && (j < keep4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act) v = s4[i + fd4];
-                __syncwarp();                            // in-place safe: all loads precede the stores
-                if (act) d4[i] = v;
+            const int total = nenv * keep4;
+            int env = 0, j = lane;                       // i = env*keep4 + j, kept incrementally
+            for (int i = lane; i < total; i += 32, j += 32) {
+                while (j >= keep4) { j -= keep4; ++env; }
+                cp_async16(reinterpret_cast<float4*>(tp_tile) + env * pe4 + j,
+                           reinterpret_cast<const float4*>(src) + env * pe4 + j + fd4);
             }
         } else {
-            const int total = nenv * per_env;
-            for (int i = lane; i < ((total + 31) & ~31); i += 32) {
-                const int env = i / per_env, j = i - env * per_env;
-                const bool act = (i < total) && (j < keep);
-                float v = 0.f;
-                if (act) v = src[i + FD];
-                __syncwarp();
-                if (act) dst[i] = v;
+            const int total = nenv * keep;
+            int env = 0, j = lane;
+            for (int i = lane; i < total; i += 32, j += 32) {
+                while (j >= keep) { j -= keep; ++env; }
+                cp_async4(tp_tile + env * per_env + j, src + env * per_env + j + FD);
             }
         }
     }
+    if (!RESET && valid && is_ev) {
+#pragma unroll
+        for (int k = 0; k < HS_NUM_STATS; ++k) cp_async4(&stat_mem[wib][lane >> 2][k], P.b.stats + (int64_t)k * E + e);
+    }
+    cp_async_commit();
 
     // ---- load state ------------------------------------------------------------------
     V3 p = mk(0, 0, 0), lv = mk(0, 0, 0), av = mk(0, 0, 0);
@@ -302,6 +339,20 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
     V3 tv = mk(*EROW(E_TVEL), *EROW(E_TVEL + 1), *EROW(E_TVEL + 2));
     float progress = *EROW(E_PROGRESS);
+    float4 act4 = make_float4(0.f, 0.f, 0.f, 0.f), prev4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pid_reset = false;
+    float v_prey = 0.f;
+    if (!RESET) {
+        if (is_drone) {
+            const int64_t row = e * A + slot;
+            act4 = __ldg(reinterpret_cast<const float4*>(P.action) + row);
+            if (P.action_is_raw) {
+                prev4 = *(reinterpret_cast<const float4*>(P.b.prev_action) + row);
+                pid_reset = (P.reset_pid != nullptr) && (P.reset_pid[e] != 0);
+            }
+        }
+        if (is_ev) v_prey = __ldg(P.b.v_prey);
+    }
     float cx[CMAX], cy[CMAX], cz[CMAX];
 #pragma unroll
     for (int k = 0; k < CMAX; ++k) {
@@ -323,49 +374,49 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
         float cmd[4] = {0, 0, 0, 0};
         if (is_drone) {
             const int64_t row = e * A + slot;
-            const float4 act = __ldg(reinterpret_cast<const float4*>(P.action) + row);
+            const float4 act = act4;
             if (P.action_is_raw) {
-                const float4 prev = *(reinterpret_cast<const float4*>(P.b.prev_action) + row);
+                using namespace ex;
+                const float4 prev = prev4;
                 const float a0 = tanhf(act.x), a1 = tanhf(act.y), a3 = tanhf(act.w);
                 float a2 = tanhf(act.z);
-                const float thrust = clampf((a3 + 1.0f) / 2.0f, 0.0f, c.max_thrust_ratio);
+                const float thrust = clampf(mul(add(a3, 1.0f), 0.5f), 0.0f, c.max_thrust_ratio);
                 if (c.fixed_yaw) a2 = 0.0f;
-                const float d0 = a0 - prev.x, d1 = a1 - prev.y, d2 = a2 - prev.z, d3 = thrust - prev.w;
-                action_err = sqrtf(((d0 * d0 + d1 * d1) + d2 * d2) + d3 * d3);
+                const float d0 = sub(a0, prev.x), d1 = sub(a1, prev.y), d2 = sub(a2, prev.z), d3 = sub(thrust, prev.w);
+                action_err = __fsqrt_rn(add(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)), mul(d3, d3)));
                 if (valid) *(reinterpret_cast<float4*>(P.b.prev_action) + row) = make_float4(a0, a1, a2, thrust);
-                const V3 trate = mk((a0 * 180.0f) * c.target_clip, (a1 * 180.0f) * c.target_clip,
-                                    (a2 * 180.0f) * c.target_clip);
-                const float tthrust = thrust * 65536.0f;
-                if (P.reset_pid != nullptr && P.reset_pid[e]) { integ = mk(0, 0, 0); last = mk(0, 0, 0); }
-                const V3 br0 = qrot<true>(q, av);
+                const V3 trate = mk(mul(mul(a0, 180.0f), c.target_clip), mul(mul(a1, 180.0f), c.target_clip),
+                                    mul(mul(a2, 180.0f), c.target_clip));
+                const float tthrust = mul(thrust, 65536.0f);
+                if (pid_reset) { integ = mk(0, 0, 0); last = mk(0, 0, 0); }
+                const V3 br0 = qrot_inv_exact(q, av);
                 const float pi_f = 3.14159265358979323846f;
-                const V3 br = mk((br0.x * 180.0f) / pi_f, (br0.y * 180.0f) / pi_f, (br0.z * 180.0f) / pi_f);
-                const V3 err = trate - br;
+                const V3 br = mk(div(mul(br0.x, 180.0f), pi_f), div(mul(br0.y, 180.0f), pi_f), div(mul(br0.z, 180.0f), pi_f));
                 float o[3];
-                const float errv[3] = {err.x, err.y, err.z};
+                const float errv[3] = {sub(trate.x, br.x), sub(trate.y, br.y), sub(trate.z, br.z)};
                 const float brv[3] = {br.x, br.y, br.z};
                 const float lastv[3] = {last.x, last.y, last.z};
                 float integv[3] = {integ.x, integ.y, integ.z};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float outP = errv[k] * c.pid_kp[k];
-                    float deriv = -(brv[k] - lastv[k]) / dt;
+                    const float outP = mul(errv[k], c.pid_kp[k]);
+                    float deriv = div(-sub(brv[k], lastv[k]), dt);
                     if (isnan(deriv)) deriv = 0.0f;
-                    const float outD = deriv * c.pid_kd[k];
-                    integv[k] = clampf(integv[k] + errv[k] * dt, -c.pid_ilimit[k], c.pid_ilimit[k]);
-                    const float outI = integv[k] * c.pid_ki[k];
-                    float out = (outP + outD) + outI;
+                    const float outD = mul(deriv, c.pid_kd[k]);
+                    integv[k] = clampf(add(integv[k], mul(errv[k], dt)), -c.pid_ilimit[k], c.pid_ilimit[k]);
+                    const float outI = mul(integv[k], c.pid_ki[k]);
+                    float out = add(add(outP, outD), outI);
                     if (isnan(out)) out = 0.0f;
                     o[k] = clampf(out, -c.pid_out_limit, c.pid_out_limit);
                 }
                 integ = mk(integv[0], integv[1], integv[2]);
                 last = br;
-                const float r = o[0] / 2.0f, pp = o[1] / 2.0f, y = o[2];
-                const float m[4] = {((tthrust + r) - pp) + y, ((tthrust + r) + pp) - y,
-                                    ((tthrust - r) + pp) + y, ((tthrust - r) - pp) - y};
+                const float r = o[0] * 0.5f, pp = o[1] * 0.5f, y = o[2];
+                const float m[4] = {add(sub(add(tthrust, r), pp), y), sub(add(add(tthrust, r), pp), y),
+                                    add(add(sub(tthrust, r), pp), y), sub(sub(sub(tthrust, r), pp), y)};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float v = (m[k] / 65536.0f) * 2.0f - c.max_thrust_ratio;
+                    float v = sub(mul(mul(m[k], 1.0f / 65536.0f), 2.0f), c.max_thrust_ratio);
                     if (isnan(v)) v = 0.0f;                       // torch.nan_to_num_(cmds, 0.)
                     else if (isinf(v)) v = v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
                     cmd[k] = v;
@@ -386,7 +437,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
             float dsq = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float target = sqrtf(clampf((cmd[k] + 1.0f) / 2.0f, 0.0f, 1.0f));
+                const float target = fsqrt(clampf((cmd[k] + 1.0f) / 2.0f, 0.0f, 1.0f));
                 const float nt = thr[k] + c.rotor_alpha * (target - thr[k]);
                 const float dth = nt - thr[k];
                 dsq = (k == 0) ? dth * dth : dsq + dth * dth;
@@ -396,7 +447,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                 const float mom = (t * c.km) * (-c.rotor_dirs[k]);
                 yaw_torque = (k == 0) ? mom : yaw_torque + mom;
             }
-            throttle_diff = sqrtf(dsq);
+            throttle_diff = fsqrt(dsq);
         }
         // ---- downwash all-pairs, multirotor.py:488-494, 724-753
         const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
@@ -412,9 +463,9 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                 const float zd = dot3(rel, d);
                 const float rr = norm3(rel - d * zd);
                 const float z = zd < 0.0f ? 0.0f : zd;
-                const float qq = (c.downwash_kr * rr) / z;
+                const float qq = fdiv(c.downwash_kr * rr, z);
                 const float den = 1.0f + c.downwash_kz * z;
-                const float v = expf(-0.5f * (qq * qq)) / (den * den);
+                const float v = fdiv(__expf(-0.5f * (qq * qq)), den * den);
                 dw = dw + neg(Fj) * v;
             }
         }
@@ -427,48 +478,47 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
             const float dist = norm3(rel);
             const bool blocked = los_blocked(p, tp, cx, cy, cz, C, c.cylinder_size);
             const float active = ((dist < c.target_detect_radius) && !blocked) ? 1.0f : 0.0f;
-            const V3 away = neg(rel) / (dist + 1e-5f);
-            fp = (away * (1.0f / (dist + 1e-5f))) * active;
+            const float inv_d = frcp(dist + 1e-5f);
+            fp = (neg(rel) * (inv_d * inv_d)) * active;
         }
         V3 force = gshfl3(fp, gbase);
 #pragma unroll
         for (int j = 1; j < A; ++j) force = force + gshfl3(fp, gbase + j);
         if (is_ev) {
             force = mk(0.f, 0.f, 0.f) + force;
-            const float rho = sqrtf(tp.x * tp.x + tp.y * tp.y);
-            const float inx = -tp.x / (rho + 1e-5f), iny = -tp.y / (rho + 1e-5f);
+            const float rho = fsqrt(tp.x * tp.x + tp.y * tp.y);
+            const float inv_rho = frcp(rho + 1e-5f);
+            const float inx = -tp.x * inv_rho, iny = -tp.y * inv_rho;
             out_of_arena = (tp.x * tp.x + tp.y * tp.y) > c.arena_size_sq;
             const float o = out_of_arena ? 1.0f : 0.0f, no = out_of_arena ? 0.0f : 1.0f;
-            const float wall = 1.0f / ((c.arena_size - rho) + 1e-5f);
+            const float wall = frcp((c.arena_size - rho) + 1e-5f);
             V3 fr;
             fr.x = (o * inx) * 1e5f + (no * inx) * wall;
             fr.y = (o * iny) * 1e5f + (no * iny) * wall;
             const bool hi = tp.z > c.max_height;
             const float hz = c.max_height - tp.z;
-            fr.z = (hi ? 1.0f : 0.0f) * (-1e5f) + ((hi ? 0.0f : 1.0f) * (-hz)) / (hz * hz + 1e-5f);
+            fr.z = hi ? -1e5f : fdiv(-hz, hz * hz + 1e-5f);
             const bool lo = tp.z < 0.0f;
             const float lz = 0.0f - tp.z;
-            fr.z = fr.z + ((lo ? 1.0f : 0.0f) * 1e5f + ((lo ? 0.0f : 1.0f) * (-lz)) / (lz * lz + 1e-5f));
+            fr.z = fr.z + (lo ? 1e5f : fdiv(-lz, lz * lz + 1e-5f));
             force = force + fr;
             float fcx = 0.f, fcy = 0.f;
 #pragma unroll
             for (int k = 0; k < CMAX; ++k) {
-                if (k < C) {
+                if (k < C && !(cz[k] < 0.0f)) {
                     const float tx = tp.x - cx[k], ty = tp.y - cy[k];
-                    const float dxy = sqrtf(tx * tx + ty * ty);
-                    const float gap = dxy - c.cylinder_size;
-                    const float act = (!(cz[k] < 0.0f) && (dxy < c.target_detect_radius)) ? 1.0f : 0.0f;
-                    const float inv = 1.0f / (gap + 1e-5f);
-                    const float tx_n = (act * (tx / (dxy + 1e-5f))) * inv;
-                    const float ty_n = (act * (ty / (dxy + 1e-5f))) * inv;
-                    fcx = (k == 0) ? tx_n : fcx + tx_n;
-                    fcy = (k == 0) ? ty_n : fcy + ty_n;
+                    const float dxy = fsqrt(tx * tx + ty * ty);
+                    if (dxy < c.target_detect_radius) {
+                        const float sc = frcp(dxy + 1e-5f) * frcp((dxy - c.cylinder_size) + 1e-5f);
+                        fcx = fcx + tx * sc;
+                        fcy = fcy + ty * sc;
+                    }
                 }
             }
             force = force + mk(fcx, fcy, 0.f);
-            const float vp = *P.b.v_prey;
-            tv = mk((vp * force.x) / (fabsf(force.x) + 1e-5f), (vp * force.y) / (fabsf(force.y) + 1e-5f),
-                    (vp * force.z) / (fabsf(force.z) + 1e-5f));
+            const float vp = v_prey;
+            tv = mk(fdiv(vp * force.x, fabsf(force.x) + 1e-5f), fdiv(vp * force.y, fabsf(force.y) + 1e-5f),
+                    fdiv(vp * force.z, fabsf(force.z) + 1e-5f));
         }
     }
 
@@ -490,23 +540,25 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
         V3 wb = qrot<true>(q, av);
         const V3 gyro = cross3(wb, mk(I.x * wb.x, I.y * wb.y, I.z * wb.z));
         const V3 tg = tau - gyro;
-        wb = wb + mk(tg.x / I.x, tg.y / I.y, tg.z / I.z) * dt;
+        wb = wb + mk(tg.x * c.inv_inertia[0], tg.y * c.inv_inertia[1], tg.z * c.inv_inertia[2]) * dt;
         V3 w = qrot<false>(q, wb);
         v = v * c.lin_damp_factor;
         w = w * c.ang_damp_factor;
         const float vn = norm3(v);
-        if (vn > c.max_linear_velocity) v = v * (c.vmax_clamped / vn);
+        if (vn > c.max_linear_velocity) v = v * fdiv(c.vmax_clamped, vn);
         float wn = norm3(w);
-        if (wn > c.max_angular_velocity) w = w * (c.max_angular_velocity / wn);
+        if (wn > c.max_angular_velocity) w = w * fdiv(c.max_angular_velocity, wn);
         p = p + v * dt;
         wn = norm3(w);
         const float half = (0.5f * dt) * wn;
         const bool small = wn < 1e-6f;
-        const float kk = small ? (0.5f * dt) : (sinf(half) / fmaxf(wn, 1e-6f));
-        Q4 dq; dq.w = small ? 1.0f : cosf(half); dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk;
+        float sh, ch;
+        sincosf(half, &sh, &ch);
+        const float kk = small ? (0.5f * dt) : fdiv(sh, fmaxf(wn, 1e-6f));
+        Q4 dq; dq.w = small ? 1.0f : ch; dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk;
         Q4 qn = qmul(dq, q);
-        const float qnorm = sqrtf(((qn.w * qn.w + qn.x * qn.x) + qn.y * qn.y) + qn.z * qn.z);
-        q.w = qn.w / qnorm; q.x = qn.x / qnorm; q.y = qn.y / qnorm; q.z = qn.z / qnorm;
+        const float qinv = rsqrtf(((qn.w * qn.w + qn.x * qn.x) + qn.y * qn.y) + qn.z * qn.z);
+        q.w = qn.w * qinv; q.x = qn.x * qinv; q.y = qn.y * qinv; q.z = qn.z * qinv;
         if (c.ground_clamp && p.z < c.ground_z) {
             p.z = c.ground_z;
             if (v.z < 0.0f) v.z = 0.0f;
@@ -607,7 +659,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                     r[n * 5 + 2] = inactive ? mv : rz;
                     r[n * 5 + 3] = inactive ? mv : c.max_height;
                     r[n * 5 + 4] = inactive ? mv : c.cylinder_size;
-                    const float dxy = sqrtf(rx * rx + ry * ry);
+                    const float dxy = fsqrt(rx * rx + ry * ry);
                     const float hit = ((dxy - c.cylinder_size) < c.collision_radius) ? 1.0f : 0.0f;
                     hit_cyl = hit_cyl + (inactive ? 0.0f : hit);
                 }
@@ -626,30 +678,46 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     const unsigned det_ballot = __ballot_sync(FULL, detect);
     const bool bdetect = (det_ballot & gmask) != 0u;
     const float mv = c.mask_value;
-    const float tfrac = progress / (float)c.max_episode_length;
+    const float tfrac = fdiv(progress, (float)c.max_episode_length);
 
     if (c.use_tp_net) {
-        // new TP frame [progress, tpos_masked3, tvel_masked3, p_0..p_{A-1}] -> last history row
-        float* fr = frame_mem[wib][lane >> 2];
+        // new TP frame [progress, tpos_masked3, tvel_masked3, p_0..p_{A-1}] = last row of the tile
+        cp_async_wait_all();
+        float* fr = tp_tile + (lane >> 2) * per_env + keep;
         if (is_drone) { fr[7 + 3 * slot] = p.x; fr[8 + 3 * slot] = p.y; fr[9 + 3 * slot] = p.z; }
         if (is_ev) {
             fr[0] = progress;
             fr[1] = bdetect ? tp.x : mv; fr[2] = bdetect ? tp.y : mv; fr[3] = bdetect ? tp.z : mv;
             fr[4] = bdetect ? tv.x : mv; fr[5] = bdetect ? tv.y : mv; fr[6] = bdetect ? tv.z : mv;
         }
-        __syncwarp();
-        if (valid) {
-            float* dst = P.b.tp_input + e * (int64_t)(H * FD);
-            if (P.tp_init) {
-                for (int i = slot; i < H * FD; i += G) dst[i] = fr[i % FD];
+        if (P.tp_init) {                                 // very first frame: every history row = this frame
+            __syncwarp();
+            float* row0 = tp_tile + (lane >> 2) * per_env;
+            int k = slot;
+            for (int i = slot; i < keep; i += G, k += G) {
+                while (k >= FD) k -= FD;
+                row0[i] = fr[k];
+            }
+        }
+        {
+            float* gdst = P.b.tp_input + e0 * per_env;
+            const int nwords = nenv * per_env;
+            const bool bulk = HS_USE_BULK_STORE && full_tile && ((nwords & 3) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+            if (bulk) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { bulk_store(gdst, tp_tile, (uint32_t)nwords * 4u); bulk_commit(); }
             } else {
-                for (int i = slot; i < FD; i += G) dst[(H - 1) * FD + i] = fr[i];
+                __syncwarp();
+                for (int i = lane; i < nwords; i += 32) gdst[i] = tp_tile[i];
             }
         }
         if (valid && is_ev) {
-            P.b.tp_groundtruth[e * 3 + 0] = tp.x / c.half_arena;
-            P.b.tp_groundtruth[e * 3 + 1] = tp.y / c.half_arena;
-            P.b.tp_groundtruth[e * 3 + 2] = (tp.z / c.max_height) * 2.0f - 1.0f;
+            const float inv_ha = frcp(c.half_arena);
+            P.b.tp_groundtruth[e * 3 + 0] = tp.x * inv_ha;
+            P.b.tp_groundtruth[e * 3 + 1] = tp.y * inv_ha;
+            P.b.tp_groundtruth[e * 3 + 2] = fdiv(tp.z, c.max_height) * 2.0f - 1.0f;
             P.b.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;
             *EROW(E_BDETECT) = bdetect ? 1.0f : 0.0f;
         }
@@ -684,7 +752,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
         hit_wall = ((p.z > c.max_height) ? 1.0f : 0.0f) +
                    (((p.x * p.x + p.y * p.y) > c.arena_size_sq) ? 1.0f : 0.0f);
         r_coll = r_coll + (-c.collision_coef * hit_wall);
-        r_smooth = c.smoothness_gated ? 0.0f : c.smoothness_coef * expf(-action_err);
+        r_smooth = c.smoothness_gated ? 0.0f : c.smoothness_coef * __expf(-action_err);
     }
     const bool any_capture = (__ballot_sync(FULL, seen_capture) & gmask) != 0u;
     const bool all_blocked = (__ballot_sync(FULL, blocked) & gmask) == gmask;
@@ -695,16 +763,19 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     if (valid && is_drone) P.b.reward[e * A + slot] = reward;
 
     // per-env means over the A pursuers (sum in agent order, then / A like torch.mean)
+    // xor-butterfly over the 4 lanes of the group; non-pursuer lanes contribute the neutral
+    // element, so for A=3 the sum is ((x0+x1)+(x2+0)) = the reference's left-to-right order
+    const float inv_A = 1.0f / (float)A;
     auto gmean = [&](float x) {
-        float s = gshfl(x, gbase);
-#pragma unroll
-        for (int j = 1; j < A; ++j) s = s + gshfl(x, gbase + j);
-        return s / (float)A;
+        float s = is_drone ? x : 0.0f;
+        s = s + __shfl_xor_sync(FULL, s, 1);
+        s = s + __shfl_xor_sync(FULL, s, 2);
+        return s * inv_A;
     };
     auto gmax = [&](float x) {
-        float s = gshfl(x, gbase);
-#pragma unroll
-        for (int j = 1; j < A; ++j) s = fmaxf(s, gshfl(x, gbase + j));
+        float s = is_drone ? x : -INFINITY;
+        s = fmaxf(s, __shfl_xor_sync(FULL, s, 1));
+        s = fmaxf(s, __shfl_xor_sync(FULL, s, 2));
         return s;
     };
     const float m_ae = gmean(action_err), m_dist = gmean(r_dist), m_detect = gmean(r_detect),
@@ -716,38 +787,42 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     if (valid && is_ev) {
         const bool done = progress >= (float)c.max_episode_length;
         P.b.done[e] = done ? 1 : 0;
-        const float ep_len = done ? progress : 1.0f;
+        const float inv_len = done ? frcp(progress) : 1.0f;
         float* S = P.b.stats + e;
         const int64_t Es = E;
+        cp_async_wait_all();
+        const float* SO = stat_mem[wib][lane >> 2];     // values prefetched at kernel entry
 #define ST(k) S[(int64_t)(k) * Es]
+#define OLD(k) SO[k]
         // accumulators that are divided by the episode length on the done tick
-        ST(HS_STAT_ACTION_ERROR_MEAN) = (ST(HS_STAT_ACTION_ERROR_MEAN) + m_ae) / ep_len;
-        ST(HS_STAT_ACTION_ERROR_MAX) = fmaxf(ST(HS_STAT_ACTION_ERROR_MAX), m_ae);
-        ST(HS_STAT_OUT_OF_ARENA) = ((ST(HS_STAT_OUT_OF_ARENA) != 0.0f) || out_of_arena) ? 1.0f : 0.0f;
-        ST(HS_STAT_DISTANCE_REWARD) = (ST(HS_STAT_DISTANCE_REWARD) + m_dist) / ep_len;
-        ST(HS_STAT_SUM_DETECT_STEP) = ST(HS_STAT_SUM_DETECT_STEP) + 1.0f * (bdetect ? 1.0f : 0.0f);
-        ST(HS_STAT_DETECT_REWARD) = (ST(HS_STAT_DETECT_REWARD) + m_detect) / ep_len;
-        ST(HS_STAT_BLOCKED) = ST(HS_STAT_BLOCKED) + (all_blocked ? 1.0f : 0.0f);
+        ST(HS_STAT_ACTION_ERROR_MEAN) = (OLD(HS_STAT_ACTION_ERROR_MEAN) + m_ae) * inv_len;
+        ST(HS_STAT_ACTION_ERROR_MAX) = fmaxf(OLD(HS_STAT_ACTION_ERROR_MAX), m_ae);
+        ST(HS_STAT_OUT_OF_ARENA) = ((OLD(HS_STAT_OUT_OF_ARENA) != 0.0f) || out_of_arena) ? 1.0f : 0.0f;
+        ST(HS_STAT_DISTANCE_REWARD) = (OLD(HS_STAT_DISTANCE_REWARD) + m_dist) * inv_len;
+        ST(HS_STAT_SUM_DETECT_STEP) = OLD(HS_STAT_SUM_DETECT_STEP) + 1.0f * (bdetect ? 1.0f : 0.0f);
+        ST(HS_STAT_DETECT_REWARD) = (OLD(HS_STAT_DETECT_REWARD) + m_detect) * inv_len;
+        ST(HS_STAT_BLOCKED) = OLD(HS_STAT_BLOCKED) + (all_blocked ? 1.0f : 0.0f);
         const bool capture_flag = r_catch != 0.0f;
-        ST(HS_STAT_SUCCESS) = (capture_flag || (ST(HS_STAT_SUCCESS) != 0.0f)) ? 1.0f : 0.0f;
+        ST(HS_STAT_SUCCESS) = (capture_flag || (OLD(HS_STAT_SUCCESS) != 0.0f)) ? 1.0f : 0.0f;
         const float step_now = (capture_flag ? 1.0f : 0.0f) * progress +
                                (capture_flag ? 0.0f : 1.0f) * (float)c.max_episode_length;
-        ST(HS_STAT_FIRST_CAPTURE_STEP) = fminf(ST(HS_STAT_FIRST_CAPTURE_STEP), step_now);
-        ST(HS_STAT_CATCH_REWARD) = (ST(HS_STAT_CATCH_REWARD) + m_catch) / ep_len;
-        ST(HS_STAT_SPEED_REWARD) = (ST(HS_STAT_SPEED_REWARD) + m_speed) / ep_len;
-        ST(HS_STAT_COLLISION_CYLINDER) = (ST(HS_STAT_COLLISION_CYLINDER) + m_hcyl) / ep_len;
-        ST(HS_STAT_COLLISION_DRONE) = (ST(HS_STAT_COLLISION_DRONE) + m_hdrone) / ep_len;
-        ST(HS_STAT_COLLISION) = (ST(HS_STAT_COLLISION) + (any_coll ? 1.0f : 0.0f)) / ep_len;
-        ST(HS_STAT_COLLISION_WALL) = (ST(HS_STAT_COLLISION_WALL) + m_hwall) / ep_len;
-        ST(HS_STAT_COLLISION_REWARD) = (ST(HS_STAT_COLLISION_REWARD) + m_coll) / ep_len;
+        ST(HS_STAT_FIRST_CAPTURE_STEP) = fminf(OLD(HS_STAT_FIRST_CAPTURE_STEP), step_now);
+        ST(HS_STAT_CATCH_REWARD) = (OLD(HS_STAT_CATCH_REWARD) + m_catch) * inv_len;
+        ST(HS_STAT_SPEED_REWARD) = (OLD(HS_STAT_SPEED_REWARD) + m_speed) * inv_len;
+        ST(HS_STAT_COLLISION_CYLINDER) = (OLD(HS_STAT_COLLISION_CYLINDER) + m_hcyl) * inv_len;
+        ST(HS_STAT_COLLISION_DRONE) = (OLD(HS_STAT_COLLISION_DRONE) + m_hdrone) * inv_len;
+        ST(HS_STAT_COLLISION) = (OLD(HS_STAT_COLLISION) + (any_coll ? 1.0f : 0.0f)) * inv_len;
+        ST(HS_STAT_COLLISION_WALL) = (OLD(HS_STAT_COLLISION_WALL) + m_hwall) * inv_len;
+        ST(HS_STAT_COLLISION_REWARD) = (OLD(HS_STAT_COLLISION_REWARD) + m_coll) * inv_len;
         if (c.write_smoothness_coef_stat) ST(HS_STAT_SMOOTHNESS_COEF) = c.smoothness_coef;
-        ST(HS_STAT_SMOOTHNESS_REWARD) = (ST(HS_STAT_SMOOTHNESS_REWARD) + m_smooth) / ep_len;
-        ST(HS_STAT_SMOOTHNESS_MEAN) = (ST(HS_STAT_SMOOTHNESS_MEAN) + m_tdiff) / ep_len;
-        ST(HS_STAT_SMOOTHNESS_MAX) = fmaxf(x_tdiff, ST(HS_STAT_SMOOTHNESS_MAX));
-        ST(HS_STAT_RETURN) = ST(HS_STAT_RETURN) + m_reward;
+        ST(HS_STAT_SMOOTHNESS_REWARD) = (OLD(HS_STAT_SMOOTHNESS_REWARD) + m_smooth) * inv_len;
+        ST(HS_STAT_SMOOTHNESS_MEAN) = (OLD(HS_STAT_SMOOTHNESS_MEAN) + m_tdiff) * inv_len;
+        ST(HS_STAT_SMOOTHNESS_MAX) = fmaxf(x_tdiff, OLD(HS_STAT_SMOOTHNESS_MAX));
+        ST(HS_STAT_RETURN) = OLD(HS_STAT_RETURN) + m_reward;
         // target_predicted_error is only ever divided (stays 0); distance_predicted_reward and
         // distance_threshold_L are never written (hideandseek.py:1023-1025).
 #undef ST
+#undef OLD
     }
     st.finish();
 }
@@ -805,7 +880,7 @@ hs_fill_kernel(const __grid_constant__ KParams P) {
     }
     V3 heading, up;
     heading_up(q, heading, up);
-    const float tfrac = progress / (float)c.max_episode_length;
+    const float tfrac = fdiv(progress, (float)c.max_episode_length);
     const V3 t_rpos = p - tp;
     const float mv = c.mask_value;
     const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
@@ -833,10 +908,12 @@ hs_fill_kernel(const __grid_constant__ KParams P) {
 // rules out the TF32/BF16 tensor-core paths).  The epilogue applies the FC + tanh, forms the
 // 35-wide rows and sends both row tiles out with TMA bulk stores.
 // =========================================================================================
-constexpr int TPB_E = 32;            // envs per CTA
-constexpr int TP_THREADS = 256;
-constexpr int TP_NE = TPB_E / 8;     // envs per thread (8 warps, one env group per warp)
+constexpr int TPB_E = 32;            // envs per tile
+constexpr int TP_THREADS = 128;      // 4 warps: warp w owns envs 8w..8w+7, lane t owns hidden units 2t, 2t+1
+constexpr int TP_NE = 8;             // envs per thread -> 8 x 8 accumulator tile: 64 FFMA per 4 LDS.128
 constexpr int TP_HID = 64;
+constexpr int TP_WS = 260;           // row pitch of the gate matrix in smem: 256 + 4 keeps float4 alignment and
+                                     // spreads the (coalesced-read) staging stores over 8 banks instead of 1
 
 struct TPParams {
     const float* w_ih;   // [256, FD]   gate order i,f,g,o (torch.nn.LSTM)
@@ -848,10 +925,12 @@ struct TPParams {
     float* pred_out;     // [E, 3F] or null
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return frcp(1.0f + __expf(-x)); }
+// tanh(x) = 1 - 2/(exp(2x)+1): exact limits at +-inf, abs error ~1e-7 (h and c are O(1))
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - 2.0f * frcp(__expf(2.0f * x) + 1.0f); }
 
 template <int A>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+__global__ void __launch_bounds__(TP_THREADS, 2)
 hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
     extern __shared__ __align__(128) float smem[];
     const hs_config& c = P.c;
@@ -862,186 +941,192 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
     const int D = 20 + F3;
     const int E = c.num_envs;
     const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * TPB_E;
-    const int nenv = (int)min((int64_t)TPB_E, E - e0);
+    const int ntiles = (E + TPB_E - 1) / TPB_E;
 
-    float* Wp = smem;                               // [KTOT][256]
-    float* bias = Wp + KTOT * 256;                  // [256]
+    float* Wp = smem;                               // [KTOT][TP_WS] permuted gate matrix
+    float* bias = Wp + KTOT * TP_WS;                // [256]
     float* fcw = bias + 256;                        // [F3][64]
     float* fcb = fcw + F3 * TP_HID;                 // [F3] (padded to 32)
-    float* xs = fcb + 32;                           // [H][FD][TPB_E]
-    float* hs = xs + H * FD * TPB_E;                // [2][64][TPB_E]
+    float* xs = fcb + 32;                           // [FD][TPB_E]   one time step of the input window
+    float* hs = xs + FD * TPB_E;                    // [2][64][TPB_E]
     float* preds = hs + 2 * TP_HID * TPB_E;         // [TPB_E][F3]
+    float* rowbuf = xs;                             // [TPB_E*A][D] row staging, aliases xs+hs (dead after the FC)
 
-    // ---- stage weights (permuted) and the input tile ------------------------------------
-    // column of (gate g, hidden unit j): thread-group t = j/2 owns columns t*8 + g*2 + (j&1)
+    // ---- stage the weights once per CTA (conflict-free: consecutive threads -> consecutive smem).
+    // column d of (gate g, hidden unit j): lane t = j/2 owns columns t*8 + g*2 + (j&1)
+    // global reads are linear (coalesced); the transposing smem stores hit 8 banks (pitch 260)
     for (int i = tid; i < 256 * FD; i += TP_THREADS) {
         const int row = i / FD, k = i - row * FD;
         const int g = row >> 6, j = row & 63;
-        Wp[k * 256 + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_ih + i);
+        Wp[k * TP_WS + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_ih + i);
     }
     for (int i = tid; i < 256 * TP_HID; i += TP_THREADS) {
         const int row = i >> 6, k = i & 63;
         const int g = row >> 6, j = row & 63;
-        Wp[(FD + k) * 256 + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_hh + i);
+        Wp[(FD + k) * TP_WS + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_hh + i);
     }
-    {
-        const int row = tid, g = row >> 6, j = row & 63;
-        bias[(j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
+    for (int col = tid; col < 256; col += TP_THREADS) {
+        const int t = col >> 3, g = (col & 7) >> 1, u = col & 1;
+        const int row = g * 64 + 2 * t + u;
+        bias[col] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
     }
     for (int i = tid; i < F3 * TP_HID; i += TP_THREADS) fcw[i] = __ldg(W.fc_w + i);
     if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
-    {
-        const float* src = P.b.tp_input + e0 * (int64_t)(H * FD);
-        const int per_env = H * FD;
-        for (int i = tid; i < TPB_E * per_env; i += TP_THREADS) {
-            const int e = i / per_env, r = i - e * per_env;       // r = s*FD + k
-            xs[r * TPB_E + e] = (e < nenv) ? __ldg(src + i) : 0.0f;
-        }
-    }
     __syncthreads();
 
-    // ---- recurrence ------------------------------------------------------------------------
-    const int t = tid & 31;              // column group: hidden units 2t, 2t+1
-    const int eg = tid >> 5;             // env group (= warp): envs eg*TP_NE .. +TP_NE-1
-    float cst[TP_NE][2];
-#pragma unroll
-    for (int e = 0; e < TP_NE; ++e) { cst[e][0] = 0.f; cst[e][1] = 0.f; }
+    const int t = tid & 31;              // column group
+    const int eg = tid >> 5;             // env group (= warp)
     float bv[8];
     {
         const float4 b0 = *reinterpret_cast<const float4*>(bias + t * 8);
         const float4 b1 = *reinterpret_cast<const float4*>(bias + t * 8 + 4);
         bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
     }
-    int cur = 0;
-    for (int s = 0; s < H; ++s) {
-        float acc[TP_NE][8];
+
+    // ---- persistent loop over 32-env tiles ----------------------------------------------------
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TPB_E;
+        const int nenv = (int)min((int64_t)TPB_E, E - e0);
+        const float* xin = P.b.tp_input + e0 * (int64_t)(H * FD);
+        float cst[TP_NE][2];
 #pragma unroll
-        for (int e = 0; e < TP_NE; ++e)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[e][q] = bv[q];
-        const float* xrow = xs + (s * FD) * TPB_E + eg * TP_NE;
-#pragma unroll 4
-        for (int k = 0; k < FD; ++k) {
-            const float4 xv = *reinterpret_cast<const float4*>(xrow + k * TPB_E);
-            const float4 w0 = *reinterpret_cast<const float4*>(Wp + k * 256 + t * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(Wp + k * 256 + t * 8 + 4);
-            const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        for (int e = 0; e < TP_NE; ++e) { cst[e][0] = 0.f; cst[e][1] = 0.f; }
+        int cur = 0;
+        for (int s = 0; s < H; ++s) {
+            // x_s tile: [FD][32] (transposed); consecutive threads read consecutive k of one env
+            for (int i = tid; i < TPB_E * FD; i += TP_THREADS) {
+                const int e = i / FD, k = i - e * FD;
+                xs[k * TPB_E + e] = (e < nenv) ? __ldg(xin + (int64_t)e * (H * FD) + s * FD + k) : 0.0f;
+            }
+            __syncthreads();             // also orders the previous step's h writes
+            float acc[TP_NE][8];
 #pragma unroll
             for (int e = 0; e < TP_NE; ++e)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(xe[e], wq[q], acc[e][q]);
-        }
-        if (s > 0) {                      // h_0 = 0
-            const float* hrow = hs + cur * TP_HID * TPB_E + eg * TP_NE;
+                for (int q = 0; q < 8; ++q) acc[e][q] = bv[q];
+            // operands of step k+1 are fetched while the 64 FFMAs of step k issue
+            auto mac_block = [&](const float* arow, const float* wrow, int nk) {
+                float4 a0 = *reinterpret_cast<const float4*>(arow);
+                float4 a1 = *reinterpret_cast<const float4*>(arow + 4);
+                float4 w0 = *reinterpret_cast<const float4*>(wrow);
+                float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
 #pragma unroll 4
-            for (int k = 0; k < TP_HID; ++k) {
-                const float4 hv = *reinterpret_cast<const float4*>(hrow + k * TPB_E);
-                const float4 w0 = *reinterpret_cast<const float4*>(Wp + (FD + k) * 256 + t * 8);
-                const float4 w1 = *reinterpret_cast<const float4*>(Wp + (FD + k) * 256 + t * 8 + 4);
-                const float he[4] = {hv.x, hv.y, hv.z, hv.w};
-                const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                for (int k = 0; k < nk; ++k) {
+                    const float ae[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const int kn = (k + 1 < nk) ? (k + 1) : k;
+                    a0 = *reinterpret_cast<const float4*>(arow + kn * TPB_E);
+                    a1 = *reinterpret_cast<const float4*>(arow + kn * TPB_E + 4);
+                    w0 = *reinterpret_cast<const float4*>(wrow + kn * TP_WS);
+                    w1 = *reinterpret_cast<const float4*>(wrow + kn * TP_WS + 4);
 #pragma unroll
-                for (int e = 0; e < TP_NE; ++e)
+                    for (int e = 0; e < TP_NE; ++e)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(he[e], wq[q], acc[e][q]);
+                        for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(ae[e], wq[q], acc[e][q]);
+                }
+            };
+            mac_block(xs + eg * TP_NE, Wp + t * 8, FD);
+            if (s > 0)                        // h_0 = 0
+                mac_block(hs + cur * TP_HID * TPB_E + eg * TP_NE, Wp + FD * TP_WS + t * 8, TP_HID);
+            float* hnext = hs + (cur ^ 1) * TP_HID * TPB_E + eg * TP_NE;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float hv[TP_NE];
+#pragma unroll
+                for (int e = 0; e < TP_NE; ++e) {
+                    const float ig = sigmoidf_(acc[e][0 + u]), fg = sigmoidf_(acc[e][2 + u]);
+                    const float gg = tanhf_(acc[e][4 + u]), og = sigmoidf_(acc[e][6 + u]);
+                    cst[e][u] = fmaf(fg, cst[e][u], ig * gg);
+                    hv[e] = og * tanhf_(cst[e][u]);
+                }
+                *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
             }
+            cur ^= 1;
+            __syncthreads();             // x tile is rewritten next; h(cur) complete
         }
-        float* hnext = hs + (cur ^ 1) * TP_HID * TPB_E + eg * TP_NE;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            float hv[TP_NE];
-#pragma unroll
-            for (int e = 0; e < TP_NE; ++e) {
-                const float ig = sigmoidf_(acc[e][0 + u]), fg = sigmoidf_(acc[e][2 + u]);
-                const float gg = tanhf(acc[e][4 + u]), og = sigmoidf_(acc[e][6 + u]);
-                cst[e][u] = fmaf(fg, cst[e][u], ig * gg);
-                hv[e] = og * tanhf(cst[e][u]);
-            }
-            *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        }
-        cur ^= 1;
-        __syncthreads();
-    }
 
-    // ---- FC + tanh -------------------------------------------------------------------------
-    {
-        const float* hfin = hs + cur * TP_HID * TPB_E;
-        for (int i = tid; i < TPB_E * F3; i += TP_THREADS) {
-            const int o = i / TPB_E, e = i - o * TPB_E;
-            float a = fcb[o];
+        // ---- FC + tanh ---------------------------------------------------------------------
+        {
+            const float* hfin = hs + cur * TP_HID * TPB_E;
+            for (int i = tid; i < TPB_E * F3; i += TP_THREADS) {
+                const int o = i / TPB_E, e = i - o * TPB_E;
+                float a = fcb[o];
 #pragma unroll 8
-            for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[j * TPB_E + e], a);
-            const float pv = tanhf(a);
-            preds[e * F3 + o] = pv;
-            if (W.pred_out != nullptr && e < nenv) W.pred_out[(e0 + e) * F3 + o] = pv;
+                for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[j * TPB_E + e], a);
+                const float pv = tanhf(a);
+                preds[e * F3 + o] = pv;
+                if (W.pred_out != nullptr && e < nenv) W.pred_out[(e0 + e) * F3 + o] = pv;
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- rows: thread (a, e) with e fastest -> coalesced arena reads ----------------------------
-    float* tile_self = Wp;                                  // weights are dead: reuse as staging
-    float* tile_all = Wp + TPB_E * A * (20 + 3 * FMAX);
-    if (tid < TPB_E * A) {
-        const int slot = tid / TPB_E, el = tid - slot * TPB_E;
-        const bool valid = el < nenv;
-        const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
-        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
-        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
-        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
-        const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
-        const float progress = *EROW(E_PROGRESS);
-        const bool bdetect = *EROW(E_BDETECT) != 0.0f;
-        V3 heading, up;
-        heading_up(q, heading, up);
-        const float tfrac = progress / (float)c.max_episode_length;
-        const V3 t_rpos = p - tp;
-        const float mv = c.mask_value;
-        const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
-        float* r1 = tile_self + (el * A + slot) * D;
-        float* r2 = tile_all + (el * A + slot) * D;
-        r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
-        r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z;
-        const float* pr = preds + el * F3;
-        for (int f = 0; f < c.future_step; ++f) {
-            const float px = (pr[3 * f] * 0.5f) * c.arena_size;
-            const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
-            const float pz = ((pr[3 * f + 2] + 1.0f) / 2.0f) * c.max_height;
-            const float dx = p.x - px, dy = p.y - py, dz = p.z - pz;
-            r1[3 + 3 * f] = dx; r1[4 + 3 * f] = dy; r1[5 + 3 * f] = dz;
-            r2[3 + 3 * f] = dx; r2[4 + 3 * f] = dy; r2[5 + 3 * f] = dz;
-        }
-        const int o = 3 + F3;
-        const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
-                                up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+        // ---- rows: thread (a, e) with e fastest -> coalesced arena reads -------------------------
+        // state_self and state_drones differ only in their first 3 words (masked / unmasked
+        // evader offset): stage the row tile once, store it, patch the heads, store it again.
+        V3 t_rpos = mk(0.f, 0.f, 0.f);
+        float* r1 = nullptr;
+        if (tid < TPB_E * A) {
+            const int slot = tid / TPB_E, el = tid - slot * TPB_E;
+            const bool valid = el < nenv;
+            const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
+            const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+            Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+            const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+            const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+            const float progress = *EROW(E_PROGRESS);
+            const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+            V3 heading, up;
+            heading_up(q, heading, up);
+            const float tfrac = fdiv(progress, (float)c.max_episode_length);
+            t_rpos = p - tp;
+            const float mv = c.mask_value;
+            const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+            r1 = rowbuf + (el * A + slot) * D;
+            r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+            const float* pr = preds + el * F3;
+            for (int f = 0; f < c.future_step; ++f) {
+                const float px = (pr[3 * f] * 0.5f) * c.arena_size;
+                const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
+                const float pz = ((pr[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
+                r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+            }
+            const int o = 3 + F3;
+            const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                    up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
 #pragma unroll
-        for (int i = 0; i < 17; ++i) { r1[o + i] = tail[i]; r2[o + i] = tail[i]; }
-    }
-    const int nwords = nenv * A * D;
-    float* g1 = P.b.state_self + e0 * A * D;
-    float* g2 = P.b.state_drones + e0 * A * D;
-    const bool bulk = HS_USE_BULK_STORE && (nenv == TPB_E) && ((nwords & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
-    if (bulk) {
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            bulk_store(g1, tile_self, (uint32_t)nwords * 4u);
-            bulk_store(g2, tile_all, (uint32_t)nwords * 4u);
-            bulk_commit();
-            bulk_wait_read<0>();
+            for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
         }
-    } else {
-        __syncthreads();
-        for (int i = tid; i < nwords; i += TP_THREADS) { g1[i] = tile_self[i]; g2[i] = tile_all[i]; }
+        const int nwords = nenv * A * D;
+        float* g1 = P.b.state_self + e0 * A * D;
+        float* g2 = P.b.state_drones + e0 * A * D;
+        const bool bulk = HS_USE_BULK_STORE && (nenv == TPB_E) && ((nwords & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            float* gdst = pass == 0 ? g1 : g2;
+            if (pass == 1 && r1 != nullptr) { r1[0] = t_rpos.x; r1[1] = t_rpos.y; r1[2] = t_rpos.z; }
+            if (bulk) {
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
+                    bulk_commit();
+                    bulk_wait_read<0>();     // the tile is patched / reused right after
+                }
+            } else {
+                __syncthreads();
+                for (int i = tid; i < nwords; i += TP_THREADS) gdst[i] = rowbuf[i];
+            }
+            __syncthreads();
+        }
     }
 }
 
 static size_t tp_smem_bytes(const hs_config& c) {
     const int FD = 7 + 3 * c.num_agents, KT = FD + TP_HID, F3 = 3 * c.future_step;
-    size_t words = (size_t)KT * 256 + 256 + (size_t)F3 * TP_HID + 32 + (size_t)c.history_step * FD * TPB_E +
-                   2 * TP_HID * TPB_E + (size_t)TPB_E * F3;
+    size_t words = (size_t)KT * TP_WS + 256 + (size_t)F3 * TP_HID + 32 + (size_t)FD * TPB_E + 2 * TP_HID * TPB_E +
+                   (size_t)TPB_E * 3 * FMAX;      // the row staging tile aliases the x/h region
     return words * sizeof(float);
 }
 
@@ -1107,6 +1192,7 @@ struct hs_handle {
     int64_t launches;
     int tp_frames;               // number of TP frames written so far (0 -> next one initialises history)
     int block;                   // threads per block for the tick kernels
+    int num_sms;
 };
 
 static thread_local char g_err[512] = "";
@@ -1176,6 +1262,7 @@ int hs_default_config(hs_config* c, int32_t num_envs) {
     c->lin_damp_factor = (float)(1.0 - 0.01 * 0.2); c->ang_damp_factor = (float)(1.0 - 0.01 * 0.2);
     c->max_linear_velocity = 1.0f; c->max_angular_velocity = 1000.0f;
     c->ground_z = 0.0125f;
+    for (int i = 0; i < 3; ++i) c->inv_inertia[i] = 1.0f / c->inertia[i];
     c->hover_throttle = sqrtf((c->total_mass * 9.81f) / (4.0f * c->kf));
     c->arena_size_sq = (float)(0.9 * 0.9);
     c->half_arena = (float)(0.5 * 0.9);
@@ -1194,6 +1281,8 @@ static int check_cfg(const hs_config* c) {
         return set_err(HS_ERR_INVALID, "obs_max_cylinder must be <= min(num_cylinders, 4)%s");
     if (c->future_step < 0 || c->future_step > HS_MAX_FUTURE) return set_err(HS_ERR_INVALID, "future_step must be 0..8%s");
     if (c->history_step < 1) return set_err(HS_ERR_INVALID, "history_step must be >= 1%s");
+    if (c->use_tp_net && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
+        return set_err(HS_ERR_INVALID, "history_step * (7 + 3*num_agents) must be <= 192%s");
     return HS_OK;
 }
 
@@ -1224,6 +1313,8 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
     h->Ep = ((int64_t)cfg->num_envs + 31) & ~(int64_t)31;
     h->launches = 0;
     h->tp_frames = 0;
+    h->num_sms = 148;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
     // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
     const int64_t warps = ((int64_t)cfg->num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
     h->block = (warps >= 4 * 148 * 4) ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
@@ -1319,7 +1410,8 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     W.w_ih = w->weight_ih; W.w_hh = w->weight_hh; W.b_ih = w->bias_ih; W.b_hh = w->bias_hh;
     W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = tp_pred_out;
     const size_t smem = tp_smem_bytes(h->cfg);
-    const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + TPB_E - 1) / TPB_E);
+    const int64_t ntiles = ((int64_t)h->cfg.num_envs + TPB_E - 1) / TPB_E;
+    const unsigned grid = (unsigned)min(ntiles, (int64_t)2 * h->num_sms);      // persistent: <= 2 CTAs per SM
     cudaStream_t s = (cudaStream_t)stream;
     switch (h->cfg.num_agents) {
         case 1: hs_tp_fill_kernel<1><<<grid, TP_THREADS, smem, s>>>(P, W); break;
