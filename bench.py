@@ -293,7 +293,8 @@ def run_gpu_arm(args):
         h_act = torch.randn(E, A, 4).pin_memory()
         d_act = torch.empty(E, A, 4, device=dev)
         slab0 = engines[0].out
-        h_res = torch.empty(slab0.slab.numel(), dtype=torch.float32).pin_memory()
+        npol = slab0.policy_words                 # observation (state_self, state_others, cylinders) + reward
+        h_res = torch.empty(npol, dtype=torch.float32).pin_memory()
         h_bytes = torch.empty(slab0.bytes.numel(), dtype=torch.uint8).pin_memory()
         tds = [env.reset() for env in envs]
         ne = max(32, min(args.steps, 256))
@@ -305,7 +306,7 @@ def run_gpu_arm(args):
             td.set(("agents", "action"), d_act)
             td = envs[r].step(td)
             out = engines[r].out                  # the tensors env.step() returned live in this slab
-            h_res.copy_(out.slab, non_blocking=True)
+            h_res.copy_(out.slab[:npol], non_blocking=True)
             h_bytes.copy_(out.bytes.reshape(-1), non_blocking=True)
             torch.cuda.synchronize()              # the caller needs the result before it can act again
             tds[r] = mupe_b200.step_mdp(td)
@@ -318,7 +319,7 @@ def run_gpu_arm(args):
         extra["e2e"] = {"value": E * ne / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4,
                         "d2h_bytes_per_step": h_res.numel() * 4 + h_bytes.numel(), "steps": ne, "n_gpus": 1,
                         "api": "TransformedEnv(HideAndSeek).step(td): pinned host action -> H2D -> tick -> "
-                               "D2H of the whole observation/reward/done slab, host sync every step"}
+                               "D2H of observation (state_self, state_others, cylinders) + reward + done, host sync every step"}
         extra["cpu_baseline"] = {k: v for k, v in time_cpu_oracle(40, 3, budget_s=20.0).items()
                                  if k in ("value", "unit", "cores", "kind", "sample")}
         value = world * E * args.steps / (ms_total * 1e-3)

@@ -9,8 +9,9 @@ from ._lib import HsError
 from .compat import (Compose, InitTracker, SyncDataCollector, TensorDict, TransformedEnv, step_mdp)
 from .config import Cfg, build_hs_config, compose, load_drone_params
 from .engine import HsEngine
-from .envs import AgentSpec, HideAndSeek, IsaacEnv, PIDRateController, TP_net
+from . import parallel
+from .envs import AgentSpec, GenBuffer, HideAndSeek, HideAndSeek_envgen, Hover, IsaacEnv, PIDRateController, TP_net
 
-__all__ = ["HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+__all__ = ["parallel", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
            "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
-           "HideAndSeek", "IsaacEnv", "PIDRateController", "TP_net"]
+           "HideAndSeek", "HideAndSeek_envgen", "GenBuffer", "Hover", "IsaacEnv", "PIDRateController", "TP_net"]

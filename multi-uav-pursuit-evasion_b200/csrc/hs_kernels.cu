@@ -255,7 +255,7 @@ __device__ __forceinline__ void write_self_row(float* row, V3 head, int F3, cons
 // that closes a reset (hideandseek.py:722-723, isaac_env.py:220-224).
 // =========================================================================================
 template <int A, bool RESET>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 hs_tick_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
     __shared__ __align__(128) float tp_mem[4][ENVS_PER_WARP * TP_ENV_WORDS_MAX];   // TP_input tile of the warp
@@ -629,7 +629,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     }
     // k nearest cylinders [E,A,K,5]; lowest index wins ties
     float hit_cyl = 0.f;
-    {
+    if (K > 0) {
         float* s = st.begin();
         if (is_drone) {
             float key[CMAX];
@@ -925,6 +925,18 @@ struct TPParams {
     float* pred_out;     // [E, 3F] or null
 };
 
+// Shared-memory layouts of the predictor kernel (both chosen for conflict-free 128-bit access):
+//  * gate matrix row k: two planes of 128 floats; lane t owns floats [t*4, t*4+4) of each plane,
+//    i.e. its 8 columns q = g*2 + u (gate g, hidden unit 2t+u) live at plane q>>2, slot q&3.
+//    A warp's LDS.128 of one plane is one contiguous 512 B span.
+//  * h[j][e]: row j is rotated by 4*(j>>1) floats, so that the 32 lanes writing rows 2t, 2t+1
+//    spread over all banks while 8 consecutive envs stay two aligned float4.
+__device__ __forceinline__ int tp_col(int g, int j) {
+    const int q = g * 2 + (j & 1);
+    return (q >> 2) * 128 + (j >> 1) * 4 + (q & 3);
+}
+__device__ __forceinline__ int tp_hoff(int j, int e) { return j * TPB_E + ((e + 4 * (j >> 1)) & (TPB_E - 1)); }
+
 __device__ __forceinline__ float sigmoidf_(float x) { return frcp(1.0f + __expf(-x)); }
 // tanh(x) = 1 - 2/(exp(2x)+1): exact limits at +-inf, abs error ~1e-7 (h and c are O(1))
 __device__ __forceinline__ float tanhf_(float x) { return 1.0f - 2.0f * frcp(__expf(2.0f * x) + 1.0f); }
@@ -947,8 +959,8 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
     float* bias = Wp + KTOT * TP_WS;                // [256]
     float* fcw = bias + 256;                        // [F3][64]
     float* fcb = fcw + F3 * TP_HID;                 // [F3] (padded to 32)
-    float* xs = fcb + 32;                           // [FD][TPB_E]   one time step of the input window
-    float* hs = xs + FD * TPB_E;                    // [2][64][TPB_E]
+    float* xs = fcb + 32;                           // [2][FD][TPB_E] double-buffered time step of the input window
+    float* hs = xs + 2 * FD * TPB_E;                // [2][64][TPB_E]
     float* preds = hs + 2 * TP_HID * TPB_E;         // [TPB_E][F3]
     float* rowbuf = xs;                             // [TPB_E*A][D] row staging, aliases xs+hs (dead after the FC)
 
@@ -958,18 +970,17 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
     for (int i = tid; i < 256 * FD; i += TP_THREADS) {
         const int row = i / FD, k = i - row * FD;
         const int g = row >> 6, j = row & 63;
-        Wp[k * TP_WS + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_ih + i);
+        Wp[k * TP_WS + tp_col(g, j)] = __ldg(W.w_ih + i);
     }
-    for (int i = tid; i < 256 * TP_HID; i += TP_THREADS) {
-        const int row = i >> 6, k = i & 63;
+    for (int i = tid; i < 256 * TP_HID / 4; i += TP_THREADS) {       // 16 float4 per row of W_hh
+        const int row = i >> 4, k = (i & 15) * 4;
         const int g = row >> 6, j = row & 63;
-        Wp[(FD + k) * TP_WS + (j >> 1) * 8 + g * 2 + (j & 1)] = __ldg(W.w_hh + i);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W.w_hh) + i);
+        float* d = Wp + (FD + k) * TP_WS + tp_col(g, j);
+        d[0] = w.x; d[TP_WS] = w.y; d[2 * TP_WS] = w.z; d[3 * TP_WS] = w.w;
     }
-    for (int col = tid; col < 256; col += TP_THREADS) {
-        const int t = col >> 3, g = (col & 7) >> 1, u = col & 1;
-        const int row = g * 64 + 2 * t + u;
-        bias[col] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
-    }
+    for (int row = tid; row < 256; row += TP_THREADS)
+        bias[tp_col(row >> 6, row & 63)] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
     for (int i = tid; i < F3 * TP_HID; i += TP_THREADS) fcw[i] = __ldg(W.fc_w + i);
     if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
     __syncthreads();
@@ -978,8 +989,8 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
     const int eg = tid >> 5;             // env group (= warp)
     float bv[8];
     {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + t * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + t * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + t * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 128 + t * 4);
         bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
     }
 
@@ -992,43 +1003,53 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
 #pragma unroll
         for (int e = 0; e < TP_NE; ++e) { cst[e][0] = 0.f; cst[e][1] = 0.f; }
         int cur = 0;
-        for (int s = 0; s < H; ++s) {
-            // x_s tile: [FD][32] (transposed); consecutive threads read consecutive k of one env
+        // x_s tile [FD][32] (transposed) arrives by cp.async one time step ahead of its use
+        auto fetch_x = [&](int s) {
+            float* dst = xs + (s & 1) * FD * TPB_E;
             for (int i = tid; i < TPB_E * FD; i += TP_THREADS) {
                 const int e = i / FD, k = i - e * FD;
-                xs[k * TPB_E + e] = (e < nenv) ? __ldg(xin + (int64_t)e * (H * FD) + s * FD + k) : 0.0f;
+                if (e < nenv) cp_async4(dst + k * TPB_E + e, xin + (int64_t)e * (H * FD) + s * FD + k);
+                else dst[k * TPB_E + e] = 0.0f;
             }
-            __syncthreads();             // also orders the previous step's h writes
+            cp_async_commit();
+        };
+        fetch_x(0);
+        for (int s = 0; s < H; ++s) {
+            cp_async_wait_all();
+            __syncthreads();             // x_s visible to all; also orders the previous step's h writes
+            if (s + 1 < H) fetch_x(s + 1);
             float acc[TP_NE][8];
 #pragma unroll
             for (int e = 0; e < TP_NE; ++e)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[e][q] = bv[q];
             // operands of step k+1 are fetched while the 64 FFMAs of step k issue
-            auto mac_block = [&](const float* arow, const float* wrow, int nk) {
-                float4 a0 = *reinterpret_cast<const float4*>(arow);
-                float4 a1 = *reinterpret_cast<const float4*>(arow + 4);
+            // SWZ: the activation rows are the rotated h rows (tp_hoff); otherwise the plain x rows
+            auto mac_block = [&](const float* abase, const float* wrow, int nk, bool swz) {
+                auto aoff = [&](int k, int e0) { return swz ? tp_hoff(k, e0) : (k * TPB_E + e0); };
+                float4 a0 = *reinterpret_cast<const float4*>(abase + aoff(0, eg * TP_NE));
+                float4 a1 = *reinterpret_cast<const float4*>(abase + aoff(0, eg * TP_NE + 4));
                 float4 w0 = *reinterpret_cast<const float4*>(wrow);
-                float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+                float4 w1 = *reinterpret_cast<const float4*>(wrow + 128);
 #pragma unroll 4
                 for (int k = 0; k < nk; ++k) {
                     const float ae[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     const float wq[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                     const int kn = (k + 1 < nk) ? (k + 1) : k;
-                    a0 = *reinterpret_cast<const float4*>(arow + kn * TPB_E);
-                    a1 = *reinterpret_cast<const float4*>(arow + kn * TPB_E + 4);
+                    a0 = *reinterpret_cast<const float4*>(abase + aoff(kn, eg * TP_NE));
+                    a1 = *reinterpret_cast<const float4*>(abase + aoff(kn, eg * TP_NE + 4));
                     w0 = *reinterpret_cast<const float4*>(wrow + kn * TP_WS);
-                    w1 = *reinterpret_cast<const float4*>(wrow + kn * TP_WS + 4);
+                    w1 = *reinterpret_cast<const float4*>(wrow + kn * TP_WS + 128);
 #pragma unroll
                     for (int e = 0; e < TP_NE; ++e)
 #pragma unroll
                         for (int q = 0; q < 8; ++q) acc[e][q] = fmaf(ae[e], wq[q], acc[e][q]);
                 }
             };
-            mac_block(xs + eg * TP_NE, Wp + t * 8, FD);
+            mac_block(xs + (s & 1) * FD * TPB_E, Wp + t * 4, FD, false);
             if (s > 0)                        // h_0 = 0
-                mac_block(hs + cur * TP_HID * TPB_E + eg * TP_NE, Wp + FD * TP_WS + t * 8, TP_HID);
-            float* hnext = hs + (cur ^ 1) * TP_HID * TPB_E + eg * TP_NE;
+                mac_block(hs + cur * TP_HID * TPB_E, Wp + FD * TP_WS + t * 4, TP_HID, true);
+            float* hnext = hs + (cur ^ 1) * TP_HID * TPB_E;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 float hv[TP_NE];
@@ -1039,12 +1060,12 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
                     cst[e][u] = fmaf(fg, cst[e][u], ig * gg);
                     hv[e] = og * tanhf_(cst[e][u]);
                 }
-                *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                *reinterpret_cast<float4*>(hnext + (2 * t + u) * TPB_E + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                *reinterpret_cast<float4*>(hnext + tp_hoff(2 * t + u, eg * TP_NE)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(hnext + tp_hoff(2 * t + u, eg * TP_NE + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
             }
             cur ^= 1;
-            __syncthreads();             // x tile is rewritten next; h(cur) complete
         }
+        __syncthreads();                 // h(cur) complete
 
         // ---- FC + tanh ---------------------------------------------------------------------
         {
@@ -1053,7 +1074,7 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
                 const int o = i / TPB_E, e = i - o * TPB_E;
                 float a = fcb[o];
 #pragma unroll 8
-                for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[j * TPB_E + e], a);
+                for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[tp_hoff(j, e)], a);
                 const float pv = tanhf(a);
                 preds[e * F3 + o] = pv;
                 if (W.pred_out != nullptr && e < nenv) W.pred_out[(e0 + e) * F3 + o] = pv;
@@ -1125,7 +1146,7 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
 
 static size_t tp_smem_bytes(const hs_config& c) {
     const int FD = 7 + 3 * c.num_agents, KT = FD + TP_HID, F3 = 3 * c.future_step;
-    size_t words = (size_t)KT * TP_WS + 256 + (size_t)F3 * TP_HID + 32 + (size_t)FD * TPB_E + 2 * TP_HID * TPB_E +
+    size_t words = (size_t)KT * TP_WS + 256 + (size_t)F3 * TP_HID + 32 + 2 * (size_t)FD * TPB_E + 2 * TP_HID * TPB_E +
                    (size_t)TPB_E * 3 * FMAX;      // the row staging tile aliases the x/h region
     return words * sizeof(float);
 }
@@ -1318,6 +1339,17 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
     // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
     const int64_t warps = ((int64_t)cfg->num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
     h->block = (warps >= 4 * 148 * 4) ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
+    {
+        // 5 CTAs x 43 KB of static shared memory per SM: ask for the largest shared carve-out
+        cudaError_t e = cudaSuccess;
+        const int co = cudaSharedmemCarveoutMaxShared;
+        switch (cfg->num_agents) {
+            case 1: e = cudaFuncSetAttribute(hs_tick_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
+            case 2: e = cudaFuncSetAttribute(hs_tick_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
+            default: e = cudaFuncSetAttribute(hs_tick_kernel<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
+        }
+        if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e)); }
+    }
     if (cfg->use_tp_net) {
         // opt in to > 48 KB dynamic shared memory once (not a stream operation: keeps the
         // step entry points legal inside CUDA-graph capture)
@@ -1342,7 +1374,7 @@ int hs_destroy(hs_handle* h) {
 int hs_bind_buffers(hs_handle* h, const hs_buffers* b) {
     if (!h || !b) return set_err(HS_ERR_INVALID, "hs_bind_buffers: null argument%s");
     const hs_config& c = h->cfg;
-    if (!b->arena || !b->stats || !b->obs_cylinders || !b->state_self || !b->state_drones || !b->reward ||
+    if (!b->arena || !b->stats || (c.obs_max_cylinder > 0 && !b->obs_cylinders) || !b->state_self || !b->state_drones || !b->reward ||
         !b->done || !b->drone_state || !b->prev_action || !b->rotor_cmds || !b->ctbr || !b->target_rate ||
         !b->action_error || !b->v_prey)
         return set_err(HS_ERR_INVALID, "hs_bind_buffers: a required buffer is NULL%s");

