@@ -283,12 +283,36 @@ def run_gpu_arm(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = ab["tick"] * E / (tick_us * 1e-6) / 1e9
         extra["roofline"] = {"bound": "hbm", "kernel": "hs_tick_kernel<3,false>", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": 4975616, "traffic_source": "profiles/r1_ncu_tick_v2.txt: dram read+write per "
+                             "4096-env launch (writes stay in the 126 MB L2 for the duration of the launch)",
                              "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_launch": ab["tick"] * E, "launch_us": tick_us,
                              "note": "launch_us = period of back-to-back hs_tick_kernel launches (CUDA graph of 64) "
                                      "over the rotating L2-cold batches; 4096 envs = 512 warps on 148 SMs is "
-                                     "latency-bound, see the large-E sweep in profiles/"}
+                                     "latency/instruction-delivery bound; large-E sweep in profiles/ reaches 0.49"}
+        # (b) the fused predictor kernel: fp32 FFMA bound (LSTM 16->64 x10 steps + FC), not HBM
+        gp = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gp, stream=side):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(64):
+                e = engines[i % ROTATE]
+                _check(_hs.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp_net)), None, st), "hs_step_post_tp")
+        gp.replay()
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            gp.replay()
+        k1.record()
+        torch.cuda.synchronize()
+        tp_us = 1e3 * k0.elapsed_time(k1) / (64 * reps)
+        flops = 2.0 * 256 * (16 * H + 64 * (H - 1)) + 2.0 * 64 * 3 * F          # per env-tick
+        simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        tf = flops * E / (tp_us * 1e-6) / 1e12
+        extra["roofline_predictor"] = {"bound": "fp32 FFMA (SIMT)", "kernel": "hs_tp_fill_kernel<3>", "achieved": tf,
+                                       "peak": simt_peak, "unit": "TFLOP/s", "frac": tf / simt_peak, "launch_us": tp_us,
+                                       "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                                       "flop_per_env_tick": flops}
         # ---- end to end through env.step(): pinned host actions in; observation, reward, done out
         h_act = torch.randn(E, A, 4).pin_memory()
         d_act = torch.empty(E, A, 4, device=dev)

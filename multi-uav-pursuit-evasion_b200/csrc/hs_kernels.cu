@@ -204,8 +204,9 @@ constexpr int TICK_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * 20;            
 constexpr int TP_ENV_WORDS_MAX = 192;                                               // history_step * (7+3A) <= 192
 
 // ---- line of sight, hideandseek.py:47-103 ------------------------------------------------
-__device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float (&cx)[CMAX],
-                                            const float (&cy)[CMAX], const float (&cz)[CMAX],
+template <int CT>
+__device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float (&cx)[CT],
+                                            const float (&cy)[CT], const float (&cz)[CT],
                                             int C, float size) {
     const float ddx = p.x - t.x, ddy = p.y - t.y;
     // dist/(seg+eps) <= size  and  0 <= num/(den+eps) <= 1  with the (positive) denominators
@@ -215,7 +216,7 @@ __device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float 
     const float den = (dx * dx + dy * dy) + 1e-5f;
     bool blocked = false;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
+    for (int c = 0; c < CT; ++c) {
         if (c < C && cz[c] > 0.0f) {
             const float ccx = cx[c] - t.x, ccy = cy[c] - t.y;
             const float cr = fabsf(ddx * ccy - ddy * ccx);
@@ -254,7 +255,7 @@ __device__ __forceinline__ void write_self_row(float* row, V3 head, int F3, cons
 // The tick.  RESET=false: full control tick.  RESET=true: the unforced physics tick + obs
 // that closes a reset (hideandseek.py:722-723, isaac_env.py:220-224).
 // =========================================================================================
-template <int A, bool RESET>
+template <int A, bool RESET, int CT>
 __global__ void __launch_bounds__(128, 5)
 hs_tick_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
@@ -281,6 +282,15 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     const int FD = 7 + 3 * A;
     const int H = c.history_step;
     const float dt = c.dt;
+    // arena offsets fit 32 bits (checked at hs_create): one IMAD + one wide add per access
+    const uint32_t Ep32 = (uint32_t)P.Ep;
+    const uint32_t o_drone = (uint32_t)slot * Ep32 + (uint32_t)e;     // + k * (A*Ep32)
+    const uint32_t o_env = (uint32_t)(ND * A) * Ep32 + (uint32_t)e;   // + k * Ep32
+    float* const arena = P.b.arena;
+#undef DROW
+#undef EROW
+#define DROW(k) (arena + (o_drone + (uint32_t)(k) * ((uint32_t)A * Ep32)))
+#define EROW(k) (arena + (o_env + (uint32_t)(k) * Ep32))
 
     Stager st;
     st.buf[0] = stage_mem[wib][0];
@@ -294,7 +304,18 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     const int per_env = H * FD, keep = (H - 1) * FD;
     if (c.use_tp_net && !P.tp_init) {
         const float* src = P.b.tp_input_prev + e0 * per_env;
-        if ((FD & 3) == 0) {
+        if ((FD & 3) == 0 && H == 10 && full_tile) {
+            // common shape (A=3, H=10): 8 envs x 36 float4 = 9 per lane, all indices compile-time
+            constexpr int fd4 = FD / 4, pe4 = 10 * fd4, keep4 = 9 * fd4;
+#pragma unroll
+            for (int it = 0; it < (ENVS_PER_WARP * keep4 + 31) / 32; ++it) {
+                const int i = it * 32 + lane;
+                const int env = i / keep4, j = i - env * keep4;      // division by a constant
+                if (i < ENVS_PER_WARP * keep4)
+                    cp_async16(reinterpret_cast<float4*>(tp_tile) + env * pe4 + j,
+                               reinterpret_cast<const float4*>(src) + env * pe4 + j + fd4);
+            }
+        } else if ((FD & 3) == 0) {
             const int pe4 = per_env >> 2, keep4 = keep >> 2, fd4 = FD >> 2;
             const int total = nenv * keep4;
             int env = 0, j = lane;                       // i = env*keep4 + j, kept incrementally
@@ -353,9 +374,9 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
         }
         if (is_ev) v_prey = __ldg(P.b.v_prey);
     }
-    float cx[CMAX], cy[CMAX], cz[CMAX];
+    float cx[CT], cy[CT], cz[CT];
 #pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
+    for (int k = 0; k < CT; ++k) {
         if (k < C) {
             cx[k] = __ldg(EROW(E_CYL + 3 * k));
             cy[k] = __ldg(EROW(E_CYL + 3 * k + 1));
@@ -504,7 +525,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
             force = force + fr;
             float fcx = 0.f, fcy = 0.f;
 #pragma unroll
-            for (int k = 0; k < CMAX; ++k) {
+            for (int k = 0; k < CT; ++k) {
                 if (k < C && !(cz[k] < 0.0f)) {
                     const float tx = tp.x - cx[k], ty = tp.y - cy[k];
                     const float dxy = fsqrt(tx * tx + ty * ty);
@@ -632,9 +653,9 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     if (K > 0) {
         float* s = st.begin();
         if (is_drone) {
-            float key[CMAX];
+            float key[CT];
 #pragma unroll
-            for (int k = 0; k < CMAX; ++k)
+            for (int k = 0; k < CT; ++k)
                 key[k] = (k < C) ? (norm3(mk(p.x - cx[k], p.y - cy[k], p.z - cz[k])) - c.cylinder_size) : INFINITY;
             unsigned taken = 0u;
             float* r = s + row_l * (K * 5);
@@ -643,14 +664,14 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                 if (n < K) {
                     int best = 0; float bk = INFINITY; bool found = false;
 #pragma unroll
-                    for (int k = 0; k < CMAX; ++k) {
+                    for (int k = 0; k < CT; ++k) {
                         const bool cand = (k < C) && !((taken >> k) & 1u);
                         if (cand && (!found || key[k] < bk)) { best = k; bk = key[k]; found = true; }
                     }
                     taken |= 1u << best;
                     float bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll
-                    for (int k = 0; k < CMAX; ++k) if (k == best) { bx = cx[k]; by = cy[k]; bz = cz[k]; }
+                    for (int k = 0; k < CT; ++k) if (k == best) { bx = cx[k]; by = cy[k]; bz = cz[k]; }
                     const bool inactive = bz < 0.0f;
                     const float rx = p.x - bx, ry = p.y - by, rz = p.z - bz;
                     const float mv = c.mask_value;
@@ -826,6 +847,11 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     }
     st.finish();
 }
+
+#undef DROW
+#undef EROW
+#define DROW(k) AROW((k) * A + slot)
+#define EROW(k) AROW(ND * A + (k))
 
 // =========================================================================================
 // Second half with the trajectory predictor: state_self / state_drones rows (width 20+3F).
@@ -1232,10 +1258,11 @@ static cudaError_t launch_tick(const hs_handle* h, const KParams& P, cudaStream_
     const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
     const int wpb = h->block / 32;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    const bool small_c = h->cfg.num_cylinders <= 5;      // compile-time cylinder capacity 5 or 8
     switch (h->cfg.num_agents) {
-        case 1: hs_tick_kernel<1, RESET><<<grid, h->block, 0, s>>>(P); break;
-        case 2: hs_tick_kernel<2, RESET><<<grid, h->block, 0, s>>>(P); break;
-        default: hs_tick_kernel<3, RESET><<<grid, h->block, 0, s>>>(P); break;
+        case 1: if (small_c) hs_tick_kernel<1, RESET, 5><<<grid, h->block, 0, s>>>(P); else hs_tick_kernel<1, RESET, CMAX><<<grid, h->block, 0, s>>>(P); break;
+        case 2: if (small_c) hs_tick_kernel<2, RESET, 5><<<grid, h->block, 0, s>>>(P); else hs_tick_kernel<2, RESET, CMAX><<<grid, h->block, 0, s>>>(P); break;
+        default: if (small_c) hs_tick_kernel<3, RESET, 5><<<grid, h->block, 0, s>>>(P); else hs_tick_kernel<3, RESET, CMAX><<<grid, h->block, 0, s>>>(P); break;
     }
     return cudaGetLastError();
 }
@@ -1302,6 +1329,8 @@ static int check_cfg(const hs_config* c) {
         return set_err(HS_ERR_INVALID, "obs_max_cylinder must be <= min(num_cylinders, 4)%s");
     if (c->future_step < 0 || c->future_step > HS_MAX_FUTURE) return set_err(HS_ERR_INVALID, "future_step must be 0..8%s");
     if (c->history_step < 1) return set_err(HS_ERR_INVALID, "history_step must be >= 1%s");
+    if (((int64_t)ND * c->num_agents + E_CYL + 3 * (int64_t)c->num_cylinders) * (((int64_t)c->num_envs + 31) & ~(int64_t)31) >= ((int64_t)1 << 31))
+        return set_err(HS_ERR_INVALID, "num_envs too large: the state arena must stay below 2^31 words%s");
     if (c->use_tp_net && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
         return set_err(HS_ERR_INVALID, "history_step * (7 + 3*num_agents) must be <= 192%s");
     return HS_OK;
@@ -1343,11 +1372,15 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
         // 5 CTAs x 43 KB of static shared memory per SM: ask for the largest shared carve-out
         cudaError_t e = cudaSuccess;
         const int co = cudaSharedmemCarveoutMaxShared;
+        const bool small_c = cfg->num_cylinders <= 5;
+#define HS_CARVE(AA) (small_c ? cudaFuncSetAttribute(hs_tick_kernel<AA, false, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, co) \
+                              : cudaFuncSetAttribute(hs_tick_kernel<AA, false, CMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, co))
         switch (cfg->num_agents) {
-            case 1: e = cudaFuncSetAttribute(hs_tick_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
-            case 2: e = cudaFuncSetAttribute(hs_tick_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
-            default: e = cudaFuncSetAttribute(hs_tick_kernel<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co); break;
+            case 1: e = HS_CARVE(1); break;
+            case 2: e = HS_CARVE(2); break;
+            default: e = HS_CARVE(3); break;
         }
+#undef HS_CARVE
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e)); }
     }
     if (cfg->use_tp_net) {
