@@ -210,7 +210,9 @@ def run_gpu_arm(args):
 
     # fast path of the product: one CUDA-graph launch per tick = fused tick kernel + fused
     # predictor/fill kernel (no cuDNN, no per-kernel launch overhead); actions resident in HBM
+    variant = int(os.environ.get("HS_TP_VARIANT", "0"))     # 1: tensor-core (3xTF32) predictor kernel
     for eng, act in zip(engines, actions):
+        eng.set_predictor_variant(variant)
         eng.capture_tick_graphs(eng.tp_weights(tp_net), raw=True)
         eng.graph_action.copy_(act)
 
@@ -234,7 +236,8 @@ def run_gpu_arm(args):
     w0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
-        eng = tick(i)
+        tick(i)
+        eng = engines[i % ROTATE]
         if world > 1 and (i + 1) % ROLLOUT == 0:
             # the one collective of the path: episode returns of the rollout, all ranks
             dist.all_gather(gather_buf, eng.stats[17].contiguous())
@@ -355,6 +358,7 @@ def run_gpu_arm(args):
                        "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
                        "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
             "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
+            "predictor_kernel": "hs_tp_fill_mma_kernel (3xTF32 mma.sync)" if variant else "hs_tp_fill_kernel (fp32 FFMA)",
         }
         line.update(extra)
         print(json.dumps(line))

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
 
 HS_ABI_VERSION = 1
 HS_NUM_STATS = 24
+HS_OPT_PREDICTOR_VARIANT = 1
 
 # field ids, include/hs_b200.h
 (FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,
@@ -88,6 +89,7 @@ _EXPORTS = {
     "hs_state_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_state_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_launch_count": (C.c_int64, [C.c_void_p]),
+    "hs_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
 }
 
 

@@ -1378,6 +1378,552 @@ static size_t tp_wide_smem_bytes(const hs_config& c) {
     return words * sizeof(float);
 }
 
+// =========================================================================================
+// Tensor-core variant of the fused predictor: the two GEMMs of every LSTM step
+// ([envs x 80] x [80 x 256]) run on the tensor pipe as error-compensated TF32 ("3xTF32":
+// a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation), which keeps fp32-level
+// accuracy (the 1e-4 parity bar) at a fraction of the issue slots of the FFMA version.
+// Warp-level mma.sync.m16n8k8: operands are staged in shared memory already in FRAGMENT
+// order, so every operand fetch is one conflict-free LDS.64/LDS.128:
+//   * weights  Wf[kstep][ntile][lane][2]      (b0,b1 of the col-major 8x8 B fragment)
+//   * h        Ah{hi,lo}[mtile][kstep][lane][4] (a0..a3 of the 16x8 A fragment), written by the
+//              cell-update epilogue directly in fragment order and pre-split into hi/lo
+//   * x_t      Ax[mtile][kstep][lane][4] raw fp32 (cp.async, split on the fly)
+// Column permutation: n-tile (warp w, pair p, half h) holds, at column 2t+b, gate 2h+b of hidden
+// unit w*16+p*4+t, so the thread that owns accumulator pair (c0,c1) of an env row owns i,f (h=0)
+// and g,o (h=1) of the same (env, unit): the LSTM cell update is thread-local.
+// =========================================================================================
+constexpr int TM_THREADS = 128;
+constexpr int TM_XK = 2;             // k-steps (of 8) covering the padded input width 16
+constexpr int TM_HK = TP_HID / 8;    // 8 k-steps for the hidden part
+constexpr int TM_KS = TM_XK + TM_HK;
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// position of element (row r of the tile, column c of k-step ks) in an A-fragment array
+__device__ __forceinline__ int tm_aidx(int nks, int r, int ks, int c) {
+    const int m = r >> 4, rr = r & 15;
+    const int lane = (rr & 7) * 4 + (c & 3), elem = (rr >> 3) + 2 * (c >> 2);
+    return ((m * nks + ks) * 32 + lane) * 4 + elem;
+}
+
+template <int A, int MT>
+__global__ void __launch_bounds__(TM_THREADS, 2)
+hs_tp_fill_mma_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+    extern __shared__ __align__(128) float smem[];
+    const hs_config& c = P.c;
+    constexpr int FD = 7 + 3 * A;
+    constexpr int TE = 16 * MT;                     // envs per tile
+    const int H = c.history_step;
+    const int F3 = 3 * c.future_step;
+    const int D = 20 + F3;
+    const int E = c.num_envs;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntiles = (E + TE - 1) / TE;
+
+    float* Wf = smem;                               // [TM_KS][32 ntiles][32 lanes][2]
+    float* bias = Wf + TM_KS * 32 * 64;             // [256] indexed gate*64+unit
+    float* fcw = bias + 256;                        // [F3][64]
+    float* fcb = fcw + F3 * TP_HID;                 // [32]
+    float* Ahi = fcb + 32;                          // [MT][TM_HK][32][4]
+    float* Alo = Ahi + MT * TM_HK * 128;
+    float* Ax = Alo + MT * TM_HK * 128;             // [2][MT][TM_XK][32][4]
+    float* preds = Ax + 2 * MT * TM_XK * 128;       // [TE][F3]
+    float* rowbuf = Ahi;                            // [TE*A][D] row staging aliases the (dead) A fragments
+    static_assert(2 * MT * TM_HK * 128 + 2 * MT * TM_XK * 128 >= 16 * MT * A * (20 + 3 * FMAX), "row staging must fit");
+
+    // ---- stage weights in fragment order (once per CTA) ---------------------------------------
+    for (int i = tid; i < TM_KS * 32 * 64; i += TM_THREADS) Wf[i] = 0.0f;
+    __syncthreads();
+    auto wf_index = [&](int k, int gate, int unit) {
+        const int ks = k >> 3, tt = k & 3, jj = (k & 7) >> 2;
+        const int ww = unit >> 4, pp = (unit & 15) >> 2, gg = 2 * (unit & 3) + (gate & 1), hh = gate >> 1;
+        const int nt = (ww * 4 + pp) * 2 + hh;
+        return ((ks * 32 + nt) * 32 + gg * 4 + tt) * 2 + jj;
+    };
+    for (int i = tid; i < 256 * FD; i += TM_THREADS) {
+        const int row = i / FD, k = i - row * FD;
+        Wf[wf_index(k, row >> 6, row & 63)] = __ldg(W.w_ih + i);
+    }
+    for (int i = tid; i < 256 * TP_HID; i += TM_THREADS) {
+        const int row = i >> 6, k = i & 63;
+        Wf[wf_index(8 * TM_XK + k, row >> 6, row & 63)] = __ldg(W.w_hh + i);
+    }
+    for (int row = tid; row < 256; row += TM_THREADS) bias[row] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
+    for (int i = tid; i < F3 * TP_HID; i += TM_THREADS) fcw[i] = __ldg(W.fc_w + i);
+    if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
+    __syncthreads();
+
+    // bias of this thread's accumulator pairs: pair p -> unit w*16+p*4+t, gates (i,f) and (g,o)
+    float bi[4], bf[4], bg[4], bo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int u = w * 16 + p * 4 + t;
+        bi[p] = bias[u]; bf[p] = bias[64 + u]; bg[p] = bias[128 + u]; bo[p] = bias[192 + u];
+    }
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TE;
+        const int nenv = (int)min((int64_t)TE, E - e0);
+        const float* xin = P.b.tp_input + e0 * (int64_t)(H * FD);
+        float cst[MT][4][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { cst[m][p][0] = 0.f; cst[m][p][1] = 0.f; }
+
+        // x_s arrives by cp.async (4 B granules, scattered into fragment order) one step ahead
+        auto fetch_x = [&](int s) {
+            float* dst = Ax + (s & 1) * MT * TM_XK * 128;
+            for (int i = tid; i < TE * 8 * TM_XK; i += TM_THREADS) {
+                const int r = i / (8 * TM_XK), k = i - r * (8 * TM_XK);
+                float* d = dst + tm_aidx(TM_XK, r, k >> 3, k & 7);
+                if (r < nenv && k < FD) cp_async4(d, xin + (int64_t)r * (H * FD) + s * FD + k);
+                else *d = 0.0f;
+            }
+            cp_async_commit();
+        };
+        fetch_x(0);
+        for (int s = 0; s < H; ++s) {
+            cp_async_wait_all();
+            __syncthreads();                 // x_s landed; h_{s-1} (written below) visible
+            if (s + 1 < H) fetch_x(s + 1);
+            float acc[MT][8][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    acc[m][2 * p][0] = bi[p]; acc[m][2 * p][1] = bf[p]; acc[m][2 * p][2] = bi[p]; acc[m][2 * p][3] = bf[p];
+                    acc[m][2 * p + 1][0] = bg[p]; acc[m][2 * p + 1][1] = bo[p]; acc[m][2 * p + 1][2] = bg[p]; acc[m][2 * p + 1][3] = bo[p];
+                }
+            const float* ax = Ax + (s & 1) * MT * TM_XK * 128;
+            const int nks = (s > 0) ? TM_KS : TM_XK;     // h_0 = 0: skip the hidden part on the first step
+#pragma unroll 1
+            for (int ks = 0; ks < nks; ++ks) {
+                uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    if (ks < TM_XK) {
+                        const float4 v = *reinterpret_cast<const float4*>(ax + ((m * TM_XK + ks) * 32 + lane) * 4);
+                        tf32_split(v.x, ahi[m][0], alo[m][0]); tf32_split(v.y, ahi[m][1], alo[m][1]);
+                        tf32_split(v.z, ahi[m][2], alo[m][2]); tf32_split(v.w, ahi[m][3], alo[m][3]);
+                    } else {
+                        const int o = ((m * TM_HK + (ks - TM_XK)) * 32 + lane) * 4;
+                        const float4 vh = *reinterpret_cast<const float4*>(Ahi + o);
+                        const float4 vl = *reinterpret_cast<const float4*>(Alo + o);
+                        ahi[m][0] = __float_as_uint(vh.x); ahi[m][1] = __float_as_uint(vh.y);
+                        ahi[m][2] = __float_as_uint(vh.z); ahi[m][3] = __float_as_uint(vh.w);
+                        alo[m][0] = __float_as_uint(vl.x); alo[m][1] = __float_as_uint(vl.y);
+                        alo[m][2] = __float_as_uint(vl.z); alo[m][3] = __float_as_uint(vl.w);
+                    }
+                }
+                const float2* wrow = reinterpret_cast<const float2*>(Wf) + (ks * 32 + w * 8) * 32 + lane;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float2 wv = wrow[n * 32];
+                    uint32_t bh0, bl0, bh1, bl1;
+                    tf32_split(wv.x, bh0, bl0);
+                    tf32_split(wv.y, bh1, bl1);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        mma_tf32(acc[m][n], alo[m], bh0, bh1);      // small terms first
+                        mma_tf32(acc[m][n], ahi[m], bl0, bl1);
+                        mma_tf32(acc[m][n], ahi[m], bh0, bh1);
+                    }
+                }
+            }
+            __syncthreads();                 // every warp has read h_{s-1}: safe to overwrite
+            // ---- cell update: thread owns (env rows g, g+8) x (unit w*16+p*4+t) per m-tile ----------
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const float ig = sigmoidf_(acc[m][2 * p][2 * rh]), fg = sigmoidf_(acc[m][2 * p][2 * rh + 1]);
+                        const float gg = tanhf_(acc[m][2 * p + 1][2 * rh]), og = sigmoidf_(acc[m][2 * p + 1][2 * rh + 1]);
+                        cst[m][p][rh] = fmaf(fg, cst[m][p][rh], ig * gg);
+                        const float hval = og * tanhf_(cst[m][p][rh]);
+                        const int u = w * 16 + p * 4 + t;            // hidden unit = k column of the next step
+                        const int idx = tm_aidx(TM_HK, m * 16 + g + 8 * rh, u >> 3, u & 7);
+                        uint32_t hh, hl;
+                        tf32_split(hval, hh, hl);
+                        Ahi[idx] = __uint_as_float(hh);
+                        Alo[idx] = __uint_as_float(hl);
+                    }
+        }
+        __syncthreads();                     // h_H complete
+
+        // ---- FC + tanh (h = hi + lo) -----------------------------------------------------------
+        for (int i = tid; i < TE * F3; i += TM_THREADS) {
+            const int o = i / TE, e = i - o * TE;
+            float a = fcb[o];
+#pragma unroll 8
+            for (int jj = 0; jj < TP_HID; ++jj) {
+                const int idx = tm_aidx(TM_HK, e, jj >> 3, jj & 7);
+                a = fmaf(fcw[o * TP_HID + jj], Ahi[idx] + Alo[idx], a);
+            }
+            const float pv = tanhf(a);
+            preds[e * F3 + o] = pv;
+            if (W.pred_out != nullptr && e < nenv) W.pred_out[(e0 + e) * F3 + o] = pv;
+        }
+        __syncthreads();
+
+        // ---- rows (same as the FFMA variants) -------------------------------------------------------
+        V3 t_rpos = mk(0.f, 0.f, 0.f);
+        float* r1 = nullptr;
+        if (tid < TE * A) {
+            const int slot = tid / TE, el = tid - slot * TE;
+            const bool valid = el < nenv;
+            const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
+            const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+            Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+            const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+            const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+            const float progress = *EROW(E_PROGRESS);
+            const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+            V3 heading, up;
+            heading_up(q, heading, up);
+            const float tfrac = fdiv(progress, (float)c.max_episode_length);
+            t_rpos = p - tp;
+            const float mv = c.mask_value;
+            const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+            r1 = rowbuf + (el * A + slot) * D;
+            r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+            const float* pr = preds + el * F3;
+            for (int f = 0; f < c.future_step; ++f) {
+                const float px = (pr[3 * f] * 0.5f) * c.arena_size;
+                const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
+                const float pz = ((pr[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
+                r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+            }
+            const int o = 3 + F3;
+            const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                    up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+#pragma unroll
+            for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
+        }
+        const int nwords = nenv * A * D;
+        float* g1 = P.b.state_self + e0 * A * D;
+        float* g2 = P.b.state_drones + e0 * A * D;
+        const bool bulk = HS_USE_BULK_STORE && (nenv == TE) && ((nwords & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            float* gdst = pass == 0 ? g1 : g2;
+            if (pass == 1 && r1 != nullptr) { r1[0] = t_rpos.x; r1[1] = t_rpos.y; r1[2] = t_rpos.z; }
+            if (bulk) {
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+            } else {
+                __syncthreads();
+                for (int i = tid; i < nwords; i += TM_THREADS) gdst[i] = rowbuf[i];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static size_t tp_mma_smem_bytes(const hs_config& c, int MT) {
+    const int F3 = 3 * c.future_step, TE = 16 * MT;
+    size_t words = (size_t)TM_KS * 32 * 64 + 256 + (size_t)F3 * TP_HID + 32 + 2 * (size_t)MT * TM_HK * 128 +
+                   2 * (size_t)MT * TM_XK * 128 + (size_t)TE * 3 * FMAX;
+    return words * sizeof(float);
+}
+
+// =========================================================================================
+// tcgen05 variant of the fused predictor (Blackwell 5th-gen tensor cores, TMEM accumulators).
+// One CTA = 128 envs.  Per LSTM step the gate pre-activations D[128 x 256] live in TMEM and are
+// produced by tcgen05.mma.kind::tf32 (M=128, N=256, K=8 per instruction) issued by ONE thread:
+//   * B = [W_ih | W_hh]^T as tf32 hi/lo pairs in shared memory (canonical K-major core-matrix
+//     layout, no swizzle: 8 rows x 16 B per core matrix, SBO between 8-column groups, LBO
+//     between 16 B K-chunks), split once per CTA;
+//   * A = [x_t | h_{t-1}] ALSO lives in TMEM (the "TS" form of tcgen05.mma): every thread owns
+//     one env = one TMEM lane and writes its row (already split into tf32 hi/lo) with tcgen05.st,
+//     so the recurrent operand never touches shared memory;
+//   * error-compensated 3xTF32: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation,
+//     which keeps the fp32 parity bar;
+//   * completion is signalled by tcgen05.commit on an mbarrier; the epilogue (tcgen05.ld, cell
+//     update, tcgen05.st of h_t) is thread-local because column n = 4*unit + gate.
+// TMEM columns: D [0,256), A_hi [256,336), A_lo [336,416) -> 512 allocated (1 CTA per SM).
+// =========================================================================================
+constexpr int TC_M = 128;
+constexpr int TC_THREADS = 128;
+constexpr int TC_K = 16 + TP_HID;                   // 80, input width padded to 16
+constexpr int TC_COL_AHI = 256, TC_COL_ALO = 256 + TC_K;
+constexpr uint32_t TC_LBO = 4096, TC_SBO = 128;     // bytes: K-chunk stride / 8-column-group stride
+constexpr uint32_t TC_B_BYTES = (TC_K / 4) * TC_LBO; // 81920 per hi or lo copy
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t tc_bdesc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
+           (1ull << 46);                              // version 1 (sm_100), no swizzle, base offset 0
+}
+
+template <int A>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const hs_config& c = P.c;
+    constexpr int FD = 7 + 3 * A;
+    const int H = c.history_step;
+    const int F3 = 3 * c.future_step;
+    const int D = 20 + F3;
+    const int E = c.num_envs;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t e0 = (int64_t)blockIdx.x * TC_M;
+    const int nenv = (int)min((int64_t)TC_M, E - e0);
+    const bool valid = tid < nenv;
+    const int64_t e = valid ? (e0 + tid) : (int64_t)(E - 1);
+
+    uint8_t* Bhi = smem_raw;                                   // [K/4][32][8][4] tf32
+    uint8_t* Blo = Bhi + TC_B_BYTES;
+    float* bias = reinterpret_cast<float*>(Blo + TC_B_BYTES); // [256], column n = unit*4 + gate
+    float* fcw = bias + 256;                                   // [F3][64]
+    float* fcb = fcw + F3 * TP_HID;                            // [32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    float* hfin = reinterpret_cast<float*>(Bhi);               // [128][65]   after the last MMA (aliases B)
+    float* rowbuf = reinterpret_cast<float*>(Bhi) + TC_M * 65; // [128*A][D]  after the last MMA
+
+    // ---- one-time setup: TMEM, barrier, B operand (tf32 hi/lo split, canonical layout) ------------
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto b_off = [&](int n, int k) { return (uint32_t)((k >> 2) * TC_LBO + (n >> 3) * TC_SBO + (n & 7) * 16 + (k & 3) * 4); };
+    for (int i = tid; i < 256 * 16; i += TC_THREADS) {           // input part, zero padded to 16
+        const int row = i >> 4, k = i & 15;
+        const float wv = (k < FD) ? __ldg(W.w_ih + row * FD + k) : 0.0f;
+        const int n = (row & 63) * 4 + (row >> 6);
+        uint32_t hi, lo;
+        tf32_split(wv, hi, lo);
+        *reinterpret_cast<uint32_t*>(Bhi + b_off(n, k)) = hi;
+        *reinterpret_cast<uint32_t*>(Blo + b_off(n, k)) = lo;
+    }
+    for (int i = tid; i < 256 * TP_HID; i += TC_THREADS) {
+        const int row = i >> 6, k = 16 + (i & 63);
+        const int n = (row & 63) * 4 + (row >> 6);
+        uint32_t hi, lo;
+        tf32_split(__ldg(W.w_hh + i), hi, lo);
+        *reinterpret_cast<uint32_t*>(Bhi + b_off(n, k)) = hi;
+        *reinterpret_cast<uint32_t*>(Blo + b_off(n, k)) = lo;
+    }
+    for (int row = tid; row < 256; row += TC_THREADS)
+        bias[(row & 63) * 4 + (row >> 6)] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
+    for (int i = tid; i < F3 * TP_HID; i += TC_THREADS) fcw[i] = __ldg(W.fc_w + i);
+    if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
+    fence_async_smem();                       // B was written through the generic proxy, the MMA reads it through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes
+    const uint32_t bar = smem_u32(mbar);
+    const uint64_t dhi = tc_bdesc(smem_u32(Bhi)), dlo = tc_bdesc(smem_u32(Blo));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+    float cst[TP_HID];
+#pragma unroll
+    for (int j = 0; j < TP_HID; ++j) cst[j] = 0.f;
+    const float* xin = P.b.tp_input + e * (int64_t)(H * FD);
+    float xf[16];
+    auto load_x = [&](int s) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xf[k] = (valid && k < FD) ? __ldg(xin + s * FD + k) : 0.0f;
+    };
+    load_x(0);
+    uint32_t phase = 0;
+    for (int s = 0; s < H; ++s) {
+        // ---- A[:, 0:16] <- x_s (hi, lo) -------------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tf32_split(xf[q * 8 + k], vh[k], vl[k]);
+            tc_st8(lane_base + TC_COL_AHI + q * 8, vh);
+            tc_st8(lane_base + TC_COL_ALO + q * 8, vl);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        if (s + 1 < H) load_x(s + 1);                // global latency hides behind the MMAs
+        // ---- D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued by one thread -----------------------
+        if (tid == 0) {
+            tc_fence_after();
+            const int nk = (s > 0) ? (TC_K / 8) : 2;         // h_0 = 0: input part only on the first step
+            uint32_t acc = 0;
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t acol = (pass == 0) ? TC_COL_ALO : TC_COL_AHI;
+                const uint64_t bd = (pass == 1) ? dlo : dhi;
+                for (int j = 0; j < nk; ++j) {
+                    tc_mma_ts(tmem, tmem + acol + 8 * j, bd + (uint64_t)((2 * j * TC_LBO) >> 4), idesc, acc);
+                    acc = 1;
+                }
+            }
+            tc_commit(bar);
+        }
+        {   // wait for the accumulator (bounded spin: a wrong descriptor must not hang the box)
+            uint32_t spins = 0;
+            while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
+            phase ^= 1;
+        }
+        tc_fence_after();
+        // ---- epilogue: 8 chunks of 32 columns = 8 hidden units x (i,f,g,o) -------------------------
+        const bool last = (s + 1 == H);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {                 // fully unrolled: cst[] stays in registers
+            uint32_t v[32];
+            tc_ld32(lane_base + ch * 32, v);
+            uint32_t hh[8], hl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = ch * 8 + u;
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + j * 4);
+                const float ig = sigmoidf_(__uint_as_float(v[4 * u]) + b4.x), fg = sigmoidf_(__uint_as_float(v[4 * u + 1]) + b4.y);
+                const float gg = tanhf_(__uint_as_float(v[4 * u + 2]) + b4.z), og = sigmoidf_(__uint_as_float(v[4 * u + 3]) + b4.w);
+                cst[j] = fmaf(fg, cst[j], ig * gg);
+                const float hval = og * tanhf_(cst[j]);
+                tf32_split(hval, hh[u], hl[u]);
+                if (last) hfin[tid * 65 + j] = hval;
+            }
+            if (!last) {
+                tc_st8(lane_base + TC_COL_AHI + 16 + ch * 8, hh);
+                tc_st8(lane_base + TC_COL_ALO + 16 + ch * 8, hl);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- FC + tanh, thread-local (one env per thread) -------------------------------------------
+    float pred[3 * FMAX];
+#pragma unroll 1
+    for (int o = 0; o < F3; ++o) {
+        float a = fcb[o];
+#pragma unroll 8
+        for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[tid * 65 + j], a);
+        pred[o] = tanhf(a);
+        if (W.pred_out != nullptr && valid) W.pred_out[e * F3 + o] = pred[o];
+    }
+    // ---- rows: this thread builds the A rows of its env --------------------------------------------
+    const V3 tpv = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+    const float progress = *EROW(E_PROGRESS);
+    const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+    const float tfrac = fdiv(progress, (float)c.max_episode_length);
+    V3 trp[A];
+#pragma unroll
+    for (int slot = 0; slot < A; ++slot) {
+        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+        V3 heading, up;
+        heading_up(q, heading, up);
+        trp[slot] = p - tpv;
+        const float mv = c.mask_value;
+        const V3 head_m = bdetect ? trp[slot] : mk(mv, mv, mv);
+        float* r1 = rowbuf + (tid * A + slot) * D;
+        r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+        for (int f = 0; f < c.future_step; ++f) {
+            const float px = (pred[3 * f] * 0.5f) * c.arena_size;
+            const float py = (pred[3 * f + 1] * 0.5f) * c.arena_size;
+            const float pz = ((pred[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
+            r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+        }
+        const int o = 3 + F3;
+        const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+#pragma unroll
+        for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
+    }
+    const int nwords = nenv * A * D;
+    float* g1 = P.b.state_self + e0 * A * D;
+    float* g2 = P.b.state_drones + e0 * A * D;
+    const bool bulk = HS_USE_BULK_STORE && (nenv == TC_M) && ((nwords & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float* gdst = pass == 0 ? g1 : g2;
+        if (pass == 1) {
+#pragma unroll
+            for (int slot = 0; slot < A; ++slot) {
+                float* r1 = rowbuf + (tid * A + slot) * D;
+                r1[0] = trp[slot].x; r1[1] = trp[slot].y; r1[2] = trp[slot].z;
+            }
+        }
+        if (bulk) {
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < nwords; i += TC_THREADS) gdst[i] = rowbuf[i];
+        }
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+static size_t tp_tc_smem_bytes(const hs_config& c) {
+    const int F3 = 3 * c.future_step;
+    return 2 * (size_t)TC_B_BYTES + (256 + (size_t)F3 * TP_HID + 32) * sizeof(float) + 64;
+}
+
 static size_t tp_smem_bytes(const hs_config& c) {
     const int FD = 7 + 3 * c.num_agents, KT = FD + TP_HID, F3 = 3 * c.future_step;
     size_t words = (size_t)KT * TP_WS + 256 + (size_t)F3 * TP_HID + 32 + 2 * (size_t)FD * TPB_E + 2 * TP_HID * TPB_E +
@@ -1448,6 +1994,7 @@ struct hs_handle {
     int tp_frames;               // number of TP frames written so far (0 -> next one initialises history)
     int block;                   // threads per block for the tick kernels
     int num_sms;
+    int tp_variant;              // 0: fp32 FFMA predictor, 1: 3xTF32 tensor-core predictor (hs_set_option)
 };
 
 static thread_local char g_err[512] = "";
@@ -1571,6 +2118,7 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
     h->Ep = ((int64_t)cfg->num_envs + 31) & ~(int64_t)31;
     h->launches = 0;
     h->tp_frames = 0;
+    h->tp_variant = 0;
     h->num_sms = 148;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
     // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
@@ -1604,6 +2152,25 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
                     if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tp_fill_wide_kernel<2>, attr, smem_w); break;
             default: e = cudaFuncSetAttribute(hs_tp_fill_kernel<3>, attr, smem);
                     if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tp_fill_wide_kernel<3>, attr, smem_w); break;
+        }
+        if (e == cudaSuccess) {
+            const int m1 = (int)tp_mma_smem_bytes(*cfg, 1), m2 = (int)tp_mma_smem_bytes(*cfg, 2);
+            switch (cfg->num_agents) {
+                case 1: e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<1, 1>, attr, m1);
+                        if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<1, 2>, attr, m2); break;
+                case 2: e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<2, 1>, attr, m1);
+                        if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<2, 2>, attr, m2); break;
+                default: e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<3, 1>, attr, m1);
+                        if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tp_fill_mma_kernel<3, 2>, attr, m2); break;
+            }
+        }
+        if (e == cudaSuccess) {
+            const int t = (int)tp_tc_smem_bytes(*cfg);
+            switch (cfg->num_agents) {
+                case 1: e = cudaFuncSetAttribute(hs_tp_fill_tc_kernel<1>, attr, t); break;
+                case 2: e = cudaFuncSetAttribute(hs_tp_fill_tc_kernel<2>, attr, t); break;
+                default: e = cudaFuncSetAttribute(hs_tp_fill_tc_kernel<3>, attr, t); break;
+            }
         }
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
     }
@@ -1688,7 +2255,31 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = tp_pred_out;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t wide_tiles = ((int64_t)h->cfg.num_envs + TW_E - 1) / TW_E;
-    if (wide_tiles >= (int64_t)2 * h->num_sms) {
+    if (h->tp_variant == 2) {
+        // tcgen05 / TMEM variant: 128-env tiles, one CTA per tile
+        const size_t smem = tp_tc_smem_bytes(h->cfg);
+        const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + TC_M - 1) / TC_M);
+        switch (h->cfg.num_agents) {
+            case 1: hs_tp_fill_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(P, W); break;
+            case 2: hs_tp_fill_tc_kernel<2><<<grid, TC_THREADS, smem, s>>>(P, W); break;
+            default: hs_tp_fill_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(P, W); break;
+        }
+    } else if (h->tp_variant == 1) {
+        // tensor-core (3xTF32 mma.sync) variant: 32-env tiles when they fill the machine, else 16-env tiles
+        const bool big = wide_tiles >= (int64_t)2 * h->num_sms;
+        const int MT = big ? 2 : 1;
+        const size_t smem = tp_mma_smem_bytes(h->cfg, MT);
+        const int64_t ntiles = ((int64_t)h->cfg.num_envs + 16 * MT - 1) / (16 * MT);
+        const unsigned grid = (unsigned)min(ntiles, (int64_t)2 * h->num_sms);
+#define HS_MMA(AA) do { if (big) hs_tp_fill_mma_kernel<AA, 2><<<grid, TM_THREADS, smem, s>>>(P, W); \
+                        else hs_tp_fill_mma_kernel<AA, 1><<<grid, TM_THREADS, smem, s>>>(P, W); } while (0)
+        switch (h->cfg.num_agents) {
+            case 1: HS_MMA(1); break;
+            case 2: HS_MMA(2); break;
+            default: HS_MMA(3); break;
+        }
+#undef HS_MMA
+    } else if (wide_tiles >= (int64_t)2 * h->num_sms) {
         // enough 32-env tiles to give every SM two CTAs: the 8x8 register tile has the better FFMA:LDS ratio
         const size_t smem = tp_wide_smem_bytes(h->cfg);
         const unsigned grid = (unsigned)min(wide_tiles, (int64_t)2 * h->num_sms);
@@ -1797,5 +2388,17 @@ int hs_state_set(hs_handle* h, int field, const float* src, void* stream) {
     return field_copy(h, field, const_cast<float*>(src), 0, stream);
 }
 int64_t hs_launch_count(const hs_handle* h) { return h ? h->launches : -1; }
+
+int hs_set_option(hs_handle* h, int option, int value) {
+    if (!h) return set_err(HS_ERR_INVALID, "hs_set_option: null handle%s");
+    switch (option) {
+        case HS_OPT_PREDICTOR_VARIANT:
+            if (value < 0 || value > 2) return set_err(HS_ERR_INVALID, "predictor variant must be 0 (fp32 FFMA), 1 (3xTF32 mma.sync) or 2 (3xTF32 tcgen05)%s");
+            h->tp_variant = value;
+            return HS_OK;
+        default:
+            return set_err(HS_ERR_INVALID, "unknown option%s");
+    }
+}
 
 }  // extern "C"

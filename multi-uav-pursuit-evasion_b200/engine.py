@@ -177,6 +177,11 @@ class HsEngine:
         check(lib.hs_step_post_tp(self._h, C.byref(weights), _ptr(pred_out), self._stream()), "hs_step_post_tp")
         return self.out
 
+    def set_predictor_variant(self, variant: int):
+        """0: fp32 FFMA predictor kernel; 1: tensor-core (3xTF32) predictor kernel."""
+        check(lib.hs_set_option(self._h, _lib.HS_OPT_PREDICTOR_VARIANT, int(variant)), "hs_set_option")
+        self._graphs = None             # captured graphs hold the old kernel
+
     # ------------------------------------------------------------------ CUDA graphs
     def capture_tick_graphs(self, tp_weights=None, raw: bool = True):
         """Captures one CUDA graph per output set holding a whole tick (hs_step_pre and, with the

@@ -180,8 +180,9 @@ def test_partial_reset_keeps_other_envs():
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["ffma", "mma3xtf32", "tcgen05"])
 @pytest.mark.parametrize("A,E", [(3, 200), (3, 32), (2, 45), (1, 64), (3, 9500)])
-def test_fused_predictor_matches_torch_lstm(A, E):
+def test_fused_predictor_matches_torch_lstm(A, E, variant):
     """hs_step_post_tp (LSTM+FC+tanh+rows in one kernel, fp32 FFMA) against torch's CPU LSTM
     and against the two-kernel path fed with the same prediction."""
     import mupe_b200
@@ -204,6 +205,7 @@ def test_fused_predictor_matches_torch_lstm(A, E):
     eng.reset(mask.to(dev), init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
     w = eng.tp_weights(tp_gpu)
     assert w is not None
+    eng.set_predictor_variant(variant)
     done_prev = torch.zeros(E, dtype=torch.bool)
     for t in range(12 if E < 5000 else 3):       # > history_step so that the window is full of distinct frames
         act = torch.randn(E, A, 4, generator=g)
