@@ -210,7 +210,7 @@ def run_gpu_arm(args):
 
     # fast path of the product: one CUDA-graph launch per tick = fused tick kernel + fused
     # predictor/fill kernel (no cuDNN, no per-kernel launch overhead); actions resident in HBM
-    variant = int(os.environ.get("HS_TP_VARIANT", "0"))     # 1: tensor-core (3xTF32) predictor kernel
+    variant = int(os.environ.get("HS_TP_VARIANT", "-1"))     # 1: tensor-core (3xTF32) predictor kernel
     for eng, act in zip(engines, actions):
         eng.set_predictor_variant(variant)
         eng.capture_tick_graphs(eng.tp_weights(tp_net), raw=True)
@@ -358,7 +358,8 @@ def run_gpu_arm(args):
                        "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
                        "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
             "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
-            "predictor_kernel": "hs_tp_fill_mma_kernel (3xTF32 mma.sync)" if variant else "hs_tp_fill_kernel (fp32 FFMA)",
+            "predictor_kernel": {-1: "auto -> hs_tp_fill_kernel (fp32 FFMA) at 4096 envs", 0: "hs_tp_fill_kernel (fp32 FFMA)",
+                                 1: "hs_tp_fill_mma_kernel (3xTF32 mma.sync)", 2: "hs_tp_fill_tc_kernel (3xTF32 tcgen05)"}[variant],
         }
         line.update(extra)
         print(json.dumps(line))

@@ -958,9 +958,31 @@ struct TPParams {
 //    consecutive rows spread over the banks while 8 consecutive envs stay two aligned float4.
 __device__ __forceinline__ int tp_hoff(int j, int e) { return j * TPB_E + ((e + 4 * j) & (TPB_E - 1)); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return frcp(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoidf_(float x) { return frcp(1.0f + fex2(-1.4426950408889634f * x)); }
+// One LSTM cell update from the four gate pre-activations with 7 SFU operations instead of 10:
+// the four reciprocals 1/(1+e^-i), 1/(1+e^-f), 1/(e^2g+1), 1/(1+e^-o) share ONE rcp of the product of
+// their denominators (inputs clamped to +-15, where sigmoid/tanh are saturated to 3e-7, so the
+// product stays below 4e32).  Returns h; c is updated in place.
+__device__ __forceinline__ float lstm_cell(float zi, float zf, float zg, float zo, float& c) {
+    const float L2E = 1.4426950408889634f;
+    zi = fminf(fmaxf(zi, -15.f), 15.f); zf = fminf(fmaxf(zf, -15.f), 15.f);
+    zg = fminf(fmaxf(zg, -15.f), 15.f); zo = fminf(fmaxf(zo, -15.f), 15.f);
+    const float di = 1.0f + fex2(-L2E * zi), df = 1.0f + fex2(-L2E * zf);
+    const float dg = 1.0f + fex2(2.0f * L2E * zg), dO = 1.0f + fex2(-L2E * zo);
+    const float p1 = di * df, p2 = dg * dO;
+    const float r = frcp(p1 * p2);
+    const float rp2 = r * p2, rp1 = r * p1;
+    const float ig = rp2 * df, fg = rp2 * di;            // 1/di, 1/df
+    const float gg = 1.0f - 2.0f * (rp1 * dO);           // tanh(zg) = 1 - 2/dg
+    const float og = rp1 * dg;                           // 1/do
+    c = fmaf(fg, c, ig * gg);
+    const float cc = fminf(fmaxf(c, -15.f), 15.f);
+    const float th = 1.0f - 2.0f * frcp(1.0f + fex2(2.0f * L2E * cc));
+    return og * th;
+}
 // tanh(x) = 1 - 2/(exp(2x)+1): exact limits at +-inf, abs error ~1e-7 (h and c are O(1))
-__device__ __forceinline__ float tanhf_(float x) { return 1.0f - 2.0f * frcp(__expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - 2.0f * frcp(fex2(2.8853900817779268f * x) + 1.0f); }
 
 template <int A>
 __global__ void __launch_bounds__(TP_THREADS, 2)
@@ -1061,10 +1083,7 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
             float hv[TP_NE];
 #pragma unroll
             for (int e = 0; e < TP_NE; ++e) {
-                const float ig = sigmoidf_(acc[e][0]), fg = sigmoidf_(acc[e][1]);
-                const float gg = tanhf_(acc[e][2]), og = sigmoidf_(acc[e][3]);
-                cst[e] = fmaf(fg, cst[e], ig * gg);
-                hv[e] = og * tanhf_(cst[e]);
+                hv[e] = lstm_cell(acc[e][0], acc[e][1], acc[e][2], acc[e][3], cst[e]);
             }
             *reinterpret_cast<float4*>(hnext + tp_hoff(j, eg * TP_NE)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
             *reinterpret_cast<float4*>(hnext + tp_hoff(j, eg * TP_NE + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
@@ -1282,10 +1301,7 @@ hs_tp_fill_wide_kernel(const __grid_constant__ KParams P, const __grid_constant_
                 float hv[TW_NE];
 #pragma unroll
                 for (int e = 0; e < TW_NE; ++e) {
-                    const float ig = sigmoidf_(acc[e][0 + u]), fg = sigmoidf_(acc[e][2 + u]);
-                    const float gg = tanhf_(acc[e][4 + u]), og = sigmoidf_(acc[e][6 + u]);
-                    cst[e][u] = fmaf(fg, cst[e][u], ig * gg);
-                    hv[e] = og * tanhf_(cst[e][u]);
+                    hv[e] = lstm_cell(acc[e][0 + u], acc[e][2 + u], acc[e][4 + u], acc[e][6 + u], cst[e][u]);
                 }
                 *reinterpret_cast<float4*>(hnext + tw_hoff(2 * t + u, eg * TW_NE)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 *reinterpret_cast<float4*>(hnext + tw_hoff(2 * t + u, eg * TW_NE + 4)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
@@ -1551,10 +1567,8 @@ hs_tp_fill_mma_kernel(const __grid_constant__ KParams P, const __grid_constant__
                 for (int p = 0; p < 4; ++p)
 #pragma unroll
                     for (int rh = 0; rh < 2; ++rh) {
-                        const float ig = sigmoidf_(acc[m][2 * p][2 * rh]), fg = sigmoidf_(acc[m][2 * p][2 * rh + 1]);
-                        const float gg = tanhf_(acc[m][2 * p + 1][2 * rh]), og = sigmoidf_(acc[m][2 * p + 1][2 * rh + 1]);
-                        cst[m][p][rh] = fmaf(fg, cst[m][p][rh], ig * gg);
-                        const float hval = og * tanhf_(cst[m][p][rh]);
+                        const float hval = lstm_cell(acc[m][2 * p][2 * rh], acc[m][2 * p][2 * rh + 1], acc[m][2 * p + 1][2 * rh],
+                                                     acc[m][2 * p + 1][2 * rh + 1], cst[m][p][rh]);
                         const int u = w * 16 + p * 4 + t;            // hidden unit = k column of the next step
                         const int idx = tm_aidx(TM_HK, m * 16 + g + 8 * rh, u >> 3, u & 7);
                         uint32_t hh, hl;
@@ -1664,7 +1678,7 @@ static size_t tp_mma_smem_bytes(const hs_config& c, int MT) {
 // TMEM columns: D [0,256), A_hi [256,336), A_lo [336,416) -> 512 allocated (1 CTA per SM).
 // =========================================================================================
 constexpr int TC_M = 128;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;                    // 2 threads per env row: each updates half of the hidden units
 constexpr int TC_K = 16 + TP_HID;                   // 80, input width padded to 16
 constexpr int TC_COL_AHI = 256, TC_COL_ALO = 256 + TC_K;
 constexpr uint32_t TC_LBO = 4096, TC_SBO = 128;     // bytes: K-chunk stride / 8-column-group stride
@@ -1718,10 +1732,9 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
     const int D = 20 + F3;
     const int E = c.num_envs;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int64_t e0 = (int64_t)blockIdx.x * TC_M;
-    const int nenv = (int)min((int64_t)TC_M, E - e0);
-    const bool valid = tid < nenv;
-    const int64_t e = valid ? (e0 + tid) : (int64_t)(E - 1);
+    const int row = (warp & 3) * 32 + (tid & 31);      // env row of the tile = TMEM lane
+    const int hf = warp >> 2;                          // which half of the hidden units this thread updates
+    const int ntiles = (E + TC_M - 1) / TC_M;
 
     uint8_t* Bhi = smem_raw;                                   // [K/4][32][8][4] tf32
     uint8_t* Blo = Bhi + TC_B_BYTES;
@@ -1730,8 +1743,8 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
     float* fcb = fcw + F3 * TP_HID;                            // [32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-    float* hfin = reinterpret_cast<float*>(Bhi);               // [128][65]   after the last MMA (aliases B)
-    float* rowbuf = reinterpret_cast<float*>(Bhi) + TC_M * 65; // [128*A][D]  after the last MMA
+    float* part = reinterpret_cast<float*>(mbar + 2);          // [2][128][3*FMAX] partial FC sums of the two halves
+    float* rowbuf = part + 2 * TC_M * 3 * FMAX;                // [128*A][D]
 
     // ---- one-time setup: TMEM, barrier, B operand (tf32 hi/lo split, canonical layout) ------------
     if (warp == 0) {
@@ -1744,24 +1757,24 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
     }
     auto b_off = [&](int n, int k) { return (uint32_t)((k >> 2) * TC_LBO + (n >> 3) * TC_SBO + (n & 7) * 16 + (k & 3) * 4); };
     for (int i = tid; i < 256 * 16; i += TC_THREADS) {           // input part, zero padded to 16
-        const int row = i >> 4, k = i & 15;
-        const float wv = (k < FD) ? __ldg(W.w_ih + row * FD + k) : 0.0f;
-        const int n = (row & 63) * 4 + (row >> 6);
+        const int r = i >> 4, k = i & 15;
+        const float wv = (k < FD) ? __ldg(W.w_ih + r * FD + k) : 0.0f;
+        const int n = (r & 63) * 4 + (r >> 6);
         uint32_t hi, lo;
         tf32_split(wv, hi, lo);
         *reinterpret_cast<uint32_t*>(Bhi + b_off(n, k)) = hi;
         *reinterpret_cast<uint32_t*>(Blo + b_off(n, k)) = lo;
     }
     for (int i = tid; i < 256 * TP_HID; i += TC_THREADS) {
-        const int row = i >> 6, k = 16 + (i & 63);
-        const int n = (row & 63) * 4 + (row >> 6);
+        const int r = i >> 6, k = 16 + (i & 63);
+        const int n = (r & 63) * 4 + (r >> 6);
         uint32_t hi, lo;
         tf32_split(__ldg(W.w_hh + i), hi, lo);
         *reinterpret_cast<uint32_t*>(Bhi + b_off(n, k)) = hi;
         *reinterpret_cast<uint32_t*>(Blo + b_off(n, k)) = lo;
     }
-    for (int row = tid; row < 256; row += TC_THREADS)
-        bias[(row & 63) * 4 + (row >> 6)] = __ldg(W.b_ih + row) + __ldg(W.b_hh + row);
+    for (int r = tid; r < 256; r += TC_THREADS)
+        bias[(r & 63) * 4 + (r >> 6)] = __ldg(W.b_ih + r) + __ldg(W.b_hh + r);
     for (int i = tid; i < F3 * TP_HID; i += TC_THREADS) fcw[i] = __ldg(W.fc_w + i);
     if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
     fence_async_smem();                       // B was written through the generic proxy, the MMA reads it through the async proxy
@@ -1769,159 +1782,188 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's 32 TMEM lanes
     const uint32_t bar = smem_u32(mbar);
     const uint64_t dhi = tc_bdesc(smem_u32(Bhi)), dlo = tc_bdesc(smem_u32(Blo));
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-    float cst[TP_HID];
-#pragma unroll
-    for (int j = 0; j < TP_HID; ++j) cst[j] = 0.f;
-    const float* xin = P.b.tp_input + e * (int64_t)(H * FD);
-    float xf[16];
-    auto load_x = [&](int s) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) xf[k] = (valid && k < FD) ? __ldg(xin + s * FD + k) : 0.0f;
-    };
-    load_x(0);
     uint32_t phase = 0;
-    for (int s = 0; s < H; ++s) {
-        // ---- A[:, 0:16] <- x_s (hi, lo) -------------------------------------------------------
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = (int64_t)tile * TC_M;
+        const int nenv = (int)min((int64_t)TC_M, E - e0);
+        const bool valid = row < nenv;
+        const int64_t e = valid ? (e0 + row) : (int64_t)(E - 1);
+        float cst[32], hreg[32];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            uint32_t vh[8], vl[8];
+        for (int j = 0; j < 32; ++j) { cst[j] = 0.f; hreg[j] = 0.f; }
+        const float* xin = P.b.tp_input + e * (int64_t)(H * FD);
+        float xf[16];
+        auto load_x = [&](int s) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tf32_split(xf[q * 8 + k], vh[k], vl[k]);
-            tc_st8(lane_base + TC_COL_AHI + q * 8, vh);
-            tc_st8(lane_base + TC_COL_ALO + q * 8, vl);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncthreads();
-        if (s + 1 < H) load_x(s + 1);                // global latency hides behind the MMAs
-        // ---- D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued by one thread -----------------------
-        if (tid == 0) {
+            for (int k = 0; k < 16; ++k) xf[k] = (valid && k < FD) ? __ldg(xin + s * FD + k) : 0.0f;
+        };
+        load_x(0);
+        for (int s = 0; s < H; ++s) {
+            // ---- A[:, 0:16] <- x_s: the hf=0 thread of the row writes the hi words, its partner the lo words
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t vv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t hi, lo;
+                    tf32_split(xf[q * 8 + k], hi, lo);
+                    vv[k] = hf ? lo : hi;
+                }
+                tc_st8(lane_base + (hf ? TC_COL_ALO : TC_COL_AHI) + q * 8, vv);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncthreads();
+            if (s + 1 < H) load_x(s + 1);                // global latency hides behind the MMAs
+            // ---- D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued by one thread -----------------------
+            if (tid == 0) {
+                tc_fence_after();
+                const int nk = (s > 0) ? (TC_K / 8) : 2;         // h_0 = 0: input part only on the first step
+                uint32_t acc = 0;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t acol = (pass == 0) ? TC_COL_ALO : TC_COL_AHI;
+                    const uint64_t bd = (pass == 1) ? dlo : dhi;
+                    for (int j = 0; j < nk; ++j) {
+                        tc_mma_ts(tmem, tmem + acol + 8 * j, bd + (uint64_t)((2 * j * TC_LBO) >> 4), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(bar);
+            }
+            {   // wait for the accumulator (bounded spin: a wrong descriptor must not hang the box)
+                uint32_t spins = 0;
+                while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
+                phase ^= 1;
+            }
             tc_fence_after();
-            const int nk = (s > 0) ? (TC_K / 8) : 2;         // h_0 = 0: input part only on the first step
-            uint32_t acc = 0;
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t acol = (pass == 0) ? TC_COL_ALO : TC_COL_AHI;
-                const uint64_t bd = (pass == 1) ? dlo : dhi;
-                for (int j = 0; j < nk; ++j) {
-                    tc_mma_ts(tmem, tmem + acol + 8 * j, bd + (uint64_t)((2 * j * TC_LBO) >> 4), idesc, acc);
-                    acc = 1;
+            // ---- epilogue: this thread owns hidden units hf*32 .. hf*32+31 of its env ------------------
+            const bool last = (s + 1 == H);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {                 // fully unrolled: cst[] stays in registers
+                const int ch = hf * 4 + cc;
+                uint32_t v[32];
+                tc_ld32(lane_base + ch * 32, v);
+                uint32_t hh[8], hl[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + (ch * 8 + u) * 4);
+                    const float hval = lstm_cell(__uint_as_float(v[4 * u]) + b4.x, __uint_as_float(v[4 * u + 1]) + b4.y,
+                                                 __uint_as_float(v[4 * u + 2]) + b4.z, __uint_as_float(v[4 * u + 3]) + b4.w,
+                                                 cst[cc * 8 + u]);
+                    tf32_split(hval, hh[u], hl[u]);
+                    hreg[cc * 8 + u] = hval;
+                }
+                if (!last) {
+                    tc_st8(lane_base + TC_COL_AHI + 16 + ch * 8, hh);
+                    tc_st8(lane_base + TC_COL_ALO + 16 + ch * 8, hl);
                 }
             }
-            tc_commit(bar);
         }
-        {   // wait for the accumulator (bounded spin: a wrong descriptor must not hang the box)
-            uint32_t spins = 0;
-            while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
-            phase ^= 1;
+        // ---- FC: each half sums over its 32 hidden units, halves are combined through smem ----------
+#pragma unroll 1
+        for (int o = 0; o < F3; ++o) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a = fmaf(fcw[o * TP_HID + hf * 32 + j], hreg[j], a);
+            part[(hf * TC_M + row) * (3 * FMAX) + o] = a;
         }
-        tc_fence_after();
-        // ---- epilogue: 8 chunks of 32 columns = 8 hidden units x (i,f,g,o) -------------------------
-        const bool last = (s + 1 == H);
+        tc_fence_before();
+        __syncthreads();
+        // ---- rows: thread (row, hf) builds drone slots hf, hf+2 of its env; the tile leaves in two
+        // halves of 64 envs (the staging buffer holds 64 envs) --------------------------------------
+        const V3 tpv = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+        const float progress = *EROW(E_PROGRESS);
+        const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+        const float tfrac = fdiv(progress, (float)c.max_episode_length);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const bool mine = (row >> 6) == half;
+            const int rl = row & 63;
+            V3 trp[2];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {                 // fully unrolled: cst[] stays in registers
-            uint32_t v[32];
-            tc_ld32(lane_base + ch * 32, v);
-            uint32_t hh[8], hl[8];
+            for (int si = 0; si < 2; ++si) {
+                const int slot = hf + 2 * si;
+                trp[si] = mk(0.f, 0.f, 0.f);
+                if (mine && slot < A) {
+                    const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+                    Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+                    const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+                    V3 heading, up;
+                    heading_up(q, heading, up);
+                    trp[si] = p - tpv;
+                    const float mv = c.mask_value;
+                    const V3 head_m = bdetect ? trp[si] : mk(mv, mv, mv);
+                    float* r1 = rowbuf + (rl * A + slot) * D;
+                    r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+                    for (int f = 0; f < c.future_step; ++f) {
+                        float pr[3];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = ch * 8 + u;
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + j * 4);
-                const float ig = sigmoidf_(__uint_as_float(v[4 * u]) + b4.x), fg = sigmoidf_(__uint_as_float(v[4 * u + 1]) + b4.y);
-                const float gg = tanhf_(__uint_as_float(v[4 * u + 2]) + b4.z), og = sigmoidf_(__uint_as_float(v[4 * u + 3]) + b4.w);
-                cst[j] = fmaf(fg, cst[j], ig * gg);
-                const float hval = og * tanhf_(cst[j]);
-                tf32_split(hval, hh[u], hl[u]);
-                if (last) hfin[tid * 65 + j] = hval;
+                        for (int k = 0; k < 3; ++k) {
+                            const int o = 3 * f + k;
+                            pr[k] = tanhf(fcb[o] + part[row * (3 * FMAX) + o] + part[(TC_M + row) * (3 * FMAX) + o]);
+                            if (W.pred_out != nullptr && valid && slot == 0) W.pred_out[e * F3 + o] = pr[k];
+                        }
+                        const float px = (pr[0] * 0.5f) * c.arena_size;
+                        const float py = (pr[1] * 0.5f) * c.arena_size;
+                        const float pz = ((pr[2] + 1.0f) * 0.5f) * c.max_height;
+                        r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+                    }
+                    const int o = 3 + F3;
+                    const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                            up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
+                }
             }
-            if (!last) {
-                tc_st8(lane_base + TC_COL_AHI + 16 + ch * 8, hh);
-                tc_st8(lane_base + TC_COL_ALO + 16 + ch * 8, hl);
+            const int nen = max(0, min(64, nenv - half * 64));
+            const int nwords = nen * A * D;
+            float* g1 = P.b.state_self + (e0 + half * 64) * A * D;
+            float* g2 = P.b.state_drones + (e0 + half * 64) * A * D;
+            const bool bulk = HS_USE_BULK_STORE && (nen == 64) && ((nwords & 3) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                float* gdst = pass == 0 ? g1 : g2;
+                if (pass == 1 && mine) {
+#pragma unroll
+                    for (int si = 0; si < 2; ++si) {
+                        const int slot = hf + 2 * si;
+                        if (slot < A) {
+                            float* r1 = rowbuf + (rl * A + slot) * D;
+                            r1[0] = trp[si].x; r1[1] = trp[si].y; r1[2] = trp[si].z;
+                        }
+                    }
+                }
+                if (bulk) {
+                    fence_async_smem();
+                    __syncthreads();
+                    if (tid == 0) {
+                        bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
+                        bulk_commit();
+                        bulk_wait_read<0>();
+                    }
+                } else {
+                    __syncthreads();
+                    for (int i = tid; i < nwords; i += TC_THREADS) gdst[i] = rowbuf[i];
+                }
+                __syncthreads();
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-
-    // ---- FC + tanh, thread-local (one env per thread) -------------------------------------------
-    float pred[3 * FMAX];
-#pragma unroll 1
-    for (int o = 0; o < F3; ++o) {
-        float a = fcb[o];
-#pragma unroll 8
-        for (int j = 0; j < TP_HID; ++j) a = fmaf(fcw[o * TP_HID + j], hfin[tid * 65 + j], a);
-        pred[o] = tanhf(a);
-        if (W.pred_out != nullptr && valid) W.pred_out[e * F3 + o] = pred[o];
-    }
-    // ---- rows: this thread builds the A rows of its env --------------------------------------------
-    const V3 tpv = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
-    const float progress = *EROW(E_PROGRESS);
-    const bool bdetect = *EROW(E_BDETECT) != 0.0f;
-    const float tfrac = fdiv(progress, (float)c.max_episode_length);
-    V3 trp[A];
-#pragma unroll
-    for (int slot = 0; slot < A; ++slot) {
-        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
-        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
-        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
-        V3 heading, up;
-        heading_up(q, heading, up);
-        trp[slot] = p - tpv;
-        const float mv = c.mask_value;
-        const V3 head_m = bdetect ? trp[slot] : mk(mv, mv, mv);
-        float* r1 = rowbuf + (tid * A + slot) * D;
-        r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
-        for (int f = 0; f < c.future_step; ++f) {
-            const float px = (pred[3 * f] * 0.5f) * c.arena_size;
-            const float py = (pred[3 * f + 1] * 0.5f) * c.arena_size;
-            const float pz = ((pred[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
-            r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
-        }
-        const int o = 3 + F3;
-        const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
-                                up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
-#pragma unroll
-        for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
-    }
-    const int nwords = nenv * A * D;
-    float* g1 = P.b.state_self + e0 * A * D;
-    float* g2 = P.b.state_drones + e0 * A * D;
-    const bool bulk = HS_USE_BULK_STORE && (nenv == TC_M) && ((nwords & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0);
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        float* gdst = pass == 0 ? g1 : g2;
-        if (pass == 1) {
-#pragma unroll
-            for (int slot = 0; slot < A; ++slot) {
-                float* r1 = rowbuf + (tid * A + slot) * D;
-                r1[0] = trp[slot].x; r1[1] = trp[slot].y; r1[2] = trp[slot].z;
-            }
-        }
-        if (bulk) {
-            fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
-                bulk_commit();
-                bulk_wait_read<0>();
-            }
-        } else {
-            __syncthreads();
-            for (int i = tid; i < nwords; i += TC_THREADS) gdst[i] = rowbuf[i];
-        }
-        __syncthreads();
-    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 static size_t tp_tc_smem_bytes(const hs_config& c) {
     const int F3 = 3 * c.future_step;
-    return 2 * (size_t)TC_B_BYTES + (256 + (size_t)F3 * TP_HID + 32) * sizeof(float) + 64;
+    return 2 * (size_t)TC_B_BYTES + (256 + (size_t)F3 * TP_HID + 32) * sizeof(float) + 16 +
+           (2 * (size_t)TC_M * 3 * FMAX + (size_t)(TC_M / 2) * c.num_agents * (20 + 3 * FMAX)) * sizeof(float);
 }
 
 static size_t tp_smem_bytes(const hs_config& c) {
@@ -1994,7 +2036,7 @@ struct hs_handle {
     int tp_frames;               // number of TP frames written so far (0 -> next one initialises history)
     int block;                   // threads per block for the tick kernels
     int num_sms;
-    int tp_variant;              // 0: fp32 FFMA predictor, 1: 3xTF32 tensor-core predictor (hs_set_option)
+    int tp_variant;              // -1 auto, 0 fp32 FFMA, 1 3xTF32 mma.sync, 2 3xTF32 tcgen05 (hs_set_option)
 };
 
 static thread_local char g_err[512] = "";
@@ -2118,7 +2160,7 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
     h->Ep = ((int64_t)cfg->num_envs + 31) & ~(int64_t)31;
     h->launches = 0;
     h->tp_frames = 0;
-    h->tp_variant = 0;
+    h->tp_variant = -1;
     h->num_sms = 148;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
     // small batches: smaller blocks spread the warps over more SMs (latency bound regime)
@@ -2255,16 +2297,19 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = tp_pred_out;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t wide_tiles = ((int64_t)h->cfg.num_envs + TW_E - 1) / TW_E;
-    if (h->tp_variant == 2) {
+    // auto (-1): the FFMA kernels win while a batch is a single wave of small tiles (one dependent
+    // chain per tile, measured crossover ~6k envs); above that the tcgen05 kernel is 2-2.5x faster
+    const int variant = (h->tp_variant >= 0) ? h->tp_variant : ((h->cfg.num_envs >= 6144) ? 2 : 0);
+    if (variant == 2) {
         // tcgen05 / TMEM variant: 128-env tiles, one CTA per tile
         const size_t smem = tp_tc_smem_bytes(h->cfg);
-        const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + TC_M - 1) / TC_M);
+        const unsigned grid = (unsigned)min(((int64_t)h->cfg.num_envs + TC_M - 1) / TC_M, (int64_t)h->num_sms);   // persistent
         switch (h->cfg.num_agents) {
             case 1: hs_tp_fill_tc_kernel<1><<<grid, TC_THREADS, smem, s>>>(P, W); break;
             case 2: hs_tp_fill_tc_kernel<2><<<grid, TC_THREADS, smem, s>>>(P, W); break;
             default: hs_tp_fill_tc_kernel<3><<<grid, TC_THREADS, smem, s>>>(P, W); break;
         }
-    } else if (h->tp_variant == 1) {
+    } else if (variant == 1) {
         // tensor-core (3xTF32 mma.sync) variant: 32-env tiles when they fill the machine, else 16-env tiles
         const bool big = wide_tiles >= (int64_t)2 * h->num_sms;
         const int MT = big ? 2 : 1;
@@ -2393,7 +2438,7 @@ int hs_set_option(hs_handle* h, int option, int value) {
     if (!h) return set_err(HS_ERR_INVALID, "hs_set_option: null handle%s");
     switch (option) {
         case HS_OPT_PREDICTOR_VARIANT:
-            if (value < 0 || value > 2) return set_err(HS_ERR_INVALID, "predictor variant must be 0 (fp32 FFMA), 1 (3xTF32 mma.sync) or 2 (3xTF32 tcgen05)%s");
+            if (value < -1 || value > 2) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync) or 2 (3xTF32 tcgen05)%s");
             h->tp_variant = value;
             return HS_OK;
         default:

@@ -178,7 +178,7 @@ class HsEngine:
         return self.out
 
     def set_predictor_variant(self, variant: int):
-        """0: fp32 FFMA predictor kernel; 1: tensor-core (3xTF32) predictor kernel."""
+        """-1: auto (default); 0: fp32 FFMA kernel; 1: 3xTF32 mma.sync kernel; 2: 3xTF32 tcgen05/TMEM kernel."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_PREDICTOR_VARIANT, int(variant)), "hs_set_option")
         self._graphs = None             # captured graphs hold the old kernel
 

@@ -33,7 +33,7 @@ def run(E, dev, peak, reps=20):
         cyl = torch.zeros(E, 5, 3, device=dev)
         cyl[..., :2] = (torch.randint(-3, 4, (E, 5, 2), device=dev)).float() * 0.2
         cyl[..., 2] = 0.6
-        eng.set_predictor_variant(int(os.environ.get("HS_TP_VARIANT", "0")))
+        eng.set_predictor_variant(int(os.environ.get("HS_TP_VARIANT", "-1")))
         eng.reset(None, dpos, rot, tpos, cyl)
         eng.step_post_tp(eng.tp_weights(tp))
         eng.graph_action = torch.randn(E, 3, 4, device=dev)
