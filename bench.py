@@ -234,6 +234,7 @@ def run_gpu_arm(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
+    torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed region
     ev0.record()
     for i in range(args.steps):
         tick(i)
@@ -243,6 +244,7 @@ def run_gpu_arm(args):
             dist.all_gather(gather_buf, eng.stats[17].contiguous())
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     wall = time.perf_counter() - w0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -253,7 +255,9 @@ def run_gpu_arm(args):
     ms_total = float(t.item())
 
     extra = {}
-    if rank == 0:
+    if rank == 0 and os.environ.get("HS_BENCH_TIMED_ONLY", "0") == "1":
+        extra["note"] = "HS_BENCH_TIMED_ONLY=1: roofline / e2e / cpu_baseline legs skipped (launch-list capture run)"
+    elif rank == 0:
         # ---- kernel-only roofline: the tick kernel alone over the rotating (L2-cold) batches
         nk = max(64, min(args.steps, 512))
         # (a) the tick kernel alone, one CUDA graph holding 64 launches over the rotating batches
@@ -349,6 +353,7 @@ def run_gpu_arm(args):
                                "D2H of observation (state_self, state_others, cylinders) + reward + done, host sync every step"}
         extra["cpu_baseline"] = {k: v for k, v in time_cpu_oracle(40, 3, budget_s=20.0).items()
                                  if k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
         value = world * E * args.steps / (ms_total * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,

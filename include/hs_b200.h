@@ -240,6 +240,39 @@ int64_t hs_launch_count(const hs_handle* h);
 enum { HS_OPT_PREDICTOR_VARIANT = 1 };
 int hs_set_option(hs_handle* h, int option, int value);
 
+/* ---- device-side reset sampler --------------------------- */
+/* Replaces the sampling half of HideAndSeek._reset_idx for use_random_cylinder == 1
+ * (hideandseek.py:609-697): the uniform pose draws (:283-303, 616-629, 696-697) and
+ * rejection_sampling_random_cylinder + select_unoccupied_positions (:576-607, 106-119 - a
+ * per-env host loop over torch.randperm in the reference).  Same distribution; the random
+ * stream is a counter-based Philox4x32-10: words = philox(counter = (global env index, block,
+ * epoch lo, epoch hi), key = seed), so a draw depends only on (seed, epoch, env_offset + e) -
+ * not on the batch size, the shard or the reset mask.  Draw order: oracle/reset_sampler.py. */
+typedef struct hs_reset_dist {
+    float drone_lo[2], drone_hi[2];     /* init_drone_pos_dist   hideandseek.py:283-286 */
+    float target_lo[2], target_hi[2];   /* init_target_pos_dist  hideandseek.py:287-290 */
+    float z_lo, z_hi;                   /* init_*_pos_dist_z     hideandseek.py:291-298 */
+    float rpy_lo[3], rpy_hi[3];         /* init_rpy_dist         hideandseek.py:300-309 */
+    float grid_size;                    /* 2 * cylinder.size     hideandseek.py:578 */
+    int32_t num_grid;                   /* int(arena_size * 2 / grid_size), <= 11  :579 */
+    float boundary;                     /* clamp of the cylinder xy, grid_to_continuous :139 */
+    float cyl_z_active, cyl_z_inactive; /* 0.5 * cylinder.height / invalid_z       :685-689 */
+    int32_t min_cylinders;              /* active count ~ U{min_cylinders..num_cylinders} :598 */
+    int32_t fixed_num;                  /* >= 0: use_fixed_num (:595-596); -1: random */
+    int32_t fixed_xy;                   /* use_eval: xy from fixed_* instead of the draws (:618-627) */
+    float fixed_drone_xy[3][2];
+    float fixed_target_xy[2];
+    int64_t env_offset;                 /* global index of this handle's env 0 (sharded jobs) */
+    uint64_t seed;
+} hs_reset_dist;
+/* Writes drone_pos [E,A,3], drone_rot [E,A,4] wxyz, target_pos [E,3], cyl_pos [E,C,3] and
+ * n_active [E] (float, `active_cylinders`) - the arguments hs_reset takes - for ALL envs.
+ * One launch, asynchronous on `stream`.  HS_ERR_INVALID when the grid cannot hold
+ * num_cylinders free cells for every env (the reference raises ValueError, :111-112). */
+int hs_sample_reset(hs_handle* h, const hs_reset_dist* dist, uint64_t epoch, float* drone_pos,
+                    float* drone_rot, float* target_pos, float* cyl_pos, float* n_active,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

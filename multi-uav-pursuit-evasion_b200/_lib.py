@@ -73,6 +73,19 @@ class hs_tp_weights(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class hs_reset_dist(C.Structure):
+    """include/hs_b200.h::hs_reset_dist (device-side reset sampler)."""
+    _fields_ = [("drone_lo", C.c_float * 2), ("drone_hi", C.c_float * 2),
+                ("target_lo", C.c_float * 2), ("target_hi", C.c_float * 2),
+                ("z_lo", C.c_float), ("z_hi", C.c_float),
+                ("rpy_lo", C.c_float * 3), ("rpy_hi", C.c_float * 3),
+                ("grid_size", C.c_float), ("num_grid", C.c_int32), ("boundary", C.c_float),
+                ("cyl_z_active", C.c_float), ("cyl_z_inactive", C.c_float),
+                ("min_cylinders", C.c_int32), ("fixed_num", C.c_int32), ("fixed_xy", C.c_int32),
+                ("fixed_drone_xy", (C.c_float * 2) * 3), ("fixed_target_xy", C.c_float * 2),
+                ("env_offset", C.c_int64), ("seed", C.c_uint64)]
+
+
 _EXPORTS = {
     "hs_abi_version": (C.c_int, []),
     "hs_last_error": (C.c_char_p, []),
@@ -90,6 +103,8 @@ _EXPORTS = {
     "hs_state_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_launch_count": (C.c_int64, [C.c_void_p]),
     "hs_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hs_sample_reset": (C.c_int, [C.c_void_p, C.POINTER(hs_reset_dist), C.c_uint64, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -2064,6 +2064,158 @@ static cudaError_t launch_tick(const hs_handle* h, const KParams& P, cudaStream_
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Device-side reset sampler.  One thread per env; counter-based Philox4x32-10
+// (Salmon et al., SC'11) so a draw depends only on (seed, epoch, global env index).  Restated on
+// the CPU in oracle/reset_sampler.py (bit-exact bar for everything but sinf/cosf).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct PhiloxStream {
+    uint4 buf;
+    uint4 ctr;
+    uint2 key;
+    int used;
+    __device__ __forceinline__ uint32_t next() {
+        if (used == 4) {
+            buf = philox4x32_10(ctr, key);
+            ctr.y += 1;
+            used = 0;
+        }
+        const uint32_t v = used == 0 ? buf.x : used == 1 ? buf.y : used == 2 ? buf.z : buf.w;
+        ++used;
+        return v;
+    }
+    __device__ __forceinline__ float uniform(float lo, float hi) {
+        const float u = __fmul_rn((float)(next() >> 8), 5.9604644775390625e-08f);     // 2^-24, exact
+        return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
+    }
+};
+
+constexpr int RS_MAX_GRID = 11;                    // num_grid^2 <= 121 bits
+constexpr int RS_WORDS = 4;
+
+__global__ void __launch_bounds__(128) hs_reset_sample_kernel(hs_reset_dist d, int E, int A, int C, uint64_t epoch,
+                                                              float* __restrict__ drone_pos, float* __restrict__ drone_rot,
+                                                              float* __restrict__ target_pos, float* __restrict__ cyl_pos,
+                                                              float* __restrict__ n_active_out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    PhiloxStream rng;
+    rng.ctr = make_uint4((uint32_t)((uint64_t)d.env_offset + (uint64_t)e), 0u, (uint32_t)epoch, (uint32_t)(epoch >> 32));
+    rng.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+    rng.used = 4;
+
+    const int ng = d.num_grid, half = ng / 2;
+    // occupancy bits (1 = free): inside the circle of radius num_grid/2 cells, hideandseek.py:168-181
+    uint32_t freew[RS_WORDS] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < ng; ++i)
+        for (int j = 0; j < ng; ++j)
+            if ((i - half) * (i - half) + (j - half) * (j - half) < half * half) {
+                const int b = i * ng + j;
+                freew[b >> 5] |= 1u << (b & 31);
+            }
+    auto occupy = [&](float x, float y) {          // continuous_to_grid, hideandseek.py:144-166
+        int gx = (int)rintf(__fdiv_rn(x, d.grid_size)) + half;
+        int gy = (int)rintf(__fdiv_rn(y, d.grid_size)) + half;
+        gx = min(max(gx, 0), ng - 1);
+        gy = min(max(gy, 0), ng - 1);
+        const int b = gx * ng + gy;
+        freew[b >> 5] &= ~(1u << (b & 31));
+    };
+
+    float dxy[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a < A) {
+            dxy[a][0] = rng.uniform(d.drone_lo[0], d.drone_hi[0]);
+            dxy[a][1] = rng.uniform(d.drone_lo[1], d.drone_hi[1]);
+        }
+    float tx = rng.uniform(d.target_lo[0], d.target_hi[0]);
+    float ty = rng.uniform(d.target_lo[1], d.target_hi[1]);
+    if (d.fixed_xy) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (a < A) { dxy[a][0] = d.fixed_drone_xy[a][0]; dxy[a][1] = d.fixed_drone_xy[a][1]; }
+        tx = d.fixed_target_xy[0];
+        ty = d.fixed_target_xy[1];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a < A) {
+            float* p = drone_pos + ((size_t)e * A + a) * 3;
+            p[0] = dxy[a][0];
+            p[1] = dxy[a][1];
+            p[2] = rng.uniform(d.z_lo, d.z_hi);
+            occupy(dxy[a][0], dxy[a][1]);
+        }
+    target_pos[(size_t)e * 3 + 0] = tx;
+    target_pos[(size_t)e * 3 + 1] = ty;
+    target_pos[(size_t)e * 3 + 2] = rng.uniform(d.z_lo, d.z_hi);
+    occupy(tx, ty);
+
+    const uint32_t wn = rng.next();
+    const int n_active = d.fixed_num >= 0 ? d.fixed_num : d.min_cylinders + (int)__umulhi(wn, (uint32_t)(C + 1 - d.min_cylinders));
+    if (n_active_out) n_active_out[e] = (float)n_active;
+
+    int nfree = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WORDS; ++w) nfree += __popc(freew[w]);
+    // max_num distinct free cells, uniformly without replacement (hideandseek.py:106-119):
+    // the k-th draw takes the r-th still-free cell in ascending cell index, r uniform in [0, free-k)
+    for (int k = 0; k < C; ++k) {
+        int r = (int)__umulhi(rng.next(), (uint32_t)(nfree - k));
+        int cellidx = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WORDS; ++w) {
+            const int c = __popc(freew[w]);
+            if (r >= 0 && r < c) {
+                const int bit = (int)__fns(freew[w], 0, r + 1);
+                cellidx = w * 32 + bit;
+                freew[w] &= ~(1u << bit);
+                r = -1;
+            } else if (r >= 0) {
+                r -= c;
+            }
+        }
+        const int gx = cellidx / ng, gy = cellidx - gx * ng;
+        float x = __fmul_rn((float)(gx - half), d.grid_size);      // grid_to_continuous, hideandseek.py:120-142
+        float y = __fmul_rn((float)(gy - half), d.grid_size);
+        x = fminf(fmaxf(x, -d.boundary), d.boundary);
+        y = fminf(fmaxf(y, -d.boundary), d.boundary);
+        float* p = cyl_pos + ((size_t)e * C + k) * 3;
+        p[0] = x;
+        p[1] = y;
+        p[2] = k >= n_active ? d.cyl_z_inactive : d.cyl_z_active;
+    }
+
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (a < A) {
+            const float hr = 0.5f * rng.uniform(d.rpy_lo[0], d.rpy_hi[0]);
+            const float hp = 0.5f * rng.uniform(d.rpy_lo[1], d.rpy_hi[1]);
+            const float hy = 0.5f * rng.uniform(d.rpy_lo[2], d.rpy_hi[2]);
+            float sr, cr, sp, cp, sy, cy;                       // euler_to_quaternion (utils/torch.py), wxyz
+            sincosf(hr, &sr, &cr);
+            sincosf(hp, &sp, &cp);
+            sincosf(hy, &sy, &cy);
+            float4 q = make_float4(cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy,
+                                   cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy);
+            *reinterpret_cast<float4*>(drone_rot + ((size_t)e * A + a) * 4) = q;
+        }
+}
+
 extern "C" {
 
 int hs_abi_version(void) { return HS_ABI_VERSION; }
@@ -2371,6 +2523,30 @@ int hs_reset(hs_handle* h, const uint8_t* env_mask, const float* drone_pos, cons
     CUDA_OK(launch_tick<true>(h, P, s));
     h->launches += 2;
     if (h->cfg.use_tp_net) h->tp_frames += 1;
+    return HS_OK;
+}
+
+int hs_sample_reset(hs_handle* h, const hs_reset_dist* dist, uint64_t epoch, float* drone_pos, float* drone_rot,
+                    float* target_pos, float* cyl_pos, float* n_active, void* stream) {
+    if (!h || !dist || !drone_pos || !drone_rot || !target_pos) return set_err(HS_ERR_INVALID, "hs_sample_reset: null argument%s");
+    const int A = h->cfg.num_agents, C = h->cfg.num_cylinders, ng = dist->num_grid;
+    if (C > 0 && !cyl_pos) return set_err(HS_ERR_INVALID, "hs_sample_reset: cyl_pos is NULL%s");
+    if (ng < 1 || ng > RS_MAX_GRID || !(dist->grid_size > 0.f))
+        return set_err(HS_ERR_INVALID, "hs_sample_reset: num_grid must be in [1, 11] and grid_size > 0%s");
+    if (dist->fixed_num > C || (dist->fixed_num < 0 && (dist->min_cylinders < 0 || dist->min_cylinders > C)))
+        return set_err(HS_ERR_INVALID, "hs_sample_reset: active-cylinder range outside [0, num_cylinders]%s");
+    int inside = 0;
+    const int half = ng / 2;
+    for (int i = 0; i < ng; ++i)
+        for (int j = 0; j < ng; ++j)
+            inside += ((i - half) * (i - half) + (j - half) * (j - half) < half * half) ? 1 : 0;
+    if (inside - (A + 1) < C)      // worst case: every body on its own free cell (reference: ValueError, :111-112)
+        return set_err(HS_ERR_INVALID, "hs_sample_reset: not enough available grid cells for num_cylinders%s");
+    const int E = h->cfg.num_envs;
+    hs_reset_sample_kernel<<<(E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*dist, E, A, C, epoch, drone_pos, drone_rot,
+                                                                             target_pos, cyl_pos, n_active);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
     return HS_OK;
 }
 

@@ -237,6 +237,24 @@ class HsEngine:
                            _ptr(cyl_pos), self._stream()), "hs_reset")
         return self.out
 
+    def sample_reset(self, dist: "_lib.hs_reset_dist", epoch: int) -> Dict[str, torch.Tensor]:
+        """Device-side reset sampler (hs_sample_reset): one launch that draws the initial poses
+        of all envs of a random-cylinder episode - what HideAndSeek._reset_idx samples with torch
+        distributions and a per-env host randperm loop (hideandseek.py:609-697, 106-119).
+        Returns the dict HsEngine.reset / HideAndSeek._reset(init=...) consume; the buffers are
+        reused by the next call."""
+        E, A, Cc = self.E, self.A, self.C
+        if getattr(self, "_rs_bufs", None) is None:
+            z = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.device)
+            self._rs_bufs = dict(drone_pos=z(E, A, 3), drone_rot=z(E, A, 4), target_pos=z(E, 3),
+                                 cyl_pos=z(E, max(Cc, 1), 3)[:, :Cc], active_cylinders=z(E, 1))
+        b = self._rs_bufs
+        check(lib.hs_sample_reset(self._h, C.byref(dist), C.c_uint64(int(epoch) & (2 ** 64 - 1)), b["drone_pos"].data_ptr(),
+                                  b["drone_rot"].data_ptr(), b["target_pos"].data_ptr(),
+                                  _ptr(b["cyl_pos"]) if Cc > 0 else None, b["active_cylinders"].data_ptr(),
+                                  self._stream()), "hs_sample_reset")
+        return b
+
     # ------------------------------------------------------------------ state views
     _SHAPES = {
         _lib.FIELD_DRONE_POS: lambda s: (s.E, s.A, 3), _lib.FIELD_DRONE_ROT: lambda s: (s.E, s.A, 4),

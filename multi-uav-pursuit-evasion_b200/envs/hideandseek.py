@@ -130,6 +130,12 @@ class HideAndSeek(IsaacEnv):
         self.fused_predictor = True if self.cfg.env.fused_predictor is None else bool(self.cfg.env.fused_predictor)
         self.use_cuda_graph = True if self.cfg.env.cuda_graph is None else bool(self.cfg.env.cuda_graph)
         self._active_fixed = float(len(_LAYOUTS.get(self.scenario_flag, [])))
+        # reset poses are drawn by hs_sample_reset (one launch, counter-based stream) unless
+        # env.device_reset_sampler=0 selects the torch sampler below (torch's global generator)
+        self.device_reset_sampler = True if self.cfg.env.device_reset_sampler is None else bool(self.cfg.env.device_reset_sampler)
+        self._reset_epoch = 0
+        self._seed = int(self.cfg.seed or 0)
+        self._reset_dist = None
 
         frame = 7 + 3 * self.num_agents
         self.TP = TP_net(input_dim=frame, output_dim=3 * self.future_predcition_step,
@@ -207,9 +213,45 @@ class HideAndSeek(IsaacEnv):
         z = torch.where(inactive, torch.tensor(self.invalid_z, device=dev), torch.tensor(0.5 * self.cylinder_height, device=dev))
         return torch.cat([xy, z.unsqueeze(-1)], dim=-1), n_active.float()
 
+    def _set_seed(self, seed=-1):
+        super()._set_seed(seed)
+        self._seed = int(seed)
+        self._reset_dist = None
+
+    def reset_dist(self) -> "_lib.hs_reset_dist":
+        """include/hs_b200.h::hs_reset_dist of this task (hideandseek.py:283-309, 576-598)."""
+        if self._reset_dist is None:
+            a = self.arena_size / math.sqrt(2.0)
+            grid = 2 * self.cylinder_size
+            d = _lib.hs_reset_dist()
+            d.drone_lo[:], d.drone_hi[:] = [0.1, -a + 0.1], [a - 0.1, a - 0.1]
+            d.target_lo[:], d.target_hi[:] = [-a + 0.1, -a + 0.1], [-0.1, a - 0.1]
+            d.z_lo, d.z_hi = self.max_height / 2 - 0.1, self.max_height / 2 + 0.1
+            if self.use_eval:
+                d.rpy_lo[:], d.rpy_hi[:] = [0.0] * 3, [0.0] * 3
+                d.fixed_xy = 1
+                for k, pnt in enumerate(_STARTS["empty"][0][:self.num_agents]):
+                    d.fixed_drone_xy[k][0], d.fixed_drone_xy[k][1] = pnt[0], pnt[1]
+                d.fixed_target_xy[:] = list(_STARTS["empty"][1][:2])
+            else:
+                d.rpy_lo[:], d.rpy_hi[:] = [-0.2 * math.pi, -0.2 * math.pi, 0.0], [0.2 * math.pi] * 3
+            d.grid_size, d.num_grid, d.boundary = grid, int(self.arena_size * 2 / grid), self.boundary
+            d.cyl_z_active, d.cyl_z_inactive = 0.5 * self.cylinder_height, self.invalid_z
+            d.min_cylinders = self.min_cylinders
+            d.fixed_num = int(self.fixed_num) if self.use_fixed_num else -1
+            d.env_offset = int(self.cfg.env.env_offset or 0)
+            d.seed = self._seed & (2 ** 64 - 1)
+            self._reset_dist = d
+        return self._reset_dist
+
     def _sample_reset(self, n: int):
         """Initial poses for n envs (draw order follows hideandseek.py:609-697)."""
         A, C, dev = self.num_agents, self.num_cylinders, self.device
+        if self.use_random_cylinder and self.device_reset_sampler and n == self.num_envs and C > 0:
+            self._reset_epoch += 1
+            init = dict(self.engine.sample_reset(self.reset_dist(), self._reset_epoch))
+            init["active_cylinders"] = init["active_cylinders"].clone()
+            return init
         a = self.arena_size / math.sqrt(2.0)
         zlo, zhi = self.max_height / 2 - 0.1, self.max_height / 2 + 0.1
         if self.use_random_cylinder:
