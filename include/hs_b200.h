@@ -275,6 +275,37 @@ int hs_sample_reset(hs_handle* h, const hs_reset_dist* dist, uint64_t epoch, flo
                     float* drone_rot, float* target_pos, float* cyl_pos, float* n_active,
                     void* stream);
 
+/* ---- HideAndSeek_envgen control plane on the device ---------- */
+/* The two loops of GenBuffer that are O(archive) / O(E) host work in the reference
+ * (omni_drones/envs/hide_and_seek/hideandseek_envgen.py): no env handle is involved. */
+typedef struct hs_gen_params {
+    int32_t num_agents, num_cylinders;  /* task = [pursuer xyz * A, evader xyz, cylinder xyz * C] */
+    float arena_size;                   /* GenBuffer.arena_size      :226 */
+    float grid_size;                    /* 2 * cylinder_size         :228 */
+    float max_height;                   /* GenBuffer.max_height      :229 */
+    int32_t num_grid;                   /* int(arena_size * 2 / grid_size), <= 11 :230 */
+    int32_t expand_cylinders;           /* task.expand_cylinders */
+    float expand_step;                  /* task.expand_step */
+    uint64_t seed;
+} hs_gen_params;
+/* GenBuffer.samplenearby (:322-372): for each of num_tasks outputs pick an archive row of
+ * `history` [n_history, 3A+3+3C] uniformly, perturb, clip to the task bounds, accept when
+ * sanity_check (:185-207) passes, at most 10 attempts.  tasks_out [num_tasks, dim];
+ * valid_out[i] = 0 when all ten attempts failed (the caller re-draws those rows from the
+ * valid ones, :361-366).  Counter-based Philox stream (task, attempt, epoch), see
+ * oracle/envgen_oracle.py.  One launch, asynchronous. */
+int hs_gen_sample_nearby(const hs_gen_params* p, const float* history, int64_t n_history,
+                         int64_t num_tasks, uint64_t epoch, float* tasks_out, uint8_t* valid_out,
+                         void* stream);
+/* Greedy farthest point sampling of k of the n points [n, dim] (row-major device fp32),
+ * starting from `start` - what dgl.geometry.farthest_point_sampler does for
+ * GenBuffer.insert_history (:300-314).  idx_out [k] int32.  scratch: at least
+ * hs_fps_scratch_bytes(n) bytes of device memory.  One cooperative launch (all SMs, a grid
+ * barrier per selected point), asynchronous on `stream`. */
+int64_t hs_fps_scratch_bytes(int64_t n);
+int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start, int32_t* idx_out,
+           void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,13 @@ class hs_reset_dist(C.Structure):
                 ("env_offset", C.c_int64), ("seed", C.c_uint64)]
 
 
+class hs_gen_params(C.Structure):
+    """include/hs_b200.h::hs_gen_params (HideAndSeek_envgen control plane)."""
+    _fields_ = [("num_agents", C.c_int32), ("num_cylinders", C.c_int32), ("arena_size", C.c_float),
+                ("grid_size", C.c_float), ("max_height", C.c_float), ("num_grid", C.c_int32),
+                ("expand_cylinders", C.c_int32), ("expand_step", C.c_float), ("seed", C.c_uint64)]
+
+
 _EXPORTS = {
     "hs_abi_version": (C.c_int, []),
     "hs_last_error": (C.c_char_p, []),
@@ -103,6 +110,10 @@ _EXPORTS = {
     "hs_state_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_launch_count": (C.c_int64, [C.c_void_p]),
     "hs_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hs_gen_sample_nearby": (C.c_int, [C.POINTER(hs_gen_params), C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "hs_fps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_sample_reset": (C.c_int, [C.c_void_p, C.POINTER(hs_reset_dist), C.c_uint64, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -174,8 +174,14 @@ class TensorDict:
             td._d[k] = v.apply(fn, batch_size) if isinstance(v, TensorDict) else fn(v)
         return td
 
+    def _shallow(self) -> "TensorDict":
+        td = TensorDict.__new__(TensorDict)
+        td._batch_size, td._device = self._batch_size, self._device
+        td._d = {k: (v._shallow() if type(v) is TensorDict else v) for k, v in self._d.items()}
+        return td
+
     def clone(self, recurse: bool = True) -> "TensorDict":
-        return self.apply((lambda t: t.clone()) if recurse else (lambda t: t))
+        return self.apply(lambda t: t.clone()) if recurse else self._shallow()
 
     def to_tensordict(self):
         return self.clone()
@@ -200,6 +206,8 @@ class TensorDict:
             cur = self._d.get(k) if isinstance(k, str) else None
             if isinstance(v, (TensorDict, dict)) and isinstance(cur, TensorDict):
                 cur.update(v, inplace)
+            elif isinstance(v, TensorDict) and isinstance(k, str):
+                self._d[k] = v.clone(False)            # never alias the other tensordict's containers
             else:
                 self.set(k, v, inplace)
         return self

@@ -180,8 +180,8 @@ class CompositeSpec(TensorSpec):
 def step_mdp(td: TensorDict, exclude_action: bool = False) -> TensorDict:
     """Root of the next tick = everything under "next" + the carried-over root entries."""
     nxt = td.get("next")
-    out = td.exclude("next").clone(False)
-    out.update(nxt.clone(False))
+    out = td.exclude("next")              # a structural copy already (leaves shared, containers new)
+    out.update(nxt)                       # containers that come from "next" are copied by update()
     return out
 
 

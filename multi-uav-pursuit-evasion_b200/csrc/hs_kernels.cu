@@ -2575,6 +2575,160 @@ __global__ void __launch_bounds__(128) hs_reset_sample_kernel(hs_reset_dist d, i
         }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// HideAndSeek_envgen control plane: archive perturbation sampler and
+// farthest point sampling.  Restated on the CPU in oracle/envgen_oracle.py (bit-exact bar).
+// ---------------------------------------------------------------------------------------------
+constexpr int GEN_MAX_DIM = 3 * 3 + 3 + 3 * CMAX;
+
+struct GenBounds { float lo[GEN_MAX_DIM], hi[GEN_MAX_DIM]; };
+
+__global__ void __launch_bounds__(128) hs_gen_sample_nearby_kernel(hs_gen_params g, GenBounds B, const float* __restrict__ history,
+                                                                   int64_t n_history, int64_t num_tasks, uint64_t epoch,
+                                                                   float* __restrict__ tasks_out, uint8_t* __restrict__ valid_out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tasks) return;
+    const int A = g.num_agents, C = g.num_cylinders;
+    const int nb = 3 * A + 3, dim = nb + 3 * C;
+    const int ng = g.num_grid, half = ng / 2;
+    const uint64_t key64 = g.seed ^ 0x9E3779B97F4A7C15ull;
+    const uint2 key = make_uint2((uint32_t)key64, (uint32_t)(key64 >> 32));
+    uint32_t inside[RS_WORDS] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < ng; ++i)
+        for (int j = 0; j < ng; ++j)
+            if ((i - half) * (i - half) + (j - half) * (j - half) < half * half) {
+                const int b = i * ng + j;
+                inside[b >> 5] |= 1u << (b & 31);
+            }
+    const uint4 w0 = philox4x32_10(make_uint4((uint32_t)t, 0xFFFF0000u, (uint32_t)epoch, (uint32_t)(epoch >> 32)), key);
+    const int64_t idx = (int64_t)__umulhi(w0.x, (uint32_t)n_history);
+    float origin[GEN_MAX_DIM], cand[GEN_MAX_DIM];
+    for (int j = 0; j < dim; ++j) origin[j] = history[idx * dim + j];
+    bool ok = false;
+    for (int attempt = 0; attempt < 10 && !ok; ++attempt) {
+        PhiloxStream rng;
+        rng.ctr = make_uint4((uint32_t)t, (uint32_t)(64 * attempt), (uint32_t)epoch, (uint32_t)(epoch >> 32));
+        rng.key = key;
+        rng.used = 4;
+        for (int j = 0; j < nb; ++j) {
+            const float u = __fmul_rn((float)(rng.next() >> 8), 5.9604644775390625e-08f);
+            const float noise = __fmul_rn(__fadd_rn(-1.0f, __fmul_rn(2.0f, u)), g.expand_step);
+            cand[j] = __fadd_rn(origin[j], noise);
+        }
+        for (int c = 0; c < C; ++c) {
+            for (int a = 0; a < 2; ++a) {
+                const int s = (int)__umulhi(rng.next(), 3u) - 1;
+                cand[nb + 3 * c + a] = g.expand_cylinders ? __fadd_rn(origin[nb + 3 * c + a], __fmul_rn((float)s, g.grid_size))
+                                                          : origin[nb + 3 * c + a];
+            }
+            cand[nb + 3 * c + 2] = origin[nb + 3 * c + 2];
+        }
+        for (int j = 0; j < dim; ++j) cand[j] = fminf(fmaxf(cand[j], B.lo[j]), B.hi[j]);
+        // sanity_check: every object on its own free cell
+        uint32_t freew[RS_WORDS] = {inside[0], inside[1], inside[2], inside[3]};
+        ok = true;
+        for (int o = 0; o < A + 1 + C; ++o) {
+            const int base = 3 * o;
+            int gx = (int)rintf(__fdiv_rn(cand[base], g.grid_size)) + half;
+            int gy = (int)rintf(__fdiv_rn(cand[base + 1], g.grid_size)) + half;
+            gx = min(max(gx, 0), ng - 1);
+            gy = min(max(gy, 0), ng - 1);
+            const int b = gx * ng + gy;
+            const uint32_t bit = 1u << (b & 31);
+            uint32_t wsel = 0u;
+#pragma unroll
+            for (int w = 0; w < RS_WORDS; ++w) if (w == (b >> 5)) wsel = freew[w];
+            if (!(wsel & bit)) { ok = false; break; }
+#pragma unroll
+            for (int w = 0; w < RS_WORDS; ++w) if (w == (b >> 5)) freew[w] &= ~bit;
+        }
+    }
+    for (int j = 0; j < dim; ++j) tasks_out[t * dim + j] = cand[j];
+    valid_out[t] = ok ? 1 : 0;
+}
+
+// Farthest point sampling: every CTA owns a contiguous chunk of the points (cached in shared memory
+// when it fits), keeps their running minimum distance in global scratch, and proposes its local
+// argmax; one grid barrier per selected point, then every CTA reduces the proposals redundantly.
+// Key = (float bits of the distance << 32) | ~index: the maximum key is the maximum distance and, among
+// equal distances, the LOWEST index - numpy's argmax.
+constexpr int FPS_THREADS = 256;
+__device__ __forceinline__ unsigned long long fps_block_max(unsigned long long v, unsigned long long* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    v = sh[0];
+#pragma unroll
+    for (int w = 1; w < FPS_THREADS / 32; ++w) v = sh[w] > v ? sh[w] : v;
+    return v;
+}
+
+__global__ void __launch_bounds__(FPS_THREADS) hs_fps_kernel(const float* __restrict__ pts, int n, int dim, int k, int start,
+                                                             int chunk, int cache_pts, int32_t* __restrict__ out_idx,
+                                                             float* __restrict__ mind, unsigned long long* slots,
+                                                             unsigned int* bar) {
+    extern __shared__ __align__(16) float fps_smem[];
+    __shared__ unsigned long long red[FPS_THREADS / 32];
+    __shared__ float q[64];
+    const int tid = threadIdx.x, G = gridDim.x, c = blockIdx.x;
+    const int lo = c * chunk, hi = min(n, lo + chunk);
+    if (cache_pts)
+        for (int i = tid; i < (hi - lo) * dim; i += FPS_THREADS) fps_smem[i] = pts[(size_t)lo * dim + i];
+    for (int p = lo + tid; p < hi; p += FPS_THREADS) mind[p] = __int_as_float(0x7f800000);
+    __syncthreads();
+    int cur = start;
+    for (int it = 0; it < k; ++it) {
+        if (c == 0 && tid == 0) out_idx[it] = cur;
+        if (it + 1 == k) break;
+        if (tid < dim) q[tid] = pts[(size_t)cur * dim + tid];
+        __syncthreads();
+        unsigned long long best = 0ull;
+        for (int p = lo + tid; p < hi; p += FPS_THREADS) {
+            const float* x = cache_pts ? (fps_smem + (size_t)(p - lo) * dim) : (pts + (size_t)p * dim);
+            float d = 0.f;
+            for (int j = 0; j < dim; ++j) {
+                const float df = __fsub_rn(x[j], q[j]);
+                d = __fadd_rn(d, __fmul_rn(df, df));
+            }
+            const float m = fminf(mind[p], d);
+            mind[p] = m;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
+            best = key > best ? key : best;
+        }
+        best = fps_block_max(best, red);
+        unsigned long long* sl = slots + (size_t)(it & 1) * G;
+        if (tid == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(sl + c) = best;
+            __threadfence();
+            // grid barrier (all CTAs are co-resident: cooperative launch)
+            const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
+            if (atomicAdd(bar, 1u) == (unsigned)(G - 1)) {
+                *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
+                __threadfence();
+                atomicAdd(bar + 1, 1u);
+            } else {
+                while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) { }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        unsigned long long v = 0ull;
+        for (int i = tid; i < G; i += FPS_THREADS) {
+            const unsigned long long o = *reinterpret_cast<volatile unsigned long long*>(sl + i);
+            v = o > v ? o : v;
+        }
+        v = fps_block_max(v, red);
+        cur = (int)(0xFFFFFFFFu - (unsigned)(v & 0xFFFFFFFFull));
+    }
+}
+
 extern "C" {
 
 int hs_abi_version(void) { return HS_ABI_VERSION; }
@@ -2930,6 +3084,66 @@ int hs_sample_reset(hs_handle* h, const hs_reset_dist* dist, uint64_t epoch, flo
                                                                              target_pos, cyl_pos, n_active);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
+    return HS_OK;
+}
+
+int hs_gen_sample_nearby(const hs_gen_params* p, const float* history, int64_t n_history, int64_t num_tasks, uint64_t epoch,
+                         float* tasks_out, uint8_t* valid_out, void* stream) {
+    if (!p || !history || !tasks_out || !valid_out) return set_err(HS_ERR_INVALID, "hs_gen_sample_nearby: null argument%s");
+    if (p->num_agents < 1 || p->num_agents > 3 || p->num_cylinders < 0 || p->num_cylinders > CMAX)
+        return set_err(HS_ERR_INVALID, "hs_gen_sample_nearby: unsupported task shape%s");
+    if (p->num_grid < 1 || p->num_grid > RS_MAX_GRID || !(p->grid_size > 0.f))
+        return set_err(HS_ERR_INVALID, "hs_gen_sample_nearby: num_grid must be in [1, 11] and grid_size > 0%s");
+    if (n_history < 1 || n_history > 0xFFFFFFFFll) return set_err(HS_ERR_INVALID, "hs_gen_sample_nearby: empty archive%s");
+    if (num_tasks <= 0) return HS_OK;
+    // task bounds, hideandseek_envgen.py:327-340 (double arithmetic, rounded to fp32 once)
+    GenBounds B;
+    const double cb = (double)(int)((double)p->arena_size / (double)p->grid_size) * (double)p->grid_size;
+    const double bxy = (double)p->arena_size / sqrt(2.0) - 0.1;
+    const int A = p->num_agents, C = p->num_cylinders;
+    int j = 0;
+    for (int o = 0; o < A + 1; ++o) {
+        B.lo[j] = (float)-bxy; B.hi[j++] = (float)bxy;
+        B.lo[j] = (float)-bxy; B.hi[j++] = (float)bxy;
+        B.lo[j] = (float)((double)p->max_height - 0.1); B.hi[j++] = (float)((double)p->max_height + 0.1);
+    }
+    for (int o = 0; o < C; ++o) {
+        B.lo[j] = (float)-cb; B.hi[j++] = (float)cb;
+        B.lo[j] = (float)-cb; B.hi[j++] = (float)cb;
+        B.lo[j] = -20.0f; B.hi[j++] = (float)((double)p->max_height / 2.0);
+    }
+    const unsigned grid = (unsigned)((num_tasks + 127) / 128);
+    hs_gen_sample_nearby_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*p, B, history, n_history, num_tasks, epoch, tasks_out, valid_out);
+    CUDA_OK(cudaGetLastError());
+    return HS_OK;
+}
+
+int64_t hs_fps_scratch_bytes(int64_t n) { return n * 4 + 8192; }
+
+int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start, int32_t* idx_out, void* scratch, void* stream) {
+    if (!points || !idx_out || !scratch) return set_err(HS_ERR_INVALID, "hs_fps: null argument%s");
+    if (n < 1 || n > 0x7FFFFFFFll || dim < 1 || dim > 64 || k < 1 || k > n || start < 0 || start >= n)
+        return set_err(HS_ERR_INVALID, "hs_fps: need 1 <= k <= n, 1 <= dim <= 64, 0 <= start < n%s");
+    int dev = 0, sms = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int G = (int)min((int64_t)sms, (n + FPS_THREADS - 1) / FPS_THREADS);
+    if (G > 256) G = 256;                                    // slots: 2 x 256 x 8 B of the scratch tail
+    int chunk = (int)((n + G - 1) / G);
+    size_t smem = (size_t)chunk * dim * sizeof(float);
+    int cache = 1;
+    if (smem > 200 * 1024) { smem = 0; cache = 0; }
+    CUDA_OK(cudaFuncSetAttribute(hs_fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaStream_t s = (cudaStream_t)stream;
+    float* mind = reinterpret_cast<float*>(scratch);
+    uint8_t* tail = reinterpret_cast<uint8_t*>(scratch) + ((n * 4 + 15) / 16) * 16;
+    unsigned int* bar = reinterpret_cast<unsigned int*>(tail);
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(tail + 64);
+    CUDA_OK(cudaMemsetAsync(tail, 0, 64, s));
+    int ni = (int)n;
+    void* args[] = {(void*)&points, (void*)&ni, (void*)&dim, (void*)&k, (void*)&start, (void*)&chunk, (void*)&cache,
+                    (void*)&idx_out, (void*)&mind, (void*)&slots, (void*)&bar};
+    CUDA_OK(cudaLaunchCooperativeKernel((const void*)hs_fps_kernel, dim3(G), dim3(FPS_THREADS), args, smem, s));
     return HS_OK;
 }
 

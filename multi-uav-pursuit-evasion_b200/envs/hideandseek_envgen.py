@@ -138,6 +138,101 @@ class GenBuffer:
         return out
 
 
+class GenBufferDevice:
+    """The same archive with everything resident on the GPU: tasks, weights
+    and the archive are device tensors; the two loops that are host work in the reference run as
+    kernels - `samplenearby` (hideandseek_envgen.py:322-372, a Python loop over tasks with up to
+    ten numpy retries each) is hs_gen_sample_nearby, the archive cap (:300-314,
+    dgl.geometry.farthest_point_sampler) is hs_fps.  Same interface as GenBuffer; arrays are
+    torch tensors instead of numpy arrays."""
+
+    def __init__(self, num_agents: int, num_cylinders: int, arena_size=0.9, cylinder_size=0.1, max_height=1.2,
+                 buffer_length: int = 5000, seed: int = 0, device="cuda:0"):
+        import ctypes as C
+        from .. import _lib
+        self._C, self._lib = C, _lib
+        self.device = torch.device(device)
+        self.num_agents, self.num_cylinders = num_agents, num_cylinders
+        self.task_dim = 3 * num_agents + 3 + 3 * num_cylinders
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self._history_buffer, self._state_buffer, self._weight_buffer = z(0, self.task_dim), z(0, self.task_dim), z(0, 1)
+        self._temp_state_buffer, self._temp_weight_buffer = [], []
+        self.buffer_length, self.eps = buffer_length, 1e-5
+        self.params = _lib.hs_gen_params()
+        self.params.num_agents, self.params.num_cylinders = num_agents, num_cylinders
+        self.params.arena_size, self.params.grid_size, self.params.max_height = arena_size, 2 * cylinder_size, max_height
+        self.params.num_grid = int(arena_size * 2 / (2 * cylinder_size))
+        self.params.seed = int(seed) & (2 ** 64 - 1)
+        self.epoch = 0
+        self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- archive bookkeeping ---------------------------------------------------------------
+    def insert(self, states: torch.Tensor):
+        self._temp_state_buffer.append(states.detach().to(self.device, torch.float32).clone())
+
+    def insert_weights(self, weights: torch.Tensor):
+        self._temp_weight_buffer.append(weights.detach().float().reshape(-1, 1).clone())
+
+    def update(self):
+        self._state_buffer = torch.cat(self._temp_state_buffer)
+        self._weight_buffer = torch.stack(self._temp_weight_buffer, dim=-1).mean(-1)
+        self._temp_state_buffer, self._temp_weight_buffer = [], []
+
+    def fps(self, points: torch.Tensor, k: int, start: int = 0) -> torch.Tensor:
+        pts = points.to(self.device, torch.float32).contiguous()
+        n, dim = pts.shape
+        k = min(k, n)
+        idx = torch.empty(k, dtype=torch.int32, device=self.device)
+        scratch = torch.empty(int(self._lib.lib.hs_fps_scratch_bytes(n)), dtype=torch.uint8, device=self.device)
+        self._lib.check(self._lib.lib.hs_fps(pts.data_ptr(), n, dim, k, start, idx.data_ptr(), scratch.data_ptr(),
+                                             self._stream()), "hs_fps")
+        self._keep = (pts, scratch)
+        return idx.long()
+
+    def insert_history(self, states: torch.Tensor):
+        if states.shape[0] == 0:
+            return
+        all_states = torch.cat([self._history_buffer, states.to(self.device, torch.float32)])
+        if all_states.shape[0] > self.buffer_length:
+            lo, hi = all_states.min(0).values, all_states.max(0).values
+            normed = (all_states - lo) / (hi - lo + self.eps)
+            all_states = all_states[self.fps(normed, self.buffer_length)]
+        self._history_buffer = all_states
+
+    def save_task(self, model_dir, episode):
+        np.save(os.path.join(model_dir, f"history_{episode}.npy"), self._history_buffer.cpu().numpy())
+
+    # -- sampling --------------------------------------------------------------------------
+    def sample(self, num_tasks):
+        idx = torch.randint(0, self._history_buffer.shape[0], (num_tasks,), device=self.device, generator=self.gen)
+        return self._history_buffer[idx]
+
+    def samplenearby(self, num_tasks, expand_cylinders, expand_step, return_valid: bool = False):
+        C = self._C
+        self.epoch += 1
+        self.params.expand_cylinders, self.params.expand_step = int(bool(expand_cylinders)), float(expand_step)
+        hist = self._history_buffer.contiguous()
+        out = torch.empty(num_tasks, self.task_dim, dtype=torch.float32, device=self.device)
+        valid = torch.empty(num_tasks, dtype=torch.uint8, device=self.device)
+        self._lib.check(self._lib.lib.hs_gen_sample_nearby(C.byref(self.params), hist.data_ptr(), hist.shape[0], num_tasks,
+                                                           C.c_uint64(self.epoch), out.data_ptr(), valid.data_ptr(),
+                                                           self._stream()), "hs_gen_sample_nearby")
+        self._keep2 = hist
+        if return_valid:
+            return out, valid.bool()
+        ok = valid.bool()
+        # rows whose ten attempts all failed are re-drawn from the accepted ones (:361-366); no host sync:
+        # a random accepted row per slot, used only where needed
+        n_ok = ok.sum()
+        order = torch.argsort((~ok).to(torch.uint8), stable=True)                  # accepted rows first
+        pick = (torch.rand(num_tasks, device=self.device, generator=self.gen) * n_ok.clamp(min=1)).long()
+        fallback = torch.where(n_ok > 0, out[order[pick]], hist[0].expand_as(out))
+        return torch.where(ok.unsqueeze(-1), out, fallback)
+
+
 class HideAndSeek_envgen(HideAndSeek):
     VARIANT_ENVGEN = True
     EXTRA_STATS = ("success_buffer", "success_unif", "history_buffer", "add_history", "ratio_unif")
@@ -153,8 +248,14 @@ class HideAndSeek_envgen(HideAndSeek):
         self.update_iter = 0
         self.num_unif = self.num_envs
         seed = int(self.cfg.seed or 0)
-        self.gen_buffer = GenBuffer(self.num_agents, self.num_cylinders, t.arena_size, t.cylinder.size, t.max_height,
-                                    rng=np.random.default_rng(seed))
+        # env.device_generator=1 (default): archive, perturbation sampler and FPS on the GPU
+        self.device_generator = True if self.cfg.env.device_generator is None else bool(self.cfg.env.device_generator)
+        if self.device_generator:
+            self.gen_buffer = GenBufferDevice(self.num_agents, self.num_cylinders, t.arena_size, t.cylinder.size,
+                                              t.max_height, seed=seed, device=self.device)
+        else:
+            self.gen_buffer = GenBuffer(self.num_agents, self.num_cylinders, t.arena_size, t.cylinder.size, t.max_height,
+                                        rng=np.random.default_rng(seed))
         self.all_tasks = None
         self._host_progress = 0
 
@@ -181,14 +282,25 @@ class HideAndSeek_envgen(HideAndSeek):
             self.num_unif = n - num_buffer
             unif = torch.cat([base["drone_pos"][:self.num_unif].reshape(self.num_unif, -1),
                               base["target_pos"][:self.num_unif].reshape(self.num_unif, -1),
-                              base["cyl_pos"][:self.num_unif].reshape(self.num_unif, -1)], dim=-1).cpu().numpy()
-            if num_buffer > 0:
-                near = self.gen_buffer.samplenearby(num_buffer, self.expand_cylinders, self.expand_step)
-                self.all_tasks = np.concatenate([unif, near])
+                              base["cyl_pos"][:self.num_unif].reshape(self.num_unif, -1)], dim=-1)
+            if self.device_generator:                          # everything stays on the GPU
+                if num_buffer > 0:
+                    near = self.gen_buffer.samplenearby(num_buffer, self.expand_cylinders, self.expand_step)
+                    self.all_tasks = torch.cat([unif, near])
+                else:
+                    self.all_tasks = unif.clone()
             else:
-                self.all_tasks = unif
+                unif = unif.cpu().numpy()
+                if num_buffer > 0:
+                    near = self.gen_buffer.samplenearby(num_buffer, self.expand_cylinders, self.expand_step)
+                    self.all_tasks = np.concatenate([unif, near])
+                else:
+                    self.all_tasks = unif
             self.gen_buffer.insert(self.all_tasks)
-        tasks = torch.from_numpy(np.ascontiguousarray(self.all_tasks)).to(dev).float()
+        if self.device_generator:
+            tasks = self.all_tasks
+        else:
+            tasks = torch.from_numpy(np.ascontiguousarray(self.all_tasks)).to(dev).float()
         base["drone_pos"] = tasks[:, :3 * A].reshape(n, A, 3)
         base["target_pos"] = tasks[:, 3 * A:3 * A + 3].reshape(n, 3)
         base["cyl_pos"] = tasks[:, 3 * A + 3:].reshape(n, -1, 3)
@@ -230,12 +342,21 @@ class HideAndSeek_envgen(HideAndSeek):
             return
         self.update_iter = 0
         self.gen_buffer.update()
-        active = self.active_cylinders.reshape(-1).cpu().numpy()
         w = self.gen_buffer._weight_buffer.reshape(-1)
-        for i in range(self.num_cylinders + 1):
-            sel = active == i
-            self.stats[f"ratio_cylinders_{i}"].fill_(float(sel.mean()))
-            self.stats[f"success_cylinders_{i}"].fill_(float(w[sel].mean()) if sel.any() else 0.0)
+        if self.device_generator:
+            active = self.active_cylinders.reshape(-1)
+            wd = w.to(active.device)
+            for i in range(self.num_cylinders + 1):            # device-side means, no host sync
+                sel = (active == i).float()
+                cnt = sel.sum()
+                self.stats[f"ratio_cylinders_{i}"].fill_(0).add_(cnt / sel.numel())
+                self.stats[f"success_cylinders_{i}"].fill_(0).add_((wd * sel).sum() / cnt.clamp(min=1))
+        else:
+            active = self.active_cylinders.reshape(-1).cpu().numpy()
+            for i in range(self.num_cylinders + 1):
+                sel = active == i
+                self.stats[f"ratio_cylinders_{i}"].fill_(float(sel.mean()))
+                self.stats[f"success_cylinders_{i}"].fill_(float(w[sel].mean()) if sel.any() else 0.0)
         keep = (w <= self.R_max) & (w >= self.R_min)
         self.gen_buffer.insert_history(self.gen_buffer._state_buffer[keep])
-        self.stats["add_history"].fill_(float(keep.sum()))
+        self.stats["add_history"].fill_(0).add_(torch.as_tensor(keep.sum(), device=self.stats["add_history"].device))

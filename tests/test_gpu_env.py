@@ -205,20 +205,23 @@ def test_hover_plumbing_config():
     env.close()
 
 
-def test_envgen_control_plane():
+@pytest.mark.parametrize("devgen", [1, 0], ids=["device_generator", "host_generator"])
+def test_envgen_control_plane(devgen):
     """HideAndSeek_envgen: uniform tasks on a prefix, archive fed every eval_iter episodes
     (hideandseek_envgen.py:875-899, 1302-1333), same tick kernels with the variant flags."""
     import mupe_b200 as m
     E, L = 64, 4
     cfg = m.compose("HideAndSeek_envgen", "mappo", overrides={
         "task.env.num_envs": E, "task.sim.device": DEV, "task.env.max_episode_length": L,
-        "task.eval_iter": 2, "task.R_min": 0.0, "task.R_max": 1.0, "task.catch_radius": 5.0})
+        "task.eval_iter": 2, "task.R_min": 0.0, "task.R_max": 1.0, "task.catch_radius": 5.0,
+        "task.env.device_generator": devgen})
     base = m.IsaacEnv.REGISTRY["HideAndSeek_envgen"](cfg, headless=True)
+    assert base.device_generator == bool(devgen)
     env = m.TransformedEnv(base, m.Compose(m.InitTracker(), m.PIDRateController()))
     assert ("stats", "ratio_cylinders_5") in base.observation_spec.keys(True, True)
     td = env.reset()
     assert base.num_unif == E and base.gen_buffer._history_buffer.shape[0] == 0
-    tasks0 = base.all_tasks.copy()
+    tasks0 = base.all_tasks.clone() if devgen else base.all_tasks.copy()
     for ep in range(4):
         for t in range(L):
             td.set(("agents", "action"), torch.randn(E, 3, 4, device=DEV) * 0.1)

@@ -18,8 +18,9 @@ import ctypes  # noqa: E402
 
 
 def run(E, dev, peak, reps=20):
-    cfg = mupe_b200.build_hs_config(E)
-    per_batch = bench.algorithmic_bytes()["total"] * E * 1.3
+    C = int(os.environ.get("HS_SWEEP_C", "5"))          # cylinder capacity, all of them active (config 3: 8)
+    cfg = mupe_b200.build_hs_config(E, num_cylinders=C)
+    per_batch = bench.algorithmic_bytes(C=C)["total"] * E * 1.3
     R = max(2, min(16, int(2 * 126e6 / per_batch) + 1))
     torch.manual_seed(0)
     tp = mupe_b200.TP_net(16, 15, 5).to(dev)
@@ -30,8 +31,8 @@ def run(E, dev, peak, reps=20):
         dpos = torch.rand(E, 3, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a + 0.1, 0.5], device=dev)
         tpos = torch.rand(E, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([-a + 0.1, -a + 0.1, 0.5], device=dev)
         rot = torch.zeros(E, 3, 4, device=dev); rot[..., 0] = 1
-        cyl = torch.zeros(E, 5, 3, device=dev)
-        cyl[..., :2] = (torch.randint(-3, 4, (E, 5, 2), device=dev)).float() * 0.2
+        cyl = torch.zeros(E, C, 3, device=dev)
+        cyl[..., :2] = (torch.randint(-3, 4, (E, C, 2), device=dev)).float() * 0.2
         cyl[..., 2] = 0.6
         eng.set_predictor_variant(int(os.environ.get("HS_TP_VARIANT", "-1")))
         eng.reset(None, dpos, rot, tpos, cyl)
@@ -40,8 +41,8 @@ def run(E, dev, peak, reps=20):
         engs.append(eng)
     torch.cuda.synchronize()
     n = max(R, 32 if E <= 65536 else 8)
-    out = {"E": E, "rotating_batches": R}
-    ab = bench.algorithmic_bytes()
+    out = {"E": E, "num_cylinders": C, "rotating_batches": R}
+    ab = bench.algorithmic_bytes(C=C)
     for name, fn, nbytes in (
             ("tick", lambda e, st: check(lib.hs_step_pre(e._h, e.graph_action.data_ptr(), 1, None, st), "pre"), ab["tick"]),
             ("tp_fill", lambda e, st: check(lib.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp)), None, st), "post"), ab["fill"])):
