@@ -359,9 +359,9 @@ def run_gpu_arm(args):
         flops = 2.0 * 256 * (16 * H + 64 * (H - 1)) + 2.0 * 64 * 3 * F          # per env-tick
         simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         tf = flops * E / (tp_us * 1e-6) / 1e12
-        used = variant if variant >= 0 else (3 if E <= 2 * 32 * 148 else 2)
+        used = variant if variant >= 0 else (3 if E <= 32 * 148 else 4)
         kname = {0: "hs_tp_fill_kernel<3>", 1: "hs_tp_fill_mma_kernel<3>", 2: "hs_tp_fill_tc_kernel<3>",
-                 3: "hs_tp_fill_tcn_kernel<3>"}[used]
+                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcp_kernel<3>"}[used]
         if used == 0:
             extra["roofline_predictor"] = {"bound": "fp32 FFMA (SIMT)", "kernel": kname, "achieved": tf,
                                            "peak": simt_peak, "unit": "TFLOP/s", "frac": tf / simt_peak, "launch_us": tp_us,
@@ -430,7 +430,8 @@ def run_gpu_arm(args):
             "predictor_kernel": {-1: "auto -> hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles) at 4096 envs",
                                  0: "hs_tp_fill_kernel (fp32 FFMA)", 1: "hs_tp_fill_mma_kernel (3xTF32 mma.sync)",
                                  2: "hs_tp_fill_tc_kernel (3xTF32 tcgen05, 128-env tiles)",
-                                 3: "hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles)"}[variant],
+                                 3: "hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles)",
+                                 4: "hs_tp_fill_tcp_kernel (3xTF32 tcgen05, 2 x 32-env tiles ping-pong)"}[variant],
         }
         line.update(extra)
         print(json.dumps(line))

@@ -233,12 +233,14 @@ int hs_state_get(hs_handle* h, int field, float* dst, void* stream);
 int hs_state_set(hs_handle* h, int field, const float* src, void* stream);
 /* Number of kernels this handle has launched so far (bench `gpu_launches`). */
 int64_t hs_launch_count(const hs_handle* h);
-/* Tunables.  HS_OPT_PREDICTOR_VARIANT: -1 = auto (default: variant 3 below ~12k envs per launch,
- * variant 2 above), 0 = fp32 FFMA predictor kernel,
+/* Tunables.  HS_OPT_PREDICTOR_VARIANT: -1 = auto (default: variant 3 while a launch has at most one
+ * 32-env tile per SM, variant 4 above), 0 = fp32 FFMA predictor kernel,
  * 1 = tensor-core predictor, warp-level mma.sync (error-compensated 3xTF32, fp32-level results),
  * 2 = tensor-core predictor, tcgen05.mma with TMEM accumulators and TMEM-resident recurrent operand,
  *     128 envs per CTA (envs on the MMA's M dimension),
- * 3 = tcgen05.mma with the gates on M and 32 envs per CTA on N (fills the SMs at small batches). */
+ * 3 = tcgen05.mma with the gates on M, weights resident in TMEM, 32 envs per CTA on N (fills the SMs
+ *     at small batches),
+ * 4 = as 3 with two 32-env tiles ping-ponging per CTA (one tile's MMAs run under the other's cell update). */
 enum { HS_OPT_PREDICTOR_VARIANT = 1 };
 int hs_set_option(hs_handle* h, int option, int value);
 

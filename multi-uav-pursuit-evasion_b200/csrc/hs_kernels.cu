@@ -2011,6 +2011,261 @@ __device__ __forceinline__ bool elect_one() {          // one lane of the (conve
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- pieces shared by the single-tile kernel (hs_tp_fill_tcn_kernel) and the ping-pong kernel
+// (hs_tp_fill_tcp_kernel) -------------------------------------------------------------------------
+struct TnLane {                 // per-thread constants of the epilogue
+    float bias0, bias1;         // exponent-argument biases of the two gate rows behind this TMEM lane
+    float sa, sb;               // second gate = sa + sb / d1: tanh(g) on even lanes (1, -2), sigmoid(o) on odd lanes (0, 1)
+    int unit;
+    bool odd;
+};
+
+// Weights -> TMEM, once per CTA.  (1) coalesced global reads into a staging tile whose row index is
+// already the TMEM lane: row (tile*128 + l) = gate (tile ? (l&1 ? o : g) : (l&1 ? f : i)) of unit l/2, pitch
+// 81 words (odd -> the row-per-lane reads below are conflict-free);  (2) warp (quarter, part cg) writes
+// the 80 k-columns of (M-tile cg>>1, hi|lo = cg&1) of its 32 lanes with tcgen05.st.  The rows are
+// PRE-SCALED by the constant of their activation (-log2 e for the sigmoid gates, +2 log2 e for the tanh
+// gate), so the accumulator already holds the argument of ex2 in the cell update.
+template <int FD>
+__device__ __forceinline__ void tn_stage_weights(const TPParams& W, float* wst, uint32_t lane_base, int row, int cg) {
+    const int tid = threadIdx.x;
+    auto lane_of = [](int wr) { const int g = wr >> 6, u = wr & 63; return (g >> 1) * 128 + 2 * u + (g & 1); };
+#pragma unroll 8
+    for (int i = tid; i < 256 * TP_HID; i += TN_THREADS) {
+        const int wr = i >> 6, k = i & 63;
+        wst[lane_of(wr) * TN_WPITCH + 16 + k] = __ldg(W.w_hh + i);
+    }
+#pragma unroll 8
+    for (int i = tid; i < 256 * 16; i += TN_THREADS) {
+        const int wr = i >> 4, k = i & 15;
+        wst[lane_of(wr) * TN_WPITCH + k] = (k < FD) ? __ldg(W.w_ih + wr * FD + k) : 0.0f;
+    }
+    __syncthreads();
+    const int tl = cg >> 1, want_lo = cg & 1;
+    const float L2E = 1.4426950408889634f;
+    const float scale = (tl == 1 && !(row & 1)) ? 2.0f * L2E : -L2E;         // tile 1, even lane = gate g (tanh)
+    const float* src = wst + (tl * 128 + row) * TN_WPITCH;
+    const uint32_t col0 = TN_COL_A + (uint32_t)(80 * cg);
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {                        // 16 k-columns per tcgen05.st
+        uint32_t vv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t hi, lo;
+            tf32_split(src[16 * ch + k] * scale, hi, lo);
+            vv[k] = want_lo ? lo : hi;
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                     :: "r"(lane_base + col0 + 16 * ch), "r"(vv[0]), "r"(vv[1]), "r"(vv[2]), "r"(vv[3]), "r"(vv[4]), "r"(vv[5]),
+                        "r"(vv[6]), "r"(vv[7]), "r"(vv[8]), "r"(vv[9]), "r"(vv[10]), "r"(vv[11]), "r"(vv[12]), "r"(vv[13]),
+                        "r"(vv[14]), "r"(vv[15]) : "memory");
+    }
+    tc_wait_st();
+}
+
+__device__ __forceinline__ TnLane tn_lane_consts(const TPParams& W, int row) {
+    TnLane L;
+    L.unit = row >> 1;
+    L.odd = (row & 1) != 0;
+    const float L2E = 1.4426950408889634f;
+    const int wr0 = (L.odd ? 64 : 0) + L.unit, wr1 = (L.odd ? 192 : 128) + L.unit;
+    L.bias0 = -L2E * (__ldg(W.b_ih + wr0) + __ldg(W.b_hh + wr0));
+    L.bias1 = (L.odd ? -L2E : 2.0f * L2E) * (__ldg(W.b_ih + wr1) + __ldg(W.b_hh + wr1));
+    L.sa = L.odd ? 0.0f : 1.0f;
+    L.sb = L.odd ? 1.0f : -2.0f;
+    return L;
+}
+
+// x of all H steps of one 32-env tile -> B operand (tf32 hi/lo): lane = (env & 7) + 8 * (k & 3) per core
+// matrix, so the 32 stores of a warp cover 128 contiguous bytes; loads are issued ten at a time.
+template <int FD>
+__device__ __forceinline__ void tn_stage_x(const float* __restrict__ tp_input, int64_t e0, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane & 7, kk = lane >> 3;
+    constexpr int NW = TN_THREADS / 32, BATCH = 10;
+    for (int b0 = warp; b0 < H * 16; b0 += NW * BATCH) {
+        float xv[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {                  // DRAM latency paid once per batch
+            const int cm = b0 + u * NW;
+            const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
+            const int n = ng * 8 + rr, k = kc * 4 + kk;
+            xv[u] = 0.0f;
+            if (cm < H * 16 && n < nenv && k < FD) xv[u] = __ldg(tp_input + (e0 + n) * (int64_t)(H * FD) + s * FD + k);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int cm = b0 + u * NW;
+            if (cm < H * 16) {
+                const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
+                uint32_t hi, lo;
+                tf32_split(xv[u], hi, lo);
+                const uint32_t off = s * TN_X_STEP + kc * TN_X_LBO + ng * TN_SBO + rr * 16 + kk * 4;
+                *reinterpret_cast<uint32_t*>(Xhi + off) = hi;
+                *reinterpret_cast<uint32_t*>(Xlo + off) = lo;
+            }
+        }
+    }
+}
+
+// Cell update of one LSTM step for this thread's 8 env columns.  Lane pair (l, l^1) = one hidden unit:
+// the even lane holds the ex2 arguments of gates i, g, the odd lane those of f, o and the cell state.
+// Per column and lane: 2 ex2 + 1 shared rcp for the two gates; tanh(c) of two columns is split between
+// the two lanes (ex2 + rcp each).  h goes to the B operand buffer as tf32 hi/lo.
+__device__ __forceinline__ void tn_epilogue(uint32_t d_taddr, const TnLane& L, int cg, float (&cst)[8], uint8_t* Hhi, uint8_t* Hlo) {
+    uint32_t v0[8], v1[8];
+    tc_ld8_nowait(d_taddr + (uint32_t)(cg * 8), v0);
+    tc_ld8_nowait(d_taddr + (uint32_t)(TN_E + cg * 8), v1);
+    tc_wait_ld();
+    const float T2 = 2.8853900817779268f;              // 2 log2 e
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+        float gb[2], cc[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int n = 2 * np + q;
+            const float a0 = fminf(__uint_as_float(v0[n]) + L.bias0, 60.f);      // upper clamp only: ex2(-inf) = 0 is fine
+            const float a1 = fminf(__uint_as_float(v1[n]) + L.bias1, 60.f);
+            const float d0 = 1.0f + fex2(a0), d1 = 1.0f + fex2(a1);
+            const float r = frcp(d0 * d1);                                        // <= 2^120: no overflow
+            const float ga = r * d1;                       // sigmoid(i) | sigmoid(f)
+            gb[q] = fmaf(L.sb, r * d0, L.sa);              // tanh(g) = 1 - 2/d1 | sigmoid(o) = 1/d1
+            const float ig = __shfl_xor_sync(0xffffffffu, ga * gb[q], 1);          // even lane: sigmoid(i) * tanh(g)
+            cst[n] = fmaf(ga, cst[n], ig);                 // (odd lanes) c = f*c + i*g
+            cc[q] = cst[n];
+        }
+        // tanh(c) of the two columns: the odd lane keeps column 2np, its even partner takes column 2np+1
+        const float other = __shfl_xor_sync(0xffffffffu, cc[1], 1);
+        const float tin = L.odd ? cc[0] : other;
+        const float th = 1.0f - 2.0f * frcp(1.0f + fex2(T2 * tin));               // |c| <= H: no overflow
+        const float thb = __shfl_xor_sync(0xffffffffu, th, 1);
+        if (L.odd) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float hval = gb[q] * (q == 0 ? th : thb);
+                const int n = cg * 8 + 2 * np + q;
+                uint32_t hh, hl;
+                tf32_split(hval, hh, hl);
+                const uint32_t off = (L.unit >> 2) * TN_H_LBO + (n >> 3) * TN_SBO + (n & 7) * 16 + (L.unit & 3) * 4;
+                *reinterpret_cast<uint32_t*>(Hhi + off) = hh;
+                *reinterpret_cast<uint32_t*>(Hlo + off) = hl;
+            }
+        }
+    }
+}
+
+// FC + tanh from the final h (hi + lo in shared memory), then the state_self / state_drones rows of the tile.
+template <int A>
+__device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, int64_t e0, int nenv, const uint8_t* Hhi,
+                                           const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf) {
+    const hs_config& c = P.c;
+    const int F3 = 3 * c.future_step, D = 20 + F3, E = c.num_envs;
+    const int tid = threadIdx.x;
+    {
+        const int n = tid & 31;
+        for (int og = tid >> 5; og < F3; og += TN_THREADS / 32) {
+            float a0 = fcb[og];
+            const float* w0 = fcw + og * TP_HID;
+#pragma unroll 4
+            for (int kc = 0; kc < TP_HID / 4; ++kc) {
+                const float4 hh = *reinterpret_cast<const float4*>(Hhi + kc * TN_H_LBO + n * 16);
+                const float4 hl = *reinterpret_cast<const float4*>(Hlo + kc * TN_H_LBO + n * 16);
+                a0 = fmaf(w0[4 * kc], hh.x + hl.x, a0); a0 = fmaf(w0[4 * kc + 1], hh.y + hl.y, a0);
+                a0 = fmaf(w0[4 * kc + 2], hh.z + hl.z, a0); a0 = fmaf(w0[4 * kc + 3], hh.w + hl.w, a0);
+            }
+            const float pv = tanhf(a0);
+            preds[n * F3 + og] = pv;
+            if (W.pred_out != nullptr && n < nenv) W.pred_out[(e0 + n) * F3 + og] = pv;
+        }
+    }
+    __syncthreads();
+    V3 t_rpos = mk(0.f, 0.f, 0.f);
+    float* r1 = nullptr;
+    if (tid < TN_E * A) {
+        const int slot = tid / TN_E, el = tid - slot * TN_E;
+        const bool valid = el < nenv;
+        const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
+        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
+        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+        const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+        const float progress = *EROW(E_PROGRESS);
+        const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+        V3 heading, up;
+        heading_up(q, heading, up);
+        const float tfrac = fdiv(progress, (float)c.max_episode_length);
+        t_rpos = p - tp;
+        const float mv = c.mask_value;
+        const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
+        r1 = rowbuf + (el * A + slot) * D;
+        r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+        const float* pr = preds + el * F3;
+        for (int f = 0; f < c.future_step; ++f) {
+            const float px = (pr[3 * f] * 0.5f) * c.arena_size;
+            const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
+            const float pz = ((pr[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
+            r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+        }
+        const int o = 3 + F3;
+        const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
+                                up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
+#pragma unroll
+        for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
+    }
+    const int nwords = nenv * A * D;
+    float* g1 = P.b.state_self + e0 * A * D;
+    float* g2 = P.b.state_drones + e0 * A * D;
+    const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float* gdst = pass == 0 ? g1 : g2;
+        if (pass == 1 && r1 != nullptr) { r1[0] = t_rpos.x; r1[1] = t_rpos.y; r1[2] = t_rpos.z; }
+        if (bulk) {
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < nwords; i += TN_THREADS) gdst[i] = rowbuf[i];
+        }
+        __syncthreads();
+    }
+}
+
+// MMA issue helpers: one elected thread per M-tile; all operands warp-uniform, every descriptor is base + immediate.
+struct TnIssue {
+    uint32_t aA_hi, aA_lo;      // TMEM column addresses of this issuer's weight tile (hi, lo)
+    uint32_t idesc;
+    __device__ __forceinline__ void x_part(uint32_t d, uint64_t dX_hi, uint64_t dX_lo, uint32_t first_acc) const {   // 6 MMAs
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)                // small terms first: A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 8 * j,
+                          ((pass == 1) ? dX_lo : dX_hi) + (uint64_t)((2 * j * TN_X_LBO) >> 4), idesc, (pass | j) ? 1u : first_acc);
+    }
+    __device__ __forceinline__ void h_part(uint32_t d, uint64_t dH_hi, uint64_t dH_lo) const {                         // 24 MMAs
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+            for (int j = 0; j < TP_HID / 8; ++j)
+                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 16 + 8 * j,
+                          ((pass == 1) ? dH_lo : dH_hi) + (uint64_t)((2 * j * TN_H_LBO) >> 4), idesc, 1u);
+    }
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& phase) {
+    uint32_t spins = 0;                                     // bounded: a wrong descriptor must not hang the box
+    while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
+    phase ^= 1;
+}
+
 template <int A>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
@@ -2019,13 +2274,10 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
     constexpr int FD = 7 + 3 * A;
     const int H = c.history_step;
     const int F3 = 3 * c.future_step;
-    const int D = 20 + F3;
     const int E = c.num_envs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;            // TMEM lane = gate row of both M-tiles
     const int cg = warp >> 2;                          // env columns [8*cg, 8*cg+8) of the tile
-    const int unit = row >> 1;
-    const bool odd = (row & 1) != 0;                   // odd lanes: gates f,o and the cell state; even lanes: gates i,g
     const int ntiles = (E + TN_E - 1) / TN_E;
 
     uint8_t* Hhi = smem_raw;                                   // [16 K chunks (528 B)][4][8][4]
@@ -2050,117 +2302,33 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
     }
     for (int i = tid; i < F3 * TP_HID; i += TN_THREADS) fcw[i] = __ldg(W.fc_w + i);
     if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
-    const int wr0 = (odd ? 64 : 0) + unit, wr1 = (odd ? 192 : 128) + unit;      // weight rows behind this lane
-    const float bias0 = __ldg(W.b_ih + wr0) + __ldg(W.b_hh + wr0);
-    const float bias1 = __ldg(W.b_ih + wr1) + __ldg(W.b_hh + wr1);
+    const TnLane L = tn_lane_consts(W, row);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    // ---- weights -> TMEM, once per CTA.  (1) coalesced global reads into a staging tile whose row
-    // index is already the TMEM lane: row (tile*128 + l) = gate (tile ? (l&1 ? o : g) : (l&1 ? f : i)) of unit l/2,
-    // pitch 81 words (odd -> the row-per-lane reads below are conflict-free);  (2) warp (quarter, part cg)
-    // writes the 80 k-columns of (M-tile cg>>1, hi|lo = cg&1) of its 32 lanes with tcgen05.st.
-    {
-        auto lane_of = [](int wr) { const int g = wr >> 6, u = wr & 63; return (g >> 1) * 128 + 2 * u + (g & 1); };
-#pragma unroll 8
-        for (int i = tid; i < 256 * TP_HID; i += TN_THREADS) {
-            const int wr = i >> 6, k = i & 63;
-            wst[lane_of(wr) * TN_WPITCH + 16 + k] = __ldg(W.w_hh + i);
-        }
-#pragma unroll 8
-        for (int i = tid; i < 256 * 16; i += TN_THREADS) {
-            const int wr = i >> 4, k = i & 15;
-            wst[lane_of(wr) * TN_WPITCH + k] = (k < FD) ? __ldg(W.w_ih + wr * FD + k) : 0.0f;
-        }
-        __syncthreads();
-        const int want_lo = cg & 1;
-        const float* src = wst + ((cg >> 1) * 128 + row) * TN_WPITCH;
-        const uint32_t col0 = TN_COL_A + (uint32_t)(80 * cg);
-#pragma unroll
-        for (int ch = 0; ch < 5; ++ch) {                        // 16 k-columns per tcgen05.st
-            uint32_t vv[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                uint32_t hi, lo;
-                tf32_split(src[16 * ch + k], hi, lo);
-                vv[k] = want_lo ? lo : hi;
-            }
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                         :: "r"(lane_base + col0 + 16 * ch), "r"(vv[0]), "r"(vv[1]), "r"(vv[2]), "r"(vv[3]), "r"(vv[4]), "r"(vv[5]),
-                            "r"(vv[6]), "r"(vv[7]), "r"(vv[8]), "r"(vv[9]), "r"(vv[10]), "r"(vv[11]), "r"(vv[12]), "r"(vv[13]),
-                            "r"(vv[14]), "r"(vv[15]) : "memory");
-        }
-        tc_wait_st();
-    }
+    tn_stage_weights<FD>(W, wst, lane_base, row, cg);
     const uint32_t bar = smem_u32(mbar);
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
     uint32_t phase = 0;
 
-    // Two issuing threads (one elected lane of warps 0 and 1), one per M-tile: the MMAs of a tile are
-    // issued in order by one thread, the two tiles' accumulators are independent.  Fully unrolled and
-    // warp-uniform: every descriptor is base + immediate in uniform registers.
+    // (warp index and TMEM base are made provably warp-uniform so that the descriptors live in uniform registers)
     const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const bool issue_warp = warp_u < 2;
     const uint32_t mytl = warp_u & 1u;
-    const uint32_t aA_hi = tmem_u + TN_COL_A + 160 * mytl, aA_lo = aA_hi + 80;
+    TnIssue I;
+    I.aA_hi = tmem_u + TN_COL_A + 160 * mytl;
+    I.aA_lo = I.aA_hi + 80;
+    I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t dH_hi = tc_desc(smem_u32(Hhi), TN_H_LBO, TN_SBO), dH_lo = tc_desc(smem_u32(Hlo), TN_H_LBO, TN_SBO);
     const uint64_t dX_hi = tc_desc(smem_u32(Xhi), TN_X_LBO, TN_SBO), dX_lo = tc_desc(smem_u32(Xlo), TN_X_LBO, TN_SBO);
     const uint32_t d_mine = tmem_u + mytl * TN_E;
-    auto issue_x = [&](int dbuf, int s) {                 // D[dbuf] = W_ih * x_s   (6 MMAs, the first overwrites)
-        const uint32_t d = d_mine + (uint32_t)(dbuf * 2 * TN_E);
-        const uint64_t xo = (uint64_t)(((uint32_t)s * TN_X_STEP) >> 4);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass)                // small terms first: A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 8 * j,
-                          ((pass == 1) ? dX_lo : dX_hi) + xo + (uint64_t)((2 * j * TN_X_LBO) >> 4), idesc, (pass | j) ? 1u : 0u);
-    };
-    auto issue_h = [&](int dbuf) {                        // D[dbuf] += W_hh * h   (24 MMAs)
-        const uint32_t d = d_mine + (uint32_t)(dbuf * 2 * TN_E);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-            for (int j = 0; j < TP_HID / 8; ++j)
-                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 16 + 8 * j,
-                          ((pass == 1) ? dH_lo : dH_hi) + (uint64_t)((2 * j * TN_H_LBO) >> 4), idesc, 1u);
-    };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TN_E;
         const int nenv = (int)min((int64_t)TN_E, E - e0);
-        // ---- x of all H steps -> B operand (tf32 hi/lo): lane = (env & 7) + 8 * (k & 3) per core matrix,
-        // so the 32 stores of a warp cover 128 contiguous bytes
-        {
-            const int rr = lane & 7, kk = lane >> 3;
-            constexpr int NW = TN_THREADS / 32, BATCH = 10;
-            for (int b0 = warp; b0 < H * 16; b0 += NW * BATCH) {
-                float xv[BATCH];
-#pragma unroll
-                for (int u = 0; u < BATCH; ++u) {              // DRAM latency paid once per batch
-                    const int cm = b0 + u * NW;
-                    const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
-                    const int n = ng * 8 + rr, k = kc * 4 + kk;
-                    xv[u] = 0.0f;
-                    if (cm < H * 16 && n < nenv && k < FD) xv[u] = __ldg(P.b.tp_input + (e0 + n) * (int64_t)(H * FD) + s * FD + k);
-                }
-#pragma unroll
-                for (int u = 0; u < BATCH; ++u) {
-                    const int cm = b0 + u * NW;
-                    if (cm < H * 16) {
-                        const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
-                        uint32_t hi, lo;
-                        tf32_split(xv[u], hi, lo);
-                        const uint32_t off = s * TN_X_STEP + kc * TN_X_LBO + ng * TN_SBO + rr * 16 + kk * 4;
-                        *reinterpret_cast<uint32_t*>(Xhi + off) = hi;
-                        *reinterpret_cast<uint32_t*>(Xlo + off) = lo;
-                    }
-                }
-            }
-        }
+        tn_stage_x<FD>(P.b.tp_input, e0, nenv, H, Xhi, Xlo);
         float cst[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) cst[j] = 0.f;
@@ -2169,149 +2337,29 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
         __syncthreads();
         if (issue_warp && elect_one()) {
             tc_fence_after();
-            issue_x(0, 0);
+            I.x_part(d_mine, dX_hi, dX_lo, 0u);
         }
         for (int s = 0; s < H; ++s) {
             const int dbuf = s & 1;
             if (issue_warp && elect_one()) {
                 if (s > 0) {
                     tc_fence_after();
-                    issue_h(dbuf);                       // += W_hh * h_{s-1}
+                    I.h_part(d_mine + (uint32_t)(dbuf * 2 * TN_E), dH_hi, dH_lo);   // += W_hh * h_{s-1}
                 }
                 tc_commit(bar);
-                if (s + 1 < H) issue_x(dbuf ^ 1, s + 1); // input half of the next step, under this epilogue
+                if (s + 1 < H) {                         // input half of the next step, under this epilogue
+                    const uint64_t xo = (uint64_t)(((uint32_t)(s + 1) * TN_X_STEP) >> 4);
+                    I.x_part(d_mine + (uint32_t)((dbuf ^ 1) * 2 * TN_E), dX_hi + xo, dX_lo + xo, 0u);
+                }
             }
-            {
-                uint32_t spins = 0;
-                while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
-                phase ^= 1;
-            }
+            mbar_wait(bar, phase);
             tc_fence_after();
-            // ---- epilogue: lane pair (l, l^1) = one hidden unit, 8 env columns per thread -----------------
-            uint32_t v0[8], v1[8];
-            tc_ld8_nowait(lane_base + (uint32_t)(dbuf * 2 * TN_E + cg * 8), v0);
-            tc_ld8_nowait(lane_base + (uint32_t)(dbuf * 2 * TN_E + TN_E + cg * 8), v1);
-            tc_wait_ld();
-            const float L2E = 1.4426950408889634f;
-            const float k1 = odd ? -L2E : 2.0f * L2E;    // second gate: sigmoid(o) on odd lanes, tanh(g) on even lanes
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                float gb[2], cc[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int n = 2 * np + q;
-                    float z0 = __uint_as_float(v0[n]) + bias0, z1 = __uint_as_float(v1[n]) + bias1;
-                    z0 = fminf(fmaxf(z0, -15.f), 15.f);
-                    z1 = fminf(fmaxf(z1, -15.f), 15.f);
-                    const float d0 = 1.0f + fex2(-L2E * z0), d1 = 1.0f + fex2(k1 * z1);
-                    const float r = frcp(d0 * d1);
-                    const float ga = r * d1;                       // sigmoid(i) | sigmoid(f)
-                    const float r1 = r * d0;                       // 1/d1
-                    gb[q] = odd ? r1 : 1.0f - 2.0f * r1;           // sigmoid(o) | tanh(g)
-                    const float pr = ga * gb[q];                   // even: sigmoid(i) * tanh(g)
-                    const float ig = __shfl_xor_sync(0xffffffffu, pr, 1);
-                    cst[n] = fmaf(ga, cst[n], ig);                 // (odd lanes) c = f*c + i*g
-                    cc[q] = fminf(fmaxf(cst[n], -15.f), 15.f);
-                }
-                // tanh(c) of the two columns: the odd lane keeps column 2np, its even partner takes column 2np+1
-                const float other = __shfl_xor_sync(0xffffffffu, cc[1], 1);
-                const float tin = odd ? cc[0] : other;
-                const float th = 1.0f - 2.0f * frcp(1.0f + fex2(2.0f * L2E * tin));
-                const float thb = __shfl_xor_sync(0xffffffffu, th, 1);
-                if (odd) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float hval = gb[q] * (q == 0 ? th : thb);
-                        const int n = cg * 8 + 2 * np + q;
-                        uint32_t hh, hl;
-                        tf32_split(hval, hh, hl);
-                        const uint32_t off = (unit >> 2) * TN_H_LBO + (n >> 3) * TN_SBO + (n & 7) * 16 + (unit & 3) * 4;
-                        *reinterpret_cast<uint32_t*>(Hhi + off) = hh;
-                        *reinterpret_cast<uint32_t*>(Hlo + off) = hl;
-                    }
-                }
-            }
+            tn_epilogue(lane_base + (uint32_t)(dbuf * 2 * TN_E), L, cg, cst, Hhi, Hlo);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
         }
-        // ---- FC + tanh: thread = (env n, output og) ------------------------------------------------------
-        {
-            const int n = tid & 31;
-            for (int og = tid >> 5; og < F3; og += TN_THREADS / 32) {
-                float a0 = fcb[og];
-                const float* w0 = fcw + og * TP_HID;
-#pragma unroll 4
-                for (int kc = 0; kc < TP_HID / 4; ++kc) {
-                    const float4 hh = *reinterpret_cast<const float4*>(Hhi + kc * TN_H_LBO + n * 16);
-                    const float4 hl = *reinterpret_cast<const float4*>(Hlo + kc * TN_H_LBO + n * 16);
-                    a0 = fmaf(w0[4 * kc], hh.x + hl.x, a0); a0 = fmaf(w0[4 * kc + 1], hh.y + hl.y, a0);
-                    a0 = fmaf(w0[4 * kc + 2], hh.z + hl.z, a0); a0 = fmaf(w0[4 * kc + 3], hh.w + hl.w, a0);
-                }
-                const float pv = tanhf(a0);
-                preds[n * F3 + og] = pv;
-                if (W.pred_out != nullptr && n < nenv) W.pred_out[(e0 + n) * F3 + og] = pv;
-            }
-        }
-        __syncthreads();
-        // ---- rows (same as the FFMA variants) -------------------------------------------------------
-        V3 t_rpos = mk(0.f, 0.f, 0.f);
-        float* r1 = nullptr;
-        if (tid < TN_E * A) {
-            const int slot = tid / TN_E, el = tid - slot * TN_E;
-            const bool valid = el < nenv;
-            const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
-            const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
-            Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
-            const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
-            const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
-            const float progress = *EROW(E_PROGRESS);
-            const bool bdetect = *EROW(E_BDETECT) != 0.0f;
-            V3 heading, up;
-            heading_up(q, heading, up);
-            const float tfrac = fdiv(progress, (float)c.max_episode_length);
-            t_rpos = p - tp;
-            const float mv = c.mask_value;
-            const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
-            r1 = rowbuf + (el * A + slot) * D;
-            r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
-            const float* pr = preds + el * F3;
-            for (int f = 0; f < c.future_step; ++f) {
-                const float px = (pr[3 * f] * 0.5f) * c.arena_size;
-                const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
-                const float pz = ((pr[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
-                r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
-            }
-            const int o = 3 + F3;
-            const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
-                                    up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
-#pragma unroll
-            for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
-        }
-        const int nwords = nenv * A * D;
-        float* g1 = P.b.state_self + e0 * A * D;
-        float* g2 = P.b.state_drones + e0 * A * D;
-        const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            float* gdst = pass == 0 ? g1 : g2;
-            if (pass == 1 && r1 != nullptr) { r1[0] = t_rpos.x; r1[1] = t_rpos.y; r1[2] = t_rpos.z; }
-            if (bulk) {
-                fence_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
-                    bulk_commit();
-                    bulk_wait_read<0>();
-                }
-            } else {
-                __syncthreads();
-                for (int i = tid; i < nwords; i += TN_THREADS) gdst[i] = rowbuf[i];
-            }
-            __syncthreads();
-        }
+        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf);
     }
     tc_fence_before();
     __syncthreads();
@@ -2323,6 +2371,141 @@ static size_t tp_tcn_smem_bytes(const hs_config& c) {
     const int F3 = 3 * c.future_step;
     return 2 * (size_t)TN_H_BYTES + ((size_t)F3 * TP_HID + 32) * sizeof(float) + 16 + 2 * (size_t)c.history_step * TN_X_STEP +
            ((size_t)TN_E * 3 * FMAX + (size_t)TN_E * c.num_agents * (20 + 3 * FMAX) + (size_t)256 * TN_WPITCH) * sizeof(float);
+}
+
+// =========================================================================================
+// Ping-pong version of the kernel above for batches with more than one 32-env tile per SM: a CTA
+// advances TWO tiles, alternating epilogue(tile 0) | MMA(tile 1) and epilogue(tile 1) | MMA(tile 0), so
+// the ~0.6 us the tensor pipe needs for the 60 dependent MMAs of a step is hidden behind the other
+// tile's cell update.  Each tile has one accumulator slot (2 M-tiles x 32 columns) and its own
+// mbarrier; the weights in TMEM are shared.  TMEM columns: D slot t at 64*t, weights at 128..447.
+// =========================================================================================
+template <int A>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const hs_config& c = P.c;
+    constexpr int FD = 7 + 3 * A;
+    const int H = c.history_step;
+    const int F3 = 3 * c.future_step;
+    const int E = c.num_envs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane;
+    const int cg = warp >> 2;
+    const int ntiles = (E + TN_E - 1) / TN_E;
+    const int npairs = (ntiles + 1) / 2;
+
+    uint8_t* Hb = smem_raw;                                    // slot t: hi at t*2*TN_H_BYTES, lo right after
+    float* fcw = reinterpret_cast<float*>(Hb + 4 * TN_H_BYTES);
+    float* fcb = fcw + F3 * TP_HID;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint8_t* Xb = reinterpret_cast<uint8_t*>(mbar + 4);        // slot t: hi at t*2*H*TN_X_STEP, lo right after
+    const size_t xslot = 2 * (size_t)H * TN_X_STEP;
+    float* preds = reinterpret_cast<float*>(Xb + 2 * xslot);
+    float* rowbuf = preds + TN_E * 3 * FMAX;
+    float* wst = reinterpret_cast<float*>(Xb);                 // prologue only: aliases the x / preds / row region
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar + 1)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < F3 * TP_HID; i += TN_THREADS) fcw[i] = __ldg(W.fc_w + i);
+    if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
+    const TnLane L = tn_lane_consts(W, row);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    tn_stage_weights<FD>(W, wst, lane_base, row, cg);
+    __syncthreads();                                           // the staging tile is overwritten by x below
+    uint32_t phase[2] = {0u, 0u};
+
+    const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const bool issue_warp = warp_u < 2;
+    const uint32_t mytl = warp_u & 1u;
+    TnIssue I;
+    I.aA_hi = tmem_u + TN_COL_A + 160 * mytl;
+    I.aA_lo = I.aA_hi + 80;
+    I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t d_mine = tmem_u + mytl * TN_E;
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nslots = (2 * pair + 1 < ntiles) ? 2 : 1;
+        float cst[2][8];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cst[t][j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (t < nslots) {
+                const int64_t e0 = (int64_t)(2 * pair + t) * TN_E;
+                tn_stage_x<FD>(P.b.tp_input, e0, (int)min((int64_t)TN_E, E - e0), H, Xb + t * xslot, Xb + t * xslot + (size_t)H * TN_X_STEP);
+            }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (issue_warp && elect_one()) {
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (t < nslots) {
+                    const uint32_t xb = smem_u32(Xb + t * xslot);
+                    I.x_part(d_mine + (uint32_t)(t * 2 * TN_E), tc_desc(xb, TN_X_LBO, TN_SBO),
+                             tc_desc(xb + (uint32_t)H * TN_X_STEP, TN_X_LBO, TN_SBO), 0u);
+                    tc_commit(smem_u32(mbar + t));
+                }
+        }
+        for (int s = 0; s < H; ++s) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (t < nslots) {
+                    uint8_t* Hhi = Hb + t * 2 * TN_H_BYTES;
+                    uint8_t* Hlo = Hhi + TN_H_BYTES;
+                    mbar_wait(smem_u32(mbar + t), phase[t]);
+                    tc_fence_after();
+                    tn_epilogue(lane_base + (uint32_t)(t * 2 * TN_E), L, cg, cst[t], Hhi, Hlo);
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncthreads();
+                    if (s + 1 < H && issue_warp && elect_one()) {     // step s+1 of this tile runs under the other tile's epilogue
+                        tc_fence_after();
+                        const uint32_t xb = smem_u32(Xb + t * xslot) + (uint32_t)(s + 1) * TN_X_STEP;
+                        const uint32_t d = d_mine + (uint32_t)(t * 2 * TN_E);
+                        I.x_part(d, tc_desc(xb, TN_X_LBO, TN_SBO), tc_desc(xb + (uint32_t)H * TN_X_STEP, TN_X_LBO, TN_SBO), 0u);
+                        I.h_part(d, tc_desc(smem_u32(Hhi), TN_H_LBO, TN_SBO), tc_desc(smem_u32(Hlo), TN_H_LBO, TN_SBO));
+                        tc_commit(smem_u32(mbar + t));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (t < nslots) {
+                const int64_t e0 = (int64_t)(2 * pair + t) * TN_E;
+                tn_fc_rows<A>(P, W, e0, (int)min((int64_t)TN_E, E - e0), Hb + t * 2 * TN_H_BYTES, Hb + t * 2 * TN_H_BYTES + TN_H_BYTES,
+                              fcw, fcb, preds, rowbuf);
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+static size_t tp_tcp_smem_bytes(const hs_config& c) {
+    const int F3 = 3 * c.future_step;
+    const size_t region = 4 * (size_t)c.history_step * TN_X_STEP +
+                          ((size_t)TN_E * 3 * FMAX + (size_t)TN_E * c.num_agents * (20 + 3 * FMAX)) * sizeof(float);
+    const size_t wst = (size_t)256 * TN_WPITCH * sizeof(float);
+    return 4 * (size_t)TN_H_BYTES + ((size_t)F3 * TP_HID + 32) * sizeof(float) + 32 + (region > wst ? region : wst);
 }
 
 static size_t tp_smem_bytes(const hs_config& c) {
@@ -2887,6 +3070,14 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
                 default: e = cudaFuncSetAttribute(hs_tp_fill_tcn_kernel<3>, attr, t); break;
             }
         }
+        if (e == cudaSuccess && tp_tcp_smem_bytes(*cfg) <= HS_MAX_DYN_SMEM) {
+            const int t = (int)tp_tcp_smem_bytes(*cfg);
+            switch (cfg->num_agents) {
+                case 1: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<1>, attr, t); break;
+                case 2: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<2>, attr, t); break;
+                default: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<3>, attr, t); break;
+            }
+        }
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
     }
     *out = h;
@@ -2972,15 +3163,26 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     const int64_t wide_tiles = ((int64_t)h->cfg.num_envs + TW_E - 1) / TW_E;
     // auto (-1): the FFMA kernels win while a batch is a single wave of small tiles (one dependent
     // chain per tile, measured crossover ~6k envs); above that the tcgen05 kernel is 2-2.5x faster
-    // auto (-1): while the 32-env tcgen05 tiles (gates on M) are at most two waves (~9.5k envs on 148 SMs)
-    // they win; above that the 128-env tcgen05 tiles do.  The FFMA kernels remain as options 0 (and
-    // the fallback when history_step makes the 32-env tile's shared memory exceed 227 KB).
-    const bool tcn_fits = tp_tcn_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
-    int variant = (h->tp_variant >= 0) ? h->tp_variant : ((h->cfg.num_envs > 2 * TN_E * h->num_sms) ? 2 : 3);
-    if (variant == 3 && !tcn_fits) {
-        if (h->tp_variant == 3) return set_err(HS_ERR_INVALID, "predictor variant 3: history_step too large for the 32-env tile%s");
-        variant = (h->cfg.num_envs >= 6144) ? 2 : 0;
+    // auto (-1): 32-env tcgen05 tiles with the gates on M; one tile per CTA while the batch has at most one
+    // tile per SM (variant 3), two tiles ping-ponging per CTA above that (variant 4).  The 128-env tcgen05
+    // tile (2) and the FFMA kernels (0) remain as options and as the fallback when history_step makes the
+    // 32-env tile's shared memory exceed 227 KB.
+    const bool tcn_fits = tp_tcn_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM, tcp_fits = tp_tcp_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
+    const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
+    int variant = (h->tp_variant >= 0) ? h->tp_variant : ((tiles32 > h->num_sms) ? 4 : 3);
+    if ((variant == 3 && !tcn_fits) || (variant == 4 && !tcp_fits)) {
+        if (h->tp_variant >= 3) return set_err(HS_ERR_INVALID, "predictor variant 3/4: history_step too large for the 32-env tile%s");
+        variant = (variant == 4 && tcn_fits) ? 3 : ((h->cfg.num_envs >= 6144) ? 2 : 0);
     }
+    if (variant == 4) {
+        const size_t smem = tp_tcp_smem_bytes(h->cfg);
+        const unsigned grid = (unsigned)min((tiles32 + 1) / 2, (int64_t)h->num_sms);   // persistent over tile pairs
+        switch (h->cfg.num_agents) {
+            case 1: hs_tp_fill_tcp_kernel<1><<<grid, TN_THREADS, smem, s>>>(P, W); break;
+            case 2: hs_tp_fill_tcp_kernel<2><<<grid, TN_THREADS, smem, s>>>(P, W); break;
+            default: hs_tp_fill_tcp_kernel<3><<<grid, TN_THREADS, smem, s>>>(P, W); break;
+        }
+    } else
     if (variant == 3) {
         const size_t smem = tp_tcn_smem_bytes(h->cfg);
         const unsigned grid = (unsigned)min(((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E, (int64_t)h->num_sms);   // persistent
@@ -3211,7 +3413,7 @@ int hs_set_option(hs_handle* h, int option, int value) {
     if (!h) return set_err(HS_ERR_INVALID, "hs_set_option: null handle%s");
     switch (option) {
         case HS_OPT_PREDICTOR_VARIANT:
-            if (value < -1 || value > 3) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles) or 3 (tcgen05, 32-env tiles)%s");
+            if (value < -1 || value > 4) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles), 3 (tcgen05, 32-env tiles) or 4 (tcgen05, 2 x 32-env tiles ping-pong)%s");
             h->tp_variant = value;
             return HS_OK;
         default:

@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/bench_r1r.json 2> gpurun_out/bench_r1r.err; tail -3 gpurun_out/bench_r1r.err; python - <<'PY'
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "fused_predictor" 2>&1 | tail -4
+for v in 3 4; do HS_TP_VARIANT=$v timeout 300 python tools/sweep.py 4096 8192 16384 65536 1048576 > gpurun_out/sweep_r1s_v$v.jsonl 2> gpurun_out/sweep.err; tail -2 gpurun_out/sweep.err; python -c "
 import json
-d=json.loads(open('gpurun_out/bench_r1r.json').read().strip().splitlines()[-1])
-print('value',d['value'],'e2e',d['e2e']['value']); print('at_scale',d.get('roofline_at_scale'))
-PY
-HS_SWEEP_C=8 timeout 300 python tools/sweep.py 16384 > gpurun_out/sweep_r1r_c8.jsonl 2> gpurun_out/sweep.err; tail -2 gpurun_out/sweep.err; cat gpurun_out/sweep_r1r_c8.jsonl | cut -c1-600
+for l in open('gpurun_out/sweep_r1s_v$v.jsonl'):
+    r=json.loads(l); print('v$v E',r['E'],'tick us',round(r['tick']['us_per_launch'],1),'tp us',round(r['tp_fill']['us_per_launch'],1),'both Menv/s',round(r['tick_plus_tp']['env_steps_per_s']/1e6,1))
+"; done
