@@ -361,7 +361,7 @@ def run_gpu_arm(args):
         tf = flops * E / (tp_us * 1e-6) / 1e12
         used = variant if variant >= 0 else (3 if E <= 32 * 148 else 4)
         kname = {0: "hs_tp_fill_kernel<3>", 1: "hs_tp_fill_mma_kernel<3>", 2: "hs_tp_fill_tc_kernel<3>",
-                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcp_kernel<3>"}[used]
+                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcw_kernel<3>"}[used]
         if used == 0:
             extra["roofline_predictor"] = {"bound": "fp32 FFMA (SIMT)", "kernel": kname, "achieved": tf,
                                            "peak": simt_peak, "unit": "TFLOP/s", "frac": tf / simt_peak, "launch_us": tp_us,
@@ -431,7 +431,7 @@ def run_gpu_arm(args):
                                  0: "hs_tp_fill_kernel (fp32 FFMA)", 1: "hs_tp_fill_mma_kernel (3xTF32 mma.sync)",
                                  2: "hs_tp_fill_tc_kernel (3xTF32 tcgen05, 128-env tiles)",
                                  3: "hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles)",
-                                 4: "hs_tp_fill_tcp_kernel (3xTF32 tcgen05, 2 x 32-env tiles ping-pong)"}[variant],
+                                 4: "hs_tp_fill_tcw_kernel (3xTF32 tcgen05, 2 x 32-env tiles ping-pong, warp-specialised)"}[variant],
         }
         line.update(extra)
         print(json.dumps(line))

@@ -2012,7 +2012,7 @@ __device__ __forceinline__ bool elect_one() {          // one lane of the (conve
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- pieces shared by the single-tile kernel (hs_tp_fill_tcn_kernel) and the ping-pong kernel
-// (hs_tp_fill_tcp_kernel) -------------------------------------------------------------------------
+// (hs_tp_fill_tcw_kernel) -------------------------------------------------------------------------
 struct TnLane {                 // per-thread constants of the epilogue
     float bias0, bias1;         // exponent-argument biases of the two gate rows behind this TMEM lane
     float sa, sb;               // second gate = sa + sb / d1: tanh(g) on even lanes (1, -2), sigmoid(o) on odd lanes (0, 1)
@@ -2026,21 +2026,22 @@ struct TnLane {                 // per-thread constants of the epilogue
 // the 80 k-columns of (M-tile cg>>1, hi|lo = cg&1) of its 32 lanes with tcgen05.st.  The rows are
 // PRE-SCALED by the constant of their activation (-log2 e for the sigmoid gates, +2 log2 e for the tanh
 // gate), so the accumulator already holds the argument of ex2 in the cell update.
-template <int FD>
+template <int FD, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_stage_weights(const TPParams& W, float* wst, uint32_t lane_base, int row, int cg) {
     const int tid = threadIdx.x;
     auto lane_of = [](int wr) { const int g = wr >> 6, u = wr & 63; return (g >> 1) * 128 + 2 * u + (g & 1); };
 #pragma unroll 8
-    for (int i = tid; i < 256 * TP_HID; i += TN_THREADS) {
+    for (int i = tid; i < 256 * TP_HID; i += NTHREADS) {
         const int wr = i >> 6, k = i & 63;
         wst[lane_of(wr) * TN_WPITCH + 16 + k] = __ldg(W.w_hh + i);
     }
 #pragma unroll 8
-    for (int i = tid; i < 256 * 16; i += TN_THREADS) {
+    for (int i = tid; i < 256 * 16; i += NTHREADS) {
         const int wr = i >> 4, k = i & 15;
         wst[lane_of(wr) * TN_WPITCH + k] = (k < FD) ? __ldg(W.w_ih + wr * FD + k) : 0.0f;
     }
     __syncthreads();
+    if (cg >= 4) return;                                    // (a dedicated issuing warp only helps with the copy above)
     const int tl = cg >> 1, want_lo = cg & 1;
     const float L2E = 1.4426950408889634f;
     const float scale = (tl == 1 && !(row & 1)) ? 2.0f * L2E : -L2E;         // tile 1, even lane = gate g (tanh)
@@ -2078,11 +2079,11 @@ __device__ __forceinline__ TnLane tn_lane_consts(const TPParams& W, int row) {
 
 // x of all H steps of one 32-env tile -> B operand (tf32 hi/lo): lane = (env & 7) + 8 * (k & 3) per core
 // matrix, so the 32 stores of a warp cover 128 contiguous bytes; loads are issued ten at a time.
-template <int FD>
+template <int FD, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_stage_x(const float* __restrict__ tp_input, int64_t e0, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane & 7, kk = lane >> 3;
-    constexpr int NW = TN_THREADS / 32, BATCH = 10;
+    constexpr int NW = NTHREADS / 32, BATCH = 10;
     for (int b0 = warp; b0 < H * 16; b0 += NW * BATCH) {
         float xv[BATCH];
 #pragma unroll
@@ -2155,7 +2156,7 @@ __device__ __forceinline__ void tn_epilogue(uint32_t d_taddr, const TnLane& L, i
 }
 
 // FC + tanh from the final h (hi + lo in shared memory), then the state_self / state_drones rows of the tile.
-template <int A>
+template <int A, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, int64_t e0, int nenv, const uint8_t* Hhi,
                                            const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf) {
     const hs_config& c = P.c;
@@ -2163,7 +2164,7 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
     const int tid = threadIdx.x;
     {
         const int n = tid & 31;
-        for (int og = tid >> 5; og < F3; og += TN_THREADS / 32) {
+        for (int og = tid >> 5; og < F3; og += NTHREADS / 32) {
             float a0 = fcb[og];
             const float* w0 = fcw + og * TP_HID;
 #pragma unroll 4
@@ -2232,7 +2233,7 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
             }
         } else {
             __syncthreads();
-            for (int i = tid; i < nwords; i += TN_THREADS) gdst[i] = rowbuf[i];
+            for (int i = tid; i < nwords; i += NTHREADS) gdst[i] = rowbuf[i];
         }
         __syncthreads();
     }
@@ -2264,6 +2265,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& phase) {
     uint32_t spins = 0;                                     // bounded: a wrong descriptor must not hang the box
     while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
     phase ^= 1;
+}
+// barrier `idx` of an array of mbarriers; `bits` holds one phase bit per barrier (no dynamically indexed registers)
+__device__ __forceinline__ void mbar_wait_idx(uint32_t bar0, uint32_t idx, uint32_t& bits) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 24)) __trap(); }
+    bits ^= 1u << idx;
 }
 
 template <int A>
@@ -2374,15 +2381,26 @@ static size_t tp_tcn_smem_bytes(const hs_config& c) {
 }
 
 // =========================================================================================
-// Ping-pong version of the kernel above for batches with more than one 32-env tile per SM: a CTA
-// advances TWO tiles, alternating epilogue(tile 0) | MMA(tile 1) and epilogue(tile 1) | MMA(tile 0), so
-// the ~0.6 us the tensor pipe needs for the 60 dependent MMAs of a step is hidden behind the other
-// tile's cell update.  Each tile has one accumulator slot (2 M-tiles x 32 columns) and its own
-// mbarrier; the weights in TMEM are shared.  TMEM columns: D slot t at 64*t, weights at 128..447.
+// Ping-pong, warp-specialised version for batches with more than one 32-env tile per SM (the default
+// there): a CTA advances TWO tiles, one accumulator slot (2 M-tiles x 32 columns) each, sharing the weights
+// in TMEM; 16 epilogue warps + 2 issuing warps (one per M-tile).  The epilogue warps never meet at a block
+// barrier inside the recurrence: a warp waits for an accumulator (mbarrier d_ready[t], armed by
+// tcgen05.commit, count 2), updates its 8 env columns x 32 gate rows, publishes h and arrives on
+// h_ready[t] (count 16); an issuing warp waits for h_ready[t], issues the 30 MMAs of the next step of its
+// M-tile and commits.  While the tensor pipe works on tile 0 the epilogue warps update tile 1 and vice
+// versa.  (For ONE tile per CTA this hand-off is slower than the block barrier of the kernel above -
+// 29.2 vs 26.6 us at 4096 envs - so small batches keep hs_tp_fill_tcn_kernel.)
+// TMEM: D slot t at columns 64*t, weights at 128..447.
 // =========================================================================================
+constexpr int TCW_THREADS = TN_THREADS + 64;            // 16 epilogue warps + 2 issuing warps (one per M-tile)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
 template <int A>
-__global__ void __launch_bounds__(TN_THREADS, 1)
-hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+__global__ void __launch_bounds__(TCW_THREADS, 1)
+hs_tp_fill_tcw_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const hs_config& c = P.c;
     constexpr int FD = 7 + 3 * A;
@@ -2391,18 +2409,19 @@ hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__
     const int E = c.num_envs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;
-    const int cg = warp >> 2;
+    const int cg = warp >> 2;                                  // 0..3 epilogue column groups, 4 = issuing warp
     const int ntiles = (E + TN_E - 1) / TN_E;
-    const int npairs = (ntiles + 1) / 2;
+    constexpr int NT = 2;
+    const int ngroups = (ntiles + NT - 1) / NT;
 
     uint8_t* Hb = smem_raw;                                    // slot t: hi at t*2*TN_H_BYTES, lo right after
-    float* fcw = reinterpret_cast<float*>(Hb + 4 * TN_H_BYTES);
+    float* fcw = reinterpret_cast<float*>(Hb + NT * 2 * TN_H_BYTES);
     float* fcb = fcw + F3 * TP_HID;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
-    uint8_t* Xb = reinterpret_cast<uint8_t*>(mbar + 4);        // slot t: hi at t*2*H*TN_X_STEP, lo right after
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // d_ready[2], h_ready[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+    uint8_t* Xb = reinterpret_cast<uint8_t*>(mbar + 6);        // slot t: hi at t*xslot, lo right after
     const size_t xslot = 2 * (size_t)H * TN_X_STEP;
-    float* preds = reinterpret_cast<float*>(Xb + 2 * xslot);
+    float* preds = reinterpret_cast<float*>(Xb + NT * xslot);
     float* rowbuf = preds + TN_E * 3 * FMAX;
     float* wst = reinterpret_cast<float*>(Xb);                 // prologue only: aliases the x / preds / row region
 
@@ -2411,11 +2430,13 @@ hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");        // d_ready: one commit per M-tile
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar + 1)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 2)) : "memory");   // h_ready: 16 epilogue warps
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 3)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < F3 * TP_HID; i += TN_THREADS) fcw[i] = __ldg(W.fc_w + i);
+    for (int i = tid; i < F3 * TP_HID; i += TCW_THREADS) fcw[i] = __ldg(W.fc_w + i);
     if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
     const TnLane L = tn_lane_consts(W, row);
     tc_fence_before();
@@ -2423,76 +2444,92 @@ hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    tn_stage_weights<FD>(W, wst, lane_base, row, cg);
-    __syncthreads();                                           // the staging tile is overwritten by x below
-    uint32_t phase[2] = {0u, 0u};
+    tn_stage_weights<FD, TCW_THREADS>(W, wst, lane_base, row, cg);
+    tc_fence_before();
+    __syncthreads();                                           // weights are in TMEM; the staging tile may be overwritten
+    const uint32_t d_ready = smem_u32(mbar), h_ready = smem_u32(mbar + 2);
+    uint32_t ph_d = 0u, ph_h = 0u;                             // phase bits; each role tracks only the barriers it waits on
 
     const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const bool issue_warp = warp_u < 2;
-    const uint32_t mytl = warp_u & 1u;
+    const bool issuer = warp_u >= TN_THREADS / 32;
+    const uint32_t mytl = warp_u & 1u;                         // M-tile of an issuing warp (warps 16, 17)
     TnIssue I;
     I.aA_hi = tmem_u + TN_COL_A + 160 * mytl;
     I.aA_lo = I.aA_hi + 80;
     I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t d_mine = tmem_u + mytl * TN_E;
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const int nslots = (2 * pair + 1 < ntiles) ? 2 : 1;
-        float cst[2][8];
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int nslots = (NT * grp + 1 >= ntiles) ? 1 : NT;
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cst[t][j] = 0.f;
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NT; ++t)
             if (t < nslots) {
-                const int64_t e0 = (int64_t)(2 * pair + t) * TN_E;
-                tn_stage_x<FD>(P.b.tp_input, e0, (int)min((int64_t)TN_E, E - e0), H, Xb + t * xslot, Xb + t * xslot + (size_t)H * TN_X_STEP);
+                const int64_t e0 = (int64_t)(NT * grp + t) * TN_E;
+                tn_stage_x<FD, TCW_THREADS>(P.b.tp_input, e0, (int)min((int64_t)TN_E, E - e0), H, Xb + t * xslot,
+                                           Xb + t * xslot + (size_t)H * TN_X_STEP);
             }
-        fence_async_smem();
+        fence_async_smem();                   // generic-proxy writes (x) -> visible to the MMA's async proxy
         tc_fence_before();
         __syncthreads();
-        if (issue_warp && elect_one()) {
-            tc_fence_after();
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-                if (t < nslots) {
-                    const uint32_t xb = smem_u32(Xb + t * xslot);
-                    I.x_part(d_mine + (uint32_t)(t * 2 * TN_E), tc_desc(xb, TN_X_LBO, TN_SBO),
-                             tc_desc(xb + (uint32_t)H * TN_X_STEP, TN_X_LBO, TN_SBO), 0u);
-                    tc_commit(smem_u32(mbar + t));
+        if (issuer) {
+            // ------------------------------------------------------------------ issuing warp
+            if (elect_one()) {
+                tc_fence_after();
+                auto xdesc = [&](int t, int s, bool lo) {
+                    return tc_desc(smem_u32(Xb + t * xslot) + (uint32_t)(lo ? H : 0) * TN_X_STEP + (uint32_t)s * TN_X_STEP, TN_X_LBO, TN_SBO);
+                };
+                auto hdesc = [&](int t, bool lo) { return tc_desc(smem_u32(Hb + t * 2 * TN_H_BYTES + (lo ? TN_H_BYTES : 0)), TN_H_LBO, TN_SBO); };
+                {
+                    for (int t = 0; t < nslots; ++t) {
+                        I.x_part(d_mine + (uint32_t)(t * 2 * TN_E), xdesc(t, 0, false), xdesc(t, 0, true), 0u);
+                        tc_commit(d_ready + 8u * (uint32_t)t);
+                    }
+                    for (int s = 0; s < H; ++s)
+                        for (int t = 0; t < nslots; ++t) {
+                            mbar_wait_idx(h_ready, (uint32_t)t, ph_h);
+                            if (s + 1 < H) {
+                                tc_fence_after();
+                                const uint32_t d = d_mine + (uint32_t)(t * 2 * TN_E);
+                                I.x_part(d, xdesc(t, s + 1, false), xdesc(t, s + 1, true), 0u);
+                                I.h_part(d, hdesc(t, false), hdesc(t, true));
+                                tc_commit(d_ready + 8u * (uint32_t)t);
+                            }
+                        }
                 }
-        }
-        for (int s = 0; s < H; ++s) {
+            }
+            __syncwarp();
+        } else {
+            // ------------------------------------------------------------------ epilogue warps
+            float cst[NT][8];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (t < nslots) {
-                    uint8_t* Hhi = Hb + t * 2 * TN_H_BYTES;
-                    uint8_t* Hlo = Hhi + TN_H_BYTES;
-                    mbar_wait(smem_u32(mbar + t), phase[t]);
-                    tc_fence_after();
-                    tn_epilogue(lane_base + (uint32_t)(t * 2 * TN_E), L, cg, cst[t], Hhi, Hlo);
-                    fence_async_smem();
-                    tc_fence_before();
-                    __syncthreads();
-                    if (s + 1 < H && issue_warp && elect_one()) {     // step s+1 of this tile runs under the other tile's epilogue
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cst[t][j] = 0.f;
+            for (int s = 0; s < H; ++s) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (t < nslots) {
+                        const int b = t;                                // accumulator slot = barrier index
+                        mbar_wait_idx(d_ready, (uint32_t)b, ph_d);
                         tc_fence_after();
-                        const uint32_t xb = smem_u32(Xb + t * xslot) + (uint32_t)(s + 1) * TN_X_STEP;
-                        const uint32_t d = d_mine + (uint32_t)(t * 2 * TN_E);
-                        I.x_part(d, tc_desc(xb, TN_X_LBO, TN_SBO), tc_desc(xb + (uint32_t)H * TN_X_STEP, TN_X_LBO, TN_SBO), 0u);
-                        I.h_part(d, tc_desc(smem_u32(Hhi), TN_H_LBO, TN_SBO), tc_desc(smem_u32(Hlo), TN_H_LBO, TN_SBO));
-                        tc_commit(smem_u32(mbar + t));
+                        uint8_t* Hhi = Hb + t * 2 * TN_H_BYTES;
+                        tn_epilogue(lane_base + (uint32_t)(b * 2 * TN_E), L, cg, cst[t], Hhi, Hhi + TN_H_BYTES);
+                        fence_async_smem();                      // h (generic proxy) -> async proxy of the next MMAs
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(h_ready + 8u * (uint32_t)t);
                     }
                 }
             }
         }
+        __syncthreads();                      // all h of the last step written; the issuing warp has consumed every arrival
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NT; ++t)
             if (t < nslots) {
-                const int64_t e0 = (int64_t)(2 * pair + t) * TN_E;
-                tn_fc_rows<A>(P, W, e0, (int)min((int64_t)TN_E, E - e0), Hb + t * 2 * TN_H_BYTES, Hb + t * 2 * TN_H_BYTES + TN_H_BYTES,
-                              fcw, fcb, preds, rowbuf);
+                const int64_t e0 = (int64_t)(NT * grp + t) * TN_E;
+                tn_fc_rows<A, TCW_THREADS>(P, W, e0, (int)min((int64_t)TN_E, E - e0), Hb + t * 2 * TN_H_BYTES,
+                                          Hb + t * 2 * TN_H_BYTES + TN_H_BYTES, fcw, fcb, preds, rowbuf);
             }
     }
     tc_fence_before();
@@ -2500,12 +2537,13 @@ hs_tp_fill_tcp_kernel(const __grid_constant__ KParams P, const __grid_constant__
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-static size_t tp_tcp_smem_bytes(const hs_config& c) {
+static size_t tp_tcw_smem_bytes(const hs_config& c) {
+    const int NT = 2;
     const int F3 = 3 * c.future_step;
-    const size_t region = 4 * (size_t)c.history_step * TN_X_STEP +
+    const size_t region = 2 * (size_t)NT * c.history_step * TN_X_STEP +
                           ((size_t)TN_E * 3 * FMAX + (size_t)TN_E * c.num_agents * (20 + 3 * FMAX)) * sizeof(float);
     const size_t wst = (size_t)256 * TN_WPITCH * sizeof(float);
-    return 4 * (size_t)TN_H_BYTES + ((size_t)F3 * TP_HID + 32) * sizeof(float) + 32 + (region > wst ? region : wst);
+    return 2 * (size_t)NT * TN_H_BYTES + ((size_t)F3 * TP_HID + 32) * sizeof(float) + 48 + (region > wst ? region : wst);
 }
 
 static size_t tp_smem_bytes(const hs_config& c) {
@@ -3070,12 +3108,12 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
                 default: e = cudaFuncSetAttribute(hs_tp_fill_tcn_kernel<3>, attr, t); break;
             }
         }
-        if (e == cudaSuccess && tp_tcp_smem_bytes(*cfg) <= HS_MAX_DYN_SMEM) {
-            const int t = (int)tp_tcp_smem_bytes(*cfg);
+        if (e == cudaSuccess && tp_tcw_smem_bytes(*cfg) <= HS_MAX_DYN_SMEM) {
+            const int t = (int)tp_tcw_smem_bytes(*cfg);
             switch (cfg->num_agents) {
-                case 1: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<1>, attr, t); break;
-                case 2: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<2>, attr, t); break;
-                default: e = cudaFuncSetAttribute(hs_tp_fill_tcp_kernel<3>, attr, t); break;
+                case 1: e = cudaFuncSetAttribute(hs_tp_fill_tcw_kernel<1>, attr, t); break;
+                case 2: e = cudaFuncSetAttribute(hs_tp_fill_tcw_kernel<2>, attr, t); break;
+                default: e = cudaFuncSetAttribute(hs_tp_fill_tcw_kernel<3>, attr, t); break;
             }
         }
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
@@ -3167,20 +3205,20 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     // tile per SM (variant 3), two tiles ping-ponging per CTA above that (variant 4).  The 128-env tcgen05
     // tile (2) and the FFMA kernels (0) remain as options and as the fallback when history_step makes the
     // 32-env tile's shared memory exceed 227 KB.
-    const bool tcn_fits = tp_tcn_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM, tcp_fits = tp_tcp_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
+    const bool tcn_fits = tp_tcn_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM, tcw_fits = tp_tcw_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
     int variant = (h->tp_variant >= 0) ? h->tp_variant : ((tiles32 > h->num_sms) ? 4 : 3);
-    if ((variant == 3 && !tcn_fits) || (variant == 4 && !tcp_fits)) {
+    if ((variant == 3 && !tcn_fits) || (variant == 4 && !tcw_fits)) {
         if (h->tp_variant >= 3) return set_err(HS_ERR_INVALID, "predictor variant 3/4: history_step too large for the 32-env tile%s");
         variant = (variant == 4 && tcn_fits) ? 3 : ((h->cfg.num_envs >= 6144) ? 2 : 0);
     }
     if (variant == 4) {
-        const size_t smem = tp_tcp_smem_bytes(h->cfg);
+        const size_t smem = tp_tcw_smem_bytes(h->cfg);
         const unsigned grid = (unsigned)min((tiles32 + 1) / 2, (int64_t)h->num_sms);   // persistent over tile pairs
         switch (h->cfg.num_agents) {
-            case 1: hs_tp_fill_tcp_kernel<1><<<grid, TN_THREADS, smem, s>>>(P, W); break;
-            case 2: hs_tp_fill_tcp_kernel<2><<<grid, TN_THREADS, smem, s>>>(P, W); break;
-            default: hs_tp_fill_tcp_kernel<3><<<grid, TN_THREADS, smem, s>>>(P, W); break;
+            case 1: hs_tp_fill_tcw_kernel<1><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
+            case 2: hs_tp_fill_tcw_kernel<2><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
+            default: hs_tp_fill_tcw_kernel<3><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
         }
     } else
     if (variant == 3) {
