@@ -213,6 +213,22 @@ int hs_reset(hs_handle* h, const uint8_t* env_mask, const float* drone_pos,
 int hs_step_host(hs_handle* h, const float* action_host, int action_is_raw,
                  float* reward_host, uint8_t* done_host, float* staging_dev, void* stream);
 
+/* Host-buffer tick INCLUDING the predictor (the end-to-end path of bench.py): H2D of `action`
+ * -> hs_step_pre -> hs_step_post_tp (when use_tp_net; `w` may be NULL otherwise) -> D2H of every
+ * non-NULL output below -> stream synchronise.  Outputs that are neighbours on the device AND in
+ * host memory with the same spacing (e.g. a host mirror of the caller's output slab) leave in a
+ * single copy.  `reset_pid` is a DEVICE pointer like in hs_step_pre (or NULL). */
+typedef struct hs_host_io {
+    const float* action;      /* in : [E,A,4] host, pinned for full speed */
+    float* state_self;        /* out: [E,A,D]      D = 20 (+3F with use_tp_net)   (any of these may be NULL) */
+    float* state_others;      /* out: [E,A,A-1,3] */
+    float* obs_cylinders;     /* out: [E,A,K,5] */
+    float* reward;            /* out: [E,A] */
+    uint8_t* done;            /* out: [E] */
+} hs_host_io;
+int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid,
+                    const hs_tp_weights* w, float* staging_dev, void* stream);
+
 /* ---- state views (what omni_drones/views/* get/set did) ------------------------------ */
 enum {
     HS_FIELD_DRONE_POS = 0,   /* [E,A,3] */

@@ -86,6 +86,12 @@ class hs_reset_dist(C.Structure):
                 ("env_offset", C.c_int64), ("seed", C.c_uint64)]
 
 
+class hs_host_io(C.Structure):
+    """include/hs_b200.h::hs_host_io (host-buffer tick)."""
+    _fields_ = [("action", C.c_void_p), ("state_self", C.c_void_p), ("state_others", C.c_void_p),
+                ("obs_cylinders", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p)]
+
+
 class hs_gen_params(C.Structure):
     """include/hs_b200.h::hs_gen_params (HideAndSeek_envgen control plane)."""
     _fields_ = [("num_agents", C.c_int32), ("num_cylinders", C.c_int32), ("arena_size", C.c_float),
@@ -110,6 +116,8 @@ _EXPORTS = {
     "hs_state_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_launch_count": (C.c_int64, [C.c_void_p]),
     "hs_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hs_step_host_io": (C.c_int, [C.c_void_p, C.POINTER(hs_host_io), C.c_int, C.c_void_p, C.POINTER(hs_tp_weights),
+                                  C.c_void_p, C.c_void_p]),
     "hs_gen_sample_nearby": (C.c_int, [C.POINTER(hs_gen_params), C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),

@@ -539,6 +539,48 @@ int hs_step_host(hs_handle* h, const float* action_host, int action_is_raw, floa
     return HS_OK;
 }
 
+int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
+                    float* staging_dev, void* stream) {
+    if (!h || !io || !io->action || !staging_dev) return set_err(HS_ERR_INVALID, "hs_step_host_io: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_host_io: call hs_bind_buffers first%s");
+    if (h->cfg.use_tp_net && !w) return set_err(HS_ERR_INVALID, "hs_step_host_io: use_tp_net == 1 needs the predictor weights%s");
+    const hs_config& c = h->cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t EA = (size_t)c.num_envs * c.num_agents;
+    CUDA_OK(cudaMemcpyAsync(staging_dev, io->action, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = hs_step_pre(h, staging_dev, action_is_raw, reset_pid, stream);
+    if (rc != HS_OK) return rc;
+    if (c.use_tp_net) {
+        rc = hs_step_post_tp(h, w, nullptr, stream);
+        if (rc != HS_OK) return rc;
+    }
+    const size_t D = 20 + (c.use_tp_net ? 3 * (size_t)c.future_step : 0);
+    struct Seg { const char* dev; char* host; size_t bytes; } seg[5] = {
+        {(const char*)h->bufs.state_self, (char*)io->state_self, EA * D * sizeof(float)},
+        {(const char*)h->bufs.state_others, (char*)io->state_others, EA * (size_t)(c.num_agents - 1) * 3 * sizeof(float)},
+        {(const char*)h->bufs.obs_cylinders, (char*)io->obs_cylinders, EA * (size_t)c.obs_max_cylinder * 5 * sizeof(float)},
+        {(const char*)h->bufs.reward, (char*)io->reward, EA * sizeof(float)},
+        {(const char*)h->bufs.done, (char*)io->done, (size_t)c.num_envs}};
+    int i = 0;
+    while (i < 5) {
+        if (!seg[i].host || !seg[i].dev || seg[i].bytes == 0) { ++i; continue; }
+        const char* d0 = seg[i].dev;
+        char* h0 = seg[i].host;
+        size_t len = seg[i].bytes;
+        int j = i + 1;
+        // merge neighbours: same spacing on both sides, gap (alignment padding) of at most 4 KB
+        while (j < 5 && seg[j].host && seg[j].dev && seg[j].bytes > 0 && seg[j].dev >= d0 + len &&
+               (size_t)(seg[j].dev - (d0 + len)) <= 4096 && (seg[j].dev - d0) == (seg[j].host - h0)) {
+            len = (size_t)(seg[j].dev - d0) + seg[j].bytes;
+            ++j;
+        }
+        CUDA_OK(cudaMemcpyAsync(h0, d0, len, cudaMemcpyDeviceToHost, s));
+        i = j;
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    return HS_OK;
+}
+
 static int field_desc(const hs_handle* h, int field, int* row0, int* n_slots, int* width, int* stride_slot,
                       int* stride_comp) {
     const int A = h->cfg.num_agents, C = h->cfg.num_cylinders;

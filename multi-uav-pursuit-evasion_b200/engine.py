@@ -140,6 +140,41 @@ class HsEngine:
         check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if raw else 0, _ptr(rp), self._stream()), "hs_step_pre")
         return self.out
 
+    def step_host(self, action_host: torch.Tensor, weights=None, raw: bool = True, reset_pid: Optional[torch.Tensor] = None):
+        """hs_step_host_io: one C-ABI call from HOST buffers to HOST buffers - pinned action in, H2D,
+        tick (+ fused predictor), D2H of observation / reward / done, stream sync.  Returns
+        (host mirror of the policy-facing slab prefix [state_self | state_others | obs_cylinders |
+        reward] as a dict of views, done).  The mirror is pinned and reused by the next call."""
+        E, A = self.E, self.A
+        if getattr(self, "_host", None) is None:
+            npol = self.sets[0].policy_words
+            mirror = torch.empty(npol, dtype=torch.float32).pin_memory()
+            self._host = dict(mirror=mirror, done=torch.empty(E, dtype=torch.uint8).pin_memory(),
+                              staging=torch.empty(E, A, 4, dtype=torch.float32, device=self.device))
+        hm = self._host
+        self._advance()
+        out = self.out
+        base = out.slab.data_ptr()
+        io = _lib.hs_host_io()
+        io.action = action_host.data_ptr()
+        views = {}
+        for k in ("state_self", "state_others", "obs_cylinders", "reward"):
+            t = out.t[k]
+            off = (t.data_ptr() - base) // 4
+            views[k] = hm["mirror"][off:off + t.numel()].view(t.shape)
+            setattr(io, k, views[k].data_ptr() if t.numel() else None)
+        io.done = hm["done"].data_ptr()
+        rp = None
+        if reset_pid is not None:
+            rp = reset_pid.reshape(E)
+            rp = rp.view(torch.uint8) if rp.dtype == torch.bool else rp.to(torch.uint8)
+            rp = rp.contiguous()
+        self._keep = [action_host, rp]
+        check(lib.hs_step_host_io(self._h, C.byref(io), 1 if raw else 0, _ptr(rp),
+                                  C.byref(weights) if weights is not None else None, hm["staging"].data_ptr(),
+                                  self._stream()), "hs_step_host_io")
+        return views, hm["done"]
+
     def step_post(self, tp_pred: torch.Tensor) -> OutputSet:
         F3 = 3 * self.cfg.future_step
         tp_pred = tp_pred.reshape(self.E, F3)

@@ -1,3 +1,7 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 512 --warmup 16 > gpurun_out/bench_n2_r1v.json 2> gpurun_out/bench_n2_r1v.err; tail -3 gpurun_out/bench_n2_r1v.err | cut -c1-300; cut -c1-700 gpurun_out/bench_n2_r1v.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 6 --warmup 1 2>&1 | tail -2 | cut -c1-400
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "host_buffer" 2>&1 | grep -E "Error|error|passed|failed|FAILED|off \(" | head
+timeout 600 python bench.py > gpurun_out/bench_r1w.json 2> gpurun_out/bench_r1w.err; tail -3 gpurun_out/bench_r1w.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r1w.json').read().strip().splitlines()[-1])
+print('value',d['value']); print('e2e',d['e2e']); print('e2e_python_env',d.get('e2e_python_env',{}).get('value'))
+PY

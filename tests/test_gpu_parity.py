@@ -224,6 +224,33 @@ def test_fused_predictor_matches_torch_lstm(A, E, variant):
     eng.close()
 
 
+def test_host_buffer_tick_with_predictor():
+    """hs_step_host_io: host action in -> tick + fused predictor -> observation/reward/done in host
+    buffers, one C-ABI call; must equal the device-side path on a twin engine."""
+    import mupe_b200
+    P, E = O.HSParams(), 300
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(4)
+    init = O.sample_reset(P, E, g)
+    engs = [mupe_b200.HsEngine(cfg, dev) for _ in range(2)]
+    for e in engs:
+        e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        e.step_post_tp(e.tp_weights(tp))
+    for t in range(3):
+        act = torch.randn(E, 3, 4, generator=g).pin_memory()
+        ref = engs[0].step_pre(act.to(dev), raw=True)
+        engs[0].step_post_tp(engs[0].tp_weights(tp))
+        views, done = engs[1].step_host(act, engs[1].tp_weights(tp), raw=True)
+        for k in ("state_self", "state_others", "obs_cylinders", "reward"):
+            assert torch.equal(views[k], ref[k].cpu()), (t, k)
+        assert torch.equal(done.bool(), ref["done"].reshape(E).cpu())
+    for e in engs:
+        e.close()
+
+
 def test_cuda_graph_replay_equals_direct_launches():
     import mupe_b200
     P, E = O.HSParams(), 256
