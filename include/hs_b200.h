@@ -305,6 +305,7 @@ typedef struct hs_gen_params {
     int32_t expand_cylinders;           /* task.expand_cylinders */
     float expand_step;                  /* task.expand_step */
     uint64_t seed;
+    int64_t task_offset;                /* global index of this call's task 0 (sharded jobs: ranks draw disjoint streams) */
 } hs_gen_params;
 /* GenBuffer.samplenearby (:322-372): for each of num_tasks outputs pick an archive row of
  * `history` [n_history, 3A+3+3C] uniformly, perturb, clip to the task bounds, accept when

@@ -96,7 +96,8 @@ class hs_gen_params(C.Structure):
     """include/hs_b200.h::hs_gen_params (HideAndSeek_envgen control plane)."""
     _fields_ = [("num_agents", C.c_int32), ("num_cylinders", C.c_int32), ("arena_size", C.c_float),
                 ("grid_size", C.c_float), ("max_height", C.c_float), ("num_grid", C.c_int32),
-                ("expand_cylinders", C.c_int32), ("expand_step", C.c_float), ("seed", C.c_uint64)]
+                ("expand_cylinders", C.c_int32), ("expand_step", C.c_float), ("seed", C.c_uint64),
+                ("task_offset", C.c_int64)]
 
 
 _EXPORTS = {

@@ -184,14 +184,15 @@ __global__ void __launch_bounds__(128) hs_gen_sample_nearby_kernel(hs_gen_params
                 const int b = i * ng + j;
                 inside[b >> 5] |= 1u << (b & 31);
             }
-    const uint4 w0 = philox4x32_10(make_uint4((uint32_t)t, 0xFFFF0000u, (uint32_t)epoch, (uint32_t)(epoch >> 32)), key);
+    const uint32_t tg = (uint32_t)((uint64_t)g.task_offset + (uint64_t)t);       // global task index = counter word 0
+    const uint4 w0 = philox4x32_10(make_uint4(tg, 0xFFFF0000u, (uint32_t)epoch, (uint32_t)(epoch >> 32)), key);
     const int64_t idx = (int64_t)__umulhi(w0.x, (uint32_t)n_history);
     float origin[GEN_MAX_DIM], cand[GEN_MAX_DIM];
     for (int j = 0; j < dim; ++j) origin[j] = history[idx * dim + j];
     bool ok = false;
     for (int attempt = 0; attempt < 10 && !ok; ++attempt) {
         PhiloxStream rng;
-        rng.ctr = make_uint4((uint32_t)t, (uint32_t)(64 * attempt), (uint32_t)epoch, (uint32_t)(epoch >> 32));
+        rng.ctr = make_uint4(tg, (uint32_t)(64 * attempt), (uint32_t)epoch, (uint32_t)(epoch >> 32));
         rng.key = key;
         rng.used = 4;
         for (int j = 0; j < nb; ++j) {

@@ -147,7 +147,7 @@ class GenBufferDevice:
     torch tensors instead of numpy arrays."""
 
     def __init__(self, num_agents: int, num_cylinders: int, arena_size=0.9, cylinder_size=0.1, max_height=1.2,
-                 buffer_length: int = 5000, seed: int = 0, device="cuda:0"):
+                 buffer_length: int = 5000, seed: int = 0, device="cuda:0", task_offset: int = 0):
         import ctypes as C
         from .. import _lib
         self._C, self._lib = C, _lib
@@ -163,6 +163,7 @@ class GenBufferDevice:
         self.params.arena_size, self.params.grid_size, self.params.max_height = arena_size, 2 * cylinder_size, max_height
         self.params.num_grid = int(arena_size * 2 / (2 * cylinder_size))
         self.params.seed = int(seed) & (2 ** 64 - 1)
+        self.params.task_offset = int(task_offset)      # sharded jobs: rank r draws tasks [offset, offset + n)
         self.epoch = 0
         self.gen = torch.Generator(device=self.device).manual_seed(int(seed))
 
@@ -252,7 +253,8 @@ class HideAndSeek_envgen(HideAndSeek):
         self.device_generator = True if self.cfg.env.device_generator is None else bool(self.cfg.env.device_generator)
         if self.device_generator:
             self.gen_buffer = GenBufferDevice(self.num_agents, self.num_cylinders, t.arena_size, t.cylinder.size,
-                                              t.max_height, seed=seed, device=self.device)
+                                              t.max_height, seed=seed, device=self.device,
+                                              task_offset=int(self.cfg.env.env_offset or 0))
         else:
             self.gen_buffer = GenBuffer(self.num_agents, self.num_cylinders, t.arena_size, t.cylinder.size, t.max_height,
                                         rng=np.random.default_rng(seed))
@@ -358,5 +360,11 @@ class HideAndSeek_envgen(HideAndSeek):
                 self.stats[f"ratio_cylinders_{i}"].fill_(float(sel.mean()))
                 self.stats[f"success_cylinders_{i}"].fill_(float(w[sel].mean()) if sel.any() else 0.0)
         keep = (w <= self.R_max) & (w >= self.R_min)
-        self.gen_buffer.insert_history(self.gen_buffer._state_buffer[keep])
+        kept = self.gen_buffer._state_buffer[keep]
+        if self.device_generator:
+            # sharded job: the archive is REPLICATED - every rank inserts the tasks all ranks evaluated, in
+            # rank order, and the (deterministic) farthest point sampling keeps the copies identical
+            from ..parallel import gather_rows
+            kept = gather_rows(kept)
+        self.gen_buffer.insert_history(kept)
         self.stats["add_history"].fill_(0).add_(torch.as_tensor(keep.sum(), device=self.stats["add_history"].device))

@@ -62,6 +62,28 @@ def gather_env_vector(local: torch.Tensor, shard: Optional[Shard] = None, group=
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
 
 
+def gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of a [n_local, d] matrix whose row count differs per rank -> [sum n, d] in rank order on
+    every rank (the envgen archive is replicated: every rank inserts the tasks ALL ranks evaluated).
+    One all_gather of the counts (host sync: episode boundary only) and one of the padded rows."""
+    local = local.contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local.clone()
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    m = max(sizes)
+    if m == 0:
+        return local.clone()
+    pad = torch.zeros(m, *local.shape[1:], dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:k] for b, k in zip(bufs, sizes)])
+
+
 def global_mean(local: torch.Tensor, group=None) -> torch.Tensor:
     """Mean over the envs of ALL ranks, computed on device without a host sync:
     all_reduce(SUM) of [sum, count]."""

@@ -86,8 +86,8 @@ def sanity_ok(task: np.ndarray, A: int, C: int, grid, ng: int, inside: np.ndarra
 
 
 def sample_nearby(history: np.ndarray, num_tasks: int, A: int, C: int, arena_size: float, cylinder_size: float,
-                  max_height: float, expand_cylinders: bool, expand_step: float, seed: int, epoch: int
-                  ) -> Dict[str, np.ndarray]:
+                  max_height: float, expand_cylinders: bool, expand_step: float, seed: int, epoch: int,
+                  task_offset: int = 0) -> Dict[str, np.ndarray]:
     hist = np.ascontiguousarray(history, np.float32)
     n_hist, dim = hist.shape
     assert dim == 3 * A + 3 + 3 * C
@@ -108,7 +108,7 @@ def sample_nearby(history: np.ndarray, num_tasks: int, A: int, C: int, arena_siz
     for t in range(num_tasks):
         def words(block0, nblk):
             ctr = np.zeros((nblk, 4), np.uint32)
-            ctr[:, 0] = np.uint32(t)
+            ctr[:, 0] = np.uint32((t + task_offset) & 0xFFFFFFFF)
             ctr[:, 1] = np.arange(block0, block0 + nblk, dtype=np.uint32)
             ctr[:, 2] = np.uint32(epoch & 0xFFFFFFFF)
             ctr[:, 3] = np.uint32((epoch >> 32) & 0xFFFFFFFF)

@@ -45,6 +45,16 @@ def _worker(rank, world, port, q):
             par.curriculum_step(v, done, torch.ones(hi - lo))
         assert abs(float(v) - 1.3) < 1e-6         # capped
         assert sh.seed(7) != par.Shard(1 - rank, 2, G).seed(7)
+        # replicated envgen archive: ragged [n_r, d] blocks -> the same [sum n, d] on every rank, rank order
+        rows = torch.full((3 if rank == 0 else 0, 4), float(rank))
+        allr = par.gather_rows(rows)
+        assert allr.shape == (3, 4) and torch.equal(allr, torch.zeros(3, 4))
+        rows = torch.arange((2 + 3 * rank) * 5, dtype=torch.float32).reshape(-1, 5) + 100 * rank
+        allr = par.gather_rows(rows)
+        want = torch.cat([torch.arange(10, dtype=torch.float32).reshape(2, 5),
+                          torch.arange(25, dtype=torch.float32).reshape(5, 5) + 100])
+        assert torch.equal(allr, want)
+        assert par.gather_rows(torch.zeros(0, 4)).shape == (0, 4)
         q.put((rank, "ok"))
     except Exception as e:                        # surface the failure in the parent
         q.put((rank, repr(e)))

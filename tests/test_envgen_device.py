@@ -104,6 +104,26 @@ def test_cuda_sample_nearby_bit_exact_against_oracle(expand_cyl, step, C):
 
 
 @pytest.mark.gpu
+def test_cuda_sample_nearby_shards_reproduce_the_single_process_stream():
+    """task_offset: two ranks drawing 600 tasks each == one process drawing 1200 (same seed, same epoch)."""
+    import mupe_b200  # noqa: F401
+    hist = _history(300)
+    one = _gb(seed=7)
+    one._history_buffer = torch.from_numpy(hist).cuda()
+    full, valid = one.samplenearby(1200, True, 0.1, return_valid=True)
+    parts = []
+    for r in range(2):
+        gb = _gb(seed=7, task_offset=600 * r)
+        gb._history_buffer = torch.from_numpy(hist).cuda()
+        parts.append(gb.samplenearby(600, True, 0.1, return_valid=True))
+    assert torch.equal(torch.cat([p[1] for p in parts]), valid)
+    ok = valid.cpu().numpy()
+    np.testing.assert_array_equal(torch.cat([p[0] for p in parts]).cpu().numpy()[ok], full.cpu().numpy()[ok])
+    want = G.sample_nearby(hist, 600, 3, 5, 0.9, 0.1, 1.2, True, 0.1, seed=7, epoch=1, task_offset=600)
+    np.testing.assert_array_equal(parts[1][1].cpu().numpy().astype(np.uint8), want["valid"])
+
+
+@pytest.mark.gpu
 def test_envgen_runs_a_generator_cycle_on_the_device():
     import mupe_b200 as m
     cfg = m.compose("HideAndSeek_envgen", "mappo", overrides={
