@@ -57,6 +57,9 @@ struct hs_handle {
     int block;                   // threads per block for the tick kernels
     int num_sms;
     int tp_variant;              // -1 auto, 0 fp32 FFMA, 1 3xTF32 mma.sync, 2/3 3xTF32 tcgen05 (128-/32-env tiles) (hs_set_option)
+    // hs_step_host_io: side stream that carries the tick's own outputs to the host while the predictor runs
+    cudaStream_t io_stream = nullptr;
+    cudaEvent_t io_tick_done = nullptr, io_copy_done = nullptr;
 };
 
 static thread_local char g_err[512] = "";
@@ -258,6 +261,11 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
 }
 
 int hs_destroy(hs_handle* h) {
+    if (h) {
+        if (h->io_tick_done) cudaEventDestroy(h->io_tick_done);
+        if (h->io_copy_done) cudaEventDestroy(h->io_copy_done);
+        if (h->io_stream) cudaStreamDestroy(h->io_stream);
+    }
     delete h;
     return HS_OK;
 }
@@ -550,32 +558,51 @@ int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const
     CUDA_OK(cudaMemcpyAsync(staging_dev, io->action, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = hs_step_pre(h, staging_dev, action_is_raw, reset_pid, stream);
     if (rc != HS_OK) return rc;
-    if (c.use_tp_net) {
-        rc = hs_step_post_tp(h, w, nullptr, stream);
-        if (rc != HS_OK) return rc;
-    }
     const size_t D = 20 + (c.use_tp_net ? 3 * (size_t)c.future_step : 0);
+    // seg[0] is written by the predictor kernel (use_tp_net) -- the rest is complete after the tick
     struct Seg { const char* dev; char* host; size_t bytes; } seg[5] = {
         {(const char*)h->bufs.state_self, (char*)io->state_self, EA * D * sizeof(float)},
         {(const char*)h->bufs.state_others, (char*)io->state_others, EA * (size_t)(c.num_agents - 1) * 3 * sizeof(float)},
         {(const char*)h->bufs.obs_cylinders, (char*)io->obs_cylinders, EA * (size_t)c.obs_max_cylinder * 5 * sizeof(float)},
         {(const char*)h->bufs.reward, (char*)io->reward, EA * sizeof(float)},
         {(const char*)h->bufs.done, (char*)io->done, (size_t)c.num_envs}};
-    int i = 0;
-    while (i < 5) {
-        if (!seg[i].host || !seg[i].dev || seg[i].bytes == 0) { ++i; continue; }
-        const char* d0 = seg[i].dev;
-        char* h0 = seg[i].host;
-        size_t len = seg[i].bytes;
-        int j = i + 1;
-        // merge neighbours: same spacing on both sides, gap (alignment padding) of at most 4 KB
-        while (j < 5 && seg[j].host && seg[j].dev && seg[j].bytes > 0 && seg[j].dev >= d0 + len &&
-               (size_t)(seg[j].dev - (d0 + len)) <= 4096 && (seg[j].dev - d0) == (seg[j].host - h0)) {
-            len = (size_t)(seg[j].dev - d0) + seg[j].bytes;
-            ++j;
+    auto copy_segments = [&](int first, int last, cudaStream_t cs) -> cudaError_t {
+        int i = first;
+        while (i < last) {
+            if (!seg[i].host || !seg[i].dev || seg[i].bytes == 0) { ++i; continue; }
+            const char* d0 = seg[i].dev;
+            char* h0 = seg[i].host;
+            size_t len = seg[i].bytes;
+            int j = i + 1;
+            // merge neighbours: same spacing on both sides, gap (alignment padding) of at most 4 KB
+            while (j < last && seg[j].host && seg[j].dev && seg[j].bytes > 0 && seg[j].dev >= d0 + len &&
+                   (size_t)(seg[j].dev - (d0 + len)) <= 4096 && (seg[j].dev - d0) == (seg[j].host - h0)) {
+                len = (size_t)(seg[j].dev - d0) + seg[j].bytes;
+                ++j;
+            }
+            const cudaError_t e = cudaMemcpyAsync(h0, d0, len, cudaMemcpyDeviceToHost, cs);
+            if (e != cudaSuccess) return e;
+            i = j;
         }
-        CUDA_OK(cudaMemcpyAsync(h0, d0, len, cudaMemcpyDeviceToHost, s));
-        i = j;
+        return cudaSuccess;
+    };
+    if (c.use_tp_net) {
+        // the rows the tick itself completed travel on a side stream while the predictor kernel runs
+        if (!h->io_stream) {
+            CUDA_OK(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&h->io_tick_done, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&h->io_copy_done, cudaEventDisableTiming));
+        }
+        CUDA_OK(cudaEventRecord(h->io_tick_done, s));
+        CUDA_OK(cudaStreamWaitEvent(h->io_stream, h->io_tick_done, 0));
+        CUDA_OK(copy_segments(1, 5, h->io_stream));
+        CUDA_OK(cudaEventRecord(h->io_copy_done, h->io_stream));
+        rc = hs_step_post_tp(h, w, nullptr, stream);
+        if (rc != HS_OK) return rc;
+        CUDA_OK(copy_segments(0, 1, s));
+        CUDA_OK(cudaStreamWaitEvent(s, h->io_copy_done, 0));
+    } else {
+        CUDA_OK(copy_segments(0, 5, s));
     }
     CUDA_OK(cudaStreamSynchronize(s));
     return HS_OK;
