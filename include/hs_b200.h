@@ -325,6 +325,34 @@ int64_t hs_fps_scratch_bytes(int64_t n);
 int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start, int32_t* idx_out,
            void* scratch, void* stream);
 
+/* ---- the caller's side of a rollout: advantages -------------- */
+/* compute_gae (omni_drones/learning/utils/gae.py:27-51) as MAPPOPolicy.train_op calls it
+ * (omni_drones/learning/mappo.py:381-397): one backward scan over the T steps per
+ * (env, agent) column, bit-identical to the reference's eager fp32 loop, optionally followed
+ * by the batch-level advantage normalisation (adv - mean) / (std + 1e-8) of mappo.py:391-396.
+ * reward / value / advantages / returns: fp32 element [e][t][a] at e*stride_env +
+ * t*stride_step + a (the reference's [N,T,k] tensors have stride_env = T*k, stride_step = k;
+ * the time-major rollout storage has stride_env = k, stride_step = N*k).  done: one byte per
+ * (env, step) at e*done_stride_env + t*done_stride_step (the reference's [N,T,1] bool
+ * broadcast over the agents).  next_value [N,k] contiguous.  gamma/lmbda are doubles because
+ * the reference rounds the Python product gamma*lmbda to fp32 once. */
+typedef struct hs_gae_params {
+    int64_t num_envs;
+    int32_t num_steps, num_agents;
+    int64_t stride_env, stride_step;
+    int64_t done_stride_env, done_stride_step;
+    double gamma, lmbda;
+    int32_t normalize;                  /* 1: advantages are normalised in place after the scan */
+    int32_t reserved;
+} hs_gae_params;
+/* scratch: 16 bytes of device memory (two doubles: sum and sum of squares of the advantages;
+ * zeroed by the call).  stats_out: NULL or 2 device floats that receive {mean, std} of the
+ * un-normalised advantages (train_info["advantages_mean"/"advantages_std"]).  One launch
+ * (two with normalize), asynchronous on `stream`. */
+int hs_gae(const hs_gae_params* p, const float* reward, const uint8_t* done, const float* value,
+           const float* next_value, float* advantages, float* returns, void* scratch,
+           float* stats_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,10 +8,12 @@ from . import _lib
 from ._lib import HsError
 from .compat import (Compose, InitTracker, SyncDataCollector, TensorDict, TransformedEnv, step_mdp)
 from .config import Cfg, build_hs_config, compose, load_drone_params
-from .engine import HsEngine
+from .engine import HsEngine, RolloutStorage
+from . import rollout
+from .rollout import compute_gae
 from . import parallel
 from .envs import AgentSpec, GenBuffer, HideAndSeek, HideAndSeek_envgen, Hover, IsaacEnv, PIDRateController, TP_net
 
-__all__ = ["parallel", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+__all__ = ["parallel", "rollout", "compute_gae", "RolloutStorage", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
            "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
            "HideAndSeek", "HideAndSeek_envgen", "GenBuffer", "Hover", "IsaacEnv", "PIDRateController", "TP_net"]

@@ -100,6 +100,14 @@ class hs_gen_params(C.Structure):
                 ("task_offset", C.c_int64)]
 
 
+class hs_gae_params(C.Structure):
+    """include/hs_b200.h::hs_gae_params (advantage scan over a rollout)."""
+    _fields_ = [("num_envs", C.c_int64), ("num_steps", C.c_int32), ("num_agents", C.c_int32),
+                ("stride_env", C.c_int64), ("stride_step", C.c_int64),
+                ("done_stride_env", C.c_int64), ("done_stride_step", C.c_int64),
+                ("gamma", C.c_double), ("lmbda", C.c_double), ("normalize", C.c_int32), ("reserved", C.c_int32)]
+
+
 _EXPORTS = {
     "hs_abi_version": (C.c_int, []),
     "hs_last_error": (C.c_char_p, []),
@@ -123,6 +131,8 @@ _EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),
     "hs_fps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_gae": (C.c_int, [C.POINTER(hs_gae_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_sample_reset": (C.c_int, [C.c_void_p, C.POINTER(hs_reset_dist), C.c_uint64, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -417,21 +417,75 @@ class SyncDataCollector:
 
     def rollout(self) -> TensorDict:
         start = time.perf_counter()
-        frames = []
-        for _ in range(self.frames_per_batch // self.n_envs):
-            td = self._td
-            td = self.policy(td) if self.policy is not None else td.update(self.env.action_spec.rand())
-            td = self.env.step(td)
-            frames.append(td.clone())
-            done = td.get(("next", "done"))
-            td = step_mdp(td)
-            if self.reset_when_done and bool(done.any()):
-                td.set("_reset", done.clone())
-                td = self.env.reset(td)
-                td.pop("_reset", None)
-            self._td = td
-        out = TensorDict.stack(frames, 1)
+        base = getattr(self.env, "base_env", self.env)
+        eng = getattr(base, "engine", None)
+        steps = self.frames_per_batch // self.n_envs
+        if eng is not None and getattr(eng, "storage", None) is not None and eng.storage.T == steps \
+                and hasattr(base, "rollout_next_td"):
+            out = self._rollout_into_storage(base, eng, steps)
+        else:
+            frames = []
+            for _ in range(steps):
+                td = self._policy_step()
+                frames.append(td.clone())
+                self._carry(td)
+            out = TensorDict.stack(frames, 1)
         self._fps = out.numel() / (time.perf_counter() - start)
+        return out
+
+    def _policy_step(self) -> TensorDict:
+        td = self._td
+        td = self.policy(td) if self.policy is not None else td.update(self.env.action_spec.rand())
+        return self.env.step(td)
+
+    def _carry(self, td: TensorDict):
+        done = td.get(("next", "done"))
+        td = step_mdp(td)
+        if self.reset_when_done and bool(done.any()):
+            td.set("_reset", done.clone())
+            td = self.env.reset(td)
+            td.pop("_reset", None)
+        self._td = td
+
+    def _rollout_into_storage(self, base, eng, steps: int) -> TensorDict:
+        """Rollout mode: the tick kernels write ``next`` straight into the
+        engine's time-major ``[T, E, ...]`` RolloutStorage, so the per-step clone and the final stack of
+        the generic path disappear; the step's input side (observation the policy saw, its outputs)
+        is copied once into preallocated ``[T, E, ...]`` tensors.  The result is the same ``[E, T]``
+        tensordict, as views."""
+        E, dev = self.n_envs, base.device
+        if eng.rollout_slot not in (-1, steps - 1):
+            raise RuntimeError("rollout storage is mid-rollout: the env was stepped outside the collector")
+        pre = getattr(self, "_pre", None)
+        for t in range(steps):
+            td = self._policy_step()
+            nxt = td.get("next")
+            if pre is None:
+                # first step ever: allocate the input-side storage from what the policy produced
+                pre = self._pre = {}
+                tup = lambda k: k if isinstance(k, tuple) else (k,)
+                for k in td.keys(True, True):
+                    if tup(k)[0] == "next":
+                        continue
+                    v = td.get(k)
+                    pre[k] = torch.empty((steps,) + tuple(v.shape), dtype=v.dtype, device=v.device)
+                self._stats_T = torch.empty(steps, E, len(base.stats.keys()), device=dev)
+                self._prev_action_T = torch.empty((steps,) + tuple(eng.prev_action.shape), device=dev)
+                # entries of ``next`` that transforms add on top of the engine's outputs (is_init, ...)
+                engine_keys = {tup(k) for k in base.rollout_next_td(self._stats_T, self._prev_action_T).keys(True, True)}
+                for k in nxt.keys(True, True):
+                    if tup(k) not in engine_keys:
+                        v = nxt.get(k)
+                        pre[("next",) + tup(k)] = torch.empty((steps,) + tuple(v.shape), dtype=v.dtype, device=v.device)
+            for k, buf in pre.items():
+                buf[t].copy_(td.get(k))
+            torch.stack([nxt.get(("stats", k)).reshape(E) for k in base.stats.keys()], dim=-1, out=self._stats_T[t])
+            self._prev_action_T[t].copy_(eng.prev_action)
+            self._carry(td)
+        out = TensorDict({}, [E, steps], dev)
+        out.set("next", base.rollout_next_td(self._stats_T, self._prev_action_T))
+        for k, buf in pre.items():
+            out.set(k, buf.transpose(0, 1))
         return out
 
     def iterator(self) -> Iterator[TensorDict]:

@@ -42,6 +42,7 @@
 #include "hs_predictor_tcgen05.cuh"
 #include "hs_reset.cuh"
 #include "hs_samplers.cuh"
+#include "hs_rollout.cuh"
 
 // =========================================================================================
 // C ABI
@@ -527,6 +528,38 @@ int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start
     void* args[] = {(void*)&points, (void*)&ni, (void*)&dim, (void*)&k, (void*)&start, (void*)&chunk, (void*)&cache,
                     (void*)&idx_out, (void*)&mind, (void*)&slots, (void*)&bar};
     CUDA_OK(cudaLaunchCooperativeKernel((const void*)hs_fps_kernel, dim3(G), dim3(FPS_THREADS), args, smem, s));
+    return HS_OK;
+}
+
+int hs_gae(const hs_gae_params* p, const float* reward, const uint8_t* done, const float* value, const float* next_value,
+           float* advantages, float* returns, void* scratch, float* stats_out, void* stream) {
+    if (!p || !reward || !done || !value || !next_value || !advantages || !returns)
+        return set_err(HS_ERR_INVALID, "hs_gae: null argument%s");
+    if (p->num_envs < 1 || p->num_steps < 1 || p->num_agents < 1)
+        return set_err(HS_ERR_INVALID, "hs_gae: num_envs, num_steps and num_agents must be >= 1%s");
+    if ((p->normalize || stats_out) && !scratch)
+        return set_err(HS_ERR_INVALID, "hs_gae: normalize / stats_out need the 16-byte scratch buffer%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ncol = p->num_envs * p->num_agents;
+    double* moments = reinterpret_cast<double*>(scratch);
+    if (moments) CUDA_OK(cudaMemsetAsync(moments, 0, 2 * sizeof(double), s));
+    const float gamma = (float)p->gamma, gl = (float)(p->gamma * p->lmbda);
+    const unsigned grid = (unsigned)((ncol + 255) / 256);
+    hs_gae_kernel<<<grid, 256, 0, s>>>(reward, done, value, next_value, advantages, returns, moments, ncol, p->num_steps,
+                                       p->num_agents, p->stride_env, p->stride_step, p->done_stride_env,
+                                       p->done_stride_step, gamma, gl);
+    CUDA_OK(cudaGetLastError());
+    if (p->normalize || stats_out) {
+        const int64_t total = ncol * p->num_steps;
+        int dev = 0, sms = 0;
+        CUDA_OK(cudaGetDevice(&dev));
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // without normalize the launch only publishes {mean, std}
+        const unsigned g2 = p->normalize ? (unsigned)min((int64_t)sms * 8, (total + 255) / 256) : 1u;
+        hs_adv_normalize_kernel<<<g2, 256, 0, s>>>(advantages, moments, stats_out, ncol, p->num_steps, p->num_agents,
+                                                   p->stride_env, p->stride_step, p->normalize ? 1 : 0);
+        CUDA_OK(cudaGetLastError());
+    }
     return HS_OK;
 }
 

@@ -22,7 +22,8 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class OutputSet:
     """One set of reference-facing tensors carved out of a single float32 slab (+ a byte slab)."""
 
-    def __init__(self, cfg: hs_config, device):
+    @staticmethod
+    def shapes(cfg: hs_config) -> Dict[str, tuple]:
         E, A = cfg.num_envs, cfg.num_agents
         K, F, H = cfg.obs_max_cylinder, cfg.future_step, cfg.history_step
         D = 20 + (3 * F if cfg.use_tp_net else 0)
@@ -37,6 +38,16 @@ class OutputSet:
         }
         if cfg.use_tp_net:
             shapes.update({"tp_input": (E, H, FD), "tp_groundtruth": (E, 3)})
+        return shapes
+
+    def __init__(self, cfg: hs_config, device, views: Optional[Dict[str, torch.Tensor]] = None):
+        E = cfg.num_envs
+        shapes = self.shapes(cfg)
+        if views is not None:
+            # slot of a RolloutStorage: every tensor is one [E, ...] row of a time-major [T, E, ...] tensor
+            self.slab, self.policy_words, self.result_words = None, 0, 0
+            self.t = dict(views)
+            return
         offs, total = {}, 0
         for k, s in shapes.items():
             n = 1
@@ -61,10 +72,40 @@ class OutputSet:
         return self.t[k]
 
 
+class RolloutStorage:
+    """Time-major rollout buffers the tick kernels write into directly: one
+    ``[T + 1, E, ...]`` tensor per output; tick ``t`` of a rollout binds row ``t`` as its output
+    set, so after T ticks ``[:T]`` IS the rollout - nothing is cloned or stacked.  Row ``T`` is the
+    scratch set that receives the outputs of resets (the reference stores the pre-reset ``next``
+    in the rollout and feeds the post-reset observation to the following step).  Every row starts
+    128-byte aligned (TMA bulk stores)."""
+
+    def __init__(self, cfg: hs_config, device, num_steps: int):
+        self.T = int(num_steps)
+        E = cfg.num_envs
+        self.data: Dict[str, torch.Tensor] = {}
+        for k, shp in OutputSet.shapes(cfg).items():
+            n = 1
+            for d in shp:
+                n *= d
+            pitch = (n + _ALIGN_WORDS - 1) // _ALIGN_WORDS * _ALIGN_WORDS
+            flat = torch.zeros(self.T + 1, max(pitch, 1), dtype=torch.float32, device=device)
+            self.data[k] = flat[:, :n].view(self.T + 1, *shp)
+        for k in ("done", "tp_done", "truncated"):
+            self.data[k] = torch.zeros(self.T + 1, E, 1, dtype=torch.uint8, device=device).view(torch.bool)
+
+    def slot(self, cfg: hs_config, device, i: int) -> OutputSet:
+        return OutputSet(cfg, device, {k: v[i] for k, v in self.data.items()})
+
+    def batch(self) -> Dict[str, torch.Tensor]:
+        """``[E, T, ...]`` views (env-major indexing, time-major memory) of the finished rollout."""
+        return {k: v[:self.T].transpose(0, 1) for k, v in self.data.items()}
+
+
 class HsEngine:
     """Owns the buffers of one environment batch on one GPU and drives the kernels."""
 
-    def __init__(self, cfg: hs_config, device="cuda:0", num_output_sets: int = 2):
+    def __init__(self, cfg: hs_config, device="cuda:0", num_output_sets: int = 2, rollout_steps: Optional[int] = None):
         device = torch.device(device)
         if device.type != "cuda" or not torch.cuda.is_available():
             raise _lib.HsError("HsEngine needs a CUDA device: the environment step has no CPU path "
@@ -81,7 +122,14 @@ class HsEngine:
         self.stats = torch.zeros(_lib.HS_NUM_STATS, self.E, dtype=torch.float32, device=device)
         self.prev_action = torch.zeros(self.E, self.A, 4, dtype=torch.float32, device=device)
         self.v_prey = torch.full((1,), 1.3, dtype=torch.float32, device=device)
-        self.sets = [OutputSet(cfg, device) for _ in range(max(1, num_output_sets))]
+        self.storage: Optional[RolloutStorage] = None
+        if rollout_steps:
+            # rollout mode: set t = row t of the time-major rollout tensors, set T = reset scratch
+            self.storage = RolloutStorage(cfg, device, int(rollout_steps))
+            self.sets = [self.storage.slot(cfg, device, i) for i in range(self.storage.T + 1)]
+            self._slot = -1                    # rollout row written by the latest tick
+        else:
+            self.sets = [OutputSet(cfg, device) for _ in range(max(1, num_output_sets))]
         self._bufs = [self._make_bufs(i) for i in range(len(self.sets))]
         self.cur = len(self.sets) - 1          # index of the set holding the latest outputs
         self._keep = []                        # keeps caller tensors alive across async launches
@@ -108,12 +156,31 @@ class HsEngine:
         b.prev_action, b.v_prey = _ptr(self.prev_action), _ptr(self.v_prey)
         return b
 
-    def _bind(self, i: int):
-        check(lib.hs_bind_buffers(self._h, C.byref(self._bufs[i])), "hs_bind_buffers")
+    def _bind(self, i: int, prev: Optional[int] = None):
+        """Binds output set i; the previous TP window is read from set ``prev`` (default: the set
+        that holds the latest outputs)."""
+        b = self._bufs[i]
+        if self.cfg.use_tp_net:
+            b.tp_input_prev = _ptr(self.sets[self.cur if prev is None else prev]["tp_input"])
+        check(lib.hs_bind_buffers(self._h, C.byref(b)), "hs_bind_buffers")
         self.cur = i
 
-    def _advance(self):
-        self._bind((self.cur + 1) % len(self.sets))
+    def next_index(self, reset: bool = False) -> int:
+        """Index of the set the next tick (or reset) will write."""
+        if self.storage is None:
+            return (self.cur + 1) % len(self.sets)
+        return self.storage.T if reset else (self._slot + 1) % self.storage.T
+
+    def _advance(self, reset: bool = False):
+        i = self.next_index(reset)
+        if self.storage is not None and not reset:
+            self._slot = i
+        self._bind(i)
+
+    @property
+    def rollout_slot(self) -> int:
+        """Rollout row the latest tick wrote (rollout mode); the rollout is complete at T - 1."""
+        return self._slot
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -146,6 +213,8 @@ class HsEngine:
         (host mirror of the policy-facing slab prefix [state_self | state_others | obs_cylinders |
         reward] as a dict of views, done).  The mirror is pinned and reused by the next call."""
         E, A = self.E, self.A
+        if self.storage is not None:
+            raise _lib.HsError("step_host: the host-buffer tick needs slab output sets (rollout_steps=None)")
         if getattr(self, "_host", None) is None:
             npol = self.sets[0].policy_words
             mirror = torch.empty(npol, dtype=torch.float32).pin_memory()
@@ -231,29 +300,44 @@ class HsEngine:
         self.graph_action = torch.zeros(self.E, self.A, 4, dtype=torch.float32, device=dev)
         self.graph_reset_pid = torch.zeros(self.E, dtype=torch.uint8, device=dev)
         self._graph_weights = tp_weights
-        self._graphs = []
+        self._graph_raw = raw
+        self._graphs = {}
         self._graph_kernels = 2 if self.cfg.use_tp_net else 1
+        self._graph_replays = getattr(self, "_graph_replays", 0)      # cumulative, like hs_launch_count
+        if self.storage is None:
+            for i in range(len(self.sets)):
+                self._capture((i - 1) % len(self.sets), i)
+        return self
+
+    def _capture(self, prev: int, i: int):
+        """One CUDA graph for 'tick into set i with the previous TP window in set prev'."""
+        dev = self.device
         keep = self.cur
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(dev)
-        for i in range(len(self.sets)):
-            self._bind(i)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                st = torch.cuda.current_stream(dev).cuda_stream
-                check(lib.hs_step_pre(self._h, self.graph_action.data_ptr(), 1 if raw else 0,
-                                      self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
-                if self.cfg.use_tp_net:
-                    check(lib.hs_step_post_tp(self._h, C.byref(tp_weights), None, st), "hs_step_post_tp (capture)")
-            self._graphs.append(g)
-        self._bind(keep)
-        self._graph_replays = 0
-        return self
+        self._bind(i, prev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            check(lib.hs_step_pre(self._h, self.graph_action.data_ptr(), 1 if self._graph_raw else 0,
+                                  self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
+            if self.cfg.use_tp_net:
+                check(lib.hs_step_post_tp(self._h, C.byref(self._graph_weights), None, st), "hs_step_post_tp (capture)")
+        self._graphs[(prev, i)] = g
+        self._graph_captures = getattr(self, "_graph_captures", 0) + 1
+        self._bind(keep, keep)
+        return g
 
     def replay_tick(self) -> OutputSet:
-        """One tick from ``graph_action`` / ``graph_reset_pid`` with a single graph launch."""
+        """One tick from ``graph_action`` / ``graph_reset_pid`` with a single graph launch.  Graphs are
+        keyed by (set holding the previous TP window, set written); in rollout mode the pairs are
+        captured on first use (t-1 -> t, T-1 -> 0 and reset scratch -> t)."""
+        prev, i = self.cur, self.next_index()
+        g = self._graphs.get((prev, i))
+        if g is None:
+            g = self._capture(prev, i)
         self._advance()
-        self._graphs[self.cur].replay()
+        g.replay()
         self._graph_replays += 1
         return self.out
 
@@ -268,7 +352,7 @@ class HsEngine:
             m = mask.to(self.device).reshape(E)
             m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
             m = m.contiguous()
-        self._advance()
+        self._advance(reset=True)
         self._keep = [m, drone_pos, drone_rot, target_pos, cyl_pos]
         check(lib.hs_reset(self._h, _ptr(m), drone_pos.data_ptr(), drone_rot.data_ptr(), target_pos.data_ptr(),
                            _ptr(cyl_pos), self._stream()), "hs_reset")
@@ -318,8 +402,8 @@ class HsEngine:
     def launches(self) -> int:
         """Kernels of libhs_b200.so launched so far (graph replays counted per captured kernel)."""
         n = int(lib.hs_launch_count(self._h))
-        if getattr(self, "_graphs", None):
-            n += (self._graph_replays - len(self._graphs)) * self._graph_kernels   # capture calls counted once each
+        if getattr(self, "_graph_captures", 0):
+            n += (self._graph_replays - getattr(self, "_graph_captures", 0)) * self._graph_kernels   # capture calls counted once each
         return n
 
     def close(self):

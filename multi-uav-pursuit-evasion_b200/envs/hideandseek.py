@@ -121,7 +121,8 @@ class HideAndSeek(IsaacEnv):
             write_smoothness_coef_stat=not self.VARIANT_ENVGEN,
             ground_clamp=True if self.cfg.sim is None or self.cfg.sim.ground_clamp is None else bool(self.cfg.sim.ground_clamp),
             max_linear_velocity=t.v_drone, drone_params=params)
-        self.engine = HsEngine(self._hs_cfg, self.device, num_output_sets=int(self.cfg.env.output_sets or 2))
+        self.engine = HsEngine(self._hs_cfg, self.device, num_output_sets=int(self.cfg.env.output_sets or 2),
+                               rollout_steps=int(self.cfg.env.get("rollout_steps", 0) or 0) or None)
         self.v_prey = t.v_drone * t.v_prey                      # hideandseek.py:263
         self.engine.v_prey.fill_(self.v_prey)
         self._curriculum = self.v_prey < 1.3 and not self.VARIANT_ENVGEN
@@ -301,6 +302,28 @@ class HideAndSeek(IsaacEnv):
         self.info.set("drone_state", out["drone_state"])
         return TensorDict({"agents": agents, "stats": self.stats, "info": self.info}, [E], dev)
 
+    def rollout_next_td(self, stats: torch.Tensor, prev_action: torch.Tensor) -> TensorDict:
+        """``next`` of a finished rollout as ``[E, T]`` views of the engine's time-major RolloutStorage
+        (rollout mode, ``env.rollout_steps=T``): nothing is copied.  ``stats`` ``[T, E, 24]`` and
+        ``prev_action`` ``[T, E, A, 4]`` are the per-step snapshots of the two live buffers the tick
+        updates in place (the reference's collector clones them with every step too)."""
+        st = self.engine.storage
+        if st is None:
+            raise RuntimeError("rollout_next_td needs rollout mode (cfg.env.rollout_steps)")
+        E, T, A, dev = self.num_envs, st.T, self.num_agents, self.device
+        b = st.batch()
+        obs = TensorDict({"state_self": b["state_self"], "cylinders": b["obs_cylinders"]}, [E, T, A], dev)
+        if A > 1:
+            obs.set("state_others", b["state_others"])
+        state = TensorDict({"state_drones": b["state_drones"], "cylinders": b["obs_cylinders"]}, [E, T], dev)
+        agents = {"observation": obs, "state": state, "reward": b["reward"]}
+        if self.use_TP_net:
+            agents["TP"] = TensorDict({"TP_input": b["tp_input"], "TP_groundtruth": b["tp_groundtruth"],
+                                       "TP_done": b["tp_done"]}, [E, T], dev)
+        stats_td = TensorDict({k: stats[..., i:i + 1].transpose(0, 1) for i, k in enumerate(STAT_KEYS)}, [E, T], dev)
+        info = TensorDict({"drone_state": b["drone_state"], "prev_action": prev_action.transpose(0, 1)}, [E, T], dev)
+        return TensorDict({"agents": agents, "stats": stats_td, "info": info, "done": b["done"]}, [E, T], dev)
+
     def _predict(self, out):
         """Second half of the tick.  A TP_net-shaped predictor is evaluated inside the fused
         kernel from its live parameters; any other module goes through torch and hs_step_post
@@ -350,7 +373,7 @@ class HideAndSeek(IsaacEnv):
             if w is None:
                 return False
         key = None if w is None else (w.weight_ih, w.weight_hh, w.bias_ih, w.bias_hh, w.fc_weight, w.fc_bias)
-        if getattr(self, "_graph_key", ...) != key or not getattr(eng, "_graphs", None):
+        if getattr(self, "_graph_key", ...) != key or getattr(eng, "_graphs", None) is None:
             eng.capture_tick_graphs(w, raw=True)
             self._graph_key = key
         return True
@@ -380,7 +403,7 @@ class HideAndSeek(IsaacEnv):
             ae = tensordict.get(("stats", "action_error_order1"), None)
             if ae is None:
                 ae = torch.zeros(self.num_envs, self.num_agents, device=self.device)
-            eng.sets[(eng.cur + 1) % len(eng.sets)]["action_error"].copy_(ae)
+            eng.sets[eng.next_index()]["action_error"].copy_(ae)
             out = eng.step_pre(action.contiguous(), raw=False, reset_pid=None)
             self._predict(out)
         nxt = self._obs_td(out)

@@ -132,6 +132,41 @@ def test_collector_rollout_and_episode_boundary():
     env.close()
 
 
+@pytest.mark.parametrize("graph", [0, 1])
+def test_rollout_storage_collector_equals_clone_and_stack(graph):
+    """with env.rollout_steps=T the tick kernels write `next` straight into the time-major
+    RolloutStorage and the collector returns [E, T] views; every entry must equal, bit for bit, what the generic
+    clone-per-step + stack collector returns for the same seeds and actions - across a rollout boundary and an
+    episode boundary (max_episode_length=5 < T), with and without CUDA graphs."""
+    E, T = 64, 8
+    outs = []
+    for steps in (0, T):
+        torch.manual_seed(5)                        # predictor weights
+        m, cfg, base, env = make(E, **{"task.env.max_episode_length": 5, "task.env.rollout_steps": steps,
+                                       "task.env.cuda_graph": graph})
+        g = torch.Generator(device=DEV).manual_seed(3)
+        torch.manual_seed(11)                       # reset sampling
+
+        def policy(td):
+            td.set(("agents", "action"), torch.randn(E, 3, 4, device=DEV, generator=g))
+            return td
+        col = m.SyncDataCollector(env, policy=policy, frames_per_batch=E * T, total_frames=E * T * 3, return_same_td=True)
+        outs.append([d.clone() for d in col])
+        assert (base.engine.storage is not None) == bool(steps)
+        env.close()
+    assert len(outs[0]) == len(outs[1]) == 3
+    for a, b in zip(*outs):
+        # (the generic path's step_mdp carries the previous reward along at the root from the second step on;
+        # the storage collector fixes its input-side key set at the first step)
+        assert set(b.keys(True, True)) <= set(a.keys(True, True))
+        assert set(a.keys(True, True)) - set(b.keys(True, True)) <= {("agents", "reward")}
+        assert tuple(b.batch_size) == (E, T)
+        for k in b.keys(True, True):
+            x, y = a.get(k), b.get(k)
+            assert x.shape == y.shape, k
+            assert torch.equal(x, y), f"{k} differs between the storage collector and clone+stack"
+
+
 def test_partial_reset_mask_and_direct_rotor_commands():
     E = 32
     import mupe_b200 as m
