@@ -353,6 +353,44 @@ int hs_gae(const hs_gae_params* p, const float* reward, const uint8_t* done, con
            const float* next_value, float* advantages, float* returns, void* scratch,
            float* stats_out, void* stream);
 
+/* ---- policy inference next to the tick ----------------------- */
+/* The MAPPO actor / critic of the reference for this task: PartialAttentionEncoder
+ * (omni_drones/learning/modules/networks.py:249-314; embed_dim = dim_feedforward = 128, one
+ * head, query = the agent's own token, post-norm) over the observation
+ * {state_self [1,D], state_others [n_others,3], cylinders [n_cyl,5]} of one agent, followed by
+ * a linear head: DiagGaussian.fc_mean + log_std (modules/distributions.py:66-82, sampled as in
+ * Actor.forward, omni_drones/learning/mappo.py:614-635) or Critic.v_out (mappo.py:652-668).
+ * All pointers are the DEVICE pointers of the live nn.Module parameters (fp32, contiguous,
+ * PyTorch layouts: Linear weight [out,in], MultiheadAttention in_proj_weight [3*128,128]). */
+typedef struct hs_policy_weights {
+    const float *embed_self_w, *embed_self_b;       /* split_embed.embed.state_self   [128,D], [128] */
+    const float *embed_others_w, *embed_others_b;   /* split_embed.embed.state_others [128,3] (NULL when n_others == 0) */
+    const float *embed_cyl_w, *embed_cyl_b;         /* split_embed.embed.cylinders    [128,5] (NULL when n_cyl == 0) */
+    const float *embed_ln_w, *embed_ln_b;           /* split_embed.layer_norm */
+    const float *attn_in_w, *attn_in_b;             /* attn.in_proj_weight / in_proj_bias */
+    const float *attn_out_w, *attn_out_b;           /* attn.out_proj */
+    const float *lin1_w, *lin1_b, *lin2_w, *lin2_b; /* linear1, linear2 */
+    const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+    const float *head_w, *head_b;                   /* fc_mean [head_dim,128] | v_out [1,128] */
+    const float *log_std;                           /* [head_dim] (actor) or NULL (critic) */
+    int32_t self_dim, head_dim;                     /* D <= 128, head_dim <= 8 */
+} hs_policy_weights;
+/* Size (floats) of the prepared parameter blob for a given state_self width. */
+int64_t hs_policy_blob_floats(int32_t self_dim);
+/* Packs the parameters K-major and folds Wk^T Wq and Wo Wv (see csrc/hs_policy.cuh); call it
+ * after every optimiser step that touched the module.  One launch, asynchronous. */
+int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream);
+/* One launch for num_rows = E * A observation rows.  head_out [num_rows, head_dim] receives the
+ * action mean (actor) or the state value (critic).  Actor extras, each may be NULL: eps
+ * [num_rows, head_dim] standard-normal noise (NULL: the mode is taken, as deterministic=True),
+ * action [num_rows, head_dim] = mean + exp(log_std) * eps, logp [num_rows] = log-probability of
+ * that action.  feat_out: NULL or [num_rows, 128] encoder features.  Asynchronous on `stream`;
+ * the action buffer can be handed to hs_step_pre as the raw action of the same tick. */
+int hs_policy_forward(const float* blob, int32_t self_dim, int32_t n_others, int32_t n_cyl, int32_t head_dim,
+                      int64_t num_rows, const float* state_self, const float* state_others,
+                      const float* cylinders, const float* eps, float* head_out, float* action,
+                      float* logp, float* feat_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,16 @@ class hs_gen_params(C.Structure):
                 ("task_offset", C.c_int64)]
 
 
+_POLICY_PTRS = ["embed_self_w", "embed_self_b", "embed_others_w", "embed_others_b", "embed_cyl_w", "embed_cyl_b",
+                "embed_ln_w", "embed_ln_b", "attn_in_w", "attn_in_b", "attn_out_w", "attn_out_b", "lin1_w", "lin1_b",
+                "lin2_w", "lin2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b", "head_w", "head_b", "log_std"]
+
+
+class hs_policy_weights(C.Structure):
+    """include/hs_b200.h::hs_policy_weights (actor / critic parameters)."""
+    _fields_ = [(n, C.c_void_p) for n in _POLICY_PTRS] + [("self_dim", C.c_int32), ("head_dim", C.c_int32)]
+
+
 class hs_gae_params(C.Structure):
     """include/hs_b200.h::hs_gae_params (advantage scan over a rollout)."""
     _fields_ = [("num_envs", C.c_int64), ("num_steps", C.c_int32), ("num_agents", C.c_int32),
@@ -131,6 +141,11 @@ _EXPORTS = {
                                        C.c_void_p, C.c_void_p]),
     "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),
     "hs_fps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_policy_blob_floats": (C.c_int64, [C.c_int32]),
+    "hs_policy_prepare": (C.c_int, [C.POINTER(hs_policy_weights), C.c_void_p, C.c_void_p]),
+    "hs_policy_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "hs_gae": (C.c_int, [C.POINTER(hs_gae_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_sample_reset": (C.c_int, [C.c_void_p, C.POINTER(hs_reset_dist), C.c_uint64, C.c_void_p, C.c_void_p,

@@ -43,6 +43,7 @@
 #include "hs_reset.cuh"
 #include "hs_samplers.cuh"
 #include "hs_rollout.cuh"
+#include "hs_policy.cuh"
 
 // =========================================================================================
 // C ABI
@@ -528,6 +529,56 @@ int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start
     void* args[] = {(void*)&points, (void*)&ni, (void*)&dim, (void*)&k, (void*)&start, (void*)&chunk, (void*)&cache,
                     (void*)&idx_out, (void*)&mind, (void*)&slots, (void*)&bar};
     CUDA_OK(cudaLaunchCooperativeKernel((const void*)hs_fps_kernel, dim3(G), dim3(FPS_THREADS), args, smem, s));
+    return HS_OK;
+}
+
+int64_t hs_policy_blob_floats(int32_t self_dim) {
+    if (self_dim < 1 || self_dim > PL_E) return 0;
+    return policy_blob_layout(self_dim).total;
+}
+
+int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream) {
+    if (!w || !blob) return set_err(HS_ERR_INVALID, "hs_policy_prepare: null argument%s");
+    if (w->self_dim < 1 || w->self_dim > PL_E || w->head_dim < 1 || w->head_dim > PL_HEAD_MAX)
+        return set_err(HS_ERR_INVALID, "hs_policy_prepare: need 1 <= self_dim <= 128 and 1 <= head_dim <= 8%s");
+    if (!w->embed_self_w || !w->embed_self_b || !w->embed_ln_w || !w->embed_ln_b || !w->attn_in_w || !w->attn_in_b ||
+        !w->attn_out_w || !w->attn_out_b || !w->lin1_w || !w->lin1_b || !w->lin2_w || !w->lin2_b || !w->norm1_w ||
+        !w->norm1_b || !w->norm2_w || !w->norm2_b || !w->head_w || !w->head_b)
+        return set_err(HS_ERR_INVALID, "hs_policy_prepare: a required parameter pointer is NULL%s");
+    hs_policy_prepare_kernel<<<PL_E, PL_E, 0, (cudaStream_t)stream>>>(*w, blob);
+    CUDA_OK(cudaGetLastError());
+    return HS_OK;
+}
+
+int hs_policy_forward(const float* blob, int32_t self_dim, int32_t n_others, int32_t n_cyl, int32_t head_dim, int64_t num_rows,
+                      const float* state_self, const float* state_others, const float* cylinders, const float* eps,
+                      float* head_out, float* action, float* logp, float* feat_out, void* stream) {
+    if (!blob || !state_self || !head_out) return set_err(HS_ERR_INVALID, "hs_policy_forward: null argument%s");
+    if (self_dim < 1 || self_dim > PL_E || head_dim < 1 || head_dim > PL_HEAD_MAX || n_others < 0 || n_others > 2 ||
+        n_cyl < 0 || n_cyl > 4 || num_rows < 1)
+        return set_err(HS_ERR_INVALID, "hs_policy_forward: need self_dim <= 128, head_dim <= 8, n_others <= 2, n_cyl <= 4%s");
+    if ((n_others > 0 && !state_others) || (n_cyl > 0 && !cylinders))
+        return set_err(HS_ERR_INVALID, "hs_policy_forward: state_others / cylinders missing%s");
+    PolicyArgs A;
+    A.blob = blob; A.state_self = state_self; A.state_others = state_others; A.cylinders = cylinders; A.eps = eps;
+    A.head_out = head_out; A.action = action; A.logp = logp; A.feat_out = feat_out;
+    A.R = num_rows; A.D = self_dim; A.n_others = n_others; A.n_cyl = n_cyl; A.head_dim = head_dim;
+    int dev = 0, sms = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t s = (cudaStream_t)stream;
+    // 64-row tiles halve the weight traffic per row; 32-row tiles fill the machine at small batches
+    const bool big = num_rows >= (int64_t)sms * 64 * 2;
+    if (big) {
+        const size_t smem = policy_smem_bytes<64>(self_dim);
+        CUDA_OK(cudaFuncSetAttribute(hs_policy_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hs_policy_forward_kernel<64><<<(unsigned)((num_rows + 63) / 64), 256, smem, s>>>(A);
+    } else {
+        const size_t smem = policy_smem_bytes<32>(self_dim);
+        CUDA_OK(cudaFuncSetAttribute(hs_policy_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hs_policy_forward_kernel<32><<<(unsigned)((num_rows + 31) / 32), 128, smem, s>>>(A);
+    }
+    CUDA_OK(cudaGetLastError());
     return HS_OK;
 }
 
