@@ -380,16 +380,28 @@ int64_t hs_policy_blob_floats(int32_t self_dim);
 /* Packs the parameters K-major and folds Wk^T Wq and Wo Wv (see csrc/hs_policy.cuh); call it
  * after every optimiser step that touched the module.  One launch, asynchronous. */
 int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream);
-/* One launch for num_rows = E * A observation rows.  head_out [num_rows, head_dim] receives the
- * action mean (actor) or the state value (critic).  Actor extras, each may be NULL: eps
- * [num_rows, head_dim] standard-normal noise (NULL: the mode is taken, as deterministic=True),
- * action [num_rows, head_dim] = mean + exp(log_std) * eps, logp [num_rows] = log-probability of
- * that action.  feat_out: NULL or [num_rows, 128] encoder features.  Asynchronous on `stream`;
- * the action buffer can be handed to hs_step_pre as the raw action of the same tick. */
-int hs_policy_forward(const float* blob, int32_t self_dim, int32_t n_others, int32_t n_cyl, int32_t head_dim,
-                      int64_t num_rows, const float* state_self, const float* state_others,
-                      const float* cylinders, const float* eps, float* head_out, float* action,
-                      float* logp, float* feat_out, void* stream);
+/* Inputs and outputs of one forward pass over num_rows = E * A observation rows. */
+typedef struct hs_policy_io {
+    int64_t num_rows;
+    int32_t n_others, n_cyl;        /* tokens besides the agent's own: n_others <= 2, n_cyl <= 4 */
+    const float* state_self;        /* [num_rows, D]                                            */
+    const float* state_others;      /* [num_rows, n_others, 3] (NULL when n_others == 0)        */
+    const float* cylinders;         /* [num_rows, n_cyl, 5]    (NULL when n_cyl == 0)           */
+    float* head_out;                /* [num_rows, head_dim]: action mean (actor) | state value (critic) */
+    /* actor extras, each may be NULL */
+    const float* eps;               /* [num_rows, head_dim] caller-supplied standard-normal noise */
+    uint64_t* rng_state;            /* device {seed, step, 0, 0}: when eps is NULL and this is set, the kernel
+                                       draws the noise itself (Philox4x32-10 keyed by seed, counter = (row, step),
+                                       Box-Muller) and advances step by one per launch - the rollout needs no
+                                       separate noise launch.  Both NULL: the mode (deterministic=True). */
+    float* action;                  /* [num_rows, head_dim] = mean + exp(log_std) * noise       */
+    float* logp;                    /* [num_rows] log-probability of that action                */
+    float* eps_out;                 /* [num_rows, head_dim] the noise that was used             */
+    float* feat_out;                /* [num_rows, 128] encoder features                         */
+} hs_policy_io;
+/* One launch.  Asynchronous on `stream`; io->action can be handed to hs_step_pre as the raw
+ * action of the same tick. */
+int hs_policy_forward(const float* blob, int32_t self_dim, int32_t head_dim, const hs_policy_io* io, void* stream);
 
 #ifdef __cplusplus
 }

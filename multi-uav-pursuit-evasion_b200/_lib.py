@@ -110,6 +110,14 @@ class hs_policy_weights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _POLICY_PTRS] + [("self_dim", C.c_int32), ("head_dim", C.c_int32)]
 
 
+class hs_policy_io(C.Structure):
+    """include/hs_b200.h::hs_policy_io."""
+    _fields_ = [("num_rows", C.c_int64), ("n_others", C.c_int32), ("n_cyl", C.c_int32),
+                ("state_self", C.c_void_p), ("state_others", C.c_void_p), ("cylinders", C.c_void_p),
+                ("head_out", C.c_void_p), ("eps", C.c_void_p), ("rng_state", C.c_void_p), ("action", C.c_void_p),
+                ("logp", C.c_void_p), ("eps_out", C.c_void_p), ("feat_out", C.c_void_p)]
+
+
 class hs_gae_params(C.Structure):
     """include/hs_b200.h::hs_gae_params (advantage scan over a rollout)."""
     _fields_ = [("num_envs", C.c_int64), ("num_steps", C.c_int32), ("num_agents", C.c_int32),
@@ -143,9 +151,7 @@ _EXPORTS = {
     "hs_fps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_policy_blob_floats": (C.c_int64, [C.c_int32]),
     "hs_policy_prepare": (C.c_int, [C.POINTER(hs_policy_weights), C.c_void_p, C.c_void_p]),
-    "hs_policy_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p]),
+    "hs_policy_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(hs_policy_io), C.c_void_p]),
     "hs_gae": (C.c_int, [C.POINTER(hs_gae_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_sample_reset": (C.c_int, [C.c_void_p, C.POINTER(hs_reset_dist), C.c_uint64, C.c_void_p, C.c_void_p,

@@ -550,19 +550,19 @@ int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream) {
     return HS_OK;
 }
 
-int hs_policy_forward(const float* blob, int32_t self_dim, int32_t n_others, int32_t n_cyl, int32_t head_dim, int64_t num_rows,
-                      const float* state_self, const float* state_others, const float* cylinders, const float* eps,
-                      float* head_out, float* action, float* logp, float* feat_out, void* stream) {
-    if (!blob || !state_self || !head_out) return set_err(HS_ERR_INVALID, "hs_policy_forward: null argument%s");
-    if (self_dim < 1 || self_dim > PL_E || head_dim < 1 || head_dim > PL_HEAD_MAX || n_others < 0 || n_others > 2 ||
-        n_cyl < 0 || n_cyl > 4 || num_rows < 1)
+int hs_policy_forward(const float* blob, int32_t self_dim, int32_t head_dim, const hs_policy_io* io, void* stream) {
+    if (!blob || !io || !io->state_self || !io->head_out) return set_err(HS_ERR_INVALID, "hs_policy_forward: null argument%s");
+    const int64_t num_rows = io->num_rows;
+    if (self_dim < 1 || self_dim > PL_E || head_dim < 1 || head_dim > PL_HEAD_MAX || io->n_others < 0 || io->n_others > 2 ||
+        io->n_cyl < 0 || io->n_cyl > 4 || num_rows < 1)
         return set_err(HS_ERR_INVALID, "hs_policy_forward: need self_dim <= 128, head_dim <= 8, n_others <= 2, n_cyl <= 4%s");
-    if ((n_others > 0 && !state_others) || (n_cyl > 0 && !cylinders))
+    if ((io->n_others > 0 && !io->state_others) || (io->n_cyl > 0 && !io->cylinders))
         return set_err(HS_ERR_INVALID, "hs_policy_forward: state_others / cylinders missing%s");
     PolicyArgs A;
-    A.blob = blob; A.state_self = state_self; A.state_others = state_others; A.cylinders = cylinders; A.eps = eps;
-    A.head_out = head_out; A.action = action; A.logp = logp; A.feat_out = feat_out;
-    A.R = num_rows; A.D = self_dim; A.n_others = n_others; A.n_cyl = n_cyl; A.head_dim = head_dim;
+    A.blob = blob; A.state_self = io->state_self; A.state_others = io->state_others; A.cylinders = io->cylinders;
+    A.eps = io->eps; A.rng = io->eps ? nullptr : io->rng_state;
+    A.head_out = io->head_out; A.action = io->action; A.logp = io->logp; A.eps_out = io->eps_out; A.feat_out = io->feat_out;
+    A.R = num_rows; A.D = self_dim; A.n_others = io->n_others; A.n_cyl = io->n_cyl; A.head_dim = head_dim;
     int dev = 0, sms = 0;
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -26,6 +26,7 @@ namespace {
 constexpr int PL_E = 128;                 // embed_dim = dim_feedforward = 128 (networks.py:256-259 defaults)
 constexpr int PL_HEAD_MAX = 8;
 constexpr int PL_KC = 16;                 // weight rows per cp.async chunk
+constexpr int PL_STAGES = 3;              // cp.async ring depth
 constexpr int PL_MAX_TOK_IN = 2 * 3 + 4 * 5;   // others (<= 2 x 3) + cylinders (<= 4 x 5) floats per row
 
 struct PolicyBlob {                        // offsets (floats) into the prepared parameter blob
@@ -107,7 +108,9 @@ struct PolicyArgs {
     const float* state_self;      // [R, D]
     const float* state_others;    // [R, n_others, 3] or nullptr
     const float* cylinders;       // [R, n_cyl, 5] or nullptr
-    const float* eps;             // [R, head_dim] standard-normal noise, or nullptr (mode)
+    const float* eps;             // [R, head_dim] standard-normal noise, or nullptr
+    uint64_t* rng;                // {seed, step, arrivals, -}: in-kernel noise when eps == nullptr (nullptr too: mode)
+    float* eps_out;               // [R, head_dim] or nullptr
     float* head_out;              // [R, head_dim]  action mean | state value
     float* action;                // [R, head_dim] or nullptr
     float* logp;                  // [R] or nullptr
@@ -124,33 +127,61 @@ __device__ __forceinline__ void pl_gemm(const float* __restrict__ Wg, int K, con
     const int tid = threadIdx.x;
     const int nchunk = (K + PL_KC - 1) / PL_KC;
     auto prefetch = [&](int ch) {
-        const int k0 = ch * PL_KC, rows = min(PL_KC, K - k0);
-        const float4* src = reinterpret_cast<const float4*>(Wg + (size_t)k0 * PL_E);
-        float4* dst = reinterpret_cast<float4*>(wbuf + (ch & 1) * PL_KC * PL_E);
-        for (int i = tid; i < rows * (PL_E / 4); i += NT) cp_async16(dst + i, src + i);
-        cp_async_commit();
-    };
-    prefetch(0);
-    for (int ch = 0; ch < nchunk; ++ch) {
-        if (ch + 1 < nchunk) { prefetch(ch + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else cp_async_wait_all();
-        __syncthreads();
-        const int k0 = ch * PL_KC, rows = min(PL_KC, K - k0);
-        const float* wb = wbuf + (ch & 1) * PL_KC * PL_E;
-#pragma unroll 4
-        for (int kk = 0; kk < rows; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(actT + (k0 + kk) * P + 4 * rg);
-            const float4 w0 = *reinterpret_cast<const float4*>(wb + kk * PL_E + 4 * cg);
-            const float4 w1 = *reinterpret_cast<const float4*>(wb + kk * PL_E + 64 + 4 * cg);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+        if (ch < nchunk) {
+            const int k0 = ch * PL_KC, rows = min(PL_KC, K - k0);
+            const float4* src = reinterpret_cast<const float4*>(Wg + (size_t)k0 * PL_E);
+            float4* dst = reinterpret_cast<float4*>(wbuf + (ch % PL_STAGES) * PL_KC * PL_E);
+            for (int i = tid; i < rows * (PL_E / 4); i += NT) cp_async16(dst + i, src + i);
         }
-        __syncthreads();                     // the buffer just read is the next prefetch target
+        cp_async_commit();                   // (empty groups keep the wait_group arithmetic uniform)
+    };
+    auto fma_row = [&](const float4& a, const float4& w0, const float4& w1) {
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+    };
+    // three-stage ring, ONE barrier per chunk: the barrier that publishes chunk ch also proves that every thread is
+    // done with chunk ch-1, whose buffer is the target of the prefetch of chunk ch+2 issued right after it
+    prefetch(0);
+    prefetch(1);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        prefetch(ch + 2);
+        const int k0 = ch * PL_KC, rows = min(PL_KC, K - k0);
+        const float* wb = wbuf + (ch % PL_STAGES) * PL_KC * PL_E + 4 * cg;
+        const float* ap = actT + k0 * P + 4 * rg;
+        // software pipeline: the operands of row kk+1 are loaded before the 32 FMAs of row kk
+        float4 a = *reinterpret_cast<const float4*>(ap);
+        float4 w0 = *reinterpret_cast<const float4*>(wb);
+        float4 w1 = *reinterpret_cast<const float4*>(wb + 64);
+        if (rows == PL_KC) {
+#pragma unroll
+            for (int kk = 0; kk < PL_KC; ++kk) {
+                constexpr int last = PL_KC - 1;
+                const int kn = kk < last ? kk + 1 : last;                       // compile-time after unrolling
+                const float4 an = *reinterpret_cast<const float4*>(ap + kn * P);
+                const float4 w0n = *reinterpret_cast<const float4*>(wb + kn * PL_E);
+                const float4 w1n = *reinterpret_cast<const float4*>(wb + kn * PL_E + 64);
+                fma_row(a, w0, w1);
+                a = an; w0 = w0n; w1 = w1n;
+            }
+        } else {
+            for (int kk = 0; kk < rows; ++kk) {
+                const int kn = min(kk + 1, rows - 1);
+                const float4 an = *reinterpret_cast<const float4*>(ap + kn * P);
+                const float4 w0n = *reinterpret_cast<const float4*>(wb + kn * PL_E);
+                const float4 w1n = *reinterpret_cast<const float4*>(wb + kn * PL_E + 64);
+                fma_row(a, w0, w1);
+                a = an; w0 = w0n; w1 = w1n;
+            }
+        }
     }
+    cp_async_wait_all();
+    __syncthreads();                         // the ring is reused by the next layer
 }
 
 // column index of this thread's c-th accumulator column
@@ -204,12 +235,26 @@ hs_policy_forward_kernel(const PolicyArgs A) {
     float* bufB = bufA + PL_E * P;                   // [128][P]   q' -> xbar -> gelu(ff1)
     float* inT = bufB + PL_E * P;                    // [Dpad][P]  state_self, K-major
     float* oc = inT + L.Dpad * P;                    // [RT][tok_in] other-agent and cylinder rows
-    float* wbuf = oc + RT * PL_MAX_TOK_IN;           // [2][16][128]
+    float* wbuf = oc + RT * PL_MAX_TOK_IN;           // [PL_STAGES][16][128]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rg = tid >> 4, cg = tid & 15;
     const int64_t row0 = (int64_t)blockIdx.x * RT;
     const int nrow = (int)min((int64_t)RT, A.R - row0);
     const int D = A.D, no3 = A.n_others * 3, nc5 = A.n_cyl * 5, tok_in = no3 + nc5;
+
+    // in-kernel noise: every CTA reads {seed, step} BEFORE it signs in; the CTA that signs in last advances the step
+    // for the next launch, so no launch is spent on the counter and no CTA can see the new value
+    __shared__ unsigned long long rng_sh[2];
+    if (A.rng != nullptr && tid == 0) {
+        rng_sh[0] = A.rng[0];
+        rng_sh[1] = *reinterpret_cast<volatile unsigned long long*>(A.rng + 1);
+        __threadfence();
+        const unsigned long long seen = atomicAdd(reinterpret_cast<unsigned long long*>(A.rng + 2), 1ull);
+        if (seen == (unsigned long long)gridDim.x - 1ull) {
+            A.rng[2] = 0ull;
+            A.rng[1] = rng_sh[1] + 1ull;
+        }
+    }
 
     // ---- stage the observation rows of the tile
     for (int i = tid; i < RT * L.Dpad; i += NT) {
@@ -268,49 +313,86 @@ hs_policy_forward_kernel(const PolicyArgs A) {
             beo[i] = __ldg(blob + L.beo + f); bec[i] = __ldg(blob + L.bec + f);
             lw[i] = __ldg(blob + L.lnE_w + f); lb[i] = __ldg(blob + L.lnE_b + f);
         }
-        auto wsum = [](float v) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-            return v;
-        };
+        // All warp reductions of a row are issued as independent butterfly chains (two rounds: the token means, then
+        // the centred second moments and the q-weighted sums), so their shuffle latencies overlap.
+        constexpr int MT = 6;                                   // tokens besides the agent's own: n_others + n_cyl <= 6
+        const int nx = A.n_others + A.n_cyl;
         for (int r = warp; r < RT; r += NW) {
-            float q[4], x[4], xb[4] = {0.f, 0.f, 0.f, 0.f};
+            float q[4], x0[4], qlw[4], y[MT][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { q[i] = bufB[(lane + 32 * i) * P + r]; x[i] = bufA[(lane + 32 * i) * P + r]; }
-            float m = -INFINITY, l = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                q[i] = bufB[(lane + 32 * i) * P + r];
+                x0[i] = bufA[(lane + 32 * i) * P + r];
+                qlw[i] = q[i] * lw[i];
+            }
             const float* in = oc + r * PL_MAX_TOK_IN;
-            const int ntok = 1 + A.n_others + A.n_cyl;
-            for (int j = 0; j < ntok; ++j) {
-                if (j > 0) {
-                    if (j <= A.n_others) {
-                        const float* t = in + (j - 1) * 3;
+            float red[3 + MT];                                  // round 1: q.x0, sum q lw, sum q lb, token sums
+            red[0] = fmaf(q[3], x0[3], fmaf(q[2], x0[2], fmaf(q[1], x0[1], q[0] * x0[0])));
+            red[1] = (qlw[0] + qlw[1]) + (qlw[2] + qlw[3]);
+            red[2] = fmaf(q[3], lb[3], fmaf(q[2], lb[2], fmaf(q[1], lb[1], q[0] * lb[0])));
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) x[i] = fmaf(t[2], weo[2][i], fmaf(t[1], weo[1][i], fmaf(t[0], weo[0][i], beo[i])));
+            for (int j = 0; j < MT; ++j) {
+                if (j < nx) {
+                    if (j < A.n_others) {
+                        const float* t = in + j * 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[j][i] = fmaf(t[2], weo[2][i], fmaf(t[1], weo[1][i], fmaf(t[0], weo[0][i], beo[i])));
                     } else {
-                        const float* t = in + no3 + (j - 1 - A.n_others) * 5;
+                        const float* t = in + no3 + (j - A.n_others) * 5;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            x[i] = fmaf(t[4], wec[4][i], fmaf(t[3], wec[3][i], fmaf(t[2], wec[2][i], fmaf(t[1], wec[1][i], fmaf(t[0], wec[0][i], bec[i])))));
+                            y[j][i] = fmaf(t[4], wec[4][i], fmaf(t[3], wec[3][i], fmaf(t[2], wec[2][i], fmaf(t[1], wec[1][i], fmaf(t[0], wec[0][i], bec[i])))));
                     }
-                    const float mean = wsum((x[0] + x[1]) + (x[2] + x[3])) * (1.0f / PL_E);
-                    float v = 0.f;
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { x[i] -= mean; v = fmaf(x[i], x[i], v); }
-                    const float rstd = rsqrtf(wsum(v) * (1.0f / PL_E) + 1e-5f);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] = x[i] * rstd * lw[i] + lb[i];
+                    for (int i = 0; i < 4; ++i) y[j][i] = 0.f;
                 }
-                const float s = wsum(fmaf(q[3], x[3], fmaf(q[2], x[2], fmaf(q[1], x[1], q[0] * x[0]))));
-                const float mn = fmaxf(m, s);
-                const float sc = expf(m - mn), pj = expf(s - mn);      // first token: exp(-inf) = 0
-                l = fmaf(l, sc, pj);
+                red[3 + j] = (y[j][0] + y[j][1]) + (y[j][2] + y[j][3]);
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xb[i] = fmaf(xb[i], sc, pj * x[i]);
-                m = mn;
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < 3 + MT; ++k) red[k] += __shfl_xor_sync(FULL, red[k], o);
+            float var[MT], dot[MT];                             // round 2 (centred): sum (y - mean)^2, sum q lw (y - mean)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const float mean = red[3 + j] * (1.0f / PL_E);
+                float v = 0.f, d = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { y[j][i] -= mean; v = fmaf(y[j][i], y[j][i], v); d = fmaf(qlw[i], y[j][i], d); }
+                var[j] = v; dot[j] = d;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                    var[j] += __shfl_xor_sync(FULL, var[j], o);
+                    dot[j] += __shfl_xor_sync(FULL, dot[j], o);
+                }
+            // scores: s_0 = q.x0, s_j = q.LN(y_j) = rstd_j sum q lw (y_j - mean_j) + sum q lb; softmax over 1 + nx tokens
+            float sc[MT], rstd[MT], m = red[0];
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                rstd[j] = rsqrtf(var[j] * (1.0f / PL_E) + 1e-5f);
+                sc[j] = j < nx ? fmaf(rstd[j], dot[j], red[2]) : -INFINITY;
+                m = fmaxf(m, sc[j]);
+            }
+            const float p0 = expf(red[0] - m);
+            float l = p0, pl = 0.f, xb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xb[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const float pj = expf(sc[j] - m);               // exp(-inf) = 0 for absent tokens
+                l += pj; pl += pj;
+                const float pr = pj * rstd[j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xb[i] = fmaf(pr, y[j][i], xb[i]);
             }
             const float inv = 1.0f / l;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bufB[(lane + 32 * i) * P + r] = xb[i] * inv;
+            for (int i = 0; i < 4; ++i)
+                bufB[(lane + 32 * i) * P + r] = (fmaf(p0, x0[i], fmaf(xb[i], lw[i], pl * lb[i]))) * inv;
         }
     }
     __syncthreads();
@@ -326,11 +408,6 @@ hs_policy_forward_kernel(const PolicyArgs A) {
     }
     pl_layernorm(acc, blob + L.ln1_w, blob + L.ln1_b, cg);
     pl_store<RT>(bufA, acc, rg, cg);      // own elements only: safe while other threads still read their x0
-    float y1[4][8];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) y1[r][c] = acc[r][c];
     __syncthreads();
 
     // ---- h = gelu(W1 y1 + b1)                                         networks.py:308-310
@@ -349,9 +426,10 @@ hs_policy_forward_kernel(const PolicyArgs A) {
     pl_gemm<RT>(blob + L.W2t, PL_E, bufB, wbuf, rg, cg, acc);
     add_bias(L.b2);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] += y1[r][c];
+    for (int c = 0; c < 8; ++c) {          // residual y1: this thread's own elements, still in bufA
+        const float4 y1 = *reinterpret_cast<const float4*>(bufA + pl_col(cg, c) * P + 4 * rg);
+        acc[0][c] += y1.x; acc[1][c] += y1.y; acc[2][c] += y1.z; acc[3][c] += y1.w;
+    }
     pl_layernorm(acc, blob + L.ln2_w, blob + L.ln2_b, cg);
     if (A.feat_out != nullptr) {
 #pragma unroll
@@ -384,6 +462,28 @@ hs_policy_forward_kernel(const PolicyArgs A) {
     if (cg < 4 && 4 * rg + cg < nrow) {            // lane cg of the row group finishes row 4 rg + cg
         const int64_t row = row0 + 4 * rg + cg;
         float lp = 0.f;
+        float z[PL_HEAD_MAX];
+#pragma unroll
+        for (int h = 0; h < PL_HEAD_MAX; ++h) z[h] = 0.f;
+        if (A.rng != nullptr) {
+            // Philox4x32-10, key = seed, counter = (row, step, block of four head columns); Box-Muller on (0,1] x [0,1)
+#pragma unroll
+            for (int blk = 0; blk < PL_HEAD_MAX / 4; ++blk) {
+                if (4 * blk < A.head_dim) {
+                    const unsigned long long seed = rng_sh[0], step = rng_sh[1];
+                    const uint4 u = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32), (uint32_t)step,
+                                                             ((uint32_t)(step >> 32) << 1) | (uint32_t)blk),
+                                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                    const float u0 = ((float)(u.x >> 8) + 1.0f) * 5.9604644775390625e-08f, u1 = (float)(u.y >> 8) * 5.9604644775390625e-08f;
+                    const float u2 = ((float)(u.z >> 8) + 1.0f) * 5.9604644775390625e-08f, u3 = (float)(u.w >> 8) * 5.9604644775390625e-08f;
+                    const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+                    float s0, c0, s1, c1;
+                    sincosf(6.283185307179586f * u1, &s0, &c0);
+                    sincosf(6.283185307179586f * u3, &s1, &c1);
+                    z[4 * blk] = r0 * c0; z[4 * blk + 1] = r0 * s0; z[4 * blk + 2] = r1 * c1; z[4 * blk + 3] = r1 * s1;
+                }
+            }
+        }
 #pragma unroll
         for (int h = 0; h < PL_HEAD_MAX; ++h) {
             if (h < A.head_dim) {
@@ -395,7 +495,9 @@ hs_policy_forward_kernel(const PolicyArgs A) {
                 if (A.action != nullptr || A.logp != nullptr) {
                     const float ls = __ldg(blob + L.log_std + h);
                     const float sd = expf(ls);
-                    const float act = A.eps ? fmaf(sd, __ldg(A.eps + row * A.head_dim + h), mean) : mean;
+                    const float noise = A.eps ? __ldg(A.eps + row * A.head_dim + h) : z[h];
+                    if (A.eps_out) A.eps_out[row * A.head_dim + h] = noise;
+                    const float act = (A.eps || A.rng) ? fmaf(sd, noise, mean) : mean;
                     if (A.action) A.action[row * A.head_dim + h] = act;
                     const float d = act - mean;
                     lp += -(d * d) / (2.0f * sd * sd) - ls - 0.91893853320467274f;      // Normal.log_prob
@@ -409,7 +511,7 @@ hs_policy_forward_kernel(const PolicyArgs A) {
 template <int RT>
 static size_t policy_smem_bytes(int self_dim) {
     const int Dpad = (self_dim + 3) & ~3;
-    return ((size_t)(2 * PL_E + Dpad) * (RT + 4) + (size_t)RT * PL_MAX_TOK_IN + 2 * PL_KC * PL_E) * sizeof(float);
+    return ((size_t)(2 * PL_E + Dpad) * (RT + 4) + (size_t)RT * PL_MAX_TOK_IN + PL_STAGES * PL_KC * PL_E) * sizeof(float);
 }
 
 }  // namespace

@@ -93,6 +93,14 @@ class RolloutStorage:
             self.data[k] = flat[:, :n].view(self.T + 1, *shp)
         for k in ("done", "tp_done", "truncated"):
             self.data[k] = torch.zeros(self.T + 1, E, 1, dtype=torch.uint8, device=device).view(torch.bool)
+        # input side of tick t when a FusedPolicy is attached to the engine: what the actor / critic produced from
+        # the observation the tick started from (rows of the same time-major rollout)
+        A = cfg.num_agents
+        self.policy: Dict[str, torch.Tensor] = {
+            "action": torch.zeros(self.T + 1, E, A, 4, dtype=torch.float32, device=device),
+            "logp": torch.zeros(self.T + 1, E, A, 1, dtype=torch.float32, device=device),
+            "action_mean": torch.zeros(self.T + 1, E, A, 4, dtype=torch.float32, device=device),
+            "state_value": torch.zeros(self.T + 1, E, A, 1, dtype=torch.float32, device=device)}
 
     def slot(self, cfg: hs_config, device, i: int) -> OutputSet:
         return OutputSet(cfg, device, {k: v[i] for k, v in self.data.items()})
@@ -100,6 +108,10 @@ class RolloutStorage:
     def batch(self) -> Dict[str, torch.Tensor]:
         """``[E, T, ...]`` views (env-major indexing, time-major memory) of the finished rollout."""
         return {k: v[:self.T].transpose(0, 1) for k, v in self.data.items()}
+
+    def policy_batch(self) -> Dict[str, torch.Tensor]:
+        """``[E, T, ...]`` views of the attached policy's outputs (action, logp, action_mean, state_value)."""
+        return {k: v[:self.T].transpose(0, 1) for k, v in self.policy.items()}
 
 
 class HsEngine:
@@ -176,6 +188,50 @@ class HsEngine:
         if self.storage is not None and not reset:
             self._slot = i
         self._bind(i)
+
+    # ------------------------------------------------------------------ policy next to the tick
+    def attach_policy(self, actor, critic=None, deterministic: bool = False):
+        """Makes ``actor`` (a :class:`~mupe_b200.policy.FusedPolicy`) - and optionally ``critic`` - part of the tick:
+        :meth:`policy_tick` and the graphs captured afterwards run actor -> critic -> hs_step_pre -> hs_step_post_tp
+        on the observation the previous tick produced, i.e. one whole rollout step (``policy(td)`` + ``env.step(td)``
+        in the reference's collector) without a host round trip.  The actor's noise is drawn in its kernel
+        (``actor.seed(...)``); ``deterministic`` takes the mode instead.  Outputs land in ``policy_out`` (per output
+        set; rows of the rollout storage in rollout mode)."""
+        if actor.head_dim != 4 or not actor.is_actor:
+            raise _lib.HsError("attach_policy: the actor must be a DiagGaussian head over the 4 CTBR commands")
+        E, A, dev = self.E, self.A, self.device
+        self._actor, self._critic, self._deterministic = actor, critic, bool(deterministic)
+        if not deterministic and getattr(actor, "rng_state", None) is None:
+            actor.seed(0)
+        if self.storage is not None:
+            pol = self.storage.policy
+            self.policy_out = [{k: v[i] for k, v in pol.items()} for i in range(len(self.sets))]
+        else:
+            z = lambda w: torch.zeros(E, A, w, dtype=torch.float32, device=dev)
+            self.policy_out = [dict(action=z(4), logp=z(1), action_mean=z(4), state_value=z(1)) for _ in self.sets]
+        self._graphs = None
+        return self
+
+    def _launch_policy(self, prev: int, i: int):
+        """actor (+ critic) on the observation held by set ``prev``; results into policy_out[i]."""
+        obs, po = self.sets[prev], self.policy_out[i]
+        others = obs["state_others"] if self.A > 1 else None
+        self._actor.forward(obs["state_self"], others, obs["obs_cylinders"], sample=not self._deterministic,
+                            out={"head": po["action_mean"], "action": po["action"], "logp": po["logp"]})
+        if self._critic is not None:
+            self._critic.forward(obs["state_self"], others, obs["obs_cylinders"], out={"head": po["state_value"]})
+
+    def policy_tick(self, tp_weights=None, reset_pid: Optional[torch.Tensor] = None) -> OutputSet:
+        """One rollout step without CUDA graphs: actor -> critic -> tick -> fused predictor (4 launches)."""
+        prev, i = self.cur, self.next_index()
+        self._launch_policy(prev, i)
+        self._policy_launches = getattr(self, "_policy_launches", 0) + (2 if self._critic is not None else 1)
+        out = self.step_pre(self.policy_out[i]["action"], raw=True, reset_pid=reset_pid)
+        if self.cfg.use_tp_net:
+            if tp_weights is None:
+                raise _lib.HsError("policy_tick: use_tp_net needs tp_weights (fused predictor)")
+            self.step_post_tp(tp_weights)
+        return out
 
     @property
     def rollout_slot(self) -> int:
@@ -302,7 +358,10 @@ class HsEngine:
         self._graph_weights = tp_weights
         self._graph_raw = raw
         self._graphs = {}
-        self._graph_kernels = 2 if self.cfg.use_tp_net else 1
+        self._graph_kernels = (2 if self.cfg.use_tp_net else 1)
+        self._graph_policy_kernels = 0
+        if getattr(self, "_actor", None) is not None:
+            self._graph_policy_kernels = 2 if self._critic is not None else 1
         self._graph_replays = getattr(self, "_graph_replays", 0)      # cumulative, like hs_launch_count
         if self.storage is None:
             for i in range(len(self.sets)):
@@ -319,7 +378,11 @@ class HsEngine:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
             st = torch.cuda.current_stream(dev).cuda_stream
-            check(lib.hs_step_pre(self._h, self.graph_action.data_ptr(), 1 if self._graph_raw else 0,
+            action = self.graph_action
+            if getattr(self, "_actor", None) is not None:
+                self._launch_policy(prev, i)
+                action = self.policy_out[i]["action"]
+            check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if self._graph_raw else 0,
                                   self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
             if self.cfg.use_tp_net:
                 check(lib.hs_step_post_tp(self._h, C.byref(self._graph_weights), None, st), "hs_step_post_tp (capture)")
@@ -402,6 +465,7 @@ class HsEngine:
     def launches(self) -> int:
         """Kernels of libhs_b200.so launched so far (graph replays counted per captured kernel)."""
         n = int(lib.hs_launch_count(self._h))
+        n += getattr(self, "_policy_launches", 0) + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_policy_kernels", 0)
         if getattr(self, "_graph_captures", 0):
             n += (self._graph_replays - getattr(self, "_graph_captures", 0)) * self._graph_kernels   # capture calls counted once each
         return n

@@ -84,38 +84,56 @@ class FusedPolicy:
             check(lib.hs_policy_prepare(C.byref(w), self.blob.data_ptr(), self._stream()), "hs_policy_prepare")
         return self
 
+    def seed(self, seed: int, step: int = 0):
+        """(Re)creates the device RNG state {seed, step, 0, 0} used when ``forward(sample=True)`` draws the noise
+        in the kernel (counter-based Philox: a draw depends only on (seed, step, row))."""
+        self.rng_state = torch.tensor([seed & (2 ** 63 - 1), step, 0, 0], dtype=torch.int64, device=self.device)
+        return self
+
     def forward(self, state_self: torch.Tensor, state_others: Optional[torch.Tensor], cylinders: Optional[torch.Tensor],
-                eps: Optional[torch.Tensor] = None, out: Optional[Dict[str, torch.Tensor]] = None,
-                want_features: bool = False) -> Dict[str, torch.Tensor]:
+                eps: Optional[torch.Tensor] = None, sample: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
+                want_features: bool = False, want_eps: bool = False) -> Dict[str, torch.Tensor]:
         """state_self [..., 1, D], state_others [..., n_others, 3], cylinders [..., n_cyl, 5] (the
         ``("agents", "observation")`` entries, any leading batch dims).  Returns ``head`` [..., head_dim]
-        (action mean or state value) and, for an actor, ``action`` [..., head_dim] and ``logp`` [..., 1];
-        ``eps=None`` takes the mode (``deterministic=True``).  ``out`` may hold preallocated result tensors
-        (static buffers for CUDA-graph capture)."""
+        (action mean or state value) and, for an actor, ``action`` [..., head_dim] and ``logp`` [..., 1].
+        Noise: ``eps`` (caller-supplied standard normal), else ``sample=True`` (drawn in the kernel from the
+        state set by :meth:`seed`), else none - the mode, as ``deterministic=True``.  ``out`` may hold
+        preallocated result tensors (static buffers for CUDA-graph capture)."""
         D = self.self_dim
         if state_self.shape[-1] != D or state_self.dtype != torch.float32 or not state_self.is_contiguous():
             raise _lib.HsError(f"FusedPolicy: state_self must be contiguous float32 [..., 1, {D}]")
         lead = tuple(state_self.shape[:-2])
         R = state_self.numel() // D
-        chk = lambda t, n, d, name: t is not None and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == R * n * d
-        if self.n_others and not chk(state_others, self.n_others, 3, "state_others"):
+        chk = lambda t, n, d: t is not None and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == R * n * d
+        if self.n_others and not chk(state_others, self.n_others, 3):
             raise _lib.HsError("FusedPolicy: state_others must be contiguous float32 [..., n_others, 3]")
-        if self.n_cyl and not chk(cylinders, self.n_cyl, 5, "cylinders"):
+        if self.n_cyl and not chk(cylinders, self.n_cyl, 5):
             raise _lib.HsError("FusedPolicy: cylinders must be contiguous float32 [..., n_cyl, 5]")
         out = {} if out is None else out
         mk = lambda k, w: out.setdefault(k, torch.empty(lead + (w,), dtype=torch.float32, device=self.device))
-        head = mk("head", self.head_dim)
-        action = mk("action", self.head_dim) if self.is_actor else None
-        logp = mk("logp", 1) if self.is_actor else None
-        feat = mk("features", 128) if want_features else None
-        if eps is not None and (eps.numel() != R * self.head_dim or not eps.is_contiguous() or eps.dtype != torch.float32):
-            raise _lib.HsError("FusedPolicy: eps must be contiguous float32 [..., head_dim]")
-        ptr = lambda t: None if t is None else t.data_ptr()
+        io = _lib.hs_policy_io()
+        io.num_rows, io.n_others, io.n_cyl = R, self.n_others, self.n_cyl
+        io.state_self = state_self.data_ptr()
+        io.state_others = state_others.data_ptr() if self.n_others else None
+        io.cylinders = cylinders.data_ptr() if self.n_cyl else None
+        io.head_out = mk("head", self.head_dim).data_ptr()
+        if self.is_actor:
+            io.action, io.logp = mk("action", self.head_dim).data_ptr(), mk("logp", 1).data_ptr()
+            if eps is not None:
+                if eps.numel() != R * self.head_dim or not eps.is_contiguous() or eps.dtype != torch.float32:
+                    raise _lib.HsError("FusedPolicy: eps must be contiguous float32 [..., head_dim]")
+                io.eps = eps.data_ptr()
+            elif sample:
+                if getattr(self, "rng_state", None) is None:
+                    self.seed(0)
+                io.rng_state = self.rng_state.data_ptr()
+            if want_eps:
+                io.eps_out = mk("eps", self.head_dim).data_ptr()
+        if want_features:
+            io.feat_out = mk("features", 128).data_ptr()
         with torch.cuda.device(self.device):
-            check(lib.hs_policy_forward(self.blob.data_ptr(), D, self.n_others, self.n_cyl, self.head_dim, R,
-                                        state_self.data_ptr(), ptr(state_others) if self.n_others else None,
-                                        ptr(cylinders) if self.n_cyl else None, ptr(eps), head.data_ptr(), ptr(action),
-                                        ptr(logp), ptr(feat), self._stream()), "hs_policy_forward")
+            check(lib.hs_policy_forward(self.blob.data_ptr(), D, self.head_dim, C.byref(io), self._stream()),
+                  "hs_policy_forward")
         return out
 
     __call__ = forward

@@ -68,3 +68,30 @@ def actor(p, obs, eps=None):
 
 def critic(p, obs):
     return head(p, encoder(p, obs))
+
+
+def philox_normal(seed: int, step: int, num_rows: int, head_dim: int):
+    """The noise hs_policy_forward draws itself (csrc/hs_policy.cuh): Philox4x32-10 (oracle/reset_sampler.py, pinned
+    by the Random123 known-answer vectors), key = seed, counter = (row, step, block of four head columns);
+    Box-Muller on u0 in (0,1], u1 in [0,1).  fp32 like the kernel; log/sin/cos differ from CUDA's by ulps."""
+    import numpy as np
+    from oracle.reset_sampler import philox4x32_10
+    rows = np.arange(num_rows, dtype=np.uint64)
+    out = np.zeros((num_rows, 4 * ((head_dim + 3) // 4)), np.float32)
+    for blk in range((head_dim + 3) // 4):
+        ctr = np.stack([(rows & np.uint64(0xFFFFFFFF)), rows >> np.uint64(32),
+                        np.full(num_rows, step & 0xFFFFFFFF, np.uint64),
+                        np.full(num_rows, (((step >> 32) << 1) | blk) & 0xFFFFFFFF, np.uint64)], -1).astype(np.uint32)
+        key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], np.uint32), (num_rows, 2))
+        u = philox4x32_10(ctr, key)
+        f = np.float32
+        s24 = f(2.0 ** -24)
+        u0 = ((u[:, 0] >> np.uint32(8)).astype(f) + f(1)) * s24
+        u1 = (u[:, 1] >> np.uint32(8)).astype(f) * s24
+        u2 = ((u[:, 2] >> np.uint32(8)).astype(f) + f(1)) * s24
+        u3 = (u[:, 3] >> np.uint32(8)).astype(f) * s24
+        r0, r1 = np.sqrt(f(-2) * np.log(u0)).astype(f), np.sqrt(f(-2) * np.log(u2)).astype(f)
+        t0, t1 = (f(6.283185307179586) * u1).astype(f), (f(6.283185307179586) * u3).astype(f)
+        out[:, 4 * blk + 0], out[:, 4 * blk + 1] = r0 * np.cos(t0), r0 * np.sin(t0)
+        out[:, 4 * blk + 2], out[:, 4 * blk + 3] = r1 * np.cos(t1), r1 * np.sin(t1)
+    return torch.from_numpy(out[:, :head_dim].copy())

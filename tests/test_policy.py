@@ -88,3 +88,92 @@ def test_gpu_policy_ragged_sizes_against_oracle(built_lib, R):
         pg["head.bias"].add_(1.0)
     out2 = net.refresh()(og["state_self"], og["state_others"], og["cylinders"], eps=eps.to(dev))
     torch.testing.assert_close(out2["head"], out["head"] + 1.0, rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_noise_is_standard_normal():
+    z = PO.philox_normal(seed=7, step=3, num_rows=50000, head_dim=4)
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z[:, 0] * z[:, 1]).mean().item()) < 0.02           # Box-Muller pair uncorrelated
+    assert not torch.equal(z, PO.philox_normal(7, 4, 50000, 4))      # the step moves the stream
+
+
+@pytest.mark.gpu
+def test_gpu_policy_in_kernel_noise(built_lib):
+    """sample=True: the kernel draws the noise (Philox + Box-Muller) and advances the device step counter itself;
+    the noise equals the CPU restatement, the action is mean + std * noise, consecutive calls use consecutive steps,
+    and a re-seeded policy replays the same sequence."""
+    import mupe_b200
+    dev = torch.device("cuda:0")
+    p, obs, _ = _load("actor_tp")
+    pg = {k: v.to(dev).contiguous() for k, v in p.items()}
+    og = {k: v.to(dev).contiguous() for k, v in obs.items()}
+    R = obs["state_self"].shape[0]
+    net = mupe_b200.FusedPolicy(pg, 2, 3, dev).seed(1234, step=5)
+    seq = []
+    for k in range(3):
+        out = net(og["state_self"], og["state_others"], og["cylinders"], sample=True, want_eps=True)
+        want = PO.philox_normal(1234, 5 + k, R, 4)
+        torch.testing.assert_close(out["eps"].cpu(), want, rtol=1e-4, atol=1e-5)
+        a, lp, _ = PO.actor(p, obs, out["eps"].cpu())
+        torch.testing.assert_close(out["action"].cpu(), a, rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(out["logp"].cpu(), lp, rtol=1e-4, atol=1e-5)
+        seq.append(out["action"].clone())
+    assert net.rng_state.cpu().tolist() == [1234, 8, 0, 0]
+    net.seed(1234, step=5)
+    again = net(og["state_self"], og["state_others"], og["cylinders"], sample=True)["action"]
+    assert torch.equal(again, seq[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rollout_steps", [0, 6])
+def test_gpu_policy_in_the_tick_graph(built_lib, rollout_steps):
+    """attach_policy: actor -> critic -> tick -> predictor replayed as ONE CUDA graph per rollout step must equal, bit
+    for bit, the same four kernels launched one by one (policy_tick), in ring mode and in rollout-storage mode (where
+    action / logp / value land in the time-major rollout rows); and the action it fed to the tick is the actor's."""
+    import mupe_b200
+    dev = torch.device("cuda:0")
+    E, T = 96, 6
+    p, _, _ = _load("actor_tp")
+    pc, _, _ = _load("critic_tp")
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(16, 15, 5).to(dev)
+    g = torch.Generator().manual_seed(2)
+    a = 0.9 / 2 ** 0.5
+    init = dict(drone_pos=torch.rand(E, 3, 3, generator=g) * 0.4 + torch.tensor([0.1, -0.2, 0.5]),
+                drone_rot=torch.tensor([1.0, 0, 0, 0]).expand(E, 3, 4).contiguous(),
+                target_pos=torch.rand(E, 3, generator=g) * 0.4 + torch.tensor([-0.5, -0.2, 0.5]),
+                cyl_pos=torch.cat([torch.rand(E, 5, 2, generator=g) - 0.5, torch.full((E, 5, 1), 0.6)], -1))
+    runs = []
+    for use_graph in (False, True):
+        eng = mupe_b200.HsEngine(mupe_b200.build_hs_config(E), dev, rollout_steps=rollout_steps or None)
+        actor = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in p.items()}, 2, 3, dev).seed(99)
+        critic = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in pc.items()}, 2, 3, dev)
+        w = eng.tp_weights(tp)
+        eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        eng.step_post_tp(w)
+        eng.attach_policy(actor, critic)
+        if use_graph:
+            eng.capture_tick_graphs(w, raw=True)
+        rec = []
+        for t in range(T):
+            prev = eng.cur
+            out = eng.replay_tick() if use_graph else eng.policy_tick(w)
+            po = eng.policy_out[eng.cur]
+            rec.append({k: out[k].clone() for k in ("state_self", "reward", "drone_state", "tp_input")} |
+                       {k: v.clone() for k, v in po.items()})
+            if t == 0 and not use_graph:       # the tick consumed the actor's action: same result as feeding it by hand
+                obs = eng.sets[prev]
+                chk = actor.forward(obs["state_self"], obs["state_others"], obs["obs_cylinders"], eps=None)
+                torch.testing.assert_close(chk["head"], po["action_mean"], rtol=0, atol=0)
+        if rollout_steps:
+            pb = eng.storage.policy_batch()
+            assert tuple(pb["action"].shape) == (E, T, 3, 4)
+            assert torch.equal(pb["logp"][:, T - 1], rec[-1]["logp"])
+        assert eng.launches >= 4 * T
+        runs.append(rec)
+        eng.close()
+    for t in range(T):
+        for k in runs[0][t]:
+            assert torch.equal(runs[0][t][k], runs[1][t][k]), f"tick {t}: {k} differs between graph replay and direct launches"
+    assert not torch.equal(runs[0][0]["action"], runs[0][1]["action"])
+    assert runs[0][0]["state_value"].abs().sum() > 0
