@@ -412,6 +412,39 @@ def run_gpu_arm(args):
                         "recurrence of 32- or 128-env tiles is bound by the per-step MMA -> epilogue -> MMA dependency "
                         "(latency), not by tensor throughput; fp32-FFMA ceiling for the same math: "
                         f"{simt_peak:.1f} TFLOP/s, this kernel delivers {tf:.1f} TFLOP/s of fp32-equivalent math"}
+        # ---- the whole rollout step of the reference's collector (policy(td) + env.step(td)) as ONE CUDA graph:
+        # fused actor + fused critic (PartialAttentionEncoder, random init, noise drawn in the kernel) -> tick -> predictor
+        try:
+            from mupe_b200.policy import FusedPolicy, init_params
+            D_self = 20 + 3 * F
+            pe = mupe_b200.HsEngine(mupe_b200.build_hs_config(E, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
+                                                              future_step=F, history_step=H), dev)
+            s0 = engines[0]
+            pe.reset(None, s0.get_state(0), s0.get_state(1), s0.get_state(7), s0.get_state(9))
+            wpe = pe.tp_weights(tp_net)
+            pe.step_post_tp(wpe)
+            actor = FusedPolicy(init_params(D_self, A - 1, K, 4, True, dev), A - 1, K, dev).seed(1)
+            critic = FusedPolicy(init_params(D_self, A - 1, K, 1, False, dev), A - 1, K, dev)
+            pe.attach_policy(actor, critic)
+            pe.capture_tick_graphs(wpe, raw=True)
+            for _ in range(8):
+                pe.replay_tick()
+            torch.cuda.synchronize()
+            npol = max(64, min(args.steps, 512))
+            k0.record()
+            for _ in range(npol):
+                pe.replay_tick()
+            k1.record()
+            torch.cuda.synchronize()
+            pol_us = 1e3 * k0.elapsed_time(k1) / npol
+            extra["rollout_step_with_policy"] = {
+                "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us, "launches_per_step": 4,
+                "what": "one CUDA graph per rollout step: hs_policy_forward (actor, in-kernel noise) + hs_policy_forward "
+                        "(critic) + hs_tick_kernel + fused predictor, observation never leaves HBM; same 4096-env batch "
+                        "every step (L2-warm), single GPU"}
+            pe.close()
+        except Exception as ex:
+            extra["rollout_step_with_policy"] = {"error": repr(ex)[:200]}
         # ---- end to end through env.step(): pinned host actions in; observation, reward, done out
         h_act = torch.randn(E, A, 4).pin_memory()
         d_act = torch.empty(E, A, 4, device=dev)

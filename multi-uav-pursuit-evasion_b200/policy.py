@@ -45,6 +45,33 @@ def _find(params: Mapping[str, torch.Tensor], names, required=True):
     return None
 
 
+def init_params(self_dim: int, n_others: int, n_cyl: int, head_dim: int, actor: bool, device="cuda:0",
+                gain: float = 0.01) -> Dict[str, torch.Tensor]:
+    """Fresh parameters with the reference's shapes and initialisers (torch defaults for the encoder,
+    networks.py:126-151, 249-279; orthogonal(gain) head with zero bias and log_std = 0, distributions.py:66-76,
+    mappo.py:596-603) under the reference's state_dict names - for benchmarks and tests, and as the layout a
+    learner's own modules must have."""
+    import torch.nn as nn
+    mods = {"split_embed.embed.state_self": nn.Linear(self_dim, 128), "split_embed.layer_norm": nn.LayerNorm(128),
+            "attn": nn.MultiheadAttention(128, 1, batch_first=True), "linear1": nn.Linear(128, 128),
+            "linear2": nn.Linear(128, 128), "norm1": nn.LayerNorm(128), "norm2": nn.LayerNorm(128)}
+    if n_others:
+        mods["split_embed.embed.state_others"] = nn.Linear(3, 128)
+    if n_cyl:
+        mods["split_embed.embed.cylinders"] = nn.Linear(5, 128)
+    head = nn.Linear(128, head_dim)
+    nn.init.orthogonal_(head.weight, gain)
+    nn.init.zeros_(head.bias)
+    out = {}
+    for name, m in mods.items():
+        for k, v in m.state_dict().items():
+            out[f"{name}.{k}"] = v.detach().to(device).contiguous()
+    out["head.weight"], out["head.bias"] = head.weight.detach().to(device).contiguous(), head.bias.detach().to(device)
+    if actor:
+        out["log_std"] = torch.zeros(head_dim, device=device)
+    return out
+
+
 class FusedPolicy:
     """One network (actor or critic) bound to its live parameters."""
 
