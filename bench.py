@@ -267,7 +267,7 @@ def run_gpu_arm(args):
         def c_step(i):
             r = i % ROTATE
             return engines[r].step_host(h_act_c, wts[r], raw=True)
-        for i in range(ROTATE):
+        for i in range(3 * ROTATE):          # warm-up: every engine captures the graph of each of its two output sets
             views, done_h = c_step(i)
         barrier()
         t0 = time.perf_counter()
@@ -280,9 +280,10 @@ def run_gpu_arm(args):
         d2h = sum(v.numel() for v in views.values()) * 4 + done_h.numel()
         e2e_c = {"value": world * E * ne_c / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4,
                  "d2h_bytes_per_step": d2h, "steps": ne_c, "n_gpus": world,
-                 "api": "C ABI hs_step_host_io(): pinned host action -> H2D -> hs_step_pre -> hs_step_post_tp -> D2H of "
+                 "api": "C ABI hs_step_host_io(): pinned host action (read in place over PCIe by the tick kernel, UVA) -> hs_step_pre -> hs_step_post_tp -> D2H of "
                         "observation (state_self, state_others, obs_cylinders) + reward + done into host buffers -> "
-                        "stream sync, every tick, every rank; wall clock, max over ranks"}
+                        "stream sync, every tick, every rank (one cached CUDA graph launch per call: memcpy + kernel "
+                        "nodes, the tick's own outputs copied under the predictor); wall clock, max over ranks"}
     if rank == 0 and timed_only:
         extra["note"] = "HS_BENCH_TIMED_ONLY=1: roofline / e2e / cpu_baseline legs skipped (launch-list capture run)"
     elif rank == 0:

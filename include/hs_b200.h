@@ -256,8 +256,12 @@ int64_t hs_launch_count(const hs_handle* h);
  *     128 envs per CTA (envs on the MMA's M dimension),
  * 3 = tcgen05.mma with the gates on M, weights resident in TMEM, 32 envs per CTA on N (fills the SMs
  *     at small batches),
- * 4 = as 3 with two 32-env tiles ping-ponging per CTA (one tile's MMAs run under the other's cell update). */
-enum { HS_OPT_PREDICTOR_VARIANT = 1 };
+ * 4 = as 3 with two 32-env tiles ping-ponging per CTA (one tile's MMAs run under the other's cell update).
+ * HS_OPT_HOST_IO_GRAPH: 1 (default) = hs_step_host_io replays its copies and kernels as ONE CUDA graph
+ * launch, cached per set of pointers (host buffers, bound outputs, weights); 0 = plain stream calls.
+ * HS_OPT_HOST_IO_ZERO_COPY_ACTION: 1 (default) = a page-locked io->action is read in place by the tick
+ * kernel (UVA), no H2D copy; 0 = always copy into the staging buffer first. */
+enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3 };
 int hs_set_option(hs_handle* h, int option, int value);
 
 /* ---- device-side reset sampler --------------------------- */

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
 HS_ABI_VERSION = 1
 HS_NUM_STATS = 24
 HS_OPT_PREDICTOR_VARIANT = 1
+HS_OPT_HOST_IO_GRAPH = 2
+HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3
 
 # field ids, include/hs_b200.h
 (FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,

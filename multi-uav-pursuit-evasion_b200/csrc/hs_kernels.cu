@@ -62,6 +62,19 @@ struct hs_handle {
     // hs_step_host_io: side stream that carries the tick's own outputs to the host while the predictor runs
     cudaStream_t io_stream = nullptr;
     cudaEvent_t io_tick_done = nullptr, io_copy_done = nullptr;
+    // ... and the whole host-to-host tick as ONE graph launch (memcpy + kernel nodes), cached per pointer set
+    struct IoKey {
+        hs_host_io io; hs_buffers bufs; hs_tp_weights w;
+        const void* staging; const void* reset_pid;
+        int raw, tp_init, variant, has_w;
+    };
+    struct IoGraph { IoKey key; cudaGraphExec_t exec; uint64_t last_use; };
+    static constexpr int IO_GRAPHS = 8;
+    IoGraph io_graphs[IO_GRAPHS] = {};
+    cudaStream_t io_capture = nullptr;
+    uint64_t io_clock = 0;
+    int io_graph_mode = 1;       // HS_OPT_HOST_IO_GRAPH: 1 = graph launch (default), 0 = stream API calls
+    int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
 };
 
 static thread_local char g_err[512] = "";
@@ -267,6 +280,8 @@ int hs_destroy(hs_handle* h) {
         if (h->io_tick_done) cudaEventDestroy(h->io_tick_done);
         if (h->io_copy_done) cudaEventDestroy(h->io_copy_done);
         if (h->io_stream) cudaStreamDestroy(h->io_stream);
+        for (auto& g : h->io_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (h->io_capture) cudaStreamDestroy(h->io_capture);
     }
     delete h;
     return HS_OK;
@@ -631,16 +646,28 @@ int hs_step_host(hs_handle* h, const float* action_host, int action_is_raw, floa
     return HS_OK;
 }
 
-int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
-                    float* staging_dev, void* stream) {
-    if (!h || !io || !io->action || !staging_dev) return set_err(HS_ERR_INVALID, "hs_step_host_io: null argument%s");
-    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_host_io: call hs_bind_buffers first%s");
-    if (h->cfg.use_tp_net && !w) return set_err(HS_ERR_INVALID, "hs_step_host_io: use_tp_net == 1 needs the predictor weights%s");
+// Enqueues H2D action -> tick -> {D2H of the tick's own outputs on the side stream || predictor -> D2H state_self} on `s`
+// (no synchronisation).  Runs either directly or under stream capture.
+static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
+                           float* staging_dev, void* stream) {
     const hs_config& c = h->cfg;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t EA = (size_t)c.num_envs * c.num_agents;
-    CUDA_OK(cudaMemcpyAsync(staging_dev, io->action, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = hs_step_pre(h, staging_dev, action_is_raw, reset_pid, stream);
+    // Pinned (page-locked, UVA-mapped) action buffers are read by the tick kernel straight over PCIe - 48 B per
+    // pursuer, prefetched at kernel entry - which removes the H2D copy node and its dependency from the critical
+    // path; pageable memory goes through the staging buffer.
+    const float* action_dev = staging_dev;
+    {
+        cudaPointerAttributes pa;
+        const cudaError_t e = cudaPointerGetAttributes(&pa, io->action);
+        if (e == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr && h->io_zero_copy_action)
+            action_dev = static_cast<const float*>(pa.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
+    if (action_dev == staging_dev)
+        CUDA_OK(cudaMemcpyAsync(staging_dev, io->action, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = hs_step_pre(h, action_dev, action_is_raw, reset_pid, stream);
     if (rc != HS_OK) return rc;
     const size_t D = 20 + (c.use_tp_net ? 3 * (size_t)c.future_step : 0);
     // seg[0] is written by the predictor kernel (use_tp_net) -- the rest is complete after the tick
@@ -688,6 +715,58 @@ int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const
     } else {
         CUDA_OK(copy_segments(0, 5, s));
     }
+    return HS_OK;
+}
+
+int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
+                    float* staging_dev, void* stream) {
+    if (!h || !io || !io->action || !staging_dev) return set_err(HS_ERR_INVALID, "hs_step_host_io: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_host_io: call hs_bind_buffers first%s");
+    if (h->cfg.use_tp_net && !w) return set_err(HS_ERR_INVALID, "hs_step_host_io: use_tp_net == 1 needs the predictor weights%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->io_graph_mode) {
+        const int rc = host_io_enqueue(h, io, action_is_raw, reset_pid, w, staging_dev, stream);
+        if (rc != HS_OK) return rc;
+        CUDA_OK(cudaStreamSynchronize(s));
+        return HS_OK;
+    }
+    // one graph launch per tick: the seven stream calls above cost ~25 us of host time per tick at 4096 envs.
+    // A graph is valid for one exact set of pointers (host buffers, bound output set, weights) -> small LRU cache.
+    hs_handle::IoKey key;
+    memset(&key, 0, sizeof(key));
+    key.io = *io; key.bufs = h->bufs;
+    if (w) { key.w = *w; key.has_w = 1; }
+    key.staging = staging_dev; key.reset_pid = reset_pid; key.raw = action_is_raw;
+    key.tp_init = (h->cfg.use_tp_net && h->tp_frames == 0) ? 1 : 0;
+    key.variant = h->tp_variant;
+    hs_handle::IoGraph* slot = nullptr;
+    for (auto& g : h->io_graphs)
+        if (g.exec && memcmp(&g.key, &key, sizeof(key)) == 0) { slot = &g; break; }
+    const int kernels = h->cfg.use_tp_net ? 2 : 1;
+    if (slot) {
+        h->launches += kernels;                              // the captured calls counted themselves once, at capture
+        if (h->cfg.use_tp_net) h->tp_frames += 1;
+    } else {
+        slot = &h->io_graphs[0];
+        for (auto& g : h->io_graphs) {
+            if (!g.exec) { slot = &g; break; }
+            if (g.last_use < slot->last_use) slot = &g;
+        }
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        if (!h->io_capture) CUDA_OK(cudaStreamCreateWithFlags(&h->io_capture, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamBeginCapture(h->io_capture, cudaStreamCaptureModeThreadLocal));
+        const int rc = host_io_enqueue(h, io, action_is_raw, reset_pid, w, staging_dev, h->io_capture);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->io_capture, &graph);
+        if (rc != HS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || !graph) return set_err(HS_ERR_CUDA, "hs_step_host_io: stream capture failed: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { slot->exec = nullptr; return set_err(HS_ERR_CUDA, "hs_step_host_io: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+        slot->key = key;
+    }
+    slot->last_use = ++h->io_clock;
+    CUDA_OK(cudaGraphLaunch(slot->exec, s));
     CUDA_OK(cudaStreamSynchronize(s));
     return HS_OK;
 }
@@ -741,6 +820,15 @@ int hs_set_option(hs_handle* h, int option, int value) {
         case HS_OPT_PREDICTOR_VARIANT:
             if (value < -1 || value > 4) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles), 3 (tcgen05, 32-env tiles) or 4 (tcgen05, 2 x 32-env tiles ping-pong)%s");
             h->tp_variant = value;
+            return HS_OK;
+        case HS_OPT_HOST_IO_ZERO_COPY_ACTION:
+            if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_ZERO_COPY_ACTION must be 0 or 1%s");
+            h->io_zero_copy_action = value;
+            for (auto& g : h->io_graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            return HS_OK;
+        case HS_OPT_HOST_IO_GRAPH:
+            if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_GRAPH must be 0 or 1%s");
+            h->io_graph_mode = value;
             return HS_OK;
         default:
             return set_err(HS_ERR_INVALID, "unknown option%s");

@@ -276,28 +276,35 @@ class HsEngine:
             mirror = torch.empty(npol, dtype=torch.float32).pin_memory()
             self._host = dict(mirror=mirror, done=torch.empty(E, dtype=torch.uint8).pin_memory(),
                               staging=torch.empty(E, A, 4, dtype=torch.float32, device=self.device))
+            self._host["staging_ptr"] = self._host["staging"].data_ptr()
         hm = self._host
         self._advance()
-        out = self.out
-        base = out.slab.data_ptr()
-        io = _lib.hs_host_io()
+        cached = hm.setdefault("io", {}).get(self.cur)
+        if cached is None:
+            # per output set: the io struct and the host views never change (static buffers)
+            out = self.out
+            base = out.slab.data_ptr()
+            io = _lib.hs_host_io()
+            views = {}
+            for k in ("state_self", "state_others", "obs_cylinders", "reward"):
+                t = out.t[k]
+                off = (t.data_ptr() - base) // 4
+                views[k] = hm["mirror"][off:off + t.numel()].view(t.shape)
+                setattr(io, k, views[k].data_ptr() if t.numel() else None)
+            io.done = hm["done"].data_ptr()
+            cached = hm["io"][self.cur] = (io, C.byref(io), views)
+        io, io_ref, views = cached
         io.action = action_host.data_ptr()
-        views = {}
-        for k in ("state_self", "state_others", "obs_cylinders", "reward"):
-            t = out.t[k]
-            off = (t.data_ptr() - base) // 4
-            views[k] = hm["mirror"][off:off + t.numel()].view(t.shape)
-            setattr(io, k, views[k].data_ptr() if t.numel() else None)
-        io.done = hm["done"].data_ptr()
         rp = None
         if reset_pid is not None:
             rp = reset_pid.reshape(E)
             rp = rp.view(torch.uint8) if rp.dtype == torch.bool else rp.to(torch.uint8)
             rp = rp.contiguous()
         self._keep = [action_host, rp]
-        check(lib.hs_step_host_io(self._h, C.byref(io), 1 if raw else 0, _ptr(rp),
-                                  C.byref(weights) if weights is not None else None, hm["staging"].data_ptr(),
-                                  self._stream()), "hs_step_host_io")
+        rc = lib.hs_step_host_io(self._h, io_ref, 1 if raw else 0, _ptr(rp),
+                                 C.byref(weights) if weights is not None else None, hm["staging_ptr"], self._stream())
+        if rc != 0:
+            check(rc, "hs_step_host_io")
         return views, hm["done"]
 
     def step_post(self, tp_pred: torch.Tensor) -> OutputSet:

@@ -224,10 +224,14 @@ def test_fused_predictor_matches_torch_lstm(A, E, variant):
     eng.close()
 
 
-def test_host_buffer_tick_with_predictor():
+@pytest.mark.parametrize("graph_mode", [1, 0])
+def test_host_buffer_tick_with_predictor(graph_mode):
     """hs_step_host_io: host action in -> tick + fused predictor -> observation/reward/done in host
-    buffers, one C-ABI call; must equal the device-side path on a twin engine."""
+    buffers, one C-ABI call; must equal the device-side path on a twin engine - both as ONE cached CUDA
+    graph launch per tick (default; 7 ticks = several replays of both output sets' graphs, a fresh
+    action buffer forces a re-capture) and as plain stream calls (HS_OPT_HOST_IO_GRAPH = 0)."""
     import mupe_b200
+    from mupe_b200 import _lib
     P, E = O.HSParams(), 300
     dev = torch.device("cuda:0")
     cfg = hs_config_from_params(P, E)
@@ -239,14 +243,19 @@ def test_host_buffer_tick_with_predictor():
     for e in engs:
         e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
         e.step_post_tp(e.tp_weights(tp))
-    for t in range(3):
-        act = torch.randn(E, 3, 4, generator=g).pin_memory()
+    _lib.check(_lib.lib.hs_set_option(engs[1]._h, _lib.HS_OPT_HOST_IO_GRAPH, graph_mode), "hs_set_option")
+    act = torch.empty(E, 3, 4).pin_memory()
+    for t in range(7):
+        if t == 5:
+            act = torch.empty(E, 3, 4).pin_memory()          # new host pointer -> new graph
+        act.copy_(torch.randn(E, 3, 4, generator=g))
         ref = engs[0].step_pre(act.to(dev), raw=True)
         engs[0].step_post_tp(engs[0].tp_weights(tp))
         views, done = engs[1].step_host(act, engs[1].tp_weights(tp), raw=True)
         for k in ("state_self", "state_others", "obs_cylinders", "reward"):
             assert torch.equal(views[k], ref[k].cpu()), (t, k)
         assert torch.equal(done.bool(), ref["done"].reshape(E).cpu())
+    assert engs[0].launches == engs[1].launches
     for e in engs:
         e.close()
 
