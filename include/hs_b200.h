@@ -195,6 +195,14 @@ typedef struct hs_tp_weights {
     int32_t reserved;
 } hs_tp_weights;
 int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, void* stream);
+/* hs_step_pre + hs_step_post_tp as one call - and, when the batch has at most one 32-env tile per
+ * SM (<= 4736 envs on a B200), the predictor policy is auto or 3, and A <= 3, as ONE kernel launch
+ * (hs_tick_tp_fused_kernel: four warps of each CTA run the tick of the tile's envs while the others
+ * stage the predictor's weights, then the CTA runs the tcgen05 predictor on the TP_input tiles still
+ * in shared memory).  Results are identical to the two-call sequence.  Arguments as in hs_step_pre
+ * and hs_step_post_tp. */
+int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const uint8_t* reset_pid,
+                  const hs_tp_weights* w, float* tp_pred_out, void* stream);
 /* Partial reset.  env_mask [E] bool (NULL = all).  Initial poses are injected (sampling
  * stays on the host side so that it can follow the reference's RNG streams):
  *   drone_pos [E,A,3], drone_rot [E,A,4] (wxyz), target_pos [E,3], cyl_pos [E,C,3];
@@ -260,8 +268,9 @@ int64_t hs_launch_count(const hs_handle* h);
  * HS_OPT_HOST_IO_GRAPH: 1 (default) = hs_step_host_io replays its copies and kernels as ONE CUDA graph
  * launch, cached per set of pointers (host buffers, bound outputs, weights); 0 = plain stream calls.
  * HS_OPT_HOST_IO_ZERO_COPY_ACTION: 1 (default) = a page-locked io->action is read in place by the tick
- * kernel (UVA), no H2D copy; 0 = always copy into the staging buffer first. */
-enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3 };
+ * kernel (UVA), no H2D copy; 0 = always copy into the staging buffer first.
+ * HS_OPT_FUSED_TICK: 1 (default) = hs_step_fused may use the one-launch kernel; 0 = always two launches. */
+enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4 };
 int hs_set_option(hs_handle* h, int option, int value);
 
 /* ---- device-side reset sampler --------------------------- */

@@ -15,6 +15,7 @@ HS_NUM_STATS = 24
 HS_OPT_PREDICTOR_VARIANT = 1
 HS_OPT_HOST_IO_GRAPH = 2
 HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3
+HS_OPT_FUSED_TICK = 4
 
 # field ids, include/hs_b200.h
 (FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,
@@ -138,6 +139,7 @@ _EXPORTS = {
     "hs_bind_buffers": (C.c_int, [C.c_void_p, C.POINTER(hs_buffers)]),
     "hs_step_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_step_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_step_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
     "hs_step_post_tp": (C.c_int, [C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
     "hs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

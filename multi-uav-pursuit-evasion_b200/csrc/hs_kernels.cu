@@ -73,6 +73,8 @@ struct hs_handle {
     IoGraph io_graphs[IO_GRAPHS] = {};
     cudaStream_t io_capture = nullptr;
     uint64_t io_clock = 0;
+    int fused_tick = 1;          // HS_OPT_FUSED_TICK: hs_step_fused may use the one-launch kernel
+    int io_fused = 0;            // hs_step_host_io: two kernels + overlapped copy (0) or the one-launch kernel (1); see DESIGN.md
     int io_graph_mode = 1;       // HS_OPT_HOST_IO_GRAPH: 1 = graph launch (default), 0 = stream API calls
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
 };
@@ -269,6 +271,17 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
                 default: e = cudaFuncSetAttribute(hs_tp_fill_tcw_kernel<3>, attr, t); break;
             }
         }
+        if (e == cudaSuccess && tp_fused_smem_bytes(*cfg) <= HS_MAX_DYN_SMEM) {
+            const int t = (int)tp_fused_smem_bytes(*cfg);
+            const bool small_c = cfg->num_cylinders <= 5;
+#define HS_FATTR(AA) (small_c ? cudaFuncSetAttribute(hs_tick_tp_fused_kernel<AA, 5>, attr, t) : cudaFuncSetAttribute(hs_tick_tp_fused_kernel<AA, 8>, attr, t))
+            switch (cfg->num_agents) {
+                case 1: e = HS_FATTR(1); break;
+                case 2: e = HS_FATTR(2); break;
+                default: e = HS_FATTR(3); break;
+            }
+#undef HS_FATTR
+        }
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
     }
     *out = h;
@@ -322,6 +335,50 @@ int hs_step_pre(hs_handle* h, const float* action, int action_is_raw, const uint
     CUDA_OK(launch_tick<false>(h, P, (cudaStream_t)stream));
     h->launches += 1;
     if (h->cfg.use_tp_net) h->tp_frames += 1;
+    return HS_OK;
+}
+
+// One control tick including the predictor.  Small batches (at most one 32-env tile per SM, auto predictor policy):
+// ONE launch of hs_tick_tp_fused_kernel; otherwise hs_step_pre followed by hs_step_post_tp.  Same results either way.
+int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
+                  float* tp_pred_out, void* stream) {
+    if (!h || !action || !w) return set_err(HS_ERR_INVALID, "hs_step_fused: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_fused: call hs_bind_buffers first%s");
+    if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_fused: config has use_tp_net == 0 (use hs_step_pre)%s");
+    const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
+    const bool one_launch = h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 3) && tiles32 <= h->num_sms &&
+                            tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
+    if (!one_launch) {
+        const int rc = hs_step_pre(h, action, action_is_raw, reset_pid, stream);
+        return rc != HS_OK ? rc : hs_step_post_tp(h, w, tp_pred_out, stream);
+    }
+    if (!w->weight_ih || !w->weight_hh || !w->bias_ih || !w->bias_hh || !w->fc_weight || !w->fc_bias)
+        return set_err(HS_ERR_INVALID, "hs_step_fused: a weight pointer is NULL%s");
+    if (w->hidden_size != TP_HID || w->input_size != 7 + 3 * h->cfg.num_agents || w->output_size != 3 * h->cfg.future_step)
+        return set_err(HS_ERR_INVALID, "hs_step_fused: predictor shape must be LSTM(7+3A -> 64) + Linear(64 -> 3F)%s");
+    KParams P = make_params(h);
+    P.action = action;
+    P.action_is_raw = action_is_raw;
+    P.reset_pid = reset_pid;
+    P.tp_init = (h->tp_frames == 0) ? 1 : 0;
+    TPParams W;
+    W.w_ih = w->weight_ih; W.w_hh = w->weight_hh; W.b_ih = w->bias_ih; W.b_hh = w->bias_hh;
+    W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = tp_pred_out;
+    const size_t smem = tp_fused_smem_bytes(h->cfg);
+    const unsigned grid = (unsigned)tiles32;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool small_c = h->cfg.num_cylinders <= 5;
+#define HS_FUSED(AA) do { if (small_c) hs_tick_tp_fused_kernel<AA, 5><<<grid, TN_THREADS, smem, s>>>(P, W); \
+                          else hs_tick_tp_fused_kernel<AA, 8><<<grid, TN_THREADS, smem, s>>>(P, W); } while (0)
+    switch (h->cfg.num_agents) {
+        case 1: HS_FUSED(1); break;
+        case 2: HS_FUSED(2); break;
+        default: HS_FUSED(3); break;
+    }
+#undef HS_FUSED
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    h->tp_frames += 1;
     return HS_OK;
 }
 
@@ -667,7 +724,13 @@ static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw
     }
     if (action_dev == staging_dev)
         CUDA_OK(cudaMemcpyAsync(staging_dev, io->action, EA * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = hs_step_pre(h, action_dev, action_is_raw, reset_pid, stream);
+    // one-launch tick + predictor when the batch qualifies: nothing is complete before that kernel ends, so the
+    // whole observation follows it in one copy (the side-branch overlap below is for the two-kernel sequence)
+    const int64_t tiles32 = ((int64_t)c.num_envs + TN_E - 1) / TN_E;
+    const bool one_launch = c.use_tp_net && h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 3) && tiles32 <= h->num_sms &&
+                            tp_fused_smem_bytes(c) <= HS_MAX_DYN_SMEM && h->io_fused;
+    int rc = one_launch ? hs_step_fused(h, action_dev, action_is_raw, reset_pid, w, nullptr, stream)
+                        : hs_step_pre(h, action_dev, action_is_raw, reset_pid, stream);
     if (rc != HS_OK) return rc;
     const size_t D = 20 + (c.use_tp_net ? 3 * (size_t)c.future_step : 0);
     // seg[0] is written by the predictor kernel (use_tp_net) -- the rest is complete after the tick
@@ -697,7 +760,9 @@ static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw
         }
         return cudaSuccess;
     };
-    if (c.use_tp_net) {
+    if (one_launch) {
+        CUDA_OK(copy_segments(0, 5, s));
+    } else if (c.use_tp_net) {
         // the rows the tick itself completed travel on a side stream while the predictor kernel runs
         if (!h->io_stream) {
             CUDA_OK(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
@@ -820,6 +885,11 @@ int hs_set_option(hs_handle* h, int option, int value) {
         case HS_OPT_PREDICTOR_VARIANT:
             if (value < -1 || value > 4) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles), 3 (tcgen05, 32-env tiles) or 4 (tcgen05, 2 x 32-env tiles ping-pong)%s");
             h->tp_variant = value;
+            return HS_OK;
+        case HS_OPT_FUSED_TICK:
+            if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_FUSED_TICK must be 0 or 1%s");
+            h->fused_tick = value;
+            for (auto& g : h->io_graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             return HS_OK;
         case HS_OPT_HOST_IO_ZERO_COPY_ACTION:
             if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_ZERO_COPY_ACTION must be 0 or 1%s");

@@ -373,21 +373,23 @@ struct TnLane {                 // per-thread constants of the epilogue
 // the 80 k-columns of (M-tile cg>>1, hi|lo = cg&1) of its 32 lanes with tcgen05.st.  The rows are
 // PRE-SCALED by the constant of their activation (-log2 e for the sigmoid gates, +2 log2 e for the tanh
 // gate), so the accumulator already holds the argument of ex2 in the cell update.
-template <int FD, int NTHREADS = TN_THREADS>
-__device__ __forceinline__ void tn_stage_weights(const TPParams& W, float* wst, uint32_t lane_base, int row, int cg) {
-    const int tid = threadIdx.x;
+// (1) global -> staging tile, by the `nt` threads numbered t = 0..nt-1
+template <int FD>
+__device__ __forceinline__ void tn_stage_weights_g2s(const TPParams& W, float* wst, int t, int nt) {
     auto lane_of = [](int wr) { const int g = wr >> 6, u = wr & 63; return (g >> 1) * 128 + 2 * u + (g & 1); };
 #pragma unroll 8
-    for (int i = tid; i < 256 * TP_HID; i += NTHREADS) {
+    for (int i = t; i < 256 * TP_HID; i += nt) {
         const int wr = i >> 6, k = i & 63;
         wst[lane_of(wr) * TN_WPITCH + 16 + k] = __ldg(W.w_hh + i);
     }
 #pragma unroll 8
-    for (int i = tid; i < 256 * 16; i += NTHREADS) {
+    for (int i = t; i < 256 * 16; i += nt) {
         const int wr = i >> 4, k = i & 15;
         wst[lane_of(wr) * TN_WPITCH + k] = (k < FD) ? __ldg(W.w_ih + wr * FD + k) : 0.0f;
     }
-    __syncthreads();
+}
+// (2) staging tile -> TMEM, by the 16 warps (quarter = warp & 3, part cg = warp >> 2 < 4)
+__device__ __forceinline__ void tn_stage_weights_s2t(const float* wst, uint32_t lane_base, int row, int cg) {
     if (cg >= 4) return;                                    // (a dedicated issuing warp only helps with the copy above)
     const int tl = cg >> 1, want_lo = cg & 1;
     const float L2E = 1.4426950408889634f;
@@ -409,6 +411,12 @@ __device__ __forceinline__ void tn_stage_weights(const TPParams& W, float* wst, 
                         "r"(vv[14]), "r"(vv[15]) : "memory");
     }
     tc_wait_st();
+}
+template <int FD, int NTHREADS = TN_THREADS>
+__device__ __forceinline__ void tn_stage_weights(const TPParams& W, float* wst, uint32_t lane_base, int row, int cg) {
+    tn_stage_weights_g2s<FD>(W, wst, threadIdx.x, NTHREADS);
+    __syncthreads();
+    tn_stage_weights_s2t(wst, lane_base, row, cg);
 }
 
 __device__ __forceinline__ TnLane tn_lane_consts(const TPParams& W, int row) {
@@ -725,6 +733,153 @@ static size_t tp_tcn_smem_bytes(const hs_config& c) {
     const int F3 = 3 * c.future_step;
     return 2 * (size_t)TN_H_BYTES + ((size_t)F3 * TP_HID + 32) * sizeof(float) + 16 + 2 * (size_t)c.history_step * TN_X_STEP +
            ((size_t)TN_E * 3 * FMAX + (size_t)TN_E * c.num_agents * (20 + 3 * FMAX) + (size_t)256 * TN_WPITCH) * sizeof(float);
+}
+
+// =========================================================================================
+// Fused tick + predictor for batches of at most one 32-env tile per SM (the BASELINE workload: 4096 envs = 128
+// CTAs): ONE launch per control tick.  Warps 0-3 of the CTA run the control tick of the tile's 32 envs
+// (hs_tick_body, 8 envs per warp) while warps 4-15 bring the predictor's weights from global memory into the
+// staging tile; after one block barrier the CTA is the small-batch tcgen05 predictor above, with the LSTM input
+// taken from the TP_input tiles the tick warps just built in shared memory instead of from global memory.
+// Against the two-kernel sequence this removes a launch boundary (~3 us of drain + ramp at this size), hides the
+// weight prologue behind the tick, and skips the global round trip of the window.  Results are bit-identical to
+// hs_tick_kernel followed by hs_tp_fill_tcn_kernel (same device functions, same operation order).
+// =========================================================================================
+constexpr int FUSED_TICK_WARPS = TN_E / ENVS_PER_WARP;                       // 4
+constexpr int FUSED_TICK_WORDS = 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX + TICK_STAT_WORDS;   // per tick warp
+
+// x of all H steps from the tick warps' shared TP_input tiles ([8 envs][H][FD] per warp) -> B operand (tf32 hi/lo)
+template <int FD>
+__device__ __forceinline__ void tn_stage_x_smem(const float* tick_mem, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = lane & 7, kk = lane >> 3;
+    constexpr int NW = TN_THREADS / 32;
+    for (int cm = warp; cm < H * 16; cm += NW) {
+        const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
+        const int n = ng * 8 + rr, k = kc * 4 + kk;
+        // env n lives in tick warp n / 8 = ng, row rr of its tile
+        const float* tile = tick_mem + ng * FUSED_TICK_WORDS + 2 * TICK_STAGE_WORDS;
+        const float xv = (n < nenv && k < FD) ? tile[rr * (H * FD) + s * FD + k] : 0.0f;
+        uint32_t hi, lo;
+        tf32_split(xv, hi, lo);
+        const uint32_t off = s * TN_X_STEP + kc * TN_X_LBO + ng * TN_SBO + rr * 16 + kk * 4;
+        *reinterpret_cast<uint32_t*>(Xhi + off) = hi;
+        *reinterpret_cast<uint32_t*>(Xlo + off) = lo;
+    }
+}
+
+template <int A, int CT>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const hs_config& c = P.c;
+    constexpr int FD = 7 + 3 * A;
+    const int H = c.history_step;
+    const int F3 = 3 * c.future_step;
+    const int E = c.num_envs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane;            // TMEM lane = gate row of both M-tiles
+    const int cg = warp >> 2;                          // env columns [8*cg, 8*cg+8) of the tile
+
+    uint8_t* Hhi = smem_raw;
+    uint8_t* Hlo = Hhi + TN_H_BYTES;
+    float* fcw = reinterpret_cast<float*>(Hlo + TN_H_BYTES);
+    float* fcb = fcw + F3 * TP_HID;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    uint8_t* Xhi = reinterpret_cast<uint8_t*>(mbar + 2);
+    uint8_t* Xlo = Xhi + (size_t)H * TN_X_STEP;
+    float* preds = reinterpret_cast<float*>(Xlo + (size_t)H * TN_X_STEP);
+    float* rowbuf = preds + TN_E * 3 * FMAX;
+    float* wst = rowbuf + TN_E * A * (20 + 3 * FMAX);
+    // tick pieces of the four tick warps, 128-byte aligned
+    float* tick_mem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wst + 256 * TN_WPITCH) + 127) & ~(uintptr_t)127);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp < FUSED_TICK_WARPS) {
+        // ---- phase 1a: the control tick of this tile's envs, one warp per 8 envs
+        float* m = tick_mem + warp * FUSED_TICK_WORDS;
+        hs_tick_body<A, false, CT>(P, (int64_t)blockIdx.x * FUSED_TICK_WARPS + warp, m, m + TICK_STAGE_WORDS,
+                                   m + 2 * TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX);
+    } else {
+        // ---- phase 1b: predictor constants and weights, global -> shared
+        const int t = tid - 32 * FUSED_TICK_WARPS, nt = TN_THREADS - 32 * FUSED_TICK_WARPS;
+        for (int i = t; i < F3 * TP_HID; i += nt) fcw[i] = __ldg(W.fc_w + i);
+        if (t < F3) fcb[t] = __ldg(W.fc_b + t);
+        tn_stage_weights_g2s<FD>(W, wst, t, nt);
+    }
+    const TnLane L = tn_lane_consts(W, row);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    tn_stage_weights_s2t(wst, lane_base, row, cg);
+    const uint32_t bar = smem_u32(mbar);
+    uint32_t phase = 0;
+
+    const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const bool issue_warp = warp_u < 2;
+    const uint32_t mytl = warp_u & 1u;
+    TnIssue I;
+    I.aA_hi = tmem_u + TN_COL_A + 160 * mytl;
+    I.aA_lo = I.aA_hi + 80;
+    I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t dH_hi = tc_desc(smem_u32(Hhi), TN_H_LBO, TN_SBO), dH_lo = tc_desc(smem_u32(Hlo), TN_H_LBO, TN_SBO);
+    const uint64_t dX_hi = tc_desc(smem_u32(Xhi), TN_X_LBO, TN_SBO), dX_lo = tc_desc(smem_u32(Xlo), TN_X_LBO, TN_SBO);
+    const uint32_t d_mine = tmem_u + mytl * TN_E;
+
+    {
+        const int64_t e0 = (int64_t)blockIdx.x * TN_E;
+        const int nenv = (int)min((int64_t)TN_E, E - e0);
+        tn_stage_x_smem<FD>(tick_mem, nenv, H, Xhi, Xlo);
+        float cst[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cst[j] = 0.f;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (issue_warp && elect_one()) {
+            tc_fence_after();
+            I.x_part(d_mine, dX_hi, dX_lo, 0u);
+        }
+        for (int s = 0; s < H; ++s) {
+            const int dbuf = s & 1;
+            if (issue_warp && elect_one()) {
+                if (s > 0) {
+                    tc_fence_after();
+                    I.h_part(d_mine + (uint32_t)(dbuf * 2 * TN_E), dH_hi, dH_lo);
+                }
+                tc_commit(bar);
+                if (s + 1 < H) {
+                    const uint64_t xo = (uint64_t)(((uint32_t)(s + 1) * TN_X_STEP) >> 4);
+                    I.x_part(d_mine + (uint32_t)((dbuf ^ 1) * 2 * TN_E), dX_hi + xo, dX_lo + xo, 0u);
+                }
+            }
+            mbar_wait(bar, phase);
+            tc_fence_after();
+            tn_epilogue(lane_base + (uint32_t)(dbuf * 2 * TN_E), L, cg, cst, Hhi, Hlo);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+static size_t tp_fused_smem_bytes(const hs_config& c) {
+    return tp_tcn_smem_bytes(c) + 128 + (size_t)FUSED_TICK_WARPS * FUSED_TICK_WORDS * sizeof(float);
 }
 
 // =========================================================================================

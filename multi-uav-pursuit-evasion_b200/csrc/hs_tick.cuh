@@ -10,17 +10,36 @@ namespace {
 // The tick.  RESET=false: full control tick.  RESET=true: the unforced physics tick + obs
 // that closes a reset (hideandseek.py:722-723, isaac_env.py:220-224).
 // =========================================================================================
-template <int A, bool RESET, int CT>
-__global__ void __launch_bounds__(128, 5)
-hs_tick_kernel(const __grid_constant__ KParams P) {
-    __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
-    __shared__ __align__(128) float tp_mem[4][ENVS_PER_WARP * TP_ENV_WORDS_MAX];   // TP_input tile of the warp
-    __shared__ __align__(16) float stat_mem[4][ENVS_PER_WARP][HS_NUM_STATS];
+// The body works on ONE warp's 8 envs (warp_g = index of the warp in the batch) with the per-warp shared-memory
+// pieces passed in, so that it can run as hs_tick_kernel or as the first phase of the fused tick + predictor
+// kernel (hs_tick_tp_fused_kernel, hs_predictor_tcgen05.cuh).  Only warp-level synchronisation inside.
+constexpr int TICK_STAT_WORDS = ENVS_PER_WARP * HS_NUM_STATS;
 
+// previous TP window -> shared tile for the uncommon shapes (ragged tile, H != 10, frame width not a multiple of 4)
+__device__ __noinline__ void tp_prefetch_slow(float* tp_tile, const float* src, int nenv, int per_env, int keep, int FD, int lane) {
+    if ((FD & 3) == 0) {
+        const int pe4 = per_env >> 2, keep4 = keep >> 2, fd4 = FD >> 2;
+        const int total = nenv * keep4;
+        int env = 0, j = lane;                       // i = env*keep4 + j, kept incrementally
+        for (int i = lane; i < total; i += 32, j += 32) {
+            while (j >= keep4) { j -= keep4; ++env; }
+            cp_async16(reinterpret_cast<float4*>(tp_tile) + env * pe4 + j,
+                       reinterpret_cast<const float4*>(src) + env * pe4 + j + fd4);
+        }
+    } else {
+        const int total = nenv * keep;
+        int env = 0, j = lane;
+        for (int i = lane; i < total; i += 32, j += 32) {
+            while (j >= keep) { j -= keep; ++env; }
+            cp_async4(tp_tile + env * per_env + j, src + env * per_env + j + FD);
+        }
+    }
+}
+template <int A, bool RESET, int CT>
+__device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t warp_g, float* stage0, float* stage1,
+                                             float* tp_tile, float* stat_tile) {
     const hs_config& c = P.c;
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int slot = lane & (G - 1);
     const int gbase = lane & ~(G - 1);
     const int64_t e0 = warp_g * ENVS_PER_WARP;           // first env of this warp
@@ -48,14 +67,13 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
 #define EROW(k) (arena + (o_env + (uint32_t)(k) * Ep32))
 
     Stager st;
-    st.buf[0] = stage_mem[wib][0];
-    st.buf[1] = stage_mem[wib][1];
+    st.buf[0] = stage0;
+    st.buf[1] = stage1;
     st.cur = 0;
     st.lane = lane;
 
     // ---- prefetch (no registers held): the previous TP_input rows 1..H-1 land in the warp's
     // shared tile already shifted to rows 0..H-2, and the env's stats row lands in stat_mem.
-    float* tp_tile = tp_mem[wib];
     const int per_env = H * FD, keep = (H - 1) * FD;
     if (c.use_tp_net && !P.tp_init) {
         const float* src = P.b.tp_input_prev + e0 * per_env;
@@ -70,27 +88,13 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                     cp_async16(reinterpret_cast<float4*>(tp_tile) + env * pe4 + j,
                                reinterpret_cast<const float4*>(src) + env * pe4 + j + fd4);
             }
-        } else if ((FD & 3) == 0) {
-            const int pe4 = per_env >> 2, keep4 = keep >> 2, fd4 = FD >> 2;
-            const int total = nenv * keep4;
-            int env = 0, j = lane;                       // i = env*keep4 + j, kept incrementally
-            for (int i = lane; i < total; i += 32, j += 32) {
-                while (j >= keep4) { j -= keep4; ++env; }
-                cp_async16(reinterpret_cast<float4*>(tp_tile) + env * pe4 + j,
-                           reinterpret_cast<const float4*>(src) + env * pe4 + j + fd4);
-            }
         } else {
-            const int total = nenv * keep;
-            int env = 0, j = lane;
-            for (int i = lane; i < total; i += 32, j += 32) {
-                while (j >= keep) { j -= keep; ++env; }
-                cp_async4(tp_tile + env * per_env + j, src + env * per_env + j + FD);
-            }
+            tp_prefetch_slow(tp_tile, src, nenv, per_env, keep, FD, lane);
         }
     }
     if (!RESET && valid && is_ev) {
 #pragma unroll
-        for (int k = 0; k < HS_NUM_STATS; ++k) cp_async4(&stat_mem[wib][lane >> 2][k], P.b.stats + (int64_t)k * E + e);
+        for (int k = 0; k < HS_NUM_STATS; ++k) cp_async4(stat_tile + (lane >> 2) * HS_NUM_STATS + k, P.b.stats + (int64_t)k * E + e);
     }
     cp_async_commit();
 
@@ -486,7 +490,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
                 if (lane == 0) { bulk_store(gdst, tp_tile, (uint32_t)nwords * 4u); bulk_commit(); }
             } else {
                 __syncwarp();
-                for (int i = lane; i < nwords; i += 32) gdst[i] = tp_tile[i];
+                warp_copy_slow(gdst, tp_tile, nwords, lane);
             }
         }
         if (valid && is_ev) {
@@ -567,7 +571,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
         float* S = P.b.stats + e;
         const int64_t Es = E;
         cp_async_wait_all();
-        const float* SO = stat_mem[wib][lane >> 2];     // values prefetched at kernel entry
+        const float* SO = stat_tile + (lane >> 2) * HS_NUM_STATS;     // values prefetched at kernel entry
 #define ST(k) S[(int64_t)(k) * Es]
 #define OLD(k) SO[k]
         // accumulators that are divided by the episode length on the done tick
@@ -601,6 +605,17 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
 #undef OLD
     }
     st.finish();
+}
+
+template <int A, bool RESET, int CT>
+__global__ void __launch_bounds__(128, 5)
+hs_tick_kernel(const __grid_constant__ KParams P) {
+    __shared__ __align__(128) float stage_mem[4][2][TICK_STAGE_WORDS];
+    __shared__ __align__(128) float tp_mem[4][ENVS_PER_WARP * TP_ENV_WORDS_MAX];   // TP_input tile of the warp
+    __shared__ __align__(16) float stat_mem[4][TICK_STAT_WORDS];
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    hs_tick_body<A, RESET, CT>(P, warp_g, stage_mem[wib][0], stage_mem[wib][1], tp_mem[wib], stat_mem[wib]);
 }
 
 #undef DROW

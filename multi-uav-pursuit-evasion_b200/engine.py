@@ -226,12 +226,11 @@ class HsEngine:
         prev, i = self.cur, self.next_index()
         self._launch_policy(prev, i)
         self._policy_launches = getattr(self, "_policy_launches", 0) + (2 if self._critic is not None else 1)
-        out = self.step_pre(self.policy_out[i]["action"], raw=True, reset_pid=reset_pid)
         if self.cfg.use_tp_net:
             if tp_weights is None:
                 raise _lib.HsError("policy_tick: use_tp_net needs tp_weights (fused predictor)")
-            self.step_post_tp(tp_weights)
-        return out
+            return self.step_fused(self.policy_out[i]["action"], tp_weights, raw=True, reset_pid=reset_pid)
+        return self.step_pre(self.policy_out[i]["action"], raw=True, reset_pid=reset_pid)
 
     @property
     def rollout_slot(self) -> int:
@@ -306,6 +305,27 @@ class HsEngine:
         if rc != 0:
             check(rc, "hs_step_host_io")
         return views, hm["done"]
+
+    def step_fused(self, action: torch.Tensor, weights: "_lib.hs_tp_weights", raw: bool = True,
+                   reset_pid: Optional[torch.Tensor] = None, pred_out: Optional[torch.Tensor] = None) -> OutputSet:
+        """hs_step_fused: tick + fused predictor in one call - ONE kernel launch for batches of at most one
+        32-env tile per SM (hs_tick_tp_fused_kernel), otherwise hs_step_pre + hs_step_post_tp."""
+        E, A = self.E, self.A
+        if action.shape != (E, A, 4) or action.dtype != torch.float32 or not action.is_contiguous() \
+                or action.device != self.device:
+            raise _lib.HsError(f"action must be a contiguous float32 [{E},{A},4] tensor on {self.device}")
+        rp = None
+        if reset_pid is not None:
+            rp = reset_pid.reshape(E)
+            rp = rp.view(torch.uint8) if rp.dtype == torch.bool else rp.to(torch.uint8)
+            rp = rp.contiguous()
+        if pred_out is not None:
+            assert pred_out.shape == (E, 3 * self.cfg.future_step) and pred_out.is_contiguous()
+        self._advance()
+        self._keep = [action, rp, pred_out]
+        check(lib.hs_step_fused(self._h, action.data_ptr(), 1 if raw else 0, _ptr(rp), C.byref(weights), _ptr(pred_out),
+                                self._stream()), "hs_step_fused")
+        return self.out
 
     def step_post(self, tp_pred: torch.Tensor) -> OutputSet:
         F3 = 3 * self.cfg.future_step
@@ -389,10 +409,16 @@ class HsEngine:
             if getattr(self, "_actor", None) is not None:
                 self._launch_policy(prev, i)
                 action = self.policy_out[i]["action"]
-            check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if self._graph_raw else 0,
-                                  self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
+            n0 = int(lib.hs_launch_count(self._h))
             if self.cfg.use_tp_net:
-                check(lib.hs_step_post_tp(self._h, C.byref(self._graph_weights), None, st), "hs_step_post_tp (capture)")
+                # one launch (hs_tick_tp_fused_kernel) when the batch qualifies, else tick + predictor
+                check(lib.hs_step_fused(self._h, action.data_ptr(), 1 if self._graph_raw else 0,
+                                        self.graph_reset_pid.data_ptr(), C.byref(self._graph_weights), None, st),
+                      "hs_step_fused (capture)")
+            else:
+                check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if self._graph_raw else 0,
+                                      self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
+            self._graph_kernels = int(lib.hs_launch_count(self._h)) - n0
         self._graphs[(prev, i)] = g
         self._graph_captures = getattr(self, "_graph_captures", 0) + 1
         self._bind(keep, keep)

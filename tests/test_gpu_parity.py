@@ -284,7 +284,8 @@ def test_cuda_graph_replay_equals_direct_launches():
         for k in ("state_self", "state_drones", "obs_cylinders", "tp_input", "reward", "drone_state"):
             assert torch.equal(a[k], b[k]), (t, k)
     assert torch.equal(engs[0].stats, engs[1].stats)
-    assert engs[1].launches - n0 == 14
+    # 7 replays x kernels per captured tick (1: hs_tick_tp_fused_kernel at this batch size; 2 with HS_OPT_FUSED_TICK=0)
+    assert engs[1]._graph_kernels == 1 and engs[1].launches - n0 == 7
     for e in engs:
         e.close()
 
@@ -314,3 +315,43 @@ def test_host_buffer_entry_point():
     assert_close("reward", rew, want["reward"].reshape(E, 3), max_bad_frac=FLIP)
     assert not done.any()
     eng.close()
+
+
+@pytest.mark.parametrize("E,C", [(300, 5), (32, 5), (5, 5), (4096, 5), (1000, 8)])
+def test_fused_tick_predictor_kernel_equals_two_launches(E, C):
+    """hs_step_fused: ONE launch (hs_tick_tp_fused_kernel: tick warps + tcgen05 predictor in the same CTA) must give,
+    bit for bit, what hs_step_pre followed by hs_step_post_tp gives - first frame (history initialisation), ragged
+    tiles, PID resets, both cylinder capacities - and fall back to the two launches when switched off."""
+    import mupe_b200
+    from mupe_b200 import _lib
+    P = O.HSParams(num_cylinders=C)
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(E)
+    init = O.sample_reset(P, E, g)
+    engs = [mupe_b200.HsEngine(cfg, dev) for _ in range(3)]
+    _lib.check(_lib.lib.hs_set_option(engs[2]._h, _lib.HS_OPT_FUSED_TICK, 0), "hs_set_option")
+    for e in engs:
+        e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        e.step_post_tp(e.tp_weights(tp))
+    keys = ("state_self", "state_drones", "state_others", "obs_cylinders", "reward", "done", "drone_state", "tp_input",
+            "tp_groundtruth", "tp_done", "rotor_cmds", "ctbr", "target_rate", "action_error")
+    for t in range(4):
+        act = torch.randn(E, 3, 4, generator=g).to(dev)
+        rp = (torch.rand(E, generator=g) < 0.3).to(dev) if t == 2 else None
+        pred = [torch.empty(E, 3 * P.future_step, device=dev) for _ in range(3)]
+        ref = engs[0].step_pre(act, raw=True, reset_pid=rp)
+        engs[0].step_post_tp(engs[0].tp_weights(tp), pred[0])
+        outs = [engs[k].step_fused(act, engs[k].tp_weights(tp), raw=True, reset_pid=rp, pred_out=pred[k]) for k in (1, 2)]
+        for name, out, pk in (("one launch", outs[0], pred[1]), ("switched off", outs[1], pred[2])):
+            for k in keys:
+                assert torch.equal(out[k], ref[k]), f"tick {t}, {name}: {k} differs"
+            assert torch.equal(pk, pred[0]), f"tick {t}, {name}: prediction differs"
+        for k in (1, 2):
+            assert torch.equal(engs[k].stats, engs[0].stats) and torch.equal(engs[k].arena, engs[0].arena)
+    # the one-launch path really is one launch per tick (the other two engines count two)
+    assert engs[0].launches - engs[1].launches == 4 and engs[2].launches == engs[0].launches
+    for e in engs:
+        e.close()

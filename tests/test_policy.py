@@ -169,7 +169,7 @@ def test_gpu_policy_in_the_tick_graph(built_lib, rollout_steps):
             pb = eng.storage.policy_batch()
             assert tuple(pb["action"].shape) == (E, T, 3, 4)
             assert torch.equal(pb["logp"][:, T - 1], rec[-1]["logp"])
-        assert eng.launches >= 4 * T
+        assert eng.launches >= 3 * T              # actor + critic + (tick+predictor as one launch at this batch size)
         runs.append(rec)
         eng.close()
     for t in range(T):

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Launches hs_step_fused a few times at a given batch size (no CUDA graph) as an ncu target."""
+import os
+import sys
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import mupe_b200  # noqa: E402
+
+
+def main():
+    E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    dev = torch.device("cuda:0")
+    cfg = mupe_b200.build_hs_config(E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(16, 15, 5).to(dev)
+    eng = mupe_b200.HsEngine(cfg, dev)
+    a = 0.9 / 2 ** 0.5
+    dpos = torch.rand(E, 3, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a + 0.1, 0.5], device=dev)
+    tpos = torch.rand(E, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([-a + 0.1, -a + 0.1, 0.5], device=dev)
+    rot = torch.zeros(E, 3, 4, device=dev); rot[..., 0] = 1
+    cyl = torch.zeros(E, 5, 3, device=dev); cyl[..., 2] = -20.0
+    eng.reset(None, dpos, rot, tpos, cyl)
+    w = eng.tp_weights(tp)
+    eng.step_post_tp(w)
+    act = torch.randn(E, 3, 4, device=dev)
+    for _ in range(reps):
+        eng.step_fused(act, w)
+    torch.cuda.synchronize()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
