@@ -50,4 +50,5 @@ def build(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [f"-D{sys.argv[i + 1]}" for i, a in enumerate(sys.argv[:-1]) if a == "--define"]     # debug builds (tools/)
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=defs))

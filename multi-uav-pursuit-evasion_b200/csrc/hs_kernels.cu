@@ -368,8 +368,8 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     const unsigned grid = (unsigned)tiles32;
     cudaStream_t s = (cudaStream_t)stream;
     const bool small_c = h->cfg.num_cylinders <= 5;
-#define HS_FUSED(AA) do { if (small_c) hs_tick_tp_fused_kernel<AA, 5><<<grid, TN_THREADS, smem, s>>>(P, W); \
-                          else hs_tick_tp_fused_kernel<AA, 8><<<grid, TN_THREADS, smem, s>>>(P, W); } while (0)
+#define HS_FUSED(AA) do { if (small_c) hs_tick_tp_fused_kernel<AA, 5><<<grid, TCW_THREADS, smem, s>>>(P, W); \
+                          else hs_tick_tp_fused_kernel<AA, 8><<<grid, TCW_THREADS, smem, s>>>(P, W); } while (0)
     switch (h->cfg.num_agents) {
         case 1: HS_FUSED(1); break;
         case 2: HS_FUSED(2); break;
@@ -381,6 +381,12 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     h->tp_frames += 1;
     return HS_OK;
 }
+
+#ifdef HS_FUSED_TIMING
+int hs_debug_times(unsigned long long* out32) {          // debug builds only (tools/fused_phases.py)
+    return cudaMemcpyFromSymbol(out32, hs_dbg_times, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int hs_step_post(hs_handle* h, const float* tp_pred, void* stream) {
     if (!h || !tp_pred) return set_err(HS_ERR_INVALID, "hs_step_post: null argument%s");

@@ -511,11 +511,39 @@ __device__ __forceinline__ void tn_epilogue(uint32_t d_taddr, const TnLane& L, i
 }
 
 // FC + tanh from the final h (hi + lo in shared memory), then the state_self / state_drones rows of the tile.
+// What a row thread (tid < 32 A: env el = tid % 32, pursuer slot = tid / 32) needs from the arena.  The fused kernel
+// loads it right after the tick phase so that the L2 round trip is not exposed after the recurrence.
+struct TnRowIn {
+    V3 p, lv, tp;
+    Q4 q;
+    float progress;
+    bool bdetect;
+};
+template <int A>
+__device__ __forceinline__ TnRowIn tn_row_load(const KParams& P, int64_t e0, int nenv) {
+    TnRowIn R;
+    R.p = mk(0.f, 0.f, 0.f); R.lv = R.p; R.tp = R.p; R.q.w = 1.f; R.q.x = R.q.y = R.q.z = 0.f; R.progress = 0.f; R.bdetect = false;
+    const int tid = threadIdx.x;
+    if (tid < TN_E * A) {
+        const int slot = tid / TN_E, el = tid - slot * TN_E;
+        const bool valid = el < nenv;
+        const int64_t e = valid ? (e0 + el) : (int64_t)(P.c.num_envs - 1);
+        R.p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
+        R.q.w = *DROW(D_ROT); R.q.x = *DROW(D_ROT + 1); R.q.y = *DROW(D_ROT + 2); R.q.z = *DROW(D_ROT + 3);
+        R.lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
+        R.tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
+        R.progress = *EROW(E_PROGRESS);
+        R.bdetect = *EROW(E_BDETECT) != 0.0f;
+    }
+    return R;
+}
+
 template <int A, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, int64_t e0, int nenv, const uint8_t* Hhi,
-                                           const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf) {
+                                           const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf,
+                                           const TnRowIn& RI) {
     const hs_config& c = P.c;
-    const int F3 = 3 * c.future_step, D = 20 + F3, E = c.num_envs;
+    const int F3 = 3 * c.future_step, D = 20 + F3;
     const int tid = threadIdx.x;
     {
         const int n = tid & 31;
@@ -539,14 +567,10 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
     float* r1 = nullptr;
     if (tid < TN_E * A) {
         const int slot = tid / TN_E, el = tid - slot * TN_E;
-        const bool valid = el < nenv;
-        const int64_t e = valid ? (e0 + el) : (int64_t)(E - 1);
-        const V3 p = mk(*DROW(D_POS), *DROW(D_POS + 1), *DROW(D_POS + 2));
-        Q4 q; q.w = *DROW(D_ROT); q.x = *DROW(D_ROT + 1); q.y = *DROW(D_ROT + 2); q.z = *DROW(D_ROT + 3);
-        const V3 lv = mk(*DROW(D_LIN), *DROW(D_LIN + 1), *DROW(D_LIN + 2));
-        const V3 tp = mk(*EROW(E_TPOS), *EROW(E_TPOS + 1), *EROW(E_TPOS + 2));
-        const float progress = *EROW(E_PROGRESS);
-        const bool bdetect = *EROW(E_BDETECT) != 0.0f;
+        const V3 p = RI.p, lv = RI.lv, tp = RI.tp;
+        const Q4 q = RI.q;
+        const float progress = RI.progress;
+        const bool bdetect = RI.bdetect;
         V3 heading, up;
         heading_up(q, heading, up);
         const float tfrac = fdiv(progress, (float)c.max_episode_length);
@@ -626,6 +650,12 @@ __device__ __forceinline__ void mbar_wait_idx(uint32_t bar0, uint32_t idx, uint3
     uint32_t spins = 0;
     while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 24)) __trap(); }
     bits ^= 1u << idx;
+}
+
+constexpr int TCW_THREADS = TN_THREADS + 64;            // 16 epilogue warps + 2 issuing warps (one per M-tile)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
 template <int A>
@@ -721,7 +751,7 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
             tc_fence_before();
             __syncthreads();
         }
-        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf);
+        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, tn_row_load<A>(P, e0, nenv));
     }
     tc_fence_before();
     __syncthreads();
@@ -746,14 +776,22 @@ static size_t tp_tcn_smem_bytes(const hs_config& c) {
 // hs_tick_kernel followed by hs_tp_fill_tcn_kernel (same device functions, same operation order).
 // =========================================================================================
 constexpr int FUSED_TICK_WARPS = TN_E / ENVS_PER_WARP;                       // 4
+#ifdef HS_FUSED_TIMING
+__device__ unsigned long long hs_dbg_times[32];
+#define HS_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == (HS_TSTAMP_TID)) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); hs_dbg_times[i] = t_; } } while (0)
+#define HS_TSTAMP_TID 0
+#else
+#define HS_TSTAMP(i) do {} while (0)
+#endif
 constexpr int FUSED_TICK_WORDS = 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX + TICK_STAT_WORDS;   // per tick warp
 
 // x of all H steps from the tick warps' shared TP_input tiles ([8 envs][H][FD] per warp) -> B operand (tf32 hi/lo)
-template <int FD>
+template <int FD, int NTHREADS>
 __device__ __forceinline__ void tn_stage_x_smem(const float* tick_mem, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane & 7, kk = lane >> 3;
-    constexpr int NW = TN_THREADS / 32;
+    constexpr int NW = NTHREADS / 32;
     for (int cm = warp; cm < H * 16; cm += NW) {
         const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
         const int n = ng * 8 + rr, k = kc * 4 + kk;
@@ -768,26 +806,94 @@ __device__ __forceinline__ void tn_stage_x_smem(const float* tick_mem, int nenv,
     }
 }
 
+// Cell update for FOUR env columns [n0, n0+4) of the tile (the fused kernel splits the 32-env tile into two 16-env
+// halves and spreads each half over all 16 epilogue warps); same arithmetic, lane pairing and h layout as tn_epilogue.
+__device__ __forceinline__ void tn_epilogue4(uint32_t d_taddr, const TnLane& L, int n0, float (&cst)[4], uint8_t* Hhi, uint8_t* Hlo) {
+    uint32_t v0[4], v1[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]) : "r"(d_taddr + (uint32_t)n0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]), "=r"(v1[3]) : "r"(d_taddr + (uint32_t)(TN_E + n0)));
+    tc_wait_ld();
+    const float T2 = 2.8853900817779268f;              // 2 log2 e
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+        float gb[2], cc[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int n = 2 * np + q;
+            const float a0 = fminf(__uint_as_float(v0[n]) + L.bias0, 60.f);
+            const float a1 = fminf(__uint_as_float(v1[n]) + L.bias1, 60.f);
+            const float d0 = 1.0f + fex2(a0), d1 = 1.0f + fex2(a1);
+            const float r = frcp(d0 * d1);
+            const float ga = r * d1;
+            gb[q] = fmaf(L.sb, r * d0, L.sa);
+            const float ig = __shfl_xor_sync(0xffffffffu, ga * gb[q], 1);
+            cst[n] = fmaf(ga, cst[n], ig);
+            cc[q] = cst[n];
+        }
+        const float other = __shfl_xor_sync(0xffffffffu, cc[1], 1);
+        const float tin = L.odd ? cc[0] : other;
+        const float th = 1.0f - 2.0f * frcp(1.0f + fex2(T2 * tin));
+        const float thb = __shfl_xor_sync(0xffffffffu, th, 1);
+        if (L.odd) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float hval = gb[q] * (q == 0 ? th : thb);
+                const int n = n0 + 2 * np + q;
+                uint32_t hh, hl;
+                tf32_split(hval, hh, hl);
+                const uint32_t off = (L.unit >> 2) * TN_H_LBO + (n >> 3) * TN_SBO + (n & 7) * 16 + (L.unit & 3) * 4;
+                *reinterpret_cast<uint32_t*>(Hhi + off) = hh;
+                *reinterpret_cast<uint32_t*>(Hlo + off) = hl;
+            }
+        }
+    }
+}
+
+// MMA issue for one 16-env half: same operand layouts as the 32-env tile (a half is two of its four 8-env core-matrix
+// groups, i.e. the descriptors move by 2 * SBO and the accumulator by 16 columns), N = 16 in the instruction descriptor.
+struct TnIssueHalf {
+    uint32_t aA_hi, aA_lo, idesc;
+    __device__ __forceinline__ void x_part(uint32_t d, uint64_t dX_hi, uint64_t dX_lo) const {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 8 * j,
+                          ((pass == 1) ? dX_lo : dX_hi) + (uint64_t)((2 * j * TN_X_LBO) >> 4), idesc, (pass | j) ? 1u : 0u);
+    }
+    __device__ __forceinline__ void h_part(uint32_t d, uint64_t dH_hi, uint64_t dH_lo) const {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+            for (int j = 0; j < TP_HID / 8; ++j)
+                tc_mma_ts(d, ((pass == 0) ? aA_lo : aA_hi) + 16 + 8 * j,
+                          ((pass == 1) ? dH_lo : dH_hi) + (uint64_t)((2 * j * TN_H_LBO) >> 4), idesc, 1u);
+    }
+};
+
 template <int A, int CT>
-__global__ void __launch_bounds__(TN_THREADS, 1)
+__global__ void __launch_bounds__(TCW_THREADS, 1)
 hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const hs_config& c = P.c;
     constexpr int FD = 7 + 3 * A;
+    constexpr int NTH = TCW_THREADS;                   // 16 tick/epilogue warps + 2 issuing warps
     const int H = c.history_step;
     const int F3 = 3 * c.future_step;
     const int E = c.num_envs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;            // TMEM lane = gate row of both M-tiles
-    const int cg = warp >> 2;                          // env columns [8*cg, 8*cg+8) of the tile
+    const int cg = warp >> 2;                          // 0..3: epilogue column group; 4: issuing warps
 
     uint8_t* Hhi = smem_raw;
     uint8_t* Hlo = Hhi + TN_H_BYTES;
     float* fcw = reinterpret_cast<float*>(Hlo + TN_H_BYTES);
     float* fcb = fcw + F3 * TP_HID;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-    uint8_t* Xhi = reinterpret_cast<uint8_t*>(mbar + 2);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // d_ready[2], h_ready[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+    uint8_t* Xhi = reinterpret_cast<uint8_t*>(mbar + 6);
     uint8_t* Xlo = Xhi + (size_t)H * TN_X_STEP;
     float* preds = reinterpret_cast<float*>(Xlo + (size_t)H * TN_X_STEP);
     float* rowbuf = preds + TN_E * 3 * FMAX;
@@ -795,12 +901,12 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     // tick pieces of the four tick warps, 128-byte aligned
     float* tick_mem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wst + 256 * TN_WPITCH) + 127) & ~(uintptr_t)127);
 
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    HS_TSTAMP(0);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");        // d_ready: one commit per M-tile
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar + 1)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 2)) : "memory");   // h_ready: 16 epilogue warps
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 3)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp < FUSED_TICK_WARPS) {
@@ -809,77 +915,110 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         hs_tick_body<A, false, CT>(P, (int64_t)blockIdx.x * FUSED_TICK_WARPS + warp, m, m + TICK_STAGE_WORDS,
                                    m + 2 * TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX);
     } else {
-        // ---- phase 1b: predictor constants and weights, global -> shared
-        const int t = tid - 32 * FUSED_TICK_WARPS, nt = TN_THREADS - 32 * FUSED_TICK_WARPS;
+        // ---- phase 1b, in the shadow of the tick: TMEM allocation (warp 4), predictor constants and weights
+        // global -> shared -> TMEM.  These warps meet at named barrier 1; a warp can only write the TMEM lane
+        // quarter (warp & 3), so the part the tick warps would own (cg 0) is taken by warps 4-7 as a second pass.
+        if (warp == FUSED_TICK_WARPS) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        const int t = tid - 32 * FUSED_TICK_WARPS;
+        constexpr int nt = NTH - 32 * FUSED_TICK_WARPS;
         for (int i = t; i < F3 * TP_HID; i += nt) fcw[i] = __ldg(W.fc_w + i);
         if (t < F3) fcb[t] = __ldg(W.fc_b + t);
         tn_stage_weights_g2s<FD>(W, wst, t, nt);
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" :: "n"(nt) : "memory");
+        tc_fence_after();
+        const uint32_t lane_base_w = *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+        tn_stage_weights_s2t(wst, lane_base_w, row, cg);
+        if (cg == 1) tn_stage_weights_s2t(wst, lane_base_w, row, 0);
     }
+    HS_TSTAMP(1);
     const TnLane L = tn_lane_consts(W, row);
     tc_fence_before();
     __syncthreads();
+    HS_TSTAMP(2);
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    tn_stage_weights_s2t(wst, lane_base, row, cg);
-    const uint32_t bar = smem_u32(mbar);
-    uint32_t phase = 0;
+    const uint32_t d_ready = smem_u32(mbar), h_ready = smem_u32(mbar + 2);
+    uint32_t ph_d = 0u, ph_h = 0u;
 
     const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const bool issue_warp = warp_u < 2;
-    const uint32_t mytl = warp_u & 1u;
-    TnIssue I;
+    const bool issuer = warp_u >= TN_THREADS / 32;
+    const uint32_t mytl = warp_u & 1u;                         // M-tile of an issuing warp (warps 16, 17)
+    TnIssueHalf I;
     I.aA_hi = tmem_u + TN_COL_A + 160 * mytl;
     I.aA_lo = I.aA_hi + 80;
-    I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t dH_hi = tc_desc(smem_u32(Hhi), TN_H_LBO, TN_SBO), dH_lo = tc_desc(smem_u32(Hlo), TN_H_LBO, TN_SBO);
-    const uint64_t dX_hi = tc_desc(smem_u32(Xhi), TN_X_LBO, TN_SBO), dX_lo = tc_desc(smem_u32(Xlo), TN_X_LBO, TN_SBO);
+    I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t d_mine = tmem_u + mytl * TN_E;
 
-    {
-        const int64_t e0 = (int64_t)blockIdx.x * TN_E;
-        const int nenv = (int)min((int64_t)TN_E, E - e0);
-        tn_stage_x_smem<FD>(tick_mem, nenv, H, Xhi, Xlo);
-        float cst[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cst[j] = 0.f;
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (issue_warp && elect_one()) {
-            tc_fence_after();
-            I.x_part(d_mine, dX_hi, dX_lo, 0u);
-        }
-        for (int s = 0; s < H; ++s) {
-            const int dbuf = s & 1;
-            if (issue_warp && elect_one()) {
-                if (s > 0) {
-                    tc_fence_after();
-                    I.h_part(d_mine + (uint32_t)(dbuf * 2 * TN_E), dH_hi, dH_lo);
-                }
-                tc_commit(bar);
-                if (s + 1 < H) {
-                    const uint64_t xo = (uint64_t)(((uint32_t)(s + 1) * TN_X_STEP) >> 4);
-                    I.x_part(d_mine + (uint32_t)((dbuf ^ 1) * 2 * TN_E), dX_hi + xo, dX_lo + xo, 0u);
-                }
-            }
-            mbar_wait(bar, phase);
-            tc_fence_after();
-            tn_epilogue(lane_base + (uint32_t)(dbuf * 2 * TN_E), L, cg, cst, Hhi, Hlo);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-        }
-        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf);
-    }
+    const int64_t e0 = (int64_t)blockIdx.x * TN_E;
+    const int nenv = (int)min((int64_t)TN_E, E - e0);
+    const TnRowIn RI = tn_row_load<A>(P, e0, nenv);          // new state of the tile (written by the tick warps above)
+    tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+    HS_TSTAMP(4);
+    // ---- the recurrence: the tile's two 16-env halves ping-pong - while the tensor pipe works on one half the 16
+    // epilogue warps update the other (4 env columns per thread and half); mbarrier hand-off, no block barrier
+    if (issuer) {
+        if (elect_one()) {
+            tc_fence_after();
+            auto xdesc = [&](int hf, int s, bool lo) {
+                return tc_desc(smem_u32(lo ? Xlo : Xhi) + (uint32_t)s * TN_X_STEP + (uint32_t)hf * 2u * TN_SBO, TN_X_LBO, TN_SBO);
+            };
+            auto hdesc = [&](int hf, bool lo) { return tc_desc(smem_u32(lo ? Hlo : Hhi) + (uint32_t)hf * 2u * TN_SBO, TN_H_LBO, TN_SBO); };
+            for (int hf = 0; hf < 2; ++hf) {
+                I.x_part(d_mine + 16u * (uint32_t)hf, xdesc(hf, 0, false), xdesc(hf, 0, true));
+                tc_commit(d_ready + 8u * (uint32_t)hf);
+            }
+            for (int s = 0; s < H; ++s)
+                for (int hf = 0; hf < 2; ++hf) {
+                    mbar_wait_idx(h_ready, (uint32_t)hf, ph_h);
+                    if (s + 1 < H) {
+                        tc_fence_after();
+                        const uint32_t d = d_mine + 16u * (uint32_t)hf;
+                        I.x_part(d, xdesc(hf, s + 1, false), xdesc(hf, s + 1, true));
+                        I.h_part(d, hdesc(hf, false), hdesc(hf, true));
+                        tc_commit(d_ready + 8u * (uint32_t)hf);
+                    }
+                }
+        }
+        __syncwarp();
+    } else {
+        float cst[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cst[hf][j] = 0.f;
+        for (int s = 0; s < H; ++s) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                mbar_wait_idx(d_ready, (uint32_t)hf, ph_d);
+                tc_fence_after();
+                tn_epilogue4(lane_base, L, 16 * hf + 4 * cg, cst[hf], Hhi, Hlo);
+                fence_async_smem();                      // h (generic proxy) -> async proxy of the next MMAs
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_ready + 8u * (uint32_t)hf);
+            }
+            HS_TSTAMP(5 + s);
+        }
+    }
+    __syncthreads();                      // all h of the last step written; the issuing warps have consumed every arrival
+    tn_fc_rows<A, NTH>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI);
+    HS_TSTAMP(20);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == FUSED_TICK_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 static size_t tp_fused_smem_bytes(const hs_config& c) {
-    return tp_tcn_smem_bytes(c) + 128 + (size_t)FUSED_TICK_WARPS * FUSED_TICK_WORDS * sizeof(float);
+    return tp_tcn_smem_bytes(c) + 32 + 128 + (size_t)FUSED_TICK_WARPS * FUSED_TICK_WORDS * sizeof(float);
 }
 
 // =========================================================================================
@@ -894,11 +1033,6 @@ static size_t tp_fused_smem_bytes(const hs_config& c) {
 // 29.2 vs 26.6 us at 4096 envs - so small batches keep hs_tp_fill_tcn_kernel.)
 // TMEM: D slot t at columns 64*t, weights at 128..447.
 // =========================================================================================
-constexpr int TCW_THREADS = TN_THREADS + 64;            // 16 epilogue warps + 2 issuing warps (one per M-tile)
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
 
 template <int A>
 __global__ void __launch_bounds__(TCW_THREADS, 1)
@@ -1030,8 +1164,9 @@ hs_tp_fill_tcw_kernel(const __grid_constant__ KParams P, const __grid_constant__
         for (int t = 0; t < NT; ++t)
             if (t < nslots) {
                 const int64_t e0 = (int64_t)(NT * grp + t) * TN_E;
-                tn_fc_rows<A, TCW_THREADS>(P, W, e0, (int)min((int64_t)TN_E, E - e0), Hb + t * 2 * TN_H_BYTES,
-                                          Hb + t * 2 * TN_H_BYTES + TN_H_BYTES, fcw, fcb, preds, rowbuf);
+                const int nenv_t = (int)min((int64_t)TN_E, E - e0);
+                tn_fc_rows<A, TCW_THREADS>(P, W, e0, nenv_t, Hb + t * 2 * TN_H_BYTES,
+                                          Hb + t * 2 * TN_H_BYTES + TN_H_BYTES, fcw, fcb, preds, rowbuf, tn_row_load<A>(P, e0, nenv_t));
             }
     }
     tc_fence_before();
