@@ -388,9 +388,10 @@ def run_gpu_arm(args):
         flops = 2.0 * 256 * (16 * H + 64 * (H - 1)) + 2.0 * 64 * 3 * F          # per env-tick
         simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         tf = flops * E / (tp_us * 1e-6) / 1e12
-        used = variant if variant >= 0 else (3 if E <= 32 * 148 else 4)
+        used = variant if variant >= 0 else (5 if E <= 32 * 148 else 4)
         kname = {0: "hs_tp_fill_kernel<3>", 1: "hs_tp_fill_mma_kernel<3>", 2: "hs_tp_fill_tc_kernel<3>",
-                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcw_kernel<3>"}[used]
+                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcw_kernel<3>",
+                 5: "hs_tick_tp_fused_kernel<3,5,false> (predictor only)"}[used]
         if used == 0:
             extra["roofline_predictor"] = {"bound": "fp32 FFMA (SIMT)", "kernel": kname, "achieved": tf,
                                            "peak": simt_peak, "unit": "TFLOP/s", "frac": tf / simt_peak, "launch_us": tp_us,
@@ -491,7 +492,9 @@ def run_gpu_arm(args):
                        "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
                        "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
             "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
-            "predictor_kernel": {-1: "auto -> hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles) at 4096 envs",
+            "predictor_kernel": {-1: "auto -> inside hs_tick_tp_fused_kernel (tick + 3xTF32 tcgen05 predictor in one launch, 32-env tile "
+                                     "as two ping-ponging 16-env halves) at 4096 envs",
+                                 5: "hs_tick_tp_fused_kernel (tick + predictor, one launch)",
                                  0: "hs_tp_fill_kernel (fp32 FFMA)", 1: "hs_tp_fill_mma_kernel (3xTF32 mma.sync)",
                                  2: "hs_tp_fill_tc_kernel (3xTF32 tcgen05, 128-env tiles)",
                                  3: "hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles)",

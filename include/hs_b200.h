@@ -196,7 +196,7 @@ typedef struct hs_tp_weights {
 } hs_tp_weights;
 int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, void* stream);
 /* hs_step_pre + hs_step_post_tp as one call - and, when the batch has at most one 32-env tile per
- * SM (<= 4736 envs on a B200), the predictor policy is auto or 3, and A <= 3, as ONE kernel launch
+ * SM (<= 4736 envs on a B200), the predictor policy is auto or 5, and A <= 3, as ONE kernel launch
  * (hs_tick_tp_fused_kernel: four warps of each CTA run the tick of the tile's envs while the others
  * stage the predictor's weights, then the CTA runs the tcgen05 predictor on the TP_input tiles still
  * in shared memory).  Results are identical to the two-call sequence.  Arguments as in hs_step_pre
@@ -257,14 +257,17 @@ int hs_state_get(hs_handle* h, int field, float* dst, void* stream);
 int hs_state_set(hs_handle* h, int field, const float* src, void* stream);
 /* Number of kernels this handle has launched so far (bench `gpu_launches`). */
 int64_t hs_launch_count(const hs_handle* h);
-/* Tunables.  HS_OPT_PREDICTOR_VARIANT: -1 = auto (default: variant 3 while a launch has at most one
+/* Tunables.  HS_OPT_PREDICTOR_VARIANT: -1 = auto (default: variant 5 while a launch has at most one
  * 32-env tile per SM, variant 4 above), 0 = fp32 FFMA predictor kernel,
  * 1 = tensor-core predictor, warp-level mma.sync (error-compensated 3xTF32, fp32-level results),
  * 2 = tensor-core predictor, tcgen05.mma with TMEM accumulators and TMEM-resident recurrent operand,
  *     128 envs per CTA (envs on the MMA's M dimension),
  * 3 = tcgen05.mma with the gates on M, weights resident in TMEM, 32 envs per CTA on N (fills the SMs
  *     at small batches),
- * 4 = as 3 with two 32-env tiles ping-ponging per CTA (one tile's MMAs run under the other's cell update).
+ * 4 = as 3 with two 32-env tiles ping-ponging per CTA (one tile's MMAs run under the other's cell update),
+ * 5 = as 3 with the 32-env tile split into two 16-env halves that ping-pong (N = 16 MMAs, 4 env columns per
+ *     epilogue thread and half, mbarrier hand-off): the small-batch default and the predictor half of the
+ *     one-launch tick (hs_step_fused).
  * HS_OPT_HOST_IO_GRAPH: 1 (default) = hs_step_host_io replays its copies and kernels as ONE CUDA graph
  * launch, cached per set of pointers (host buffers, bound outputs, weights); 0 = plain stream calls.
  * HS_OPT_HOST_IO_ZERO_COPY_ACTION: 1 (default) = a page-locked io->action is read in place by the tick

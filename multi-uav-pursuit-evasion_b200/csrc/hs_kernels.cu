@@ -282,6 +282,14 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
             }
 #undef HS_FATTR
         }
+        if (e == cudaSuccess && tp_half_smem_bytes(*cfg) <= HS_MAX_DYN_SMEM) {
+            const int t = (int)tp_half_smem_bytes(*cfg);
+            switch (cfg->num_agents) {
+                case 1: e = cudaFuncSetAttribute(hs_tick_tp_fused_kernel<1, 5, false>, attr, t); break;
+                case 2: e = cudaFuncSetAttribute(hs_tick_tp_fused_kernel<2, 5, false>, attr, t); break;
+                default: e = cudaFuncSetAttribute(hs_tick_tp_fused_kernel<3, 5, false>, attr, t); break;
+            }
+        }
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s", cudaGetErrorString(e)); }
     }
     *out = h;
@@ -346,7 +354,7 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_fused: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_fused: config has use_tp_net == 0 (use hs_step_pre)%s");
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 3) && tiles32 <= h->num_sms &&
+    const bool one_launch = h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
                             tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
     if (!one_launch) {
         const int rc = hs_step_pre(h, action, action_is_raw, reset_pid, stream);
@@ -430,11 +438,23 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     // 32-env tile's shared memory exceed 227 KB.
     const bool tcn_fits = tp_tcn_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM, tcw_fits = tp_tcw_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
-    int variant = (h->tp_variant >= 0) ? h->tp_variant : ((tiles32 > h->num_sms) ? 4 : 3);
-    if ((variant == 3 && !tcn_fits) || (variant == 4 && !tcw_fits)) {
-        if (h->tp_variant >= 3) return set_err(HS_ERR_INVALID, "predictor variant 3/4: history_step too large for the 32-env tile%s");
+    const bool half_fits = tp_half_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM;
+    int variant = (h->tp_variant >= 0) ? h->tp_variant : ((tiles32 > h->num_sms) ? 4 : 5);
+    if (variant == 5 && !half_fits && h->tp_variant < 0) variant = 3;
+    if ((variant == 3 && !tcn_fits) || (variant == 4 && !tcw_fits) || (variant == 5 && !half_fits)) {
+        if (h->tp_variant >= 3) return set_err(HS_ERR_INVALID, "predictor variant 3/4/5: history_step too large for the 32-env tile%s");
         variant = (variant == 4 && tcn_fits) ? 3 : ((h->cfg.num_envs >= 6144) ? 2 : 0);
     }
+    if (variant == 5) {
+        // one 32-env tile per CTA, its two 16-env halves ping-pong (the predictor half of hs_tick_tp_fused_kernel)
+        const size_t smem = tp_half_smem_bytes(h->cfg);
+        const unsigned grid = (unsigned)tiles32;
+        switch (h->cfg.num_agents) {
+            case 1: hs_tick_tp_fused_kernel<1, 5, false><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
+            case 2: hs_tick_tp_fused_kernel<2, 5, false><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
+            default: hs_tick_tp_fused_kernel<3, 5, false><<<grid, TCW_THREADS, smem, s>>>(P, W); break;
+        }
+    } else
     if (variant == 4) {
         const size_t smem = tp_tcw_smem_bytes(h->cfg);
         const unsigned grid = (unsigned)min((tiles32 + 1) / 2, (int64_t)h->num_sms);   // persistent over tile pairs
@@ -733,7 +753,7 @@ static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw
     // one-launch tick + predictor when the batch qualifies: nothing is complete before that kernel ends, so the
     // whole observation follows it in one copy (the side-branch overlap below is for the two-kernel sequence)
     const int64_t tiles32 = ((int64_t)c.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = c.use_tp_net && h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 3) && tiles32 <= h->num_sms &&
+    const bool one_launch = c.use_tp_net && h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
                             tp_fused_smem_bytes(c) <= HS_MAX_DYN_SMEM && h->io_fused;
     int rc = one_launch ? hs_step_fused(h, action_dev, action_is_raw, reset_pid, w, nullptr, stream)
                         : hs_step_pre(h, action_dev, action_is_raw, reset_pid, stream);
@@ -889,7 +909,7 @@ int hs_set_option(hs_handle* h, int option, int value) {
     if (!h) return set_err(HS_ERR_INVALID, "hs_set_option: null handle%s");
     switch (option) {
         case HS_OPT_PREDICTOR_VARIANT:
-            if (value < -1 || value > 4) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles), 3 (tcgen05, 32-env tiles) or 4 (tcgen05, 2 x 32-env tiles ping-pong)%s");
+            if (value < -1 || value > 5) return set_err(HS_ERR_INVALID, "predictor variant must be -1 (auto), 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (tcgen05, 128-env tiles), 3 (tcgen05, 32-env tiles), 4 (tcgen05, 2 x 32-env tiles ping-pong) or 5 (tcgen05, 32-env tile as 2 x 16-env halves ping-pong)%s");
             h->tp_variant = value;
             return HS_OK;
         case HS_OPT_FUSED_TICK:

@@ -873,7 +873,9 @@ struct TnIssueHalf {
     }
 };
 
-template <int A, int CT>
+// WITH_TICK = false: the same predictor as a kernel of its own (hs_step_post_tp variant 5, the default for small
+// batches): all warps stage the weights, the LSTM input comes from TP_input in global memory.
+template <int A, int CT, bool WITH_TICK = true>
 __global__ void __launch_bounds__(TCW_THREADS, 1)
 hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -909,7 +911,19 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 3)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp < FUSED_TICK_WARPS) {
+    if (!WITH_TICK) {
+        if (warp == FUSED_TICK_WARPS) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        for (int i = tid; i < F3 * TP_HID; i += NTH) fcw[i] = __ldg(W.fc_w + i);
+        if (tid < F3) fcb[tid] = __ldg(W.fc_b + tid);
+        tn_stage_weights_g2s<FD>(W, wst, tid, NTH);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tn_stage_weights_s2t(wst, *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16), row, cg);
+    } else if (warp < FUSED_TICK_WARPS) {
         // ---- phase 1a: the control tick of this tile's envs, one warp per 8 envs
         float* m = tick_mem + warp * FUSED_TICK_WORDS;
         hs_tick_body<A, false, CT>(P, (int64_t)blockIdx.x * FUSED_TICK_WARPS + warp, m, m + TICK_STAGE_WORDS,
@@ -958,7 +972,8 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     const int64_t e0 = (int64_t)blockIdx.x * TN_E;
     const int nenv = (int)min((int64_t)TN_E, E - e0);
     const TnRowIn RI = tn_row_load<A>(P, e0, nenv);          // new state of the tile (written by the tick warps above)
-    tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
+    if (WITH_TICK) tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
+    else tn_stage_x<FD, NTH>(P.b.tp_input, e0, nenv, H, Xhi, Xlo);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -1017,6 +1032,7 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     if (warp == FUSED_TICK_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
+static size_t tp_half_smem_bytes(const hs_config& c) { return tp_tcn_smem_bytes(c) + 32 + 128; }     // WITH_TICK = false
 static size_t tp_fused_smem_bytes(const hs_config& c) {
     return tp_tcn_smem_bytes(c) + 32 + 128 + (size_t)FUSED_TICK_WARPS * FUSED_TICK_WORDS * sizeof(float);
 }

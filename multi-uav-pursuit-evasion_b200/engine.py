@@ -367,7 +367,8 @@ class HsEngine:
     def set_predictor_variant(self, variant: int):
         """-1: auto (default); 0: fp32 FFMA kernel; 1: 3xTF32 mma.sync kernel; 2: 3xTF32 tcgen05/TMEM kernel
         (128-env tiles); 3: 3xTF32 tcgen05 kernel with the gates on M and 32-env tiles (small batches);
-        4: as 3 with two tiles ping-ponging per CTA (larger batches)."""
+        4: as 3 with two tiles ping-ponging per CTA (larger batches); 5: the 32-env tile as two ping-ponging 16-env
+        halves (small-batch default, and the predictor half of the one-launch tick)."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_PREDICTOR_VARIANT, int(variant)), "hs_set_option")
         self._graphs = None             # captured graphs hold the old kernel
 

@@ -180,7 +180,7 @@ def test_partial_reset_keeps_other_envs():
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["ffma", "mma3xtf32", "tcgen05", "tcgen05n32", "tcgen05n32x2"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5], ids=["ffma", "mma3xtf32", "tcgen05", "tcgen05n32", "tcgen05n32x2", "tcgen05n16x2"])
 @pytest.mark.parametrize("A,E", [(3, 200), (3, 32), (2, 45), (1, 64), (3, 9500)])
 def test_fused_predictor_matches_torch_lstm(A, E, variant):
     """hs_step_post_tp (LSTM+FC+tanh+rows in one kernel, fp32 FFMA) against torch's CPU LSTM
