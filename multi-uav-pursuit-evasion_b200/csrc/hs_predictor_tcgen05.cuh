@@ -511,6 +511,14 @@ __device__ __forceinline__ void tn_epilogue(uint32_t d_taddr, const TnLane& L, i
 }
 
 // FC + tanh from the final h (hi + lo in shared memory), then the state_self / state_drones rows of the tile.
+#ifdef HS_FUSED_TIMING
+__device__ unsigned long long hs_dbg_times[32];
+#define HS_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == (HS_TSTAMP_TID)) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); hs_dbg_times[i] = t_; } } while (0)
+#define HS_TSTAMP_TID 0
+#else
+#define HS_TSTAMP(i) do {} while (0)
+#endif
 // What a row thread (tid < 32 A: env el = tid % 32, pursuer slot = tid / 32) needs from the arena.  The fused kernel
 // loads it right after the tick phase so that the L2 round trip is not exposed after the recurrence.
 struct TnRowIn {
@@ -541,7 +549,7 @@ __device__ __forceinline__ TnRowIn tn_row_load(const KParams& P, int64_t e0, int
 template <int A, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, int64_t e0, int nenv, const uint8_t* Hhi,
                                            const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf,
-                                           const TnRowIn& RI) {
+                                           const TnRowIn& RI, float* rowbuf2 = nullptr) {
     const hs_config& c = P.c;
     const int F3 = 3 * c.future_step, D = 20 + F3;
     const int tid = threadIdx.x;
@@ -550,12 +558,13 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
         for (int og = tid >> 5; og < F3; og += NTHREADS / 32) {
             float a0 = fcb[og];
             const float* w0 = fcw + og * TP_HID;
-#pragma unroll 4
-            for (int kc = 0; kc < TP_HID / 4; ++kc) {
+#pragma unroll
+            for (int kc = 0; kc < TP_HID / 4; ++kc) {          // fully unrolled: the 32 LDS.128 are issued ahead of the FMA chain
                 const float4 hh = *reinterpret_cast<const float4*>(Hhi + kc * TN_H_LBO + n * 16);
                 const float4 hl = *reinterpret_cast<const float4*>(Hlo + kc * TN_H_LBO + n * 16);
-                a0 = fmaf(w0[4 * kc], hh.x + hl.x, a0); a0 = fmaf(w0[4 * kc + 1], hh.y + hl.y, a0);
-                a0 = fmaf(w0[4 * kc + 2], hh.z + hl.z, a0); a0 = fmaf(w0[4 * kc + 3], hh.w + hl.w, a0);
+                const float4 ww = *reinterpret_cast<const float4*>(w0 + 4 * kc);
+                a0 = fmaf(ww.x, hh.x + hl.x, a0); a0 = fmaf(ww.y, hh.y + hl.y, a0);
+                a0 = fmaf(ww.z, hh.z + hl.z, a0); a0 = fmaf(ww.w, hh.w + hl.w, a0);
             }
             const float pv = tanhf(a0);
             preds[n * F3 + og] = pv;
@@ -563,6 +572,7 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
         }
     }
     __syncthreads();
+    HS_TSTAMP(21);
     V3 t_rpos = mk(0.f, 0.f, 0.f);
     float* r1 = nullptr;
     if (tid < TN_E * A) {
@@ -592,12 +602,30 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
 #pragma unroll
         for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
     }
+    HS_TSTAMP(22);
     const int nwords = nenv * A * D;
     float* g1 = P.b.state_self + e0 * A * D;
     float* g2 = P.b.state_drones + e0 * A * D;
     const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
+    if (rowbuf2 != nullptr && bulk && ((reinterpret_cast<uintptr_t>(rowbuf2) & 15) == 0)) {
+        // both tensors in one pass: state_drones = the same rows with the unmasked target offset, built in a second tile
+        __syncthreads();
+        for (int i = tid; i < nwords; i += NTHREADS) rowbuf2[i] = rowbuf[i];
+        __syncthreads();
+        if (r1 != nullptr) { float* r2 = rowbuf2 + (r1 - rowbuf); r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z; }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(g1, rowbuf, (uint32_t)nwords * 4u);
+            bulk_store(g2, rowbuf2, (uint32_t)nwords * 4u);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+        __syncthreads();
+        return;
+    }
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         float* gdst = pass == 0 ? g1 : g2;
@@ -776,14 +804,7 @@ static size_t tp_tcn_smem_bytes(const hs_config& c) {
 // hs_tick_kernel followed by hs_tp_fill_tcn_kernel (same device functions, same operation order).
 // =========================================================================================
 constexpr int FUSED_TICK_WARPS = TN_E / ENVS_PER_WARP;                       // 4
-#ifdef HS_FUSED_TIMING
-__device__ unsigned long long hs_dbg_times[32];
-#define HS_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == (HS_TSTAMP_TID)) { unsigned long long t_; \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); hs_dbg_times[i] = t_; } } while (0)
-#define HS_TSTAMP_TID 0
-#else
-#define HS_TSTAMP(i) do {} while (0)
-#endif
+
 constexpr int FUSED_TICK_WORDS = 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX + TICK_STAT_WORDS;   // per tick warp
 
 // x of all H steps from the tick warps' shared TP_input tiles ([8 envs][H][FD] per warp) -> B operand (tf32 hi/lo)
@@ -1025,7 +1046,7 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         }
     }
     __syncthreads();                      // all h of the last step written; the issuing warps have consumed every arrival
-    tn_fc_rows<A, NTH>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI);
+    tn_fc_rows<A, NTH>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI, reinterpret_cast<float*>(Xhi));   // x is dead
     HS_TSTAMP(20);
     tc_fence_before();
     __syncthreads();

@@ -37,10 +37,10 @@ def main():
     assert raw.hs_debug_times(buf) == 0
     t = list(buf)
     names = {1: "tick body / weights g2s done (thread 0 = tick warp 0)", 2: "after block barrier", 3: "weights smem -> TMEM",
-             4: "x staged + barrier", 20: "FC + rows"}
+             4: "x staged + barrier", 21: "FC + tanh + barrier", 22: "row assembly (thread 0)", 20: "row stores"}
     names.update({5 + s: f"LSTM step {s}" for s in range(10)})
     prev = t[0]
-    for i in [1, 2, 3, 4] + list(range(5, 15)) + [20]:
+    for i in [1, 2, 3, 4] + list(range(5, 15)) + [21, 22, 20]:
         print(f"{names[i]:55s} +{(t[i] - prev) / 1e3:7.2f} us   (t = {(t[i] - t[0]) / 1e3:7.2f})")
         prev = t[i]
     eng.close()
