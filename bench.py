@@ -166,12 +166,15 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+_JSON_OUT = sys.stdout
+
+
 def make_env(mupe_b200, E, device):
     """BASELINE.json configs[1] through the public API (cfg tree -> registry class -> transforms)."""
     cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides={
@@ -531,7 +534,7 @@ def run_gpu_arm(args):
         line.update(extra)
         if e2e_c is not None:
             line["e2e"] = e2e_c
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     for env in envs:
         env.close()
     if world > 1:
@@ -545,6 +548,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         if args.steps == 512:
             args.steps = 60
