@@ -502,7 +502,7 @@ def run_gpu_arm(args):
             ach = ab_all["total"] * E / (step_us * 1e-6) / 1e9
             extra["roofline"] = {
                 "bound": "hbm", "kernel": "hs_tick_tp_fused_kernel<3,5,true>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
-                "frac": ach / peak_hbm, "traffic": 5097472,
+                "frac": ach / peak_hbm, "traffic": 5112320,
                 "traffic_source": "profiles/r1_ncu_fused_4k.txt: dram read + write of one 4096-env launch (the 8 MB it "
                                   "writes stay in the 126 MB L2 for the duration of the launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E, "launch_us": step_us,
