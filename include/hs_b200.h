@@ -391,7 +391,8 @@ typedef struct hs_policy_weights {
     const float *log_std;                           /* [head_dim] (actor) or NULL (critic) */
     int32_t self_dim, head_dim;                     /* D <= 128, head_dim <= 8 */
 } hs_policy_weights;
-/* Size (floats) of the prepared parameter blob for a given state_self width. */
+/* Size (floats) of the prepared parameter blob for a given state_self width (K-major fp32 matrices
+ * and vectors for the FFMA kernel, followed by the tf32 hi/lo weight images of the tcgen05 kernel). */
 int64_t hs_policy_blob_floats(int32_t self_dim);
 /* Packs the parameters K-major and folds Wk^T Wq and Wo Wv (see csrc/hs_policy.cuh); call it
  * after every optimiser step that touched the module.  One launch, asynchronous. */
@@ -414,6 +415,9 @@ typedef struct hs_policy_io {
     float* logp;                    /* [num_rows] log-probability of that action                */
     float* eps_out;                 /* [num_rows, head_dim] the noise that was used             */
     float* feat_out;                /* [num_rows, 128] encoder features                         */
+    int32_t impl;                   /* 0 = auto (tensor cores from 1024 rows on), 1 = fp32 FFMA kernel,
+                                       2 = tcgen05 kernel (3xTF32: fp32-level results)          */
+    int32_t reserved;
 } hs_policy_io;
 /* One launch.  Asynchronous on `stream`; io->action can be handed to hs_step_pre as the raw
  * action of the same tick. */

@@ -118,7 +118,8 @@ class hs_policy_io(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("n_others", C.c_int32), ("n_cyl", C.c_int32),
                 ("state_self", C.c_void_p), ("state_others", C.c_void_p), ("cylinders", C.c_void_p),
                 ("head_out", C.c_void_p), ("eps", C.c_void_p), ("rng_state", C.c_void_p), ("action", C.c_void_p),
-                ("logp", C.c_void_p), ("eps_out", C.c_void_p), ("feat_out", C.c_void_p)]
+                ("logp", C.c_void_p), ("eps_out", C.c_void_p), ("feat_out", C.c_void_p),
+                ("impl", C.c_int32), ("reserved", C.c_int32)]
 
 
 class hs_gae_params(C.Structure):

@@ -44,6 +44,7 @@
 #include "hs_samplers.cuh"
 #include "hs_rollout.cuh"
 #include "hs_policy.cuh"
+#include "hs_policy_tc.cuh"
 
 // =========================================================================================
 // C ABI
@@ -632,7 +633,8 @@ int hs_fps(const float* points, int64_t n, int32_t dim, int32_t k, int32_t start
 
 int64_t hs_policy_blob_floats(int32_t self_dim) {
     if (self_dim < 1 || self_dim > PL_E) return 0;
-    return policy_blob_layout(self_dim).total;
+    // fp32 part rounded up to 1 KB so that the tensor-core image that follows is bulk-copy aligned
+    return (((int64_t)policy_blob_layout(self_dim).total + 255) & ~(int64_t)255) + policy_tc_layout(self_dim).total / 4;
 }
 
 int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream) {
@@ -644,6 +646,9 @@ int hs_policy_prepare(const hs_policy_weights* w, float* blob, void* stream) {
         !w->norm1_b || !w->norm2_w || !w->norm2_b || !w->head_w || !w->head_b)
         return set_err(HS_ERR_INVALID, "hs_policy_prepare: a required parameter pointer is NULL%s");
     hs_policy_prepare_kernel<<<PL_E, PL_E, 0, (cudaStream_t)stream>>>(*w, blob);
+    CUDA_OK(cudaGetLastError());
+    uint8_t* img = reinterpret_cast<uint8_t*>(blob + (((int64_t)policy_blob_layout(w->self_dim).total + 255) & ~(int64_t)255));
+    hs_policy_prepare_tc_kernel<<<dim3(PL_E, 5), PL_E, 0, (cudaStream_t)stream>>>(blob, img, w->self_dim);
     CUDA_OK(cudaGetLastError());
     return HS_OK;
 }
@@ -665,6 +670,17 @@ int hs_policy_forward(const float* blob, int32_t self_dim, int32_t head_dim, con
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t s = (cudaStream_t)stream;
+    const int impl = io->impl ? io->impl : (num_rows >= 1024 ? 2 : 1);
+    if (impl == 2) {
+        // tcgen05 kernel: 128-row tiles, persistent CTAs (one per SM)
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(blob + (((int64_t)policy_blob_layout(self_dim).total + 255) & ~(int64_t)255));
+        const size_t smem = policy_tc_smem_bytes();
+        CUDA_OK(cudaFuncSetAttribute(hs_policy_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t ntiles = (num_rows + PT_M - 1) / PT_M;
+        hs_policy_forward_tc_kernel<0><<<(unsigned)min(ntiles, (int64_t)sms), PT_THREADS, smem, s>>>(A, img);
+        CUDA_OK(cudaGetLastError());
+        return HS_OK;
+    }
     // 64-row tiles halve the weight traffic per row; 32-row tiles fill the machine at small batches
     const bool big = num_rows >= (int64_t)sms * 64 * 2;
     if (big) {

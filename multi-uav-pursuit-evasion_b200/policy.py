@@ -80,6 +80,7 @@ class FusedPolicy:
         if device.type != "cuda" or not torch.cuda.is_available():
             raise _lib.HsError("FusedPolicy needs a CUDA device: policy inference has no CPU path")
         self.device, self.n_others, self.n_cyl = device, int(n_others), int(n_cyl)
+        self.impl = 0                                           # kernel choice of forward(): 0 auto, 1 FFMA, 2 tcgen05
         self._p: Dict[str, Optional[torch.Tensor]] = {}
         for f, n in _ENC.items():
             optional = (f.startswith("embed_others") and n_others == 0) or (f.startswith("embed_cyl") and n_cyl == 0)
@@ -119,7 +120,7 @@ class FusedPolicy:
 
     def forward(self, state_self: torch.Tensor, state_others: Optional[torch.Tensor], cylinders: Optional[torch.Tensor],
                 eps: Optional[torch.Tensor] = None, sample: bool = False, out: Optional[Dict[str, torch.Tensor]] = None,
-                want_features: bool = False, want_eps: bool = False) -> Dict[str, torch.Tensor]:
+                want_features: bool = False, want_eps: bool = False, impl: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """state_self [..., 1, D], state_others [..., n_others, 3], cylinders [..., n_cyl, 5] (the
         ``("agents", "observation")`` entries, any leading batch dims).  Returns ``head`` [..., head_dim]
         (action mean or state value) and, for an actor, ``action`` [..., head_dim] and ``logp`` [..., 1].
@@ -140,6 +141,7 @@ class FusedPolicy:
         mk = lambda k, w: out.setdefault(k, torch.empty(lead + (w,), dtype=torch.float32, device=self.device))
         io = _lib.hs_policy_io()
         io.num_rows, io.n_others, io.n_cyl = R, self.n_others, self.n_cyl
+        io.impl = int(self.impl if impl is None else impl)      # 0 auto, 1 fp32 FFMA kernel, 2 tcgen05 (3xTF32) kernel
         io.state_self = state_self.data_ptr()
         io.state_others = state_others.data_ptr() if self.n_others else None
         io.cylinders = cylinders.data_ptr() if self.n_cyl else None

@@ -40,14 +40,16 @@ def test_oracle_matches_reference_modules(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
 @pytest.mark.parametrize("name", CASES)
-def test_gpu_policy_matches_reference_modules(built_lib, name):
+def test_gpu_policy_matches_reference_modules(built_lib, name, impl):
     import mupe_b200
     dev = torch.device("cuda:0")
     p, obs, ref = _load(name)
     pg = {k: v.to(dev).contiguous() for k, v in p.items()}
     og = {k: v.to(dev).contiguous() for k, v in obs.items()}
     net = mupe_b200.FusedPolicy(pg, n_others=obs["state_others"].shape[1], n_cyl=obs["cylinders"].shape[1], device=dev)
+    net.impl = impl                     # 1: fp32 FFMA kernel, 2: tcgen05 kernel (3xTF32)
     is_actor = "log_std" in p
     eps = ref["eps"].to(dev).contiguous() if is_actor else None
     out = net(og["state_self"], og["state_others"], og["cylinders"], eps=eps, want_features=True)
@@ -64,8 +66,9 @@ def test_gpu_policy_matches_reference_modules(built_lib, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("R", [1, 31, 33, 4096 * 3, 148 * 128 + 5])
-def test_gpu_policy_ragged_sizes_against_oracle(built_lib, R):
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("R", [1, 31, 33, 129, 4096 * 3, 148 * 128 + 5])
+def test_gpu_policy_ragged_sizes_against_oracle(built_lib, R, impl):
     """Row counts around the 32- and 64-row tiles (both kernels), against the restatement on seeded inputs; refresh()
     picks up in-place parameter updates."""
     import mupe_b200
@@ -77,6 +80,7 @@ def test_gpu_policy_ragged_sizes_against_oracle(built_lib, R):
     eps = torch.randn(R, 4, generator=g)
     pg = {k: v.to(dev).contiguous() for k, v in p.items()}
     net = mupe_b200.FusedPolicy(pg, 2, 3, dev)
+    net.impl = impl
     og = {k: v.to(dev) for k, v in obs.items()}
     out = net(og["state_self"], og["state_others"], og["cylinders"], eps=eps.to(dev))
     n = min(R, 3000)                      # the CPU restatement on a prefix and a suffix is enough at the large sizes
@@ -98,7 +102,8 @@ def test_oracle_noise_is_standard_normal():
 
 
 @pytest.mark.gpu
-def test_gpu_policy_in_kernel_noise(built_lib):
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+def test_gpu_policy_in_kernel_noise(built_lib, impl):
     """sample=True: the kernel draws the noise (Philox + Box-Muller) and advances the device step counter itself;
     the noise equals the CPU restatement, the action is mean + std * noise, consecutive calls use consecutive steps,
     and a re-seeded policy replays the same sequence."""
@@ -109,6 +114,7 @@ def test_gpu_policy_in_kernel_noise(built_lib):
     og = {k: v.to(dev).contiguous() for k, v in obs.items()}
     R = obs["state_self"].shape[0]
     net = mupe_b200.FusedPolicy(pg, 2, 3, dev).seed(1234, step=5)
+    net.impl = impl
     seq = []
     for k in range(3):
         out = net(og["state_self"], og["state_others"], og["cylinders"], sample=True, want_eps=True)
