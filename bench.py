@@ -444,10 +444,10 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             pol_us = 1e3 * k0.elapsed_time(k1) / npol
             extra["rollout_step_with_policy"] = {
-                "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us, "launches_per_step": 4,
-                "what": "one CUDA graph per rollout step: hs_policy_forward (actor, in-kernel noise) + hs_policy_forward "
-                        "(critic) + hs_tick_kernel + fused predictor, observation never leaves HBM; same 4096-env batch "
-                        "every step (L2-warm), single GPU"}
+                "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us, "launches_per_step": 3,
+                "what": "one CUDA graph per rollout step: hs_policy_forward_tc_kernel (actor, tcgen05 3xTF32, in-kernel noise) + "
+                        "hs_policy_forward_tc_kernel (critic) + hs_tick_tp_fused_kernel (tick + predictor), observation never "
+                        "leaves HBM; same 4096-env batch every step (L2-warm), single GPU"}
             pe.close()
         except Exception as ex:
             extra["rollout_step_with_policy"] = {"error": repr(ex)[:200]}

@@ -666,16 +666,25 @@ int hs_policy_forward(const float* blob, int32_t self_dim, int32_t head_dim, con
     A.eps = io->eps; A.rng = io->eps ? nullptr : io->rng_state;
     A.head_out = io->head_out; A.action = io->action; A.logp = io->logp; A.eps_out = io->eps_out; A.feat_out = io->feat_out;
     A.R = num_rows; A.D = self_dim; A.n_others = io->n_others; A.n_cyl = io->n_cyl; A.head_dim = head_dim;
-    int dev = 0, sms = 0;
+    int dev = 0;
     CUDA_OK(cudaGetDevice(&dev));
-    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static int sm_count[64] = {};
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
+    if (sms == 0) {
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const int impl = io->impl ? io->impl : (num_rows >= 1024 ? 2 : 1);
     if (impl == 2) {
         // tcgen05 kernel: 128-row tiles, persistent CTAs (one per SM)
         const uint8_t* img = reinterpret_cast<const uint8_t*>(blob + (((int64_t)policy_blob_layout(self_dim).total + 255) & ~(int64_t)255));
         const size_t smem = policy_tc_smem_bytes();
-        CUDA_OK(cudaFuncSetAttribute(hs_policy_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static bool attr_set[64] = {};                       // per device, once (the call costs ~10 us of host time)
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            CUDA_OK(cudaFuncSetAttribute(hs_policy_forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
         const int64_t ntiles = (num_rows + PT_M - 1) / PT_M;
         hs_policy_forward_tc_kernel<0><<<(unsigned)min(ntiles, (int64_t)sms), PT_THREADS, smem, s>>>(A, img);
         CUDA_OK(cudaGetLastError());

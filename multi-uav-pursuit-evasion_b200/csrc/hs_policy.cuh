@@ -31,8 +31,11 @@ constexpr int PL_MAX_TOK_IN = 2 * 3 + 4 * 5;   // others (<= 2 x 3) + cylinders 
 
 struct PolicyBlob {                        // offsets (floats) into the prepared parameter blob
     int We0t, be0, Weo, beo, Wec, bec, lnE_w, lnE_b, Wkqt, bkq, Wovt, bov, ln1_w, ln1_b, W1t, b1, W2t, b2, ln2_w, ln2_b,
-        Wh, bh, log_std, total, Dpad;
+        Wh, bh, log_std, gram, total, Dpad;
 };
+// gram: column sums and Gram matrices of the two token embeddings over the 128 features (constants of the network):
+// [0..3] c^o_a = sum_f W^o_af (a = 3: bias), [4..19] M^o_ab = sum_f W^o_af W^o_bf, [20..25] c^c_a (a = 5: bias), [26..61] M^c_ab.
+// With them the LayerNorm statistics of a token embedding follow from the token's 3 or 5 raw inputs alone.
 __host__ __device__ inline PolicyBlob policy_blob_layout(int self_dim) {
     PolicyBlob L;
     int o = 0;
@@ -49,6 +52,7 @@ __host__ __device__ inline PolicyBlob policy_blob_layout(int self_dim) {
     L.W2t = take(PL_E * PL_E); L.b2 = take(PL_E);
     L.ln2_w = take(PL_E); L.ln2_b = take(PL_E);
     L.Wh = take(PL_HEAD_MAX * PL_E); L.bh = take(PL_HEAD_MAX); L.log_std = take(PL_HEAD_MAX);
+    L.gram = take(64);
     L.total = o;
     return L;
 }
@@ -99,6 +103,19 @@ hs_policy_prepare_kernel(const hs_policy_weights w, float* __restrict__ blob) {
             blob[L.bh + a] = a < w.head_dim ? w.head_b[a] : 0.f;
             blob[L.log_std + a] = (w.log_std && a < w.head_dim) ? w.log_std[a] : 0.f;
         }
+    }
+    if (b == 1 && a < 62) {
+        // augmented embedding rows: others (W_0, W_1, W_2, bias), cylinders (W_0..W_4, bias)
+        auto wo = [&](int r, int f) { return !w.embed_others_w ? 0.f : (r < 3 ? w.embed_others_w[f * 3 + r] : w.embed_others_b[f]); };
+        auto wc = [&](int r, int f) { return !w.embed_cyl_w ? 0.f : (r < 5 ? w.embed_cyl_w[f * 5 + r] : w.embed_cyl_b[f]); };
+        float acc = 0.f;
+        for (int f = 0; f < PL_E; ++f) {
+            if (a < 4) acc += wo(a, f);
+            else if (a < 20) acc = fmaf(wo((a - 4) >> 2, f), wo((a - 4) & 3, f), acc);
+            else if (a < 26) acc += wc(a - 20, f);
+            else acc = fmaf(wc((a - 26) / 6, f), wc((a - 26) % 6, f), acc);
+        }
+        blob[L.gram + a] = acc;
     }
 }
 

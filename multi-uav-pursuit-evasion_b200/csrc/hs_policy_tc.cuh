@@ -79,16 +79,44 @@ __device__ __forceinline__ float pt_erf(float x) {
     return copysignf(r, x);
 }
 
+// 32 consecutive floats of a staged vector (this thread's features) as 8 broadcast LDS.128 - the epilogues are bound by
+// the shared-memory pipe (every lane of a warp reads the same address), so scalar loads cost four times as much
+__device__ __forceinline__ void pt_ld32f(const float* p, float (&o)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p + i);
+        o[i] = t.x; o[i + 1] = t.y; o[i + 2] = t.z; o[i + 3] = t.w;
+    }
+}
+
+// 32-term dot product / sums with four independent accumulators (the epilogues run 4 warps per scheduler: a 32-long
+// dependent FMA chain per value would leave the pipe idle three cycles out of four)
+__device__ __forceinline__ float pt_dot32(const float (&a)[32], const float (&b)[32]) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        s0 = fmaf(a[i], b[i], s0); s1 = fmaf(a[i + 1], b[i + 1], s1);
+        s2 = fmaf(a[i + 2], b[i + 2], s2); s3 = fmaf(a[i + 3], b[i + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float pt_sum32(const float (&a)[32]) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) { s0 += a[i]; s1 += a[i + 1]; s2 += a[i + 2]; s3 += a[i + 3]; }
+    return (s0 + s1) + (s2 + s3);
+}
+
 // sum over the 4 threads of a row of N partial values (two block barriers: the buffer is reused)
 template <int N>
 __device__ __forceinline__ void pt_row_exchange(float* xch, int row, int part, const float (&mine)[N], float (&total)[N]) {
-    float* slot = xch + (row * 4 + part) * PT_XW;
+    // layout [part][value][row]: the 32 lanes of a warp (32 consecutive rows) hit 32 different banks
 #pragma unroll
-    for (int i = 0; i < N; ++i) slot[i] = mine[i];
+    for (int i = 0; i < N; ++i) xch[(part * PT_XW + i) * PT_M + row] = mine[i];
     __syncthreads();
-    const float* r0 = xch + row * 4 * PT_XW;
 #pragma unroll
-    for (int i = 0; i < N; ++i) total[i] = (r0[i] + r0[PT_XW + i]) + (r0[2 * PT_XW + i] + r0[3 * PT_XW + i]);
+    for (int i = 0; i < N; ++i)
+        total[i] = (xch[i * PT_M + row] + xch[(PT_XW + i) * PT_M + row]) + (xch[(2 * PT_XW + i) * PT_M + row] + xch[(3 * PT_XW + i) * PT_M + row]);
     __syncthreads();
 }
 
@@ -105,7 +133,7 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
     float* vec = oc + PT_M * PL_MAX_TOK_IN;                            // staged vectors, see V_* below
     enum { V_BE0 = 0, V_LNE_W = 128, V_LNE_B = 256, V_BKQ = 384, V_BOV = 512, V_LN1_W = 640, V_LN1_B = 768, V_B1 = 896,
            V_B2 = 1024, V_LN2_W = 1152, V_LN2_B = 1280, V_BEO = 1408, V_BEC = 1536, V_WEO = 1664, V_WEC = 2048,
-           V_WH = 2688, V_BH = 3712, V_LS = 3720, V_TOTAL = 3728 };
+           V_WH = 2688, V_BH = 3712, V_LS = 3720, V_GRAM = 3728, V_TOTAL = 3792 };
     uint64_t* mbar = reinterpret_cast<uint64_t*>(vec + V_TOTAL);       // [0] MMA done, [1] weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
     __shared__ unsigned long long rng_sh[2];
@@ -141,6 +169,7 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
         for (int i = tid; i < 5 * PL_E; i += PT_THREADS) vec[V_WEC + i] = __ldg(blob + L.Wec + i);
         for (int i = tid; i < PL_HEAD_MAX * PL_E; i += PT_THREADS) vec[V_WH + i] = __ldg(blob + L.Wh + i);
         if (tid < PL_HEAD_MAX) { vec[V_BH + tid] = __ldg(blob + L.bh + tid); vec[V_LS + tid] = __ldg(blob + L.log_std + tid); }
+        if (tid < 64) vec[V_GRAM + tid] = __ldg(blob + L.gram + tid);
     }
     tc_fence_before();
     __syncthreads();
@@ -194,14 +223,21 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
         pt_st32(lane_base + PT_COL_ALO + f0, lo);
     };
     auto layernorm = [&](float (&v)[32], int vw, int vb) {
-        float p[2] = {0.f, 0.f}, t[2];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { p[0] += v[i]; p[1] = fmaf(v[i], v[i], p[1]); }
+        float p[2] = {pt_sum32(v), pt_dot32(v, v)}, t[2];
         pt_row_exchange<2>(xch, row, part, p, t);
         const float mean = t[0] * (1.0f / PL_E);
         const float rstd = rsqrtf(fmaxf(t[1] * (1.0f / PL_E) - mean * mean, 0.0f) + 1e-5f);
+        float g[32], b[32];
+        pt_ld32f(vec + vw + f0, g);
+        pt_ld32f(vec + vb + f0, b);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * vec[vw + f0 + i] + vec[vb + f0 + i];
+        for (int i = 0; i < 32; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+    };
+    auto add_vec = [&](float (&v)[32], int off) {
+        float b[32];
+        pt_ld32f(vec + off + f0, b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += b[i];
     };
 
     if (tid == 0) load_weights(T.L0, k0);
@@ -227,7 +263,7 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
             for (int i = part; i < tok_in; i += 4) {
                 float v = 0.f;
                 if (valid) v = i < no3 ? __ldg(A.state_others + r * no3 + i) : __ldg(A.cylinders + r * nc5 + (i - no3));
-                oc[row * PL_MAX_TOK_IN + i] = v;
+                oc[i * PT_M + row] = v;
             }
         }
         float v[32];
@@ -238,99 +274,156 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         };
 
+        HS_TSTAMP(0);
         // ---- L0: x0 = LN(We0 s + be0)
         gemm(k0, T.L1, PL_E);
+        HS_TSTAMP(1);
         load_D();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += vec[V_BE0 + f0 + i];
+        add_vec(v, V_BE0);
         layernorm(v, V_LNE_W, V_LNE_B);
 #pragma unroll
         for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(v[i]);
         pt_st32(lane_base + PT_COL_STASH + f0, raw);          // x0 (fp32) for the attention and the residual
         store_A(v);
 
+        HS_TSTAMP(2);
         // ---- L1: q' = W_kq x0 + b_kq (kept in registers)
         gemm(PL_E, T.L2, PL_E);
+        HS_TSTAMP(3);
         float q[32];
         tc_ld32(lane_base + PT_COL_D + f0, raw);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) q[i] = __uint_as_float(raw[i]) + vec[V_BKQ + f0 + i];
+        for (int i = 0; i < 32; ++i) q[i] = __uint_as_float(raw[i]);
+        add_vec(q, V_BKQ);
 
-        // ---- attention over the agent's own token and the nx other tokens (networks.py:296-306)
+        // ---- attention over the agent's own token and the nx other tokens (networks.py:296-306).
+        // A token embedding is affine in the token's 3 or 5 raw inputs, y_f = sum_a in~_a W~_af (in~ = inputs and 1,
+        // W~ = weights and bias), so the LayerNorm statistics of every token follow from the network constants
+        // c_a = sum_f W~_af and M_ab = sum_f W~_af W~_bf (hs_policy_prepare), the scores from the ten row sums
+        // G_a = sum_f q_f lw_f W~_af, and the weighted token average from U_a = sum_j p_j rstd_j in~_ja: no token is
+        // ever embedded feature by feature.
         {
             constexpr int MT = 6;
+            HS_TSTAMP(11);
             tc_ld32(lane_base + PT_COL_STASH + f0, raw);      // x0
-            float part_s[3 + 3 * MT], tot[3 + 3 * MT];
-            float s0 = 0.f, c1 = 0.f, c2 = 0.f;
+            HS_TSTAMP(12);
+            float ps[13], tot[13];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float qlw = q[i] * vec[V_LNE_W + f0 + i];
-                s0 = fmaf(q[i], __uint_as_float(raw[i]), s0);
-                c1 += qlw;
-                c2 = fmaf(q[i], vec[V_LNE_B + f0 + i], c2);
-            }
-            part_s[0] = s0; part_s[1] = c1; part_s[2] = c2;
-            const float* in = oc + row * PL_MAX_TOK_IN;
-            auto token = [&](int j, int i) {              // raw embedding of token j (1-based among the extra tokens), feature f0 + i
-                const int f = f0 + i;
-                if (j < A.n_others) {
-                    const float* t = in + j * 3;
-                    return fmaf(t[2], vec[V_WEO + 2 * PL_E + f], fmaf(t[1], vec[V_WEO + PL_E + f], fmaf(t[0], vec[V_WEO + f], vec[V_BEO + f])));
-                }
-                const float* t = in + no3 + (j - A.n_others) * 5;
-                return fmaf(t[4], vec[V_WEC + 4 * PL_E + f], fmaf(t[3], vec[V_WEC + 3 * PL_E + f], fmaf(t[2], vec[V_WEC + 2 * PL_E + f],
-                       fmaf(t[1], vec[V_WEC + PL_E + f], fmaf(t[0], vec[V_WEC + f], vec[V_BEC + f])))));
-            };
+            for (int a = 0; a < 13; ++a) ps[a] = 0.f;
+            float qlw[32];
+            {
+                float t[32];
+                pt_ld32f(vec + V_LNE_W + f0, t);
 #pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                float a = 0.f, b = 0.f, d = 0.f;
-                if (j < nx) {
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const float y = token(j, i);
-                        a += y; b = fmaf(y, y, b); d = fmaf(q[i] * vec[V_LNE_W + f0 + i], y, d);
-                    }
+                for (int i = 0; i < 32; ++i) qlw[i] = q[i] * t[i];
+                ps[1] = pt_sum32(qlw);
+                pt_ld32f(vec + V_LNE_B + f0, t);
+                ps[2] = pt_dot32(q, t);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(raw[i]);
+                ps[0] = pt_dot32(q, t);
+                // G_a: rows of the augmented embedding matrices (3 weights + bias, 5 weights + bias)
+                const int rows[10] = {V_WEO, V_WEO + PL_E, V_WEO + 2 * PL_E, V_BEO, V_WEC, V_WEC + PL_E, V_WEC + 2 * PL_E,
+                                      V_WEC + 3 * PL_E, V_WEC + 4 * PL_E, V_BEC};
+#pragma unroll
+                for (int a = 0; a < 10; ++a) {
+                    pt_ld32f(vec + rows[a] + f0, t);
+                    ps[3 + a] = pt_dot32(qlw, t);
                 }
-                part_s[3 + 3 * j] = a; part_s[4 + 3 * j] = b; part_s[5 + 3 * j] = d;
             }
-            pt_row_exchange<3 + 3 * MT>(xch, row, part, part_s, tot);
+            HS_TSTAMP(13);
+            pt_row_exchange<13>(xch, row, part, ps, tot);
+            HS_TSTAMP(14);
+            auto in = [&](int i) { return oc[i * PT_M + row]; };        // [input][row]: conflict-free
+            const float* gr = vec + V_GRAM;
             float mean[MT], rstd[MT], sc[MT], m = tot[0];
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
-                mean[j] = tot[3 + 3 * j] * (1.0f / PL_E);
-                rstd[j] = rsqrtf(fmaxf(tot[4 + 3 * j] * (1.0f / PL_E) - mean[j] * mean[j], 0.0f) + 1e-5f);
-                sc[j] = j < nx ? fmaf(rstd[j], tot[5 + 3 * j] - mean[j] * tot[1], tot[2]) : -INFINITY;
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                if (j < A.n_others) {
+                    const float t[4] = {in(j * 3), in(j * 3 + 1), in(j * 3 + 2), 1.0f};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const float4 mrow = *reinterpret_cast<const float4*>(gr + 4 + 4 * a);
+                        s1 = fmaf(t[a], gr[a], s1);
+                        s3 = fmaf(t[a], tot[3 + a], s3);
+                        s2 = fmaf(t[a], fmaf(t[3], mrow.w, fmaf(t[2], mrow.z, fmaf(t[1], mrow.y, t[0] * mrow.x))), s2);
+                    }
+                } else if (j < nx) {
+                    const int tb = no3 + (j - A.n_others) * 5;
+                    const float t[6] = {in(tb), in(tb + 1), in(tb + 2), in(tb + 3), in(tb + 4), 1.0f};
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const float2 m0 = *reinterpret_cast<const float2*>(gr + 26 + 6 * a);
+                        const float2 m1 = *reinterpret_cast<const float2*>(gr + 28 + 6 * a);
+                        const float2 m2 = *reinterpret_cast<const float2*>(gr + 30 + 6 * a);
+                        s1 = fmaf(t[a], gr[20 + a], s1);
+                        s3 = fmaf(t[a], tot[7 + a], s3);
+                        s2 = fmaf(t[a], fmaf(t[5], m2.y, fmaf(t[4], m2.x, fmaf(t[3], m1.y, fmaf(t[2], m1.x, fmaf(t[1], m0.y, t[0] * m0.x))))), s2);
+                    }
+                }
+                mean[j] = s1 * (1.0f / PL_E);
+                rstd[j] = rsqrtf(fmaxf(s2 * (1.0f / PL_E) - mean[j] * mean[j], 0.0f) + 1e-5f);
+                sc[j] = j < nx ? fmaf(rstd[j], s3 - mean[j] * tot[1], tot[2]) : -INFINITY;
                 m = fmaxf(m, sc[j]);
             }
+            HS_TSTAMP(15);
             const float p0 = expf(tot[0] - m);
-            float l = p0, pl = 0.f, pj[MT];
-#pragma unroll
-            for (int j = 0; j < MT; ++j) { pj[j] = expf(sc[j] - m); l += pj[j]; pl += pj[j]; }
-            const float inv = 1.0f / l;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            float l = p0, pl = 0.f, pm = 0.f, uo[4] = {0.f, 0.f, 0.f, 0.f}, uc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
-                if (j < nx) {
-                    const float pr = pj[j] * rstd[j];
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) v[i] = fmaf(pr, token(j, i) - mean[j], v[i]);
+                const float pj = expf(sc[j] - m);               // exp(-inf) = 0 for absent tokens
+                l += pj; pl += pj;
+                const float pr = pj * rstd[j];
+                pm = fmaf(pr, mean[j], pm);
+                if (j < A.n_others) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) uo[a] = fmaf(pr, in(j * 3 + a), uo[a]);
+                    uo[3] += pr;
+                } else if (j < nx) {
+                    const int tb = no3 + (j - A.n_others) * 5;
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) uc[a] = fmaf(pr, in(tb + a), uc[a]);
+                    uc[5] += pr;
                 }
             }
+            const float inv = 1.0f / l;
+            HS_TSTAMP(16);
+            {
+                float y[32], t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                v[i] = fmaf(p0, __uint_as_float(raw[i]), fmaf(v[i], vec[V_LNE_W + f0 + i], pl * vec[V_LNE_B + f0 + i])) * inv;
+                for (int i = 0; i < 32; ++i) y[i] = -pm;
+                const int rows[10] = {V_WEO, V_WEO + PL_E, V_WEO + 2 * PL_E, V_BEO, V_WEC, V_WEC + PL_E, V_WEC + 2 * PL_E,
+                                      V_WEC + 3 * PL_E, V_WEC + 4 * PL_E, V_BEC};
+                const float u[10] = {uo[0], uo[1], uo[2], uo[3], uc[0], uc[1], uc[2], uc[3], uc[4], uc[5]};
+#pragma unroll
+                for (int a = 0; a < 10; ++a) {
+                    pt_ld32f(vec + rows[a] + f0, t);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) y[i] = fmaf(u[a], t[i], y[i]);
+                }
+                float lwv[32];
+                pt_ld32f(vec + V_LNE_W + f0, lwv);
+                pt_ld32f(vec + V_LNE_B + f0, t);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(p0, __uint_as_float(raw[i]), fmaf(y[i], lwv[i], pl * t[i])) * inv;
+            }
+            HS_TSTAMP(17);
             store_A(v);                                   // xbar
+            HS_TSTAMP(18);
         }
 
+        HS_TSTAMP(4);
         // ---- L2: y1 = LN1(x0 + W_ov xbar + b_ov)
         gemm(PL_E, T.L3, PL_E);
+        HS_TSTAMP(5);
         load_D();
         {
             uint32_t x0r[32];
             tc_ld32(lane_base + PT_COL_STASH + f0, x0r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += vec[V_BOV + f0 + i] + __uint_as_float(x0r[i]);
+            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(x0r[i]);
+            add_vec(v, V_BOV);
         }
         layernorm(v, V_LN1_W, V_LN1_B);
 #pragma unroll
@@ -338,25 +431,28 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
         pt_st32(lane_base + PT_COL_STASH + f0, raw);          // y1 replaces x0
         store_A(v);
 
+        HS_TSTAMP(6);
         // ---- L3: h = gelu(W1 y1 + b1)
         gemm(PL_E, T.L4, PL_E);
+        HS_TSTAMP(7);
         load_D();
+        add_vec(v, V_B1);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float h = v[i] + vec[V_B1 + f0 + i];
-            v[i] = 0.5f * h * (1.0f + pt_erf(h * 0.70710678118654752f));
-        }
+        for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + pt_erf(v[i] * 0.70710678118654752f));
         store_A(v);
 
         // ---- L4: y2 = LN2(y1 + W2 h + b2); the next tile's first layer is requested behind it
         const bool more = tile + gridDim.x < ntiles;
+        HS_TSTAMP(8);
         gemm(PL_E, T.L0, more ? k0 : 0u);
+        HS_TSTAMP(9);
         load_D();
         {
             uint32_t y1r[32];
             tc_ld32(lane_base + PT_COL_STASH + f0, y1r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += vec[V_B2 + f0 + i] + __uint_as_float(y1r[i]);
+            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(y1r[i]);
+            add_vec(v, V_B2);
         }
         layernorm(v, V_LN2_W, V_LN2_B);
         if (A.feat_out != nullptr && valid) {
@@ -371,8 +467,9 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
             for (int h = 0; h < PL_HEAD_MAX; ++h) {
                 float s = 0.f;
                 if (h < A.head_dim) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) s = fmaf(v[i], vec[V_WH + h * PL_E + f0 + i], s);
+                    float t[32];
+                    pt_ld32f(vec + V_WH + h * PL_E + f0, t);
+                    s = pt_dot32(v, t);
                 }
                 ph[h] = s;
             }
@@ -421,13 +518,14 @@ hs_policy_forward_tc_kernel(const PolicyArgs A, const uint8_t* __restrict__ img)
             }
         }
     }
+    HS_TSTAMP(10);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 static size_t policy_tc_smem_bytes() {
-    return 2 * (size_t)PT_LAYER_BYTES + ((size_t)PT_M * 4 * PT_XW + (size_t)PT_M * PL_MAX_TOK_IN + 3728) * sizeof(float) + 64;
+    return 2 * (size_t)PT_LAYER_BYTES + ((size_t)PT_M * 4 * PT_XW + (size_t)PT_M * PL_MAX_TOK_IN + 3792) * sizeof(float) + 64;
 }
 
 }  // namespace

@@ -76,14 +76,18 @@ def main():
         s, o, c = torch.randn(E, A, 1, D, device=dev), torch.randn(E, A, 2, 3, device=dev), torch.randn(E, A, 3, 5, device=dev)
         eps = torch.randn(E, A, 4, device=dev)
         out = {}
-        us = timed(lambda: net(s, o, c, eps=eps, out=out))
+        us_ffma = timed(lambda: net(s, o, c, eps=eps, out=out, impl=1))
+        us = timed(lambda: net(s, o, c, eps=eps, out=out, impl=2))
         with torch.no_grad():
             us_ref = timed(lambda: ref(s, o, c, eps), reps=5)
             a_ref, lp_ref = ref(s, o, c, eps)
         err = (out["action"] - a_ref).abs().max().item()
         R = E * A
-        print(json.dumps({"what": "hs_policy_forward", "E": E, "rows": R, "us": us, "rows_per_s": R / (us * 1e-6),
-                          "fp32_TFLOPs": 2 * mac_per_row * R / (us * 1e-6) / 1e12, "torch_eager_us": us_ref,
+        print(json.dumps({"what": "hs_policy_forward", "E": E, "rows": R, "us_tcgen05": us, "us_ffma": us_ffma,
+                          "rows_per_s": R / (us * 1e-6),
+                          "fp32_equiv_TFLOPs": 2 * mac_per_row * R / (us * 1e-6) / 1e12,
+                          "tf32_TFLOPs_executed": 3 * 2 * (40 * 128 + 4 * 128 * 128) * R / (us * 1e-6) / 1e12,
+                          "ffma_TFLOPs": 2 * mac_per_row * R / (us_ffma * 1e-6) / 1e12, "torch_eager_us": us_ref,
                           "speedup": us_ref / us, "max_abs_action_diff_vs_eager": err}), flush=True)
 
 
