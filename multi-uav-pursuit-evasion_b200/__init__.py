@@ -11,10 +11,10 @@ from .config import Cfg, build_hs_config, compose, load_drone_params
 from .engine import HsEngine, RolloutStorage
 from . import rollout
 from .rollout import compute_gae
-from .policy import FusedPolicy
+from .policy import FusedPolicy, MAPPOActorCritic
 from . import parallel
 from .envs import AgentSpec, GenBuffer, HideAndSeek, HideAndSeek_envgen, Hover, IsaacEnv, PIDRateController, TP_net
 
-__all__ = ["parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+__all__ = ["parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "MAPPOActorCritic", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
            "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
            "HideAndSeek", "HideAndSeek_envgen", "GenBuffer", "Hover", "IsaacEnv", "PIDRateController", "TP_net"]

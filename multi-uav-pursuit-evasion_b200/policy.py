@@ -166,3 +166,42 @@ class FusedPolicy:
         return out
 
     __call__ = forward
+
+
+class MAPPOActorCritic:
+    """What ``MAPPOPolicy.__call__`` does during a rollout (omni_drones/learning/mappo.py:235-251: shared actor over
+    ``("agents", "observation")`` -> ``("agents", "action")`` + ``"drone.action_logp"``, then ``value_op`` with
+    ``critic_input: obs`` -> ``"state_value"``), as two kernel launches.  A drop-in for the ``policy`` argument of the
+    collector (``SyncDataCollector(env, policy=MAPPOActorCritic(actor, critic))``); the learner keeps its own modules and
+    calls :meth:`refresh` after its optimiser steps."""
+
+    def __init__(self, actor: FusedPolicy, critic: Optional[FusedPolicy] = None, agent_name: str = "drone",
+                 obs_key=("agents", "observation"), action_key=("agents", "action"), keep_noise: bool = False):
+        if not actor.is_actor:
+            raise _lib.HsError("MAPPOActorCritic: `actor` needs a log_std parameter (DiagGaussian head)")
+        self.actor, self.critic = actor, critic
+        self.obs_key, self.action_key = tuple(obs_key), tuple(action_key)
+        self.logp_key, self.keep_noise = f"{agent_name}.action_logp", keep_noise
+        if getattr(actor, "rng_state", None) is None:
+            actor.seed(0)
+
+    def refresh(self):
+        self.actor.refresh()
+        if self.critic is not None:
+            self.critic.refresh()
+        return self
+
+    def __call__(self, tensordict, deterministic: bool = False):
+        obs = tensordict.get(self.obs_key)
+        s = obs.get("state_self")
+        o = obs.get("state_others") if self.actor.n_others else None
+        c = obs.get("cylinders") if self.actor.n_cyl else None
+        # fresh result tensors every call: the collector keeps references to the previous step's
+        a = self.actor.forward(s, o, c, sample=not deterministic, want_eps=self.keep_noise)
+        tensordict.set(self.action_key, a["action"])
+        tensordict.set(self.logp_key, a["logp"])
+        if self.keep_noise and "eps" in a:
+            tensordict.set("action_noise", a["eps"])
+        if self.critic is not None:
+            tensordict.set("state_value", self.critic.forward(s, o, c)["head"])
+        return tensordict

@@ -183,3 +183,41 @@ def test_gpu_policy_in_the_tick_graph(built_lib, rollout_steps):
             assert torch.equal(runs[0][t][k], runs[1][t][k]), f"tick {t}: {k} differs between graph replay and direct launches"
     assert not torch.equal(runs[0][0]["action"], runs[0][1]["action"])
     assert runs[0][0]["state_value"].abs().sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rollout_steps", [0, 5])
+def test_gpu_collector_with_fused_actor_critic(built_lib, rollout_steps):
+    """MAPPOActorCritic as the collector's policy (what MAPPOPolicy.__call__ does in the reference's rollout,
+    mappo.py:235-251): the [E, T] batch carries action / drone.action_logp / state_value that equal the CPU restatement
+    evaluated on the observations of the same batch, with the noise the kernel reports; and the env consumed exactly
+    those actions (prev_action = tanh-squashed CTBR of the sampled action, transforms.py:431-441)."""
+    import mupe_b200
+    dev = torch.device("cuda:0")
+    E, T = 48, 5
+    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides={"task.env.num_envs": E, "task.sim.device": "cuda:0",
+                                                                 "task.env.rollout_steps": rollout_steps})
+    base = mupe_b200.IsaacEnv.REGISTRY[cfg.task.name.lower()](cfg, headless=True)
+    env = mupe_b200.TransformedEnv(base, mupe_b200.Compose(mupe_b200.InitTracker(), mupe_b200.PIDRateController()))
+    p, _, _ = _load("actor_tp")
+    pc, _, _ = _load("critic_tp")
+    actor = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in p.items()}, 2, 3, dev).seed(5)
+    critic = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in pc.items()}, 2, 3, dev)
+    pol = mupe_b200.MAPPOActorCritic(actor, critic, keep_noise=True)
+    col = mupe_b200.SyncDataCollector(env, policy=pol, frames_per_batch=E * T, total_frames=E * T, return_same_td=True)
+    d = next(iter(col)).clone()
+    assert tuple(d.batch_size) == (E, T)
+    obs = {"state_self": d[("agents", "observation", "state_self")].cpu().flatten(0, 2),
+           "state_others": d[("agents", "observation", "state_others")].cpu().flatten(0, 2),
+           "cylinders": d[("agents", "observation", "cylinders")].cpu().flatten(0, 2)}
+    eps = d["action_noise"].cpu().flatten(0, 2)
+    a_w, lp_w, _ = PO.actor(p, obs, eps)
+    torch.testing.assert_close(d["drone.action_logp"].cpu().flatten(0, 2), lp_w, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(d["state_value"].cpu().flatten(0, 2), PO.critic(pc, obs), rtol=1e-4, atol=2e-6)
+    assert eps.std() > 0.8 and not torch.equal(eps[:E * 3], eps[E * 3:2 * E * 3])       # fresh noise every step
+    # ("agents", "action") of the batch holds the rotor commands the PID transform wrote over it (transforms.py:455); the
+    # sampled action itself is checked through what the tick derived from it: prev_action = [tanh(a_0..2), clamp((tanh(a_3)+1)/2)]
+    prev = d[("next", "info", "prev_action")].cpu().flatten(0, 2)
+    want_prev = torch.cat([torch.tanh(a_w[:, :3]), ((torch.tanh(a_w[:, 3:]) + 1) / 2).clamp(0, 0.9)], -1)
+    torch.testing.assert_close(prev, want_prev, rtol=1e-4, atol=2e-6)
+    env.close()
