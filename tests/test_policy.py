@@ -220,4 +220,15 @@ def test_gpu_collector_with_fused_actor_critic(built_lib, rollout_steps):
     prev = d[("next", "info", "prev_action")].cpu().flatten(0, 2)
     want_prev = torch.cat([torch.tanh(a_w[:, :3]), ((torch.tanh(a_w[:, 3:]) + 1) / 2).clamp(0, 0.9)], -1)
     torch.testing.assert_close(prev, want_prev, rtol=1e-4, atol=2e-6)
+    # ... and the learner's first step on that batch: GAE straight on the [E, T] views (time-major memory in rollout
+    # mode: no copy), bit-identical to the reference's loop on the same numbers (oracle/gae_oracle.py)
+    from oracle import gae_oracle as GO
+    reward, value, done = d[("next", "agents", "reward")], d["state_value"], d[("next", "done")]
+    nobs = d[("next", "agents", "observation")]
+    nv = critic.forward(nobs.get("state_self")[:, -1].contiguous(), nobs.get("state_others")[:, -1].contiguous(),
+                        nobs.get("cylinders")[:, -1].contiguous())["head"]
+    adv, ret = mupe_b200.compute_gae(reward, done, value, nv, 0.995, 0.95)
+    a_want, r_want = GO.compute_gae(reward.cpu().numpy(), done.cpu().unsqueeze(2).expand(E, T, 3, 1).numpy(),
+                                    value.cpu().numpy(), nv.cpu().numpy(), 0.995, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), a_want) and np.array_equal(ret.cpu().numpy(), r_want)
     env.close()
