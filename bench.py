@@ -222,6 +222,12 @@ def run_gpu_arm(args):
     def tick(i):
         return engines[i % ROTATE].replay_tick()
 
+    # the timed region replays ONE graph per 64-tick rollout: 64 kernel nodes rotating over the 16 L2-cold batches
+    # (nothing in a rollout needs the host once the actions are on the device); leftover ticks use the per-tick graphs
+    from mupe_b200.engine import RotatingRolloutGraph
+    rollout_graph = RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT) \
+        if os.environ.get("HS_BENCH_PER_TICK_GRAPHS", "0") != "1" and ROLLOUT % (2 * ROTATE) == 0 else None
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -230,6 +236,8 @@ def run_gpu_arm(args):
     W = max(args.warmup, 3)
     for i in range(W):
         tick(i)
+    if rollout_graph is not None:
+        rollout_graph.replay()
     barrier()
     launches0 = sum(e.launches for e in engines)
     sampler = ClockSampler(local)
@@ -239,10 +247,16 @@ def run_gpu_arm(args):
     w0 = time.perf_counter()
     torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed region
     ev0.record()
-    for i in range(args.steps):
-        tick(i)
-        eng = engines[i % ROTATE]
-        if world > 1 and (i + 1) % ROLLOUT == 0:
+    i = 0
+    while i < args.steps:
+        if rollout_graph is not None and i % ROLLOUT == 0 and i + ROLLOUT <= args.steps:
+            rollout_graph.replay()
+            i += ROLLOUT
+        else:
+            tick(i)
+            i += 1
+        eng = engines[(i - 1) % ROTATE]
+        if world > 1 and i % ROLLOUT == 0:
             # the one collective of the path: episode returns of the rollout, all ranks
             dist.all_gather(gather_buf, eng.stats[17].contiguous())
     ev1.record()
@@ -508,8 +522,7 @@ def run_gpu_arm(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E, "launch_us": step_us,
                 "share_of_step": 1.0,
                 "note": "3077 algorithmic B/env-tick (SURVEY 8d, tick + predictor rows) x 4096 envs per launch over the "
-                        "launch period measured in the timed region (CUDA events, one graph launch per tick, L2-cold rotating "
-                        "batches).  A 12.6 MB launch cannot be HBM-bound: the kernel is a dependent chain - 7.9 us control "
+                        "launch period measured in the timed region (CUDA events, L2-cold rotating batches).  A 12.6 MB launch cannot be HBM-bound: the kernel is a dependent chain - 7.9 us control "
                         "tick on 4 warps per SM, then 10 LSTM steps x 1.3 us on the tensor pipe + cell update, 3 us FC + rows "
                         "(tools/fused_phases.py) - so the fraction states how far a latency-bound launch is from the "
                         "bandwidth roof, not a kernel inefficiency; the HBM-bound regime is roofline_at_scale"}
@@ -521,6 +534,8 @@ def run_gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "parallelism": f"env-sharded x{world}",
                        "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
+                       "launch": ("one CUDA graph per 64-tick rollout (64 kernel nodes, one per tick, rotating over the batches)"
+                                  if rollout_graph is not None else "one CUDA graph launch per tick"),
                        "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
             "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
             "predictor_kernel": {-1: "auto -> inside hs_tick_tp_fused_kernel (tick + 3xTF32 tcgen05 predictor in one launch, 32-env tile "

@@ -355,3 +355,41 @@ def test_fused_tick_predictor_kernel_equals_two_launches(E, C):
     assert engs[0].launches - engs[1].launches == 4 and engs[2].launches == engs[0].launches
     for e in engs:
         e.close()
+
+
+def test_rotating_rollout_graph_equals_per_tick_launches():
+    """RotatingRolloutGraph: one CUDA graph of 8 ticks rotating over 2 engines (4 ticks each) must leave both engines
+    exactly where 4 direct hs_step_fused calls per engine leave twin engines, replay after replay."""
+    import mupe_b200
+    from mupe_b200.engine import RotatingRolloutGraph
+    P, E = O.HSParams(), 200
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(9)
+    engs, twins, acts = [], [], []
+    for k in range(2):
+        init = O.sample_reset(P, E, g)
+        act = torch.randn(E, 3, 4, generator=g).to(dev)
+        for lst in (engs, twins):
+            e = mupe_b200.HsEngine(cfg, dev)
+            e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+            e.step_post_tp(e.tp_weights(tp))
+            lst.append(e)
+        acts.append(act)
+    rg = RotatingRolloutGraph(engs, [e.tp_weights(tp) for e in engs], ticks=8)
+    for e, a in zip(engs, acts):
+        e.graph_action.copy_(a)
+    for rep in range(3):
+        rg.replay()
+        for e, t, a in zip(engs, twins, acts):
+            for _ in range(4):
+                ref = t.step_fused(a, t.tp_weights(tp))
+            out = e.out
+            for k in ("state_self", "state_drones", "reward", "tp_input", "drone_state", "done"):
+                assert torch.equal(out[k], ref[k]), (rep, k)
+            assert torch.equal(e.arena, t.arena) and torch.equal(e.stats, t.stats)
+            assert e.launches == t.launches
+    for e in engs + twins:
+        e.close()

@@ -45,7 +45,10 @@ def run(E, dev, peak, reps=20):
     ab = bench.algorithmic_bytes(C=C)
     for name, fn, nbytes in (
             ("tick", lambda e, st: check(lib.hs_step_pre(e._h, e.graph_action.data_ptr(), 1, None, st), "pre"), ab["tick"]),
-            ("tp_fill", lambda e, st: check(lib.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp)), None, st), "post"), ab["fill"])):
+            ("tp_fill", lambda e, st: check(lib.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp)), None, st), "post"), ab["fill"]),
+            # the whole tick as hs_step_fused launches it: ONE kernel up to one 32-env tile per SM, tick + predictor above
+            ("step_fused", lambda e, st: check(lib.hs_step_fused(e._h, e.graph_action.data_ptr(), 1, None,
+                                                                 ctypes.byref(e.tp_weights(tp)), None, st), "fused"), ab["total"])):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
         with torch.cuda.graph(g, stream=side):
