@@ -446,20 +446,19 @@ def run_gpu_arm(args):
             actor = FusedPolicy(init_params(D_self, A - 1, K, 4, True, dev), A - 1, K, dev).seed(1)
             critic = FusedPolicy(init_params(D_self, A - 1, K, 1, False, dev), A - 1, K, dev)
             pe.attach_policy(actor, critic)
-            pe.capture_tick_graphs(wpe, raw=True)
-            for _ in range(8):
-                pe.replay_tick()
+            prg = RotatingRolloutGraph([pe], [wpe], ROLLOUT)       # (actor -> critic -> tick) x 64 as ONE graph
+            prg.replay()
             torch.cuda.synchronize()
-            npol = max(64, min(args.steps, 512))
+            npol = max(1, min(args.steps, 512) // ROLLOUT) * ROLLOUT
             k0.record()
-            for _ in range(npol):
-                pe.replay_tick()
+            for _ in range(npol // ROLLOUT):
+                prg.replay()
             k1.record()
             torch.cuda.synchronize()
             pol_us = 1e3 * k0.elapsed_time(k1) / npol
             extra["rollout_step_with_policy"] = {
                 "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us, "launches_per_step": 3,
-                "what": "one CUDA graph per rollout step: hs_policy_forward_tc_kernel (actor, tcgen05 3xTF32, in-kernel noise) + "
+                "what": "one CUDA graph per 64-step rollout, per step: hs_policy_forward_tc_kernel (actor, tcgen05 3xTF32, in-kernel noise) + "
                         "hs_policy_forward_tc_kernel (critic) + hs_tick_tp_fused_kernel (tick + predictor), observation never "
                         "leaves HBM; same 4096-env batch every step (L2-warm), single GPU"}
             pe.close()
