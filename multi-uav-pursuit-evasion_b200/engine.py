@@ -545,12 +545,18 @@ class RotatingRolloutGraph:
             st = torch.cuda.current_stream(dev).cuda_stream
             for t in range(ticks):
                 e, w = engines[t % n], tp_weights[t % n]
-                e._bind(e.next_index(), e.cur)
+                prev, i = e.cur, e.next_index()
+                action = e.graph_action
+                if getattr(e, "_actor", None) is not None:       # attached policy: actor (+ critic) on the previous observation
+                    e._launch_policy(prev, i)
+                    action = e.policy_out[i]["action"]
+                    self.policy_kernels = 2 if e._critic is not None else 1
+                e._bind(i, prev)
                 if e.cfg.use_tp_net:
-                    check(lib.hs_step_fused(e._h, e.graph_action.data_ptr(), 1 if raw else 0, e.graph_reset_pid.data_ptr(),
+                    check(lib.hs_step_fused(e._h, action.data_ptr(), 1 if raw else 0, e.graph_reset_pid.data_ptr(),
                                             C.byref(w), None, st), "hs_step_fused (capture)")
                 else:
-                    check(lib.hs_step_pre(e._h, e.graph_action.data_ptr(), 1 if raw else 0, e.graph_reset_pid.data_ptr(), st),
+                    check(lib.hs_step_pre(e._h, action.data_ptr(), 1 if raw else 0, e.graph_reset_pid.data_ptr(), st),
                           "hs_step_pre (capture)")
         # kernels per replay and engine; the capture-time calls were counted by the handle but never ran
         self.kernels = [int(lib.hs_launch_count(e._h)) - c for e, c in zip(engines, counts0)]
@@ -563,4 +569,5 @@ class RotatingRolloutGraph:
         self.graph.replay()
         self.replays += 1
         for e, k in zip(self.engines, self.kernels):
-            e._uncounted = getattr(e, "_uncounted", 0) + k       # cur is unchanged: a multiple of the set count ticks
+            # (cur is unchanged: every engine advanced by a multiple of its set count)
+            e._uncounted = getattr(e, "_uncounted", 0) + k + getattr(self, "policy_kernels", 0) * self.per_engine

@@ -232,3 +232,46 @@ def test_gpu_collector_with_fused_actor_critic(built_lib, rollout_steps):
                                     value.cpu().numpy(), nv.cpu().numpy(), 0.995, 0.95)
     assert np.array_equal(adv.cpu().numpy(), a_want) and np.array_equal(ret.cpu().numpy(), r_want)
     env.close()
+
+
+@pytest.mark.gpu
+def test_gpu_rollout_graph_with_attached_policy(built_lib):
+    """RotatingRolloutGraph with an attached policy: (actor -> critic -> tick) x 4 as ONE graph equals four policy_tick
+    calls on a twin engine with the same seed, bit for bit (actions really come from the actor: they change every tick)."""
+    import mupe_b200
+    from mupe_b200.engine import RotatingRolloutGraph
+    dev = torch.device("cuda:0")
+    E = 64
+    p, _, _ = _load("actor_tp")
+    pc, _, _ = _load("critic_tp")
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(16, 15, 5).to(dev)
+    g = torch.Generator().manual_seed(3)
+    init = dict(drone_pos=torch.rand(E, 3, 3, generator=g) * 0.4 + torch.tensor([0.1, -0.2, 0.5]),
+                drone_rot=torch.tensor([1.0, 0, 0, 0]).expand(E, 3, 4).contiguous(),
+                target_pos=torch.rand(E, 3, generator=g) * 0.4 + torch.tensor([-0.5, -0.2, 0.5]),
+                cyl_pos=torch.cat([torch.rand(E, 5, 2, generator=g) - 0.5, torch.full((E, 5, 1), 0.6)], -1))
+    engs = []
+    for _ in range(2):
+        eng = mupe_b200.HsEngine(mupe_b200.build_hs_config(E), dev)
+        actor = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in p.items()}, 2, 3, dev).seed(42)
+        critic = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in pc.items()}, 2, 3, dev)
+        eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        eng.step_post_tp(eng.tp_weights(tp))
+        eng.attach_policy(actor, critic)
+        engs.append(eng)
+    rg = RotatingRolloutGraph([engs[0]], [engs[0].tp_weights(tp)], ticks=4)
+    acts = []
+    for rep in range(2):
+        rg.replay()
+        for _ in range(4):
+            ref = engs[1].policy_tick(engs[1].tp_weights(tp))
+            acts.append(engs[1].policy_out[engs[1].cur]["action"].clone())
+        for k in ("state_self", "reward", "tp_input", "drone_state"):
+            assert torch.equal(engs[0].out[k], ref[k]), (rep, k)
+        for k in ("action", "logp", "state_value"):
+            assert torch.equal(engs[0].policy_out[engs[0].cur][k], engs[1].policy_out[engs[1].cur][k]), (rep, k)
+        assert engs[0].launches == engs[1].launches
+    assert not torch.equal(acts[0], acts[1])
+    for e in engs:
+        e.close()
