@@ -33,6 +33,10 @@ CASES = {
     "wall_tp": (dict(num_cylinders=5), 16, "wall", 4, 5, None),
     "c8_tp": (dict(num_cylinders=8), 16, "random_cylinders", 8, 4, None),
     "done_tick": (dict(), 8, "random_cylinders", 4, 4, 797.0),
+    "passage_tp": (dict(num_cylinders=6), 16, "passage", 4, 4, None),
+    "narrow_gap_tp": (dict(num_cylinders=5), 16, "narrow_gap", 4, 4, None),
+    "deploy_smooth_tp": (dict(use_deployment=True), 12, "random_cylinders", 4, 4, None),     # smoothness reward not gated
+    "a2_tp": (dict(num_agents=2), 12, "random_cylinders", 4, 4, None),
 }
 
 
