@@ -35,7 +35,8 @@ CASES = {
     "done_tick": (dict(), 8, "random_cylinders", 4, 4, 797.0),
     "passage_tp": (dict(num_cylinders=6), 16, "passage", 4, 4, None),
     "narrow_gap_tp": (dict(num_cylinders=5), 16, "narrow_gap", 4, 4, None),
-    "deploy_smooth_tp": (dict(use_deployment=True), 12, "random_cylinders", 4, 4, None),     # smoothness reward not gated
+    "deploy_smooth_tp": (dict(use_deployment=True, smoothness_coef=2.0), 12, "random_cylinders", 4, 4, None),   # smoothness reward paid
+    "gated_smooth_tp": (dict(use_deployment=False, smoothness_coef=2.0), 12, "random_cylinders", 4, 3, None),   # ... and gated off (hideandseek.py:992-994)
     "a2_tp": (dict(num_agents=2), 12, "random_cylinders", 4, 4, None),
 }
 
