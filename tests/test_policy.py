@@ -275,3 +275,33 @@ def test_gpu_rollout_graph_with_attached_policy(built_lib):
     assert not torch.equal(acts[0], acts[1])
     for e in engs:
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+def test_gpu_policy_full_size_properties(built_lib, impl):
+    """65 536 envs x 3 agents = 196 608 rows (BASELINE config 4 size), size-independent properties of the network:
+    (a) rows are independent - a row permutation of the inputs permutes the outputs; (b) the attention is a set function
+    of the keys - swapping the two other-agent tokens, or permuting the cylinder tokens, leaves the result unchanged up to
+    fp32 summation order; (c) the two kernels (fp32 FFMA, tcgen05 3xTF32) agree within the parity tolerance."""
+    import mupe_b200
+    dev = torch.device("cuda:0")
+    R = 65536 * 3
+    p, _, _ = _load("actor_tp")
+    net = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in p.items()}, 2, 3, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    s = torch.randn(R, 1, 35, generator=g, device=dev)
+    o = torch.randn(R, 2, 3, generator=g, device=dev)
+    c = torch.randn(R, 3, 5, generator=g, device=dev)
+    c[torch.rand(R, 3, generator=g, device=dev) < 0.3] = -5.0
+    eps = torch.randn(R, 4, generator=g, device=dev)
+    base = net(s, o, c, eps=eps, impl=impl, out={})
+    perm = torch.randperm(R, generator=g, device=dev)
+    out_p = net(s[perm].contiguous(), o[perm].contiguous(), c[perm].contiguous(), eps=eps[perm].contiguous(), impl=impl, out={})
+    assert torch.equal(out_p["action"], base["action"][perm]) and torch.equal(out_p["logp"], base["logp"][perm])
+    out_s = net(s, o.flip(1).contiguous(), c[:, [2, 0, 1]].contiguous(), eps=eps, impl=impl, out={})
+    torch.testing.assert_close(out_s["action"], base["action"], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(out_s["logp"], base["logp"], rtol=1e-4, atol=1e-5)
+    other = net(s, o, c, eps=eps, impl=3 - impl, out={})
+    torch.testing.assert_close(other["action"], base["action"], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(other["head"], base["head"], rtol=1e-4, atol=2e-6)
