@@ -317,14 +317,14 @@ def test_host_buffer_entry_point():
     eng.close()
 
 
-@pytest.mark.parametrize("E,C", [(300, 5), (32, 5), (5, 5), (4096, 5), (1000, 8)])
-def test_fused_tick_predictor_kernel_equals_two_launches(E, C):
+@pytest.mark.parametrize("E,C,A", [(300, 5, 3), (32, 5, 3), (5, 5, 3), (4096, 5, 3), (1000, 8, 3), (333, 5, 2), (100, 8, 1)])
+def test_fused_tick_predictor_kernel_equals_two_launches(E, C, A):
     """hs_step_fused: ONE launch (hs_tick_tp_fused_kernel: tick warps + tcgen05 predictor in the same CTA) must give,
     bit for bit, what hs_step_pre followed by hs_step_post_tp gives - first frame (history initialisation), ragged
     tiles, PID resets, both cylinder capacities - and fall back to the two launches when switched off."""
     import mupe_b200
     from mupe_b200 import _lib
-    P = O.HSParams(num_cylinders=C)
+    P = O.HSParams(num_cylinders=C, num_agents=A)
     dev = torch.device("cuda:0")
     cfg = hs_config_from_params(P, E)
     torch.manual_seed(0)
@@ -336,10 +336,10 @@ def test_fused_tick_predictor_kernel_equals_two_launches(E, C):
     for e in engs:
         e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
         e.step_post_tp(e.tp_weights(tp))
-    keys = ("state_self", "state_drones", "state_others", "obs_cylinders", "reward", "done", "drone_state", "tp_input",
-            "tp_groundtruth", "tp_done", "rotor_cmds", "ctbr", "target_rate", "action_error")
+    keys = ("state_self", "state_drones", "obs_cylinders", "reward", "done", "drone_state", "tp_input",
+            "tp_groundtruth", "tp_done", "rotor_cmds", "ctbr", "target_rate", "action_error") + (("state_others",) if A > 1 else ())
     for t in range(4):
-        act = torch.randn(E, 3, 4, generator=g).to(dev)
+        act = torch.randn(E, A, 4, generator=g).to(dev)
         rp = (torch.rand(E, generator=g) < 0.3).to(dev) if t == 2 else None
         pred = [torch.empty(E, 3 * P.future_step, device=dev) for _ in range(3)]
         ref = engs[0].step_pre(act, raw=True, reset_pid=rp)
