@@ -236,6 +236,12 @@ typedef struct hs_host_io {
 } hs_host_io;
 int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid,
                     const hs_tp_weights* w, float* staging_dev, void* stream);
+/* The same call without the final synchronisation, and the wait that completes it: lets a host that
+ * drives several env batches (one handle and one stream each) keep one batch's copies on the PCIe
+ * link while another batch computes.  The host buffers of `io` are valid after hs_host_io_wait. */
+int hs_step_host_io_async(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid,
+                          const hs_tp_weights* w, float* staging_dev, void* stream);
+int hs_host_io_wait(hs_handle* h, void* stream);
 
 /* ---- state views (what omni_drones/views/* get/set did) ------------------------------ */
 enum {

@@ -150,6 +150,9 @@ _EXPORTS = {
     "hs_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "hs_step_host_io": (C.c_int, [C.c_void_p, C.POINTER(hs_host_io), C.c_int, C.c_void_p, C.POINTER(hs_tp_weights),
                                   C.c_void_p, C.c_void_p]),
+    "hs_step_host_io_async": (C.c_int, [C.c_void_p, C.POINTER(hs_host_io), C.c_int, C.c_void_p, C.POINTER(hs_tp_weights),
+                                        C.c_void_p, C.c_void_p]),
+    "hs_host_io_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hs_gen_sample_nearby": (C.c_int, [C.POINTER(hs_gen_params), C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),

@@ -836,15 +836,26 @@ static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw
 
 int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
                     float* staging_dev, void* stream) {
+    const int rc = hs_step_host_io_async(h, io, action_is_raw, reset_pid, w, staging_dev, stream);
+    if (rc != HS_OK) return rc;
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return HS_OK;
+}
+
+int hs_host_io_wait(hs_handle* h, void* stream) {
+    if (!h) return set_err(HS_ERR_INVALID, "hs_host_io_wait: null handle%s");
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return HS_OK;
+}
+
+int hs_step_host_io_async(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid, const hs_tp_weights* w,
+                          float* staging_dev, void* stream) {
     if (!h || !io || !io->action || !staging_dev) return set_err(HS_ERR_INVALID, "hs_step_host_io: null argument%s");
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_host_io: call hs_bind_buffers first%s");
     if (h->cfg.use_tp_net && !w) return set_err(HS_ERR_INVALID, "hs_step_host_io: use_tp_net == 1 needs the predictor weights%s");
     cudaStream_t s = (cudaStream_t)stream;
     if (!h->io_graph_mode) {
-        const int rc = host_io_enqueue(h, io, action_is_raw, reset_pid, w, staging_dev, stream);
-        if (rc != HS_OK) return rc;
-        CUDA_OK(cudaStreamSynchronize(s));
-        return HS_OK;
+        return host_io_enqueue(h, io, action_is_raw, reset_pid, w, staging_dev, stream);
     }
     // one graph launch per tick: the seven stream calls above cost ~25 us of host time per tick at 4096 envs.
     // A graph is valid for one exact set of pointers (host buffers, bound output set, weights) -> small LRU cache.
@@ -883,7 +894,6 @@ int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const
     }
     slot->last_use = ++h->io_clock;
     CUDA_OK(cudaGraphLaunch(slot->exec, s));
-    CUDA_OK(cudaStreamSynchronize(s));
     return HS_OK;
 }
 

@@ -262,7 +262,15 @@ class HsEngine:
         check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if raw else 0, _ptr(rp), self._stream()), "hs_step_pre")
         return self.out
 
-    def step_host(self, action_host: torch.Tensor, weights=None, raw: bool = True, reset_pid: Optional[torch.Tensor] = None):
+    def wait_host(self):
+        """Completes a ``step_host(..., sync=False)``: the host views it returned are valid afterwards."""
+        st = getattr(self, "_host_stream", None)
+        if st is not None:
+            check(lib.hs_host_io_wait(self._h, st), "hs_host_io_wait")
+            self._host_stream = None
+
+    def step_host(self, action_host: torch.Tensor, weights=None, raw: bool = True, reset_pid: Optional[torch.Tensor] = None,
+                  sync: bool = True):
         """hs_step_host_io: one C-ABI call from HOST buffers to HOST buffers - pinned action in, H2D,
         tick (+ fused predictor), D2H of observation / reward / done, stream sync.  Returns
         (host mirror of the policy-facing slab prefix [state_self | state_others | obs_cylinders |
@@ -300,10 +308,13 @@ class HsEngine:
             rp = rp.view(torch.uint8) if rp.dtype == torch.bool else rp.to(torch.uint8)
             rp = rp.contiguous()
         self._keep = [action_host, rp]
-        rc = lib.hs_step_host_io(self._h, io_ref, 1 if raw else 0, _ptr(rp),
-                                 C.byref(weights) if weights is not None else None, hm["staging_ptr"], self._stream())
+        st = self._stream()
+        fn = lib.hs_step_host_io if sync else lib.hs_step_host_io_async
+        rc = fn(self._h, io_ref, 1 if raw else 0, _ptr(rp), C.byref(weights) if weights is not None else None,
+                hm["staging_ptr"], st)
         if rc != 0:
             check(rc, "hs_step_host_io")
+        self._host_stream = None if sync else st      # sync=False: call wait_host() before reading the views
         return views, hm["done"]
 
     def step_fused(self, action: torch.Tensor, weights: "_lib.hs_tp_weights", raw: bool = True,

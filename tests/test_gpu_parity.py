@@ -393,3 +393,41 @@ def test_rotating_rollout_graph_equals_per_tick_launches():
             assert e.launches == t.launches
     for e in engs + twins:
         e.close()
+
+
+def test_host_buffer_tick_async_two_batches_in_flight():
+    """hs_step_host_io_async + hs_host_io_wait: two env batches in flight on two streams give, tick for tick, what the
+    synchronous call gives on twin engines."""
+    import mupe_b200
+    P, E = O.HSParams(), 200
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(11)
+    engs, twins, acts = [], [], []
+    for k in range(2):
+        init = O.sample_reset(P, E, g)
+        for lst in (engs, twins):
+            e = mupe_b200.HsEngine(cfg, dev)
+            e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+            e.step_post_tp(e.tp_weights(tp))
+            lst.append(e)
+        acts.append(torch.empty(E, 3, 4).pin_memory())
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    torch.cuda.synchronize()
+    for t in range(4):
+        res = []
+        for k in range(2):
+            acts[k].copy_(torch.randn(E, 3, 4, generator=g))
+            with torch.cuda.stream(streams[k]):
+                res.append(engs[k].step_host(acts[k], engs[k].tp_weights(tp), raw=True, sync=False))
+        for k in range(2):
+            engs[k].wait_host()
+            views, done = res[k]
+            ref, rdone = twins[k].step_host(acts[k], twins[k].tp_weights(tp), raw=True)
+            for key in ("state_self", "state_others", "obs_cylinders", "reward"):
+                assert torch.equal(views[key], ref[key]), (t, k, key)
+            assert torch.equal(done, rdone)
+    for e in engs + twins:
+        e.close()
