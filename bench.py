@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -239,10 +239,26 @@ def run_gpu_arm(args):
     if rollout_graph is not None:
         rollout_graph.replay()
     barrier()
-    launches0 = sum(e.launches for e in engines)
     sampler = ClockSampler(local)
-    if rank == 0:
+    timed_only_early = os.environ.get("HS_BENCH_TIMED_ONLY", "0") == "1"
+
+    def same_load(seconds):
+        # the timed region is ~15 ms, shorter than nvidia-smi's sampling period: keep the GPU on the identical work
+        # (same graphs, same batches) around it so that the clock samples are taken under exactly this load
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            if rollout_graph is not None:
+                rollout_graph.replay()
+            else:
+                for j in range(ROLLOUT):
+                    tick(j)
+            torch.cuda.synchronize()
+    if rank == 0 and not timed_only_early:
         sampler.start()
+    if not timed_only_early:
+        same_load(0.6)                      # nvidia-smi needs ~0.2 s to start; also serves as extra warm-up
+    barrier()
+    launches0 = sum(e.launches for e in engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed region
@@ -264,8 +280,14 @@ def run_gpu_arm(args):
     torch.cuda.profiler.stop()
     wall = time.perf_counter() - w0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = sum(e.launches for e in engines) - launches0
+    launches_timed = sum(e.launches for e in engines) - launches0
+    if not timed_only_early:
+        same_load(0.3)
+    clocks = sampler.stop() if (rank == 0 and not timed_only_early) else None
+    if clocks is not None:
+        clocks["window"] = ("~0.9 s of continuous identical load (same graphs, same batches) around the timed region, "
+                            "which is shorter than nvidia-smi's 20 ms sampling period")
+    launches = launches_timed
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
