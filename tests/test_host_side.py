@@ -151,3 +151,38 @@ def test_farthest_point_sampling_and_archive():
     gb.insert(tasks[:4]); gb.insert_weights(torch.tensor([1.0, 0.0, 1.0, 0.0])); gb.insert_weights(torch.tensor([1.0, 1.0, 0.0, 0.0]))
     gb.update()
     assert gb._weight_buffer.reshape(-1).tolist() == [1.0, 0.5, 0.5, 0.0] and gb._state_buffer.shape == (4, 27)
+
+
+def test_rollout_and_policy_host_logic(built_lib):
+    """Host-side pieces of the rollout rows that need no GPU: stride analysis of compute_gae's inputs,
+    parameter-name matching and shapes of the policy wrapper, blob sizing, and the loud failure without a CUDA device."""
+    import torch
+    import mupe_b200
+    from mupe_b200 import _lib, policy, rollout
+    # [N, T, k, 1] in the reference's env-major layout and as an [N, T] view of time-major storage
+    x = torch.zeros(5, 7, 3, 1)
+    assert rollout._col_view(x, "x")[1:] == (3, 21, 3)
+    xt = torch.zeros(7, 5, 3, 1).transpose(0, 1)
+    assert rollout._col_view(xt, "x")[1:] == (3, 3, 15)
+    with pytest.raises(_lib.HsError):
+        rollout._col_view(torch.zeros(5, 7, 6)[..., ::2], "x")          # trailing dims must be contiguous
+    with pytest.raises(_lib.HsError):
+        rollout.compute_gae(x, torch.zeros(5, 7, 1, dtype=torch.bool), x, torch.zeros(5, 3, 1))     # no CPU path
+    # parameters under the reference's names, also with the prefixes make_functional / named_parameters give them
+    p = policy.init_params(35, 2, 3, 4, True, device="cpu")
+    assert p["split_embed.embed.state_self.weight"].shape == (128, 35) and p["attn.in_proj_weight"].shape == (384, 128)
+    assert p["head.weight"].shape == (4, 128) and p["log_std"].shape == (4,)
+    pref = {("module", "encoder") + tuple(k.split(".")): v for k, v in p.items() if not k.startswith(("head", "log_std"))}
+    pref.update({"module.act_dist.fc_mean.weight": p["head.weight"], "module.act_dist.fc_mean.bias": p["head.bias"],
+                 "module.act_dist.log_std": p["log_std"]})
+    assert policy._find(pref, "attn.out_proj.weight") is p["attn.out_proj.weight"]
+    assert policy._find(pref, policy._HEAD["head_w"]) is p["head.weight"]
+    assert policy._find(pref, ("log_std",)) is p["log_std"]
+    assert policy._find(p, "split_embed.embed.nothing.weight", required=False) is None
+    with pytest.raises(_lib.HsError):
+        policy.FusedPolicy(p, 2, 3, device="cpu")                        # no CPU path either
+    # blob = fp32 part (1 KB aligned) + five tf32 hi/lo weight images; embedding K padded to a multiple of 8
+    n35, n20 = _lib.lib.hs_policy_blob_floats(35), _lib.lib.hs_policy_blob_floats(20)
+    img = lambda k0: 2 * (k0 // 4) * 2048 + 4 * 2 * 65536
+    assert n35 > n20 > 0 and (n35 - n20) * 4 >= img(40) - img(24)
+    assert _lib.lib.hs_policy_blob_floats(0) == 0 and _lib.lib.hs_policy_blob_floats(129) == 0
