@@ -186,3 +186,21 @@ def test_rollout_and_policy_host_logic(built_lib):
     img = lambda k0: 2 * (k0 // 4) * 2048 + 4 * 2 * 65536
     assert n35 > n20 > 0 and (n35 - n20) * 4 >= img(40) - img(24)
     assert _lib.lib.hs_policy_blob_floats(0) == 0 and _lib.lib.hs_policy_blob_floats(129) == 0
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on stdout with
+    the contract's keys; it times the oracle port on the host cores and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("env-steps/sec") and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
