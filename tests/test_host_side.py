@@ -204,3 +204,15 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["metric"].startswith("env-steps/sec") and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_header_is_plain_c():
+    """include/hs_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(REPO, "include", "hs_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
