@@ -243,7 +243,7 @@ int hs_step_host_io_async(hs_handle* h, const hs_host_io* io, int action_is_raw,
                           const hs_tp_weights* w, float* staging_dev, void* stream);
 int hs_host_io_wait(hs_handle* h, void* stream);
 
-/* ---- state views (what omni_drones/views/* get/set did) ------------------------------ */
+/* ---- state views (what the get/set methods of omni_drones/views did) ------------------- */
 enum {
     HS_FIELD_DRONE_POS = 0,   /* [E,A,3] */
     HS_FIELD_DRONE_ROT,       /* [E,A,4] wxyz */
