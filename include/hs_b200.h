@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define HS_ABI_VERSION 1
+#define HS_ABI_VERSION 2
 #define HS_NUM_STATS 24
 #define HS_MAX_AGENTS 3
 #define HS_MAX_CYLINDERS 8
@@ -148,6 +148,11 @@ typedef struct hs_buffers {
     float* target_rate;         /* [E,A,3]  'target_rate' */
     float* action_error;        /* [E,A]    ("stats","action_error_order1") */
     const float* v_prey;        /* device scalar: current evader speed (curriculum, hideandseek.py:1012-1015) */
+    const float* smoothness_coef; /* device scalar or NULL (= cfg.smoothness_coef): min(max_smoothness_coef,
+                                   init_smoothness_coef + smooth_lr * update_epoch), recomputed by the host whenever
+                                   `update_epoch` changes (hideandseek.py:988-991; scripts/train_deploy.py writes
+                                   base_env.update_epoch every iteration).  Read by every tick, so captured CUDA
+                                   graphs follow the curriculum without re-capture. */
 } hs_buffers;
 
 typedef struct hs_handle hs_handle;
@@ -278,8 +283,13 @@ int64_t hs_launch_count(const hs_handle* h);
  * launch, cached per set of pointers (host buffers, bound outputs, weights); 0 = plain stream calls.
  * HS_OPT_HOST_IO_ZERO_COPY_ACTION: 1 (default) = a page-locked io->action is read in place by the tick
  * kernel (UVA), no H2D copy; 0 = always copy into the staging buffer first.
- * HS_OPT_FUSED_TICK: 1 (default) = hs_step_fused may use the one-launch kernel; 0 = always two launches. */
-enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4 };
+ * HS_OPT_FUSED_TICK: 1 (default) = hs_step_fused may use the one-launch kernel; 0 = always two launches.
+ * HS_OPT_EXACT_MATH: 0 (default) = the product tick kernel (rcp/sqrt/ex2.approx, FMA contraction); 1 = the same
+ * source built with IEEE round-to-nearest division / square root / exp, no FMA contraction, and the reference's
+ * operation order in the ill-conditioned stages (csrc/hs_tick_exact.cu).  About 2x slower; exists so that parity
+ * tests can separate rounding amplified by the task's discontinuities from defects. */
+enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4,
+       HS_OPT_EXACT_MATH = 5 };
 int hs_set_option(hs_handle* h, int option, int value);
 
 /* ---- device-side reset sampler --------------------------- */

@@ -10,12 +10,13 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
 
-HS_ABI_VERSION = 1
+HS_ABI_VERSION = 2
 HS_NUM_STATS = 24
 HS_OPT_PREDICTOR_VARIANT = 1
 HS_OPT_HOST_IO_GRAPH = 2
 HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3
 HS_OPT_FUSED_TICK = 4
+HS_OPT_EXACT_MATH = 5
 
 # field ids, include/hs_b200.h
 (FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,
@@ -61,7 +62,7 @@ class hs_config(C.Structure):
 _BUF_FIELDS = [
     "arena", "stats", "state_self", "state_others", "obs_cylinders", "state_drones", "tp_input",
     "tp_input_prev", "tp_groundtruth", "tp_done", "reward", "done", "truncated", "drone_state",
-    "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey",
+    "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey", "smoothness_coef",
 ]
 
 

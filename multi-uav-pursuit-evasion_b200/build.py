@@ -7,13 +7,17 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "hs_kernels.cu")
+# the tick kernel once more with IEEE arithmetic (HS_OPT_EXACT_MATH, csrc/hs_tick_exact.cu): no FMA contraction
+SRC_EXACT = os.path.join(PKG_DIR, "csrc", "hs_tick_exact.cu")
 LIB = os.path.join(PKG_DIR, "libhs_b200.so")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
+EXACT_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"]
 
 
 def nvcc_path():
@@ -36,16 +40,26 @@ def needs_build():
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags, "-I", os.path.join(REPO, "include"), "-o", LIB, SRC]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    inc = ["-I", os.path.join(REPO, "include")]
+    objs = [os.path.join(OBJ_DIR, "hs_kernels.o"), os.path.join(OBJ_DIR, "hs_tick_exact.o")]
+    cmds = [[nvcc_path(), *NVCC_FLAGS, *extra_flags, *inc, "-c", "-o", objs[0], SRC],
+            [nvcc_path(), *NVCC_FLAGS, *EXACT_FLAGS, *extra_flags, *inc, "-c", "-o", objs[1], SRC_EXACT]]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        for cmd in cmds:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+            print(" ".join(cmd))
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for cmd in cmds]   # in parallel
+    outs = [p.communicate()[0] for p in procs]
+    if any(p.returncode != 0 for p in procs):
+        raise RuntimeError("nvcc failed:\n" + "\n".join(outs))
+    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs]
+    r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stdout + r.stderr)
+        print("\n".join(outs) + r.stdout + r.stderr)
     return LIB
 
 

@@ -41,10 +41,29 @@ __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+// Division / square root / exp: the product build uses the SFU approximations (rcp/sqrt/ex2.approx, <= 2 ulp; the
+// tick is instruction-bound, profiles/).  HS_EXACT_MATH=1 (csrc/hs_tick_exact.cu, compiled with -fmad=false; selected by
+// HS_OPT_EXACT_MATH) swaps in IEEE round-to-nearest operations and follows the reference's operation order in the
+// ill-conditioned stages, so that parity tests can show that every element outside the tolerance of the fast build
+// sits on a discontinuity / cancellation and not on a defect.
+#ifndef HS_EXACT_MATH
+#define HS_EXACT_MATH 0
+#endif
+#if HS_EXACT_MATH
+__device__ __forceinline__ float frcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float fsqrt(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)); }
+__device__ __forceinline__ float fexp(float x) { return expf(x); }
+__device__ __forceinline__ float frsqrt(float x) { return __frcp_rn(__fsqrt_rn(x)); }
+#else
 __device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
 __device__ __forceinline__ V3 operator/(V3 a, float s) { const float r = frcp(s); return mk(a.x * r, a.y * r, a.z * r); }
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float frsqrt(float x) { return rsqrtf(x); }
+#endif
 __device__ __forceinline__ V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ float norm3(V3 a) { return fsqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
@@ -184,12 +203,25 @@ __device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float 
                                             const float (&cy)[CT], const float (&cz)[CT],
                                             int C, float size) {
     const float ddx = p.x - t.x, ddy = p.y - t.y;
-    // dist/(seg+eps) <= size  and  0 <= num/(den+eps) <= 1  with the (positive) denominators
-    // multiplied out: no division per cylinder; underground (inactive) cylinders are skipped
-    const float seg_sz = (fsqrt(ddx * ddx + ddy * ddy) + 1e-5f) * size;
     const float dx = t.x - p.x, dy = t.y - p.y;
     const float den = (dx * dx + dy * dy) + 1e-5f;
     bool blocked = false;
+#if HS_EXACT_MATH
+    // the reference's own form: |cross| / (|seg| + 1e-5) <= size  and  0 <= num / (den + 1e-5) <= 1
+    const float seg1 = __fsqrt_rn(ddx * ddx + ddy * ddy) + 1e-5f;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        if (c < C && cz[c] > 0.0f) {
+            const float ccx = cx[c] - t.x, ccy = cy[c] - t.y;
+            const float dl = __fdiv_rn(fabsf(ddx * ccy - ddy * ccx), seg1);
+            const float tt = __fdiv_rn((cx[c] - p.x) * dx + (cy[c] - p.y) * dy, den);
+            blocked = blocked || ((dl <= size) && (tt >= 0.0f) && (tt <= 1.0f));
+        }
+    }
+#else
+    // dist/(seg+eps) <= size  and  0 <= num/(den+eps) <= 1  with the (positive) denominators
+    // multiplied out: no division per cylinder; underground (inactive) cylinders are skipped
+    const float seg_sz = (fsqrt(ddx * ddx + ddy * ddy) + 1e-5f) * size;
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
         if (c < C && cz[c] > 0.0f) {
@@ -199,6 +231,7 @@ __device__ __forceinline__ bool los_blocked(const V3 p, const V3 t, const float 
             blocked = blocked || ((cr <= seg_sz) && (num >= 0.0f) && (num <= den));
         }
     }
+#endif
     return blocked;
 }
 

@@ -36,6 +36,7 @@
 #endif
 
 #include "hs_common.cuh"
+#include "hs_stages.cuh"
 #include "hs_tick.cuh"
 #include "hs_predictor_ffma.cuh"
 #include "hs_predictor_mma.cuh"
@@ -45,6 +46,10 @@
 #include "hs_rollout.cuh"
 #include "hs_policy.cuh"
 #include "hs_policy_tc.cuh"
+
+// the tick kernel built with IEEE arithmetic (csrc/hs_tick_exact.cu, HS_OPT_EXACT_MATH)
+cudaError_t hs_launch_tick_exact(const void* kparams, size_t bytes, int num_agents, int reset, int small_c, unsigned grid,
+                                 unsigned block, cudaStream_t s);
 
 // =========================================================================================
 // C ABI
@@ -78,6 +83,7 @@ struct hs_handle {
     int io_fused = 0;            // hs_step_host_io: two kernels + overlapped copy (0) or the one-launch kernel (1); see DESIGN.md
     int io_graph_mode = 1;       // HS_OPT_HOST_IO_GRAPH: 1 = graph launch (default), 0 = stream API calls
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
+    int exact_math = 0;          // HS_OPT_EXACT_MATH: the tick runs the IEEE-arithmetic build of hs_tick_kernel (parity evidence)
 };
 
 static thread_local char g_err[512] = "";
@@ -97,6 +103,8 @@ static cudaError_t launch_tick(const hs_handle* h, const KParams& P, cudaStream_
     const int wpb = h->block / 32;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
     const bool small_c = h->cfg.num_cylinders <= 5;      // compile-time cylinder capacity 5 or 8
+    if (h->exact_math)
+        return hs_launch_tick_exact(&P, sizeof(P), h->cfg.num_agents, RESET ? 1 : 0, small_c ? 1 : 0, grid, (unsigned)h->block, s);
     switch (h->cfg.num_agents) {
         case 1: if (small_c) hs_tick_kernel<1, RESET, 5><<<grid, h->block, 0, s>>>(P); else hs_tick_kernel<1, RESET, CMAX><<<grid, h->block, 0, s>>>(P); break;
         case 2: if (small_c) hs_tick_kernel<2, RESET, 5><<<grid, h->block, 0, s>>>(P); else hs_tick_kernel<2, RESET, CMAX><<<grid, h->block, 0, s>>>(P); break;
@@ -355,7 +363,7 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_fused: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_fused: config has use_tp_net == 0 (use hs_step_pre)%s");
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
+    const bool one_launch = h->fused_tick && !h->exact_math && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
                             tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
     if (!one_launch) {
         const int rc = hs_step_pre(h, action, action_is_raw, reset_pid, stream);
@@ -778,8 +786,8 @@ static int host_io_enqueue(hs_handle* h, const hs_host_io* io, int action_is_raw
     // one-launch tick + predictor when the batch qualifies: nothing is complete before that kernel ends, so the
     // whole observation follows it in one copy (the side-branch overlap below is for the two-kernel sequence)
     const int64_t tiles32 = ((int64_t)c.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = c.use_tp_net && h->fused_tick && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
-                            tp_fused_smem_bytes(c) <= HS_MAX_DYN_SMEM && h->io_fused;
+    const bool one_launch = c.use_tp_net && h->fused_tick && !h->exact_math && (h->tp_variant < 0 || h->tp_variant == 5) &&
+                            tiles32 <= h->num_sms && tp_fused_smem_bytes(c) <= HS_MAX_DYN_SMEM && h->io_fused;
     int rc = one_launch ? hs_step_fused(h, action_dev, action_is_raw, reset_pid, w, nullptr, stream)
                         : hs_step_pre(h, action_dev, action_is_raw, reset_pid, stream);
     if (rc != HS_OK) return rc;
@@ -960,6 +968,11 @@ int hs_set_option(hs_handle* h, int option, int value) {
         case HS_OPT_HOST_IO_GRAPH:
             if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_GRAPH must be 0 or 1%s");
             h->io_graph_mode = value;
+            return HS_OK;
+        case HS_OPT_EXACT_MATH:
+            if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_EXACT_MATH must be 0 or 1%s");
+            h->exact_math = value;
+            for (auto& g : h->io_graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             return HS_OK;
         default:
             return set_err(HS_ERR_INVALID, "unknown option%s");

@@ -3,6 +3,7 @@
 // namespace so that nvcc can inline across the pieces; -lineinfo still maps SASS to this file).
 #pragma once
 #include "hs_common.cuh"
+#include "hs_stages.cuh"
 
 namespace {
 
@@ -154,80 +155,27 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
         float cmd[4] = {0, 0, 0, 0};
         if (is_drone) {
             const int64_t row = e * A + slot;
-            const float4 act = act4;
             if (P.action_is_raw) {
-                using namespace ex;
-                const float4 prev = prev4;
-                const float a0 = tanhf(act.x), a1 = tanhf(act.y), a3 = tanhf(act.w);
-                float a2 = tanhf(act.z);
-                const float thrust = clampf(mul(add(a3, 1.0f), 0.5f), 0.0f, c.max_thrust_ratio);
-                if (c.fixed_yaw) a2 = 0.0f;
-                const float d0 = sub(a0, prev.x), d1 = sub(a1, prev.y), d2 = sub(a2, prev.z), d3 = sub(thrust, prev.w);
-                action_err = __fsqrt_rn(add(add(add(mul(d0, d0), mul(d1, d1)), mul(d2, d2)), mul(d3, d3)));
-                if (valid) *(reinterpret_cast<float4*>(P.b.prev_action) + row) = make_float4(a0, a1, a2, thrust);
-                const V3 trate = mk(mul(mul(a0, 180.0f), c.target_clip), mul(mul(a1, 180.0f), c.target_clip),
-                                    mul(mul(a2, 180.0f), c.target_clip));
-                const float tthrust = mul(thrust, 65536.0f);
-                if (pid_reset) { integ = mk(0, 0, 0); last = mk(0, 0, 0); }
-                const V3 br0 = qrot_inv_exact(q, av);
-                const float pi_f = 3.14159265358979323846f;
-                const V3 br = mk(div(mul(br0.x, 180.0f), pi_f), div(mul(br0.y, 180.0f), pi_f), div(mul(br0.z, 180.0f), pi_f));
-                float o[3];
-                const float errv[3] = {sub(trate.x, br.x), sub(trate.y, br.y), sub(trate.z, br.z)};
-                const float brv[3] = {br.x, br.y, br.z};
-                const float lastv[3] = {last.x, last.y, last.z};
-                float integv[3] = {integ.x, integ.y, integ.z};
+                CtbrOut o;
+                stage_ctbr_pid(c, act4, prev4, pid_reset, q, av, integ, last, o);
+                action_err = o.action_err;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float outP = mul(errv[k], c.pid_kp[k]);
-                    float deriv = div(-sub(brv[k], lastv[k]), dt);
-                    if (isnan(deriv)) deriv = 0.0f;
-                    const float outD = mul(deriv, c.pid_kd[k]);
-                    integv[k] = clampf(add(integv[k], mul(errv[k], dt)), -c.pid_ilimit[k], c.pid_ilimit[k]);
-                    const float outI = mul(integv[k], c.pid_ki[k]);
-                    float out = add(add(outP, outD), outI);
-                    if (isnan(out)) out = 0.0f;
-                    o[k] = clampf(out, -c.pid_out_limit, c.pid_out_limit);
-                }
-                integ = mk(integv[0], integv[1], integv[2]);
-                last = br;
-                const float r = o[0] * 0.5f, pp = o[1] * 0.5f, y = o[2];
-                const float m[4] = {add(sub(add(tthrust, r), pp), y), sub(add(add(tthrust, r), pp), y),
-                                    add(add(sub(tthrust, r), pp), y), sub(sub(sub(tthrust, r), pp), y)};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float v = sub(mul(mul(m[k], 1.0f / 65536.0f), 2.0f), c.max_thrust_ratio);
-                    if (isnan(v)) v = 0.0f;                       // torch.nan_to_num_(cmds, 0.)
-                    else if (isinf(v)) v = v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-                    cmd[k] = v;
-                }
+                for (int k = 0; k < 4; ++k) cmd[k] = o.cmd[k];
                 if (valid) {
+                    *(reinterpret_cast<float4*>(P.b.prev_action) + row) = o.prev_new;
                     *(reinterpret_cast<float4*>(P.b.rotor_cmds) + row) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
-                    *(reinterpret_cast<float4*>(P.b.ctbr) + row) = make_float4(r, pp, y, tthrust);
-                    P.b.target_rate[row * 3 + 0] = trate.x;
-                    P.b.target_rate[row * 3 + 1] = trate.y;
-                    P.b.target_rate[row * 3 + 2] = trate.z;
+                    *(reinterpret_cast<float4*>(P.b.ctbr) + row) = o.ctbr;
+                    P.b.target_rate[row * 3 + 0] = o.trate.x;
+                    P.b.target_rate[row * 3 + 1] = o.trate.y;
+                    P.b.target_rate[row * 3 + 2] = o.trate.z;
                     P.b.action_error[row] = action_err;
                 }
             } else {
-                cmd[0] = act.x; cmd[1] = act.y; cmd[2] = act.z; cmd[3] = act.w;
+                cmd[0] = act4.x; cmd[1] = act4.y; cmd[2] = act4.z; cmd[3] = act4.w;
                 action_err = P.b.action_error[row];
             }
             // ---- rotor model, rotor_group.py:55-71
-            float dsq = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float target = fsqrt(clampf((cmd[k] + 1.0f) / 2.0f, 0.0f, 1.0f));
-                const float nt = thr[k] + c.rotor_alpha * (target - thr[k]);
-                const float dth = nt - thr[k];
-                dsq = (k == 0) ? dth * dth : dsq + dth * dth;
-                thr[k] = nt;
-                const float t = clampf(nt * nt + 0.0f, 0.0f, 1.0f);
-                T[k] = t * c.kf;
-                const float mom = (t * c.km) * (-c.rotor_dirs[k]);
-                yaw_torque = (k == 0) ? mom : yaw_torque + mom;
-            }
-            throttle_diff = fsqrt(dsq);
+            stage_rotor(c, cmd, thr, T, yaw_torque, throttle_diff);
         }
         // ---- downwash all-pairs, multirotor.py:488-494, 724-753
         const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
@@ -237,114 +185,21 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
         for (int j = 0; j < A; ++j) {
             const V3 Fj = gshfl3(Fw, gbase + j);
             const V3 pj = gshfl3(p, gbase + j);
-            if (is_drone && j != slot) {
-                const V3 d = Fj / (norm3(Fj) + 1e-6f);
-                const V3 rel = pj - p;
-                const float zd = dot3(rel, d);
-                const float rr = norm3(rel - d * zd);
-                const float z = zd < 0.0f ? 0.0f : zd;
-                const float qq = fdiv(c.downwash_kr * rr, z);
-                const float den = 1.0f + c.downwash_kz * z;
-                const float v = fdiv(__expf(-0.5f * (qq * qq)), den * den);
-                dw = dw + neg(Fj) * v;
-            }
+            if (is_drone && j != slot) dw = dw + downwash_term(c, Fj, pj, p);
         }
         ext = dw + lv * c.drag_coef_times_mass;
 
         // ---- evader, hideandseek.py:1067-1141 + 737-744
         V3 fp = mk(0.f, 0.f, 0.f);
-        if (is_drone) {
-            const V3 rel = p - tp;
-            const float dist = norm3(rel);
-            const bool blocked = los_blocked(p, tp, cx, cy, cz, C, c.cylinder_size);
-            const float active = ((dist < c.target_detect_radius) && !blocked) ? 1.0f : 0.0f;
-            const float inv_d = frcp(dist + 1e-5f);
-            fp = (neg(rel) * (inv_d * inv_d)) * active;
-        }
+        if (is_drone) fp = evader_pursuer_term(c, p, tp, los_blocked(p, tp, cx, cy, cz, C, c.cylinder_size));
         V3 force = gshfl3(fp, gbase);
 #pragma unroll
         for (int j = 1; j < A; ++j) force = force + gshfl3(fp, gbase + j);
-        if (is_ev) {
-            force = mk(0.f, 0.f, 0.f) + force;
-            const float rho = fsqrt(tp.x * tp.x + tp.y * tp.y);
-            const float inv_rho = frcp(rho + 1e-5f);
-            const float inx = -tp.x * inv_rho, iny = -tp.y * inv_rho;
-            out_of_arena = (tp.x * tp.x + tp.y * tp.y) > c.arena_size_sq;
-            const float o = out_of_arena ? 1.0f : 0.0f, no = out_of_arena ? 0.0f : 1.0f;
-            const float wall = frcp((c.arena_size - rho) + 1e-5f);
-            V3 fr;
-            fr.x = (o * inx) * 1e5f + (no * inx) * wall;
-            fr.y = (o * iny) * 1e5f + (no * iny) * wall;
-            const bool hi = tp.z > c.max_height;
-            const float hz = c.max_height - tp.z;
-            fr.z = hi ? -1e5f : fdiv(-hz, hz * hz + 1e-5f);
-            const bool lo = tp.z < 0.0f;
-            const float lz = 0.0f - tp.z;
-            fr.z = fr.z + (lo ? 1e5f : fdiv(-lz, lz * lz + 1e-5f));
-            force = force + fr;
-            float fcx = 0.f, fcy = 0.f;
-#pragma unroll
-            for (int k = 0; k < CT; ++k) {
-                if (k < C && !(cz[k] < 0.0f)) {
-                    const float tx = tp.x - cx[k], ty = tp.y - cy[k];
-                    const float dxy = fsqrt(tx * tx + ty * ty);
-                    if (dxy < c.target_detect_radius) {
-                        const float sc = frcp(dxy + 1e-5f) * frcp((dxy - c.cylinder_size) + 1e-5f);
-                        fcx = fcx + tx * sc;
-                        fcy = fcy + ty * sc;
-                    }
-                }
-            }
-            force = force + mk(fcx, fcy, 0.f);
-            const float vp = v_prey;
-            tv = mk(fdiv(vp * force.x, fabsf(force.x) + 1e-5f), fdiv(vp * force.y, fabsf(force.y) + 1e-5f),
-                    fdiv(vp * force.z, fabsf(force.z) + 1e-5f));
-        }
+        if (is_ev) tv = evader_velocity(c, force, tp, cx, cy, cz, C, v_prey, out_of_arena);
     }
 
     // ---- rigid-body integration (PhysX stand-in; oracle/hs_oracle.py rigid_body_step) ----
-    if (is_drone) {
-        V3 force = mk(0.f, 0.f, 0.f), tau = mk(0.f, 0.f, 0.f);
-        if (!RESET) {
-            const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
-            force = qrot<false>(q, mk(0.f, 0.f, total_thrust));
-            tau.x = ((c.rotor_y[0] * T[0] + c.rotor_y[1] * T[1]) + c.rotor_y[2] * T[2]) + c.rotor_y[3] * T[3];
-            tau.y = (((-c.rotor_x[0]) * T[0] + (-c.rotor_x[1]) * T[1]) + (-c.rotor_x[2]) * T[2]) + (-c.rotor_x[3]) * T[3];
-            tau.z = yaw_torque;
-            force = force + ext;
-        }
-        V3 acc = force / c.total_mass;
-        acc.z = acc.z - c.gravity;
-        V3 v = lv + acc * dt;
-        const V3 I = mk(c.inertia[0], c.inertia[1], c.inertia[2]);
-        V3 wb = qrot<true>(q, av);
-        const V3 gyro = cross3(wb, mk(I.x * wb.x, I.y * wb.y, I.z * wb.z));
-        const V3 tg = tau - gyro;
-        wb = wb + mk(tg.x * c.inv_inertia[0], tg.y * c.inv_inertia[1], tg.z * c.inv_inertia[2]) * dt;
-        V3 w = qrot<false>(q, wb);
-        v = v * c.lin_damp_factor;
-        w = w * c.ang_damp_factor;
-        const float vn = norm3(v);
-        if (vn > c.max_linear_velocity) v = v * fdiv(c.vmax_clamped, vn);
-        float wn = norm3(w);
-        if (wn > c.max_angular_velocity) w = w * fdiv(c.max_angular_velocity, wn);
-        p = p + v * dt;
-        wn = norm3(w);
-        const float half = (0.5f * dt) * wn;
-        const bool small = wn < 1e-6f;
-        float sh, ch;
-        sincosf(half, &sh, &ch);
-        const float kk = small ? (0.5f * dt) : fdiv(sh, fmaxf(wn, 1e-6f));
-        Q4 dq; dq.w = small ? 1.0f : ch; dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk;
-        Q4 qn = qmul(dq, q);
-        const float qinv = rsqrtf(((qn.w * qn.w + qn.x * qn.x) + qn.y * qn.y) + qn.z * qn.z);
-        q.w = qn.w * qinv; q.x = qn.x * qinv; q.y = qn.y * qinv; q.z = qn.z * qinv;
-        if (c.ground_clamp && p.z < c.ground_z) {
-            p.z = c.ground_z;
-            if (v.z < 0.0f) v.z = 0.0f;
-        }
-        lv = v; av = w;
-    }
+    if (is_drone) stage_integrate<!RESET>(c, p, q, lv, av, T, yaw_torque, ext);
     if (is_ev) tp = tp + tv * dt;
     // everyone needs the evader's new position/velocity
     tp = gshfl3(tp, gbase + A);
@@ -411,40 +266,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     float hit_cyl = 0.f;
     if (K > 0) {
         float* s = st.begin();
-        if (is_drone) {
-            float key[CT];
-#pragma unroll
-            for (int k = 0; k < CT; ++k)
-                key[k] = (k < C) ? (norm3(mk(p.x - cx[k], p.y - cy[k], p.z - cz[k])) - c.cylinder_size) : INFINITY;
-            unsigned taken = 0u;
-            float* r = s + row_l * (K * 5);
-#pragma unroll
-            for (int n = 0; n < KMAX; ++n) {
-                if (n < K) {
-                    int best = 0; float bk = INFINITY; bool found = false;
-#pragma unroll
-                    for (int k = 0; k < CT; ++k) {
-                        const bool cand = (k < C) && !((taken >> k) & 1u);
-                        if (cand && (!found || key[k] < bk)) { best = k; bk = key[k]; found = true; }
-                    }
-                    taken |= 1u << best;
-                    float bx = 0.f, by = 0.f, bz = 0.f;
-#pragma unroll
-                    for (int k = 0; k < CT; ++k) if (k == best) { bx = cx[k]; by = cy[k]; bz = cz[k]; }
-                    const bool inactive = bz < 0.0f;
-                    const float rx = p.x - bx, ry = p.y - by, rz = p.z - bz;
-                    const float mv = c.mask_value;
-                    r[n * 5 + 0] = inactive ? mv : rx;
-                    r[n * 5 + 1] = inactive ? mv : ry;
-                    r[n * 5 + 2] = inactive ? mv : rz;
-                    r[n * 5 + 3] = inactive ? mv : c.max_height;
-                    r[n * 5 + 4] = inactive ? mv : c.cylinder_size;
-                    const float dxy = fsqrt(rx * rx + ry * ry);
-                    const float hit = ((dxy - c.cylinder_size) < c.collision_radius) ? 1.0f : 0.0f;
-                    hit_cyl = hit_cyl + (inactive ? 0.0f : hit);
-                }
-            }
-        }
+        if (is_drone) stage_knearest(c, p, cx, cy, cz, C, K, s + row_l * (K * 5), hit_cyl);
         st.flush(P.b.obs_cylinders + tile_row0 * (K * 5), nenv * A * K * 5, full_tile);
     }
     // target visibility
@@ -494,9 +316,8 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
             }
         }
         if (valid && is_ev) {
-            const float inv_ha = frcp(c.half_arena);
-            P.b.tp_groundtruth[e * 3 + 0] = tp.x * inv_ha;
-            P.b.tp_groundtruth[e * 3 + 1] = tp.y * inv_ha;
+            P.b.tp_groundtruth[e * 3 + 0] = fdiv(tp.x, c.half_arena);
+            P.b.tp_groundtruth[e * 3 + 1] = fdiv(tp.y, c.half_arena);
             P.b.tp_groundtruth[e * 3 + 2] = fdiv(tp.z, c.max_height) * 2.0f - 1.0f;
             P.b.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;
             *EROW(E_BDETECT) = bdetect ? 1.0f : 0.0f;
@@ -522,17 +343,12 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     // ---- reward / done / stats, hideandseek.py:919-1065 --------------------------------
     float r_dist = 0.f, r_speed = 0.f, r_coll = 0.f, r_smooth = 0.f, hit_wall = 0.f;
     bool seen_capture = false;
+    // device scalar when bound: follows update_epoch without re-capturing graphs (hideandseek.py:988-991)
+    const float sm_coef = (P.b.smoothness_coef != nullptr) ? __ldg(P.b.smoothness_coef) : c.smoothness_coef;
     if (is_drone) {
-        const float dist = norm3(tp - p);
-        r_dist = (-c.dist_reward_coef * dist) * ((dist > c.catch_radius) ? 1.0f : 0.0f);
-        seen_capture = (dist < c.catch_radius) && !blocked;
-        r_speed = -c.speed_coef * ((norm3(lv) > c.v_drone) ? 1.0f : 0.0f);
-        r_coll = -c.collision_coef * hit_cyl;
-        r_coll = r_coll + (-c.collision_coef * hit_drone);
-        hit_wall = ((p.z > c.max_height) ? 1.0f : 0.0f) +
-                   (((p.x * p.x + p.y * p.y) > c.arena_size_sq) ? 1.0f : 0.0f);
-        r_coll = r_coll + (-c.collision_coef * hit_wall);
-        r_smooth = c.smoothness_gated ? 0.0f : c.smoothness_coef * __expf(-action_err);
+        const RewardTerms rt = stage_reward_terms(c, p, lv, tp, blocked, hit_cyl, hit_drone, action_err, sm_coef);
+        r_dist = rt.r_dist; r_speed = rt.r_speed; r_coll = rt.r_coll; r_smooth = rt.r_smooth; hit_wall = rt.hit_wall;
+        seen_capture = rt.seen_capture;
     }
     const bool any_capture = (__ballot_sync(FULL, seen_capture) & gmask) != 0u;
     const bool all_blocked = (__ballot_sync(FULL, blocked) & gmask) == gmask;
@@ -558,51 +374,20 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
         s = fmaxf(s, __shfl_xor_sync(FULL, s, 2));
         return s;
     };
-    const float m_ae = gmean(action_err), m_dist = gmean(r_dist), m_detect = gmean(r_detect),
-                m_catch = gmean(r_catch), m_speed = gmean(r_speed), m_hcyl = gmean(hit_cyl),
-                m_hdrone = gmean(hit_drone), m_hwall = gmean(hit_wall), m_coll = gmean(r_coll),
-                m_smooth = gmean(r_smooth), m_tdiff = gmean(throttle_diff), m_reward = gmean(reward),
-                x_tdiff = gmax(throttle_diff);
+    EnvTick et;
+    et.m_ae = gmean(action_err); et.m_dist = gmean(r_dist); et.m_detect = gmean(r_detect); et.m_catch = gmean(r_catch);
+    et.m_speed = gmean(r_speed); et.m_hcyl = gmean(hit_cyl); et.m_hdrone = gmean(hit_drone); et.m_hwall = gmean(hit_wall);
+    et.m_coll = gmean(r_coll); et.m_smooth = gmean(r_smooth); et.m_tdiff = gmean(throttle_diff); et.m_reward = gmean(reward);
+    et.x_tdiff = gmax(throttle_diff);
+    et.r_catch = r_catch; et.bdetect = bdetect; et.all_blocked = all_blocked; et.any_coll = any_coll; et.out_of_arena = out_of_arena;
 
     if (valid && is_ev) {
-        const bool done = progress >= (float)c.max_episode_length;
-        P.b.done[e] = done ? 1 : 0;
-        const float inv_len = done ? frcp(progress) : 1.0f;
+        P.b.done[e] = (progress >= (float)c.max_episode_length) ? 1 : 0;
         float* S = P.b.stats + e;
         const int64_t Es = E;
         cp_async_wait_all();
         const float* SO = stat_tile + (lane >> 2) * HS_NUM_STATS;     // values prefetched at kernel entry
-#define ST(k) S[(int64_t)(k) * Es]
-#define OLD(k) SO[k]
-        // accumulators that are divided by the episode length on the done tick
-        ST(HS_STAT_ACTION_ERROR_MEAN) = (OLD(HS_STAT_ACTION_ERROR_MEAN) + m_ae) * inv_len;
-        ST(HS_STAT_ACTION_ERROR_MAX) = fmaxf(OLD(HS_STAT_ACTION_ERROR_MAX), m_ae);
-        ST(HS_STAT_OUT_OF_ARENA) = ((OLD(HS_STAT_OUT_OF_ARENA) != 0.0f) || out_of_arena) ? 1.0f : 0.0f;
-        ST(HS_STAT_DISTANCE_REWARD) = (OLD(HS_STAT_DISTANCE_REWARD) + m_dist) * inv_len;
-        ST(HS_STAT_SUM_DETECT_STEP) = OLD(HS_STAT_SUM_DETECT_STEP) + 1.0f * (bdetect ? 1.0f : 0.0f);
-        ST(HS_STAT_DETECT_REWARD) = (OLD(HS_STAT_DETECT_REWARD) + m_detect) * inv_len;
-        ST(HS_STAT_BLOCKED) = OLD(HS_STAT_BLOCKED) + (all_blocked ? 1.0f : 0.0f);
-        const bool capture_flag = r_catch != 0.0f;
-        ST(HS_STAT_SUCCESS) = (capture_flag || (OLD(HS_STAT_SUCCESS) != 0.0f)) ? 1.0f : 0.0f;
-        const float step_now = (capture_flag ? 1.0f : 0.0f) * progress +
-                               (capture_flag ? 0.0f : 1.0f) * (float)c.max_episode_length;
-        ST(HS_STAT_FIRST_CAPTURE_STEP) = fminf(OLD(HS_STAT_FIRST_CAPTURE_STEP), step_now);
-        ST(HS_STAT_CATCH_REWARD) = (OLD(HS_STAT_CATCH_REWARD) + m_catch) * inv_len;
-        ST(HS_STAT_SPEED_REWARD) = (OLD(HS_STAT_SPEED_REWARD) + m_speed) * inv_len;
-        ST(HS_STAT_COLLISION_CYLINDER) = (OLD(HS_STAT_COLLISION_CYLINDER) + m_hcyl) * inv_len;
-        ST(HS_STAT_COLLISION_DRONE) = (OLD(HS_STAT_COLLISION_DRONE) + m_hdrone) * inv_len;
-        ST(HS_STAT_COLLISION) = (OLD(HS_STAT_COLLISION) + (any_coll ? 1.0f : 0.0f)) * inv_len;
-        ST(HS_STAT_COLLISION_WALL) = (OLD(HS_STAT_COLLISION_WALL) + m_hwall) * inv_len;
-        ST(HS_STAT_COLLISION_REWARD) = (OLD(HS_STAT_COLLISION_REWARD) + m_coll) * inv_len;
-        if (c.write_smoothness_coef_stat) ST(HS_STAT_SMOOTHNESS_COEF) = c.smoothness_coef;
-        ST(HS_STAT_SMOOTHNESS_REWARD) = (OLD(HS_STAT_SMOOTHNESS_REWARD) + m_smooth) * inv_len;
-        ST(HS_STAT_SMOOTHNESS_MEAN) = (OLD(HS_STAT_SMOOTHNESS_MEAN) + m_tdiff) * inv_len;
-        ST(HS_STAT_SMOOTHNESS_MAX) = fmaxf(x_tdiff, OLD(HS_STAT_SMOOTHNESS_MAX));
-        ST(HS_STAT_RETURN) = OLD(HS_STAT_RETURN) + m_reward;
-        // target_predicted_error is only ever divided (stays 0); distance_predicted_reward and
-        // distance_threshold_L are never written (hideandseek.py:1023-1025).
-#undef ST
-#undef OLD
+        stage_stats(c, et, progress, sm_coef, [&](int k) { return SO[k]; }, [&](int k, float v) { S[(int64_t)k * Es] = v; });
     }
     st.finish();
 }

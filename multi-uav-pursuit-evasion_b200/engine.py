@@ -134,6 +134,8 @@ class HsEngine:
         self.stats = torch.zeros(_lib.HS_NUM_STATS, self.E, dtype=torch.float32, device=device)
         self.prev_action = torch.zeros(self.E, self.A, 4, dtype=torch.float32, device=device)
         self.v_prey = torch.full((1,), 1.3, dtype=torch.float32, device=device)
+        # device scalar read by every tick (hs_buffers.smoothness_coef): the host refreshes it when update_epoch changes
+        self.smoothness_coef = torch.full((1,), float(cfg.smoothness_coef), dtype=torch.float32, device=device)
         self.storage: Optional[RolloutStorage] = None
         if rollout_steps:
             # rollout mode: set t = row t of the time-major rollout tensors, set T = reset scratch
@@ -166,6 +168,7 @@ class HsEngine:
             b.tp_groundtruth = _ptr(s["tp_groundtruth"])
         b.tp_done, b.done, b.truncated = _ptr(s["tp_done"]), _ptr(s["done"]), _ptr(s["truncated"])
         b.prev_action, b.v_prey = _ptr(self.prev_action), _ptr(self.v_prey)
+        b.smoothness_coef = _ptr(self.smoothness_coef)
         return b
 
     def _bind(self, i: int, prev: Optional[int] = None):
@@ -382,6 +385,11 @@ class HsEngine:
         halves (small-batch default, and the predictor half of the one-launch tick)."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_PREDICTOR_VARIANT, int(variant)), "hs_set_option")
         self._graphs = None             # captured graphs hold the old kernel
+
+    def set_exact_math(self, on: bool):
+        """HS_OPT_EXACT_MATH: run the tick with the IEEE-arithmetic build of the kernel (parity evidence; ~2x slower)."""
+        check(lib.hs_set_option(self._h, _lib.HS_OPT_EXACT_MATH, 1 if on else 0), "hs_set_option")
+        self._graphs = None
 
     # ------------------------------------------------------------------ CUDA graphs
     def capture_tick_graphs(self, tp_weights=None, raw: bool = True):

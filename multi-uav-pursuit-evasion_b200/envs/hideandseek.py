@@ -96,11 +96,11 @@ class HideAndSeek(IsaacEnv):
         self.time_encoding_dim = 4
         self.collision_radius = t.collision_radius
         self.mask_value = -5
-        self.update_epoch = 0
+        self._update_epoch = 0
         self.init_smoothness_coef = t.init_smoothness_coef if t.init_smoothness_coef is not None else (t.smoothness_coef or 0.0)
         self.smooth_lr = t.smooth_lr or 0.0
         self.max_smoothness_coef = t.max_smoothness_coef if t.max_smoothness_coef is not None else 5.0
-        self.smoothness_coef = min(self.max_smoothness_coef, self.init_smoothness_coef + self.smooth_lr * self.update_epoch)
+        self.smoothness_coef = min(self.max_smoothness_coef, self.init_smoothness_coef + self.smooth_lr * self._update_epoch)
         if not self.use_random_cylinder and self.scenario_flag not in _LAYOUTS:
             raise ValueError(f"unknown scenario_flag {self.scenario_flag!r}")
         if not self.use_random_cylinder and len(_LAYOUTS[self.scenario_flag]) > self.num_cylinders:
@@ -172,6 +172,22 @@ class HideAndSeek(IsaacEnv):
 
     def _stat_keys(self):
         return STAT_KEYS
+
+    # ------------------------------------------------------------------ smoothness curriculum
+    @property
+    def update_epoch(self) -> int:
+        return self._update_epoch
+
+    @update_epoch.setter
+    def update_epoch(self, i):
+        """scripts/train_deploy.py writes ``base_env.update_epoch = i`` every iteration; the reference turns it into
+        ``smoothness_coef = min(max, init + smooth_lr * update_epoch)`` at the next reward call (hideandseek.py:988-991).
+        The coefficient is a device scalar every tick reads, so already captured CUDA graphs follow it."""
+        self._update_epoch = i
+        self.smoothness_coef = min(self.max_smoothness_coef, self.init_smoothness_coef + self.smooth_lr * i)
+        eng = getattr(self, "engine", None)
+        if eng is not None:
+            eng.smoothness_coef.fill_(float(self.smoothness_coef))
 
     # ------------------------------------------------------------------ views
     @property

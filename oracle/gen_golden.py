@@ -38,7 +38,12 @@ CASES = {
     "deploy_smooth_tp": (dict(use_deployment=True, smoothness_coef=2.0), 12, "random_cylinders", 4, 4, None),   # smoothness reward paid
     "gated_smooth_tp": (dict(use_deployment=False, smoothness_coef=2.0), 12, "random_cylinders", 4, 3, None),   # ... and gated off (hideandseek.py:992-994)
     "a2_tp": (dict(num_agents=2), 12, "random_cylinders", 4, 4, None),
+    # smoothness curriculum: base_env.update_epoch is rewritten between ticks (scripts/train_deploy.py:270) and the
+    # coefficient min(max, init + smooth_lr * update_epoch) is recomputed at every reward call (hideandseek.py:988-991)
+    "deploy_epoch_tp": (dict(use_deployment=True, smoothness_coef=0.5, smooth_lr=0.4, max_smoothness_coef=5.0), 12,
+                        "random_cylinders", 4, 4, None),
 }
+UPDATE_EPOCHS = {"deploy_epoch_tp": [0, 3, 3, 20]}        # -> 0.5, 1.7, 1.7, min(5, 8.5)
 
 
 def snapshot_state(ref: RefEnv):
@@ -125,6 +130,9 @@ def gen_case(name, pk, E, scenario, min_cyl, ticks, progress0):
         act = torch.randn(E, P.num_agents, 4, generator=g) * (1.5 if t % 2 == 0 else 0.4)
         pre = snapshot_state(ref)
         load_oracle_state(orc, pre)                       # teacher forcing
+        if name in UPDATE_EPOCHS:
+            ref.env.update_epoch = orc.update_epoch = UPDATE_EPOCHS[name][t]
+            rec[f"t{t}/update_epoch"] = np.array(float(UPDATE_EPOCHS[name][t]))
         nxt, aux = ref.step(act, done_prev)
         out = outputs_from_ref(P, nxt, aux, ref)
         want = orc.step(act, done_prev, tp_fn)
@@ -157,8 +165,10 @@ def gen_case(name, pk, E, scenario, min_cyl, ticks, progress0):
 def main():
     if not os.path.isdir("/root/reference"):
         raise SystemExit("gen_golden needs the reference tree at /root/reference (build container only)")
+    only = sys.argv[1:]
     for name, spec in CASES.items():
-        gen_case(name, *spec)
+        if not only or name in only:
+            gen_case(name, *spec)
 
 
 if __name__ == "__main__":

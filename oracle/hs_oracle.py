@@ -92,7 +92,9 @@ class HSParams:
     detect_reward_coef: float = 0.0
     collision_coef: float = 100.0
     speed_coef: float = 10.0
-    smoothness_coef: float = 0.0      # init + lr*epoch, clipped (hideandseek.py:988-989)
+    smoothness_coef: float = 0.0      # init_smoothness_coef; the coefficient used is
+    smooth_lr: float = 0.0            #   min(max_smoothness_coef, init + smooth_lr * update_epoch), recomputed at
+    max_smoothness_coef: float = 5.0  #   every reward call (hideandseek.py:988-989; envgen: the constant, :465)
     use_deployment: bool = False      # HideAndSeek gates smoothness on this; envgen does not
     envgen_variant: bool = False
     # controller (crazyflie.yaml:4-6, lee_position_controller.py:448-454)
@@ -343,8 +345,9 @@ def los_blocked(P: HSParams, drone_pos, target_pos, cyl_pos):
 # ----------------------------------------------------------------------------
 # stage 4: potential-field evader (hideandseek.py:1067-1141 and 737-744)
 # ----------------------------------------------------------------------------
-def evader_velocity(P: HSParams, v_prey: float, drone_pos, target_pos, cyl_pos, cyl_inactive):
-    """Returns (new evader velocity [E,3], out_of_arena bool [E])."""
+def evader_force(P: HSParams, drone_pos, target_pos, cyl_pos, cyl_inactive):
+    """hideandseek.py:1067-1141.  Returns (force [E,3], magnitude [E,3] = sum of |terms| per component, i.e. the
+    scale of the rounding error the cancellation in `force` is exposed to, out_of_arena bool [E])."""
     E = drone_pos.shape[0]
     rel = drone_pos - target_pos.unsqueeze(1)                  # drone - evader [E,A,3]
     dist = torch.linalg.vector_norm(rel, dim=-1, keepdim=True)  # [E,A,1]
@@ -358,6 +361,7 @@ def evader_velocity(P: HSParams, v_prey: float, drone_pos, target_pos, cyl_pos, 
     for a in range(1, A):
         acc = acc + f_p[:, a]
     force = force + acc
+    mag = f_p.abs().sum(1)
 
     # arena wall, ceiling, floor
     rho = torch.linalg.vector_norm(target_pos[:, :2], dim=-1)  # [E]
@@ -371,12 +375,15 @@ def evader_velocity(P: HSParams, v_prey: float, drone_pos, target_pos, cyl_pos, 
             + no * inward[:, ax] * (1 / ((P.arena_size - rho) + 1e-5))
     z = target_pos[:, 2]
     hi = z > P.max_height
-    f_r[:, 2] = hi.float() * (-1 / 1e-5) \
+    up = hi.float() * (-1 / 1e-5) \
         + (~hi).float() * -(P.max_height - z) / ((P.max_height - z) ** 2 + 1e-5)
     lo = z < 0.0
-    f_r[:, 2] += (lo.float() * (1 / 1e-5)
-                  + (~lo).float() * -(0.0 - z) / ((0.0 - z) ** 2 + 1e-5))
+    down = (lo.float() * (1 / 1e-5)
+            + (~lo).float() * -(0.0 - z) / ((0.0 - z) ** 2 + 1e-5))
+    f_r[:, 2] = up
+    f_r[:, 2] += down
     force = force + f_r
+    mag = mag + torch.stack([f_r[:, 0].abs(), f_r[:, 1].abs(), up.abs() + down.abs()], dim=-1)
 
     # cylinders: xy repulsion from every active cylinder
     tc = target_pos.unsqueeze(1) - cyl_pos                     # [E,C,3]
@@ -384,11 +391,17 @@ def evader_velocity(P: HSParams, v_prey: float, drone_pos, target_pos, cyl_pos, 
     gap = d_xy - P.cylinder_size
     act = ((~cyl_inactive) & (d_xy < P.target_detect_radius)).float()
     dir_xy = tc[..., :2] / (d_xy + 1e-5).unsqueeze(-1)
-    f_c_xy = (act.unsqueeze(-1) * dir_xy * (1 / (gap.unsqueeze(-1) + 1e-5))).sum(1)
+    terms = act.unsqueeze(-1) * dir_xy * (1 / (gap.unsqueeze(-1) + 1e-5))
     f_c = torch.zeros(E, 3, dtype=F32)
-    f_c[:, :2] = f_c_xy
+    f_c[:, :2] = terms.sum(1)
     force = force + f_c
+    mag[:, :2] = mag[:, :2] + terms.abs().sum(1)
+    return force.to(F32), mag, outside
 
+
+def evader_velocity(P: HSParams, v_prey: float, drone_pos, target_pos, cyl_pos, cyl_inactive):
+    """Returns (new evader velocity [E,3], out_of_arena bool [E])."""
+    force, _, outside = evader_force(P, drone_pos, target_pos, cyl_pos, cyl_inactive)
     # per-component normalisation (torch.norm over the size-1 agent dim), hideandseek.py:741
     vel = v_prey * force / (torch.abs(force) + 1e-5)
     return vel.to(F32), outside
@@ -535,8 +548,10 @@ def observe(P: HSParams, st: Dict[str, torch.Tensor], tp_pred: Optional[torch.Te
 # ----------------------------------------------------------------------------
 # stage 7: reward / done / stats (hideandseek.py:919-1065)
 # ----------------------------------------------------------------------------
-def reward_done(P: HSParams, st, obs, action_error, throttle_diff, stats):
-    """Returns reward [E,A,1], done [E,1]; updates `stats` [E,24] in place."""
+def reward_done(P: HSParams, st, obs, action_error, throttle_diff, stats, smoothness_coef=None):
+    """Returns reward [E,A,1], done [E,1]; updates `stats` [E,24] in place.  `smoothness_coef`: the value
+    hideandseek.py:988-989 recomputes from update_epoch (default: P.smoothness_coef, i.e. update_epoch = 0)."""
+    coef = P.smoothness_coef if smoothness_coef is None else smoothness_coef
     pos, linvel, tpos, progress = st["pos"], st["linvel"], st["tpos"], st["progress"]
     E, A, _ = pos.shape
     blocked, bdetect = obs["blocked"], obs["bdetect"]
@@ -587,8 +602,8 @@ def reward_done(P: HSParams, st, obs, action_error, throttle_diff, stats):
     add("collision_reward", r_coll)
 
     if not P.envgen_variant:
-        stats[:, S["smoothness_coef"]] = P.smoothness_coef
-    r_smooth = P.smoothness_coef * torch.exp(-action_error)
+        stats[:, S["smoothness_coef"]] = coef
+    r_smooth = coef * torch.exp(-action_error)
     if (not P.envgen_variant) and (not P.use_deployment):
         r_smooth = torch.zeros_like(r_smooth)
     add("smoothness_reward", r_smooth)
@@ -626,7 +641,14 @@ class HideAndSeekOracle:
         self.stats = z(E, len(STAT_KEYS))
         self.tp_hist = None                 # [E,H,frame] once the first frame arrives
         self.v_prey = float(params.v_prey)
+        self.update_epoch = 0               # scripts/train_deploy.py writes base_env.update_epoch = i
         self.last = {}
+
+    def smoothness_coef(self) -> float:
+        P = self.P
+        if P.envgen_variant:
+            return P.smoothness_coef
+        return min(P.max_smoothness_coef, P.smoothness_coef + P.smooth_lr * self.update_epoch)
 
     # -- helpers --------------------------------------------------------------
     def hover_throttle(self) -> float:
@@ -712,7 +734,7 @@ class HideAndSeekOracle:
         st["tpos"] = st["tpos"] + P.dt * st["tvel"]
         st["progress"] = st["progress"] + 1
         obs = self._observe(tp_fn)
-        reward, done = reward_done(P, st, obs, ae, throttle_diff, self.stats)
+        reward, done = reward_done(P, st, obs, ae, throttle_diff, self.stats, self.smoothness_coef())
         if bool(done.any()) and float(self.stats[:, S["success"]].mean()) >= 0.98 and not P.envgen_variant:
             self.v_prey = min(1.3, self.v_prey + 0.05)
         obs.update(reward=reward, done=done, cmds=c["cmds"], ctbr=c["ctbr"],

@@ -313,7 +313,7 @@ class RefEnv:
         e.catch_radius, e.collision_radius = P.catch_radius, P.collision_radius
         e.dist_reward_coef, e.detect_reward_coef = P.dist_reward_coef, P.detect_reward_coef
         e.catch_reward_coef, e.speed_coef, e.collision_coef = P.catch_reward_coef, P.speed_coef, P.collision_coef
-        e.init_smoothness_coef, e.smooth_lr, e.update_epoch, e.max_smoothness_coef = P.smoothness_coef, 0.0, 0, 5.0
+        e.init_smoothness_coef, e.smooth_lr, e.update_epoch, e.max_smoothness_coef = P.smoothness_coef, P.smooth_lr, 0, P.max_smoothness_coef
         e.use_deployment = P.use_deployment
         e.cfg = _Obj()
         e.cfg.task = _Obj()

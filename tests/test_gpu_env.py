@@ -76,30 +76,59 @@ def test_env_matches_oracle_through_public_api():
     assert_close("reset/state_self", td[("agents", "observation", "state_self")], want["state_self"], rtol=2e-4, atol=2e-5)
     assert_close("reset/TP_input", td[("agents", "TP", "TP_input")], want["tp_input"])
     g = torch.Generator().manual_seed(11)
+    from oracle import conditioning as CD
+    traj = CD.TrajectoryConditioning(P, E)           # free-running: strict on the envs that stayed well conditioned
     for t in range(12):
         act = torch.randn(E, 3, 4, generator=g)
         td.set(("agents", "action"), act.to(DEV))
         done_prev = td.get("done").reshape(-1).cpu()
         td = env.step(td)
+        pre, v_prey = {k: v.clone() for k, v in orc.st.items()}, orc.v_prey
         want = orc.step(act, done_prev, tp_fn)
+        traj.update(v_prey, pre, orc.st)
         nxt = td.get("next")
-        flip = 0.02      # free-running: a few envs may sit on a discontinuity
-        assert_close(f"t{t}/state_self", nxt[("agents", "observation", "state_self")], want["state_self"], rtol=2e-4, atol=2e-5, max_bad_frac=flip)
-        assert_close(f"t{t}/state_others", nxt[("agents", "observation", "state_others")], want["others"], max_bad_frac=flip)
-        assert_close(f"t{t}/cylinders", nxt[("agents", "observation", "cylinders")], want["cylinders"], max_bad_frac=flip)
+        # cuDNN-free predictor vs CPU LSTM differ by ~1e-6 in the prediction -> state rows at 2e-4
+        traj.check(f"t{t}/state_self", nxt[("agents", "observation", "state_self")], want["state_self"], rtol=2e-4, atol=2e-5)
+        traj.check(f"t{t}/state_others", nxt[("agents", "observation", "state_others")], want["others"])
+        traj.check(f"t{t}/cylinders", nxt[("agents", "observation", "cylinders")], want["cylinders"])
         assert nxt[("agents", "state", "cylinders")] is nxt[("agents", "observation", "cylinders")]
-        assert_close(f"t{t}/state_drones", nxt[("agents", "state", "state_drones")], want["state_drones"], rtol=2e-4, atol=2e-5, max_bad_frac=flip)
-        assert_close(f"t{t}/TP_input", nxt[("agents", "TP", "TP_input")], want["tp_input"], max_bad_frac=flip)
-        assert_close(f"t{t}/reward", nxt[("agents", "reward")], want["reward"], max_bad_frac=flip)
-        assert_close(f"t{t}/drone_state", nxt[("info", "drone_state")], want["drone_state"], max_bad_frac=flip)
-        assert_close(f"t{t}/return", nxt[("stats", "return")], want["stats"][:, O.S["return"]], atol=1e-3, max_bad_frac=flip)
+        traj.check(f"t{t}/state_drones", nxt[("agents", "state", "state_drones")], want["state_drones"], rtol=2e-4, atol=2e-5)
+        traj.check(f"t{t}/TP_input", nxt[("agents", "TP", "TP_input")], want["tp_input"])
+        traj.check(f"t{t}/reward", nxt[("agents", "reward")], want["reward"])
+        traj.check(f"t{t}/drone_state", nxt[("info", "drone_state")], want["drone_state"])
+        traj.check(f"t{t}/return", nxt[("stats", "return")], want["stats"][:, O.S["return"]], atol=1e-3)
         # keys the reference's PIDrate transform leaves on the input tensordict
-        assert_close(f"t{t}/ctbr", td["ctbr"], want["ctbr"], max_bad_frac=flip)
-        assert_close(f"t{t}/target_rate", td["target_rate"], want["target_rate"], max_bad_frac=flip)
-        assert_close(f"t{t}/action", td[("agents", "action")], want["cmds"], max_bad_frac=flip)
-        assert_close(f"t{t}/action_error", td[("stats", "action_error_order1")], want["action_error"], max_bad_frac=flip)
+        traj.check(f"t{t}/ctbr", td["ctbr"], want["ctbr"], atol=1e-4 * float(want["ctbr"].abs().max()))
+        traj.check(f"t{t}/target_rate", td["target_rate"], want["target_rate"])
+        traj.check(f"t{t}/action", td[("agents", "action")], want["cmds"])
+        traj.check(f"t{t}/action_error", td[("stats", "action_error_order1")], want["action_error"])
         assert not nxt.get("is_init").any()
         td = m.step_mdp(td)
+    assert traj.clean.float().mean() > 0.7, f"only {int(traj.clean.sum())}/{E} envs stayed well conditioned over 12 ticks"
+    env.close()
+
+
+def test_update_epoch_property_reaches_graph_replayed_ticks():
+    """scripts/train_deploy.py:270 writes base_env.update_epoch = i; hideandseek.py:988-991 turns it into the smoothness
+    coefficient at the next reward call.  The ticks here are CUDA-graph replays captured BEFORE the write."""
+    E = 64
+    m, cfg, base, env = make(E, **{"task.use_deployment": 1, "task.init_smoothness_coef": 0.5, "task.smooth_lr": 0.4,
+                                   "task.max_smoothness_coef": 5.0})
+    td = env.reset()
+    g = torch.Generator().manual_seed(2)
+    coefs, rewards = [], []
+    for t, epoch in enumerate([0, 0, 3, 20]):
+        base.update_epoch = epoch
+        assert base.update_epoch == epoch
+        td.set(("agents", "action"), torch.zeros(E, 3, 4, device=DEV))       # same action: only the coefficient changes
+        td = env.step(td)
+        coefs.append(float(td[("next", "stats", "smoothness_coef")][0]))
+        rewards.append(td[("next", "stats", "smoothness_reward")].clone())
+        td = m.step_mdp(td)
+    assert coefs == pytest.approx([0.5, 0.5, 1.7, 5.0], rel=1e-6), coefs
+    assert getattr(base.engine, "_graph_replays", 0) >= 3                   # the fast path really was graph replay
+    inc = [rewards[0]] + [rewards[i] - rewards[i - 1] for i in range(1, 4)]
+    assert (inc[2] > inc[1] * 2).all() and (inc[3] > inc[2] * 2).all()       # exp(-action_error) x 0.5 -> 1.7 -> 5.0
     env.close()
 
 

@@ -122,11 +122,15 @@ def test_full_size_properties(E, C, active):
     orc.tp_hist = small.out["tp_input"].cpu().clone()
     act = torch.randn(64, P.num_agents, 4, device=DEV, generator=gen)
     dprev = small.out["done"].reshape(64).clone()
+    from oracle import conditioning as CD
+    pre, v_prey = {k: v.clone() for k, v in orc.st.items()}, orc.v_prey
     want = orc.step(act.cpu(), dprev.cpu(), tp_fn)
+    cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=1e-6)
     got = small.step_pre(act, raw=True, reset_pid=dprev)
     small.step_post_tp(small.tp_weights(tp))
-    for k, w in (("reward", "reward"), ("drone_state", "drone_state"), ("tp_input", "tp_input"), ("obs_cylinders", "cylinders"),
-                 ("state_self", "state_self")):
-        assert_close(f"oracle/{k}", got[k], want[w], max_bad_frac=2e-2)
+    for k, w in (("reward", "reward"), ("drone_state", "drone_state"), ("tp_input", "tp_input"), ("obs_cylinders", "cylinders")):
+        cond.check(f"oracle/{k}", got[k], want[w])
+    well = (cond.dv < 1e-6) & ~cond.edge          # state_self also carries the (nonlinear) predictor's output
+    assert_close("oracle/state_self", got["state_self"].cpu()[well], want["state_self"][well], rtol=2e-4, atol=2e-5)
     for e in (big, twin, small):
         e.close()

@@ -1,20 +1,21 @@
 """GPU: the CUDA kernels against fixtures produced by the REFERENCE'S OWN SOURCE
 (tests/golden/*.npz, written by oracle/gen_golden.py in the build container).  Each recorded
-tick is replayed from its stored pre-tick state; bar = 1e-4 relative fp32 (north_star)."""
+tick is replayed from its stored pre-tick state; bar = 1e-4 relative fp32 (north_star), with the
+per-env conditioning allowances of oracle/conditioning.py (computed from the fixture's own pre/post
+state) instead of a blanket budget, for both builds of the tick kernel (see tests/test_gpu_parity.py)."""
+import json
+import os
+
 import pytest
 import torch
 
+from oracle import conditioning as CD
 from tests.golden_util import Golden, golden_files
 from tests.util import assert_close, hs_config_from_params
 
 pytestmark = pytest.mark.gpu
-FLIP = 5e-3          # see tests/test_gpu_parity.py
-# 'wall' is mirror-symmetric about y=0 with the evader and one pursuer ON the axis: the y
-# component of the evader's potential-field force is an exact cancellation (true value 0), so
-# its sign-normalised velocity v*f/(|f|+1e-5) is pure rounding noise in ANY implementation
-# (the reference's own value there is -8e-3 m/s from a force of -6e-8).  Everything derived
-# from the evader's y gets a per-tensor budget for those elements in that fixture.
-SYMMETRIC_FLIP = {"wall_tp": 0.02}
+EPS = {False: 1e-6, True: 2e-7}
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "golden_parity_report.jsonl")
 
 
 def load_engine_state(eng, st, v_prey=1.3):
@@ -36,13 +37,16 @@ def load_engine_state(eng, st, v_prey=1.3):
 NAMES = {"cmds": "rotor_cmds", "others": "state_others", "cylinders": "obs_cylinders"}
 
 
+@pytest.mark.parametrize("exact", [False, True], ids=["fast", "ieee"])
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("hs_")[-1][:-4])
-def test_kernels_replay_reference_ticks(path):
+def test_kernels_replay_reference_ticks(path, exact):
     import mupe_b200
+    from mupe_b200 import _lib as L
     G = Golden(path)
     P, E = G.P, G.E
     dev = torch.device("cuda:0")
     eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    eng.set_exact_math(exact)
     init = G.group("init/")
     got = eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
     want = G.group("reset/out/")
@@ -51,9 +55,17 @@ def test_kernels_replay_reference_ticks(path):
     for k, v in want.items():
         if k != "tp_pred":
             assert_close(f"{G.name}/reset/{k}", got[NAMES.get(k, k)], v)
+    n_edge_envs = n_exempt = n_dv = 0
     for t in range(G.ticks):
-        load_engine_state(eng, G.group(f"t{t}/pre/"))
+        pre, post = G.group(f"t{t}/pre/"), G.group(f"t{t}/post/")
+        load_engine_state(eng, pre)
         io = G.group(f"t{t}/")
+        if "update_epoch" in io:                  # smoothness curriculum, hideandseek.py:988-991
+            coef = min(P.max_smoothness_coef, P.smoothness_coef + P.smooth_lr * float(io["update_epoch"]))
+            eng.smoothness_coef.fill_(coef)
+        post_c = dict(post)
+        post_c["cyl"] = pre["cyl"]
+        cond = CD.TickConditioning(P, P.v_prey, pre, post_c, eps=EPS[exact])
         got = eng.step_pre(io["action"].to(dev), raw=True, reset_pid=io["done_prev"].bool().to(dev))
         want = G.group(f"t{t}/out/")
         if P.use_tp_net:
@@ -67,19 +79,27 @@ def test_kernels_replay_reference_ticks(path):
                 g = eng.prev_action
             else:
                 g = got[NAMES.get(k, k)].float()
-            flip = SYMMETRIC_FLIP.get(G.name, FLIP)
             # ctbr carries the raw PID output whose D term amplifies 1-ulp body-rate differences by
             # 1/dt * kd * 180/pi ~ 1.4e4 -> compare it relative to the tensor's scale
             atol = 1e-4 if k == "stats" else (1e-4 * float(v.abs().max()) if k == "ctbr" else 1e-5)
-            if G.name in SYMMETRIC_FLIP and k in ("state_self", "state_drones", "tp_input", "tp_groundtruth"):
-                atol = 5e-3         # these carry the evader's y position / velocity (noise, see above)
-            assert_close(f"{G.name}/t{t}/{k}", g, v, rtol=1e-4, atol=atol, max_bad_frac=flip)
-        post = G.group(f"t{t}/post/")
-        from mupe_b200 import _lib as L
+            cond.check(f"{G.name}/t{t}/{k}", g, v, rtol=1e-4, atol=atol)
         for f, k in ((L.FIELD_DRONE_POS, "pos"), (L.FIELD_DRONE_ROT, "quat"), (L.FIELD_DRONE_LINVEL, "linvel"),
                      (L.FIELD_DRONE_ANGVEL, "angvel"), (L.FIELD_THROTTLE, "throttle"), (L.FIELD_PID_INTEG, "integ"),
                      (L.FIELD_TARGET_POS, "tpos"), (L.FIELD_TARGET_VEL, "tvel"), (L.FIELD_PROGRESS, "progress")):
-            atol = 5e-3 if (G.name in SYMMETRIC_FLIP and k in ("tpos", "tvel")) else 1e-5
-            assert_close(f"{G.name}/t{t}/post/{k}", eng.get_state(f), post[k], atol=atol,
-                         max_bad_frac=SYMMETRIC_FLIP.get(G.name, FLIP))
+            cond.check(f"{G.name}/t{t}/post/{k}", eng.get_state(f), post[k])
+        n_edge_envs += int(cond.edge.sum())
+        n_exempt += getattr(cond, "n_edge_exempt", 0)
+        n_dv += getattr(cond, "n_dv_needed", 0)
     eng.close()
+    try:                                          # evidence for profiles/: how much of the allowance was actually used
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, "a") as f:
+            f.write(json.dumps({"fixture": G.name, "build": "ieee" if exact else "fast", "envs_x_ticks": E * G.ticks,
+                                "edge_envs": n_edge_envs, "elements_exempted_as_edge": n_exempt,
+                                "elements_within_dv_allowance_only": n_dv}) + "\n")
+    except OSError:
+        pass
+    if exact:
+        # the IEEE build reproduces the reference's numbers without ANY exemption: no flipped indicator, and nothing
+        # beyond the plain 1e-4 tolerance (not even inside the conditioning allowance)
+        assert n_exempt == 0 and n_dv == 0, (G.name, n_exempt, n_dv)

@@ -4,23 +4,26 @@ Tolerance: 1e-4 relative (+1e-5 absolute) in fp32, the bar BASELINE.json's north
 states.  Every tick starts from the oracle's state ("teacher forcing"), because the task
 contains sign/threshold discontinuities (evader velocity = v * f/(|f|+eps) per component,
 capture / collision indicators) that make free-running fp32 trajectories of ANY two
-implementations diverge after O(100) ticks; a small budget of discontinuity flips per
-tensor is allowed and stated next to each check.
+implementations diverge after O(100) ticks.  There is NO blanket budget of "wrong" elements:
+oracle/conditioning.py computes, per tick and env, the a-priori bound on the evader-velocity
+error (rounding level x force magnitude x slope of the normalisation) and the envs in which an
+indicator sits within 2e-5 of its threshold; every element outside 1e-4 must be explained by
+exactly that, in both builds of the tick kernel (product: SFU approximations; HS_OPT_EXACT_MATH:
+IEEE arithmetic, where the rounding level - and with it the allowance - is 5x smaller).
 """
 import pytest
 import torch
 
+from oracle import conditioning as CD
 from oracle import hs_oracle as O
 from tests.util import assert_close, hs_config_from_params, pull_state, push_state
 
 pytestmark = pytest.mark.gpu
 
-# Fraction of a tensor's elements that may sit on a discontinuity / exact cancellation in one
-# tick.  The evader's force is a sum of O(1..10) repulsion terms that routinely cancel to 1e-4;
-# its per-component sign-normalisation then turns 1e-7-level term differences (rcp/sqrt.approx
-# vs IEEE, FMA vs mul+add) into 1e-3 relative velocity differences for that env.  Measured: up
-# to 3e-3 of the evader-derived elements per tick; everything else matches at 1e-4.
-FLIP = 5e-3
+# relative rounding level of the evader-force terms: rcp/sqrt.approx (2 ulp each, squared) + FMA contraction in the
+# product build; IEEE operations in a different association order than torch's in the exact build
+EPS = {False: 1e-6, True: 2e-7}
+MAX_EDGE_FRAC = 0.03         # envs per tick with an indicator within 2e-5 of its threshold (measured: 0.2-0.6 %)
 
 
 def make_tp(P, seed=0):
@@ -35,31 +38,31 @@ def make_tp(P, seed=0):
     return fn
 
 
-def compare_obs(P, got, want, tag, flip=FLIP, ev_atol=1e-5):
-    """ev_atol: absolute tolerance for tensors that carry the evader's position/velocity (see
-    `symmetric` in run_case)."""
-    assert_close(f"{tag}/drone_state", got["drone_state"], want["drone_state"], max_bad_frac=flip)
+def compare_obs(P, got, want, tag, cond=None):
+    """cond: TickConditioning of the tick (None: plain 1e-4 check, e.g. right after a reset)."""
+    chk = cond.check if cond is not None else (lambda n, g, w, **kw: assert_close(n, g, w))
+    chk(f"{tag}/drone_state", got["drone_state"], want["drone_state"])
     if P.num_agents > 1:
-        assert_close(f"{tag}/state_others", got["state_others"], want["others"], max_bad_frac=flip)
-    assert_close(f"{tag}/obs_cylinders", got["obs_cylinders"], want["cylinders"], max_bad_frac=flip)
-    assert_close(f"{tag}/state_self", got["state_self"], want["state_self"], atol=ev_atol, max_bad_frac=flip)
-    assert_close(f"{tag}/state_drones", got["state_drones"], want["state_drones"], atol=ev_atol, max_bad_frac=flip)
+        chk(f"{tag}/state_others", got["state_others"], want["others"])
+    chk(f"{tag}/obs_cylinders", got["obs_cylinders"], want["cylinders"])
+    chk(f"{tag}/state_self", got["state_self"], want["state_self"])
+    chk(f"{tag}/state_drones", got["state_drones"], want["state_drones"])
     if P.use_tp_net:
-        assert_close(f"{tag}/tp_input", got["tp_input"], want["tp_input"], atol=ev_atol, max_bad_frac=flip)
-        assert_close(f"{tag}/tp_groundtruth", got["tp_groundtruth"], want["tp_groundtruth"], atol=ev_atol, max_bad_frac=flip)
+        chk(f"{tag}/tp_input", got["tp_input"], want["tp_input"])
+        chk(f"{tag}/tp_groundtruth", got["tp_groundtruth"], want["tp_groundtruth"])
         assert torch.equal(got["tp_done"].cpu().reshape(-1), want["tp_done"].reshape(-1))
 
 
-def run_case(P, E, scenario, steps, seed=0, progress0=None, min_cyl=None, free_run=False, symmetric=False):
-    """symmetric: the fixed 'wall' layout is mirror-symmetric about y=0 with the evader and one
-    pursuer on the axis, so the y component of the evader's force is an exact cancellation whose
-    sign-normalised velocity is rounding noise in any implementation (see tests/test_gpu_golden.py);
-    evader-derived tensors then get an absolute tolerance of 5e-3."""
-    ev_atol = 5e-3 if symmetric else 1e-5
+def snapshot(orc):
+    return {k: v.clone() for k, v in orc.st.items()}
+
+
+def run_case(P, E, scenario, steps, seed=0, progress0=None, min_cyl=None, exact=False):
     import mupe_b200
     dev = torch.device("cuda:0")
     cfg = hs_config_from_params(P, E)
     eng = mupe_b200.HsEngine(cfg, dev, num_output_sets=2)
+    eng.set_exact_math(exact)
     orc = O.HideAndSeekOracle(P, E)
     tp_fn = make_tp(P) if P.use_tp_net else None
     g = torch.Generator().manual_seed(seed)
@@ -71,78 +74,125 @@ def run_case(P, E, scenario, steps, seed=0, progress0=None, min_cyl=None, free_r
     got = eng.reset(mask.to(dev), init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
     if P.use_tp_net:
         eng.step_post(want["tp_pred"].to(dev))
-    compare_obs(P, got, want, "reset", flip=0.0)
+    compare_obs(P, got, want, "reset")
     assert not got["truncated"].any()
 
     if progress0 is not None:
         orc.st["progress"][:] = progress0
     done_prev = torch.zeros(E, dtype=torch.bool)
-    worst = {}
+    n_edge_envs = n_exempt = n_dv = 0
     for t in range(steps):
         ga = torch.Generator().manual_seed(1234 + t)
         act = torch.randn(E, P.num_agents, 4, generator=ga) * (0.3 if t % 3 else 1.5)
-        if not free_run or t == 0:
-            push_state(eng, orc)
+        push_state(eng, orc)
+        pre, v_prey = snapshot(orc), orc.v_prey
         want = orc.step(act, done_prev, tp_fn)
+        cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=EPS[exact])
         got = eng.step_pre(act.to(dev), raw=True, reset_pid=done_prev.to(dev))
         if P.use_tp_net:
             # the predictor itself is outside the kernels: feed both sides the same prediction
             eng.step_post(want["tp_pred"].to(dev))
-        flip = 0.02 if free_run else FLIP
         tag = f"t{t}"
         for k in ("rotor_cmds", "ctbr", "target_rate", "action_error"):
-            assert_close(f"{tag}/{k}", got[k], want["cmds" if k == "rotor_cmds" else k], max_bad_frac=flip)
-        assert_close(f"{tag}/prev_action", eng.prev_action, want["prev_action"], max_bad_frac=flip)
-        compare_obs(P, got, want, tag, flip=flip, ev_atol=ev_atol)
-        assert_close(f"{tag}/reward", got["reward"], want["reward"], max_bad_frac=flip)
+            cond.check(f"{tag}/{k}", got[k], want["cmds" if k == "rotor_cmds" else k])
+        cond.check(f"{tag}/prev_action", eng.prev_action, want["prev_action"])
+        compare_obs(P, got, want, tag, cond)
+        cond.check(f"{tag}/reward", got["reward"], want["reward"])
         assert torch.equal(got["done"].cpu().reshape(-1), want["done"].reshape(-1))
         st = pull_state(eng)
         for k in ("pos", "quat", "linvel", "angvel", "tpos", "tvel", "progress"):
-            assert_close(f"{tag}/state/{k}", st[k], orc.st[k], atol=ev_atol if k in ("tpos", "tvel") else 1e-5, max_bad_frac=flip)
-        assert_close(f"{tag}/state/throttle", st["throttle"], orc.throttle, max_bad_frac=flip)
-        assert_close(f"{tag}/state/integ", st["integ"], orc.integ, max_bad_frac=flip)
-        assert_close(f"{tag}/state/last_rate", st["last_rate"], orc.last_rate, rtol=1e-4, atol=1e-3, max_bad_frac=flip)
+            cond.check(f"{tag}/state/{k}", st[k], orc.st[k])
+        cond.check(f"{tag}/state/throttle", st["throttle"], orc.throttle)
+        cond.check(f"{tag}/state/integ", st["integ"], orc.integ)
+        cond.check(f"{tag}/state/last_rate", st["last_rate"], orc.last_rate, rtol=1e-4, atol=1e-3)
         stats = eng.stats.t().cpu()
         for i, k in enumerate(O.STAT_KEYS):
-            assert_close(f"{tag}/stats/{k}", stats[:, i], want["stats"][:, i], rtol=1e-4, atol=1e-4, max_bad_frac=flip)
+            cond.check(f"{tag}/stats/{k}", stats[:, i], want["stats"][:, i], rtol=1e-4, atol=1e-4)
+        n_edge_envs += int(cond.edge.sum())
+        n_exempt += cond.n_edge_exempt
+        n_dv += cond.n_dv_needed
         done_prev = want["done"].reshape(-1).clone()
     torch.cuda.synchronize()
     eng.close()
+    # the exemptions stay rare: edge envs are a small, stated fraction of all (env, tick) pairs
+    assert n_edge_envs <= max(2 * steps, MAX_EDGE_FRAC * E * steps), (n_edge_envs, E, steps)
+    return dict(edge_envs=n_edge_envs, exempt_elements=n_exempt, dv_elements=n_dv)
 
 
-def test_default_3v1_random_cylinders_tp():
-    run_case(O.HSParams(), E=512, scenario="random_cylinders", steps=30)
+BUILDS = pytest.mark.parametrize("exact", [False, True], ids=["fast", "ieee"])
 
 
-def test_3v1_empty_no_tp():
-    run_case(O.HSParams(use_tp_net=False), E=256, scenario="empty", steps=20)
+@BUILDS
+def test_default_3v1_random_cylinders_tp(exact):
+    run_case(O.HSParams(), E=512, scenario="random_cylinders", steps=30, exact=exact)
 
 
-def test_3v1_eight_cylinders():
+@BUILDS
+def test_3v1_empty_no_tp(exact):
+    run_case(O.HSParams(use_tp_net=False), E=256, scenario="empty", steps=20, exact=exact)
+
+
+@BUILDS
+def test_3v1_eight_cylinders(exact):
     P = O.HSParams(num_cylinders=8, obs_max_cylinder=3)
-    run_case(P, E=256, scenario="random_cylinders", steps=20, min_cyl=8)
+    run_case(P, E=256, scenario="random_cylinders", steps=20, min_cyl=8, exact=exact)
 
 
+@BUILDS
 @pytest.mark.parametrize("scenario", ["wall", "narrow_gap", "passage", "random"])
-def test_fixed_scenarios(scenario):
+def test_fixed_scenarios(scenario, exact):
+    # 'wall' is mirror-symmetric about y = 0 with the evader and one pursuer on the axis: the y component of the
+    # evader's force is an exact cancellation -> the conditioning bound (not a special case here) widens exactly those envs
     P = O.HSParams(num_cylinders=6)
-    run_case(P, E=64, scenario=scenario, steps=12, symmetric=(scenario == "wall"))
+    run_case(P, E=64, scenario=scenario, steps=12, exact=exact)
 
 
-def test_ragged_batch_and_done_tick():
+@BUILDS
+def test_ragged_batch_and_done_tick(exact):
     # E not a multiple of 8 exercises the partial warp tile; progress starts at 797 so the
     # done tick (stats divided by the episode length) falls inside the run
-    run_case(O.HSParams(), E=77, scenario="random_cylinders", steps=5, progress0=797.0)
-    run_case(O.HSParams(use_tp_net=False), E=3, scenario="random_cylinders", steps=4, progress0=798.0)
+    run_case(O.HSParams(), E=77, scenario="random_cylinders", steps=5, progress0=797.0, exact=exact)
+    run_case(O.HSParams(use_tp_net=False), E=3, scenario="random_cylinders", steps=4, progress0=798.0, exact=exact)
 
 
+@BUILDS
 @pytest.mark.parametrize("A", [1, 2])
-def test_fewer_pursuers(A):
-    run_case(O.HSParams(num_agents=A), E=128, scenario="random_cylinders", steps=10)
+def test_fewer_pursuers(A, exact):
+    run_case(O.HSParams(num_agents=A), E=128, scenario="random_cylinders", steps=10, exact=exact)
 
 
-def test_free_running_short_horizon():
-    run_case(O.HSParams(), E=256, scenario="random_cylinders", steps=10, free_run=True)
+def test_update_epoch_drives_the_smoothness_coefficient():
+    """hideandseek.py:988-991: the coefficient is recomputed from update_epoch at every reward call; here it is a device
+    scalar, so a change between two ticks must show in the very next reward and in stats.smoothness_coef."""
+    import mupe_b200
+    P = O.HSParams(use_deployment=True, smoothness_coef=0.5, smooth_lr=0.4, max_smoothness_coef=5.0)
+    E, dev = 96, torch.device("cuda:0")
+    eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    orc = O.HideAndSeekOracle(P, E)
+    tp_fn = make_tp(P)
+    g = torch.Generator().manual_seed(5)
+    init = O.sample_reset(P, E, g)
+    mask = torch.ones(E, dtype=torch.bool)
+    orc.reset(mask, init, tp_fn)
+    eng.reset(mask.to(dev), init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    done_prev = torch.zeros(E, dtype=torch.bool)
+    for t, epoch in enumerate([0, 3, 3, 20]):                 # 0.5, 1.7, 1.7, min(5, 8.5) = 5
+        orc.update_epoch = epoch
+        eng.smoothness_coef.fill_(orc.smoothness_coef())
+        act = torch.randn(E, 3, 4, generator=g)
+        push_state(eng, orc)
+        pre, v_prey = snapshot(orc), orc.v_prey
+        want = orc.step(act, done_prev, tp_fn)
+        cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=EPS[False])
+        got = eng.step_pre(act.to(dev), raw=True, reset_pid=done_prev.to(dev))
+        eng.step_post(want["tp_pred"].to(dev))
+        cond.check(f"t{t}/reward", got["reward"], want["reward"])
+        coef = eng.stats[O.S["smoothness_coef"]].cpu()
+        assert torch.allclose(coef, torch.full_like(coef, orc.smoothness_coef())), (t, coef[0].item())
+        cond.check(f"t{t}/stats/smoothness_reward", eng.stats[O.S["smoothness_reward"]], want["stats"][:, O.S["smoothness_reward"]],
+                   atol=1e-4)
+    assert abs(orc.smoothness_coef() - 5.0) < 1e-12
+    eng.close()
 
 
 def test_partial_reset_keeps_other_envs():
@@ -171,7 +221,7 @@ def test_partial_reset_keeps_other_envs():
     want = orc.reset(mask, init2, tp_fn)
     got = eng.reset(mask.to(dev), init2["drone_pos"], init2["drone_rot"], init2["target_pos"], init2["cyl_pos"])
     eng.step_post(want["tp_pred"].to(dev))
-    compare_obs(P, got, want, "partial-reset")
+    compare_obs(P, got, want, "partial-reset")   # a reset runs no evader policy and no reward: plain 1e-4
     st = pull_state(eng)
     assert_close("progress", st["progress"], orc.st["progress"])
     assert_close("stats", eng.stats.t(), orc.stats, atol=1e-4)
@@ -210,17 +260,23 @@ def test_fused_predictor_matches_torch_lstm(A, E, variant):
     for t in range(12 if E < 5000 else 3):       # > history_step so that the window is full of distinct frames
         act = torch.randn(E, A, 4, generator=g)
         push_state(eng, orc)
+        pre, v_prey = snapshot(orc), orc.v_prey
         want = orc.step(act, done_prev, tp_fn)
+        cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=EPS[False])
         eng.step_pre(act.to(dev), True, None)
         pred = torch.empty(E, 3 * P.future_step, device=dev)
         got = eng.step_post_tp(w, pred)
-        FLIP_TP = 0.02      # a flipped evader-velocity sign in one frame changes that env's whole prediction
         # the predictor itself: against torch's LSTM evaluated on the very same input window
         # pred = tanh(.) in [-1, 1]; 1e-4 relative + 5e-6 absolute (ex2/rcp.approx in the gates, ~1e-6 abs near 0)
         assert_close(f"t{t}/pred", pred, tp_fn(got["tp_input"].cpu()), rtol=1e-4, atol=5e-6)
-        assert_close(f"t{t}/pred-vs-oracle", pred, want["tp_pred"], rtol=1e-4, atol=5e-6, max_bad_frac=0.02)
-        assert_close(f"t{t}/state_self", got["state_self"], want["state_self"], max_bad_frac=FLIP_TP)
-        assert_close(f"t{t}/state_drones", got["state_drones"], want["state_drones"], max_bad_frac=FLIP_TP)
+        # against the oracle's prediction (made from the ORACLE's window): the newest frame carries the evader's velocity,
+        # and the LSTM is a nonlinear function of it -> strict comparison on the envs whose evader velocity is well
+        # conditioned this tick (all but ~1 %), none on the others
+        well = (cond.dv < 1e-6) & ~cond.edge
+        assert well.float().mean() > 0.9
+        assert_close(f"t{t}/pred-vs-oracle", pred.cpu()[well], want["tp_pred"][well], rtol=1e-4, atol=5e-6)
+        assert_close(f"t{t}/state_self", got["state_self"].cpu()[well], want["state_self"][well])
+        assert_close(f"t{t}/state_drones", got["state_drones"].cpu()[well], want["state_drones"][well])
     eng.close()
 
 
@@ -308,11 +364,13 @@ def test_host_buffer_entry_point():
     done = torch.empty(E, dtype=torch.uint8).pin_memory()
     staging = torch.empty(E, 3, 4, device=dev)
     push_state(eng, orc)
+    pre, v_prey = snapshot(orc), orc.v_prey
     want = orc.step(act.clone(), torch.zeros(E, dtype=torch.bool))
+    cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=EPS[False])
     eng._advance()
     check(lib.hs_step_host(eng._h, act.data_ptr(), 1, rew.data_ptr(), done.data_ptr(), staging.data_ptr(),
                            torch.cuda.current_stream().cuda_stream), "hs_step_host")
-    assert_close("reward", rew, want["reward"].reshape(E, 3), max_bad_frac=FLIP)
+    cond.check("reward", rew, want["reward"].reshape(E, 3))
     assert not done.any()
     eng.close()
 

@@ -29,6 +29,8 @@ def test_oracle_replays_reference_ticks(path):
         load_oracle_state(orc, G.group(f"t{t}/pre/"))
         act = G.group(f"t{t}/")["action"]
         done_prev = G.group(f"t{t}/")["done_prev"].bool()
+        if "update_epoch" in G.group(f"t{t}/"):
+            orc.update_epoch = float(G.group(f"t{t}/")["update_epoch"])
         got = orc.step(act, done_prev, tp_fn)
         for k, v in G.group(f"t{t}/out/").items():
             g = got[k].float() if k not in ("done", "tp_done") else got[k].float()

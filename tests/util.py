@@ -54,17 +54,19 @@ def pull_state(engine):
                 progress=g(L.FIELD_PROGRESS))
 
 
-def assert_close(name, got, want, rtol=1e-4, atol=1e-5, max_bad_frac=0.0):
+def assert_close(name, got, want, rtol=1e-4, atol=1e-5):
+    """Every element within atol + rtol * |want|; there is deliberately no "fraction of elements may be off" escape
+    hatch - ticks that run the evader's sign normalisation or a reward indicator use oracle/conditioning.py, which
+    derives per-env allowances from the task's own conditioning."""
     got = got.detach().cpu().float()
     want = want.detach().cpu().float().reshape(got.shape)
     err = (got - want).abs()
     tol = atol + rtol * want.abs()
     bad = err > tol
-    frac = bad.float().mean().item()
-    if frac > max_bad_frac:
+    if bad.any():
         i = int(torch.argmax((err - tol).flatten()))
         raise AssertionError(
-            f"{name}: {int(bad.sum())}/{bad.numel()} elements off (frac {frac:.2e} > {max_bad_frac:.2e}); "
+            f"{name}: {int(bad.sum())}/{bad.numel()} elements off; "
             f"worst |err|={err.flatten()[i].item():.3e} got={got.flatten()[i].item():.6e} "
             f"want={want.flatten()[i].item():.6e}")
-    return frac
+    return 0.0
