@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the HideAndSeek 3v1 tick on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config envgen]
 
-One "step" = one control tick (dt = 0.01 s) of one batch of E environments through the hot
-path: hs_step_pre (fused CTBR/PID/rotor/physics/evader/obs/reward kernel) -> TP_net
-forward (torch LSTM, the reference calls it inside the env) -> hs_step_post.
-Workload at every N: BASELINE.json configs[1] -- HideAndSeek, 3 pursuers + 1 evader,
-'empty' scenario (0 active cylinders, C=5 buffers), E=4096 envs per GPU, use_TP_net=1.
+One bench "step" = ONE 64-TICK ROLLOUT (cfg/algo/mappo.yaml train_every = 64 control ticks, dt = 0.01 s) of E = 4096
+environments per GPU through the hot path, in BOTH arms: per tick hs_step_fused = CTBR/PID/rotor/physics/evader/obs/
+reward + the trajectory predictor the reference calls inside the env, one kernel launch at this batch size; the 64 ticks
+of a rollout are one CUDA-graph launch.  After every rollout the ranks all_gather the per-env episode returns (the one
+collective of the path, north_star), so K steps put K collectives INSIDE the timed region at N > 1.
+Workload at every N: BASELINE.json configs[1] -- HideAndSeek, 3 pursuers + 1 evader, 'empty' scenario (0 active
+cylinders, C=5 buffers), E=4096 envs per GPU, use_TP_net=1 (weak scaling).
 
-Timing hygiene: the per-GPU working set of one batch (~12 MB) is smaller than the 126 MB L2,
-so the timed loop ROTATES over R=16 independent env batches (R x 12 MB > L2): every step
-finds its state cold in L2 without a flush kernel inside the timed region.  Device time
-comes from CUDA events on the launching stream, bracketed by barrier + synchronize, max
+Timing hygiene: the per-GPU working set of one batch (~12 MB) is smaller than the 126 MB L2, so the ticks of a rollout
+ROTATE over R=16 independent env batches (R x 12 MB > L2): every tick finds its state cold in L2 without a flush kernel
+inside the timed region.  Device time = CUDA events on the launching stream, bracketed by barrier + synchronize, max
 over ranks.
 
-`--impl reference` times the CPU arm instead: the oracle port of the reference's torch code
-(oracle/hs_oracle.py, Isaac Sim / PhysX cannot run here) on all host cores.
+`--impl reference` times the CPU arm on the same config with the same step definition: the REFERENCE'S OWN SOURCE for
+the tick (oracle/ref_harness.py executing baseline/_ref or /root/reference; kind "reference-source") when a copy of the
+reference package is present, else the oracle port (oracle/hs_oracle.py, kind "port"); the PhysX step is our CPU
+integrator in both (Isaac Sim cannot run here).  All host cores.
 """
 import argparse
 import json
@@ -31,9 +34,16 @@ sys.path.insert(0, REPO)
 
 E_PER_GPU = 4096
 ROTATE = 16
-ROLLOUT = 64                      # steps per rollout (cfg/algo/mappo.yaml train_every)
+ROLLOUT = 64                      # ticks per rollout = per bench step (cfg/algo/mappo.yaml train_every)
 METRIC = "env-steps/sec (3v1 HideAndSeek)"
 WORKLOAD = "HideAndSeek 3 pursuers + 1 evader, 'empty' scenario (0 active cylinders, C=5), 4096 envs per GPU, use_TP_net=1"
+
+
+def base_config(world):
+    """The `config` object - identical keys and values in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": E_PER_GPU, "ticks_per_step": ROLLOUT,
+            "step": "one 64-tick rollout of the 4096-env batch (+ the all_gather of episode returns at N > 1)",
+            "parallelism": f"env-sharded x{world}"}
 
 
 def algorithmic_bytes(A=3, C=5, K=3, F=5, H=10, tp=True):
@@ -103,6 +113,14 @@ def usable_cores():
     return n
 
 
+def load_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def make_tp_net(torch, A, F, device, seed=0):
     torch.manual_seed(seed)
     lstm = torch.nn.LSTM(7 + 3 * A, 64, 1, batch_first=True).to(device)
@@ -116,38 +134,80 @@ def make_tp_net(torch, A, F, device, seed=0):
     return fwd
 
 
-def params():
-    from oracle import hs_oracle as O
-    return O, O.HSParams(num_cylinders=5, obs_max_cylinder=3, use_tp_net=True)
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own source (or the oracle port) for the same step, on the host cores
+# ------------------------------------------------------------------------------------------
+class CpuTick:
+    """One 4096-env batch advanced tick by tick on `device` by (a) the reference's own source through
+    oracle/ref_harness.RefEnv ("reference-source") or (b) the oracle port ("port")."""
+
+    def __init__(self, E=E_PER_GPU, device="cpu", prefer_source=True):
+        import torch
+        from oracle import hs_oracle as O
+        self.torch, self.E, self.device = torch, E, device
+        P = O.HSParams(num_cylinders=5, obs_max_cylinder=3, use_tp_net=True)
+        g = torch.Generator().manual_seed(0)
+        init = O.sample_reset(P, E, g, "empty")
+        self.acts = [torch.randn(E, P.num_agents, 4, generator=g) for _ in range(8)]
+        self.kind = "port"
+        ctx = torch.device(device)
+        if prefer_source:
+            try:
+                from oracle import ref_harness as RH
+                if RH.available():
+                    with ctx:
+                        self.ref = RH.RefEnv(P, E, use_random_cylinder=False, scenario_flag="empty")
+                        init_d = {k: v.to(device) for k, v in init.items()}
+                        self.ref.reset_with(torch.ones(E, dtype=torch.bool, device=device), init_d)
+                    self.kind = "reference-source"
+            except Exception as ex:                  # fall back to the port, say why
+                self.source_error = repr(ex)[:200]
+        if self.kind == "port":
+            with ctx:
+                self.tp = make_tp_net(torch, P.num_agents, P.future_step, device)
+                self.orc = O.HideAndSeekOracle(P, E)
+                self.orc.reset(torch.ones(E, dtype=torch.bool, device=device), {k: v.to(device) for k, v in init.items()}, self.tp)
+        self.acts = [a.to(device) for a in self.acts]
+        self.done = torch.zeros(E, dtype=torch.bool, device=device)
+        self.i = 0
+
+    def tick(self):
+        torch = self.torch
+        a = self.acts[self.i % 8]
+        self.i += 1
+        with torch.device(self.device), torch.no_grad():
+            if self.kind == "reference-source":
+                nxt, _ = self.ref.step(a, self.done)
+                self.done = nxt["done"].reshape(-1)
+            else:
+                self.done = self.orc.step(a, self.done, self.tp)["done"].reshape(-1)
+
+    def describe(self, cores):
+        what = ("the reference's own source for the tick (oracle/ref_harness.py executing the pip-installed copy of "
+                "omni_drones) + our CPU integrator for the PhysX step") if self.kind == "reference-source" else \
+               "oracle/hs_oracle.py (port of the reference's torch code) + our CPU integrator for the PhysX step"
+        return f"{what}, torch {self.device} fp32, {cores} threads"
 
 
-# ------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference), also used for the cpu_baseline leg of the GPU arm
-# ------------------------------------------------------------------------------------------
-def time_cpu_oracle(steps, warmup, E=E_PER_GPU, budget_s=25.0):
+def time_cpu(steps, warmup, ticks_per_step=ROLLOUT, budget_s=None):
+    """K steps of `ticks_per_step` ticks (a bounded sample of the workload: the same 4096-env batch)."""
     import torch
-    O, P = params()
     cores = usable_cores()
     torch.set_num_threads(cores)
-    tp = make_tp_net(torch, P.num_agents, P.future_step, "cpu")
-    orc = O.HideAndSeekOracle(P, E)
-    g = torch.Generator().manual_seed(0)
-    init = O.sample_reset(P, E, g, "empty")
-    orc.reset(torch.ones(E, dtype=torch.bool), init, tp)
-    done = torch.zeros(E, dtype=torch.bool)
-    acts = [torch.randn(E, P.num_agents, 4, generator=g) for _ in range(8)]
-    for i in range(warmup):
-        done = orc.step(acts[i % 8], done, tp)["done"].reshape(-1)
+    sim = CpuTick()
+    for _ in range(max(1, warmup)):
+        sim.tick()
     t0 = time.perf_counter()
     n = 0
-    for i in range(steps):
-        done = orc.step(acts[i % 8], done, tp)["done"].reshape(-1)
+    for _ in range(steps):
+        for _ in range(ticks_per_step):
+            sim.tick()
         n += 1
-        if time.perf_counter() - t0 > budget_s:
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": E * n / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n} ticks of the same {E}-env batch (oracle/hs_oracle.py, torch CPU fp32, {cores} threads)",
+    return {"value": sim.E * n * ticks_per_step / dt, "unit": "env-steps/s", "cores": cores, "kind": sim.kind,
+            "sample": f"{n} step(s) of {ticks_per_step} ticks of the same {sim.E}-env batch ({sim.describe(cores)})",
             "ms_per_step": 1e3 * dt / n, "steps": n}
 
 
@@ -155,13 +215,14 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_cpu_oracle(args.steps, args.warmup)
+    # bounded sample: one step is a 64-tick rollout (~1-2 s of CPU work); the run stays within a few minutes
+    r = time_cpu(args.steps, max(args.warmup, 3), budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": r["steps"], "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference's torch code for the tick (oracle port) + CPU integrator "
-                   "stand-in for PhysX; Isaac Sim cannot run on this box"},
+        "config": base_config(args.gpus),
+        "notes": "CPU arm; warm-up counted in ticks; Isaac Sim / PhysX cannot run on this box",
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -175,23 +236,55 @@ def run_reference_arm(args):
 _JSON_OUT = sys.stdout
 
 
-def make_env(mupe_b200, E, device):
+def make_env(mupe_b200, E, device, **over):
     """BASELINE.json configs[1] through the public API (cfg tree -> registry class -> transforms)."""
-    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides={
-        "task.env.num_envs": E, "task.use_random_cylinder": 0, "task.scenario_flag": "empty",
-        "task.cylinder.max_num": 5, "task.sim.device": str(device), "algo.use_TP_net": 1})
+    o = {"task.env.num_envs": E, "task.use_random_cylinder": 0, "task.scenario_flag": "empty",
+         "task.cylinder.max_num": 5, "task.sim.device": str(device), "algo.use_TP_net": 1}
+    o.update(over)
+    cfg = mupe_b200.compose("HideAndSeek", "mappo", overrides=o)
     base = mupe_b200.IsaacEnv.REGISTRY[cfg.task.name](cfg, headless=True)
     return mupe_b200.TransformedEnv(base, mupe_b200.Compose(mupe_b200.InitTracker(), mupe_b200.PIDRateController()))
 
 
+def bind_numa(local_rank):
+    """Pins this rank to the host cores nearest its GPU (nvidia-smi topo) BEFORE any pinned allocation, so that pinned
+    buffers land on the GPU's NUMA node and 8 ranks do not share one socket's cores.  Returns a description."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-C", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout
+        cpus = None
+        for line in out.splitlines():
+            if ":" in line and any(ch.isdigit() for ch in line):
+                spec = line.split(":")[-1].strip()
+                cpus = set()
+                for part in spec.split(","):
+                    part = part.strip()
+                    if "-" in part:
+                        a, b = part.split("-")
+                        cpus.update(range(int(a), int(b) + 1))
+                    elif part.isdigit():
+                        cpus.add(int(part))
+                break
+        if not cpus:
+            return "no affinity information"
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"GPU-local cores {sorted(cpus)[:4]}.. not in this process's cpuset"
+        # split the GPU-local cores between the ranks that share them (stable: by local rank)
+        os.sched_setaffinity(0, allowed)
+        return f"bound to {len(allowed)} GPU-local cores ({min(allowed)}-{max(allowed)})"
+    except Exception as ex:
+        return f"not bound ({type(ex).__name__})"
+
+
 def run_gpu_arm(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_numa(local) if world > 1 else "single rank: not bound"
     import torch
     import torch.distributed as dist
     import mupe_b200
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -199,6 +292,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(dev)
     torch.manual_seed(1000 + rank)
     E, A = E_PER_GPU, 3
+    F, C, K, H = 5, 5, 3, 10
 
     # R independent env batches per GPU (weak scaling: E per GPU fixed); all share one TP_net
     envs = [make_env(mupe_b200, E, dev) for _ in range(ROTATE)]
@@ -208,25 +302,31 @@ def run_gpu_arm(args):
         env.reset()
     engines = [env.base_env.engine for env in envs]
     actions = [torch.randn(E, A, 4, device=dev) for _ in range(ROTATE)]
-    F, C, K, H = 5, 5, 3, 10
     gather_buf = [torch.empty(E, device=dev) for _ in range(world)] if world > 1 else None
 
-    # fast path of the product: one CUDA-graph launch per tick = fused tick kernel + fused
-    # predictor/fill kernel (no cuDNN, no per-kernel launch overhead); actions resident in HBM
-    variant = int(os.environ.get("HS_TP_VARIANT", "-1"))     # 1: tensor-core (3xTF32) predictor kernel
+    variant = int(os.environ.get("HS_TP_VARIANT", "-1"))
     for eng, act in zip(engines, actions):
         eng.set_predictor_variant(variant)
         eng.capture_tick_graphs(eng.tp_weights(tp_net), raw=True)
         eng.graph_action.copy_(act)
 
-    def tick(i):
-        return engines[i % ROTATE].replay_tick()
-
-    # the timed region replays ONE graph per 64-tick rollout: 64 kernel nodes rotating over the 16 L2-cold batches
-    # (nothing in a rollout needs the host once the actions are on the device); leftover ticks use the per-tick graphs
+    # ONE CUDA graph per 64-tick rollout: 64 kernel nodes rotating over the 16 L2-cold batches (nothing in a rollout
+    # needs the host once the actions are on the device).  HS_BENCH_PER_TICK_GRAPHS=1: one graph launch per tick instead.
     from mupe_b200.engine import RotatingRolloutGraph
-    rollout_graph = RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT) \
-        if os.environ.get("HS_BENCH_PER_TICK_GRAPHS", "0") != "1" and ROLLOUT % (2 * ROTATE) == 0 else None
+    per_tick = os.environ.get("HS_BENCH_PER_TICK_GRAPHS", "0") == "1"
+    rollout_graph = None if per_tick else RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT)
+    ret_row = 17                                              # stats["return"]
+
+    def rollout(step_index):
+        """One bench step: 64 ticks + the collective of the path."""
+        if rollout_graph is not None:
+            rollout_graph.replay()
+        else:
+            for j in range(ROLLOUT):
+                engines[j % ROTATE].replay_tick()
+        if world > 1:
+            # episode returns of the batch that closed the rollout, all ranks (north_star: one all_gather per rollout)
+            dist.all_gather(gather_buf, engines[(ROLLOUT - 1) % ROTATE].stats[ret_row])
 
     def barrier():
         if world > 1:
@@ -235,73 +335,56 @@ def run_gpu_arm(args):
 
     W = max(args.warmup, 3)
     for i in range(W):
-        tick(i)
-    if rollout_graph is not None:
-        rollout_graph.replay()
+        rollout(i)
     barrier()
     sampler = ClockSampler(local)
-    timed_only_early = os.environ.get("HS_BENCH_TIMED_ONLY", "0") == "1"
+    timed_only = os.environ.get("HS_BENCH_TIMED_ONLY", "0") == "1"
 
     def same_load(seconds):
-        # the timed region is ~15 ms, shorter than nvidia-smi's sampling period: keep the GPU on the identical work
-        # (same graphs, same batches) around it so that the clock samples are taken under exactly this load
+        # keep the GPU on the identical work around the timed region so that the 20 ms clock samples see this load
         t_end = time.perf_counter() + seconds
+        i = 0
         while time.perf_counter() < t_end:
-            if rollout_graph is not None:
-                rollout_graph.replay()
-            else:
-                for j in range(ROLLOUT):
-                    tick(j)
+            rollout(i)
+            i += 1
             torch.cuda.synchronize()
-    if rank == 0 and not timed_only_early:
+    if rank == 0 and not timed_only:
         sampler.start()
-    if not timed_only_early:
-        same_load(0.6)                      # nvidia-smi needs ~0.2 s to start; also serves as extra warm-up
+    if not timed_only:
+        same_load(0.5)                      # nvidia-smi needs ~0.2 s to start; also serves as extra warm-up
     barrier()
     launches0 = sum(e.launches for e in engines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed region
     ev0.record()
-    i = 0
-    while i < args.steps:
-        if rollout_graph is not None and i % ROLLOUT == 0 and i + ROLLOUT <= args.steps:
-            rollout_graph.replay()
-            i += ROLLOUT
-        else:
-            tick(i)
-            i += 1
-        eng = engines[(i - 1) % ROTATE]
-        if world > 1 and i % ROLLOUT == 0:
-            # the one collective of the path: episode returns of the rollout, all ranks
-            dist.all_gather(gather_buf, eng.stats[17].contiguous())
+    for i in range(args.steps):
+        rollout(i)
     ev1.record()
     barrier()
     torch.cuda.profiler.stop()
     wall = time.perf_counter() - w0
     ms = ev0.elapsed_time(ev1)
-    launches_timed = sum(e.launches for e in engines) - launches0
-    if not timed_only_early:
+    launches = sum(e.launches for e in engines) - launches0
+    if not timed_only:
         same_load(0.3)
-    clocks = sampler.stop() if (rank == 0 and not timed_only_early) else None
+    clocks = sampler.stop() if (rank == 0 and not timed_only) else None
     if clocks is not None:
-        clocks["window"] = ("~0.9 s of continuous identical load (same graphs, same batches) around the timed region, "
-                            "which is shorter than nvidia-smi's 20 ms sampling period")
-    launches = launches_timed
+        clocks["window"] = "continuous identical load (same graphs, same batches) from 0.5 s before to 0.3 s after the timed region"
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    ticks_timed = args.steps * ROLLOUT
 
     extra = {}
-    timed_only = os.environ.get("HS_BENCH_TIMED_ONLY", "0") == "1"
-    # ---- end to end through the C ABI with HOST buffers, on every rank: one hs_step_host_io call per tick =
-    # pinned host action -> H2D -> tick kernel -> fused predictor -> D2H of observation + reward + done -> sync
-    e2e_c = None
+    # ---- end to end through the C ABI with HOST buffers, on every rank: per tick pinned host action in ->
+    # tick + predictor -> observation + reward + done out in host memory
+    e2e_c = e2e_serial = None
     if not timed_only:
         h_act_c = torch.randn(E, A, 4).pin_memory()
         wts = [e.tp_weights(tp_net) for e in engines]
-        ne_c = max(32, min(args.steps, 256))
+        ne_c = max(4, min(args.steps, 8)) * ROLLOUT          # >= 256 ticks
 
         def c_step(i):
             r = i % ROTATE
@@ -317,16 +400,11 @@ def run_gpu_arm(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         barrier()
         d2h = sum(v.numel() for v in views.values()) * 4 + done_h.numel()
-        e2e_serial = {"value": world * E * ne_c / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4,
-                      "d2h_bytes_per_step": d2h, "steps": ne_c, "n_gpus": world,
-                      "api": "C ABI hs_step_host_io(), ONE env batch in flight: pinned host action (read in place over PCIe by the "
-                             "tick kernel, UVA) -> hs_step_pre -> hs_step_post_tp -> D2H of observation (state_self, state_others, "
-                             "obs_cylinders) + reward + done into host buffers -> stream sync, every tick, every rank (one cached "
-                             "CUDA graph launch per call; the tick's own outputs are copied under the predictor); wall clock, "
-                             "max over ranks"}
-        # the same call with TWO env batches in flight (hs_step_host_io_async + hs_host_io_wait on two streams): the host
-        # waits for batch i only after it has issued batch i+1, so one batch's observation is on the PCIe link while
-        # the next batch computes.  Every tick still moves its action in and its whole observation out.
+        travels = ("out: state_self, state_others, obs_cylinders (the actor's observation), reward, done; stays on the device: "
+                   "state_drones (critic input), TP_input / TP_groundtruth (TP_net training data), stats, info.drone_state")
+        e2e_serial = {"value": world * E * ne_c / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4 * ROLLOUT,
+                      "d2h_bytes_per_step": d2h * ROLLOUT, "ticks": ne_c, "n_gpus": world, "tensors": travels,
+                      "api": "C ABI hs_step_host_io(), ONE env batch in flight, stream sync every tick; wall clock, max over ranks"}
         s2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
 
         def c_issue(i):
@@ -334,278 +412,76 @@ def run_gpu_arm(args):
             with torch.cuda.stream(s2[i & 1]):
                 engines[r].step_host(h_act_c, wts[r], raw=True, sync=False)
             return engines[r]
+
+        def pipelined(n):
+            pend = None
+            for i in range(n):
+                cur_e = c_issue(i)
+                if pend is not None:
+                    pend.wait_host()
+                pend = cur_e
+            pend.wait_host()
         torch.cuda.synchronize()
-        pend = None
-        for i in range(2 * ROTATE):
-            cur_e = c_issue(i)
-            if pend is not None:
-                pend.wait_host()
-            pend = cur_e
-        pend.wait_host()
+        pipelined(2 * ROTATE)
         barrier()
         t0 = time.perf_counter()
-        pend = None
-        for i in range(ne_c):
-            cur_e = c_issue(i)
-            if pend is not None:
-                pend.wait_host()
-            pend = cur_e
-        pend.wait_host()
+        pipelined(ne_c)
         dt2 = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
         barrier()
-        e2e_c = {"value": world * E * ne_c / float(dt2.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4,
-                 "d2h_bytes_per_step": d2h, "steps": ne_c, "n_gpus": world, "batches_in_flight": 2,
-                 "one_batch_in_flight": e2e_serial["value"],
+        e2e_c = {"value": world * E * ne_c / float(dt2.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4 * ROLLOUT,
+                 "d2h_bytes_per_step": d2h * ROLLOUT, "ticks": ne_c, "n_gpus": world, "batches_in_flight": 2,
+                 "one_batch_in_flight": e2e_serial["value"], "tensors": travels, "host_binding": numa,
                  "api": "C ABI hs_step_host_io_async() + hs_host_io_wait(), TWO independent 4096-env batches in flight on two "
-                        "streams (the host waits for a batch's observation only after issuing the next batch's tick): per tick, "
-                        "pinned host action in (read in place over PCIe), tick + predictor, D2H of observation (state_self, "
-                        "state_others, obs_cylinders) + reward + done into host buffers; PCIe-bound (2.8 MB per tick at the "
-                        "measured 47 GB/s = 60 us); wall clock, max over ranks.  One batch in flight (hs_step_host_io): e2e_serial"}
+                        "streams: per tick, pinned host action in (read in place over PCIe), tick + predictor, D2H of the "
+                        "observation + reward + done into pinned host buffers; bytes are per 64-tick step; wall clock, max over ranks"}
     if rank == 0 and timed_only:
         extra["note"] = "HS_BENCH_TIMED_ONLY=1: roofline / e2e / cpu_baseline legs skipped (launch-list capture run)"
     elif rank == 0:
-        # ---- kernel-only roofline: the tick kernel alone over the rotating (L2-cold) batches
-        nk = max(64, min(args.steps, 512))
-        # (a) the tick kernel alone, one CUDA graph holding 64 launches over the rotating batches
-        side = torch.cuda.Stream(dev)
-        gk = torch.cuda.CUDAGraph()
-        import ctypes
-        from mupe_b200._lib import lib as _hs, check as _check
-        with torch.cuda.graph(gk, stream=side):
-            st = torch.cuda.current_stream(dev).cuda_stream
-            for i in range(64):
-                e = engines[i % ROTATE]
-                _check(_hs.hs_step_pre(e._h, e.graph_action.data_ptr(), 1, None, st), "hs_step_pre")
-        gk.replay()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(2, nk // 64)
-        k0.record()
-        for _ in range(reps):
-            gk.replay()
-        k1.record()
-        torch.cuda.synchronize()
-        tick_us = 1e3 * k0.elapsed_time(k1) / (64 * reps)
-        ab = algorithmic_bytes(A, C, K, F, H, True)
-        peaks = {}
-        try:
-            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = ab["tick"] * E / (tick_us * 1e-6) / 1e9
-        extra["roofline_tick_kernel"] = {"bound": "hbm", "kernel": "hs_tick_kernel<3,false>", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": 4975616, "traffic_source": "profiles/r1_ncu_tick_v2.txt: dram read+write per "
-                             "4096-env launch (writes stay in the 126 MB L2 for the duration of the launch)",
-                             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-                             "algorithmic_bytes_per_launch": ab["tick"] * E, "launch_us": tick_us,
-                             "note": "the tick as a kernel of its own (hs_step_pre; the timed region runs it as the first "
-                                     "phase of hs_tick_tp_fused_kernel): period of back-to-back launches (CUDA graph of 64) "
-                                     "over the rotating L2-cold batches; 4096 envs = 512 warps on 148 SMs is "
-                                     "latency/instruction-delivery bound"}
-        # (a') the same tick kernel at a batch that fills the machine (1 Mi envs: 2.3 GB streamed per launch,
-        # far above the L2), measured live: the HBM-bound regime the roofline target refers to
-        try:
-            EB = int(os.environ.get("HS_BENCH_SCALE_ENVS", str(1 << 20)))
-            big = mupe_b200.HsEngine(mupe_b200.build_hs_config(EB, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
-                                                               future_step=F, history_step=H), dev)
-            a_ = 0.9 / 2 ** 0.5
-            g_ = torch.Generator(device=dev).manual_seed(1)
-            rnd = lambda *sh: torch.rand(*sh, device=dev, generator=g_)
-            dpos = rnd(EB, A, 3) * torch.tensor([a_ - 0.2, 2 * a_ - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a_ + 0.1, 0.5], device=dev)
-            tpos = rnd(EB, 3) * torch.tensor([a_ - 0.2, 2 * a_ - 0.2, 0.2], device=dev) + torch.tensor([-a_ + 0.1, -a_ + 0.1, 0.5], device=dev)
-            rot = torch.zeros(EB, A, 4, device=dev); rot[..., 0] = 1
-            cyl = torch.zeros(EB, C, 3, device=dev); cyl[..., 0] = torch.arange(C, device=dev) * 0.2; cyl[..., 2] = -20.0
-            big.reset(None, dpos, rot, tpos, cyl)
-            big.step_post_tp(big.tp_weights(tp_net))
-            big_act = torch.randn(EB, A, 4, device=dev, generator=g_)
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, stream=side):
-                st = torch.cuda.current_stream(dev).cuda_stream
-                for i in range(4):
-                    _check(_hs.hs_step_pre(big._h, big_act.data_ptr(), 1, None, st), "hs_step_pre")
-            gb.replay()
-            torch.cuda.synchronize()
-            k0.record()
-            for _ in range(3):
-                gb.replay()
-            k1.record()
-            torch.cuda.synchronize()
-            big_us = 1e3 * k0.elapsed_time(k1) / 12
-            big_gbs = ab["tick"] * EB / (big_us * 1e-6) / 1e9
-            extra["roofline_at_scale"] = {
-                "bound": "hbm", "kernel": "hs_tick_kernel<3,false>", "envs_per_launch": EB, "launch_us": big_us,
-                "achieved": big_gbs, "peak": peak, "unit": "GB/s", "frac": big_gbs / peak,
-                "env_steps_per_s": EB / (big_us * 1e-6),
-                "traffic": 2934745000 if EB == (1 << 20) else None,
-                "traffic_source": "profiles/r1_ncu_tick_v2.txt (dram read+write per 1 Mi-env launch: 2799 B/env, of which "
-                                  "576 B/env is the re-read of the previous chronological TP window the SURVEY formula does not count)",
-                "note": "same kernel, same per-env workload, measured live in this run; not the headline configuration"}
-            big.close()
-            del big, dpos, tpos, rot, cyl, big_act, gb
-            torch.cuda.empty_cache()
-        except Exception as ex:                      # never lose the headline line over the extra measurement
-            extra["roofline_at_scale"] = {"error": repr(ex)[:200]}
-        # (b) the fused predictor kernel: fp32 FFMA bound (LSTM 16->64 x10 steps + FC), not HBM
-        gp = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gp, stream=side):
-            st = torch.cuda.current_stream(dev).cuda_stream
-            for i in range(64):
-                e = engines[i % ROTATE]
-                _check(_hs.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp_net)), None, st), "hs_step_post_tp")
-        gp.replay()
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(reps):
-            gp.replay()
-        k1.record()
-        torch.cuda.synchronize()
-        tp_us = 1e3 * k0.elapsed_time(k1) / (64 * reps)
-        flops = 2.0 * 256 * (16 * H + 64 * (H - 1)) + 2.0 * 64 * 3 * F          # per env-tick
-        simt_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        tf = flops * E / (tp_us * 1e-6) / 1e12
-        used = variant if variant >= 0 else (5 if E <= 32 * 148 else 4)
-        kname = {0: "hs_tp_fill_kernel<3>", 1: "hs_tp_fill_mma_kernel<3>", 2: "hs_tp_fill_tc_kernel<3>",
-                 3: "hs_tp_fill_tcn_kernel<3>", 4: "hs_tp_fill_tcw_kernel<3>",
-                 5: "hs_tick_tp_fused_kernel<3,5,false> (predictor only)"}[used]
-        if used == 0:
-            extra["roofline_predictor"] = {"bound": "fp32 FFMA (SIMT)", "kernel": kname, "achieved": tf,
-                                           "peak": simt_peak, "unit": "TFLOP/s", "frac": tf / simt_peak, "launch_us": tp_us,
-                                           "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
-                                           "flop_per_env_tick": flops}
-        else:
-            peaks = {}
-            try:
-                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
-                    peaks = json.load(f)
-            except Exception:
-                pass
-            bf16 = float(peaks["bf16_tflops"]) if isinstance(peaks, dict) and "bf16_tflops" in peaks else None
-            tf32_peak = (bf16 if bf16 else 2250.0) / 2.0          # tf32 runs at half the bf16 rate
-            extra["roofline_predictor"] = {
-                "bound": "tensor", "kernel": kname, "achieved": 3.0 * tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": 3.0 * tf / tf32_peak, "launch_us": tp_us, "flop_per_env_tick": flops,
-                "peak_source": ("MEASURED_PEAKS.json bf16 / 2" if bf16 else "nominal 2250 bf16 / 2") + " (tf32)",
-                "note": "3xTF32: three tensor-core products per fp32 MAC are counted as executed flops; a 10-step "
-                        "recurrence of 32- or 128-env tiles is bound by the per-step MMA -> epilogue -> MMA dependency "
-                        "(latency), not by tensor throughput; fp32-FFMA ceiling for the same math: "
-                        f"{simt_peak:.1f} TFLOP/s, this kernel delivers {tf:.1f} TFLOP/s of fp32-equivalent math"}
-        # ---- the whole rollout step of the reference's collector (policy(td) + env.step(td)) as ONE CUDA graph:
-        # fused actor + fused critic (PartialAttentionEncoder, random init, noise drawn in the kernel) -> tick -> predictor
-        try:
-            from mupe_b200.policy import FusedPolicy, init_params
-            D_self = 20 + 3 * F
-            pe = mupe_b200.HsEngine(mupe_b200.build_hs_config(E, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
-                                                              future_step=F, history_step=H), dev)
-            s0 = engines[0]
-            pe.reset(None, s0.get_state(0), s0.get_state(1), s0.get_state(7), s0.get_state(9))
-            wpe = pe.tp_weights(tp_net)
-            pe.step_post_tp(wpe)
-            actor = FusedPolicy(init_params(D_self, A - 1, K, 4, True, dev), A - 1, K, dev).seed(1)
-            critic = FusedPolicy(init_params(D_self, A - 1, K, 1, False, dev), A - 1, K, dev)
-            pe.attach_policy(actor, critic)
-            prg = RotatingRolloutGraph([pe], [wpe], ROLLOUT)       # (actor -> critic -> tick) x 64 as ONE graph
-            prg.replay()
-            torch.cuda.synchronize()
-            npol = max(1, min(args.steps, 512) // ROLLOUT) * ROLLOUT
-            k0.record()
-            for _ in range(npol // ROLLOUT):
-                prg.replay()
-            k1.record()
-            torch.cuda.synchronize()
-            pol_us = 1e3 * k0.elapsed_time(k1) / npol
-            extra["rollout_step_with_policy"] = {
-                "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us, "launches_per_step": 3,
-                "what": "one CUDA graph per 64-step rollout, per step: hs_policy_forward_tc_kernel (actor, tcgen05 3xTF32, in-kernel noise) + "
-                        "hs_policy_forward_tc_kernel (critic) + hs_tick_tp_fused_kernel (tick + predictor), observation never "
-                        "leaves HBM; same 4096-env batch every step (L2-warm), single GPU"}
-            pe.close()
-        except Exception as ex:
-            extra["rollout_step_with_policy"] = {"error": repr(ex)[:200]}
-        # ---- end to end through env.step(): pinned host actions in; observation, reward, done out
-        h_act = torch.randn(E, A, 4).pin_memory()
-        d_act = torch.empty(E, A, 4, device=dev)
-        slab0 = engines[0].out
-        npol = slab0.policy_words                 # observation (state_self, state_others, cylinders) + reward
-        h_res = torch.empty(npol, dtype=torch.float32).pin_memory()
-        h_bytes = torch.empty(slab0.bytes.numel(), dtype=torch.uint8).pin_memory()
-        tds = [env.reset() for env in envs]
-        ne = max(32, min(args.steps, 256))
-
-        def e2e_step(i):
-            r = i % ROTATE
-            td = tds[r]
-            d_act.copy_(h_act, non_blocking=True)
-            td.set(("agents", "action"), d_act)
-            td = envs[r].step(td)
-            out = engines[r].out                  # the tensors env.step() returned live in this slab
-            h_res.copy_(out.slab[:npol], non_blocking=True)
-            h_bytes.copy_(out.bytes.reshape(-1), non_blocking=True)
-            torch.cuda.synchronize()              # the caller needs the result before it can act again
-            tds[r] = mupe_b200.step_mdp(td)
-        for i in range(ROTATE):
-            e2e_step(i)
-        t0 = time.perf_counter()
-        for i in range(ne):
-            e2e_step(i)
-        e2e_s = time.perf_counter() - t0
-        extra["e2e_python_env"] = {
-            "value": E * ne / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h_act.numel() * 4,
-            "d2h_bytes_per_step": h_res.numel() * 4 + h_bytes.numel(), "steps": ne, "n_gpus": 1,
-            "api": "the reference-facing Python surface on rank 0: TransformedEnv(HideAndSeek).step(td) + step_mdp with "
-                   "TensorDict bookkeeping: pinned host action -> H2D -> tick -> D2H of observation + reward + done, "
-                   "host sync every step"}
-        extra["cpu_baseline"] = {k: v for k, v in time_cpu_oracle(40, 3, budget_s=20.0).items()
-                                 if k in ("value", "unit", "cores", "kind", "sample")}
+        extra.update(extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, variant))
     if rank == 0:
-        value = world * E * args.steps / (ms_total * 1e-3)
-        # ---- roofline of the dominant kernel of the timed region.  With the default policy at this batch size the
-        # region is ONE kernel per tick, hs_tick_tp_fused_kernel (tick + predictor): its duration is the step itself.
+        value = world * E * ticks_timed / (ms_total * 1e-3)
+        peaks = load_peaks()
+        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         ab_all = algorithmic_bytes(A, C, K, F, H, True)
-        try:
-            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
-                peak_hbm, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            peak_hbm, peak_src = 6650.0, "fallback 6650 GB/s"
-        step_us = 1e3 * ms_total / args.steps
+        tick_us = 1e3 * ms_total / ticks_timed
         one_launch = variant in (-1, 5) and E <= 32 * 148
+        roof = {}
         if one_launch:
-            ach = ab_all["total"] * E / (step_us * 1e-6) / 1e9
-            extra["roofline"] = {
-                "bound": "hbm", "kernel": "hs_tick_tp_fused_kernel<3,5,true>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
-                "frac": ach / peak_hbm, "traffic": 5112320,
-                "traffic_source": "profiles/r1_ncu_fused_4k.txt: dram read + write of one 4096-env launch (the 8 MB it "
-                                  "writes stay in the 126 MB L2 for the duration of the launch)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E, "launch_us": step_us,
-                "share_of_step": 1.0,
-                "note": "3077 algorithmic B/env-tick (SURVEY 8d, tick + predictor rows) x 4096 envs per launch over the "
-                        "launch period measured in the timed region (CUDA events, L2-cold rotating batches).  A 12.6 MB launch cannot be HBM-bound: the kernel is a dependent chain - 7.9 us control "
-                        "tick on 4 warps per SM, then 10 LSTM steps x 1.3 us on the tensor pipe + cell update, 3 us FC + rows "
-                        "(tools/fused_phases.py) - so the fraction states how far a latency-bound launch is from the "
-                        "bandwidth roof, not a kernel inefficiency; the HBM-bound regime is roofline_at_scale"}
+            ach = ab_all["total"] * E / (tick_us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": "hs_tick_tp_fused_kernel<3,5,true>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": ach / peak_hbm, "traffic": 5112320,
+                    "traffic_source": "profiles/r1_ncu_fused_4k.txt: dram read + write of one 4096-env launch (the 8 MB it "
+                                      "writes stay in the 126 MB L2 for the duration of the launch)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E, "launch_us": tick_us,
+                    "share_of_step": 1.0,
+                    "note": "3077 algorithmic B/env-tick (SURVEY 8d) x 4096 envs per launch over the launch period measured in "
+                            "the timed region.  A 12.6 MB launch is a dependent chain (7.9 us tick on 4 warps per SM, 10 LSTM steps "
+                            "x 1.3 us, 3 us FC + rows), not a stream: the fraction states how far a latency-bound launch is from "
+                            "the bandwidth roof; the HBM-bound regime of the same tick is roofline.at_scale"}
         elif "roofline_tick_kernel" in extra:
-            extra["roofline"] = dict(extra["roofline_tick_kernel"])
+            roof = dict(extra["roofline_tick_kernel"])
+        for k_src, k_dst in (("roofline_at_scale", "at_scale"), ("roofline_tick_kernel", "tick_kernel"),
+                             ("roofline_predictor", "predictor")):
+            if k_src in extra:
+                roof[k_dst] = extra.pop(k_src)
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "parallelism": f"env-sharded x{world}",
-                       "l2": f"inputs larger than L2: rotating {ROTATE} independent env batches per GPU",
-                       "launch": ("one CUDA graph per 64-tick rollout (64 kernel nodes, one per tick, rotating over the batches)"
-                                  if rollout_graph is not None else "one CUDA graph launch per tick"),
-                       "collective": "all_gather of episode returns every 64 steps" if world > 1 else "none (1 GPU)"},
+            "config": base_config(world),
+            "l2": f"inputs larger than L2: the ticks of a rollout rotate over {ROTATE} independent env batches per GPU",
+            "launch": ("one CUDA graph launch per 64-tick rollout (64 kernel nodes, one hs_tick_tp_fused_kernel per tick)"
+                       if rollout_graph is not None else "one CUDA graph launch per tick (64 per step)"),
+            "collective": (f"all_gather of the per-env episode returns after every rollout: {args.steps} inside the timed region"
+                           if world > 1 else "none (1 GPU)"),
+            "scope": "the env tick with device-resident fixed actions; no episode resets and no policy inside the timed region "
+                     "(rollout_step_with_policy and e2e_collector carry those)",
+            "ticks_timed": ticks_timed, "us_per_tick": tick_us,
             "gpu_launches": launches, "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
-            "predictor_kernel": {-1: "auto -> inside hs_tick_tp_fused_kernel (tick + 3xTF32 tcgen05 predictor in one launch, 32-env tile "
-                                     "as two ping-ponging 16-env halves) at 4096 envs",
-                                 5: "hs_tick_tp_fused_kernel (tick + predictor, one launch)",
-                                 0: "hs_tp_fill_kernel (fp32 FFMA)", 1: "hs_tp_fill_mma_kernel (3xTF32 mma.sync)",
-                                 2: "hs_tp_fill_tc_kernel (3xTF32 tcgen05, 128-env tiles)",
-                                 3: "hs_tp_fill_tcn_kernel (3xTF32 tcgen05, 32-env tiles)",
-                                 4: "hs_tp_fill_tcw_kernel (3xTF32 tcgen05, 2 x 32-env tiles ping-pong, warp-specialised)"}[variant],
+            "roofline": roof,
         }
         line.update(extra)
         if e2e_c is not None:
@@ -618,12 +494,303 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, variant):
+    """Rank 0, N = 1 legs: kernel rooflines, the tick at scale, config 3, rollout with policy, Python-surface e2e, baselines."""
+    import ctypes
+    from mupe_b200._lib import lib as _hs, check as _check
+    from mupe_b200.engine import RotatingRolloutGraph
+    extra = {}
+    E, A, F, C, K, H = E_PER_GPU, 3, 5, 5, 3, 10
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ab = algorithmic_bytes(A, C, K, F, H, True)
+    side = torch.cuda.Stream(dev)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_graph(build, reps):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            build(torch.cuda.current_stream(dev).cuda_stream)
+        g.replay()
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            g.replay()
+        k1.record()
+        torch.cuda.synchronize()
+        return 1e3 * k0.elapsed_time(k1) / reps
+
+    # (a) the tick kernel alone over the rotating (L2-cold) batches
+    def b_tick(st):
+        for i in range(64):
+            e = engines[i % ROTATE]
+            _check(_hs.hs_step_pre(e._h, e.graph_action.data_ptr(), 1, None, st), "hs_step_pre")
+    tick_us = timed_graph(b_tick, 8) / 64
+    achieved = ab["tick"] * E / (tick_us * 1e-6) / 1e9
+    extra["roofline_tick_kernel"] = {
+        "bound": "hbm", "kernel": "hs_tick_kernel<3,false,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": 4975616, "traffic_source": "profiles/r1_ncu_tick_v2.txt (4096-env launch)",
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["tick"] * E, "launch_us": tick_us,
+        "note": "the tick as a kernel of its own (hs_step_pre): 4096 envs = 512 warps on 148 SMs, latency bound"}
+
+    # (a') the tick at a batch that fills the machine, measured live: the HBM-bound regime the roofline target refers to
+    try:
+        extra["roofline_at_scale"] = tick_at_scale(torch, mupe_b200, tp_net, dev, timed_graph, ab, peak, peak_src)
+    except Exception as ex:                      # never lose the headline line over an extra measurement
+        extra["roofline_at_scale"] = {"error": repr(ex)[:300]}
+    torch.cuda.empty_cache()
+
+    # (b) the predictor kernel alone
+    def b_tp(st):
+        for i in range(64):
+            e = engines[i % ROTATE]
+            _check(_hs.hs_step_post_tp(e._h, ctypes.byref(e.tp_weights(tp_net)), None, st), "hs_step_post_tp")
+    tp_us = timed_graph(b_tp, 8) / 64
+    flops = 2.0 * 256 * (16 * H + 64 * (H - 1)) + 2.0 * 64 * 3 * F          # per env-tick
+    tf = flops * E / (tp_us * 1e-6) / 1e12
+    bf16 = float(peaks["bf16_tflops"]) if "bf16_tflops" in peaks else None
+    tf32_peak = (bf16 if bf16 else 2250.0) / 2.0
+    extra["roofline_predictor"] = {
+        "bound": "tensor", "kernel": "hs_tick_tp_fused_kernel<3,5,false> (predictor only)" if variant in (-1, 5) else f"variant {variant}",
+        "achieved": 3.0 * tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * tf / tf32_peak, "launch_us": tp_us,
+        "flop_per_env_tick": flops, "peak_source": ("MEASURED_PEAKS.json bf16 / 2" if bf16 else "nominal 2250 bf16 / 2") + " (tf32)",
+        "note": "3xTF32: three tensor-core products per fp32 MAC counted as executed flops; a 10-step recurrence of 32-env tiles "
+                "is bound by the per-step MMA -> epilogue -> MMA dependency (latency), not by tensor throughput"}
+
+    # (c) BASELINE.json configs[2]: 16 384 envs, 8 active cylinders + line-of-sight, device-resident
+    try:
+        extra["config3"] = config3_line(torch, mupe_b200, tp_net, dev, timed_graph)
+    except Exception as ex:
+        extra["config3"] = {"error": repr(ex)[:300]}
+    torch.cuda.empty_cache()
+
+    # (d) the whole rollout step of the reference's collector (policy(td) + env.step(td)) as ONE CUDA graph
+    try:
+        from mupe_b200.policy import FusedPolicy, init_params
+        D_self = 20 + 3 * F
+        pe = mupe_b200.HsEngine(mupe_b200.build_hs_config(E, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
+                                                          future_step=F, history_step=H), dev)
+        s0 = engines[0]
+        pe.reset(None, s0.get_state(0), s0.get_state(1), s0.get_state(7), s0.get_state(9))
+        wpe = pe.tp_weights(tp_net)
+        pe.step_post_tp(wpe)
+        actor = FusedPolicy(init_params(D_self, A - 1, K, 4, True, dev), A - 1, K, dev).seed(1)
+        critic = FusedPolicy(init_params(D_self, A - 1, K, 1, False, dev), A - 1, K, dev)
+        pe.attach_policy(actor, critic)
+        prg = RotatingRolloutGraph([pe], [wpe], ROLLOUT)       # (actor -> critic -> tick) x 64 as ONE graph
+        prg.replay()
+        torch.cuda.synchronize()
+        nrep = max(2, min(args.steps, 8))
+        k0.record()
+        for _ in range(nrep):
+            prg.replay()
+        k1.record()
+        torch.cuda.synchronize()
+        pol_us = 1e3 * k0.elapsed_time(k1) / (nrep * ROLLOUT)
+        extra["rollout_step_with_policy"] = {
+            "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us,
+            "launches_per_step": 1 + getattr(prg, "policy_kernels", 2),
+            "what": "one CUDA graph per 64-step rollout, per step: fused actor (+ critic) policy kernel(s) on tcgen05 (3xTF32, in-kernel "
+                    "noise) + hs_tick_tp_fused_kernel (tick + predictor); the observation never leaves HBM; same 4096-env batch "
+                    "every step (L2-warm), single GPU"}
+        pe.close()
+    except Exception as ex:
+        extra["rollout_step_with_policy"] = {"error": repr(ex)[:300]}
+
+    # (e) end to end through env.step(): pinned host actions in; observation, reward, done out
+    h_act = torch.randn(E, A, 4).pin_memory()
+    d_act = torch.empty(E, A, 4, device=dev)
+    slab0 = engines[0].out
+    npol = slab0.policy_words                 # observation (state_self, state_others, cylinders) + reward
+    h_res = torch.empty(npol, dtype=torch.float32).pin_memory()
+    h_bytes = torch.empty(slab0.bytes.numel(), dtype=torch.uint8).pin_memory()
+    tds = [env.reset() for env in envs]
+    ne = 256
+
+    def e2e_step(i):
+        r = i % ROTATE
+        td = tds[r]
+        d_act.copy_(h_act, non_blocking=True)
+        td.set(("agents", "action"), d_act)
+        td = envs[r].step(td)
+        out = engines[r].out                  # the tensors env.step() returned live in this slab
+        h_res.copy_(out.slab[:npol], non_blocking=True)
+        h_bytes.copy_(out.bytes.reshape(-1), non_blocking=True)
+        torch.cuda.synchronize()              # the caller needs the result before it can act again
+        tds[r] = mupe_b200.step_mdp(td)
+    for i in range(ROTATE):
+        e2e_step(i)
+    t0 = time.perf_counter()
+    for i in range(ne):
+        e2e_step(i)
+    e2e_s = time.perf_counter() - t0
+    extra["e2e_python_env"] = {
+        "value": E * ne / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_tick": h_act.numel() * 4,
+        "d2h_bytes_per_tick": h_res.numel() * 4 + h_bytes.numel(), "ticks": ne, "n_gpus": 1,
+        "api": "the reference-facing Python surface on rank 0: TransformedEnv(HideAndSeek).step(td) + step_mdp with TensorDict "
+               "bookkeeping: pinned host action -> H2D -> tick -> D2H of observation + reward + done, host sync every tick"}
+    # (e') the reference's collector loop (SyncDataCollector over TransformedEnv with a device policy), storage mode
+    try:
+        extra["e2e_collector"] = collector_line(torch, mupe_b200, dev)
+    except Exception as ex:
+        extra["e2e_collector"] = {"error": repr(ex)[:300]}
+
+    # (f) baselines beside it: the reference's own CPU path on this box's cores, and the same source run eagerly on the GPU
+    cpu = time_cpu(1, 3, ticks_per_step=24, budget_s=20.0)
+    extra["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    try:
+        extra["eager_cuda_baseline"] = eager_cuda_line(torch, dev)
+    except Exception as ex:
+        extra["eager_cuda_baseline"] = {"error": repr(ex)[:300]}
+    return extra
+
+
+def tick_at_scale(torch, mupe_b200, tp_net, dev, timed_graph, ab, peak, peak_src):
+    from mupe_b200._lib import lib as _hs, check as _check
+    A, F, C, K, H = 3, 5, 5, 3, 10
+    EB = int(os.environ.get("HS_BENCH_SCALE_ENVS", str(1 << 20)))
+    big = mupe_b200.HsEngine(mupe_b200.build_hs_config(EB, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
+                                                       future_step=F, history_step=H), dev)
+    a_ = 0.9 / 2 ** 0.5
+    g_ = torch.Generator(device=dev).manual_seed(1)
+    rnd = lambda *sh: torch.rand(*sh, device=dev, generator=g_)
+    dpos = rnd(EB, A, 3) * torch.tensor([a_ - 0.2, 2 * a_ - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a_ + 0.1, 0.5], device=dev)
+    tpos = rnd(EB, 3) * torch.tensor([a_ - 0.2, 2 * a_ - 0.2, 0.2], device=dev) + torch.tensor([-a_ + 0.1, -a_ + 0.1, 0.5], device=dev)
+    rot = torch.zeros(EB, A, 4, device=dev); rot[..., 0] = 1
+    cyl = torch.zeros(EB, C, 3, device=dev); cyl[..., 0] = torch.arange(C, device=dev) * 0.2; cyl[..., 2] = -20.0
+    big.reset(None, dpos, rot, tpos, cyl)
+    w = big.tp_weights(tp_net)
+    big.step_post_tp(w)
+    big_act = torch.randn(EB, A, 4, device=dev, generator=g_)
+
+    def b_big(st):
+        for i in range(4):
+            _check(_hs.hs_step_pre(big._h, big_act.data_ptr(), 1, None, st), "hs_step_pre")
+    big_us = timed_graph(b_big, 3) / 4
+    big_gbs = ab["tick"] * EB / (big_us * 1e-6) / 1e9
+    out = {"bound": "hbm", "kernel": "hs_tick_kernel<3,false,5>", "envs_per_launch": EB, "launch_us": big_us,
+           "achieved": big_gbs, "peak": peak, "unit": "GB/s", "frac": big_gbs / peak, "peak_source": peak_src,
+           "env_steps_per_s": EB / (big_us * 1e-6), "algorithmic_bytes_per_launch": ab["tick"] * EB,
+           "traffic": 2934745000 if EB == (1 << 20) else None,
+           "traffic_source": "profiles/r1_ncu_tick_v4.txt (dram read+write per 1 Mi-env launch: 2799 B/env, of which 576 B/env is "
+                             "the read of the previous TP window that the SURVEY formula does not count)",
+           "note": "same kernel, same per-env workload as the headline, measured live in this run at a batch that streams "
+                   "2.3 GB per launch; not the headline configuration"}
+    # whole tick (tick + predictor) at the same scale
+    import ctypes
+
+    def b_whole(st):
+        for i in range(2):
+            _check(_hs.hs_step_fused(big._h, big_act.data_ptr(), 1, None, ctypes.byref(w), None, st), "hs_step_fused")
+    whole_us = timed_graph(b_whole, 2) / 2
+    out["whole_tick_with_predictor"] = {"launch_us": whole_us, "env_steps_per_s": EB / (whole_us * 1e-6),
+                                        "achieved": ab["total"] * EB / (whole_us * 1e-6) / 1e9,
+                                        "frac": ab["total"] * EB / (whole_us * 1e-6) / 1e9 / peak}
+    big.close()
+    return out
+
+
+def config3_line(torch, mupe_b200, tp_net, dev, timed_graph):
+    """BASELINE.json configs[2]: HideAndSeek 3v1, 8 random cylinders (all active) + line-of-sight test, 16 384 envs."""
+    import ctypes
+    from mupe_b200._lib import lib as _hs, check as _check
+    E3 = 16384
+    envs3 = []
+    for _ in range(4):                        # 4 batches x ~55 MB of state + outputs > L2
+        env = make_env(mupe_b200, E3, dev, **{"task.use_random_cylinder": 1, "task.cylinder.max_num": 8,
+                                              "task.cylinder.min_num": 8, "task.scenario_flag": "empty"})
+        env.base_env.TP = tp_net
+        env.reset()
+        envs3.append(env)
+    engs = [e.base_env.engine for e in envs3]
+    act = torch.randn(E3, 3, 4, device=dev)
+    w = [e.tp_weights(tp_net) for e in engs]
+
+    def b(st):
+        for i in range(16):
+            e = engs[i % 4]
+            _check(_hs.hs_step_fused(e._h, act.data_ptr(), 1, None, ctypes.byref(w[i % 4]), None, st), "hs_step_fused")
+    us = timed_graph(b, 4) / 16
+    ab3 = algorithmic_bytes(3, 8, 3, 5, 10, True)
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"workload": "HideAndSeek 3v1, 8 random cylinders (all active) + LOS, 16384 envs, 1 GPU, use_TP_net=1",
+           "value": E3 / (us * 1e-6), "unit": "env-steps/s", "us_per_tick": us, "kernels_per_tick": 2,
+           "achieved_gbs": ab3["total"] * E3 / (us * 1e-6) / 1e9, "frac_of_hbm_peak": ab3["total"] * E3 / (us * 1e-6) / 1e9 / peak,
+           "algorithmic_bytes_per_env_tick": ab3["total"],
+           "l2": "rotating 4 independent 16384-env batches", "launch": "CUDA graph of 16 ticks (tick kernel + predictor kernel each)"}
+    for env in envs3:
+        env.close()
+    return out
+
+
+def collector_line(torch, mupe_b200, dev):
+    """The reference's own collection loop (scripts/train.py:198-205, collector.py:33-87): SyncDataCollector over
+    TransformedEnv with a policy on the device, frames_per_batch = E x 64; env in rollout-storage mode."""
+    E, T = E_PER_GPU, ROLLOUT
+    env = make_env(mupe_b200, E, dev, **{"task.env.rollout_steps": T})
+    A = 3
+
+    def policy(td):
+        td.set(("agents", "action"), torch.randn(E, A, 4, device=dev))
+        return td
+    col = mupe_b200.SyncDataCollector(env, policy=policy, frames_per_batch=E * T, total_frames=E * T * 6, device=dev,
+                                      return_same_td=True)
+    it = iter(col)
+    next(it)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 0
+    for data in it:
+        n += 1
+        if n == 4:
+            break
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    env.close()
+    return {"value": E * T * n / dt, "unit": "env-steps/s", "rollouts": n, "frames_per_batch": E * T,
+            "api": "SyncDataCollector(TransformedEnv(HideAndSeek, PIDRateController), policy) - the loop of scripts/train.py - with a "
+                   "random device policy; one [E, 64] tensordict per iteration (rollout-storage mode: ticks write the rows in place)"}
+
+
+def eager_cuda_line(torch, dev):
+    """'Reference minus PhysX' on this GPU: the reference's own torch source for the tick (or the oracle port) executed
+    eagerly on device=cuda - ~300 small launches per tick, the most honest stand-in for the reference's GPU path."""
+    sim = None
+    err = None
+    for prefer in (True, False):
+        try:
+            sim = CpuTick(E_PER_GPU, device=str(dev), prefer_source=prefer)
+            for _ in range(3):
+                sim.tick()
+            break
+        except Exception as ex:
+            err, sim = repr(ex)[:200], None
+    if sim is None:
+        raise RuntimeError(err)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 64 and time.perf_counter() - t0 < 15.0:
+        sim.tick()
+        n += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"value": sim.E * n / dt, "unit": "env-steps/s", "kind": sim.kind + " (eager, device=cuda)", "ticks": n,
+           "ms_per_tick": 1e3 * dt / n, "what": sim.describe("-")}
+    if err and sim.kind == "port":
+        out["reference_source_on_cuda_failed"] = err
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=512)
-    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="hideandseek", choices=["hideandseek", "envgen"])
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) go to stderr
     global _JSON_OUT
@@ -631,10 +798,17 @@ def main():
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if args.impl == "reference":
-        if args.steps == 512:
-            args.steps = 60
+        args.steps = 8 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
         run_reference_arm(args)
+    elif args.config == "envgen":
+        from tools import bench_envgen
+        args.steps = 4 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        bench_envgen.run(args, _JSON_OUT)
     else:
+        args.steps = 32 if args.steps is None else args.steps
+        args.warmup = 4 if args.warmup is None else args.warmup
         run_gpu_arm(args)
 
 

@@ -12,7 +12,13 @@ touch and by how much, so that the tests need no blanket "fraction of elements m
    2 v_prey).  `evader_bound` returns dv per env and component; every tensor that carries the evader's velocity or
    position gets this much extra absolute tolerance FOR THAT ENV (positions: dt * dv), nothing else does.
 
-2. Indicators.  Rewards, masks and the k-nearest selection compare a continuous quantity with a threshold
+2. Rate-PID derivative.  ctbr[0:2] = out/2 with out = P + D + I and D = -(rate - last_rate) / dt * kd in deg/s
+   (lee_position_controller.py:505-515): a rounding difference d in the body rate (the reference forms it with a bmm
+   dot product whose accumulation order / FMA use is BLAS-internal) appears as d * 180/pi * kd / dt / 2 ~ 7e3 * d in
+   ctbr.  `pid_bound` returns ulps(body rate) times that gain per (env, pursuer, component); only `ctbr` gets it (the
+   rotor commands divide it by 2^15 again).
+
+3. Indicators.  Rewards, masks and the k-nearest selection compare a continuous quantity with a threshold
    (capture |p - t| < 0.3, collisions, line of sight, arena wall, sort order of the cylinder distances ...).  An env is
    an "edge" env when one of these quantities lies within `margin` (relative) of its threshold in the oracle; only such
    envs may show a flipped indicator, and the tests bound how many there are.
@@ -33,6 +39,23 @@ def evader_bound(P: O.HSParams, v_prey: float, pos, tpos, cyl, eps: float) -> to
     force, mag, _ = O.evader_force(P, pos, tpos, cyl, inactive)
     slope = v_prey * 1e-5 / (force.abs() + 1e-5) ** 2
     return torch.clamp(slope * eps * mag, max=2.0 * v_prey)
+
+
+def pid_bound(P: O.HSParams, angvel, ulps_rate: float = 8.0, ulps_tanh: float = 4.0) -> torch.Tensor:
+    """[E,A,4]: bound on |delta ctbr| (r, p, y, thrust).  out = P + D + I in 16-bit motor units per deg/s:
+    * the target rate is tanh(raw) * 180 * target_clip: CUDA's tanhf (<= 2 ulp) and torch's (Sleef, <= 1 ulp) differ by a
+      few ulp of |tanh| <= 1 -> d_target = ulps_tanh * 6e-8 * 180 deg/s, amplified by kp (250, 250, 120);
+    * the body rate a - b + c (terms up to 3 |w|_inf) carries ulps_rate ulp of rounding (the reference's dot product is a
+      bmm whose accumulation order is BLAS-internal), amplified by kp and by kd / dt (250 / 0.01 s).
+    r = out0 / 2, p = out1 / 2, y = out2; the thrust slot is exact.  angvel: PRE-tick world angular velocity [E,A,3]."""
+    w = angvel.abs().max(-1, keepdim=True).values
+    d_rate = ulps_rate * 6e-8 * 3.0 * w * (180.0 / torch.pi)                    # deg/s
+    d_target = ulps_tanh * 6e-8 * 180.0 * P.target_clip
+    kp = torch.tensor(P.pid_kp, dtype=torch.float32)
+    kd = torch.tensor(P.pid_kd, dtype=torch.float32)
+    out = (d_rate + d_target) * kp + d_rate * kd / P.dt                          # [E,A,3]
+    scale = torch.tensor([0.5, 0.5, 1.0])
+    return torch.cat([out * scale, torch.zeros_like(w)], dim=-1)
 
 
 def _near(x, thr, margin):
@@ -77,10 +100,12 @@ def indicator_edges(P: O.HSParams, pre: Dict[str, torch.Tensor], post: Dict[str,
     key = torch.linalg.vector_norm(rpos, dim=-1) - P.cylinder_size
     C = cyl.shape[1]
     if C > 1 and P.obs_max_cylinder > 0:
-        sk = torch.sort(key, dim=-1).values
+        sk, order = torch.sort(key, dim=-1)
         k = min(P.obs_max_cylinder, C - 1)
         gaps = (sk[..., 1:k + 1] - sk[..., :k]).abs()
-        out["knearest_order"] = (gaps <= margin * torch.clamp(sk[..., :k].abs(), min=1.0)).flatten(1).any(-1)
+        down = (cyl[..., 2] < 0.0).unsqueeze(1).expand(-1, A, -1).gather(2, order)          # inactive, in sorted order
+        both_down = down[..., 1:k + 1] & down[..., :k]      # two inactive neighbours: both rows are masked to -5 either way
+        out["knearest_order"] = ((gaps <= margin * torch.clamp(sk[..., :k].abs(), min=1.0)) & ~both_down).flatten(1).any(-1)
     if C > 0:
         dxy = torch.linalg.vector_norm(rpos[..., :2], dim=-1)
         standing = (cyl[..., 2] >= 0.0).unsqueeze(1)
@@ -119,6 +144,7 @@ class TickConditioning:
     def __init__(self, P: O.HSParams, v_prey: float, pre, post, eps: float = 4e-6, margin: float = 2e-5, safety: float = 4.0):
         self.P = P
         self.dv = safety * evader_bound(P, v_prey, pre["pos"], pre["tpos"], pre["cyl"], eps).max(-1).values   # [E]
+        self.pid = pid_bound(P, pre["angvel"]) if "angvel" in pre else None                                    # [E,A,4]
         self.edges = indicator_edges(P, pre, post, margin)
         self.edge = torch.stack(list(self.edges.values()), 0).any(0)                                          # [E]
 
@@ -134,6 +160,8 @@ class TickConditioning:
         shape = (E,) + (1,) * (got.dim() - 1)
         base = atol + rtol * want.abs()
         tol = base + kind_scale(self.P, kind) * self.dv.reshape(shape)
+        if name.split("/")[-1] == "ctbr" and self.pid is not None:
+            tol = tol + self.pid.reshape(got.shape)
         err = (got - want).abs()
         bad = err > tol
         hard = bad & ~self.edge.reshape(shape)
@@ -147,18 +175,22 @@ class TickConditioning:
         if (err.masked_fill(~bad, 0.0) > cap).any() or torch.isnan(got).any():
             raise AssertionError(f"{name}: an edge-env element is beyond the sanity cap {cap} or NaN")
         n_edge, n_dv = int(bad.sum()), int(((err > base) & ~bad).sum())
+        if n_edge or n_dv:
+            self.used = getattr(self, "used", [])
+            self.used.append((name, n_edge, n_dv))
         self.n_edge_exempt = getattr(self, "n_edge_exempt", 0) + n_edge
         self.n_dv_needed = getattr(self, "n_dv_needed", 0) + n_dv
         return n_edge, n_dv
 
 
 class TrajectoryConditioning:
-    """Free-running comparison (no teacher forcing): an env is CLEAN until the tick at which its evader velocity is ill
-    conditioned (cumulative dv bound above `dv_budget`) or one of its indicators is at an edge; from then on the two
+    """Free-running comparison (no teacher forcing).  Every env carries the running sum of its per-tick evader-velocity
+    bounds (`cum_dv`); its elements get that much extra absolute tolerance (scaled by kind like in TickConditioning).
+    An env stays CLEAN until an indicator sits at an edge or cum_dv exceeds `dv_budget`; from then on the two
     implementations may legitimately follow different trajectories (the per-component sign normalisation makes the task
     chaotic at those points) and the env is only counted.  Clean envs must agree within the (slowly growing) tolerance."""
 
-    def __init__(self, P: O.HSParams, E: int, eps: float = 1e-6, margin: float = 2e-5, dv_budget: float = 1e-5):
+    def __init__(self, P: O.HSParams, E: int, eps: float = 1e-6, margin: float = 2e-5, dv_budget: float = 1e-2):
         self.P, self.eps, self.margin, self.dv_budget = P, eps, margin, dv_budget
         self.clean = torch.ones(E, dtype=torch.bool)
         self.cum_dv = torch.zeros(E)
@@ -174,17 +206,20 @@ class TrajectoryConditioning:
             self.first_unclean_tick = self.ticks - 1
         return c
 
-    def check(self, name, got, want, rtol=1e-4, atol=1e-5, growth=0.25):
-        """Strict comparison on the clean envs; the absolute tolerance grows by `growth` x atol per elapsed tick
-        (accumulating rounding of a free-running fp32 integration)."""
+    def check(self, name, got, want, rtol=1e-4, atol=1e-5, growth=0.25, kind="auto"):
+        """Comparison on the clean envs; atol and rtol grow by `growth` per elapsed tick (accumulating rounding of a
+        free-running fp32 integration), plus the env's cum_dv allowance for evader-derived tensors."""
+        if kind == "auto":
+            kind = KIND.get(name.split("/")[-1].lower())
         got = got.detach().cpu().float()
         want = want.detach().cpu().float().reshape(got.shape)
         m = self.clean
         if not bool(m.any()):
             return 0
-        a = atol * (1.0 + growth * self.ticks)
+        g = 1.0 + growth * self.ticks
+        shape = (int(m.sum()),) + (1,) * (got.dim() - 1)
         err = (got[m] - want[m]).abs()
-        tol = a + rtol * (1.0 + growth * self.ticks) * want[m].abs()
+        tol = atol * g + rtol * g * want[m].abs() + kind_scale(self.P, kind) * self.cum_dv[m].reshape(shape)
         if (err > tol).any():
             i = int(torch.argmax((err - tol).flatten()))
             raise AssertionError(f"{name}: {int((err > tol).sum())}/{err.numel()} elements of CLEAN envs outside tolerance after "

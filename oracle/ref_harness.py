@@ -27,7 +27,25 @@ import yaml
 
 from . import hs_oracle as O
 
-REF = Path("/root/reference")
+# The reference tree: where it lies in the build container, or the copy `pip install --target baseline/_ref` made of its
+# Python package (git-ignored, travels to the GPU box; see __graft_entry__.build and DESIGN.md).  Nothing is ever copied
+# into the tracked tree.
+_REPO = Path(__file__).resolve().parent.parent
+REF = next((p for p in (Path("/root/reference"), _REPO / "baseline" / "_ref") if (p / "omni_drones" / "envs").is_dir()),
+           Path("/root/reference"))
+
+
+def available() -> bool:
+    return (REF / "omni_drones" / "envs" / "hide_and_seek" / "hideandseek.py").is_file()
+
+
+def _drone_yaml():
+    """crazyflie.yaml of the reference (the pip-installed copy carries only .py files: then the package's own copy of the
+    vehicle parameters, which is configuration data)."""
+    p = REF / "omni_drones/robots/assets/usd/crazyflie.yaml"
+    if not p.is_file():
+        p = _REPO / "multi-uav-pursuit-evasion_b200" / "assets" / "crazyflie.yaml"
+    return yaml.safe_load(p.read_text())
 
 
 # ----------------------------------------------------------------------------
@@ -248,7 +266,7 @@ class RefEnv:
         store["cpos"][..., 2] = -20.0
         self.store = store
 
-        params = yaml.safe_load((REF / "omni_drones/robots/assets/usd/crazyflie.yaml").read_text())
+        params = _drone_yaml()
         # ---- drone (MultirotorBase stand-in, attributes as multirotor.py:159-263 sets them)
         d = _Obj()
         d.shape, d.n, d.num_rotors, d.device, d.dt = (E, A), A, 4, dev, P.dt

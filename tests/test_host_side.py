@@ -190,11 +190,11 @@ def test_rollout_and_policy_host_logic(built_lib):
 
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on stdout with
-    the contract's keys; it times the oracle port on the host cores and needs no GPU."""
+    the contract's keys; it times the reference's own source (or the oracle port) on the host cores and needs no GPU."""
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -202,7 +202,8 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"].startswith("env-steps/sec") and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["ticks_per_step"] == 64 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference-source", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
