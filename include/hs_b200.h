@@ -50,7 +50,7 @@ extern "C" {
 
 #define HS_ABI_VERSION 2
 #define HS_NUM_STATS 24
-#define HS_MAX_AGENTS 3
+#define HS_MAX_AGENTS 6          /* 1..3: both tick mappings and every fused kernel; 4..6: one-lane-per-env tick only */
 #define HS_MAX_CYLINDERS 8
 #define HS_MAX_OBS_CYLINDERS 4
 #define HS_MAX_FUTURE 8
@@ -289,7 +289,14 @@ int64_t hs_launch_count(const hs_handle* h);
  * operation order in the ill-conditioned stages (csrc/hs_tick_exact.cu).  About 2x slower; exists so that parity
  * tests can separate rounding amplified by the task's discontinuities from defects. */
 enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4,
-       HS_OPT_EXACT_MATH = 5 };
+       HS_OPT_EXACT_MATH = 5, HS_OPT_TICK_MAPPING = 6 };
+/* HS_OPT_TICK_MAPPING: which work decomposition hs_step_pre / hs_reset use for the tick kernel.
+ *   0 (default) = auto: 4 lanes per env (hs_tick_kernel, latency-bound small batches) below 32768 envs, one lane per
+ *       env (hs_tick_wide_kernel: TMA tensor loads of the SoA state tile, bulk stores of the outputs; bandwidth-bound
+ *       large batches) from 32768 envs on and always for num_agents > 3;
+ *   1 = always 4 lanes per env (num_agents <= 3 only);  2 = always one lane per env.
+ * Both give bit-identical results.  The one-lane mapping needs num_envs % 4 == 0 (16-byte row pitch of the stats
+ * tensor map) and distinct tp_input / tp_input_prev buffers; otherwise auto stays with the 4-lane kernel. */
 int hs_set_option(hs_handle* h, int option, int value);
 
 /* ---- device-side reset sampler --------------------------- */

@@ -193,8 +193,9 @@ struct Stager {
     }
 };
 
-constexpr int FILL_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * (20 + 3 * FMAX);   // 8*3*44 = 1056
-constexpr int TICK_STAGE_WORDS = ENVS_PER_WARP * HS_MAX_AGENTS * 20;                // widest tick tile: [24][20]
+constexpr int NARROW_MAX_AGENTS = 3;                 // the 4-lanes-per-env mapping: lanes 0..2 pursuers, lane A the evader
+constexpr int FILL_STAGE_WORDS = ENVS_PER_WARP * NARROW_MAX_AGENTS * (20 + 3 * FMAX);   // 8*3*44 = 1056
+constexpr int TICK_STAGE_WORDS = ENVS_PER_WARP * NARROW_MAX_AGENTS * 20;                // widest tick tile: [24][20]
 constexpr int TP_ENV_WORDS_MAX = 192;                                               // history_step * (7+3A) <= 192
 
 // ---- line of sight, hideandseek.py:47-103 ------------------------------------------------

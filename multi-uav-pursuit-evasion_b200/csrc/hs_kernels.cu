@@ -38,6 +38,7 @@
 #include "hs_common.cuh"
 #include "hs_stages.cuh"
 #include "hs_tick.cuh"
+#include "hs_tick_wide.cuh"
 #include "hs_predictor_ffma.cuh"
 #include "hs_predictor_mma.cuh"
 #include "hs_predictor_tcgen05.cuh"
@@ -50,6 +51,9 @@
 // the tick kernel built with IEEE arithmetic (csrc/hs_tick_exact.cu, HS_OPT_EXACT_MATH)
 cudaError_t hs_launch_tick_exact(const void* kparams, size_t bytes, int num_agents, int reset, int small_c, unsigned grid,
                                  unsigned block, cudaStream_t s);
+cudaError_t hs_launch_tick_wide_exact(const void* kparams, size_t bytes, const void* maps3, int num_agents, int reset, int small_c,
+                                      unsigned grid, size_t smem, cudaStream_t s);
+cudaError_t hs_wide_exact_set_smem(int num_agents, int small_c, int bytes);
 
 // =========================================================================================
 // C ABI
@@ -84,6 +88,12 @@ struct hs_handle {
     int io_graph_mode = 1;       // HS_OPT_HOST_IO_GRAPH: 1 = graph launch (default), 0 = stream API calls
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
     int exact_math = 0;          // HS_OPT_EXACT_MATH: the tick runs the IEEE-arithmetic build of hs_tick_kernel (parity evidence)
+    int tick_mapping = 0;        // HS_OPT_TICK_MAPPING: 0 auto, 1 four lanes per env, 2 one lane per env (hs_tick_wide_kernel)
+    // TMA tensor maps of the one-lane mapping (state tile load / store, stats tile), valid for tm_arena / tm_stats
+    CUtensorMap tm[3];
+    const void* tm_arena = nullptr;
+    const void* tm_stats = nullptr;
+    bool wide_ready = false;     // shared-memory opt-in done for this handle's kernels
 };
 
 static thread_local char g_err[512] = "";
@@ -97,12 +107,109 @@ static int set_err(int code, const char* fmt, const char* detail = "") {
         if (_e != cudaSuccess) return set_err(HS_ERR_CUDA, #call ": %s", cudaGetErrorString(_e)); \
     } while (0)
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*hs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static hs_encode_tiled_fn tensor_map_encoder() {
+    static hs_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<hs_encode_tiled_fn>(p);
+    }
+    return fn;
+}
+// 2-D fp32 tensor [rows][cols] with row pitch `pitch_floats`, box = [box_rows][32 columns]
+static bool encode_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_floats, uint32_t box_rows) {
+    hs_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
+    const cuuint32_t box[2] = {32u, box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// one lane per env? (HS_OPT_TICK_MAPPING; the wide kernel needs a 16-byte stats row pitch and a TP window that is not shifted in place)
+static bool wide_possible(const hs_handle* h) {
+    const hs_config& c = h->cfg;
+    if ((c.num_envs & 3) != 0 || c.num_agents < 3) return false;
+    if (c.use_tp_net && h->bufs.tp_input == h->bufs.tp_input_prev) return false;
+    return true;
+}
+static bool use_wide(const hs_handle* h) {
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS) return true;
+    if (h->tick_mapping == 1) return false;
+    if (h->tick_mapping == 2) return wide_possible(h);
+    return h->cfg.num_envs >= 32768 && wide_possible(h);
+}
+
+template <int A, int CT, bool RESET>
+static cudaError_t launch_wide_one(const KParams& P, const CUtensorMap* tm, unsigned grid, size_t smem, cudaStream_t s) {
+    hs_tick_wide_kernel<A, CT, RESET><<<grid, WIDE_WARPS * 32, smem, s>>>(P, tm[0], tm[1], tm[2]);
+    return cudaGetLastError();
+}
+template <int A, int CT>
+static cudaError_t wide_set_smem(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(hs_tick_wide_kernel<A, CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tick_wide_kernel<A, CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
+}
+#define HS_WIDE_DISPATCH(CALL)                                                                        \
+    switch (A) {                                                                                      \
+        case 3: return small_c ? CALL(3, 5) : CALL(3, CMAX);                                          \
+        case 4: return small_c ? CALL(4, 5) : CALL(4, CMAX);                                          \
+        case 5: return small_c ? CALL(5, 5) : CALL(5, CMAX);                                          \
+        case 6: return small_c ? CALL(6, 5) : CALL(6, CMAX);                                          \
+        default: return cudaErrorInvalidValue;                                                        \
+    }
+static cudaError_t wide_set_smem_dispatch(int A, bool small_c, int bytes) {
+#define HS_CALL(AA, CC) wide_set_smem<AA, CC>(bytes)
+    HS_WIDE_DISPATCH(HS_CALL)
+#undef HS_CALL
+}
 template <bool RESET>
-static cudaError_t launch_tick(const hs_handle* h, const KParams& P, cudaStream_t s) {
+static cudaError_t launch_wide_dispatch(int A, bool small_c, const KParams& P, const CUtensorMap* tm, unsigned grid, size_t smem, cudaStream_t s) {
+#define HS_CALL(AA, CC) launch_wide_one<AA, CC, RESET>(P, tm, grid, smem, s)
+    HS_WIDE_DISPATCH(HS_CALL)
+#undef HS_CALL
+}
+
+template <bool RESET>
+static cudaError_t launch_tick(hs_handle* h, const KParams& P, cudaStream_t s) {
+    const bool small_c = h->cfg.num_cylinders <= 5;      // compile-time cylinder capacity 5 or 8
+    if (use_wide(h)) {
+        const hs_config& c = h->cfg;
+        if (!wide_possible(h)) return cudaErrorInvalidConfiguration;
+        const WidePlan w = wide_plan(c.num_agents, c.num_cylinders, c.obs_max_cylinder, c.use_tp_net != 0);
+        const size_t smem = (size_t)WIDE_WARPS * w.total * sizeof(float);
+        if (!h->wide_ready) {
+            cudaError_t e = wide_set_smem_dispatch(c.num_agents, small_c, (int)smem);
+            if (e == cudaSuccess) e = hs_wide_exact_set_smem(c.num_agents, small_c ? 1 : 0, (int)smem);
+            if (e != cudaSuccess) return e;
+            h->wide_ready = true;
+        }
+        if (h->tm_arena != h->bufs.arena || h->tm_stats != h->bufs.stats) {
+            const uint64_t Ep = (uint64_t)h->Ep;
+            if (!encode_map(&h->tm[0], h->bufs.arena, Ep, (uint64_t)w.rows_all, Ep, (uint32_t)w.rows_all) ||
+                !encode_map(&h->tm[1], h->bufs.arena, Ep, (uint64_t)w.rows_all, Ep, (uint32_t)w.rows_rw) ||
+                !encode_map(&h->tm[2], h->bufs.stats, (uint64_t)c.num_envs, HS_NUM_STATS, (uint64_t)c.num_envs, HS_NUM_STATS))
+                return cudaErrorInvalidValue;
+            h->tm_arena = h->bufs.arena;
+            h->tm_stats = h->bufs.stats;
+        }
+        const int64_t tiles = ((int64_t)c.num_envs + 31) / 32;
+        const unsigned grid = (unsigned)((tiles + WIDE_WARPS - 1) / WIDE_WARPS);
+        if (h->exact_math)
+            return hs_launch_tick_wide_exact(&P, sizeof(P), h->tm, c.num_agents, RESET ? 1 : 0, small_c ? 1 : 0, grid, smem, s);
+        return launch_wide_dispatch<RESET>(c.num_agents, small_c, P, h->tm, grid, smem, s);
+    }
     const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
     const int wpb = h->block / 32;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
-    const bool small_c = h->cfg.num_cylinders <= 5;      // compile-time cylinder capacity 5 or 8
     if (h->exact_math)
         return hs_launch_tick_exact(&P, sizeof(P), h->cfg.num_agents, RESET ? 1 : 0, small_c ? 1 : 0, grid, (unsigned)h->block, s);
     switch (h->cfg.num_agents) {
@@ -170,7 +277,9 @@ static int check_cfg(const hs_config* c) {
     if (!c) return set_err(HS_ERR_INVALID, "null config%s");
     if (c->abi_version != HS_ABI_VERSION) return set_err(HS_ERR_INVALID, "config abi_version mismatch%s");
     if (c->num_envs <= 0) return set_err(HS_ERR_INVALID, "num_envs must be > 0%s");
-    if (c->num_agents < 1 || c->num_agents > HS_MAX_AGENTS) return set_err(HS_ERR_INVALID, "num_agents must be 1..3%s");
+    if (c->num_agents < 1 || c->num_agents > HS_MAX_AGENTS) return set_err(HS_ERR_INVALID, "num_agents must be 1..6%s");
+    if (c->num_agents > NARROW_MAX_AGENTS && (c->num_envs & 3) != 0)
+        return set_err(HS_ERR_INVALID, "num_agents > 3 runs on the one-lane-per-env kernel, which needs num_envs % 4 == 0%s");
     if (c->num_cylinders < 0 || c->num_cylinders > HS_MAX_CYLINDERS) return set_err(HS_ERR_INVALID, "num_cylinders must be 0..8%s");
     if (c->obs_max_cylinder < 0 || c->obs_max_cylinder > HS_MAX_OBS_CYLINDERS || c->obs_max_cylinder > c->num_cylinders)
         return set_err(HS_ERR_INVALID, "obs_max_cylinder must be <= min(num_cylinders, 4)%s");
@@ -178,7 +287,7 @@ static int check_cfg(const hs_config* c) {
     if (c->history_step < 1) return set_err(HS_ERR_INVALID, "history_step must be >= 1%s");
     if (((int64_t)ND * c->num_agents + E_CYL + 3 * (int64_t)c->num_cylinders) * (((int64_t)c->num_envs + 31) & ~(int64_t)31) >= ((int64_t)1 << 31))
         return set_err(HS_ERR_INVALID, "num_envs too large: the state arena must stay below 2^31 words%s");
-    if (c->use_tp_net && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
+    if (c->use_tp_net && c->num_agents <= NARROW_MAX_AGENTS && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
         return set_err(HS_ERR_INVALID, "history_step * (7 + 3*num_agents) must be <= 192%s");
     return HS_OK;
 }
@@ -231,7 +340,7 @@ int hs_create(const hs_config* cfg, hs_handle** out) {
 #undef HS_CARVE
         if (e != cudaSuccess) { delete h; return set_err(HS_ERR_CUDA, "cudaFuncSetAttribute(carveout): %s", cudaGetErrorString(e)); }
     }
-    if (cfg->use_tp_net) {
+    if (cfg->use_tp_net && cfg->num_agents <= NARROW_MAX_AGENTS) {
         // opt in to > 48 KB dynamic shared memory once (not a stream operation: keeps the
         // step entry points legal inside CUDA-graph capture)
         const int smem = (int)tp_smem_bytes(*cfg), smem_w = (int)tp_wide_smem_bytes(*cfg);
@@ -362,9 +471,11 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     if (!h || !action || !w) return set_err(HS_ERR_INVALID, "hs_step_fused: null argument%s");
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_fused: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_fused: config has use_tp_net == 0 (use hs_step_pre)%s");
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS)
+        return set_err(HS_ERR_INVALID, "hs_step_fused: the fused predictor kernels cover num_agents <= 3; use hs_step_pre + the module + hs_step_post%s");
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = h->fused_tick && !h->exact_math && (h->tp_variant < 0 || h->tp_variant == 5) && tiles32 <= h->num_sms &&
-                            tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
+    const bool one_launch = h->fused_tick && !h->exact_math && h->tick_mapping != 2 && (h->tp_variant < 0 || h->tp_variant == 5) &&
+                            tiles32 <= h->num_sms && tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
     if (!one_launch) {
         const int rc = hs_step_pre(h, action, action_is_raw, reset_pid, stream);
         return rc != HS_OK ? rc : hs_step_post_tp(h, w, tp_pred_out, stream);
@@ -411,14 +522,23 @@ int hs_step_post(hs_handle* h, const float* tp_pred, void* stream) {
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_post: config has use_tp_net == 0%s");
     KParams P = make_params(h);
     P.tp_pred = tp_pred;
-    const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
-    const int wpb = h->block / 32;
-    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
     cudaStream_t s = (cudaStream_t)stream;
-    switch (h->cfg.num_agents) {
-        case 1: hs_fill_kernel<1><<<grid, h->block, 0, s>>>(P); break;
-        case 2: hs_fill_kernel<2><<<grid, h->block, 0, s>>>(P); break;
-        default: hs_fill_kernel<3><<<grid, h->block, 0, s>>>(P); break;
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS) {
+        const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + 127) / 128);
+        switch (h->cfg.num_agents) {
+            case 4: hs_fill_wide_kernel<4><<<grid, 128, 0, s>>>(P); break;
+            case 5: hs_fill_wide_kernel<5><<<grid, 128, 0, s>>>(P); break;
+            default: hs_fill_wide_kernel<6><<<grid, 128, 0, s>>>(P); break;
+        }
+    } else {
+        const int64_t warps = ((int64_t)h->cfg.num_envs + ENVS_PER_WARP - 1) / ENVS_PER_WARP;
+        const int wpb = h->block / 32;
+        const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+        switch (h->cfg.num_agents) {
+            case 1: hs_fill_kernel<1><<<grid, h->block, 0, s>>>(P); break;
+            case 2: hs_fill_kernel<2><<<grid, h->block, 0, s>>>(P); break;
+            default: hs_fill_kernel<3><<<grid, h->block, 0, s>>>(P); break;
+        }
     }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
@@ -429,6 +549,8 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     if (!h || !w) return set_err(HS_ERR_INVALID, "hs_step_post_tp: null argument%s");
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_post_tp: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_post_tp: config has use_tp_net == 0%s");
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS)
+        return set_err(HS_ERR_INVALID, "hs_step_post_tp: the fused predictor kernels cover num_agents <= 3; use the module + hs_step_post%s");
     if (!w->weight_ih || !w->weight_hh || !w->bias_ih || !w->bias_hh || !w->fc_weight || !w->fc_bias)
         return set_err(HS_ERR_INVALID, "hs_step_post_tp: a weight pointer is NULL%s");
     if (w->hidden_size != TP_HID || w->input_size != 7 + 3 * h->cfg.num_agents || w->output_size != 3 * h->cfg.future_step)
@@ -541,12 +663,15 @@ int hs_reset(hs_handle* h, const uint8_t* env_mask, const float* drone_pos, cons
     P.init_target_pos = target_pos; P.init_cyl_pos = cyl_pos;
     P.tp_init = (h->cfg.use_tp_net && h->tp_frames == 0) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t threads = (int64_t)h->cfg.num_envs * G;
+    const int64_t threads = (int64_t)h->cfg.num_envs * (h->cfg.num_agents + 1);
     const unsigned grid = (unsigned)((threads + 127) / 128);
     switch (h->cfg.num_agents) {
         case 1: hs_reset_scatter_kernel<1><<<grid, 128, 0, s>>>(P); break;
         case 2: hs_reset_scatter_kernel<2><<<grid, 128, 0, s>>>(P); break;
-        default: hs_reset_scatter_kernel<3><<<grid, 128, 0, s>>>(P); break;
+        case 3: hs_reset_scatter_kernel<3><<<grid, 128, 0, s>>>(P); break;
+        case 4: hs_reset_scatter_kernel<4><<<grid, 128, 0, s>>>(P); break;
+        case 5: hs_reset_scatter_kernel<5><<<grid, 128, 0, s>>>(P); break;
+        default: hs_reset_scatter_kernel<6><<<grid, 128, 0, s>>>(P); break;
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(launch_tick<true>(h, P, s));
@@ -968,6 +1093,15 @@ int hs_set_option(hs_handle* h, int option, int value) {
         case HS_OPT_HOST_IO_GRAPH:
             if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_GRAPH must be 0 or 1%s");
             h->io_graph_mode = value;
+            return HS_OK;
+        case HS_OPT_TICK_MAPPING:
+            if (value < 0 || value > 2) return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING must be 0 (auto), 1 (4 lanes per env) or 2 (one lane per env)%s");
+            if (value == 1 && h->cfg.num_agents > NARROW_MAX_AGENTS)
+                return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING = 1: the 4-lane mapping covers num_agents <= 3%s");
+            if (value == 2 && (h->cfg.num_agents < 3 || (h->cfg.num_envs & 3) != 0))
+                return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING = 2: the one-lane mapping needs num_agents >= 3 and num_envs % 4 == 0%s");
+            h->tick_mapping = value;
+            for (auto& g : h->io_graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
             return HS_OK;
         case HS_OPT_EXACT_MATH:
             if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_EXACT_MATH must be 0 or 1%s");

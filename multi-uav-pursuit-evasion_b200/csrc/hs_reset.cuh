@@ -13,9 +13,10 @@ template <int A>
 __global__ void __launch_bounds__(128)
 hs_reset_scatter_kernel(const __grid_constant__ KParams P) {
     const hs_config& c = P.c;
+    // one thread per (env, body): bodies 0..A-1 = pursuers, body A = the evader + cylinders + stats of the env
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = (int)(gt & (G - 1));
-    const int64_t e = gt >> 2;
+    const int64_t e = gt / (A + 1);
+    const int slot = (int)(gt - e * (A + 1));
     const int E = c.num_envs;
     if (e >= E) return;
     const bool masked = (P.env_mask == nullptr) || (P.env_mask[e] != 0);

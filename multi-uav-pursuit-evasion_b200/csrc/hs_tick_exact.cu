@@ -21,6 +21,7 @@
 #include "hs_common.cuh"
 #include "hs_stages.cuh"
 #include "hs_tick.cuh"
+#include "hs_tick_wide.cuh"
 
 // kparams: the caller's KParams (same header, same layout), passed by address because types in anonymous namespaces
 // are private to their translation unit
@@ -38,5 +39,31 @@ cudaError_t hs_launch_tick_exact(const void* kparams, size_t bytes, int num_agen
         default: return cudaErrorInvalidValue;
     }
 #undef HS_X
+    return cudaGetLastError();
+}
+
+// the one-lane-per-env mapping in IEEE arithmetic (A = 3 and 4: what the parity tests exercise)
+cudaError_t hs_wide_exact_set_smem(int num_agents, int small_c, int bytes) {
+    cudaError_t e = cudaSuccess;
+#define HS_S(AA, CC) do { e = cudaFuncSetAttribute(hs_tick_wide_kernel<AA, CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+                          if (e == cudaSuccess) e = cudaFuncSetAttribute(hs_tick_wide_kernel<AA, CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); } while (0)
+    if (num_agents == 3) { if (small_c) HS_S(3, 5); else HS_S(3, CMAX); }
+    else if (num_agents == 4) { if (small_c) HS_S(4, 5); else HS_S(4, CMAX); }
+#undef HS_S
+    return e;                          // other agent counts: no exact build (hs_launch_tick_wide_exact reports it)
+}
+cudaError_t hs_launch_tick_wide_exact(const void* kparams, size_t bytes, const void* maps3, int num_agents, int reset, int small_c,
+                                      unsigned grid, size_t smem, cudaStream_t s) {
+    KParams P;
+    if (bytes != sizeof(P)) return cudaErrorInvalidValue;
+    memcpy(&P, kparams, sizeof(P));
+    const CUtensorMap* tm = static_cast<const CUtensorMap*>(maps3);
+#define HS_W(AA, CC, RR) hs_tick_wide_kernel<AA, CC, RR><<<grid, WIDE_WARPS * 32, smem, s>>>(P, tm[0], tm[1], tm[2])
+#define HS_WC(AA, RR) do { if (small_c) HS_W(AA, 5, RR); else HS_W(AA, CMAX, RR); } while (0)
+    if (num_agents == 3) { if (reset) HS_WC(3, true); else HS_WC(3, false); }
+    else if (num_agents == 4) { if (reset) HS_WC(4, true); else HS_WC(4, false); }
+    else return cudaErrorInvalidValue;
+#undef HS_WC
+#undef HS_W
     return cudaGetLastError();
 }

@@ -357,6 +357,8 @@ class HsEngine:
         lstm, fc = getattr(module, "lstm", None), getattr(module, "fc", None)
         if not isinstance(lstm, torch.nn.LSTM) or not isinstance(fc, torch.nn.Linear):
             return None
+        if self.A > 3:              # the fused predictor kernels cover up to 3 pursuers: module forward + hs_step_post
+            return None
         if lstm.num_layers != 1 or lstm.bidirectional or lstm.hidden_size != 64 or not lstm.batch_first \
                 or lstm.proj_size != 0 or not lstm.bias:
             return None
@@ -385,6 +387,12 @@ class HsEngine:
         halves (small-batch default, and the predictor half of the one-launch tick)."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_PREDICTOR_VARIANT, int(variant)), "hs_set_option")
         self._graphs = None             # captured graphs hold the old kernel
+
+    def set_tick_mapping(self, mapping: int):
+        """HS_OPT_TICK_MAPPING: 0 auto (4 lanes per env below 32768 envs, one lane per env above and for more than 3
+        pursuers), 1 always 4 lanes per env, 2 always one lane per env (hs_tick_wide_kernel).  Same results bit for bit."""
+        check(lib.hs_set_option(self._h, _lib.HS_OPT_TICK_MAPPING, int(mapping)), "hs_set_option")
+        self._graphs = None
 
     def set_exact_math(self, on: bool):
         """HS_OPT_EXACT_MATH: run the tick with the IEEE-arithmetic build of the kernel (parity evidence; ~2x slower)."""

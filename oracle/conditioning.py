@@ -172,8 +172,11 @@ class TickConditioning:
                 f"{name}: {int(hard.sum())}/{bad.numel()} elements outside tolerance in well-conditioned envs; worst env {e} "
                 f"|err|={err.flatten()[i].item():.3e} tol={tol.flatten()[i].item():.3e} got={got.flatten()[i].item():.6e} "
                 f"want={want.flatten()[i].item():.6e} (dv bound of that env {self.dv[e].item():.2e})")
-        if (err.masked_fill(~bad, 0.0) > cap).any() or torch.isnan(got).any():
-            raise AssertionError(f"{name}: an edge-env element is beyond the sanity cap {cap} or NaN")
+        if (err.masked_fill(~bad, 0.0) > cap).any() or torch.isnan(got).any() or torch.isnan(want).any():
+            i = int(torch.argmax(torch.nan_to_num(err, nan=float("inf")).flatten()))
+            raise AssertionError(f"{name}: an edge-env element is beyond the sanity cap {cap} or NaN: flat index {i} of shape "
+                                 f"{tuple(got.shape)} got={got.flatten()[i].item()} want={want.flatten()[i].item()} "
+                                 f"(NaNs: got {int(torch.isnan(got).sum())}, want {int(torch.isnan(want).sum())})")
         n_edge, n_dv = int(bad.sum()), int(((err > base) & ~bad).sum())
         if n_edge or n_dv:
             self.used = getattr(self, "used", [])

@@ -89,16 +89,21 @@ def test_kernels_replay_reference_ticks(path, exact):
                      (L.FIELD_TARGET_POS, "tpos"), (L.FIELD_TARGET_VEL, "tvel"), (L.FIELD_PROGRESS, "progress")):
             cond.check(f"{G.name}/t{t}/post/{k}", eng.get_state(f), post[k])
         n_edge_envs += int(cond.edge.sum())
-        n_exempt += getattr(cond, "n_edge_exempt", 0)
-        n_dv += getattr(cond, "n_dv_needed", 0)
-        used += getattr(cond, "used", [])
+        # (ctbr is kept apart: its allowance is the rate PID's gain on ulp-level differences between CUDA's and torch's
+        # tanh, conditioning.pid_bound - not the evader / indicator mechanism the zero-claim below is about)
+        u = getattr(cond, "used", [])
+        used += u
+        n_exempt += sum(x[1] for x in u if not x[0].endswith("/ctbr"))
+        n_dv += sum(x[2] for x in u if not x[0].endswith("/ctbr"))
+        n_pid = locals().get("n_pid", 0) + sum(x[1] + x[2] for x in u if x[0].endswith("/ctbr"))
     eng.close()
     try:                                          # evidence for profiles/: how much of the allowance was actually used
         os.makedirs(os.path.dirname(REPORT), exist_ok=True)
         with open(REPORT, "a") as f:
             f.write(json.dumps({"fixture": G.name, "build": "ieee" if exact else "fast", "envs_x_ticks": E * G.ticks,
                                 "edge_envs": n_edge_envs, "elements_exempted_as_edge": n_exempt,
-                                "elements_within_dv_allowance_only": n_dv, "where": used[:8]}) + "\n")
+                                "elements_within_dv_allowance_only": n_dv, "ctbr_elements_within_pid_allowance": locals().get("n_pid", 0),
+                                "where": used[:8]}) + "\n")
     except OSError:
         pass
     if exact:

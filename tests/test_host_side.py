@@ -42,7 +42,7 @@ def test_config_struct_layout_matches_c_defaults(built_lib):
 
 def test_invalid_configs_are_rejected(built_lib):
     from mupe_b200 import _lib
-    for field, bad in (("num_agents", 4), ("num_cylinders", 9), ("obs_max_cylinder", 6), ("num_envs", 0), ("abi_version", 99)):
+    for field, bad in (("num_agents", 7), ("num_cylinders", 9), ("obs_max_cylinder", 6), ("num_envs", 0), ("abi_version", 99)):
         c = _lib.default_config(64)
         setattr(c, field, bad)
         assert _lib.lib.hs_arena_floats(ctypes.byref(c)) == -1, field
