@@ -669,14 +669,19 @@ def tick_at_scale(torch, mupe_b200, tp_net, dev, timed_graph, ab, peak, peak_src
             _check(_hs.hs_step_pre(big._h, big_act.data_ptr(), 1, None, st), "hs_step_pre")
     big_us = timed_graph(b_big, 3) / 4
     big_gbs = ab["tick"] * EB / (big_us * 1e-6) / 1e9
-    out = {"bound": "hbm", "kernel": "hs_tick_kernel<3,false,5>", "envs_per_launch": EB, "launch_us": big_us,
+    out = {"bound": "hbm", "kernel": "hs_tick_wide_kernel<3,5,false> (auto mapping from 32768 envs: one lane per env, TMA tensor tile loads)",
+           "envs_per_launch": EB, "launch_us": big_us,
            "achieved": big_gbs, "peak": peak, "unit": "GB/s", "frac": big_gbs / peak, "peak_source": peak_src,
            "env_steps_per_s": EB / (big_us * 1e-6), "algorithmic_bytes_per_launch": ab["tick"] * EB,
-           "traffic": 2934745000 if EB == (1 << 20) else None,
-           "traffic_source": "profiles/r1_ncu_tick_v4.txt (dram read+write per 1 Mi-env launch: 2799 B/env, of which 576 B/env is "
-                             "the read of the previous TP window that the SURVEY formula does not count)",
-           "note": "same kernel, same per-env workload as the headline, measured live in this run at a batch that streams "
-                   "2.3 GB per launch; not the headline configuration"}
+           "traffic": 2929741000 if EB == (1 << 20) else None,
+           "traffic_source": "profiles/r2_ncu_tick_wide_v5_1M.txt (dram read 1.2416 GB + write 1.6881 GB per 1 Mi-env launch = 2794 B/env)",
+           "algorithmic_bytes_incl_window_read": (ab["tick"] + 576) * EB,
+           "frac_incl_window_read": (ab["tick"] + 576) * EB / (big_us * 1e-6) / 1e9 / peak,
+           "note": "same per-env workload as the headline, measured live in this run at a batch that streams 2.9 GB per launch; not the "
+                   "headline configuration.  `achieved` uses SURVEY 8d's 2177 B/env for the tick kernel; that formula leaves out the 576 B/env "
+                   "READ of the previous TP window which writing the chronological [E,H,16] TP_input requires of any implementation "
+                   "(the reference re-stacks its deque every tick, hideandseek.py:819-831): with it the kernel's contract moves 2753 B/env "
+                   "(frac_incl_window_read) and the measured DRAM traffic is 1.015x that"}
     # whole tick (tick + predictor) at the same scale
     import ctypes
 
@@ -779,8 +784,8 @@ def eager_cuda_line(torch, dev):
     dt = time.perf_counter() - t0
     out = {"value": sim.E * n / dt, "unit": "env-steps/s", "kind": sim.kind + " (eager, device=cuda)", "ticks": n,
            "ms_per_tick": 1e3 * dt / n, "what": sim.describe("-")}
-    if err and sim.kind == "port":
-        out["reference_source_on_cuda_failed"] = err
+    if sim.kind == "port" and (err or getattr(sim, "source_error", None)):
+        out["reference_source_on_cuda_failed"] = err or sim.source_error
     return out
 
 

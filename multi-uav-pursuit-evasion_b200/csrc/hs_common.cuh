@@ -21,7 +21,8 @@ enum { E_TPOS = 0, E_TVEL = 3, E_PROGRESS = 6, E_BDETECT = 7, E_CYL = 8 };
 struct KParams {
     hs_config c;
     hs_buffers b;
-    int64_t Ep;                      // arena row pitch (E rounded up to 32)
+    int64_t Ep;                      // E rounded up to 32 (the arena holds Ep / 32 tiles)
+    int32_t R;                       // arena rows per tile: 23 A + 8 + 3 C
     const float* action;
     const uint8_t* reset_pid;
     const uint8_t* env_mask;
@@ -256,7 +257,11 @@ __device__ __forceinline__ void write_self_row(float* row, V3 head, int F3, cons
     row[o + 13] = t; row[o + 14] = t; row[o + 15] = t; row[o + 16] = t;
 }
 
-#define AROW(r) (P.b.arena + (int64_t)(r) * P.Ep + e)
+// State arena = tile-blocked SoA: tile t = envs [32 t, 32 t + 32) is ONE contiguous block of R rows x 32 floats, row r of
+// env e at ((e >> 5) * R + r) * 32 + (e & 31).  A tile is what a CTA of the one-lane mapping moves with a single TMA box
+// and what four warps of the 4-lane mapping share sector by sector; nothing of a tick is more than 12 KB away from the
+// rest of its env (DRAM page locality; the plain [row][E] layout put the 92 rows of an env 4 MB apart at 1 Mi envs).
+#define AROW(r) (P.b.arena + (((int64_t)(e) >> 5) * P.R + (r)) * 32 + ((e) & 31))
 #define DROW(k) AROW((k) * A + slot)
 #define EROW(k) AROW(ND * A + (k))
 

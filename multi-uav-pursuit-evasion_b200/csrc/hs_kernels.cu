@@ -149,7 +149,7 @@ static bool use_wide(const hs_handle* h) {
 
 template <int A, int CT, bool RESET>
 static cudaError_t launch_wide_one(const KParams& P, const CUtensorMap* tm, unsigned grid, size_t smem, cudaStream_t s) {
-    hs_tick_wide_kernel<A, CT, RESET><<<grid, WIDE_WARPS * 32, smem, s>>>(P, tm[0], tm[1], tm[2]);
+    hs_tick_wide_kernel<A, CT, RESET><<<grid, (A + 1) * 32, smem, s>>>(P, tm[0], tm[1]);
     return cudaGetLastError();
 }
 template <int A, int CT>
@@ -192,11 +192,11 @@ static cudaError_t launch_tick(hs_handle* h, const KParams& P, cudaStream_t s) {
             if (e != cudaSuccess) return e;
             h->wide_ready = true;
         }
-        if (h->tm_arena != h->bufs.arena || h->tm_stats != h->bufs.stats) {
-            const uint64_t Ep = (uint64_t)h->Ep;
-            if (!encode_map(&h->tm[0], h->bufs.arena, Ep, (uint64_t)w.rows_all, Ep, (uint32_t)w.rows_all) ||
-                !encode_map(&h->tm[1], h->bufs.arena, Ep, (uint64_t)w.rows_all, Ep, (uint32_t)w.rows_rw) ||
-                !encode_map(&h->tm[2], h->bufs.stats, (uint64_t)c.num_envs, HS_NUM_STATS, (uint64_t)c.num_envs, HS_NUM_STATS))
+        if (h->tm_arena != h->bufs.arena) {
+            // the tile-blocked arena as a 2-D tensor [tiles x R rows][32 floats]: a tile is the box of its R consecutive rows
+            const uint64_t rows = (uint64_t)(h->Ep / 32) * (uint64_t)w.rows_all;
+            if (!encode_map(&h->tm[0], h->bufs.arena, 32, rows, 32, (uint32_t)w.rows_all) ||
+                !encode_map(&h->tm[1], h->bufs.arena, 32, rows, 32, (uint32_t)w.rows_rw))
                 return cudaErrorInvalidValue;
             h->tm_arena = h->bufs.arena;
             h->tm_stats = h->bufs.stats;
@@ -447,6 +447,7 @@ static KParams make_params(const hs_handle* h) {
     P.c = h->cfg;
     P.b = h->bufs;
     P.Ep = h->Ep;
+    P.R = ND * h->cfg.num_agents + E_CYL + 3 * h->cfg.num_cylinders;
     return P;
 }
 
@@ -1060,7 +1061,7 @@ static int field_copy(hs_handle* h, int field, float* aos, int to_aos, void* str
     const int64_t n = (int64_t)h->cfg.num_envs * n_slots * width;
     if (n == 0) return HS_OK;
     const unsigned grid = (unsigned)((n + 255) / 256);
-    hs_field_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->bufs.arena, h->Ep, row0, n_slots, width, ss, sc,
+    hs_field_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->bufs.arena, ND * h->cfg.num_agents + E_CYL + 3 * h->cfg.num_cylinders, row0, n_slots, width, ss, sc,
                                                                  h->cfg.num_envs, aos, to_aos);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;

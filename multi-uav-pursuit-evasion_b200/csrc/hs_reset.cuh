@@ -43,7 +43,7 @@ hs_reset_scatter_kernel(const __grid_constant__ KParams P) {
 }
 
 // ---- AoS <-> arena field copies (views/* replacement, used by tests and tools) -----------
-__global__ void hs_field_copy_kernel(float* arena, int64_t Ep, int row0, int n_slots, int width,
+__global__ void hs_field_copy_kernel(float* arena, int R, int row0, int n_slots, int width,
                                      int row_stride_slot, int row_stride_comp, int E, float* aos, int to_aos) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per_env = (int64_t)n_slots * width;
@@ -51,7 +51,8 @@ __global__ void hs_field_copy_kernel(float* arena, int64_t Ep, int row0, int n_s
     const int64_t e = i / per_env;
     const int r = (int)(i - e * per_env);
     const int a = r / width, k = r - a * width;
-    float* ap = arena + ((int64_t)row0 + (int64_t)k * row_stride_comp + (int64_t)a * row_stride_slot) * Ep + e;
+    const int64_t arow = (int64_t)row0 + (int64_t)k * row_stride_comp + (int64_t)a * row_stride_slot;
+    float* ap = arena + ((e >> 5) * R + arow) * 32 + (e & 31);
     if (to_aos) aos[i] = *ap; else *ap = aos[i];
 }
 

@@ -58,9 +58,10 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     const int H = c.history_step;
     const float dt = c.dt;
     // arena offsets fit 32 bits (checked at hs_create): one IMAD + one wide add per access
-    const uint32_t Ep32 = (uint32_t)P.Ep;
-    const uint32_t o_drone = (uint32_t)slot * Ep32 + (uint32_t)e;     // + k * (A*Ep32)
-    const uint32_t o_env = (uint32_t)(ND * A) * Ep32 + (uint32_t)e;   // + k * Ep32
+    const uint32_t Ep32 = 32u;                                         // row pitch inside a tile (hs_common.cuh AROW)
+    const uint32_t tile_off = (uint32_t)(e >> 5) * ((uint32_t)P.R * 32u) + ((uint32_t)e & 31u);
+    const uint32_t o_drone = (uint32_t)slot * Ep32 + tile_off;         // + k * (A*Ep32)
+    const uint32_t o_env = (uint32_t)(ND * A) * Ep32 + tile_off;       // + k * Ep32
     float* const arena = P.b.arena;
 #undef DROW
 #undef EROW

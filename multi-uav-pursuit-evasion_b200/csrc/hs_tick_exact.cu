@@ -58,7 +58,7 @@ cudaError_t hs_launch_tick_wide_exact(const void* kparams, size_t bytes, const v
     if (bytes != sizeof(P)) return cudaErrorInvalidValue;
     memcpy(&P, kparams, sizeof(P));
     const CUtensorMap* tm = static_cast<const CUtensorMap*>(maps3);
-#define HS_W(AA, CC, RR) hs_tick_wide_kernel<AA, CC, RR><<<grid, WIDE_WARPS * 32, smem, s>>>(P, tm[0], tm[1], tm[2])
+#define HS_W(AA, CC, RR) hs_tick_wide_kernel<AA, CC, RR><<<grid, ((AA) + 1) * 32, smem, s>>>(P, tm[0], tm[1])
 #define HS_WC(AA, RR) do { if (small_c) HS_W(AA, 5, RR); else HS_W(AA, CMAX, RR); } while (0)
     if (num_agents == 3) { if (reset) HS_WC(3, true); else HS_WC(3, false); }
     else if (num_agents == 4) { if (reset) HS_WC(4, true); else HS_WC(4, false); }

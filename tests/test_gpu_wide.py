@@ -35,10 +35,9 @@ def test_wide_equals_narrow_bit_for_bit(E, C, tp):
     def same(tag, a, b):
         for k in keys:
             assert torch.equal(a[k], b[k]), f"{tag}: {k} differs"
-        E_ = narrow.E
-        na = narrow.arena.view(-1, (E_ + 31) // 32 * 32)[:, :E_]
-        wa = wide.arena.view(-1, (E_ + 31) // 32 * 32)[:, :E_]
-        assert torch.equal(na, wa), f"{tag}: arena differs in rows {torch.nonzero((na != wa).any(1)).flatten().tolist()}"
+        # (tile-blocked arena [tile][row][32]; neither kernel touches the padding lanes of a ragged last tile)
+        na, wa = narrow.arena.view(-1, 32), wide.arena.view(-1, 32)
+        assert torch.equal(na, wa), f"{tag}: arena differs in (tile x row) {torch.nonzero((na != wa).any(1)).flatten().tolist()[:12]}"
         assert torch.equal(narrow.stats, wide.stats), f"{tag}: stats differ"
         assert torch.equal(narrow.prev_action, wide.prev_action), f"{tag}: prev_action differs"
 

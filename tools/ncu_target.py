@@ -20,6 +20,7 @@ def main():
     torch.manual_seed(0)
     tp = mupe_b200.TP_net(16, 15, 5).to(dev)
     eng = mupe_b200.HsEngine(cfg, dev)
+    eng.set_tick_mapping(int(os.environ.get("HS_TICK_MAPPING", "0")))      # 1: 4 lanes per env, 2: one lane per env
     a = 0.9 / 2 ** 0.5
     dpos = torch.rand(E, 3, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a + 0.1, 0.5], device=dev)
     tpos = torch.rand(E, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([-a + 0.1, -a + 0.1, 0.5], device=dev)
