@@ -342,7 +342,11 @@ class InitTracker(Transform):
     """Adds "is_init": true on the first tick after a reset."""
 
     def _call(self, td):
-        td.set("is_init", torch.zeros_like(td.get("done")))
+        done = td.get("done")
+        z = getattr(self, "_zeros", None)
+        if z is None or z.shape != done.shape or z.device != done.device:
+            z = self._zeros = torch.zeros_like(done)      # read-only constant: one allocation, no launch per step
+        td.set("is_init", z)
         return td
 
     def reset(self, td):
@@ -438,10 +442,21 @@ class SyncDataCollector:
         td = self.policy(td) if self.policy is not None else td.update(self.env.action_spec.rand())
         return self.env.step(td)
 
+    def _any_done(self, done) -> bool:
+        """`done.any()` without a device sync whenever the env can rule it out on the host (progress counters)."""
+        base = getattr(self.env, "base_env", self.env)
+        eng = getattr(base, "engine", None)
+        if eng is not None and hasattr(eng, "maybe_done"):
+            if eng.host_max_progress is None:
+                eng.refresh_host_progress()               # one sync after a partial reset / injected state
+            if not eng.maybe_done():
+                return False
+        return bool(done.any())
+
     def _carry(self, td: TensorDict):
         done = td.get(("next", "done"))
         td = step_mdp(td)
-        if self.reset_when_done and bool(done.any()):
+        if self.reset_when_done and self._any_done(done):
             td.set("_reset", done.clone())
             td = self.env.reset(td)
             td.pop("_reset", None)
@@ -469,7 +484,7 @@ class SyncDataCollector:
                         continue
                     v = td.get(k)
                     pre[k] = torch.empty((steps,) + tuple(v.shape), dtype=v.dtype, device=v.device)
-                self._stats_T = torch.empty(steps, E, len(base.stats.keys()), device=dev)
+                self._stats_T = torch.empty((steps,) + tuple(eng.stats.shape), device=dev)     # [T, 24, E]: one copy per step
                 self._prev_action_T = torch.empty((steps,) + tuple(eng.prev_action.shape), device=dev)
                 # entries of ``next`` that transforms add on top of the engine's outputs (is_init, ...)
                 engine_keys = {tup(k) for k in base.rollout_next_td(self._stats_T, self._prev_action_T).keys(True, True)}
@@ -477,10 +492,10 @@ class SyncDataCollector:
                     if tup(k) not in engine_keys:
                         v = nxt.get(k)
                         pre[("next",) + tup(k)] = torch.empty((steps,) + tuple(v.shape), dtype=v.dtype, device=v.device)
-            for k, buf in pre.items():
-                buf[t].copy_(td.get(k))
-            torch.stack([nxt.get(("stats", k)).reshape(E) for k in base.stats.keys()], dim=-1, out=self._stats_T[t])
-            self._prev_action_T[t].copy_(eng.prev_action)
+            # one multi-tensor copy for the whole input side, one for the 24 stats rows (the engine keeps them as [24, E])
+            dsts = [buf[t] for buf in pre.values()] + [self._stats_T[t], self._prev_action_T[t]]
+            srcs = [td.get(k) for k in pre.keys()] + [eng.stats, eng.prev_action]
+            torch._foreach_copy_(dsts, srcs)
             self._carry(td)
         out = TensorDict({}, [E, steps], dev)
         out.set("next", base.rollout_next_td(self._stats_T, self._prev_action_T))

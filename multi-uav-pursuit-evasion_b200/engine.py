@@ -146,6 +146,9 @@ class HsEngine:
             self.sets = [OutputSet(cfg, device) for _ in range(max(1, num_output_sets))]
         self._bufs = [self._make_bufs(i) for i in range(len(self.sets))]
         self.cur = len(self.sets) - 1          # index of the set holding the latest outputs
+        # Host-side upper bound of the env progress counters (None = unknown): `done` is progress >= max_episode_length
+        # (hideandseek.py:1008-1010), so callers can rule out "some env is done" without reading the device.
+        self.host_max_progress: Optional[int] = 0
         self._keep = []                        # keeps caller tensors alive across async launches
         # identity quaternions so that an un-reset arena is still well formed
         ident = torch.zeros(self.E, self.A, 4, device=device)
@@ -186,7 +189,18 @@ class HsEngine:
             return (self.cur + 1) % len(self.sets)
         return self.storage.T if reset else (self._slot + 1) % self.storage.T
 
+    def maybe_done(self) -> bool:
+        """False: certainly no env reports done after the latest tick (host-side counter, no device sync)."""
+        return self.host_max_progress is None or self.host_max_progress >= self.cfg.max_episode_length
+
+    def refresh_host_progress(self) -> int:
+        """Re-reads the largest progress counter from the device (one sync; after partial resets / state injection)."""
+        self.host_max_progress = int(self.get_state(_lib.FIELD_PROGRESS).max().item())
+        return self.host_max_progress
+
     def _advance(self, reset: bool = False):
+        if not reset and self.host_max_progress is not None:
+            self.host_max_progress += 1
         i = self.next_index(reset)
         if self.storage is not None and not reset:
             self._slot = i
@@ -477,6 +491,7 @@ class HsEngine:
             m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
             m = m.contiguous()
         self._advance(reset=True)
+        self.host_max_progress = 0 if m is None else None       # a partial reset leaves the other envs' counters unknown
         self._keep = [m, drone_pos, drone_rot, target_pos, cyl_pos]
         check(lib.hs_reset(self._h, _ptr(m), drone_pos.data_ptr(), drone_rot.data_ptr(), target_pos.data_ptr(),
                            _ptr(cyl_pos), self._stream()), "hs_reset")
@@ -518,6 +533,8 @@ class HsEngine:
 
     def set_state(self, field: int, value: torch.Tensor):
         v = value.to(self.device, torch.float32).reshape(self._SHAPES[field](self)).contiguous()
+        if field == _lib.FIELD_PROGRESS:
+            self.host_max_progress = None
         if v.numel():
             check(lib.hs_state_set(self._h, field, v.data_ptr(), self._stream()), "hs_state_set")
             self._keep.append(v)
@@ -595,6 +612,9 @@ class RotatingRolloutGraph:
     def replay(self):
         self.graph.replay()
         self.replays += 1
+        for e in self.engines:
+            if e.host_max_progress is not None:
+                e.host_max_progress += self.per_engine
         for e, k in zip(self.engines, self.kernels):
             # (cur is unchanged: every engine advanced by a multiple of its set count)
             e._uncounted = getattr(e, "_uncounted", 0) + k + getattr(self, "policy_kernels", 0) * self.per_engine

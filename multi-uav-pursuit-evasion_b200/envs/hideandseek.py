@@ -320,7 +320,7 @@ class HideAndSeek(IsaacEnv):
 
     def rollout_next_td(self, stats: torch.Tensor, prev_action: torch.Tensor) -> TensorDict:
         """``next`` of a finished rollout as ``[E, T]`` views of the engine's time-major RolloutStorage
-        (rollout mode, ``env.rollout_steps=T``): nothing is copied.  ``stats`` ``[T, E, 24]`` and
+        (rollout mode, ``env.rollout_steps=T``): nothing is copied.  ``stats`` ``[T, 24, E]`` and
         ``prev_action`` ``[T, E, A, 4]`` are the per-step snapshots of the two live buffers the tick
         updates in place (the reference's collector clones them with every step too)."""
         st = self.engine.storage
@@ -336,7 +336,7 @@ class HideAndSeek(IsaacEnv):
         if self.use_TP_net:
             agents["TP"] = TensorDict({"TP_input": b["tp_input"], "TP_groundtruth": b["tp_groundtruth"],
                                        "TP_done": b["tp_done"]}, [E, T], dev)
-        stats_td = TensorDict({k: stats[..., i:i + 1].transpose(0, 1) for i, k in enumerate(STAT_KEYS)}, [E, T], dev)
+        stats_td = TensorDict({k: stats[:, i].transpose(0, 1).unsqueeze(-1) for i, k in enumerate(STAT_KEYS)}, [E, T], dev)
         info = TensorDict({"drone_state": b["drone_state"], "prev_action": prev_action.transpose(0, 1)}, [E, T], dev)
         return TensorDict({"agents": agents, "stats": stats_td, "info": info, "done": b["done"]}, [E, T], dev)
 

@@ -78,7 +78,12 @@ class IsaacEnv(EnvBase):
         self._should_render = (lambda substep: enable) if isinstance(enable, bool) else enable
 
     def render(self, mode: str = "human"):
-        return None            # no viewport in this backend
+        """No viewport in this backend: "rgb_array" returns a black 4x4 frame so that the reference's evaluation loop
+        (scripts/train.py:212-246 stacks the frames into a video) keeps its shape contract."""
+        if mode == "rgb_array":
+            import numpy as np
+            return np.zeros((4, 4, 3), dtype=np.uint8)
+        return None
 
     def close(self):
         self._is_closed = True
