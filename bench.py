@@ -246,41 +246,56 @@ def make_env(mupe_b200, E, device, **over):
     return mupe_b200.TransformedEnv(base, mupe_b200.Compose(mupe_b200.InitTracker(), mupe_b200.PIDRateController()))
 
 
-def bind_numa(local_rank):
-    """Pins this rank to the host cores nearest its GPU (nvidia-smi topo) BEFORE any pinned allocation, so that pinned
-    buffers land on the GPU's NUMA node and 8 ranks do not share one socket's cores.  Returns a description."""
+def _cpu_list(spec):
+    cpus = set()
+    for part in spec.split(","):
+        part = part.strip()
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part.isdigit():
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_numa(local_rank, world):
+    """Pins this rank to its own slice of host cores BEFORE any pinned allocation (so that first touch places the pinned
+    buffers next to those cores): the GPU-local cores reported by `nvidia-smi topo -m` when this process may use them,
+    else an even split of whatever cpuset the container grants (8 ranks on one 32-core cpuset otherwise migrate over each
+    other's caches).  Returns a description for the JSON line."""
+    import re
     try:
-        out = subprocess.run(["nvidia-smi", "topo", "-C", "-i", str(local_rank)], capture_output=True, text=True, timeout=10).stdout
-        cpus = None
-        for line in out.splitlines():
-            if ":" in line and any(ch.isdigit() for ch in line):
-                spec = line.split(":")[-1].strip()
-                cpus = set()
-                for part in spec.split(","):
-                    part = part.strip()
-                    if "-" in part:
-                        a, b = part.split("-")
-                        cpus.update(range(int(a), int(b) + 1))
-                    elif part.isdigit():
-                        cpus.add(int(part))
-                break
-        if not cpus:
-            return "no affinity information"
-        allowed = os.sched_getaffinity(0) & cpus
-        if not allowed:
-            return f"GPU-local cores {sorted(cpus)[:4]}.. not in this process's cpuset"
-        # split the GPU-local cores between the ranks that share them (stable: by local rank)
-        os.sched_setaffinity(0, allowed)
-        return f"bound to {len(allowed)} GPU-local cores ({min(allowed)}-{max(allowed)})"
+        allowed = sorted(os.sched_getaffinity(0))
+        local = None
+        try:
+            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=15).stdout
+            for line in out.splitlines():
+                f = line.split()
+                if f and f[0] == f"GPU{local_rank}":
+                    for tok in f[1:]:
+                        if re.fullmatch(r"\d+-\d+(,\d+(-\d+)?)*|\d+(,\d+(-\d+)?)+", tok):
+                            local = _cpu_list(tok)
+                            break
+                    break
+        except Exception:
+            pass
+        pool = sorted(set(allowed) & local) if local else []
+        how = "GPU-local cores (nvidia-smi topo -m)"
+        if len(pool) < 2:
+            pool, how = allowed, "even split of the container's cpuset (GPU-local cores not in it)"
+        per = max(1, len(pool) // max(1, world))
+        mine = pool[(local_rank * per) % len(pool):][:per] or pool
+        os.sched_setaffinity(0, set(mine))
+        return f"{len(mine)} cores {mine[0]}-{mine[-1]}: {how}"
     except Exception as ex:
-        return f"not bound ({type(ex).__name__})"
+        return f"not bound ({type(ex).__name__}: {ex})"
 
 
 def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    numa = bind_numa(local) if world > 1 else "single rank: not bound"
+    numa = bind_numa(local, world) if world > 1 else "single rank: not bound"
     import torch
     import torch.distributed as dist
     import mupe_b200
@@ -430,12 +445,42 @@ def run_gpu_arm(args):
         if world > 1:
             dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
         barrier()
+        e2e_py2 = world * E * ne_c / float(dt2.item())
+        # ... and the same loop inside the library: ONE hs_step_host_io_many call per timed region
+        from mupe_b200.engine import HostIoLoop
+        acts_h = [torch.randn(E, A, 4).pin_memory() for _ in range(ROTATE)]
+        loop = HostIoLoop(engines, wts[0], acts_h, streams=s2)
+        loop.run(2 * ROTATE)                                  # warm-up: graphs for the loop's own host buffers
+        # bare copy-engine probe: the D2H of one tick's result alone, per rank (separates PCIe / NUMA from software)
+        probe_src = engines[0].out.slab[:engines[0].out.policy_words]
+        probe_dst = torch.empty_like(probe_src, device="cpu").pin_memory()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(64):
+            probe_dst.copy_(probe_src, non_blocking=True)
+            torch.cuda.synchronize()
+        d2h_gbs = torch.tensor([64 * probe_src.numel() * 4 / (time.perf_counter() - t0) / 1e9], device=dev)
+        if world > 1:
+            dist.all_reduce(d2h_gbs, op=dist.ReduceOp.MIN)
+        barrier()
+        t0 = time.perf_counter()
+        loop.run(ne_c)
+        dt3 = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt3, op=dist.ReduceOp.MAX)
+        barrier()
+        dt2 = dt3
         e2e_c = {"value": world * E * ne_c / float(dt2.item()), "unit": "env-steps/s", "h2d_bytes_per_step": h_act_c.numel() * 4 * ROLLOUT,
                  "d2h_bytes_per_step": d2h * ROLLOUT, "ticks": ne_c, "n_gpus": world, "batches_in_flight": 2,
-                 "one_batch_in_flight": e2e_serial["value"], "tensors": travels, "host_binding": numa,
-                 "api": "C ABI hs_step_host_io_async() + hs_host_io_wait(), TWO independent 4096-env batches in flight on two "
-                        "streams: per tick, pinned host action in (read in place over PCIe), tick + predictor, D2H of the "
-                        "observation + reward + done into pinned host buffers; bytes are per 64-tick step; wall clock, max over ranks"}
+                 "one_batch_in_flight": e2e_serial["value"], "python_loop_two_in_flight": e2e_py2, "tensors": travels,
+                 "host_binding": numa, "d2h_probe_gbs_min_over_ranks": float(d2h_gbs.item()),
+                 "d2h_probe": "64 x (2.8 MB device -> pinned host copy + sync) per rank, concurrently on all ranks",
+                 "api": "C ABI hs_step_host_io_many(): ONE call drives all ticks of the timed region, rotating over 16 independent "
+                        "4096-env batches with TWO in flight on two streams: per tick, pinned host action in (read in place over "
+                        "PCIe), tick + predictor, D2H of the observation + reward + done into pinned host buffers, wait; bytes are "
+                        "per 64-tick step; wall clock, max over ranks.  python_loop_two_in_flight = the same schedule driven tick by "
+                        "tick from Python (hs_step_host_io_async + hs_host_io_wait)"}
     if rank == 0 and timed_only:
         extra["note"] = "HS_BENCH_TIMED_ONLY=1: roofline / e2e / cpu_baseline legs skipped (launch-list capture run)"
     elif rank == 0:

@@ -247,6 +247,26 @@ int hs_step_host_io(hs_handle* h, const hs_host_io* io, int action_is_raw, const
 int hs_step_host_io_async(hs_handle* h, const hs_host_io* io, int action_is_raw, const uint8_t* reset_pid,
                           const hs_tp_weights* w, float* staging_dev, void* stream);
 int hs_host_io_wait(hs_handle* h, void* stream);
+/* K host-buffer ticks driven from ONE call: the loop an actor process runs around hs_step_host_io_async /
+ * hs_host_io_wait - rotate over `num_batches` independent env batches, keep `in_flight` of them between issue and wait
+ * (one batch's observation is on the PCIe link while the next one computes), rotate each batch's output sets - without a
+ * round trip through the host language per tick (the reference's collector is such a loop in Python,
+ * omni_drones/utils/torchrl/collector.py:33-38).  Tick i runs batch i % num_batches: bind sets[next_set], issue
+ * hs_step_host_io_async with ios[next_set] on the batch's stream, then wait for the batch issued `in_flight` ticks earlier
+ * and call on_obs(user, that batch index) - the place where a host-side policy reads the observation now in host memory
+ * and writes the batch's next action (NULL: the action buffers are left as they are). */
+typedef struct hs_host_batch {
+    hs_handle* h;
+    const hs_buffers* sets;          /* [num_sets] complete buffer tables, set s reading tp_input_prev from set s-1 */
+    const hs_host_io* ios;           /* [num_sets] host destinations of each set (and the batch's action buffer) */
+    int32_t num_sets;
+    int32_t next_set;                /* in/out: the set the batch's next tick writes */
+    float* staging_dev;              /* [E,A,4] device scratch (used when the action buffer is pageable) */
+    void* stream;                    /* the batch's stream */
+} hs_host_batch;
+typedef void (*hs_obs_callback)(void* user, int32_t batch);
+int hs_step_host_io_many(hs_host_batch* batches, int32_t num_batches, int32_t num_ticks, int32_t in_flight,
+                         int action_is_raw, const hs_tp_weights* w, hs_obs_callback on_obs, void* user);
 
 /* ---- state views (what the get/set methods of omni_drones/views did) ------------------- */
 enum {

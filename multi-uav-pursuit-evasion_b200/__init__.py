@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import HsError
 from .compat import (Compose, InitTracker, SyncDataCollector, TensorDict, TransformedEnv, step_mdp)
 from .config import Cfg, build_hs_config, compose, load_drone_params
-from .engine import HsEngine, RolloutStorage
+from .engine import HostIoLoop, HsEngine, RolloutStorage
 from . import rollout
 from .rollout import compute_gae
 from .policy import FusedPolicy, MAPPOActorCritic
@@ -68,6 +68,6 @@ def install_shim(force_standins: bool = False) -> dict:
     return bound
 
 
-__all__ = ["shim_path", "install_shim", "parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "MAPPOActorCritic", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+__all__ = ["shim_path", "install_shim", "HostIoLoop", "parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "MAPPOActorCritic", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
            "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
            "HideAndSeek", "HideAndSeek_envgen", "GenBuffer", "Hover", "IsaacEnv", "PIDRateController", "TP_net"]

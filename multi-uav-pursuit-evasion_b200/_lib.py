@@ -97,6 +97,15 @@ class hs_host_io(C.Structure):
                 ("obs_cylinders", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p)]
 
 
+class hs_host_batch(C.Structure):
+    """include/hs_b200.h::hs_host_batch (hs_step_host_io_many)."""
+    _fields_ = [("h", C.c_void_p), ("sets", C.POINTER(hs_buffers)), ("ios", C.POINTER(hs_host_io)), ("num_sets", C.c_int32),
+                ("next_set", C.c_int32), ("staging_dev", C.c_void_p), ("stream", C.c_void_p)]
+
+
+HS_OBS_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
+
+
 class hs_gen_params(C.Structure):
     """include/hs_b200.h::hs_gen_params (HideAndSeek_envgen control plane)."""
     _fields_ = [("num_agents", C.c_int32), ("num_cylinders", C.c_int32), ("arena_size", C.c_float),
@@ -155,6 +164,8 @@ _EXPORTS = {
     "hs_step_host_io_async": (C.c_int, [C.c_void_p, C.POINTER(hs_host_io), C.c_int, C.c_void_p, C.POINTER(hs_tp_weights),
                                         C.c_void_p, C.c_void_p]),
     "hs_host_io_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hs_step_host_io_many": (C.c_int, [C.POINTER(hs_host_batch), C.c_int32, C.c_int32, C.c_int32, C.c_int, C.POINTER(hs_tp_weights),
+                                       C.c_void_p, C.c_void_p]),
     "hs_gen_sample_nearby": (C.c_int, [C.POINTER(hs_gen_params), C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "hs_fps_scratch_bytes": (C.c_int64, [C.c_int64]),

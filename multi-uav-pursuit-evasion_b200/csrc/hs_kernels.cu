@@ -1031,6 +1031,33 @@ int hs_step_host_io_async(hs_handle* h, const hs_host_io* io, int action_is_raw,
     return HS_OK;
 }
 
+int hs_step_host_io_many(hs_host_batch* batches, int32_t num_batches, int32_t num_ticks, int32_t in_flight,
+                         int action_is_raw, const hs_tp_weights* w, hs_obs_callback on_obs, void* user) {
+    if (!batches || num_batches < 1 || num_ticks < 0 || in_flight < 1 || in_flight > num_batches)
+        return set_err(HS_ERR_INVALID, "hs_step_host_io_many: need 1 <= in_flight <= num_batches and num_ticks >= 0%s");
+    for (int32_t b = 0; b < num_batches; ++b)
+        if (!batches[b].h || !batches[b].sets || !batches[b].ios || batches[b].num_sets < 1 || batches[b].next_set < 0 ||
+            batches[b].next_set >= batches[b].num_sets)
+            return set_err(HS_ERR_INVALID, "hs_step_host_io_many: incomplete batch descriptor%s");
+    for (int32_t i = 0; i < num_ticks + in_flight - 1; ++i) {
+        if (i < num_ticks) {
+            hs_host_batch& B = batches[i % num_batches];
+            int rc = hs_bind_buffers(B.h, &B.sets[B.next_set]);
+            if (rc != HS_OK) return rc;
+            rc = hs_step_host_io_async(B.h, &B.ios[B.next_set], action_is_raw, nullptr, w, B.staging_dev, B.stream);
+            if (rc != HS_OK) return rc;
+            B.next_set = (B.next_set + 1) % B.num_sets;
+        }
+        const int32_t j = i - (in_flight - 1);                   // the tick whose results the host needs now
+        if (j >= 0) {
+            hs_host_batch& W = batches[j % num_batches];
+            CUDA_OK(cudaStreamSynchronize((cudaStream_t)W.stream));
+            if (on_obs) on_obs(user, j % num_batches);
+        }
+    }
+    return HS_OK;
+}
+
 static int field_desc(const hs_handle* h, int field, int* row0, int* n_slots, int* width, int* stride_slot,
                       int* stride_comp) {
     const int A = h->cfg.num_agents, C = h->cfg.num_cylinders;

@@ -289,7 +289,9 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
             XS(9 * a + WX_POLD) = p.x; XS(9 * a + WX_POLD + 1) = p.y; XS(9 * a + WX_POLD + 2) = p.z;
         }
     }
-    if (!RESET) __syncthreads();                                  // (1) thrusts, repulsion terms, old positions published
+    // (1) thrusts, repulsion terms, old positions published - and every warp has read the evader rows of the tile, which
+    // the evader warp overwrites next (also in the RESET variant: compute-sanitizer racecheck found that one)
+    __syncthreads();
 
     // ================= phase 2: wrench + integration (pursuers) | evader policy (evader warp) =======
     if (is_drone) {

@@ -618,3 +618,66 @@ class RotatingRolloutGraph:
         for e, k in zip(self.engines, self.kernels):
             # (cur is unchanged: every engine advanced by a multiple of its set count)
             e._uncounted = getattr(e, "_uncounted", 0) + k + getattr(self, "policy_kernels", 0) * self.per_engine
+
+
+class HostIoLoop:
+    """hs_step_host_io_many: K host-buffer ticks rotating over several engines (independent env batches of one GPU) from
+    ONE C call - per tick pinned host action in, tick + predictor, observation / reward / done back in pinned host memory,
+    `in_flight` batches between issue and wait.  The per-tick host work of the Python loop around
+    ``HsEngine.step_host(sync=False)`` / ``wait_host()`` (ctypes call, graph lookup, set rotation, stream sync: ~25 us,
+    and N ranks share the host's cores) stays inside the library.  ``on_obs(batch_index)`` is called when a batch's
+    results are in host memory - where a host-side policy writes that batch's next action."""
+
+    def __init__(self, engines, tp_weights, actions_host, streams=None):
+        dev = engines[0].device
+        n = len(engines)
+        self.engines, self.weights = list(engines), tp_weights
+        self.streams = streams or [torch.cuda.Stream(dev) for _ in range(2)]
+        self.batches = (_lib.hs_host_batch * n)()
+        self._keep = [actions_host]
+        self.views = []
+        for b, (e, act) in enumerate(zip(engines, actions_host)):
+            if e.storage is not None:
+                raise _lib.HsError("HostIoLoop needs slab output sets (rollout_steps=None)")
+            E, A = e.E, e.A
+            ns = len(e.sets)
+            mirror = torch.empty(e.sets[0].policy_words, dtype=torch.float32).pin_memory()
+            done = torch.empty(E, dtype=torch.uint8).pin_memory()
+            staging = torch.empty(E, A, 4, dtype=torch.float32, device=dev)
+            sets = (hs_buffers * ns)(*[e._make_bufs(i) for i in range(ns)])
+            ios = (_lib.hs_host_io * ns)()
+            per_set = []
+            for i in range(ns):
+                out, base = e.sets[i], e.sets[i].slab.data_ptr()
+                v = {}
+                for k in ("state_self", "state_others", "obs_cylinders", "reward"):
+                    t = out.t[k]
+                    off = (t.data_ptr() - base) // 4
+                    v[k] = mirror[off:off + t.numel()].view(t.shape)
+                    setattr(ios[i], k, v[k].data_ptr() if t.numel() else None)
+                ios[i].done = done.data_ptr()
+                ios[i].action = act.data_ptr()
+                per_set.append(v)
+            self.views.append((per_set, done))
+            hb = self.batches[b]
+            hb.h, hb.sets, hb.ios, hb.num_sets = e._h, sets, ios, ns
+            hb.next_set = e.next_index()
+            hb.staging_dev = staging.data_ptr()
+            hb.stream = self.streams[b % len(self.streams)].cuda_stream
+            self._keep += [mirror, done, staging, sets, ios]
+
+    def run(self, num_ticks: int, in_flight: int = 2, on_obs=None):
+        cb = _lib.HS_OBS_CALLBACK(lambda user, b: on_obs(int(b))) if on_obs is not None else None
+        w = self.weights
+        for b, e in enumerate(self.engines):
+            self.batches[b].next_set = e.next_index()
+        check(lib.hs_step_host_io_many(self.batches, len(self.engines), int(num_ticks), int(in_flight), 1,
+                                       C.byref(w) if w is not None else None, cb, None), "hs_step_host_io_many")
+        n = len(self.engines)
+        for b, e in enumerate(self.engines):
+            ticks_b = num_ticks // n + (1 if b < num_ticks % n else 0)
+            if ticks_b:
+                e.cur = (self.batches[b].next_set - 1) % len(e.sets)      # the library bound that set last
+                if e.host_max_progress is not None:
+                    e.host_max_progress += ticks_b
+        return self

@@ -162,6 +162,61 @@ def gen_case(name, pk, E, scenario, min_cyl, ticks, progress0):
     print(f"{name}: reference == oracle on {ticks} ticks; wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def gen_partial_reset(name="partial_reset_tp", E=16, warm_ticks=3):
+    """IsaacEnv._reset with a PARTIAL `_reset` mask in the middle of an episode, executed by the reference's own source
+    (isaac_env.py:210-225 -> hideandseek.py:609-723): the quirks of SURVEY App. D ride on it - the evader's velocity and the
+    rate slots of prev_action are NOT reset, first_capture_step is overwritten for every env, the extra physics tick moves
+    the envs outside the mask too, and the stats handed back are the pre-reset clone."""
+    torch.manual_seed(0)
+    P = O.HSParams()
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    init = O.sample_reset(P, E, g, "random_cylinders")
+    ref = RefEnv(P, E, use_random_cylinder=True, scenario_flag="empty")
+    tp_fn = lambda x: ref.env.TP(x).detach()
+    rec = {f"tp_weights/{k}": v.numpy() for k, v in ref.env.TP.state_dict().items()}
+    full = torch.ones(E, dtype=torch.bool)
+    ref.reset_with(full, init)
+    done_prev = torch.zeros(E, dtype=torch.bool)
+    for t in range(warm_ticks):
+        nxt, _ = ref.step(torch.randn(E, P.num_agents, 4, generator=g), done_prev)
+        done_prev = nxt["done"].reshape(-1).clone()
+    init2 = O.sample_reset(P, E, g, "random_cylinders")
+    mask = torch.rand(E, generator=g) < 0.5
+    mask[0], mask[1] = True, False
+    pre = snapshot_state(ref)
+    orc = O.HideAndSeekOracle(P, E)
+    load_oracle_state(orc, pre)
+    r = ref.reset_with(mask, init2)
+    o = orc.reset(mask, init2, tp_fn)
+    ro = dict(state_self=r["agents"]["observation"]["state_self"], cylinders=r["agents"]["observation"]["cylinders"],
+              others=r["agents"]["observation"]["state_others"], state_drones=r["agents"]["state"]["state_drones"],
+              drone_state=r["info"]["drone_state"], tp_input=r["agents"]["TP"]["TP_input"],
+              last_stats=torch.cat([r["stats"][k] for k in O.STAT_KEYS], dim=-1), truncated=r["truncated"].float())
+    ro["tp_pred"] = ref.env.TP(ro["tp_input"]).detach()
+    post = snapshot_state(ref)
+    for k, v in ro.items():
+        check(f"{name}/{k}", v, o[k].float())
+    for k in ("pos", "quat", "linvel", "angvel", "tpos", "tvel", "progress"):
+        check(f"{name}/post/{k}", post[k], orc.st[k])
+    check(f"{name}/post/throttle", post["throttle"], orc.throttle)
+    check(f"{name}/post/stats", post["stats"], orc.stats)
+    check(f"{name}/post/prev_action", post["prev_action"], orc.prev_action)
+    rec["mask"] = mask.numpy()
+    for k, v in init2.items():
+        rec[f"init/{k}"] = v.numpy()
+    for k, v in pre.items():
+        rec[f"pre/{k}"] = v.numpy()
+    for k, v in ro.items():
+        rec[f"out/{k}"] = v.detach().clone().float().numpy()
+    for k, v in post.items():
+        rec[f"post/{k}"] = v.numpy()
+    rec["meta/params"] = np.array(repr({}))
+    rec["meta/E"] = np.array(E)
+    path = os.path.join(OUT_DIR, f"reset_{name}.npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: reference == oracle for a partial-mask reset ({int(mask.sum())}/{E} envs); wrote {path}")
+
+
 def main():
     if not os.path.isdir("/root/reference"):
         raise SystemExit("gen_golden needs the reference tree at /root/reference (build container only)")
@@ -169,6 +224,8 @@ def main():
     for name, spec in CASES.items():
         if not only or name in only:
             gen_case(name, *spec)
+    if not only or "partial_reset_tp" in only:
+        gen_partial_reset()
 
 
 if __name__ == "__main__":

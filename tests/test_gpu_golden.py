@@ -110,3 +110,41 @@ def test_kernels_replay_reference_ticks(path, exact):
         # the IEEE build reproduces the reference's numbers without ANY exemption: no flipped indicator, and nothing
         # beyond the plain 1e-4 tolerance (not even inside the conditioning allowance)
         assert n_exempt == 0 and n_dv == 0, (G.name, n_exempt, n_dv, used)
+
+
+@pytest.mark.parametrize("mapping", [1, 2], ids=["4-lane", "1-lane"])
+def test_partial_mask_reset_replays_reference(mapping):
+    """hs_reset with a partial mask against what the REFERENCE'S OWN `_reset` produced (tests/golden/
+    reset_partial_reset_tp.npz): observation, the pre-reset stats clone, progress, prev_action, and the quirks
+    (evader velocity kept, first_capture_step rewritten everywhere, the extra physics tick for every env)."""
+    import numpy as np
+    import mupe_b200
+    from mupe_b200 import _lib as L
+    from oracle import hs_oracle as O
+    from tests.golden_util import GOLDEN_DIR
+    G = Golden.__new__(Golden)
+    z = np.load(os.path.join(GOLDEN_DIR, "reset_partial_reset_tp.npz"), allow_pickle=False)
+    G.z = {k: z[k] for k in z.files}
+    P, E = O.HSParams(), int(G.z["meta/E"])
+    dev = torch.device("cuda:0")
+    eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    eng.set_tick_mapping(mapping)
+    pre, post, out, init = G.group("pre/"), G.group("post/"), G.group("out/"), G.group("init/")
+    # a first full reset so that the TP history exists, then the fixture's pre-reset state
+    eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    load_engine_state(eng, pre)
+    last_stats = eng.stats.t().clone()
+    mask = torch.from_numpy(G.z["mask"].copy())
+    got = eng.reset(mask.to(dev), init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    eng.step_post(out["tp_pred"].to(dev))
+    for k in ("state_self", "cylinders", "others", "state_drones", "drone_state", "tp_input"):
+        assert_close(f"partial_reset/{k}", got[NAMES.get(k, k)], out[k])
+    assert_close("partial_reset/last_stats", last_stats, out["last_stats"])
+    assert torch.equal(got["truncated"].cpu().reshape(-1).float(), out["truncated"].reshape(-1))
+    for f, k in ((L.FIELD_DRONE_POS, "pos"), (L.FIELD_DRONE_ROT, "quat"), (L.FIELD_DRONE_LINVEL, "linvel"),
+                 (L.FIELD_DRONE_ANGVEL, "angvel"), (L.FIELD_THROTTLE, "throttle"), (L.FIELD_TARGET_POS, "tpos"),
+                 (L.FIELD_TARGET_VEL, "tvel"), (L.FIELD_PROGRESS, "progress")):
+        assert_close(f"partial_reset/post/{k}", eng.get_state(f), post[k])
+    assert_close("partial_reset/post/stats", eng.stats.t(), post["stats"])
+    assert_close("partial_reset/post/prev_action", eng.prev_action, post["prev_action"])
+    eng.close()

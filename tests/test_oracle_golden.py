@@ -60,3 +60,34 @@ def test_done_tick_divides_stats_once_per_done_step():
     assert prog == [798.0, 799.0, 800.0, 801.0]
     done = [bool(G.group(f"t{t}/out/")["done"][0]) for t in range(G.ticks)]
     assert done == [False, False, True, True]
+
+
+def test_partial_mask_reset_matches_reference():
+    """isaac_env.py:210-225 + hideandseek.py:609-723 run by the reference's own source with a partial `_reset` mask
+    (tests/golden/reset_partial_reset_tp.npz, oracle/gen_golden.py::gen_partial_reset)."""
+    import os
+    import numpy as np
+    from tests.golden_util import GOLDEN_DIR, Golden
+    G = Golden.__new__(Golden)
+    z = np.load(os.path.join(GOLDEN_DIR, "reset_partial_reset_tp.npz"), allow_pickle=False)
+    G.z = {k: z[k] for k in z.files}
+    G.P, G.E = O.HSParams(), int(G.z["meta/E"])
+    tp_fn = G.tp_fn()
+    orc = O.HideAndSeekOracle(G.P, G.E)
+    pre, post, out = G.group("pre/"), G.group("post/"), G.group("out/")
+    load_oracle_state(orc, pre)
+    mask = torch.from_numpy(G.z["mask"].copy())
+    assert 0 < int(mask.sum()) < G.E
+    got = orc.reset(mask, G.group("init/"), tp_fn)
+    for k, v in out.items():
+        assert_close(f"partial_reset/{k}", got[k].float(), v, rtol=2e-5, atol=2e-6)
+    for k in ("pos", "quat", "linvel", "angvel", "tpos", "tvel", "progress"):
+        assert_close(f"partial_reset/post/{k}", orc.st[k], post[k], rtol=2e-5, atol=2e-6)
+    assert_close("partial_reset/post/stats", orc.stats, post["stats"], rtol=2e-5, atol=2e-6)
+    assert_close("partial_reset/post/prev_action", orc.prev_action, post["prev_action"], rtol=2e-5, atol=2e-6)
+    # the quirks: evader velocity survives the reset, first_capture_step is rewritten for EVERY env, envs outside the mask
+    # still take the extra physics tick
+    assert torch.equal(post["tvel"], pre["tvel"])
+    assert (post["stats"][:, O.S["first_capture_step"]] == G.P.max_episode_length).all()
+    assert not torch.equal(post["pos"][~mask], pre["pos"][~mask])
+    assert torch.equal(post["progress"][~mask], pre["progress"][~mask]) and (post["progress"][mask] == 0).all()
