@@ -302,7 +302,8 @@ def run_gpu_arm(args):
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), timeout=datetime.timedelta(seconds=120))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     torch.manual_seed(1000 + rank)
@@ -332,14 +333,14 @@ def run_gpu_arm(args):
     rollout_graph = None if per_tick else RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT)
     ret_row = 17                                              # stats["return"]
 
-    def rollout(step_index):
+    def rollout(step_index, collective=True):
         """One bench step: 64 ticks + the collective of the path."""
         if rollout_graph is not None:
             rollout_graph.replay()
         else:
             for j in range(ROLLOUT):
                 engines[j % ROTATE].replay_tick()
-        if world > 1:
+        if world > 1 and collective:
             # episode returns of the batch that closed the rollout, all ranks (north_star: one all_gather per rollout)
             dist.all_gather(gather_buf, engines[(ROLLOUT - 1) % ROTATE].stats[ret_row])
 
@@ -360,7 +361,7 @@ def run_gpu_arm(args):
         t_end = time.perf_counter() + seconds
         i = 0
         while time.perf_counter() < t_end:
-            rollout(i)
+            rollout(i, collective=False)          # time-bounded loop: ranks run different counts, so no collective here
             i += 1
             torch.cuda.synchronize()
     if rank == 0 and not timed_only:

@@ -153,6 +153,8 @@ typedef struct hs_buffers {
                                    `update_epoch` changes (hideandseek.py:988-991; scripts/train_deploy.py writes
                                    base_env.update_epoch every iteration).  Read by every tick, so captured CUDA
                                    graphs follow the curriculum without re-capture. */
+    float* throttle_diff;       /* [E,A] or NULL: |throttle_t - throttle_{t-1}|_2 per pursuer = drone.throttle_difference
+                                   (multirotor.py:480-484), an output for callers that log it (Hover's action_smoothness) */
 } hs_buffers;
 
 typedef struct hs_handle hs_handle;
@@ -318,6 +320,33 @@ enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZE
  * Both give bit-identical results.  The one-lane mapping needs num_envs % 4 == 0 (16-byte row pitch of the stats
  * tensor map) and distinct tp_input / tp_input_prev buffers; otherwise auto stays with the 4-lane kernel. */
 int hs_set_option(hs_handle* h, int option, int value);
+
+/* ---- Hover (BASELINE config 1): observation / reward / stats post-kernel ------------------ */
+/* omni_drones/envs/single/hover.py:334-523 after a tick of a handle created with num_agents == 1, num_cylinders == 0:
+ * _pre_sim_step's logging stats (:334-359), _compute_state_and_obs (:361-437) and _compute_reward_and_done (:439-523) in
+ * one launch, one thread per env.  Reads what the tick left in the handle's bound buffers (drone_state, rotor_cmds, ctbr,
+ * target_rate, throttle_diff) and the arena (progress, throttle).  Stats slot order = the declaration order of the
+ * reference's stats spec (:239-279), stats layout [HS_HOVER_NUM_STATS][E]. */
+#define HS_HOVER_NUM_STATS 39
+#define HS_HOVER_NUM_STATE 12
+typedef struct hs_hover_params {
+    float reward_distance_scale, reward_v_scale, reward_acc_scale, reward_jerk_scale;
+    float linear_vel_max, linear_acc_max;
+    float alpha;                        /* 0.8: stats.lerp_(x, 1 - alpha)  hover.py:498-501 */
+    float target_pos[3];                /* (0, 0, 1)  hover.py:149 */
+    int32_t time_encoding;              /* append progress / max_episode_length x 4 */
+    int32_t omega, motor;               /* append the world angular velocity / throttle * 2 - 1 (cfg.task.omega / motor) */
+    int32_t with_reward;                /* 0: the observation half only (what _reset runs), 1: the whole step */
+} hs_hover_params;
+typedef struct hs_hover_io {
+    float* observation;                 /* [E,1,16 (+3 omega) (+4 motor) (+4 time)] */
+    float* reward;                      /* [E,1,1] */
+    uint8_t* done;                      /* [E,1] */
+    float* stats;                       /* [HS_HOVER_NUM_STATS][E] read-modify-write */
+    float* state;                       /* [HS_HOVER_NUM_STATE][E]: last linear/angular v, a, jerk; the six episode sums */
+    const float* target_heading;        /* [E,3] */
+} hs_hover_io;
+int hs_hover_post(hs_handle* h, const hs_hover_params* p, const hs_hover_io* io, void* stream);
 
 /* ---- device-side reset sampler --------------------------- */
 /* Replaces the sampling half of HideAndSeek._reset_idx for use_random_cylinder == 1

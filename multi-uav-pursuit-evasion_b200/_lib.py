@@ -63,7 +63,7 @@ class hs_config(C.Structure):
 _BUF_FIELDS = [
     "arena", "stats", "state_self", "state_others", "obs_cylinders", "state_drones", "tp_input",
     "tp_input_prev", "tp_groundtruth", "tp_done", "reward", "done", "truncated", "drone_state",
-    "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey", "smoothness_coef",
+    "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey", "smoothness_coef", "throttle_diff",
 ]
 
 
@@ -95,6 +95,22 @@ class hs_host_io(C.Structure):
     """include/hs_b200.h::hs_host_io (host-buffer tick)."""
     _fields_ = [("action", C.c_void_p), ("state_self", C.c_void_p), ("state_others", C.c_void_p),
                 ("obs_cylinders", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p)]
+
+
+HS_HOVER_NUM_STATS, HS_HOVER_NUM_STATE = 39, 12
+
+
+class hs_hover_params(C.Structure):
+    """include/hs_b200.h::hs_hover_params."""
+    _fields_ = [("reward_distance_scale", C.c_float), ("reward_v_scale", C.c_float), ("reward_acc_scale", C.c_float),
+                ("reward_jerk_scale", C.c_float), ("linear_vel_max", C.c_float), ("linear_acc_max", C.c_float), ("alpha", C.c_float),
+                ("target_pos", C.c_float * 3), ("time_encoding", C.c_int32), ("omega", C.c_int32), ("motor", C.c_int32),
+                ("with_reward", C.c_int32)]
+
+
+class hs_hover_io(C.Structure):
+    _fields_ = [("observation", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("stats", C.c_void_p),
+                ("state", C.c_void_p), ("target_heading", C.c_void_p)]
 
 
 class hs_host_batch(C.Structure):
@@ -164,6 +180,7 @@ _EXPORTS = {
     "hs_step_host_io_async": (C.c_int, [C.c_void_p, C.POINTER(hs_host_io), C.c_int, C.c_void_p, C.POINTER(hs_tp_weights),
                                         C.c_void_p, C.c_void_p]),
     "hs_host_io_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hs_hover_post": (C.c_int, [C.c_void_p, C.POINTER(hs_hover_params), C.POINTER(hs_hover_io), C.c_void_p]),
     "hs_step_host_io_many": (C.c_int, [C.POINTER(hs_host_batch), C.c_int32, C.c_int32, C.c_int32, C.c_int, C.POINTER(hs_tp_weights),
                                        C.c_void_p, C.c_void_p]),
     "hs_gen_sample_nearby": (C.c_int, [C.POINTER(hs_gen_params), C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,

@@ -43,6 +43,7 @@
 #include "hs_predictor_mma.cuh"
 #include "hs_predictor_tcgen05.cuh"
 #include "hs_reset.cuh"
+#include "hs_hover.cuh"
 #include "hs_samplers.cuh"
 #include "hs_rollout.cuh"
 #include "hs_policy.cuh"
@@ -1055,6 +1056,20 @@ int hs_step_host_io_many(hs_host_batch* batches, int32_t num_batches, int32_t nu
             if (on_obs) on_obs(user, j % num_batches);
         }
     }
+    return HS_OK;
+}
+
+int hs_hover_post(hs_handle* h, const hs_hover_params* p, const hs_hover_io* io, void* stream) {
+    if (!h || !p || !io || !io->observation || !io->stats || !io->state || !io->target_heading)
+        return set_err(HS_ERR_INVALID, "hs_hover_post: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_hover_post: call hs_bind_buffers first%s");
+    if (h->cfg.num_agents != 1) return set_err(HS_ERR_INVALID, "hs_hover_post: the handle must have num_agents == 1%s");
+    if (p->with_reward && (!io->reward || !io->done)) return set_err(HS_ERR_INVALID, "hs_hover_post: reward / done missing%s");
+    KParams P = make_params(h);
+    const unsigned grid = (unsigned)(((int64_t)h->cfg.num_envs + 127) / 128);
+    hs_hover_post_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, *p, *io);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
     return HS_OK;
 }
 

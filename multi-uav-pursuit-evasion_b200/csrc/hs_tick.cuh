@@ -177,6 +177,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
             }
             // ---- rotor model, rotor_group.py:55-71
             stage_rotor(c, cmd, thr, T, yaw_torque, throttle_diff);
+            if (P.b.throttle_diff != nullptr && valid) P.b.throttle_diff[row] = throttle_diff;
         }
         // ---- downwash all-pairs, multirotor.py:488-494, 724-753
         const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];

@@ -280,6 +280,7 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
                 action_err = P.b.action_error[ec * A + a];
             }
             stage_rotor(c, cmd, thr, T, yaw_torque, throttle_diff);
+            if (P.b.throttle_diff != nullptr && valid) P.b.throttle_diff[e * A + a] = throttle_diff;
             if (valid) { SD(D_THR, a) = thr[0]; SD(D_THR + 1, a) = thr[1]; SD(D_THR + 2, a) = thr[2]; SD(D_THR + 3, a) = thr[3]; }
             const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
             const V3 Fw = qrot<false>(q, mk(0.f, 0.f, total_thrust));

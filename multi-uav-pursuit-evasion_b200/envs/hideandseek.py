@@ -425,8 +425,13 @@ class HideAndSeek(IsaacEnv):
         nxt = self._obs_td(out)
         nxt.set(("agents", "reward"), out["reward"])
         nxt.set("done", out["done"])
-        if self._curriculum:
+        # evader-speed curriculum (hideandseek.py:1012-1015): its gate `torch.any(done)` can only open on a tick where some
+        # env finishes an episode - the host-side progress bound knows those ticks, so the two all_reduces of a sharded job
+        # run once per episode instead of every tick; the flag is dropped once the speed has reached its cap
+        if self._curriculum and eng.maybe_done():
             self._update_v_prey(out["done"])
+            if float(eng.v_prey) >= 1.3:
+                self._curriculum = False
         return TensorDict({"next": nxt}, self.batch_size, self.device)
 
     def _update_v_prey(self, done):

@@ -260,6 +260,10 @@ class HideAndSeek_envgen(HideAndSeek):
                                         rng=np.random.default_rng(seed))
         self.all_tasks = None
         self._host_progress = 0
+        # sharded job: this rank owns the envs [env_offset, env_offset + E) of `global_num_envs` (default: a single shard).
+        # The reference's uniform / archive split is a PREFIX of the global env order (hideandseek_envgen.py:1241-1246).
+        self.env_offset = int(self.cfg.env.env_offset or 0)
+        self.global_num_envs = int(self.cfg.env.global_num_envs or (self.env_offset + self.num_envs))
 
     def _stat_keys(self):
         extra = list(self.EXTRA_STATS)
@@ -280,8 +284,11 @@ class HideAndSeek_envgen(HideAndSeek):
             return base
         A, dev = self.num_agents, self.device
         if self.update_iter == 0:
-            num_buffer = min(self.gen_buffer._history_buffer.shape[0], int(n * (1 - self.ratio_unif)))
-            self.num_unif = n - num_buffer
+            # global split first, then this shard's part of it (single shard: identical to the reference)
+            Eg = max(self.global_num_envs, self.env_offset + n)
+            num_buffer_g = min(self.gen_buffer._history_buffer.shape[0], int(Eg * (1 - self.ratio_unif)))
+            self.num_unif = int(min(max(Eg - num_buffer_g - self.env_offset, 0), n))
+            num_buffer = n - self.num_unif
             unif = torch.cat([base["drone_pos"][:self.num_unif].reshape(self.num_unif, -1),
                               base["target_pos"][:self.num_unif].reshape(self.num_unif, -1),
                               base["cyl_pos"][:self.num_unif].reshape(self.num_unif, -1)], dim=-1)
@@ -321,13 +328,28 @@ class HideAndSeek_envgen(HideAndSeek):
         self._host_progress += 1
         success = self.engine.stats[0]
         st = self.stats
-        if self.num_unif < self.num_envs:
+        done_tick = self._host_progress >= self.max_episode_length  # == torch.any(done), without a host sync
+        sharded = self.global_num_envs > self.num_envs
+        if sharded and done_tick:
+            # the values the scripts harvest (EpisodeStats reads the post-done step) are means over the GLOBAL prefix /
+            # suffix: one all_reduce of four numbers per episode; between episode ends the per-rank means stand in
+            from ..parallel import global_sum
+            nu = self.num_unif
+            acc = global_sum(torch.stack([success[:nu].sum(), success.new_tensor(float(nu)),
+                                          success[nu:].sum(), success.new_tensor(float(self.num_envs - nu))]))
+            st["success_unif"].fill_(0).add_(acc[0] / acc[1].clamp(min=1))
+            st["success_buffer"].fill_(0).add_(acc[2] / acc[3].clamp(min=1))
+        elif self.num_unif < self.num_envs:
             st["success_buffer"].fill_(0).add_(success[self.num_unif:].mean())
-            st["success_unif"].fill_(0).add_(success[:self.num_unif].mean())
-        else:
+            if self.num_unif > 0:
+                st["success_unif"].fill_(0).add_(success[:self.num_unif].mean())
+        elif not sharded:
             st["success_buffer"].zero_()
             st["success_unif"].copy_(success.unsqueeze(-1))
-        if self._host_progress >= self.max_episode_length:          # == torch.any(done), without a host sync
+        else:
+            st["success_buffer"].zero_()
+            st["success_unif"].fill_(0).add_(success.mean())
+        if done_tick:
             self._on_episode_end(success)
         st["history_buffer"].fill_(float(len(self.gen_buffer._history_buffer)))
         st["ratio_unif"].fill_(self.ratio_unif)

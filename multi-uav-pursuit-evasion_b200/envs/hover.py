@@ -3,10 +3,12 @@
 Reference: omni_drones/envs/single/hover.py:40-523.  The vehicle side of the tick (PIDrate
 transform, rate PID, rotor model, rigid-body step) is the SAME fused kernel as HideAndSeek,
 instantiated with one pursuer and no cylinders; the evader slot idles far away.  The
-Hover-specific observation (20 wide) and reward are a handful of elementwise torch ops on the
-kernel's `drone_state` output -- this task is plumbing (64..100 envs), not the measured path.
+Hover-specific observation (20 wide), reward and the 39 logging stats are ONE small post-kernel
+(hs_hover_post, csrc/hs_hover.cuh) on what the tick left in the engine's buffers.
 Not built: payload / mass randomisation, observation latency and noise options (all off in
 cfg/task/Hover.yaml)."""
+import ctypes as C
+
 import torch
 
 from .. import _lib
@@ -18,15 +20,21 @@ from .hideandseek import DroneView
 from .isaac_env import IsaacEnv
 
 
-def _quat_rotate(q, v):
-    w, u = q[..., 0:1], q[..., 1:4]
-    return v * (2.0 * w ** 2 - 1.0) + torch.linalg.cross(u, v, dim=-1) * w * 2.0 + u * (u * v).sum(-1, keepdim=True) * 2.0
-
-
 class Hover(IsaacEnv):
+    # declaration order of the reference's stats spec (hover.py:239-279) = slot order of hs_hover_post
+    STAT_KEYS = ("return", "pos_bonus", "head_bonus", "reward_pos", "reward_up", "reward_vel", "reward_acc", "reward_jerk",
+                 "episode_len", "pos_error", "heading_alignment", "uprightness", "action_smoothness",
+                 "linear_v_max", "angular_v_max", "linear_a_max", "angular_a_max", "linear_jerk_max", "angular_jerk_max",
+                 "linear_v_mean", "angular_v_mean", "linear_a_mean", "angular_a_mean", "linear_jerk_mean", "angular_jerk_mean",
+                 "motor1", "motor2", "motor3", "motor4", "cmd_r", "cmd_p", "cmd_y", "cmd_thrust",
+                 "target_r_rate", "target_p_rate", "target_y_rate", "real_r_rate", "real_p_rate", "real_y_rate")
+    # MultirotorBase.intrinsics_spec (multirotor.py:78-88): all zeros unless a randomisation is configured (:652-697)
+    INTRINSICS = (("mass", 1), ("inertia", 3), ("KF", 4), ("KM", 4), ("tau_up", 4), ("tau_down", 4), ("drag_coef", 1),
+                  ("rotor_offset", 1))
+
     def _design_scene(self):
         t = self.cfg.task
-        for flag in ("omega", "motor", "add_noise", "latency", "action_noise"):
+        for flag in ("add_noise", "latency", "action_noise"):
             if t[flag]:
                 raise NotImplementedError(f"Hover option {flag}=true is not built (off in cfg/task/Hover.yaml)")
         self.reward_distance_scale = t.reward_distance_scale
@@ -34,6 +42,7 @@ class Hover(IsaacEnv):
         self.linear_vel_max, self.linear_acc_max = t.linear_vel_max, t.linear_acc_max
         self.time_encoding = bool(t.time_encoding)
         self.time_encoding_dim = 4 if self.time_encoding else 0
+        self.use_omega, self.use_motor = bool(t.omega), bool(t.motor)
         params = load_drone_params()
         # Hover keeps PhysX's default velocity limits (no v_drone clamp): robots/config.py:36-38
         self._hs_cfg = build_hs_config(self.num_envs, num_agents=1, num_cylinders=0, obs_max_cylinder=0,
@@ -44,22 +53,35 @@ class Hover(IsaacEnv):
         self.action_is_raw = False
         E, dev = self.num_envs, self.device
         self.target_pos = torch.tensor([[0.0, 0.0, 1.0]], device=dev)
-        self.target_heading = torch.zeros(E, 1, 3, device=dev)
-        self.target_heading[..., 0] = 1.0
+        self.target_heading = torch.zeros(E, 1, 3, device=dev)         # quat_axis(target_rot, 0) at reset (hover.py:317-319)
         self.alpha = 0.8
         self._far = torch.tensor([50.0, 50.0, 0.5], device=dev).expand(E, 3).contiguous()   # idle evader slot
-        self.last_linear_v = torch.zeros(E, 1, device=dev)
-        self.last_linear_a = torch.zeros(E, 1, device=dev)
-
-    STAT_KEYS = ("return", "pos_bonus", "head_bonus", "reward_pos", "reward_vel", "reward_acc", "reward_jerk",
-                 "pos_error", "heading_alignment", "uprightness", "action_smoothness", "episode_len",
-                 "linear_v_max", "linear_a_max", "linear_jerk_max")
+        self.obs_dim = 16 + (3 if self.use_omega else 0) + (4 if self.use_motor else 0) + self.time_encoding_dim
+        # post-kernel buffers: stats [39, E], last values + episode sums [12, E], throttle difference of the tick [E, 1]
+        self._stats = torch.zeros(_lib.HS_HOVER_NUM_STATS, E, device=dev)
+        self._state = torch.zeros(_lib.HS_HOVER_NUM_STATE, E, device=dev)
+        self._throttle_diff = torch.zeros(E, 1, device=dev)
+        for b in self.engine._bufs:
+            b.throttle_diff = self._throttle_diff.data_ptr()
+        self.engine._bind(self.engine.cur)
+        self._obs_buf = [torch.zeros(E, 1, self.obs_dim, device=dev) for _ in range(2)]
+        self._reward_buf = [torch.zeros(E, 1, 1, device=dev) for _ in range(2)]
+        self._done_buf = [torch.zeros(E, 1, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._flip = 0
+        hp = _lib.hs_hover_params()
+        hp.reward_distance_scale, hp.reward_v_scale = self.reward_distance_scale, self.reward_v_scale
+        hp.reward_acc_scale, hp.reward_jerk_scale = self.reward_acc_scale, self.reward_jerk_scale
+        hp.linear_vel_max, hp.linear_acc_max, hp.alpha = self.linear_vel_max, self.linear_acc_max, self.alpha
+        hp.target_pos[:] = [0.0, 0.0, 1.0]
+        hp.time_encoding, hp.omega, hp.motor = int(self.time_encoding), int(self.use_omega), int(self.use_motor)
+        self._hp = hp
 
     def _set_specs(self):
         E, dev = self.num_envs, self.device
         U = UnboundedContinuousTensorSpec
-        obs_dim = 3 + 7 + 6 + self.time_encoding_dim
-        self.observation_spec = CompositeSpec({"agents": CompositeSpec({"observation": U((1, obs_dim), device=dev)})}).expand(E).to(dev)
+        intr_spec = CompositeSpec({k: U((1, w), device=dev) for k, w in self.INTRINSICS})
+        self.observation_spec = CompositeSpec({"agents": CompositeSpec({
+            "observation": U((1, self.obs_dim), device=dev), "intrinsics": intr_spec})}).expand(E).to(dev)
         self.action_spec = CompositeSpec({"agents": CompositeSpec({"action": self.drone.action_spec.unsqueeze(0)})}).expand(E).to(dev)
         self.reward_spec = CompositeSpec({"agents": CompositeSpec({"reward": U((1, 1))})}).expand(E).to(dev)
         self.agent_spec["drone"] = AgentSpec("drone", 1, observation_key=("agents", "observation"),
@@ -69,34 +91,29 @@ class Hover(IsaacEnv):
                                    "prev_action": self.drone.action_spec.unsqueeze(0)}).expand(E).to(dev)
         self.observation_spec["stats"] = stats_spec
         self.observation_spec["info"] = info_spec
-        self.stats = stats_spec.zero()
+        # live views of the post-kernel's stats rows (the reference hands out live references too)
+        self.stats = TensorDict({k: self._stats[i].unsqueeze(-1) for i, k in enumerate(self.STAT_KEYS)}, [E], dev)
+        self.intrinsics = TensorDict({k: torch.zeros(E, 1, w, device=dev) for k, w in self.INTRINSICS}, [E], dev)
         self.info = TensorDict({"drone_state": self.engine.out["drone_state"], "prev_action": self.engine.prev_action}, [E], dev)
 
     @property
     def progress_buf(self):
         return self.engine.get_state(_lib.FIELD_PROGRESS)
 
-    def _obs(self, out):
-        ds = out["drone_state"]                                   # [E,1,13]
-        pos, quat, linvel = ds[..., :3], ds[..., 3:7], ds[..., 7:10]
-        ex = torch.zeros_like(pos); ex[..., 0] = 1.0
-        ez = torch.zeros_like(pos); ez[..., 2] = 1.0
-        self.heading, self.up = _quat_rotate(quat, ex), _quat_rotate(quat, ez)
-        self.rpos = self.target_pos - pos
-        self.rheading = self.target_heading - self.heading
-        parts = [self.rpos, quat, linvel, self.heading, self.up]
-        prog = self.progress_buf
-        if self.time_encoding:
-            parts.append((prog / self.max_episode_length).reshape(-1, 1, 1).expand(-1, 1, 4))
-        self.linear_v = torch.linalg.vector_norm(linvel, dim=-1)
-        self.linear_a = torch.abs(self.linear_v - self.last_linear_v) / self.dt
-        self.linear_jerk = torch.abs(self.linear_a - self.last_linear_a) / self.dt
-        for k, v in (("linear_v_max", self.linear_v), ("linear_a_max", self.linear_a), ("linear_jerk_max", self.linear_jerk)):
-            self.stats[k].copy_(torch.max(self.stats[k], v))
-        self.last_linear_v, self.last_linear_a = self.linear_v.clone(), self.linear_a.clone()
-        self.info.set("drone_state", ds)
-        self._progress = prog
-        return TensorDict({"agents": {"observation": torch.cat(parts, dim=-1)}, "stats": self.stats, "info": self.info},
+    def _post(self, out, with_reward: bool):
+        """hs_hover_post on the engine's latest outputs; returns (observation, reward, done) of this tick."""
+        self._flip ^= 1
+        obs, rew, done = self._obs_buf[self._flip], self._reward_buf[self._flip], self._done_buf[self._flip]
+        io = _lib.hs_hover_io()
+        io.observation, io.reward, io.done = obs.data_ptr(), rew.data_ptr(), done.data_ptr()
+        io.stats, io.state, io.target_heading = self._stats.data_ptr(), self._state.data_ptr(), self.target_heading.data_ptr()
+        self._hp.with_reward = 1 if with_reward else 0
+        _lib.check(_lib.lib.hs_hover_post(self.engine._h, C.byref(self._hp), C.byref(io), self.engine._stream()), "hs_hover_post")
+        self.info.set("drone_state", out["drone_state"])
+        return obs, rew, done.view(torch.bool)
+
+    def _obs_td(self, obs):
+        return TensorDict({"agents": {"observation": obs, "intrinsics": self.intrinsics}, "stats": self.stats, "info": self.info},
                           self.batch_size, self.device)
 
     def _reset(self, tensordict=None, init=None, **kwargs):
@@ -115,13 +132,17 @@ class Hover(IsaacEnv):
                                cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy], dim=-1)
             init = dict(drone_pos=pos, drone_rot=rot)
         m = slice(None) if mask is None else mask
-        for v in self.stats.values():
-            v[m] = 0.0
-        self.last_linear_v[m] = 0.0
-        self.last_linear_a[m] = 0.0
+        # hover.py:296-332: stats and the last_* values of the reset envs are zeroed (init_vels = 0); the episode sums are
+        # re-created for ALL envs (`self.linear_v_episode = torch.zeros_like(...)`, a reference quirk); target heading =
+        # quat_axis(euler(0, 0, 0), 0) = x
+        self._stats[:, m] = 0.0
+        self._state[:6, m] = 0.0
+        self._state[6:] = 0.0
+        self.target_heading[m] = torch.tensor([1.0, 0.0, 0.0], device=dev)
         out = self.engine.reset(mask, init["drone_pos"], init["drone_rot"], self._far, torch.zeros(E, 0, 3, device=dev))
+        obs, _, _ = self._post(out, with_reward=False)
         td = TensorDict({}, self.batch_size, dev)
-        td.update(self._obs(out))
+        td.update(self._obs_td(obs))
         td.set("stats", last_stats)
         td.set("truncated", out["truncated"])
         return td
@@ -136,31 +157,17 @@ class Hover(IsaacEnv):
             tensordict.set("target_rate", out["target_rate"])
             tensordict.set(("info", "prev_action"), eng.prev_action)
         else:
+            # rotor commands applied directly: the keys the PIDrate transform would have written are taken from the input
+            # tensordict when present (hover.py:349-359 reads td['ctbr'] / td['target_rate'])
+            nxt_set = eng.sets[eng.next_index()]
+            nxt_set["rotor_cmds"].copy_(action)
+            for k, w in (("ctbr", 4), ("target_rate", 3)):
+                v = tensordict.get(k, None)
+                nxt_set[k].copy_(v.reshape(self.num_envs, 1, w)) if v is not None else nxt_set[k].zero_()
             out = eng.step_pre(action, raw=False, reset_pid=None)
-        nxt = self._obs(out)
-        # reward, hover.py:439-523
-        pos_error = torch.linalg.vector_norm(self.rpos, dim=-1)
-        head_error = torch.linalg.vector_norm(self.rheading, dim=-1)
-        reward_pos = -pos_error * self.reward_distance_scale
-        bonus = ((pos_error <= 0.02) * 10).float()
-        reward_head = -head_error * (bonus > 0)
-        head_bonus = ((head_error <= 0.02) * 10 * (bonus > 0)).float()
-        reward_up = torch.square((self.up[..., 2] + 1) / 2)
-        reward_v = self.reward_v_scale * (bonus > 0) * (self.linear_v < self.linear_vel_max)
-        reward_acc = self.reward_acc_scale * (bonus > 0) * (self.linear_a < self.linear_acc_max)
-        reward_jerk = self.reward_jerk_scale * (bonus > 0) * (-self.linear_jerk)
-        reward = reward_pos + bonus + reward_head + head_bonus + reward_up + reward_v + reward_acc + reward_jerk
-        done = (self._progress >= self.max_episode_length).unsqueeze(-1)
-        st = self.stats
-        st["pos_error"].lerp_(pos_error, 1 - self.alpha)
-        st["heading_alignment"].lerp_((self.heading * self.target_heading).sum(-1), 1 - self.alpha)
-        st["uprightness"].lerp_(self.up[..., 2], 1 - self.alpha)
-        st["return"].add_(reward)
-        for k, v in (("reward_pos", reward_pos), ("pos_bonus", bonus), ("head_bonus", head_bonus),
-                     ("reward_vel", reward_v), ("reward_acc", reward_acc), ("reward_jerk", reward_jerk)):
-            st[k].copy_(v.float() if torch.is_tensor(v) else torch.full_like(st[k], float(v)))
-        st["episode_len"].copy_(self._progress.unsqueeze(1))
-        nxt.set(("agents", "reward"), reward.unsqueeze(-1))
+        obs, rew, done = self._post(out, with_reward=True)
+        nxt = self._obs_td(obs)
+        nxt.set(("agents", "reward"), rew)
         nxt.set("done", done)
         return TensorDict({"next": nxt}, self.batch_size, self.device)
 

@@ -94,6 +94,14 @@ def global_mean(local: torch.Tensor, group=None) -> torch.Tensor:
     return acc[0] / acc[1]
 
 
+def global_sum(values: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise sum over all ranks of a small device vector (one all_reduce, no host sync)."""
+    out = values.clone().float()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
 def global_any(flag: torch.Tensor, group=None) -> torch.Tensor:
     f = flag.reshape(-1).any().float().reshape(1)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

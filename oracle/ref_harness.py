@@ -194,11 +194,13 @@ def load_reference():
     drone_m = extract(mr, ["apply_action", "get_state", "_reset_idx", "downwash"], cls="MultirotorBase")
     tr = extract("omni_drones/utils/torchrl/transforms.py", ["_inv_call"], cls="PIDRateController")
     ie = extract("omni_drones/envs/isaac_env.py", ["_reset", "_step", "get_env_poses"], cls="IsaacEnv")
+    hover_m = extract("omni_drones/envs/single/hover.py",
+                      ["_reset_idx", "_pre_sim_step", "_compute_state_and_obs", "_compute_reward_and_done"], cls="Hover")
     tp = ast.parse((REF / "omni_drones/learning/mappo.py").read_text())
     node = next(n for n in tp.body if isinstance(n, ast.ClassDef) and n.name == "TP_net")
     tp_ns = dict(torch=torch, nn=torch.nn)
     exec(compile(ast.Module(body=[node], type_ignores=[]), "<ref:TP_net>", "exec"), tp_ns)
-    _LOADED.update(ut=ut, rg=rg, lc=lc, env=env_m, drone=drone_m, transform=tr, isaac=ie,
+    _LOADED.update(ut=ut, rg=rg, lc=lc, env=env_m, drone=drone_m, transform=tr, isaac=ie, hover=hover_m,
                    TP_net=tp_ns["TP_net"], ns=ns)
     return _LOADED
 
@@ -447,3 +449,93 @@ class RefEnv:
                    action_error=td[("stats", "action_error_order1")].clone())
         out = e._step(td)
         return out["next"], aux
+
+
+class RefHover:
+    """The reference's Hover task (omni_drones/envs/single/hover.py:296-523) driven from its extracted source: `_reset_idx`,
+    `_pre_sim_step`, `_compute_state_and_obs`, `_compute_reward_and_done` bound to a fake self, the drone and the PIDrate
+    transform exactly as in RefEnv (one pursuer, no evader, no cylinders), hs_oracle.rigid_body_step for PhysX."""
+
+    STAT_KEYS = ("return", "pos_bonus", "head_bonus", "reward_pos", "reward_up", "reward_vel", "reward_acc", "reward_jerk",
+                 "episode_len", "pos_error", "heading_alignment", "uprightness", "action_smoothness",
+                 "linear_v_max", "angular_v_max", "linear_a_max", "angular_a_max", "linear_jerk_max", "angular_jerk_max",
+                 "linear_v_mean", "angular_v_mean", "linear_a_mean", "angular_a_mean", "linear_jerk_mean", "angular_jerk_mean",
+                 "motor1", "motor2", "motor3", "motor4", "cmd_r", "cmd_p", "cmd_y", "cmd_thrust",
+                 "target_r_rate", "target_p_rate", "target_y_rate", "real_r_rate", "real_p_rate", "real_y_rate")
+
+    def __init__(self, E: int, max_episode_length: int = 500, task=None):
+        P = O.HSParams(num_agents=1, num_cylinders=0, obs_max_cylinder=0, use_tp_net=False,
+                       max_episode_length=max_episode_length, max_linear_velocity=1000.0)
+        # reuse RefEnv for the drone / transform / PhysX stand-in, then swap the task methods
+        self.base = RefEnv(P, E, use_random_cylinder=False, scenario_flag="empty")
+        self.P, self.E = P, E
+        R, d, store = self.base.R, self.base.drone, self.base.store
+        store["tpos"][:] = torch.tensor([50.0, 50.0, 0.5])          # the unused evader slot, far away
+        d.acc, d.jerk = torch.zeros(E, 1, 6), torch.zeros(E, 1, 6)
+        d.intrinsics = TD({"mass": torch.zeros(E, 1, 1)}, [E, 1])
+        t = dict(reward_action_smoothness_weight=0.0, reward_distance_scale=10.0, reward_v_scale=0.0, reward_acc_scale=0.0,
+                 reward_jerk_scale=0.0, linear_vel_max=3.0, linear_acc_max=10.0, omega=False, motor=False, time_encoding=True,
+                 add_noise=False, action_noise=False, latency=False)
+        t.update(task or {})
+        e = _Obj()
+        e.num_envs, e.device, e.batch_size, e.drone, e.training = E, torch.device("cpu"), [E], d, True
+        e.cfg = _Obj()
+        e.cfg.task = _Obj()
+        for k, v in t.items():
+            setattr(e.cfg.task, k, v)
+        e.reward_distance_scale, e.reward_v_scale = t["reward_distance_scale"], t["reward_v_scale"]
+        e.reward_acc_scale, e.reward_jerk_scale = t["reward_acc_scale"], t["reward_jerk_scale"]
+        e.linear_vel_max, e.linear_acc_max = t["linear_vel_max"], t["linear_acc_max"]
+        e.time_encoding, e.time_encoding_dim, e.latency, e.has_payload = t["time_encoding"], 4, t["latency"], False
+        e.dt, e.max_episode_length, e.alpha = P.dt, max_episode_length, 0.8
+        e.envs_positions = torch.zeros(E, 3)
+        e.progress_buf = torch.zeros(E)
+        U = torch.distributions.Uniform
+        e.init_pos_dist = U(torch.tensor([-1., -1., 0.05]), torch.tensor([1., 1., 2.0]))
+        e.init_rpy_dist = U(torch.tensor([-0.2, -0.2, 0.0]) * torch.pi, torch.tensor([0.2, 0.2, 0.5]) * torch.pi)
+        # (degenerate Uniform(0, 0) like the reference's: modern torch validates low < high, the old pinned one did not)
+        e.target_rpy_dist = U(torch.tensor([0., 0., 0.]) * torch.pi, torch.tensor([0., 0., 0.]) * torch.pi, validate_args=False)
+        e.target_pos = torch.tensor([[0.0, 0.0, 1.0]])
+        e.target_heading = torch.zeros(E, 1, 3)
+        e.target_vis = _Obj()
+        e.target_vis.set_world_poses = lambda orientations=None, env_indices=None: None
+        e.init_vels = torch.zeros(E, 1, 6)
+        for k in ("last_linear_v", "last_angular_v", "last_linear_a", "last_angular_a", "last_linear_jerk", "last_angular_jerk"):
+            setattr(e, k, torch.zeros(E, 1))
+        e.stats = TD({k: torch.zeros(E, 1) for k in self.STAT_KEYS}, [E])
+        e.info = TD({"drone_state": torch.zeros(E, 1, 13), "prev_action": torch.zeros(E, 1, 4)}, [E])
+        for name, fn in R["hover"].items():
+            setattr(e, name, types.MethodType(fn, e))
+        self.env = e
+
+    def reset_with(self, mask, pos, rot):
+        """hover.py:296-332 with the sampled pose replaced by (pos [E,1,3], rot [E,1,4]); then the observation half that
+        IsaacEnv._reset runs (isaac_env.py:217-224; Hover's _reset_idx does not step the simulator)."""
+        e, d = self.env, self.base.drone
+        env_ids = mask.nonzero().squeeze(-1)
+        real_set = d.set_world_poses
+        d.set_world_poses = lambda positions=None, orientations=None, env_indices=None: real_set(pos[env_indices], rot[env_indices], env_indices)
+        try:
+            e._reset_idx(env_ids)
+        finally:
+            d.set_world_poses = real_set
+        e.progress_buf[env_ids] = 0.0
+        return e._compute_state_and_obs()
+
+    def step(self, raw_action, done_prev):
+        e, b = self.env, self.base
+        td = TD({"agents": {"action": raw_action.clone()},
+                 "info": {"drone_state": e.info["drone_state"].clone(), "prev_action": e.info["prev_action"].clone()},
+                 "stats": TD({}, [self.E]), "done": done_prev.reshape(self.E, 1).clone()}, [self.E])
+        td = b.transform._inv_call(td)
+        e.info["prev_action"] = td[("info", "prev_action")]
+        e._pre_sim_step(td)
+        b._sim_step()
+        e.progress_buf += 1
+        obs = e._compute_state_and_obs()
+        rd = e._compute_reward_and_done()
+        aux = dict(cmds=td[("agents", "action")].clone(), ctbr=td["ctbr"].clone(), target_rate=td["target_rate"].clone())
+        return obs, rd, aux
+
+    def stats_matrix(self):
+        return torch.cat([self.env.stats[k].reshape(self.E, 1) for k in self.STAT_KEYS], dim=-1).detach().clone().float()

@@ -55,6 +55,12 @@ def _worker(rank, world, port, q):
                           torch.arange(25, dtype=torch.float32).reshape(5, 5) + 100])
         assert torch.equal(allr, want)
         assert par.gather_rows(torch.zeros(0, 4)).shape == (0, 4)
+        # envgen: success over the GLOBAL uniform prefix / archive suffix from per-rank [sum, count] pairs
+        # (hideandseek_envgen.py:1241-1246): 8 global envs, prefix of 5 -> rank 0 holds 4 uniform envs, rank 1 one
+        s_local = torch.tensor([1., 0., 1., 1.]) if rank == 0 else torch.tensor([0., 1., 1., 1.])
+        nu = 4 if rank == 0 else 1
+        acc = par.global_sum(torch.stack([s_local[:nu].sum(), torch.tensor(float(nu)), s_local[nu:].sum(), torch.tensor(float(4 - nu))]))
+        assert abs(float(acc[0] / acc[1]) - 3 / 5) < 1e-6 and abs(float(acc[2] / acc[3]) - 3 / 3) < 1e-6
         q.put((rank, "ok"))
     except Exception as e:                        # surface the failure in the parent
         q.put((rank, repr(e)))
