@@ -93,7 +93,16 @@ typedef struct hs_config {
     int32_t write_smoothness_coef_stat; /* 1 for HideAndSeek, 0 for the envgen variant */
     int32_t fixed_yaw;
     int32_t ground_clamp;
-    int32_t reserved_i[3];
+    int32_t use_obstacles;      /* 1: every TP frame also carries [x, y, size] of the C cylinders (hideandseek.py:808-817);
+                                   frame width 7 + 3A + 3C.  Runs on the one-lane-per-env tick (num_agents >= 3) with the
+                                   predictor as a module between hs_step_pre and hs_step_post */
+    int32_t contact_mode;       /* 0 (default): ground clamp only.  1: + analytic inelastic contacts of every pursuer with the
+                                   standing cylinders (2-D, radius cylinder_size + drone_radius, below the cylinder top) and
+                                   with the evader's sphere (at its position when the tick starts): projection out of the
+                                   overlap, inward normal velocity removed.  PhysX resolves these contacts in the reference
+                                   (robot.py:125-135 colliders); like the integrator itself this response is a documented
+                                   stand-in, PARITY UNPINNED.  Pursuer-pursuer contacts are not modelled. */
+    int32_t reserved_i[1];
     float dt;
     float arena_size, max_height, cylinder_size, catch_radius, collision_radius;
     float drone_detect_radius, target_detect_radius, v_drone, mask_value;
@@ -118,6 +127,8 @@ typedef struct hs_config {
     float coll_radius_x2;       /* 2*collision_radius      hideandseek.py:975 */
     float vmax_clamped;         /* max_linear_velocity*(1-1e-6): see DESIGN.md "Integrator" */
     float inv_inertia[3];       /* 1/inertia */
+    float drone_radius;         /* 0.06: base_link collider (USD cylinder r = 0.06, h = 0.025) */
+    float evader_radius;        /* 0.05: the evader's sphere (hideandseek.py:544-551) */
     float reserved_f[1];
 } hs_config;
 

@@ -35,7 +35,7 @@ class hs_config(C.Structure):
         ("num_cylinders", C.c_int32), ("obs_max_cylinder", C.c_int32), ("future_step", C.c_int32),
         ("history_step", C.c_int32), ("max_episode_length", C.c_int32), ("use_tp_net", C.c_int32),
         ("smoothness_gated", C.c_int32), ("write_smoothness_coef_stat", C.c_int32),
-        ("fixed_yaw", C.c_int32), ("ground_clamp", C.c_int32), ("reserved_i", C.c_int32 * 3),
+        ("fixed_yaw", C.c_int32), ("ground_clamp", C.c_int32), ("use_obstacles", C.c_int32), ("contact_mode", C.c_int32), ("reserved_i", C.c_int32 * 1),
         ("dt", C.c_float),
         ("arena_size", C.c_float), ("max_height", C.c_float), ("cylinder_size", C.c_float),
         ("catch_radius", C.c_float), ("collision_radius", C.c_float),
@@ -56,7 +56,8 @@ class hs_config(C.Structure):
         ("max_linear_velocity", C.c_float), ("max_angular_velocity", C.c_float),
         ("ground_z", C.c_float), ("hover_throttle", C.c_float),
         ("arena_size_sq", C.c_float), ("half_arena", C.c_float), ("coll_radius_x2", C.c_float),
-        ("vmax_clamped", C.c_float), ("inv_inertia", C.c_float * 3), ("reserved_f", C.c_float * 1),
+        ("vmax_clamped", C.c_float), ("inv_inertia", C.c_float * 3), ("drone_radius", C.c_float), ("evader_radius", C.c_float),
+        ("reserved_f", C.c_float * 1),
     ]
 
 

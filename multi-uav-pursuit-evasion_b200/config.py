@@ -99,7 +99,7 @@ def build_hs_config(num_envs: int, *, num_agents=3, num_cylinders=5, obs_max_cyl
                     v_drone=1.0, mask_value=-5.0, dist_reward_coef=1.0, catch_reward_coef=20.0,
                     detect_reward_coef=0.0, collision_coef=100.0, speed_coef=10.0,
                     smoothness_coef=0.0, smoothness_gated=True, write_smoothness_coef_stat=True,
-                    ground_clamp=True, max_linear_velocity=None, drone_params: Optional[dict] = None
+                    ground_clamp=True, max_linear_velocity=None, use_obstacles=False, contact_mode=0, drone_params: Optional[dict] = None
                     ) -> "_lib.hs_config":
     """All arithmetic on parameters happens here in double precision and is rounded to
     fp32 once, the way the reference's Python scalars meet its fp32 tensors."""
@@ -114,6 +114,9 @@ def build_hs_config(num_envs: int, *, num_agents=3, num_cylinders=5, obs_max_cyl
     c.write_smoothness_coef_stat = int(bool(write_smoothness_coef_stat))
     c.fixed_yaw = int(bool(dp.get("fixed_yaw", 0)))
     c.ground_clamp = int(bool(ground_clamp))
+    c.use_obstacles = int(bool(use_obstacles))
+    c.contact_mode = int(contact_mode)
+    c.drone_radius, c.evader_radius = rb.get("collider_radius", 0.06), 0.05
     c.dt = dt
     c.arena_size, c.max_height, c.cylinder_size = arena_size, max_height, cylinder_size
     c.catch_radius, c.collision_radius = catch_radius, collision_radius

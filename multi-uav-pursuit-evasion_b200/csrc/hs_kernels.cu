@@ -142,7 +142,7 @@ static bool wide_possible(const hs_handle* h) {
     return true;
 }
 static bool use_wide(const hs_handle* h) {
-    if (h->cfg.num_agents > NARROW_MAX_AGENTS) return true;
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS || (h->cfg.use_obstacles && h->cfg.use_tp_net)) return true;
     if (h->tick_mapping == 1) return false;
     if (h->tick_mapping == 2) return wide_possible(h);
     return h->cfg.num_envs >= 32768 && wide_possible(h);
@@ -271,6 +271,7 @@ int hs_default_config(hs_config* c, int32_t num_envs) {
     c->half_arena = (float)(0.5 * 0.9);
     c->coll_radius_x2 = (float)(2.0 * 0.07);
     c->vmax_clamped = (float)(1.0 * (1.0 - 1e-6));
+    c->drone_radius = 0.06f; c->evader_radius = 0.05f;
     return HS_OK;
 }
 
@@ -288,7 +289,9 @@ static int check_cfg(const hs_config* c) {
     if (c->history_step < 1) return set_err(HS_ERR_INVALID, "history_step must be >= 1%s");
     if (((int64_t)ND * c->num_agents + E_CYL + 3 * (int64_t)c->num_cylinders) * (((int64_t)c->num_envs + 31) & ~(int64_t)31) >= ((int64_t)1 << 31))
         return set_err(HS_ERR_INVALID, "num_envs too large: the state arena must stay below 2^31 words%s");
-    if (c->use_tp_net && c->num_agents <= NARROW_MAX_AGENTS && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
+    if (c->use_obstacles && c->use_tp_net && (c->num_agents < 3 || (c->num_envs & 3) != 0))
+        return set_err(HS_ERR_INVALID, "use_obstacles runs on the one-lane-per-env tick: needs num_agents >= 3 and num_envs % 4 == 0%s");
+    if (c->use_tp_net && !c->use_obstacles && c->num_agents <= NARROW_MAX_AGENTS && c->history_step * (7 + 3 * c->num_agents) > TP_ENV_WORDS_MAX)
         return set_err(HS_ERR_INVALID, "history_step * (7 + 3*num_agents) must be <= 192%s");
     return HS_OK;
 }
@@ -473,8 +476,8 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     if (!h || !action || !w) return set_err(HS_ERR_INVALID, "hs_step_fused: null argument%s");
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_fused: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_fused: config has use_tp_net == 0 (use hs_step_pre)%s");
-    if (h->cfg.num_agents > NARROW_MAX_AGENTS)
-        return set_err(HS_ERR_INVALID, "hs_step_fused: the fused predictor kernels cover num_agents <= 3; use hs_step_pre + the module + hs_step_post%s");
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS || h->cfg.use_obstacles)
+        return set_err(HS_ERR_INVALID, "hs_step_fused: the fused predictor kernels cover num_agents <= 3 without use_obstacles; use hs_step_pre + the module + hs_step_post%s");
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
     const bool one_launch = h->fused_tick && !h->exact_math && h->tick_mapping != 2 && (h->tp_variant < 0 || h->tp_variant == 5) &&
                             tiles32 <= h->num_sms && tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
@@ -551,8 +554,8 @@ int hs_step_post_tp(hs_handle* h, const hs_tp_weights* w, float* tp_pred_out, vo
     if (!h || !w) return set_err(HS_ERR_INVALID, "hs_step_post_tp: null argument%s");
     if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_step_post_tp: call hs_bind_buffers first%s");
     if (!h->cfg.use_tp_net) return set_err(HS_ERR_INVALID, "hs_step_post_tp: config has use_tp_net == 0%s");
-    if (h->cfg.num_agents > NARROW_MAX_AGENTS)
-        return set_err(HS_ERR_INVALID, "hs_step_post_tp: the fused predictor kernels cover num_agents <= 3; use the module + hs_step_post%s");
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS || h->cfg.use_obstacles)
+        return set_err(HS_ERR_INVALID, "hs_step_post_tp: the fused predictor kernels cover num_agents <= 3 without use_obstacles; use the module + hs_step_post%s");
     if (!w->weight_ih || !w->weight_hh || !w->bias_ih || !w->bias_hh || !w->fc_weight || !w->fc_bias)
         return set_err(HS_ERR_INVALID, "hs_step_post_tp: a weight pointer is NULL%s");
     if (w->hidden_size != TP_HID || w->input_size != 7 + 3 * h->cfg.num_agents || w->output_size != 3 * h->cfg.future_step)
@@ -1139,7 +1142,7 @@ int hs_set_option(hs_handle* h, int option, int value) {
             return HS_OK;
         case HS_OPT_TICK_MAPPING:
             if (value < 0 || value > 2) return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING must be 0 (auto), 1 (4 lanes per env) or 2 (one lane per env)%s");
-            if (value == 1 && h->cfg.num_agents > NARROW_MAX_AGENTS)
+            if (value == 1 && (h->cfg.num_agents > NARROW_MAX_AGENTS || (h->cfg.use_obstacles && h->cfg.use_tp_net)))
                 return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING = 1: the 4-lane mapping covers num_agents <= 3%s");
             if (value == 2 && (h->cfg.num_agents < 3 || (h->cfg.num_envs & 3) != 0))
                 return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING = 2: the one-lane mapping needs num_agents >= 3 and num_envs % 4 == 0%s");

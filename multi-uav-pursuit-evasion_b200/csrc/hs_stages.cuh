@@ -240,6 +240,41 @@ __device__ __forceinline__ void stage_integrate(const hs_config& c, V3& p, Q4& q
     lv = v; av = w;
 }
 
+// ---- analytic contacts (hs_config.contact_mode = 1; PhysX stand-in, PARITY UNPINNED) -------------------------
+// After the integration: project the pursuer out of every standing cylinder it penetrates (2-D, below the cylinder top)
+// and out of the evader's sphere (evader position at the start of the tick), and remove the velocity component that
+// points into the obstacle (inelastic).  oracle/hs_oracle.py::apply_contacts is the same arithmetic.
+template <int CT>
+__device__ __forceinline__ void stage_contacts(const hs_config& c, V3& p, V3& v, const V3 tp, const float (&cx)[CT],
+                                               const float (&cy)[CT], const float (&cz)[CT], const int C) {
+    if (!c.contact_mode) return;
+    const float Rc = c.cylinder_size + c.drone_radius;
+#pragma unroll
+    for (int k = 0; k < CT; ++k) {
+        if (k < C && cz[k] > 0.0f && p.z < 2.0f * cz[k]) {
+            const float dx = p.x - cx[k], dy = p.y - cy[k];
+            const float d = fsqrt(dx * dx + dy * dy);
+            if (d < Rc) {
+                const float inv = frcp(fmaxf(d, 1e-6f));
+                const float nx = dx * inv, ny = dy * inv;
+                p.x = cx[k] + nx * Rc;
+                p.y = cy[k] + ny * Rc;
+                const float vn = v.x * nx + v.y * ny;
+                if (vn < 0.0f) { v.x = v.x - vn * nx; v.y = v.y - vn * ny; }
+            }
+        }
+    }
+    const float Re = c.evader_radius + c.drone_radius;
+    const V3 rel = p - tp;
+    const float d = norm3(rel);
+    if (d < Re) {
+        const V3 n = rel * frcp(fmaxf(d, 1e-6f));
+        p = tp + n * Re;
+        const float vn = dot3(v, n);
+        if (vn < 0.0f) v = v - n * vn;
+    }
+}
+
 // ---- k nearest cylinders [K,5] of the pursuer at p; lowest index wins ties (hideandseek.py:757-778) ----
 // also counts the cylinder collisions among them (hideandseek.py:961-968)
 template <int CT>

@@ -201,7 +201,10 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     }
 
     // ---- rigid-body integration (PhysX stand-in; oracle/hs_oracle.py rigid_body_step) ----
-    if (is_drone) stage_integrate<!RESET>(c, p, q, lv, av, T, yaw_torque, ext);
+    if (is_drone) {
+        stage_integrate<!RESET>(c, p, q, lv, av, T, yaw_torque, ext);
+        stage_contacts(c, p, lv, tp, cx, cy, cz, C);
+    }
     if (is_ev) tp = tp + tv * dt;
     // everyone needs the evader's new position/velocity
     tp = gshfl3(tp, gbase + A);

@@ -176,8 +176,9 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
     const int E = c.num_envs;
     const int64_t e0 = (int64_t)blockIdx.x * 32;
     const int C = c.num_cylinders, K = c.obs_max_cylinder, H = c.history_step;
-    constexpr int FD = 7 + 3 * A;
+    constexpr int FD0 = 7 + 3 * A;                               // frame without cylinders
     const bool tp_on = c.use_tp_net != 0;
+    const int FD = FD0 + (c.use_obstacles ? 3 * C : 0);          // hideandseek.py:808-817
     const WidePlan w = wide_plan(A, C, K, tp_on);
     float* const mem = wide_mem;
     const int nenv = (int)min((int64_t)32, E - e0);
@@ -217,7 +218,7 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
         const float* src = P.b.tp_input_prev + e0 * per_env;
         float* dst = P.b.tp_input + e0 * per_env;
         constexpr int NT = (A + 1) * 32;
-        if ((FD & 3) == 0 && H == 10) wd_window_shift_fixed<9 * (FD / 4), 10 * (FD / 4), FD / 4, NT>(dst, src, nenv, threadIdx.x);
+        if ((FD0 & 3) == 0 && H == 10 && FD == FD0) wd_window_shift_fixed<9 * (FD0 / 4), 10 * (FD0 / 4), FD0 / 4, NT>(dst, src, nenv, threadIdx.x);
         else if ((FD & 3) == 0) wd_window_shift<4, NT>(dst, src, nenv, per_env, keep, FD, threadIdx.x);
         else wd_window_shift<1, NT>(dst, src, nenv, per_env, keep, FD, threadIdx.x);
     }
@@ -310,6 +311,7 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
             ext = dw + lv * c.drag_coef_times_mass;
         }
         stage_integrate<!RESET>(c, p, q, lv, av, T, yaw_torque, ext);
+        stage_contacts(c, p, lv, tp, cx, cy, cz, C);
         if (valid) {
             SD(D_POS, a) = p.x; SD(D_POS + 1, a) = p.y; SD(D_POS + 2, a) = p.z;
             SD(D_ROT, a) = q.w; SD(D_ROT + 1, a) = q.x; SD(D_ROT + 2, a) = q.y; SD(D_ROT + 3, a) = q.z;
@@ -414,24 +416,26 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
         if (tp_on) {
             // new TP frame [progress, tpos_masked3, tvel_masked3, p_0..p_{A-1}], written straight to its slot (row H-1;
             // every row on the very first frame)
-            float fr[FD];
+            float fr[FD0 + 3 * CT];
             fr[0] = progress;
             fr[1] = bdetect ? tp.x : mv; fr[2] = bdetect ? tp.y : mv; fr[3] = bdetect ? tp.z : mv;
             fr[4] = bdetect ? tv.x : mv; fr[5] = bdetect ? tv.y : mv; fr[6] = bdetect ? tv.z : mv;
 #pragma unroll
             for (int j = 0; j < A; ++j) { fr[7 + 3 * j] = SD(D_POS, j); fr[8 + 3 * j] = SD(D_POS + 1, j); fr[9 + 3 * j] = SD(D_POS + 2, j); }
+#pragma unroll
+            for (int k = 0; k < CT; ++k) { fr[FD0 + 3 * k] = cx[k]; fr[FD0 + 3 * k + 1] = cy[k]; fr[FD0 + 3 * k + 2] = c.cylinder_size; }
             if (valid) {
                 float* win = P.b.tp_input + e * per_env;
                 const int h0 = P.tp_init ? 0 : H - 1;
                 for (int h = h0; h < H; ++h) {
                     float* row = win + h * FD;
-                    if ((FD & 3) == 0) {
+                    if ((FD0 & 3) == 0 && FD == FD0) {
 #pragma unroll
-                        for (int k = 0; k < FD / 4; ++k)
+                        for (int k = 0; k < FD0 / 4; ++k)
                             reinterpret_cast<float4*>(row)[k] = make_float4(fr[4 * k], fr[4 * k + 1], fr[4 * k + 2], fr[4 * k + 3]);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < FD; ++k) row[k] = fr[k];
+                        for (int k = 0; k < FD0 + 3 * CT; ++k) if (k < FD) row[k] = fr[k];
                     }
                 }
                 P.b.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;

@@ -27,7 +27,7 @@ class OutputSet:
         E, A = cfg.num_envs, cfg.num_agents
         K, F, H = cfg.obs_max_cylinder, cfg.future_step, cfg.history_step
         D = 20 + (3 * F if cfg.use_tp_net else 0)
-        FD = 7 + 3 * A
+        FD = 7 + 3 * A + (3 * cfg.num_cylinders if cfg.use_obstacles else 0)
         # the tensors a policy consumes come first, so that they form one contiguous prefix of
         # the slab (a single D2H copy moves observation + reward when the policy lives on the host)
         shapes = {
@@ -382,7 +382,7 @@ class HsEngine:
         w = _lib.hs_tp_weights()
         w.weight_ih, w.weight_hh, w.bias_ih, w.bias_hh, w.fc_weight, w.fc_bias = [p.data_ptr() for p in ps]
         w.input_size, w.hidden_size, w.output_size = lstm.input_size, lstm.hidden_size, fc.out_features
-        if w.input_size != 7 + 3 * self.A or w.output_size != 3 * self.cfg.future_step:
+        if w.input_size != 7 + 3 * self.A or w.output_size != 3 * self.cfg.future_step or self.cfg.use_obstacles:
             return None
         return w
 

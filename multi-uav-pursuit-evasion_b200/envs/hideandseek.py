@@ -91,8 +91,7 @@ class HideAndSeek(IsaacEnv):
         self.obs_max_cylinder = int(t.cylinder.obs_max_cylinder)
         self.future_predcition_step, self.history_step = int(t.future_predcition_step), int(t.history_step)
         self.window_step = int(t.window_step or 1)
-        if t.use_obstacles:
-            raise NotImplementedError("use_obstacles=1 (cylinders in the TP frame) is not built; the task YAMLs use 0")
+        self.use_obstacles = bool(t.use_obstacles)          # TP frame also carries [x, y, size] per cylinder (hideandseek.py:808-817)
         self.time_encoding_dim = 4
         self.collision_radius = t.collision_radius
         self.mask_value = -5
@@ -120,6 +119,8 @@ class HideAndSeek(IsaacEnv):
             smoothness_gated=(not self.VARIANT_ENVGEN) and (not self.use_deployment),
             write_smoothness_coef_stat=not self.VARIANT_ENVGEN,
             ground_clamp=True if self.cfg.sim is None or self.cfg.sim.ground_clamp is None else bool(self.cfg.sim.ground_clamp),
+            use_obstacles=self.use_obstacles and self.use_TP_net,
+            contact_mode=int((self.cfg.sim.contact_mode if self.cfg.sim is not None else 0) or 0),
             max_linear_velocity=t.v_drone, drone_params=params)
         self.engine = HsEngine(self._hs_cfg, self.device, num_output_sets=int(self.cfg.env.output_sets or 2),
                                rollout_steps=int(self.cfg.env.get("rollout_steps", 0) or 0) or None)
@@ -138,7 +139,7 @@ class HideAndSeek(IsaacEnv):
         self._seed = int(self.cfg.seed or 0)
         self._reset_dist = None
 
-        frame = 7 + 3 * self.num_agents
+        frame = 7 + 3 * self.num_agents + (3 * self.num_cylinders if self.use_obstacles else 0)
         self.TP = TP_net(input_dim=frame, output_dim=3 * self.future_predcition_step,
                          future_predcition_step=self.future_predcition_step, window_step=self.window_step).to(self.device)
 
@@ -149,7 +150,8 @@ class HideAndSeek(IsaacEnv):
         D = 3 + (3 * F if self.use_TP_net else 0) + self.time_encoding_dim + 13
         observation_spec = CompositeSpec({"state_self": U((1, D)), "state_others": U((n - 1, 3)), "cylinders": U((K, 5))}).to(dev)
         state_spec = CompositeSpec({"state_drones": U((n, D)), "cylinders": U((K, 5))}).to(dev)
-        TP_spec = CompositeSpec({"TP_input": U((self.history_step, 7 + 3 * n)), "TP_groundtruth": U((1, 3)),
+        frame = 7 + 3 * n + (3 * self.num_cylinders if self.use_obstacles else 0)
+        TP_spec = CompositeSpec({"TP_input": U((self.history_step, frame)), "TP_groundtruth": U((1, 3)),
                                  "TP_done": U((1, 3))}).to(dev)
         E = self.num_envs
         self.observation_spec = CompositeSpec({"agents": CompositeSpec({

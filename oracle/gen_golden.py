@@ -43,6 +43,7 @@ CASES = {
     "deploy_epoch_tp": (dict(use_deployment=True, smoothness_coef=0.5, smooth_lr=0.4, max_smoothness_coef=5.0), 12,
                         "random_cylinders", 4, 4, None),
 }
+CASES["obstacles_tp"] = (dict(use_obstacles=True), 12, "random_cylinders", 4, 4, None)     # cylinders inside the TP frame
 UPDATE_EPOCHS = {"deploy_epoch_tp": [0, 3, 3, 20]}        # -> 0.5, 1.7, 1.7, min(5, 8.5)
 
 

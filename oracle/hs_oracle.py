@@ -74,6 +74,7 @@ class HSParams:
     future_step: int = 5              # future_predcition_step
     history_step: int = 10
     use_tp_net: bool = True
+    use_obstacles: bool = False       # TP frame also carries [x, y, size] per cylinder (hideandseek.py:808-817)
     max_episode_length: int = 800
     dt: float = 0.01
     # arena / task
@@ -127,6 +128,9 @@ class HSParams:
     max_angular_velocity: float = 1000.0
     ground_clamp: bool = True
     ground_z: float = 0.0125          # collider half height, USD cylinder h=0.025
+    contact_mode: int = 0             # 1: analytic cylinder / evader contacts after the integration (unpinned stand-in)
+    drone_radius: float = 0.06        # base_link collider radius (USD)
+    evader_radius: float = 0.05       # hideandseek.py:544-551
 
     # derived -----------------------------------------------------------------
     @property
@@ -154,7 +158,7 @@ class HSParams:
 
     @property
     def tp_frame_dim(self) -> int:
-        return 7 + 3 * self.num_agents
+        return 7 + 3 * self.num_agents + (3 * self.num_cylinders if self.use_obstacles else 0)
 
     @property
     def self_dim(self) -> int:
@@ -469,6 +473,38 @@ def rigid_body_step(P: HSParams, pos, quat, linvel, angvel, thrusts, yaw_torque,
     return p, q, v, w
 
 
+def apply_contacts(P: HSParams, p, v, tpos_old, cyl):
+    """contact_mode = 1 (PhysX stand-in, PARITY UNPINNED; the CUDA kernel's stage_contacts is the same arithmetic): project
+    every pursuer out of the standing cylinders it penetrates (2-D, below the cylinder top, in cylinder order) and out of the
+    evader's sphere (evader position at the start of the tick); the inward normal velocity is removed."""
+    if not P.contact_mode:
+        return p, v
+    p, v = p.clone(), v.clone()
+    Rc = P.cylinder_size + P.drone_radius
+    for k in range(cyl.shape[1]):
+        c = cyl[:, k].unsqueeze(1)                                # [E,1,3]
+        dx, dy = p[..., 0] - c[..., 0], p[..., 1] - c[..., 1]
+        d = torch.sqrt(dx * dx + dy * dy)
+        hit = (c[..., 2] > 0.0) & (p[..., 2] < 2.0 * c[..., 2]) & (d < Rc)
+        inv = 1.0 / d.clamp(min=1e-6)
+        nx, ny = dx * inv, dy * inv
+        p[..., 0] = torch.where(hit, c[..., 0] + nx * Rc, p[..., 0])
+        p[..., 1] = torch.where(hit, c[..., 1] + ny * Rc, p[..., 1])
+        vn = v[..., 0] * nx + v[..., 1] * ny
+        rem = hit & (vn < 0)
+        v[..., 0] = torch.where(rem, v[..., 0] - vn * nx, v[..., 0])
+        v[..., 1] = torch.where(rem, v[..., 1] - vn * ny, v[..., 1])
+    Re = P.evader_radius + P.drone_radius
+    rel = p - tpos_old.unsqueeze(1)
+    d = torch.linalg.vector_norm(rel, dim=-1, keepdim=True)
+    hit = d < Re
+    n = rel / d.clamp(min=1e-6)
+    p = torch.where(hit, tpos_old.unsqueeze(1) + n * Re, p)
+    vn = (v * n).sum(-1, keepdim=True)
+    v = torch.where(hit & (vn < 0), v - n * vn, v)
+    return p, v
+
+
 # ----------------------------------------------------------------------------
 # stage 6: observation (hideandseek.py:746-917)
 # ----------------------------------------------------------------------------
@@ -524,6 +560,9 @@ def observe(P: HSParams, st: Dict[str, torch.Tensor], tp_pred: Optional[torch.Te
 
     if P.use_tp_net:
         frame = torch.cat([progress.unsqueeze(-1), tpos_masked, tvel_masked, pos.reshape(E, -1)], dim=-1)
+        if P.use_obstacles:
+            frame = torch.cat([frame, torch.cat([cyl[..., :2], torch.full((E, cyl.shape[1], 1), P.cylinder_size, dtype=F32)],
+                                                dim=-1).reshape(E, -1)], dim=-1)
         out["tp_frame"] = frame
         out["tp_done"] = (progress <= (P.max_episode_length - P.future_step)).unsqueeze(-1)
         gt = tpos.clone()
@@ -699,6 +738,7 @@ class HideAndSeekOracle:
         self.prev_action[m, :, 3] = (0.5 * (P.max_thrust_ratio + cmd_init)).mean(-1)
         # one unforced physics tick for every env (hideandseek.py:722-723)
         p, q, v, w = rigid_body_step(P, st["pos"], st["quat"], st["linvel"], st["angvel"], None, None, None)
+        p, v = apply_contacts(P, p, v, st["tpos"], st["cyl"])
         st["pos"], st["quat"], st["linvel"], st["angvel"] = p, q, v, w
         st["tpos"] = st["tpos"] + P.dt * st["tvel"]
         st["progress"][m] = 0.0
@@ -730,6 +770,7 @@ class HideAndSeekOracle:
         self.stats[:, S["out_of_arena"]] = torch.logical_or(self.stats[:, S["out_of_arena"]].bool(), outside).float()
         st["tvel"] = tvel
         p, q, v, w = rigid_body_step(P, st["pos"], st["quat"], st["linvel"], st["angvel"], thrusts, moments.sum(-1), ext)
+        p, v = apply_contacts(P, p, v, st["tpos"], st["cyl"])
         st["pos"], st["quat"], st["linvel"], st["angvel"] = p, q, v, w
         st["tpos"] = st["tpos"] + P.dt * st["tvel"]
         st["progress"] = st["progress"] + 1

@@ -323,7 +323,7 @@ class RefEnv:
         e.drone_detect_radius, e.target_detect_radius = P.drone_detect_radius, P.target_detect_radius
         e.progress_buf = torch.zeros(E)
         e.max_episode_length = P.max_episode_length
-        e.use_TP_net, e.use_obstacles = P.use_tp_net, 0
+        e.use_TP_net, e.use_obstacles = P.use_tp_net, int(P.use_obstacles)
         e.history_step = P.history_step
         e.history_data = collections.deque(maxlen=P.history_step)
         e.future_predcition_step, e.arena_size, e.max_height = P.future_step, P.arena_size, P.max_height
@@ -356,7 +356,7 @@ class RefEnv:
         e.init_rpy_dist = U(torch.tensor([-0.2, -0.2, 0.0]) * torch.pi, torch.tensor([0.2, 0.2, 0.2]) * torch.pi)
         e.active_cylinders = torch.zeros(E, 1)
         if P.use_tp_net:
-            e.TP = R["TP_net"](input_dim=7 + 3 * A, output_dim=3 * P.future_step,
+            e.TP = R["TP_net"](input_dim=P.tp_frame_dim, output_dim=3 * P.future_step,
                                future_predcition_step=P.future_step, window_step=1)
             if tp_state_dict is not None:
                 e.TP.load_state_dict(tp_state_dict)

@@ -132,6 +132,28 @@ def test_update_epoch_property_reaches_graph_replayed_ticks():
     env.close()
 
 
+def test_use_obstacles_puts_the_cylinders_into_the_tp_frame():
+    """task.use_obstacles=1 (hideandseek.py:808-817): every TP frame also carries [x, y, size] of the C cylinders, the
+    predictor module (input width 7 + 3A + 3C) runs between hs_step_pre and hs_step_post."""
+    E = 32
+    m, cfg, base, env = make(E, **{"task.use_obstacles": 1})
+    C = base.num_cylinders
+    assert base.TP.lstm.input_size == 16 + 3 * C
+    td = env.reset()
+    from mupe_b200 import _lib as L
+    cyl = base.engine.get_state(L.FIELD_CYL_POS)
+    for t in range(3):
+        td.set(("agents", "action"), torch.randn(E, 3, 4, device=DEV))
+        td = env.step(td)
+        win = td[("next", "agents", "TP", "TP_input")]
+        assert tuple(win.shape) == (E, 10, 16 + 3 * C)
+        tail = win[:, -1, 16:].reshape(E, C, 3)
+        assert torch.equal(tail[..., :2], cyl[..., :2]) and (tail[..., 2] == 0.1).all()
+        assert tuple(td[("next", "agents", "observation", "state_self")].shape) == (E, 3, 1, 35)
+        td = m.step_mdp(td)
+    env.close()
+
+
 def test_collector_rollout_and_episode_boundary():
     E, T = 64, 8
     m, cfg, base, env = make(E, **{"task.env.max_episode_length": 5})

@@ -125,3 +125,51 @@ def test_wide_three_pursuers_against_oracle_both_builds():
         import mupe_b200  # noqa: F401
         P = O.HSParams()
         run_case(P, E=512, scenario="random_cylinders", steps=12, exact=exact, mapping=2)
+
+
+@pytest.mark.parametrize("mapping", [1, 2], ids=["4-lane", "1-lane"])
+def test_analytic_contacts_against_oracle(mapping):
+    """hs_config.contact_mode = 1 (cylinder / evader contact response after the integration; the PhysX stand-in's optional
+    part, parity unpinned like the integrator): both mappings against oracle.apply_contacts, from states that put pursuers
+    INSIDE cylinders and inside the evader's sphere, then through ordinary ticks."""
+    import mupe_b200
+    from tests.util import push_state, pull_state
+    P = O.HSParams(contact_mode=1, num_cylinders=8)
+    E, dev = 128, torch.device("cuda:0")
+    eng = mupe_b200.HsEngine(hs_config_from_params(P, E), dev)
+    eng.set_tick_mapping(mapping)
+    orc = O.HideAndSeekOracle(P, E)
+    tp_fn = make_tp(P)
+    g = torch.Generator().manual_seed(3)
+    init = O.sample_reset(P, E, g, min_cylinders=8)
+    # pursuer 0 starts 5 cm from the axis of cylinder 0, pursuer 1 3 cm from the evader, pursuer 2 where it was sampled
+    init["drone_pos"][:, 0, :2] = init["cyl_pos"][:, 0, :2] + torch.tensor([0.03, 0.04])
+    init["drone_pos"][:, 1] = init["target_pos"] + torch.tensor([0.02, -0.02, 0.01])
+    mask = torch.ones(E, dtype=torch.bool)
+    want = orc.reset(mask, init, tp_fn)
+    got = eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+    eng.step_post(want["tp_pred"].to(dev))
+    st = pull_state(eng)
+    d0 = (orc.st["pos"][:, 0, :2] - init["cyl_pos"][:, 0, :2]).norm(dim=-1)
+    # projected onto the contact circle of cylinder 0 (a neighbouring cylinder 0.2 m away may push it on: sequential projection)
+    assert (torch.isclose(d0, torch.full_like(d0, 0.16), atol=1e-5).float().mean() > 0.6) and (d0 > 0.1).all()
+    d1 = (orc.st["pos"][:, 1] - orc.st["tpos"]).norm(dim=-1)
+    assert (d1 > 0.1).all()                                                      # pushed out of the evader's sphere (then it moved on)
+    for k in ("pos", "linvel"):
+        from tests.util import assert_close
+        assert_close(f"reset/{k}", st[k], orc.st[k])
+    done_prev = torch.zeros(E, dtype=torch.bool)
+    for t in range(15):
+        act = torch.randn(E, 3, 4, generator=g) * 0.5
+        push_state(eng, orc)
+        pre, v_prey = {k: v.clone() for k, v in orc.st.items()}, orc.v_prey
+        want = orc.step(act, done_prev, tp_fn)
+        cond = CD.TickConditioning(P, v_prey, pre, orc.st, eps=EPS[False])
+        got = eng.step_pre(act.to(dev), raw=True, reset_pid=done_prev.to(dev))
+        eng.step_post(want["tp_pred"].to(dev))
+        st = pull_state(eng)
+        for k in ("pos", "linvel", "quat", "tpos"):
+            cond.check(f"t{t}/state/{k}", st[k], orc.st[k])
+        cond.check(f"t{t}/reward", got["reward"], want["reward"])
+        cond.check(f"t{t}/drone_state", got["drone_state"], want["drone_state"])
+    eng.close()

@@ -19,7 +19,7 @@ def hs_config_from_params(P: O.HSParams, E: int):
         collision_coef=P.collision_coef, speed_coef=P.speed_coef, smoothness_coef=P.smoothness_coef,
         smoothness_gated=(not P.envgen_variant) and (not P.use_deployment),
         write_smoothness_coef_stat=not P.envgen_variant, ground_clamp=P.ground_clamp,
-        max_linear_velocity=P.max_linear_velocity)
+        max_linear_velocity=P.max_linear_velocity, use_obstacles=P.use_obstacles, contact_mode=P.contact_mode)
 
 
 def push_state(engine, orc):
