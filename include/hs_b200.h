@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define HS_ABI_VERSION 2
+#define HS_ABI_VERSION 3
 #define HS_NUM_STATS 24
 #define HS_MAX_AGENTS 6          /* 1..3: both tick mappings and every fused kernel; 4..6: one-lane-per-env tick only */
 #define HS_MAX_CYLINDERS 8
@@ -166,6 +166,15 @@ typedef struct hs_buffers {
                                    graphs follow the curriculum without re-capture. */
     float* throttle_diff;       /* [E,A] or NULL: |throttle_t - throttle_{t-1}|_2 per pursuer = drone.throttle_difference
                                    (multirotor.py:480-484), an output for callers that log it (Hover's action_smoothness) */
+    /* Ring form of the TP window (optional, both or neither; wide tick mapping, num_agents >= 3).  When set, the tick
+     * does NOT shift a chronological [E,H,FD] tensor every tick (576 B read + 640 B written per env for the reference's
+     * shape, hideandseek.py:819-831 re-stacks its deque); it writes the new frame twice, at slots p and p + H of
+     * tp_ring [E, 2H, FD], and advances p = tp_ring_pos[e / 32].  The chronological window of env e after the tick is
+     * the CONTIGUOUS span tp_ring[e, p' : p' + H, :] with p' the advanced position - a strided [E,H,FD] view with env
+     * stride 2*H*FD, valid until the next tick; hs_step_post_tp reads it in place.  tp_input / tp_input_prev are
+     * ignored (may be NULL). */
+    float* tp_ring;             /* [E, 2H, FD] or NULL */
+    int32_t* tp_ring_pos;       /* [ceil(E/32)] zero-initialised by the caller, or NULL */
 } hs_buffers;
 
 typedef struct hs_handle hs_handle;

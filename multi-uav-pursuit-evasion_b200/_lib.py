@@ -10,7 +10,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
 
-HS_ABI_VERSION = 2
+HS_ABI_VERSION = 3
 HS_NUM_STATS = 24
 HS_OPT_PREDICTOR_VARIANT = 1
 HS_OPT_HOST_IO_GRAPH = 2
@@ -65,6 +65,7 @@ _BUF_FIELDS = [
     "arena", "stats", "state_self", "state_others", "obs_cylinders", "state_drones", "tp_input",
     "tp_input_prev", "tp_groundtruth", "tp_done", "reward", "done", "truncated", "drone_state",
     "prev_action", "rotor_cmds", "ctbr", "target_rate", "action_error", "v_prey", "smoothness_coef", "throttle_diff",
+    "tp_ring", "tp_ring_pos",
 ]
 
 

@@ -35,6 +35,15 @@ struct KParams {
     int tp_init;                     // 1: first frame ever -> fill all H history rows
 };
 
+// Chronological TP window of the tile that starts at env e0 (a multiple of 32): base pointer + distance between
+// consecutive envs.  Plain mode: bufs.tp_input [E,H,FD].  Ring mode (bufs.tp_ring, include/hs_b200.h): the span that
+// starts at the tile's advanced ring position; the position is the same for every tile of a batch.
+__device__ __forceinline__ const float* tp_window_base(const KParams& P, int64_t e0, int HFD, int FD, int64_t& env_stride) {
+    if (P.b.tp_ring == nullptr) { env_stride = HFD; return P.b.tp_input + e0 * (int64_t)HFD; }
+    env_stride = 2 * (int64_t)HFD;
+    return P.b.tp_ring + e0 * env_stride + (int64_t)P.b.tp_ring_pos[e0 >> 5] * FD;
+}
+
 struct V3 { float x, y, z; };
 struct Q4 { float w, x, y, z; };
 

@@ -138,11 +138,12 @@ static bool encode_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t
 static bool wide_possible(const hs_handle* h) {
     const hs_config& c = h->cfg;
     if ((c.num_envs & 3) != 0 || c.num_agents < 3) return false;
-    if (c.use_tp_net && h->bufs.tp_input == h->bufs.tp_input_prev) return false;
+    if (c.use_tp_net && !h->bufs.tp_ring && h->bufs.tp_input == h->bufs.tp_input_prev) return false;
     return true;
 }
+static bool tp_ring_mode(const hs_handle* h) { return h->cfg.use_tp_net && h->bufs.tp_ring != nullptr; }
 static bool use_wide(const hs_handle* h) {
-    if (h->cfg.num_agents > NARROW_MAX_AGENTS || (h->cfg.use_obstacles && h->cfg.use_tp_net)) return true;
+    if (h->cfg.num_agents > NARROW_MAX_AGENTS || (h->cfg.use_obstacles && h->cfg.use_tp_net) || tp_ring_mode(h)) return true;
     if (h->tick_mapping == 1) return false;
     if (h->tick_mapping == 2) return wide_possible(h);
     return h->cfg.num_envs >= 32768 && wide_possible(h);
@@ -438,8 +439,12 @@ int hs_bind_buffers(hs_handle* h, const hs_buffers* b) {
         !b->action_error || !b->v_prey)
         return set_err(HS_ERR_INVALID, "hs_bind_buffers: a required buffer is NULL%s");
     if (c.num_agents > 1 && !b->state_others) return set_err(HS_ERR_INVALID, "state_others is NULL%s");
-    if (c.use_tp_net && (!b->tp_input || !b->tp_input_prev || !b->tp_groundtruth || !b->tp_done))
-        return set_err(HS_ERR_INVALID, "use_tp_net needs tp_input/tp_input_prev/tp_groundtruth/tp_done%s");
+    if ((b->tp_ring != nullptr) != (b->tp_ring_pos != nullptr))
+        return set_err(HS_ERR_INVALID, "tp_ring and tp_ring_pos come together%s");
+    if (c.use_tp_net && b->tp_ring && (c.num_agents < 3 || (c.num_envs & 3) != 0))
+        return set_err(HS_ERR_INVALID, "tp_ring needs the lane-per-env tick mapping: num_agents >= 3 and num_envs a multiple of 4%s");
+    if (c.use_tp_net && (!(b->tp_ring || (b->tp_input && b->tp_input_prev)) || !b->tp_groundtruth || !b->tp_done))
+        return set_err(HS_ERR_INVALID, "use_tp_net needs tp_input/tp_input_prev (or tp_ring/tp_ring_pos) and tp_groundtruth/tp_done%s");
     h->bufs = *b;
     h->bound = true;
     return HS_OK;
@@ -479,7 +484,7 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     if (h->cfg.num_agents > NARROW_MAX_AGENTS || h->cfg.use_obstacles)
         return set_err(HS_ERR_INVALID, "hs_step_fused: the fused predictor kernels cover num_agents <= 3 without use_obstacles; use hs_step_pre + the module + hs_step_post%s");
     const int64_t tiles32 = ((int64_t)h->cfg.num_envs + TN_E - 1) / TN_E;
-    const bool one_launch = h->fused_tick && !h->exact_math && h->tick_mapping != 2 && (h->tp_variant < 0 || h->tp_variant == 5) &&
+    const bool one_launch = h->fused_tick && !h->exact_math && h->tick_mapping != 2 && !tp_ring_mode(h) && (h->tp_variant < 0 || h->tp_variant == 5) &&
                             tiles32 <= h->num_sms && tp_fused_smem_bytes(h->cfg) <= HS_MAX_DYN_SMEM && h->cfg.num_agents <= 3;
     if (!one_launch) {
         const int rc = hs_step_pre(h, action, action_is_raw, reset_pid, stream);

@@ -116,7 +116,8 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TPB_E;
         const int nenv = (int)min((int64_t)TPB_E, E - e0);
-        const float* xin = P.b.tp_input + e0 * (int64_t)(H * FD);
+        int64_t xstride;
+        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride);
         float cst[TP_NE];
 #pragma unroll
         for (int e = 0; e < TP_NE; ++e) cst[e] = 0.f;
@@ -126,7 +127,7 @@ hs_tp_fill_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPP
             float* dst = xs + (s & 1) * FD * TPB_E;
             for (int i = tid; i < TPB_E * FD; i += TP_THREADS) {
                 const int e = i / FD, k = i - e * FD;
-                if (e < nenv) cp_async4(dst + k * TPB_E + e, xin + (int64_t)e * (H * FD) + s * FD + k);
+                if (e < nenv) cp_async4(dst + k * TPB_E + e, xin + (int64_t)e * xstride + s * FD + k);
                 else dst[k * TPB_E + e] = 0.0f;
             }
             cp_async_commit();
@@ -328,7 +329,8 @@ hs_tp_fill_wide_kernel(const __grid_constant__ KParams P, const __grid_constant_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TW_E;
         const int nenv = (int)min((int64_t)TW_E, E - e0);
-        const float* xin = P.b.tp_input + e0 * (int64_t)(H * FD);
+        int64_t xstride;
+        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride);
         float cst[TW_NE][2];
 #pragma unroll
         for (int e = 0; e < TW_NE; ++e) { cst[e][0] = 0.f; cst[e][1] = 0.f; }
@@ -338,7 +340,7 @@ hs_tp_fill_wide_kernel(const __grid_constant__ KParams P, const __grid_constant_
             float* dst = xs + (s & 1) * FD * TW_E;
             for (int i = tid; i < TW_E * FD; i += TW_THREADS) {
                 const int e = i / FD, k = i - e * FD;
-                if (e < nenv) cp_async4(dst + k * TW_E + e, xin + (int64_t)e * (H * FD) + s * FD + k);
+                if (e < nenv) cp_async4(dst + k * TW_E + e, xin + (int64_t)e * xstride + s * FD + k);
                 else dst[k * TW_E + e] = 0.0f;
             }
             cp_async_commit();

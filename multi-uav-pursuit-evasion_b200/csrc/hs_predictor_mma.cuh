@@ -105,7 +105,8 @@ hs_tp_fill_mma_kernel(const __grid_constant__ KParams P, const __grid_constant__
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TE;
         const int nenv = (int)min((int64_t)TE, E - e0);
-        const float* xin = P.b.tp_input + e0 * (int64_t)(H * FD);
+        int64_t xstride;
+        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride);
         float cst[MT][4][2];
 #pragma unroll
         for (int m = 0; m < MT; ++m)
@@ -118,7 +119,7 @@ hs_tp_fill_mma_kernel(const __grid_constant__ KParams P, const __grid_constant__
             for (int i = tid; i < TE * 8 * TM_XK; i += TM_THREADS) {
                 const int r = i / (8 * TM_XK), k = i - r * (8 * TM_XK);
                 float* d = dst + tm_aidx(TM_XK, r, k >> 3, k & 7);
-                if (r < nenv && k < FD) cp_async4(d, xin + (int64_t)r * (H * FD) + s * FD + k);
+                if (r < nenv && k < FD) cp_async4(d, xin + (int64_t)r * xstride + s * FD + k);
                 else *d = 0.0f;
             }
             cp_async_commit();

@@ -143,7 +143,8 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
         float cst[32], hreg[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) { cst[j] = 0.f; hreg[j] = 0.f; }
-        const float* xin = P.b.tp_input + e * (int64_t)(H * FD);
+        int64_t xstride;
+        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride) + (e - e0) * xstride;
         float xf[16];
         auto load_x = [&](int s) {
 #pragma unroll
@@ -435,7 +436,9 @@ __device__ __forceinline__ TnLane tn_lane_consts(const TPParams& W, int row) {
 // x of all H steps of one 32-env tile -> B operand (tf32 hi/lo): lane = (env & 7) + 8 * (k & 3) per core
 // matrix, so the 32 stores of a warp cover 128 contiguous bytes; loads are issued ten at a time.
 template <int FD, int NTHREADS = TN_THREADS>
-__device__ __forceinline__ void tn_stage_x(const float* __restrict__ tp_input, int64_t e0, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
+__device__ __forceinline__ void tn_stage_x(const KParams& P, int64_t e0, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
+    int64_t xstride;
+    const float* __restrict__ win = tp_window_base(P, e0, H * FD, FD, xstride);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane & 7, kk = lane >> 3;
     constexpr int NW = NTHREADS / 32, BATCH = 10;
@@ -447,7 +450,7 @@ __device__ __forceinline__ void tn_stage_x(const float* __restrict__ tp_input, i
             const int s = cm >> 4, kc = (cm >> 2) & 3, ng = cm & 3;
             const int n = ng * 8 + rr, k = kc * 4 + kk;
             xv[u] = 0.0f;
-            if (cm < H * 16 && n < nenv && k < FD) xv[u] = __ldg(tp_input + (e0 + n) * (int64_t)(H * FD) + s * FD + k);
+            if (cm < H * 16 && n < nenv && k < FD) xv[u] = __ldg(win + n * xstride + s * FD + k);
         }
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
@@ -748,7 +751,7 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = (int64_t)tile * TN_E;
         const int nenv = (int)min((int64_t)TN_E, E - e0);
-        tn_stage_x<FD>(P.b.tp_input, e0, nenv, H, Xhi, Xlo);
+        tn_stage_x<FD>(P, e0, nenv, H, Xhi, Xlo);
         float cst[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) cst[j] = 0.f;
@@ -994,7 +997,7 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     const int nenv = (int)min((int64_t)TN_E, E - e0);
     const TnRowIn RI = tn_row_load<A>(P, e0, nenv);          // new state of the tile (written by the tick warps above)
     if (WITH_TICK) tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
-    else tn_stage_x<FD, NTH>(P.b.tp_input, e0, nenv, H, Xhi, Xlo);
+    else tn_stage_x<FD, NTH>(P, e0, nenv, H, Xhi, Xlo);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -1139,7 +1142,7 @@ hs_tp_fill_tcw_kernel(const __grid_constant__ KParams P, const __grid_constant__
         for (int t = 0; t < NT; ++t)
             if (t < nslots) {
                 const int64_t e0 = (int64_t)(NT * grp + t) * TN_E;
-                tn_stage_x<FD, TCW_THREADS>(P.b.tp_input, e0, (int)min((int64_t)TN_E, E - e0), H, Xb + t * xslot,
+                tn_stage_x<FD, TCW_THREADS>(P, e0, (int)min((int64_t)TN_E, E - e0), H, Xb + t * xslot,
                                            Xb + t * xslot + (size_t)H * TN_X_STEP);
             }
         fence_async_smem();                   // generic-proxy writes (x) -> visible to the MMA's async proxy

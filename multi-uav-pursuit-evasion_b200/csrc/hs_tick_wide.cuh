@@ -214,7 +214,10 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
     __syncthreads();                                              // the barrier is initialised before anyone polls it
     // ---- the TP window moves global -> global while the tile is in flight (all warps: one round trip, under the TMA wait)
     const int per_env = H * FD, keep = (H - 1) * FD;
-    if (tp_on && !P.tp_init && keep > 0) {
+    // ring form of the window (hs_buffers.tp_ring): nothing to shift - the new frame is written twice in phase 4
+    const bool ring = tp_on && P.b.tp_ring != nullptr;
+    const int ring_pos = ring ? P.b.tp_ring_pos[blockIdx.x] : 0;
+    if (tp_on && !ring && !P.tp_init && keep > 0) {
         const float* src = P.b.tp_input_prev + e0 * per_env;
         float* dst = P.b.tp_input + e0 * per_env;
         constexpr int NT = (A + 1) * 32;
@@ -425,9 +428,13 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < CT; ++k) { fr[FD0 + 3 * k] = cx[k]; fr[FD0 + 3 * k + 1] = cy[k]; fr[FD0 + 3 * k + 2] = c.cylinder_size; }
             if (valid) {
-                float* win = P.b.tp_input + e * per_env;
-                const int h0 = P.tp_init ? 0 : H - 1;
-                for (int h = h0; h < H; ++h) {
+                // plain: row H-1 of the shifted window (every row on the very first frame); ring: slots p and p + H of
+                // the env's 2H slots (every slot on the very first frame)
+                float* win = ring ? P.b.tp_ring + e * (2 * per_env) : P.b.tp_input + e * per_env;
+                const int h0 = P.tp_init ? 0 : (ring ? ring_pos : H - 1);
+                const int h1 = ring ? (P.tp_init ? 2 * H : ring_pos + H + 1) : H;
+                const int hs = (ring && !P.tp_init) ? H : 1;
+                for (int h = h0; h < h1; h += hs) {
                     float* row = win + h * FD;
                     if ((FD0 & 3) == 0 && FD == FD0) {
 #pragma unroll
@@ -498,6 +505,7 @@ hs_tick_wide_kernel(const __grid_constant__ KParams P, const __grid_constant__ C
     if (role == 0) {
         if (lane == 0) {
             wd_tma_store_2d(&tm_state_st, 0, (int)(e0 >> 5) * P.R, wd_smem(S));
+            if (ring) P.b.tp_ring_pos[blockIdx.x] = (ring_pos + 1 == H) ? 0 : ring_pos + 1;
         }
         const int64_t r0 = e0 * A;
         wd_store_span(P.b.drone_state + r0 * 13, mem + w.o_dstate, A * 13, nenv, full, lane);

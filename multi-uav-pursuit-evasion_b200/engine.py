@@ -172,7 +172,36 @@ class HsEngine:
         b.tp_done, b.done, b.truncated = _ptr(s["tp_done"]), _ptr(s["done"]), _ptr(s["truncated"])
         b.prev_action, b.v_prey = _ptr(self.prev_action), _ptr(self.v_prey)
         b.smoothness_coef = _ptr(self.smoothness_coef)
+        if getattr(self, "tp_ring", None) is not None:
+            b.tp_ring, b.tp_ring_pos = _ptr(self.tp_ring), _ptr(self.tp_ring_pos)
         return b
+
+    def set_tp_ring(self, on: bool = True):
+        """Ring form of the TP window (hs_buffers.tp_ring, include/hs_b200.h): the tick writes the new frame twice into
+        ``tp_ring`` [E, 2H, FD] instead of shifting a chronological [E,H,FD] tensor (1216 B/env/tick less HBM traffic for
+        the reference's shape).  The window is then :meth:`tp_window`, a strided view valid until the next tick, and
+        ``out["tp_input"]`` is NOT written.  Lane-per-env tick mapping only (num_agents >= 3); call before the first
+        reset / tick."""
+        if not self.cfg.use_tp_net:
+            raise _lib.HsError("set_tp_ring: config has use_tp_net == 0")
+        if on:
+            H, FD = self.cfg.history_step, self.sets[0]["tp_input"].shape[-1]
+            self.tp_ring = torch.zeros(self.E, 2 * H, FD, dtype=torch.float32, device=self.device)
+            self.tp_ring_pos = torch.zeros((self.E + 31) // 32, dtype=torch.int32, device=self.device)
+        else:
+            self.tp_ring = self.tp_ring_pos = None
+        self._bufs = [self._make_bufs(i) for i in range(len(self.sets))]
+        self._graphs = None
+        self._bind(self.cur)
+        return self
+
+    def tp_window(self) -> torch.Tensor:
+        """The chronological TP window [E,H,FD] of the latest tick: ``out["tp_input"]`` in plain mode, the strided view
+        into the ring in ring mode (reads the ring position from the device: one 4-byte D2H)."""
+        if getattr(self, "tp_ring", None) is None:
+            return self.out["tp_input"]
+        p, H = int(self.tp_ring_pos[0].item()), self.cfg.history_step
+        return self.tp_ring[:, p:p + H, :]
 
     def _bind(self, i: int, prev: Optional[int] = None):
         """Binds output set i; the previous TP window is read from set ``prev`` (default: the set
@@ -218,6 +247,7 @@ class HsEngine:
             raise _lib.HsError("attach_policy: the actor must be a DiagGaussian head over the 4 CTBR commands")
         E, A, dev = self.E, self.A, self.device
         self._actor, self._critic, self._deterministic = actor, critic, bool(deterministic)
+        self.parallel_critic = True         # graphs: critic as a parallel branch beside actor -> tick
         if not deterministic and getattr(actor, "rng_state", None) is None:
             actor.seed(0)
         if self.storage is not None:
@@ -229,14 +259,29 @@ class HsEngine:
         self._graphs = None
         return self
 
-    def _launch_policy(self, prev: int, i: int):
-        """actor (+ critic) on the observation held by set ``prev``; results into policy_out[i]."""
+    def _launch_policy(self, prev: int, i: int, fork: bool = False):
+        """actor (+ critic) on the observation held by set ``prev``; results into policy_out[i].  ``fork`` (graph capture):
+        the critic, which nothing in the tick depends on, goes to a side stream and becomes a parallel branch of the
+        graph; returns the event the caller joins on after the tick."""
         obs, po = self.sets[prev], self.policy_out[i]
         others = obs["state_others"] if self.A > 1 else None
+        joined = None
+        if self._critic is not None and fork:
+            cur = torch.cuda.current_stream(self.device)
+            if getattr(self, "_critic_stream", None) is None:
+                self._critic_stream = torch.cuda.Stream(self.device)
+            start = torch.cuda.Event()
+            start.record(cur)
+            self._critic_stream.wait_event(start)
+            with torch.cuda.stream(self._critic_stream):
+                self._critic.forward(obs["state_self"], others, obs["obs_cylinders"], out={"head": po["state_value"]})
+                joined = torch.cuda.Event()
+                joined.record(self._critic_stream)
         self._actor.forward(obs["state_self"], others, obs["obs_cylinders"], sample=not self._deterministic,
                             out={"head": po["action_mean"], "action": po["action"], "logp": po["logp"]})
-        if self._critic is not None:
+        if self._critic is not None and not fork:
             self._critic.forward(obs["state_self"], others, obs["obs_cylinders"], out={"head": po["state_value"]})
+        return joined
 
     def policy_tick(self, tp_weights=None, reset_pid: Optional[torch.Tensor] = None) -> OutputSet:
         """One rollout step without CUDA graphs: actor -> critic -> tick -> fused predictor (4 launches)."""
@@ -448,8 +493,9 @@ class HsEngine:
         with torch.cuda.graph(g, stream=side):
             st = torch.cuda.current_stream(dev).cuda_stream
             action = self.graph_action
+            joined = None
             if getattr(self, "_actor", None) is not None:
-                self._launch_policy(prev, i)
+                joined = self._launch_policy(prev, i, fork=self.parallel_critic)
                 action = self.policy_out[i]["action"]
             n0 = int(lib.hs_launch_count(self._h))
             if self.cfg.use_tp_net:
@@ -461,6 +507,8 @@ class HsEngine:
                 check(lib.hs_step_pre(self._h, action.data_ptr(), 1 if self._graph_raw else 0,
                                       self.graph_reset_pid.data_ptr(), st), "hs_step_pre (capture)")
             self._graph_kernels = int(lib.hs_launch_count(self._h)) - n0
+            if joined is not None:
+                torch.cuda.current_stream(dev).wait_event(joined)
         self._graphs[(prev, i)] = g
         self._graph_captures = getattr(self, "_graph_captures", 0) + 1
         self._bind(keep, keep)

@@ -173,3 +173,63 @@ def test_analytic_contacts_against_oracle(mapping):
         cond.check(f"t{t}/reward", got["reward"], want["reward"])
         cond.check(f"t{t}/drone_state", got["drone_state"], want["drone_state"])
     eng.close()
+
+
+@pytest.mark.parametrize("E,A,variant", [(256, 3, -1), (100, 3, 0), (128, 3, 1), (300, 3, 2), (2052, 3, 3), (64, 4, None)])
+def test_tp_ring_window_equals_shifted_window(E, A, variant):
+    """hs_buffers.tp_ring: the frame written twice into a 2H-slot ring gives, as a strided view, the same chronological
+    window the plain mode shifts every tick - bit for bit over more than two wraps of the ring, through a partial reset -
+    and the fused predictor kernels read it in place (same prediction-dependent rows)."""
+    import mupe_b200
+    P = O.HSParams(num_agents=A)
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    g = torch.Generator().manual_seed(E + A)
+    init = O.sample_reset(P, E, g)
+    plain, ring = mupe_b200.HsEngine(cfg, dev), mupe_b200.HsEngine(cfg, dev)
+    plain.set_tick_mapping(2)
+    ring.set_tp_ring(True)
+    w = None
+    if variant is not None:
+        torch.manual_seed(0)
+        tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+        for e in (plain, ring):
+            e.set_predictor_variant(variant)
+        w = True
+    keys = KEYS + ("tp_groundtruth", "tp_done") + (("state_self", "state_drones") if w else ())
+
+    def post(e):
+        if w:
+            e.step_post_tp(e.tp_weights(tp))
+
+    def same(tag):
+        assert torch.equal(plain.out["tp_input"], ring.tp_window()), f"{tag}: window differs"
+        for k in keys:
+            assert torch.equal(plain.out[k], ring.out[k]), f"{tag}: {k} differs"
+        assert torch.equal(plain.arena, ring.arena) and torch.equal(plain.stats, ring.stats), tag
+
+    for e in (plain, ring):
+        e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        post(e)
+    same("reset")
+    H = P.history_step
+    for t in range(2 * H + 5):
+        act = torch.randn(E, A, 4, generator=g).to(dev)
+        for e in (plain, ring):
+            e.step_pre(act, raw=True)
+            post(e)
+        same(f"tick {t}")
+        if t == H + 2:
+            init2 = O.sample_reset(P, E, g)
+            mask = (torch.rand(E, generator=g) < 0.5).to(dev)
+            for e in (plain, ring):
+                e.reset(mask, init2["drone_pos"], init2["drone_rot"], init2["target_pos"], init2["cyl_pos"])
+                post(e)
+            same("partial reset")
+    assert int(ring.tp_ring_pos.min()) == int(ring.tp_ring_pos.max())
+    # the ring needs the lane-per-env mapping
+    with pytest.raises(mupe_b200.HsError):
+        small = mupe_b200.HsEngine(hs_config_from_params(O.HSParams(num_agents=2), 64), dev)
+        small.set_tp_ring(True)
+    for e in (plain, ring):
+        e.close()

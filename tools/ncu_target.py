@@ -21,6 +21,8 @@ def main():
     tp = mupe_b200.TP_net(16, 15, 5).to(dev)
     eng = mupe_b200.HsEngine(cfg, dev)
     eng.set_tick_mapping(int(os.environ.get("HS_TICK_MAPPING", "0")))      # 1: 4 lanes per env, 2: one lane per env
+    if os.environ.get("HS_TP_RING", "0") == "1":
+        eng.set_tp_ring(True)                                              # TP window as a ring (hs_buffers.tp_ring)
     a = 0.9 / 2 ** 0.5
     dpos = torch.rand(E, 3, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a + 0.1, 0.5], device=dev)
     tpos = torch.rand(E, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([-a + 0.1, -a + 0.1, 0.5], device=dev)

@@ -36,13 +36,16 @@ def run(E, dev, peak, reps=20):
         cyl[..., 2] = 0.6
         eng.set_predictor_variant(int(os.environ.get("HS_TP_VARIANT", "-1")))
         eng.set_tick_mapping(int(os.environ.get("HS_TICK_MAPPING", "0")))      # 1: 4 lanes per env, 2: one lane per env
+        if os.environ.get("HS_TP_RING", "0") == "1":
+            eng.set_tp_ring(True)
         eng.reset(None, dpos, rot, tpos, cyl)
         eng.step_post_tp(eng.tp_weights(tp))
         eng.graph_action = torch.randn(E, 3, 4, device=dev)
         engs.append(eng)
     torch.cuda.synchronize()
     n = max(R, 32 if E <= 65536 else 8)
-    out = {"E": E, "num_cylinders": C, "rotating_batches": R, "tick_mapping": int(os.environ.get("HS_TICK_MAPPING", "0"))}
+    out = {"E": E, "num_cylinders": C, "rotating_batches": R, "tick_mapping": int(os.environ.get("HS_TICK_MAPPING", "0")),
+           "tp_ring": int(os.environ.get("HS_TP_RING", "0"))}
     ab = bench.algorithmic_bytes(C=C)
     for name, fn, nbytes in (
             ("tick", lambda e, st: check(lib.hs_step_pre(e._h, e.graph_action.data_ptr(), 1, None, st), "pre"), ab["tick"]),
