@@ -310,6 +310,23 @@ int hs_state_get(hs_handle* h, int field, float* dst, void* stream);
 int hs_state_set(hs_handle* h, int field, const float* src, void* stream);
 /* Number of kernels this handle has launched so far (bench `gpu_launches`). */
 int64_t hs_launch_count(const hs_handle* h);
+/* A whole rollout of `num_ticks` control ticks (tick + predictor, as hs_step_fused) in ONE kernel launch: what the
+ * collector's loop `for t in range(T): td = env.step(td)` (omni_drones/utils/torchrl/collector.py:34-66) does when the
+ * actions of the T ticks are already on the device (open-loop action sequences, replayed rollouts, benchmarks) - with a
+ * policy in the loop use hs_step_fused per tick.  Every CTA keeps its 32-env tile for the whole rollout: the predictor's
+ * weights go to tensor memory once, the TP window stays in shared memory, and the tick of step t+1 runs on dedicated
+ * warps while the tensor cores work on the predictor of step t.
+ *   sets_device [num_sets]: DEVICE array of buffer tables; tick t writes sets[(first_set + t) % num_sets] (e.g. the rows of
+ *     a time-major rollout storage).  The handle must be bound (hs_bind_buffers) to a table with the same arena / stats /
+ *     prev_action; tp_input_prev of the tables is ignored: the window before the first tick is first_tp_prev [E,H,7+3A].
+ *   action [T][E,A,4] with action_tick_stride floats between ticks (0 = the same action every tick).
+ *   tp_pred_out (or NULL) [T][E,3F] with pred_tick_stride floats between ticks.
+ * Same results, bit for bit, as num_ticks calls of hs_step_fused.  HS_ERR_INVALID unless num_agents == 3, history_step == 10,
+ * use_tp_net, no use_obstacles, fast-math build, plain TP window, and hs_reset has run. */
+int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, int first_set, const float* first_tp_prev,
+                     const float* action, int64_t action_tick_stride, int action_is_raw, int num_ticks, const hs_tp_weights* w,
+                     float* tp_pred_out, int64_t pred_tick_stride, void* stream);
+
 /* Tunables.  HS_OPT_PREDICTOR_VARIANT: -1 = auto (default: variant 5 while a launch has at most one
  * 32-env tile per SM, variant 4 above), 0 = fp32 FFMA predictor kernel,
  * 1 = tensor-core predictor, warp-level mma.sync (error-compensated 3xTF32, fp32-level results),

@@ -170,6 +170,8 @@ _EXPORTS = {
     "hs_step_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_step_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_step_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
+    "hs_rollout_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                   C.POINTER(hs_tp_weights), C.c_void_p, C.c_int64, C.c_void_p]),
     "hs_step_post_tp": (C.c_int, [C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
     "hs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -42,6 +42,7 @@
 #include "hs_predictor_ffma.cuh"
 #include "hs_predictor_mma.cuh"
 #include "hs_predictor_tcgen05.cuh"
+#include "hs_rollout_fused.cuh"
 #include "hs_reset.cuh"
 #include "hs_hover.cuh"
 #include "hs_samplers.cuh"
@@ -89,6 +90,7 @@ struct hs_handle {
     int io_graph_mode = 1;       // HS_OPT_HOST_IO_GRAPH: 1 = graph launch (default), 0 = stream API calls
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
     int exact_math = 0;          // HS_OPT_EXACT_MATH: the tick runs the IEEE-arithmetic build of hs_tick_kernel (parity evidence)
+    bool rollout_ready = false;  // hs_rollout_fused_kernel's shared-memory attribute set
     int tick_mapping = 0;        // HS_OPT_TICK_MAPPING: 0 auto, 1 four lanes per env, 2 one lane per env (hs_tick_wide_kernel)
     // TMA tensor maps of the one-lane mapping (state tile load / store, stats tile), valid for tm_arena / tm_stats
     CUtensorMap tm[3];
@@ -517,6 +519,52 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     h->tp_frames += 1;
+    return HS_OK;
+}
+
+// T control ticks (tick + predictor each) in ONE launch: hs_rollout_fused_kernel keeps a 32-env tile per CTA for the whole
+// rollout (csrc/hs_rollout_fused.cuh).  Same results as T calls of hs_step_fused.
+int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, int first_set, const float* first_tp_prev,
+                     const float* action, int64_t action_tick_stride, int action_is_raw, int num_ticks, const hs_tp_weights* w,
+                     float* tp_pred_out, int64_t pred_tick_stride, void* stream) {
+    if (!h || !sets_device || !first_tp_prev || !action || !w) return set_err(HS_ERR_INVALID, "hs_rollout_fused: null argument%s");
+    if (!h->bound) return set_err(HS_ERR_UNBOUND, "hs_rollout_fused: call hs_bind_buffers first%s");
+    const hs_config& c = h->cfg;
+    if (num_sets < 1 || first_set < 0 || first_set >= num_sets || num_ticks < 1)
+        return set_err(HS_ERR_INVALID, "hs_rollout_fused: num_sets >= 1, 0 <= first_set < num_sets, num_ticks >= 1%s");
+    const int64_t tiles32 = ((int64_t)c.num_envs + TN_E - 1) / TN_E;
+    if (!c.use_tp_net || c.num_agents != 3 || c.history_step != 10 || c.use_obstacles || h->exact_math || tp_ring_mode(h) ||
+        rollout_fused_smem_bytes(c) > HS_MAX_DYN_SMEM)
+        return set_err(HS_ERR_INVALID, "hs_rollout_fused covers the reference's shape (3 pursuers, history_step 10, use_tp_net, no use_obstacles, "
+                                       "fast-math build, plain TP window); use hs_step_fused per tick otherwise%s");
+    if (h->tp_frames == 0) return set_err(HS_ERR_INVALID, "hs_rollout_fused: run hs_reset first (the first frame fills the TP window)%s");
+    if (!w->weight_ih || !w->weight_hh || !w->bias_ih || !w->bias_hh || !w->fc_weight || !w->fc_bias)
+        return set_err(HS_ERR_INVALID, "hs_rollout_fused: a weight pointer is NULL%s");
+    if (w->hidden_size != TP_HID || w->input_size != 7 + 3 * c.num_agents || w->output_size != 3 * c.future_step)
+        return set_err(HS_ERR_INVALID, "hs_rollout_fused: predictor shape must be LSTM(7+3A -> 64) + Linear(64 -> 3F)%s");
+    KParams P = make_params(h);
+    P.action = action;
+    P.action_is_raw = action_is_raw;
+    TPParams W;
+    W.w_ih = w->weight_ih; W.w_hh = w->weight_hh; W.b_ih = w->bias_ih; W.b_hh = w->bias_hh;
+    W.fc_w = w->fc_weight; W.fc_b = w->fc_bias; W.pred_out = nullptr;
+    RolloutParams RP;
+    RP.sets = sets_device; RP.num_sets = num_sets; RP.first_set = first_set; RP.num_ticks = num_ticks;
+    RP.first_tp_prev = first_tp_prev;
+    RP.action = action; RP.action_tick_stride = action_tick_stride;
+    RP.pred_out = tp_pred_out; RP.pred_tick_stride = pred_tick_stride;
+    const size_t smem = rollout_fused_smem_bytes(c);
+    if (!h->rollout_ready) {
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->rollout_ready = true;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c.num_cylinders <= 5) hs_rollout_fused_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    else hs_rollout_fused_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    h->tp_frames += num_ticks;
     return HS_OK;
 }
 

@@ -549,8 +549,16 @@ __device__ __forceinline__ TnRowIn tn_row_load(const KParams& P, int64_t e0, int
     return R;
 }
 
-template <int A, int NTHREADS = TN_THREADS>
-__device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, int64_t e0, int nenv, const uint8_t* Hhi,
+// SYNC_ID 0: the NTHREADS threads are the whole CTA (__syncthreads); otherwise they meet at named barrier SYNC_ID (the
+// rollout kernel, where the tick warps run ahead beside them).
+template <int SYNC_ID, int NTHREADS>
+__device__ __forceinline__ void tn_sync() {
+    if (SYNC_ID == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "n"(SYNC_ID), "n"(NTHREADS) : "memory");
+}
+template <int A, int NTHREADS = TN_THREADS, int SYNC_ID = 0>
+__device__ __forceinline__ void tn_fc_rows(const KParams& P, float* state_self, float* state_drones, float* pred_out,
+                                           int64_t e0, int nenv, const uint8_t* Hhi,
                                            const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf,
                                            const TnRowIn& RI, float* rowbuf2 = nullptr) {
     const hs_config& c = P.c;
@@ -571,10 +579,10 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
             }
             const float pv = tanhf(a0);
             preds[n * F3 + og] = pv;
-            if (W.pred_out != nullptr && n < nenv) W.pred_out[(e0 + n) * F3 + og] = pv;
+            if (pred_out != nullptr && n < nenv) pred_out[(e0 + n) * F3 + og] = pv;
         }
     }
-    __syncthreads();
+    tn_sync<SYNC_ID, NTHREADS>();
     HS_TSTAMP(21);
     V3 t_rpos = mk(0.f, 0.f, 0.f);
     float* r1 = nullptr;
@@ -607,26 +615,26 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
     }
     HS_TSTAMP(22);
     const int nwords = nenv * A * D;
-    float* g1 = P.b.state_self + e0 * A * D;
-    float* g2 = P.b.state_drones + e0 * A * D;
+    float* g1 = state_self + e0 * A * D;
+    float* g2 = state_drones + e0 * A * D;
     const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
     if (rowbuf2 != nullptr && bulk && ((reinterpret_cast<uintptr_t>(rowbuf2) & 15) == 0)) {
         // both tensors in one pass: state_drones = the same rows with the unmasked target offset, built in a second tile
-        __syncthreads();
+        tn_sync<SYNC_ID, NTHREADS>();
         for (int i = tid; i < nwords; i += NTHREADS) rowbuf2[i] = rowbuf[i];
-        __syncthreads();
+        tn_sync<SYNC_ID, NTHREADS>();
         if (r1 != nullptr) { float* r2 = rowbuf2 + (r1 - rowbuf); r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z; }
         fence_async_smem();
-        __syncthreads();
+        tn_sync<SYNC_ID, NTHREADS>();
         if (tid == 0) {
             bulk_store(g1, rowbuf, (uint32_t)nwords * 4u);
             bulk_store(g2, rowbuf2, (uint32_t)nwords * 4u);
             bulk_commit();
             bulk_wait_read<0>();
         }
-        __syncthreads();
+        tn_sync<SYNC_ID, NTHREADS>();
         return;
     }
 #pragma unroll
@@ -635,17 +643,17 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, const TPParams& W, 
         if (pass == 1 && r1 != nullptr) { r1[0] = t_rpos.x; r1[1] = t_rpos.y; r1[2] = t_rpos.z; }
         if (bulk) {
             fence_async_smem();
-            __syncthreads();
+            tn_sync<SYNC_ID, NTHREADS>();
             if (tid == 0) {
                 bulk_store(gdst, rowbuf, (uint32_t)nwords * 4u);
                 bulk_commit();
                 bulk_wait_read<0>();
             }
         } else {
-            __syncthreads();
+            tn_sync<SYNC_ID, NTHREADS>();
             for (int i = tid; i < nwords; i += NTHREADS) gdst[i] = rowbuf[i];
         }
-        __syncthreads();
+        tn_sync<SYNC_ID, NTHREADS>();
     }
 }
 
@@ -782,7 +790,7 @@ hs_tp_fill_tcn_kernel(const __grid_constant__ KParams P, const __grid_constant__
             tc_fence_before();
             __syncthreads();
         }
-        tn_fc_rows<A>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, tn_row_load<A>(P, e0, nenv));
+        tn_fc_rows<A>(P, P.b.state_self, P.b.state_drones, W.pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, tn_row_load<A>(P, e0, nenv));
     }
     tc_fence_before();
     __syncthreads();
@@ -950,7 +958,7 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     } else if (warp < FUSED_TICK_WARPS) {
         // ---- phase 1a: the control tick of this tile's envs, one warp per 8 envs
         float* m = tick_mem + warp * FUSED_TICK_WORDS;
-        hs_tick_body<A, false, CT>(P, (int64_t)blockIdx.x * FUSED_TICK_WARPS + warp, m, m + TICK_STAGE_WORDS,
+        hs_tick_body<A, false, CT>(P, P.b, P.action, (int64_t)blockIdx.x * FUSED_TICK_WARPS + warp, m, m + TICK_STAGE_WORDS,
                                    m + 2 * TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX);
     } else {
         // ---- phase 1b, in the shadow of the tick: TMEM allocation (warp 4), predictor constants and weights
@@ -1049,7 +1057,7 @@ hs_tick_tp_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         }
     }
     __syncthreads();                      // all h of the last step written; the issuing warps have consumed every arrival
-    tn_fc_rows<A, NTH>(P, W, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI, reinterpret_cast<float*>(Xhi));   // x is dead
+    tn_fc_rows<A, NTH>(P, P.b.state_self, P.b.state_drones, W.pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI, reinterpret_cast<float*>(Xhi));   // x is dead
     HS_TSTAMP(20);
     tc_fence_before();
     __syncthreads();
@@ -1205,7 +1213,7 @@ hs_tp_fill_tcw_kernel(const __grid_constant__ KParams P, const __grid_constant__
             if (t < nslots) {
                 const int64_t e0 = (int64_t)(NT * grp + t) * TN_E;
                 const int nenv_t = (int)min((int64_t)TN_E, E - e0);
-                tn_fc_rows<A, TCW_THREADS>(P, W, e0, nenv_t, Hb + t * 2 * TN_H_BYTES,
+                tn_fc_rows<A, TCW_THREADS>(P, P.b.state_self, P.b.state_drones, W.pred_out, e0, nenv_t, Hb + t * 2 * TN_H_BYTES,
                                           Hb + t * 2 * TN_H_BYTES + TN_H_BYTES, fcw, fcb, preds, rowbuf, tn_row_load<A>(P, e0, nenv_t));
             }
     }

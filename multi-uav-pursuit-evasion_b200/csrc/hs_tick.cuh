@@ -36,9 +36,12 @@ __device__ __noinline__ void tp_prefetch_slow(float* tp_tile, const float* src, 
         }
     }
 }
-template <int A, bool RESET, int CT>
-__device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t warp_g, float* stage0, float* stage1,
-                                             float* tp_tile, float* stat_tile) {
+// B / action: the buffer table and the action of THIS tick (P.b / P.action for a one-tick launch; the rollout kernel
+// passes a different table every tick).  TP_IN_SMEM: tp_tile still holds the previous tick's window (rollout kernel,
+// common shape only): it is shifted in place instead of being fetched from B.tp_input_prev.
+template <int A, bool RESET, int CT, bool TP_IN_SMEM = false>
+__device__ __forceinline__ void hs_tick_body(const KParams& P, const hs_buffers& B, const float* __restrict__ action,
+                                             const int64_t warp_g, float* stage0, float* stage1, float* tp_tile, float* stat_tile) {
     const hs_config& c = P.c;
     const int lane = threadIdx.x & 31;
     const int slot = lane & (G - 1);
@@ -62,7 +65,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     const uint32_t tile_off = (uint32_t)(e >> 5) * ((uint32_t)P.R * 32u) + ((uint32_t)e & 31u);
     const uint32_t o_drone = (uint32_t)slot * Ep32 + tile_off;         // + k * (A*Ep32)
     const uint32_t o_env = (uint32_t)(ND * A) * Ep32 + tile_off;       // + k * Ep32
-    float* const arena = P.b.arena;
+    float* const arena = B.arena;
 #undef DROW
 #undef EROW
 #define DROW(k) (arena + (o_drone + (uint32_t)(k) * ((uint32_t)A * Ep32)))
@@ -77,8 +80,27 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     // ---- prefetch (no registers held): the previous TP_input rows 1..H-1 land in the warp's
     // shared tile already shifted to rows 0..H-2, and the env's stats row lands in stat_mem.
     const int per_env = H * FD, keep = (H - 1) * FD;
-    if (c.use_tp_net && !P.tp_init) {
-        const float* src = P.b.tp_input_prev + e0 * per_env;
+    if (TP_IN_SMEM && c.use_tp_net && (FD & 3) == 0) {
+        // rows 1..H-1 of the 8 windows move to rows 0..H-2 inside the tile: all loads, then all stores
+        constexpr int fd4 = FD / 4, pe4 = 10 * fd4, keep4 = 9 * fd4, NIT = (ENVS_PER_WARP * keep4 + 31) / 32;
+        float4 v[NIT];
+        float4* t4 = reinterpret_cast<float4*>(tp_tile);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = it * 32 + lane;
+            const int env = i / keep4, j = i - env * keep4;
+            if (i < ENVS_PER_WARP * keep4) v[it] = t4[env * pe4 + j + fd4];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = it * 32 + lane;
+            const int env = i / keep4, j = i - env * keep4;
+            if (i < ENVS_PER_WARP * keep4) t4[env * pe4 + j] = v[it];
+        }
+        __syncwarp();
+    } else if (c.use_tp_net && !P.tp_init) {
+        const float* src = B.tp_input_prev + e0 * per_env;
         if ((FD & 3) == 0 && H == 10 && full_tile) {
             // common shape (A=3, H=10): 8 envs x 36 float4 = 9 per lane, all indices compile-time
             constexpr int fd4 = FD / 4, pe4 = 10 * fd4, keep4 = 9 * fd4;
@@ -96,7 +118,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     }
     if (!RESET && valid && is_ev) {
 #pragma unroll
-        for (int k = 0; k < HS_NUM_STATS; ++k) cp_async4(stat_tile + (lane >> 2) * HS_NUM_STATS + k, P.b.stats + (int64_t)k * E + e);
+        for (int k = 0; k < HS_NUM_STATS; ++k) cp_async4(stat_tile + (lane >> 2) * HS_NUM_STATS + k, B.stats + (int64_t)k * E + e);
     }
     cp_async_commit();
 
@@ -127,13 +149,13 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     if (!RESET) {
         if (is_drone) {
             const int64_t row = e * A + slot;
-            act4 = __ldg(reinterpret_cast<const float4*>(P.action) + row);
+            act4 = __ldg(reinterpret_cast<const float4*>(action) + row);
             if (P.action_is_raw) {
-                prev4 = *(reinterpret_cast<const float4*>(P.b.prev_action) + row);
+                prev4 = *(reinterpret_cast<const float4*>(B.prev_action) + row);
                 pid_reset = (P.reset_pid != nullptr) && (P.reset_pid[e] != 0);
             }
         }
-        if (is_ev) v_prey = __ldg(P.b.v_prey);
+        if (is_ev) v_prey = __ldg(B.v_prey);
     }
     float cx[CT], cy[CT], cz[CT];
 #pragma unroll
@@ -163,21 +185,21 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
 #pragma unroll
                 for (int k = 0; k < 4; ++k) cmd[k] = o.cmd[k];
                 if (valid) {
-                    *(reinterpret_cast<float4*>(P.b.prev_action) + row) = o.prev_new;
-                    *(reinterpret_cast<float4*>(P.b.rotor_cmds) + row) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
-                    *(reinterpret_cast<float4*>(P.b.ctbr) + row) = o.ctbr;
-                    P.b.target_rate[row * 3 + 0] = o.trate.x;
-                    P.b.target_rate[row * 3 + 1] = o.trate.y;
-                    P.b.target_rate[row * 3 + 2] = o.trate.z;
-                    P.b.action_error[row] = action_err;
+                    *(reinterpret_cast<float4*>(B.prev_action) + row) = o.prev_new;
+                    *(reinterpret_cast<float4*>(B.rotor_cmds) + row) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
+                    *(reinterpret_cast<float4*>(B.ctbr) + row) = o.ctbr;
+                    B.target_rate[row * 3 + 0] = o.trate.x;
+                    B.target_rate[row * 3 + 1] = o.trate.y;
+                    B.target_rate[row * 3 + 2] = o.trate.z;
+                    B.action_error[row] = action_err;
                 }
             } else {
                 cmd[0] = act4.x; cmd[1] = act4.y; cmd[2] = act4.z; cmd[3] = act4.w;
-                action_err = P.b.action_error[row];
+                action_err = B.action_error[row];
             }
             // ---- rotor model, rotor_group.py:55-71
             stage_rotor(c, cmd, thr, T, yaw_torque, throttle_diff);
-            if (P.b.throttle_diff != nullptr && valid) P.b.throttle_diff[row] = throttle_diff;
+            if (B.throttle_diff != nullptr && valid) B.throttle_diff[row] = throttle_diff;
         }
         // ---- downwash all-pairs, multirotor.py:488-494, 724-753
         const float total_thrust = ((T[0] + T[1]) + T[2]) + T[3];
@@ -247,7 +269,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
             r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = q.w; r[4] = q.x; r[5] = q.y; r[6] = q.z;
             r[7] = lv.x; r[8] = lv.y; r[9] = lv.z; r[10] = av.x; r[11] = av.y; r[12] = av.z;
         }
-        st.flush(P.b.drone_state + tile_row0 * 13, nenv * A * 13, full_tile);
+        st.flush(B.drone_state + tile_row0 * 13, nenv * A * 13, full_tile);
     }
     // state_others [E,A,A-1,3] = p_a - p_j, j != a ascending; also drone-drone collisions
     float hit_drone = 0.f;
@@ -265,14 +287,14 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
                 ++o;
             }
         }
-        st.flush(P.b.state_others + tile_row0 * ((A - 1) * 3), nenv * A * (A - 1) * 3, full_tile);
+        st.flush(B.state_others + tile_row0 * ((A - 1) * 3), nenv * A * (A - 1) * 3, full_tile);
     }
     // k nearest cylinders [E,A,K,5]; lowest index wins ties
     float hit_cyl = 0.f;
     if (K > 0) {
         float* s = st.begin();
         if (is_drone) stage_knearest(c, p, cx, cy, cz, C, K, s + row_l * (K * 5), hit_cyl);
-        st.flush(P.b.obs_cylinders + tile_row0 * (K * 5), nenv * A * K * 5, full_tile);
+        st.flush(B.obs_cylinders + tile_row0 * (K * 5), nenv * A * K * 5, full_tile);
     }
     // target visibility
     const V3 t_rpos = p - tp;
@@ -307,7 +329,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
             }
         }
         {
-            float* gdst = P.b.tp_input + e0 * per_env;
+            float* gdst = B.tp_input + e0 * per_env;
             const int nwords = nenv * per_env;
             const bool bulk = HS_USE_BULK_STORE && full_tile && ((nwords & 3) == 0) &&
                               ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
@@ -321,10 +343,10 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
             }
         }
         if (valid && is_ev) {
-            P.b.tp_groundtruth[e * 3 + 0] = fdiv(tp.x, c.half_arena);
-            P.b.tp_groundtruth[e * 3 + 1] = fdiv(tp.y, c.half_arena);
-            P.b.tp_groundtruth[e * 3 + 2] = fdiv(tp.z, c.max_height) * 2.0f - 1.0f;
-            P.b.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;
+            B.tp_groundtruth[e * 3 + 0] = fdiv(tp.x, c.half_arena);
+            B.tp_groundtruth[e * 3 + 1] = fdiv(tp.y, c.half_arena);
+            B.tp_groundtruth[e * 3 + 2] = fdiv(tp.z, c.max_height) * 2.0f - 1.0f;
+            B.tp_done[e] = (progress <= (float)(c.max_episode_length - c.future_step)) ? 1 : 0;
             *EROW(E_BDETECT) = bdetect ? 1.0f : 0.0f;
         }
     } else {
@@ -332,15 +354,15 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
         const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
         float* s = st.begin();
         if (is_drone) write_self_row(s + row_l * 20, head_m, 0, nullptr, q, lv, heading, up, tfrac);
-        st.flush(P.b.state_self + tile_row0 * 20, nenv * A * 20, full_tile);
+        st.flush(B.state_self + tile_row0 * 20, nenv * A * 20, full_tile);
         s = st.begin();
         if (is_drone) write_self_row(s + row_l * 20, t_rpos, 0, nullptr, q, lv, heading, up, tfrac);
-        st.flush(P.b.state_drones + tile_row0 * 20, nenv * A * 20, full_tile);
+        st.flush(B.state_drones + tile_row0 * 20, nenv * A * 20, full_tile);
     }
 
     if (RESET) {
-        if (valid && is_ev && P.b.truncated != nullptr)
-            P.b.truncated[e] = (progress > (float)c.max_episode_length) ? 1 : 0;
+        if (valid && is_ev && B.truncated != nullptr)
+            B.truncated[e] = (progress > (float)c.max_episode_length) ? 1 : 0;
         st.finish();
         return;
     }
@@ -349,7 +371,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     float r_dist = 0.f, r_speed = 0.f, r_coll = 0.f, r_smooth = 0.f, hit_wall = 0.f;
     bool seen_capture = false;
     // device scalar when bound: follows update_epoch without re-capturing graphs (hideandseek.py:988-991)
-    const float sm_coef = (P.b.smoothness_coef != nullptr) ? __ldg(P.b.smoothness_coef) : c.smoothness_coef;
+    const float sm_coef = (B.smoothness_coef != nullptr) ? __ldg(B.smoothness_coef) : c.smoothness_coef;
     if (is_drone) {
         const RewardTerms rt = stage_reward_terms(c, p, lv, tp, blocked, hit_cyl, hit_drone, action_err, sm_coef);
         r_dist = rt.r_dist; r_speed = rt.r_speed; r_coll = rt.r_coll; r_smooth = rt.r_smooth; hit_wall = rt.hit_wall;
@@ -361,7 +383,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     const float r_detect = c.detect_reward_coef * (bdetect ? 1.0f : 0.0f);
     const float r_catch = c.catch_reward_coef * (any_capture ? 1.0f : 0.0f);
     const float reward = ((((r_dist + r_detect) + r_catch) + r_coll) + r_speed) + r_smooth;
-    if (valid && is_drone) P.b.reward[e * A + slot] = reward;
+    if (valid && is_drone) B.reward[e * A + slot] = reward;
 
     // per-env means over the A pursuers (sum in agent order, then / A like torch.mean)
     // xor-butterfly over the 4 lanes of the group; non-pursuer lanes contribute the neutral
@@ -387,8 +409,8 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const int64_t war
     et.r_catch = r_catch; et.bdetect = bdetect; et.all_blocked = all_blocked; et.any_coll = any_coll; et.out_of_arena = out_of_arena;
 
     if (valid && is_ev) {
-        P.b.done[e] = (progress >= (float)c.max_episode_length) ? 1 : 0;
-        float* S = P.b.stats + e;
+        B.done[e] = (progress >= (float)c.max_episode_length) ? 1 : 0;
+        float* S = B.stats + e;
         const int64_t Es = E;
         cp_async_wait_all();
         const float* SO = stat_tile + (lane >> 2) * HS_NUM_STATS;     // values prefetched at kernel entry
@@ -405,7 +427,7 @@ hs_tick_kernel(const __grid_constant__ KParams P) {
     __shared__ __align__(16) float stat_mem[4][TICK_STAT_WORDS];
     const int wib = threadIdx.x >> 5;
     const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    hs_tick_body<A, RESET, CT>(P, warp_g, stage_mem[wib][0], stage_mem[wib][1], tp_mem[wib], stat_mem[wib]);
+    hs_tick_body<A, RESET, CT>(P, P.b, P.action, warp_g, stage_mem[wib][0], stage_mem[wib][1], tp_mem[wib], stat_mem[wib]);
 }
 
 #undef DROW

@@ -400,6 +400,39 @@ class HsEngine:
                                 self._stream()), "hs_step_fused")
         return self.out
 
+    def rollout_fused(self, actions: torch.Tensor, num_ticks: int, weights: "_lib.hs_tp_weights", raw: bool = True,
+                      pred_out: Optional[torch.Tensor] = None) -> OutputSet:
+        """hs_rollout_fused: ``num_ticks`` control ticks (tick + predictor) in ONE kernel launch for actions that are
+        already on the device - ``actions`` [T,E,A,4], or [E,A,4] applied every tick.  Tick t writes the next output set
+        (rollout mode: the next row of the time-major storage), exactly like ``num_ticks`` calls of :meth:`step_fused`;
+        returns the set of the last tick.  ``pred_out`` [T,E,3F] optional."""
+        E, A, T = self.E, self.A, int(num_ticks)
+        per_tick = actions.dim() == 4
+        ok = actions.shape == ((T, E, A, 4) if per_tick else (E, A, 4))
+        if not ok or actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
+            raise _lib.HsError(f"actions must be a contiguous float32 [{T},{E},{A},4] or [{E},{A},4] tensor on {self.device}")
+        F3 = 3 * self.cfg.future_step
+        if pred_out is not None:
+            assert pred_out.shape == (T, E, F3) and pred_out.is_contiguous() and pred_out.dtype == torch.float32
+        n = len(self.sets) if self.storage is None else self.storage.T
+        if getattr(self, "_sets_table", None) is None or self._sets_table_src is not self._bufs:
+            raw_bytes = b"".join(bytes(self._bufs[i]) for i in range(n))
+            self._sets_table = torch.frombuffer(bytearray(raw_bytes), dtype=torch.uint8).to(self.device)
+            self._sets_table_src = self._bufs
+        first = self.next_index()
+        prev_tp = self.sets[self.cur]["tp_input"]
+        self._keep = [actions, pred_out]
+        check(lib.hs_rollout_fused(self._h, self._sets_table.data_ptr(), n, first, prev_tp.data_ptr(), actions.data_ptr(),
+                                   E * A * 4 if per_tick else 0, 1 if raw else 0, T, C.byref(weights), _ptr(pred_out), E * F3,
+                                   self._stream()), "hs_rollout_fused")
+        last = (first + T - 1) % n
+        if self.host_max_progress is not None:
+            self.host_max_progress += T
+        if self.storage is not None:
+            self._slot = last
+        self._bind(last, prev=(last - 1) % n)
+        return self.out
+
     def step_post(self, tp_pred: torch.Tensor) -> OutputSet:
         F3 = 3 * self.cfg.future_step
         tp_pred = tp_pred.reshape(self.E, F3)

@@ -419,6 +419,54 @@ def test_fused_tick_predictor_kernel_equals_two_launches(E, C, A):
         e.close()
 
 
+@pytest.mark.parametrize("E,C,T,storage", [(300, 5, 7, False), (32, 5, 3, False), (4096, 5, 12, False), (1000, 8, 5, False),
+                                           (200, 5, 6, True), (4100, 5, 9, True)])
+def test_rollout_fused_kernel_equals_per_tick_launches(E, C, T, storage):
+    """hs_rollout_fused: T ticks in ONE launch (tick warps one tick ahead of the tcgen05 predictor warps, weights staged
+    once, TP window resident in shared memory) must leave, bit for bit, what T hs_step_fused calls leave - every tick's
+    outputs (rollout storage rows), predictions, arena, stats - with per-tick and with constant actions, twice in a row,
+    ragged tiles included."""
+    import mupe_b200
+    P = O.HSParams(num_cylinders=C)
+    dev = torch.device("cuda:0")
+    cfg = hs_config_from_params(P, E)
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(P.tp_frame_dim, 3 * P.future_step, P.future_step).to(dev)
+    g = torch.Generator().manual_seed(E + T)
+    init = O.sample_reset(P, E, g)
+    kw = dict(rollout_steps=T) if storage else {}
+    one, ref = mupe_b200.HsEngine(cfg, dev, **kw), mupe_b200.HsEngine(cfg, dev, **kw)
+    for e in (one, ref):
+        e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        e.step_post_tp(e.tp_weights(tp))
+    keys = ("state_self", "state_drones", "obs_cylinders", "reward", "done", "drone_state", "tp_input", "tp_groundtruth",
+            "tp_done", "rotor_cmds", "ctbr", "target_rate", "action_error", "state_others")
+    F3 = 3 * P.future_step
+    for rep in range(2):
+        acts = torch.randn(T, E, 3, 4, generator=g).to(dev) if rep == 0 else torch.randn(E, 3, 4, generator=g).to(dev)
+        pred_one, pred_ref = torch.zeros(T, E, F3, device=dev), torch.zeros(T, E, F3, device=dev)
+        n0 = one.launches
+        out = one.rollout_fused(acts, T, one.tp_weights(tp), pred_out=pred_one)
+        assert one.launches - n0 == 1
+        for t in range(T):
+            r = ref.step_fused(acts[t] if rep == 0 else acts, ref.tp_weights(tp), pred_out=pred_ref[t])
+            if storage:                       # every tick's row of the time-major storage
+                for k in keys:
+                    assert torch.equal(one.sets[ref.cur][k], r[k]), f"rep {rep}, tick {t}: {k} differs"
+        assert one.cur == ref.cur
+        for k in keys:
+            assert torch.equal(out[k], ref.out[k]), f"rep {rep}: last tick's {k} differs"
+        assert torch.equal(pred_one, pred_ref), f"rep {rep}: predictions differ"
+        assert torch.equal(one.arena, ref.arena) and torch.equal(one.stats, ref.stats) and torch.equal(one.prev_action, ref.prev_action)
+        # and the engines keep ticking from there
+        a = torch.randn(E, 3, 4, generator=g).to(dev)
+        o1, o2 = one.step_fused(a, one.tp_weights(tp)), ref.step_fused(a, ref.tp_weights(tp))
+        for k in keys:
+            assert torch.equal(o1[k], o2[k]), f"rep {rep}, tick after the rollout: {k} differs"
+    for e in (one, ref):
+        e.close()
+
+
 def test_rotating_rollout_graph_equals_per_tick_launches():
     """RotatingRolloutGraph: one CUDA graph of 8 ticks rotating over 2 engines (4 ticks each) must leave both engines
     exactly where 4 direct hs_step_fused calls per engine leave twin engines, replay after replay."""
