@@ -34,6 +34,7 @@ sys.path.insert(0, REPO)
 
 E_PER_GPU = 4096
 ROTATE = 16
+ROLL_ROTATE = 4          # rollout-storage batches the one-kernel rollout rotates over (512 MB of outputs each)
 ROLLOUT = 64                      # ticks per rollout = per bench step (cfg/algo/mappo.yaml train_every)
 METRIC = "env-steps/sec (3v1 HideAndSeek)"
 WORKLOAD = "HideAndSeek 3 pursuers + 1 evader, 'empty' scenario (0 active cylinders, C=5), 4096 envs per GPU, use_TP_net=1"
@@ -330,19 +331,37 @@ def run_gpu_arm(args):
     # needs the host once the actions are on the device).  HS_BENCH_PER_TICK_GRAPHS=1: one graph launch per tick instead.
     from mupe_b200.engine import RotatingRolloutGraph
     per_tick = os.environ.get("HS_BENCH_PER_TICK_GRAPHS", "0") == "1"
-    rollout_graph = None if per_tick else RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT)
+    # HS_BENCH_ROLLOUT_KERNEL=1 (default): a bench step is ONE launch of hs_rollout_fused_kernel - the 64 ticks of one env
+    # batch, written into that batch's time-major rollout storage (512 MB per rollout: every tick's outputs go to HBM, and
+    # consecutive steps take different batches).  0: the round-1 form, one graph of 64 one-tick kernels.
+    one_kernel = os.environ.get("HS_BENCH_ROLLOUT_KERNEL", "1") == "1" and not per_tick
+    rollout_graph = None if (per_tick or one_kernel) else RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT)
     ret_row = 17                                              # stats["return"]
+    roll_envs, roll_engs, roll_w, roll_actions = [], [], [], None
+    if one_kernel:
+        for _ in range(ROLL_ROTATE):
+            env = make_env(mupe_b200, E, dev, **{"task.env.rollout_steps": ROLLOUT})
+            env.base_env.TP = tp_net
+            env.reset()
+            roll_envs.append(env)
+            roll_engs.append(env.base_env.engine)
+            roll_w.append(env.base_env.engine.tp_weights(tp_net))
+        roll_actions = torch.randn(ROLLOUT, E, A, 4, device=dev)        # a different action every tick
 
     def rollout(step_index, collective=True):
         """One bench step: 64 ticks + the collective of the path."""
-        if rollout_graph is not None:
+        last = engines[(ROLLOUT - 1) % ROTATE]
+        if one_kernel:
+            last = roll_engs[step_index % ROLL_ROTATE]
+            last.rollout_fused(roll_actions, ROLLOUT, roll_w[step_index % ROLL_ROTATE])
+        elif rollout_graph is not None:
             rollout_graph.replay()
         else:
             for j in range(ROLLOUT):
                 engines[j % ROTATE].replay_tick()
         if world > 1 and collective:
             # episode returns of the batch that closed the rollout, all ranks (north_star: one all_gather per rollout)
-            dist.all_gather(gather_buf, engines[(ROLLOUT - 1) % ROTATE].stats[ret_row])
+            dist.all_gather(gather_buf, last.stats[ret_row])
 
     def barrier():
         if world > 1:
@@ -369,7 +388,7 @@ def run_gpu_arm(args):
     if not timed_only:
         same_load(0.5)                      # nvidia-smi needs ~0.2 s to start; also serves as extra warm-up
     barrier()
-    launches0 = sum(e.launches for e in engines)
+    launches0 = sum(e.launches for e in engines + roll_engs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed region
@@ -381,7 +400,7 @@ def run_gpu_arm(args):
     torch.cuda.profiler.stop()
     wall = time.perf_counter() - w0
     ms = ev0.elapsed_time(ev1)
-    launches = sum(e.launches for e in engines) - launches0
+    launches = sum(e.launches for e in engines + roll_engs) - launches0
     if not timed_only:
         same_load(0.3)
     clocks = sampler.stop() if (rank == 0 and not timed_only) else None
@@ -495,7 +514,20 @@ def run_gpu_arm(args):
         tick_us = 1e3 * ms_total / ticks_timed
         one_launch = variant in (-1, 5) and E <= 32 * 148
         roof = {}
-        if one_launch:
+        if one_kernel:
+            step_us = 1e3 * ms_total / args.steps
+            ach = ab_all["total"] * E * ROLLOUT / (step_us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": "hs_rollout_fused_kernel<3,5>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": ach / peak_hbm, "traffic": ROLLOUT_TRAFFIC, "traffic_source": ROLLOUT_TRAFFIC_SRC,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E * ROLLOUT, "launch_us": step_us,
+                    "share_of_step": 1.0,
+                    "note": "3077 algorithmic B/env-tick (SURVEY 8d) x 4096 envs x 64 ticks per launch over the launch period "
+                            "measured in the timed region.  A CTA keeps its 32-env tile for the whole rollout; per tick it is a "
+                            "dependent chain - 10 LSTM steps x ~1.3 us on the tensor pipe + staging + FC/rows, with the ~8 us "
+                            "control tick of the NEXT step hidden under it on dedicated warps - not a stream: the fraction states how "
+                            "far this latency-bound launch is from the bandwidth roof; the HBM-bound regime of the tick is "
+                            "roofline.at_scale"}
+        elif one_launch:
             ach = ab_all["total"] * E / (tick_us * 1e-6) / 1e9
             roof = {"bound": "hbm", "kernel": "hs_tick_tp_fused_kernel<3,5,true>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
                     "frac": ach / peak_hbm, "traffic": 5112320,
@@ -518,8 +550,12 @@ def run_gpu_arm(args):
             "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": base_config(world),
-            "l2": f"inputs larger than L2: the ticks of a rollout rotate over {ROTATE} independent env batches per GPU",
-            "launch": ("one CUDA graph launch per 64-tick rollout (64 kernel nodes, one hs_tick_tp_fused_kernel per tick)"
+            "l2": (f"outputs larger than L2: every rollout writes its 64 ticks into 512 MB of time-major rollout storage, and consecutive "
+                   f"steps rotate over {ROLL_ROTATE} independent env batches per GPU" if one_kernel else
+                   f"inputs larger than L2: the ticks of a rollout rotate over {ROTATE} independent env batches per GPU"),
+            "launch": ("ONE kernel launch per 64-tick rollout (hs_rollout_fused: the tick of step t+1 on dedicated warps beside "
+                       "the tcgen05 predictor of step t; a different device-resident action every tick)" if one_kernel else
+                       "one CUDA graph launch per 64-tick rollout (64 kernel nodes, one hs_tick_tp_fused_kernel per tick)"
                        if rollout_graph is not None else "one CUDA graph launch per tick (64 per step)"),
             "collective": (f"all_gather of the per-env episode returns after every rollout: {args.steps} inside the timed region"
                            if world > 1 else "none (1 GPU)"),
@@ -534,7 +570,7 @@ def run_gpu_arm(args):
             line["e2e"] = e2e_c
             line["e2e_serial"] = e2e_serial
         print(json.dumps(line), file=_JSON_OUT, flush=True)
-    for env in envs:
+    for env in envs + roll_envs:
         env.close()
     if world > 1:
         dist.destroy_process_group()
@@ -579,6 +615,22 @@ def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, varia
         "frac": achieved / peak, "traffic": 4975616, "traffic_source": "profiles/r1_ncu_tick_v2.txt (4096-env launch)",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["tick"] * E, "launch_us": tick_us,
         "note": "the tick as a kernel of its own (hs_step_pre): 4096 envs = 512 warps on 148 SMs, latency bound"}
+
+    # (a0) round 1's form of the bench step, for comparison: one CUDA graph of 64 one-tick kernels rotating over the batches
+    try:
+        rg = RotatingRolloutGraph(engines, [e.tp_weights(tp_net) for e in engines], ROLLOUT)
+        rg.replay(); torch.cuda.synchronize()
+        k0.record()
+        for _ in range(4):
+            rg.replay()
+        k1.record(); torch.cuda.synchronize()
+        us = 1e3 * k0.elapsed_time(k1) / (4 * ROLLOUT)
+        extra["one_kernel_per_tick"] = {"value": E / (us * 1e-6), "unit": "env-steps/s", "us_per_tick": us,
+                                        "what": "the same 64-tick step as one CUDA graph of 64 hs_tick_tp_fused_kernel launches "
+                                                f"rotating over {ROTATE} L2-cold batches (the bench step of round 1)"}
+        del rg
+    except Exception as ex:
+        extra["one_kernel_per_tick"] = {"error": repr(ex)[:300]}
 
     # (a') the tick at a batch that fills the machine, measured live: the HBM-bound regime the roofline target refers to
     try:
@@ -692,6 +744,9 @@ def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, varia
     return extra
 
 
+ROLLOUT_TRAFFIC = 516387072     # dram read + write of one 64-tick hs_rollout_fused launch at 4096 envs (ncu)
+ROLLOUT_TRAFFIC_SRC = ("profiles/r2_ncu_rollout_fused_4k.txt: dram read 17.5 MB + write 498.9 MB per 64-tick launch (the tile's state and "
+                       "TP window never leave the SM between ticks; what reaches HBM is every tick's outputs)")
 RING_TRAFFIC_1M = 1728035512    # dram read + write of one 1 Mi-env launch in ring mode (ncu)
 RING_TRAFFIC_SRC = "profiles/r2_ncu_tick_wide_ring_v6_1M.txt (dram read 0.5707 GB + write 1.1573 GB per 1 Mi-env launch = 1648 B/env)"
 
