@@ -667,16 +667,17 @@ def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, varia
     try:
         from mupe_b200.policy import FusedPolicy, init_params
         D_self = 20 + 3 * F
+        from mupe_b200.engine import PolicyRolloutGraph
         pe = mupe_b200.HsEngine(mupe_b200.build_hs_config(E, num_agents=A, num_cylinders=C, obs_max_cylinder=K,
-                                                          future_step=F, history_step=H), dev)
+                                                          future_step=F, history_step=H), dev, rollout_steps=ROLLOUT)
         s0 = engines[0]
         pe.reset(None, s0.get_state(0), s0.get_state(1), s0.get_state(7), s0.get_state(9))
         wpe = pe.tp_weights(tp_net)
         pe.step_post_tp(wpe)
         actor = FusedPolicy(init_params(D_self, A - 1, K, 4, True, dev), A - 1, K, dev).seed(1)
         critic = FusedPolicy(init_params(D_self, A - 1, K, 1, False, dev), A - 1, K, dev)
-        pe.attach_policy(actor, critic)
-        prg = RotatingRolloutGraph([pe], [wpe], ROLLOUT)       # (actor -> critic -> tick) x 64 as ONE graph
+        pe.attach_policy(actor, critic, defer_critic=True)
+        prg = PolicyRolloutGraph(pe, wpe)          # 64 x (actor -> tick) + ONE critic launch over the 64 stored observations
         prg.replay()
         torch.cuda.synchronize()
         nrep = max(2, min(args.steps, 8))
@@ -688,10 +689,11 @@ def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, varia
         pol_us = 1e3 * k0.elapsed_time(k1) / (nrep * ROLLOUT)
         extra["rollout_step_with_policy"] = {
             "value": E / (pol_us * 1e-6), "unit": "env-steps/s", "us_per_step": pol_us,
-            "launches_per_step": 1 + getattr(prg, "policy_kernels", 2),
-            "what": "one CUDA graph per 64-step rollout, per step: fused actor (+ critic) policy kernel(s) on tcgen05 (3xTF32, in-kernel "
-                    "noise) + hs_tick_tp_fused_kernel (tick + predictor); the observation never leaves HBM; same 4096-env batch "
-                    "every step (L2-warm), single GPU"}
+            "launches_per_rollout": 2 * ROLLOUT + 1,
+            "what": "one CUDA graph per 64-step rollout into time-major rollout storage: per step the fused actor kernel on tcgen05 "
+                    "(3xTF32, in-kernel noise) + hs_tick_tp_fused_kernel (tick + predictor); the critic ONCE per rollout over the "
+                    "64 x 4096 x 3 stored observations (it has no state: the values the reference's per-step value_op computes, "
+                    "mappo.py:235-251, at the cost of one large launch); the observation never leaves HBM; single GPU"}
         pe.close()
     except Exception as ex:
         extra["rollout_step_with_policy"] = {"error": repr(ex)[:300]}

@@ -236,7 +236,7 @@ class HsEngine:
         self._bind(i)
 
     # ------------------------------------------------------------------ policy next to the tick
-    def attach_policy(self, actor, critic=None, deterministic: bool = False):
+    def attach_policy(self, actor, critic=None, deterministic: bool = False, defer_critic: bool = False):
         """Makes ``actor`` (a :class:`~mupe_b200.policy.FusedPolicy`) - and optionally ``critic`` - part of the tick:
         :meth:`policy_tick` and the graphs captured afterwards run actor -> critic -> hs_step_pre -> hs_step_post_tp
         on the observation the previous tick produced, i.e. one whole rollout step (``policy(td)`` + ``env.step(td)``
@@ -248,6 +248,11 @@ class HsEngine:
         E, A, dev = self.E, self.A, self.device
         self._actor, self._critic, self._deterministic = actor, critic, bool(deterministic)
         self.parallel_critic = True         # graphs: critic as a parallel branch beside actor -> tick
+        # defer_critic (rollout mode): the per-step launches leave the critic out; :class:`PolicyRolloutGraph` evaluates
+        # it ONCE per rollout over the T stored observations (the critic has no state: same values, one large launch)
+        self._defer_critic = bool(defer_critic) and critic is not None
+        if self._defer_critic and self.storage is None:
+            raise _lib.HsError("attach_policy(defer_critic=True) needs rollout mode (rollout_steps=T)")
         if not deterministic and getattr(actor, "rng_state", None) is None:
             actor.seed(0)
         if self.storage is not None:
@@ -266,6 +271,10 @@ class HsEngine:
         obs, po = self.sets[prev], self.policy_out[i]
         others = obs["state_others"] if self.A > 1 else None
         joined = None
+        if getattr(self, "_defer_critic", False):
+            self._actor.forward(obs["state_self"], others, obs["obs_cylinders"], sample=not self._deterministic,
+                                out={"head": po["action_mean"], "action": po["action"], "logp": po["logp"]})
+            return None
         if self._critic is not None and fork:
             cur = torch.cuda.current_stream(self.device)
             if getattr(self, "_critic_stream", None) is None:
@@ -699,6 +708,68 @@ class RotatingRolloutGraph:
         for e, k in zip(self.engines, self.kernels):
             # (cur is unchanged: every engine advanced by a multiple of its set count)
             e._uncounted = getattr(e, "_uncounted", 0) + k + getattr(self, "policy_kernels", 0) * self.per_engine
+
+
+class PolicyRolloutGraph:
+    """ONE CUDA graph = one whole rollout of a rollout-mode engine with an attached policy
+    (``attach_policy(actor, critic, defer_critic=True)``): T x (actor on the latest observation -> tick + predictor into
+    row t of the time-major storage), then the critic ONCE over the T stored observations.  The reference's collector
+    evaluates the critic every step (``MAPPOPolicy.__call__`` -> ``value_op``, mappo.py:235-251); it has no state, so one
+    launch over T x E x A rows gives the same values at a fraction of the cost of T small launches.
+    After :meth:`replay`: ``storage.policy["state_value"][t]`` = V(observation step t started from) and
+    ``next_state_value[t]`` = V(observation step t produced) - the two inputs of ``compute_gae``."""
+
+    def __init__(self, engine, tp_weights, raw: bool = True):
+        e = engine
+        if e.storage is None or getattr(e, "_actor", None) is None or not getattr(e, "_defer_critic", False):
+            raise _lib.HsError("PolicyRolloutGraph needs rollout mode and attach_policy(actor, critic, defer_critic=True)")
+        T, dev = e.storage.T, e.device
+        self.engine, self.T = e, T
+        obs_keys = ("state_self", "state_others", "obs_cylinders")
+        if any(not e.storage.data[k][:T].is_contiguous() for k in obs_keys if not (k == "state_others" and e.A == 1)):
+            raise _lib.HsError("PolicyRolloutGraph: the rollout rows of the observation are padded (num_envs x row width not a multiple of 32 words)")
+        self.next_state_value = torch.zeros(T, e.E, e.A, 1, dtype=torch.float32, device=dev)
+        if getattr(e, "graph_reset_pid", None) is None:
+            e.graph_reset_pid = torch.zeros(e.E, dtype=torch.uint8, device=dev)
+        # steady state: the latest observation sits in row T-1 (a first rollout is run eagerly to get there)
+        while e._slot != T - 1:
+            e.policy_tick(tp_weights)
+        self._critic_rows(T - 1, T)                              # carry for the first replay
+        sv = e.storage.policy["state_value"]
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self._keep = tp_weights
+        n0 = int(lib.hs_launch_count(e._h))
+        with torch.cuda.graph(self.graph, stream=side):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            sv[0].copy_(self.next_state_value[T - 1])           # value of the observation step 0 starts from
+            for t in range(T):
+                prev, i = e.cur, e.next_index()
+                e._launch_policy(prev, i)
+                e._bind(i, prev)
+                e._slot = i
+                check(lib.hs_step_fused(e._h, e.policy_out[i]["action"].data_ptr(), 1 if raw else 0,
+                                        e.graph_reset_pid.data_ptr(), C.byref(tp_weights), None, st), "hs_step_fused (capture)")
+            self._critic_rows(0, T)
+            sv[1:T].copy_(self.next_state_value[:T - 1])
+        self.kernels = int(lib.hs_launch_count(e._h)) - n0
+        e._uncounted = getattr(e, "_uncounted", 0) - self.kernels
+        self.policy_kernels_per_rollout = T + 1
+        self.replays = 0
+
+    def _critic_rows(self, a: int, b: int):
+        e, d = self.engine, self.engine.storage.data
+        others = d["state_others"][a:b] if e.A > 1 else None
+        e._critic.forward(d["state_self"][a:b], others, d["obs_cylinders"][a:b], out={"head": self.next_state_value[a:b]})
+
+    def replay(self):
+        e = self.engine
+        self.graph.replay()
+        self.replays += 1
+        if e.host_max_progress is not None:
+            e.host_max_progress += self.T
+        e._uncounted = getattr(e, "_uncounted", 0) + self.kernels + self.policy_kernels_per_rollout
 
 
 class HostIoLoop:

@@ -305,3 +305,58 @@ def test_gpu_policy_full_size_properties(built_lib, impl):
     other = net(s, o, c, eps=eps, impl=3 - impl, out={})
     torch.testing.assert_close(other["action"], base["action"], rtol=1e-4, atol=2e-6)
     torch.testing.assert_close(other["head"], base["head"], rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_policy_rollout_graph_with_deferred_critic(built_lib):
+    """PolicyRolloutGraph: T x (actor -> tick) plus ONE critic launch over the T stored observations, as one CUDA graph,
+    gives the rollout a twin engine produces with actor + critic launched every step: same actions / observations bit
+    for bit, the same state values (the critic has no state; batch size may switch its kernel variant: 1e-5), and
+    next_state_value = the values GAE bootstraps from."""
+    import mupe_b200
+    from mupe_b200.engine import PolicyRolloutGraph
+    dev = torch.device("cuda:0")
+    E, T = 64, 6
+    p, _, _ = _load("actor_tp")
+    pc, _, _ = _load("critic_tp")
+    torch.manual_seed(0)
+    tp = mupe_b200.TP_net(16, 15, 5).to(dev)
+    g = torch.Generator().manual_seed(5)
+    init = dict(drone_pos=torch.rand(E, 3, 3, generator=g) * 0.4 + torch.tensor([0.1, -0.2, 0.5]),
+                drone_rot=torch.tensor([1.0, 0, 0, 0]).expand(E, 3, 4).contiguous(),
+                target_pos=torch.rand(E, 3, generator=g) * 0.4 + torch.tensor([-0.5, -0.2, 0.5]),
+                cyl_pos=torch.cat([torch.rand(E, 5, 2, generator=g) - 0.5, torch.full((E, 5, 1), 0.6)], -1))
+    engs = []
+    for defer in (True, False):
+        eng = mupe_b200.HsEngine(mupe_b200.build_hs_config(E), dev, rollout_steps=T)
+        actor = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in p.items()}, 2, 3, dev).seed(7)
+        critic = mupe_b200.FusedPolicy({k: v.to(dev).contiguous() for k, v in pc.items()}, 2, 3, dev)
+        eng.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
+        eng.step_post_tp(eng.tp_weights(tp))
+        eng.attach_policy(actor, critic, defer_critic=defer)
+        engs.append(eng)
+    one, ref = engs
+    w_ref = ref.tp_weights(tp)
+    prg = PolicyRolloutGraph(one, one.tp_weights(tp))            # runs a first rollout eagerly (steady state), then captures
+    for _ in range(T):
+        ref.policy_tick(w_ref)
+    for rep in range(2):
+        prg.replay()
+        obs0 = {k: ref.sets[ref.cur][k].clone() for k in ("state_self", "state_others", "obs_cylinders")}
+        for _ in range(T):
+            ref.policy_tick(w_ref)
+        torch.cuda.synchronize()
+        for k in ("state_self", "reward", "tp_input", "drone_state", "done"):
+            assert torch.equal(one.storage.data[k][:T], ref.storage.data[k][:T]), (rep, k)
+        for k in ("action", "logp", "action_mean"):
+            assert torch.equal(one.storage.policy[k][:T], ref.storage.policy[k][:T]), (rep, k)
+        torch.testing.assert_close(one.storage.policy["state_value"][:T], ref.storage.policy["state_value"][:T], rtol=1e-5, atol=1e-6)
+        assert one.storage.policy["state_value"][:T].abs().sum() > 0
+        # next_state_value[t] = V(observation produced by step t) = state_value[t + 1]; the last one bootstraps GAE
+        torch.testing.assert_close(prg.next_state_value[:T - 1], ref.storage.policy["state_value"][1:T], rtol=1e-5, atol=1e-6)
+        last = ref.sets[ref.cur]
+        want = ref._critic.forward(last["state_self"], last["state_others"], last["obs_cylinders"])["head"]
+        torch.testing.assert_close(prg.next_state_value[T - 1], want, rtol=1e-5, atol=1e-6)
+        assert one.cur == ref.cur
+    for e in engs:
+        e.close()
