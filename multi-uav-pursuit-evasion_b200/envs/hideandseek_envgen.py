@@ -320,6 +320,10 @@ class HideAndSeek_envgen(HideAndSeek):
         if tensordict is not None and "_reset" in tensordict and not bool(tensordict.get("_reset").all()):
             raise RuntimeError("HideAndSeek_envgen resets all envs together (hideandseek_envgen.py:896-898)")
         self._host_progress = 0
+        # `self.stats[env_ids] = 0.` (hideandseek_envgen.py:997) also clears the generator's stats: add_history and the
+        # per-cylinder-count ratios are non-zero only from the update tick to the next reset
+        for k in self._stat_keys()[len(STAT_KEYS):]:
+            self.stats[k].zero_()
         return super()._reset(None if tensordict is None else tensordict.exclude("_reset"), init=init, **kwargs)
 
     # ------------------------------------------------------------------ step

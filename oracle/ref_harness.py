@@ -201,8 +201,35 @@ def load_reference():
     tp_ns = dict(torch=torch, nn=torch.nn)
     exec(compile(ast.Module(body=[node], type_ignores=[]), "<ref:TP_net>", "exec"), tp_ns)
     _LOADED.update(ut=ut, rg=rg, lc=lc, env=env_m, drone=drone_m, transform=tr, isaac=ie, hover=hover_m,
-                   TP_net=tp_ns["TP_net"], ns=ns)
+                   TP_net=tp_ns["TP_net"], ns=ns, extract=extract)
     return _LOADED
+
+
+def load_envgen():
+    """HideAndSeek_envgen's own source (omni_drones/envs/hide_and_seek/hideandseek_envgen.py): the env methods, the free
+    function `sanity_check` and the `GenBuffer` class.  `dgl.geometry.farthest_point_sampler` (dgl is not in this image) is
+    replaced by the numpy restatement of farthest point sampling in oracle/envgen_oracle.py with start index 0 (dgl draws a
+    random start): the archive bookkeeping around it is the reference's."""
+    R = load_reference()
+    if "envgen" in R:
+        return R
+    import copy as _copy
+    from . import envgen_oracle as EO
+    eg = "omni_drones/envs/hide_and_seek/hideandseek_envgen.py"
+    ns, extract = R["ns"], R["extract"]
+
+    def farthest_point_sampler(points, npoints, start_idx=None):
+        pts = points[0].numpy() if isinstance(points, torch.Tensor) else np.asarray(points)[0]
+        return torch.from_numpy(EO.fps(pts.astype(np.float32), int(npoints), start=0).astype(np.int64)).unsqueeze(0)
+    ns.update(copy=_copy, deque=collections.deque, farthest_point_sampler=farthest_point_sampler)
+    ns.update(extract(eg, ["sanity_check"]))
+    tree = ast.parse((REF / eg).read_text())
+    node = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "GenBuffer")
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "<ref:GenBuffer>", "exec"), ns)
+    env_m = extract(eg, ["_pre_sim_step", "_compute_state_and_obs", "_compute_reward_and_done", "_get_dummy_policy_prey",
+                         "_reset_idx", "uniform_sampling", "rejection_sampling_random_cylinder"], cls="HideAndSeek_envgen")
+    R.update(envgen=env_m, GenBuffer=ns["GenBuffer"])
+    return R
 
 
 # ----------------------------------------------------------------------------
@@ -449,6 +476,44 @@ class RefEnv:
                    action_error=td[("stats", "action_error_order1")].clone())
         out = e._step(td)
         return out["next"], aux
+
+
+class RefEnvgen(RefEnv):
+    """The reference's HideAndSeek_envgen driven from its own source: reset with the particle generator
+    (hideandseek_envgen.py:875-1013 - uniform / archive split, GenBuffer.samplenearby, insert), the tick, and
+    `_compute_reward_and_done` with the archive bookkeeping of an episode end (:1241-1333).  Only PhysX is ours."""
+
+    EXTRA = ("success_buffer", "success_unif", "history_buffer", "add_history", "ratio_unif")
+
+    def __init__(self, P: O.HSParams, E: int, eval_iter=2, ratio_unif=0.3, R_min=0.5, R_max=0.9, success_threshold=0.98,
+                 expand_cylinders=True, expand_step=0.05, buffer_length=5000, min_cylinders=4, tp_state_dict=None):
+        super().__init__(P, E, use_random_cylinder=True, scenario_flag="empty", min_cylinders=min_cylinders,
+                         tp_state_dict=tp_state_dict)
+        R = load_envgen()
+        e = self.env
+        e.smoothness_coef = P.smoothness_coef
+        e.use_particle_generator, e.update_iter, e.eval_iter = True, 0, eval_iter
+        e.ratio_unif, e.R_min, e.R_max, e.success_threshold = ratio_unif, R_min, R_max, success_threshold
+        e.expand_cylinders, e.expand_step = expand_cylinders, expand_step
+        e.num_unif = E
+        e.gen_buffer = R["GenBuffer"](P.num_agents, P.num_cylinders, e.device)
+        e.gen_buffer.buffer_length = buffer_length
+        # GenBuffer.insert_weights keeps `weights.to('cpu').numpy()`: on the reference's CUDA device that is a copy; on this
+        # CPU harness it would alias stats["success"], which the next reset zeroes in place - hand it a copy as CUDA does
+        _iw = e.gen_buffer.insert_weights
+        e.gen_buffer.insert_weights = lambda w: _iw(w.clone())
+        keys = [k for k in O.STAT_KEYS if k != "smoothness_coef"] + list(self.EXTRA)
+        for i in range(P.num_cylinders + 1):
+            keys += [f"ratio_cylinders_{i}", f"success_cylinders_{i}"]
+        self.stat_keys = keys
+        e.stats = TD({k: torch.zeros(E, 1) for k in keys}, [E])
+        for name, fn in R["envgen"].items():
+            setattr(e, name, types.MethodType(fn, e))
+
+    def reset_all(self):
+        """IsaacEnv._reset of every env with the reference's own sampling (torch / numpy global RNG state)."""
+        self.td = self.env._reset(TD({"_reset": torch.ones(self.E, dtype=torch.bool)}, [self.E]))
+        return self.td
 
 
 class RefHover:
