@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libhs_b200.so")
+# HS_B200_LIB: an instrumented build for the tools/ phase timers (never set in tests, smoke or bench)
+LIB_PATH = os.environ.get("HS_B200_LIB") or os.path.join(PKG_DIR, "libhs_b200.so")
 
 HS_ABI_VERSION = 3
 HS_NUM_STATS = 24

@@ -37,12 +37,14 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    if out is None and not force and not needs_build():
         return LIB
+    lib_out = out or LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     inc = ["-I", os.path.join(REPO, "include")]
-    objs = [os.path.join(OBJ_DIR, "hs_kernels.o"), os.path.join(OBJ_DIR, "hs_tick_exact.o")]
+    tag = "" if out is None else "_" + os.path.splitext(os.path.basename(out))[0]
+    objs = [os.path.join(OBJ_DIR, f"hs_kernels{tag}.o"), os.path.join(OBJ_DIR, f"hs_tick_exact{tag}.o")]
     cmds = [[nvcc_path(), *NVCC_FLAGS, *extra_flags, *inc, "-c", "-o", objs[0], SRC],
             [nvcc_path(), *NVCC_FLAGS, *EXACT_FLAGS, *extra_flags, *inc, "-c", "-o", objs[1], SRC_EXACT]]
     if verbose:
@@ -54,15 +56,16 @@ def build(force=False, verbose=False, extra_flags=()):
     outs = [p.communicate()[0] for p in procs]
     if any(p.returncode != 0 for p in procs):
         raise RuntimeError("nvcc failed:\n" + "\n".join(outs))
-    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs]
+    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", lib_out, *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     if verbose:
         print("\n".join(outs) + r.stdout + r.stderr)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
     defs = [f"-D{sys.argv[i + 1]}" for i, a in enumerate(sys.argv[:-1]) if a == "--define"]     # debug builds (tools/)
-    print(build(force="--force" in sys.argv, verbose=True, extra_flags=defs))
+    out = next((sys.argv[i + 1] for i, a in enumerate(sys.argv[:-1]) if a == "--out"), None)        # e.g. a timing build for tools/
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=defs, out=out))

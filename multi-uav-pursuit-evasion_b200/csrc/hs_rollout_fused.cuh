@@ -81,13 +81,16 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         }
         for (int t = 0; t < T; ++t) {
             // sB[t & 1] was last read by the predictor warps for tick t-2, which ended before they released the tile of t-1
+            if (t == 8) HS_TSTAMP_AT(10, NTH);
             if (t > 0) asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
+            if (t == 8) HS_TSTAMP_AT(11, NTH);
             load_table(t, ttid, 32 * FUSED_TICK_WARPS);
             asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TICKW), "n"(32 * FUSED_TICK_WARPS) : "memory");
             const float* act = RP.action + (int64_t)t * RP.action_tick_stride;
             hs_tick_body<A, false, CT, true>(P, sB[t & 1], act, warp_g, m, m + TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS,
                                              m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX);
             __threadfence_block();
+            if (t == 8) HS_TSTAMP_AT(12, NTH);
             asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TICK_DONE), "n"(RF_THREADS) : "memory");
         }
         return;
@@ -137,7 +140,10 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     const int nenv = (int)min((int64_t)TN_E, E - e0);
 
     for (int t = 0; t < T; ++t) {
+        if (t == 8) HS_TSTAMP_AT(0, 0);
+        if (t == 9) HS_TSTAMP_AT(6, 0);
         asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TICK_DONE), "n"(RF_THREADS) : "memory");   // tick t is complete
+        if (t == 8) HS_TSTAMP_AT(1, 0);
         const TnRowIn RI = tn_row_load<A>(P, e0, nenv);          // new state of the tile (written by the tick warps)
         tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
         float* const state_self = sB[t & 1].state_self;
@@ -147,6 +153,7 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         __threadfence_block();
         if (t + 1 < T) asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
         tn_sync<RF_BAR_MAIN, NTH>();
+        if (t == 8) HS_TSTAMP_AT(2, 0);
         // ---- the recurrence (hs_tick_tp_fused_kernel): two 16-env halves ping-pong between tensor pipe and epilogue
         if (issuer) {
             if (elect_one()) {
@@ -192,11 +199,13 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
             }
         }
         tn_sync<RF_BAR_MAIN, NTH>();          // all h of the last step written; the issuing warps have consumed every arrival
+        if (t == 8) HS_TSTAMP_AT(3, 0);
         float* pred_out = (RP.pred_out != nullptr) ? RP.pred_out + (int64_t)t * RP.pred_tick_stride : nullptr;
         tn_fc_rows<A, NTH, RF_BAR_MAIN>(P, state_self, state_drones, pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI,
                                         reinterpret_cast<float*>(Xhi));   // x is dead
         tc_fence_before();
         tn_sync<RF_BAR_MAIN, NTH>();
+        if (t == 8) HS_TSTAMP_AT(4, 0);
     }
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
