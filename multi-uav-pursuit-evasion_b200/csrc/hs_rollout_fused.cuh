@@ -23,6 +23,28 @@ constexpr int RF_MAIN_THREADS = TCW_THREADS;                    // 576: 16 epilo
 constexpr int RF_THREADS = RF_MAIN_THREADS + 32 * FUSED_TICK_WARPS;   // + 4 tick warps = 704
 constexpr int RF_BAR_MAIN = 1, RF_BAR_TICK_DONE = 2, RF_BAR_TILE_FREE = 3, RF_BAR_TICKW = 4;
 
+// New TP frame of a tick warp's 8 envs -> one step slot of the predictor's B operand (tf32 hi / lo, the layout of
+// tn_stage_x_smem: lane = (env & 7) + 8 * (k & 3) per core matrix), so that the predictor warps do not restage the window.
+struct XRingHook {
+    static constexpr bool ACTIVE = true;
+    uint8_t *xhi, *xlo;              // slot base + (tick warp) * TN_SBO; nullptr: leave the staging to the predictor warps
+    int nenv_w;                      // valid envs of this warp
+    template <int FD> __device__ __forceinline__ void frame(const float* tile, int per_env, int keep, int lane) const {
+        if (xhi == nullptr) return;
+        const int rr = lane & 7, kk = lane >> 3;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            const int k = kc * 4 + kk;
+            const float xv = (rr < nenv_w && k < FD) ? tile[rr * per_env + keep + k] : 0.0f;
+            uint32_t hi, lo;
+            tf32_split(xv, hi, lo);
+            const uint32_t off = kc * TN_X_LBO + rr * 16 + kk * 4;
+            *reinterpret_cast<uint32_t*>(xhi + off) = hi;
+            *reinterpret_cast<uint32_t*>(xlo + off) = lo;
+        }
+    }
+};
+
 struct RolloutParams {
     const hs_buffers* sets;          // device memory: [num_sets] buffer tables
     int num_sets, first_set, num_ticks;
@@ -87,8 +109,15 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
             load_table(t, ttid, 32 * FUSED_TICK_WARPS);
             asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TICKW), "n"(32 * FUSED_TICK_WARPS) : "memory");
             const float* act = RP.action + (int64_t)t * RP.action_tick_stride;
-            hs_tick_body<A, false, CT, true>(P, sB[t & 1], act, warp_g, m, m + TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS,
-                                             m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX);
+            // from the second tick on the new frame goes straight into the operand ring: slot (t-1) % H held the oldest
+            // frame of the previous window (the predictor warps release the tile only after the MMAs that read it)
+            XRingHook hook;
+            hook.nenv_w = (int)max((int64_t)0, min((int64_t)ENVS_PER_WARP, E - warp_g * ENVS_PER_WARP));
+            hook.xhi = (t > 0) ? Xhi + (size_t)((t - 1) % H) * TN_X_STEP + (size_t)tw * TN_SBO : nullptr;
+            hook.xlo = (t > 0) ? Xlo + (size_t)((t - 1) % H) * TN_X_STEP + (size_t)tw * TN_SBO : nullptr;
+            hs_tick_body<A, false, CT, true, XRingHook>(P, sB[t & 1], act, warp_g, m, m + TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS,
+                                                        m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX, hook);
+            fence_async_smem();                          // operand ring: generic-proxy stores -> the MMAs' async proxy
             __threadfence_block();
             if (t == 8) HS_TSTAMP_AT(12, NTH);
             asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TICK_DONE), "n"(RF_THREADS) : "memory");
@@ -145,13 +174,19 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TICK_DONE), "n"(RF_THREADS) : "memory");   // tick t is complete
         if (t == 8) HS_TSTAMP_AT(1, 0);
         const TnRowIn RI = tn_row_load<A>(P, e0, nenv);          // new state of the tile (written by the tick warps)
-        tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
+        // step s of this tick's window sits in operand slot (head + s) % H: tick 0 stages the whole window, afterwards the
+        // tick warps replace the oldest slot by the new frame
+        const int head = t % H;
+        if (t == 0) tn_stage_x_smem<FD, NTH>(tick_mem, nenv, H, Xhi, Xlo);
         float* const state_self = sB[t & 1].state_self;
         float* const state_drones = sB[t & 1].state_drones;
         fence_async_smem();
         tc_fence_before();
         __threadfence_block();
-        if (t + 1 < T) asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
+        // "tile free" (the tick warps may start tick t+1): they overwrite the arena rows loaded above, the TP tile and the
+        // operand slot of this window's OLDEST frame - the epilogue warps therefore arrive only once the step-0 MMAs of both
+        // halves have completed (below); the issuing warps have nothing to protect
+        if (issuer && t + 1 < T) asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
         tn_sync<RF_BAR_MAIN, NTH>();
         if (t == 8) HS_TSTAMP_AT(2, 0);
         // ---- the recurrence (hs_tick_tp_fused_kernel): two 16-env halves ping-pong between tensor pipe and epilogue
@@ -159,7 +194,8 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
             if (elect_one()) {
                 tc_fence_after();
                 auto xdesc = [&](int hf, int s, bool lo) {
-                    return tc_desc(smem_u32(lo ? Xlo : Xhi) + (uint32_t)s * TN_X_STEP + (uint32_t)hf * 2u * TN_SBO, TN_X_LBO, TN_SBO);
+                    const int sl = (head + s >= H) ? head + s - H : head + s;
+                    return tc_desc(smem_u32(lo ? Xlo : Xhi) + (uint32_t)sl * TN_X_STEP + (uint32_t)hf * 2u * TN_SBO, TN_X_LBO, TN_SBO);
                 };
                 auto hdesc = [&](int hf, bool lo) { return tc_desc(smem_u32(lo ? Hlo : Hhi) + (uint32_t)hf * 2u * TN_SBO, TN_H_LBO, TN_SBO); };
                 for (int hf = 0; hf < 2; ++hf) {
@@ -195,6 +231,9 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(h_ready + 8u * (uint32_t)hf);
+                    __syncwarp();
+                    if (s == 0 && hf == 1 && t + 1 < T)      // both halves' step-0 MMAs are complete: release the tile
+                        asm volatile("bar.arrive %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
                 }
             }
         }
@@ -202,7 +241,7 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         if (t == 8) HS_TSTAMP_AT(3, 0);
         float* pred_out = (RP.pred_out != nullptr) ? RP.pred_out + (int64_t)t * RP.pred_tick_stride : nullptr;
         tn_fc_rows<A, NTH, RF_BAR_MAIN>(P, state_self, state_drones, pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI,
-                                        reinterpret_cast<float*>(Xhi));   // x is dead
+                                        wst);   // second row tile: the weight staging tile is dead after the prologue
         tc_fence_before();
         tn_sync<RF_BAR_MAIN, NTH>();
         if (t == 8) HS_TSTAMP_AT(4, 0);

@@ -39,9 +39,16 @@ __device__ __noinline__ void tp_prefetch_slow(float* tp_tile, const float* src, 
 // B / action: the buffer table and the action of THIS tick (P.b / P.action for a one-tick launch; the rollout kernel
 // passes a different table every tick).  TP_IN_SMEM: tp_tile still holds the previous tick's window (rollout kernel,
 // common shape only): it is shifted in place instead of being fetched from B.tp_input_prev.
-template <int A, bool RESET, int CT, bool TP_IN_SMEM = false>
+// Hook: called by the whole warp once the new TP frame of its 8 envs is complete in the shared tile (the rollout kernel
+// writes it straight into the predictor's MMA operand ring).
+struct NoFrameHook {
+    static constexpr bool ACTIVE = false;
+    template <int FD> __device__ __forceinline__ void frame(const float*, int, int, int) const {}
+};
+template <int A, bool RESET, int CT, bool TP_IN_SMEM = false, class Hook = NoFrameHook>
 __device__ __forceinline__ void hs_tick_body(const KParams& P, const hs_buffers& B, const float* __restrict__ action,
-                                             const int64_t warp_g, float* stage0, float* stage1, float* tp_tile, float* stat_tile) {
+                                             const int64_t warp_g, float* stage0, float* stage1, float* tp_tile, float* stat_tile,
+                                             const Hook hook = Hook()) {
     const hs_config& c = P.c;
     const int lane = threadIdx.x & 31;
     const int slot = lane & (G - 1);
@@ -327,6 +334,10 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const hs_buffers&
                 while (k >= FD) k -= FD;
                 row0[i] = fr[k];
             }
+        }
+        if (Hook::ACTIVE) {
+            __syncwarp();
+            hook.template frame<FD>(tp_tile, per_env, keep, lane);
         }
         {
             float* gdst = B.tp_input + e0 * per_env;
