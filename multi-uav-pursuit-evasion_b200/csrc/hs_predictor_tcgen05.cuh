@@ -559,7 +559,9 @@ __device__ __forceinline__ void tn_sync() {
     if (SYNC_ID == 0) __syncthreads();
     else asm volatile("bar.sync %0, %1;" :: "n"(SYNC_ID), "n"(NTHREADS) : "memory");
 }
-template <int A, int NTHREADS = TN_THREADS, int SYNC_ID = 0>
+// DEFER (rollout kernel): the bulk stores of the two row tiles are left in flight - the wait for their shared-memory reads
+// moves to the next call (before the tiles are rewritten) and, after the last tick, to the caller.
+template <int A, int NTHREADS = TN_THREADS, int SYNC_ID = 0, bool DEFER = false>
 __device__ __forceinline__ void tn_fc_rows(const KParams& P, float* state_self, float* state_drones, float* pred_out,
                                            int64_t e0, int nenv, const uint8_t* Hhi,
                                            const uint8_t* Hlo, const float* fcw, const float* fcb, float* preds, float* rowbuf,
@@ -585,8 +587,17 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, float* state_self, 
             if (pred_out != nullptr && n < nenv) pred_out[(e0 + n) * F3 + og] = pv;
         }
     }
+    if (DEFER && tid == 0) bulk_wait_read<0>();               // the previous call's row tiles have left shared memory
     tn_sync<SYNC_ID, NTHREADS>();
     HS_TSTAMP(21);
+    const int nwords = nenv * A * D;
+    float* g1 = state_self + e0 * A * D;
+    float* g2 = state_drones + e0 * A * D;
+    const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
+    // both tensors in one pass: state_drones = the same rows with the unmasked target offset, built in a second tile
+    const bool both = rowbuf2 != nullptr && bulk && ((reinterpret_cast<uintptr_t>(rowbuf2) & 15) == 0);
     V3 t_rpos = mk(0.f, 0.f, 0.f);
     float* r1 = nullptr;
     if (tid < TN_E * A) {
@@ -602,42 +613,35 @@ __device__ __forceinline__ void tn_fc_rows(const KParams& P, float* state_self, 
         const float mv = c.mask_value;
         const V3 head_m = bdetect ? t_rpos : mk(mv, mv, mv);
         r1 = rowbuf + (el * A + slot) * D;
+        float* r2 = both ? rowbuf2 + (el * A + slot) * D : r1;           // (!both: every store below lands in r1 twice)
         r1[0] = head_m.x; r1[1] = head_m.y; r1[2] = head_m.z;
+        if (both) { r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z; }
         const float* pr = preds + el * F3;
         for (int f = 0; f < c.future_step; ++f) {
             const float px = (pr[3 * f] * 0.5f) * c.arena_size;
             const float py = (pr[3 * f + 1] * 0.5f) * c.arena_size;
             const float pz = ((pr[3 * f + 2] + 1.0f) * 0.5f) * c.max_height;
-            r1[3 + 3 * f] = p.x - px; r1[4 + 3 * f] = p.y - py; r1[5 + 3 * f] = p.z - pz;
+            const float dx = p.x - px, dy = p.y - py, dz = p.z - pz;
+            r1[3 + 3 * f] = dx; r1[4 + 3 * f] = dy; r1[5 + 3 * f] = dz;
+            r2[3 + 3 * f] = dx; r2[4 + 3 * f] = dy; r2[5 + 3 * f] = dz;
         }
         const int o = 3 + F3;
         const float tail[17] = {q.w, q.x, q.y, q.z, lv.x, lv.y, lv.z, heading.x, heading.y, heading.z,
                                 up.x, up.y, up.z, tfrac, tfrac, tfrac, tfrac};
 #pragma unroll
-        for (int i = 0; i < 17; ++i) r1[o + i] = tail[i];
+        for (int i = 0; i < 17; ++i) { r1[o + i] = tail[i]; r2[o + i] = tail[i]; }
     }
     HS_TSTAMP(22);
-    const int nwords = nenv * A * D;
-    float* g1 = state_self + e0 * A * D;
-    float* g2 = state_drones + e0 * A * D;
-    const bool bulk = HS_USE_BULK_STORE && (nenv == TN_E) && ((nwords & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g2) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(rowbuf) & 15) == 0);
-    if (rowbuf2 != nullptr && bulk && ((reinterpret_cast<uintptr_t>(rowbuf2) & 15) == 0)) {
-        // both tensors in one pass: state_drones = the same rows with the unmasked target offset, built in a second tile
-        tn_sync<SYNC_ID, NTHREADS>();
-        for (int i = tid; i < nwords; i += NTHREADS) rowbuf2[i] = rowbuf[i];
-        tn_sync<SYNC_ID, NTHREADS>();
-        if (r1 != nullptr) { float* r2 = rowbuf2 + (r1 - rowbuf); r2[0] = t_rpos.x; r2[1] = t_rpos.y; r2[2] = t_rpos.z; }
+    if (both) {
         fence_async_smem();
         tn_sync<SYNC_ID, NTHREADS>();
         if (tid == 0) {
             bulk_store(g1, rowbuf, (uint32_t)nwords * 4u);
             bulk_store(g2, rowbuf2, (uint32_t)nwords * 4u);
             bulk_commit();
-            bulk_wait_read<0>();
+            if (!DEFER) bulk_wait_read<0>();
         }
-        tn_sync<SYNC_ID, NTHREADS>();
+        if (!DEFER) tn_sync<SYNC_ID, NTHREADS>();
         return;
     }
 #pragma unroll

@@ -240,12 +240,14 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
         tn_sync<RF_BAR_MAIN, NTH>();          // all h of the last step written; the issuing warps have consumed every arrival
         if (t == 8) HS_TSTAMP_AT(3, 0);
         float* pred_out = (RP.pred_out != nullptr) ? RP.pred_out + (int64_t)t * RP.pred_tick_stride : nullptr;
-        tn_fc_rows<A, NTH, RF_BAR_MAIN>(P, state_self, state_drones, pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI,
+        tn_fc_rows<A, NTH, RF_BAR_MAIN, true>(P, state_self, state_drones, pred_out, e0, nenv, Hhi, Hlo, fcw, fcb, preds, rowbuf, RI,
                                         wst);   // second row tile: the weight staging tile is dead after the prologue
-        tc_fence_before();
-        tn_sync<RF_BAR_MAIN, NTH>();
+        // (no barrier here: the next one every predictor warp meets is the one before the next recurrence)
         if (t == 8) HS_TSTAMP_AT(4, 0);
     }
+    if (tid == 0) bulk_wait_read<0>();        // the last tick's row tiles are still being read by the bulk engine
+    tc_fence_before();
+    tn_sync<RF_BAR_MAIN, NTH>();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
