@@ -42,10 +42,13 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in the barrier unit until the phase completes (or the hint expires)
+// instead of polling - in the rollout kernel the polling of 18 waiting warps was 15 % of all issued instructions, taken
+// from the tick warps that share the SM (profiles/r2_ncu_rollout_fused_4k.txt, per-line table).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -185,7 +188,7 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
             }
             {   // wait for the accumulator (bounded spin: a wrong descriptor must not hang the box)
                 uint32_t spins = 0;
-                while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
+                while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 16)) __trap(); }
                 phase ^= 1;
             }
             tc_fence_after();
@@ -688,13 +691,13 @@ struct TnIssue {
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& phase) {
     uint32_t spins = 0;                                     // bounded: a wrong descriptor must not hang the box
-    while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 24)) __trap(); }
+    while (!mbar_try_wait(bar, phase)) { if (++spins > (1u << 16)) __trap(); }
     phase ^= 1;
 }
 // barrier `idx` of an array of mbarriers; `bits` holds one phase bit per barrier (no dynamically indexed registers)
 __device__ __forceinline__ void mbar_wait_idx(uint32_t bar0, uint32_t idx, uint32_t& bits) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 24)) __trap(); }
+    while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 16)) __trap(); }
     bits ^= 1u << idx;
 }
 

@@ -82,12 +82,6 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
     float* wst = rowbuf + TN_E * A * (20 + 3 * FMAX);
     float* tick_mem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wst + 256 * TN_WPITCH) + 127) & ~(uintptr_t)127);
 
-    auto load_table = [&](int t, int l, int nl) {                // sB[t & 1] <- sets[(first + t) % num_sets], by nl lanes
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(RP.sets + (RP.first_set + t) % RP.num_sets);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sB[t & 1]);
-        for (int i = l; i < (int)(sizeof(hs_buffers) / 4); i += nl) dst[i] = __ldg(src + i);
-    };
-
     if (warp >= NTH / 32) {
         // ================= tick warps: tick t while the predictor warps work on tick t-1 =================
         const int tw = warp - NTH / 32;
@@ -101,12 +95,20 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
             for (int i = lane; i < nw; i += 32) tile[i] = RP.first_tp_prev[ew * (H * FD) + i];
             __syncwarp();
         }
+        constexpr int TBL_WORDS = (int)(sizeof(hs_buffers) / 4);
+        static_assert(TBL_WORDS <= 32 * FUSED_TICK_WARPS, "one table word per tick thread");
+        auto table_word = [&](int t) -> uint32_t {                    // this thread's word of tick t's buffer table
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(RP.sets + (RP.first_set + t) % RP.num_sets);
+            return (ttid < TBL_WORDS && t < T) ? __ldg(src + ttid) : 0u;
+        };
+        uint32_t tbl = table_word(0);
         for (int t = 0; t < T; ++t) {
             // sB[t & 1] was last read by the predictor warps for tick t-2, which ended before they released the tile of t-1
             if (t == 8) HS_TSTAMP_AT(10, NTH);
             if (t > 0) asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TILE_FREE), "n"(RF_THREADS) : "memory");
             if (t == 8) HS_TSTAMP_AT(11, NTH);
-            load_table(t, ttid, 32 * FUSED_TICK_WARPS);
+            if (ttid < TBL_WORDS) reinterpret_cast<uint32_t*>(&sB[t & 1])[ttid] = tbl;
+            tbl = table_word(t + 1);                                  // in flight during the tick: no global latency at the loop top
             asm volatile("bar.sync %0, %1;" :: "n"(RF_BAR_TICKW), "n"(32 * FUSED_TICK_WARPS) : "memory");
             const float* act = RP.action + (int64_t)t * RP.action_tick_stride;
             // from the second tick on the new frame goes straight into the operand ring: slot (t-1) % H held the oldest

@@ -69,8 +69,8 @@ __device__ __forceinline__ void wd_mbar_expect(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void wd_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");      // suspend-time hint: sleep, do not poll
     }
 }
 __device__ __forceinline__ void wd_tma_load_2d(uint32_t sdst, const CUtensorMap* map, int x, int y, uint32_t bar) {
