@@ -864,21 +864,28 @@ def collector_line(torch, mupe_b200, dev):
     def policy(td):
         td.set(("agents", "action"), torch.randn(E, A, 4, device=dev))
         return td
-    col = mupe_b200.SyncDataCollector(env, policy=policy, frames_per_batch=E * T, total_frames=E * T * 6, device=dev,
+    col = mupe_b200.SyncDataCollector(env, policy=policy, frames_per_batch=E * T, total_frames=E * T * 10, device=dev,
                                       return_same_td=True)
     it = iter(col)
     next(it)
+    next(it)                                  # second rollout: the wrap-around graph (row T-1 -> row 0) is captured here
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    times = []
     n = 0
+    t0 = time.perf_counter()
     for data in it:
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        times.append(t1 - t0)
+        t0 = t1
         n += 1
-        if n == 4:
+        if n == 6:
             break
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
     env.close()
+    times.sort()
+    dt = n * 0.5 * (times[n // 2 - 1] + times[n // 2])          # median rollout time x n: a Python loop on a shared host is noisy
     return {"value": E * T * n / dt, "unit": "env-steps/s", "rollouts": n, "frames_per_batch": E * T,
+            "statistic": "median of the per-rollout wall times", "best": E * T / times[0], "worst": E * T / times[-1],
             "api": "SyncDataCollector(TransformedEnv(HideAndSeek, PIDRateController), policy) - the loop of scripts/train.py - with a "
                    "random device policy; one [E, 64] tensordict per iteration (rollout-storage mode: ticks write the rows in place)"}
 
