@@ -524,9 +524,12 @@ __device__ unsigned long long hs_dbg_times[32];
 #define HS_TSTAMP_TID 0
 #define HS_TSTAMP_AT(i, tid_) do { if (blockIdx.x == 0 && threadIdx.x == (tid_)) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); hs_dbg_times[i] = t_; } } while (0)
+#define HS_TSTAMP_IF(i, cond_) do { if (blockIdx.x == 0 && (cond_)) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); hs_dbg_times[i] = t_; } } while (0)
 #else
 #define HS_TSTAMP(i) do {} while (0)
 #define HS_TSTAMP_AT(i, tid_) do {} while (0)
+#define HS_TSTAMP_IF(i, cond_) do {} while (0)
 #endif
 // What a row thread (tid < 32 A: env el = tid % 32, pursuer slot = tid / 32) needs from the arena.  The fused kernel
 // loads it right after the tick phase so that the L2 round trip is not exposed after the recurrence.

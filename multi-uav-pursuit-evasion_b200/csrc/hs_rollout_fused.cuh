@@ -207,6 +207,7 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
                 for (int s = 0; s < H; ++s)
                     for (int hf = 0; hf < 2; ++hf) {
                         mbar_wait_idx(h_ready, (uint32_t)hf, ph_h);
+                        HS_TSTAMP_IF(16 + 4 * hf + 8 * (s - 3), t == 8 && (s == 3 || s == 4) && warp_u == 16u);
                         if (s + 1 < H) {
                             tc_fence_after();
                             const uint32_t d = d_mine + 16u * (uint32_t)hf;
@@ -214,6 +215,7 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
                             I.h_part(d, hdesc(hf, false), hdesc(hf, true));
                             tc_commit(d_ready + 8u * (uint32_t)hf);
                         }
+                        HS_TSTAMP_IF(17 + 4 * hf, t == 8 && s == 3 && warp_u == 16u);
                     }
             }
             __syncwarp();
@@ -227,11 +229,13 @@ hs_rollout_fused_kernel(const __grid_constant__ KParams P, const __grid_constant
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     mbar_wait_idx(d_ready, (uint32_t)hf, ph_d);
+                    HS_TSTAMP_IF(18 + 4 * hf, t == 8 && s == 4 && tid == 0);
                     tc_fence_after();
                     tn_epilogue4(lane_base, L, 16 * hf + 4 * cg, cst[hf], Hhi, Hlo);
                     fence_async_smem();                      // h (generic proxy) -> async proxy of the next MMAs
                     tc_fence_before();
                     __syncwarp();
+                    HS_TSTAMP_IF(19 + 4 * hf, t == 8 && s == 4 && tid == 0);
                     if (lane == 0) mbar_arrive(h_ready + 8u * (uint32_t)hf);
                     __syncwarp();
                     if (s == 0 && hf == 1 && t + 1 < T)      // both halves' step-0 MMAs are complete: release the tile

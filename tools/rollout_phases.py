@@ -47,6 +47,13 @@ def main():
     print(f"  wait for 'tile free'                    {us(11, 10):7.2f} us")
     print(f"  table + hs_tick_body                    {us(12, 11):7.2f} us")
     print(f"  tick warps start their wait {us(10, 0):+7.2f} us relative to the predictor warps' loop top")
+    # one LSTM step inside the recurrence (tick 8): the issuer's wait on h of step 3 -> the MMAs of step 4 -> epilogue of step 4
+    for hf in (0, 1):
+        b = 16 + 4 * hf
+        print(f"half {hf}: issue of step 4 (30 MMAs per M-tile + commit) {us(b + 1, b):6.2f} us | accumulator ready for the epilogue "
+              f"{us(b + 2, b + 1):+6.2f} us after the commit | epilogue (tcgen05.ld, gates, h, fences) {us(b + 3, b + 2):6.2f} us")
+    print(f"half 0: h of step 4 seen by the issuer {us(24, 19):+6.2f} us after the epilogue's last fence; step period (h3 -> h4 seen) {us(24, 16):6.2f} us")
+    print(f"half 1: step period {us(28, 20):6.2f} us; half 1 lags half 0 by {us(20, 16):6.2f} us")
     eng.close()
 
 
