@@ -19,6 +19,7 @@ HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3
 HS_OPT_FUSED_TICK = 4
 HS_OPT_EXACT_MATH = 5
 HS_OPT_TICK_MAPPING = 6
+HS_OPT_ROLLOUT_VARIANT = 7
 
 # field ids, include/hs_b200.h
 (FIELD_DRONE_POS, FIELD_DRONE_ROT, FIELD_DRONE_LINVEL, FIELD_DRONE_ANGVEL, FIELD_THROTTLE,

@@ -43,6 +43,7 @@
 #include "hs_predictor_mma.cuh"
 #include "hs_predictor_tcgen05.cuh"
 #include "hs_rollout_fused.cuh"
+#include "hs_rollout_pair.cuh"
 #include "hs_reset.cuh"
 #include "hs_hover.cuh"
 #include "hs_samplers.cuh"
@@ -91,6 +92,7 @@ struct hs_handle {
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
     int exact_math = 0;          // HS_OPT_EXACT_MATH: the tick runs the IEEE-arithmetic build of hs_tick_kernel (parity evidence)
     bool rollout_ready = false;  // hs_rollout_fused_kernel's shared-memory attribute set
+    int rollout_variant = 0;     // HS_OPT_ROLLOUT_VARIANT: 0 auto (two ticks per predictor pass), 1 one tick per pass
     int tick_mapping = 0;        // HS_OPT_TICK_MAPPING: 0 auto, 1 four lanes per env, 2 one lane per env (hs_tick_wide_kernel)
     // TMA tensor maps of the one-lane mapping (state tile load / store, stats tile), valid for tm_arena / tm_stats
     CUtensorMap tm[3];
@@ -553,15 +555,26 @@ int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, 
     RP.first_tp_prev = first_tp_prev;
     RP.action = action; RP.action_tick_stride = action_tick_stride;
     RP.pred_out = tp_pred_out; RP.pred_tick_stride = pred_tick_stride;
-    const size_t smem = rollout_fused_smem_bytes(c);
+    const bool pair = h->rollout_variant != 1 && rollout_pair_smem_bytes(c) <= HS_MAX_DYN_SMEM;
+    const size_t smem = pair ? rollout_pair_smem_bytes(c) : rollout_fused_smem_bytes(c);
     if (!h->rollout_ready) {
-        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_fused_smem_bytes(c)));
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_fused_smem_bytes(c)));
+        if (rollout_pair_smem_bytes(c) <= HS_MAX_DYN_SMEM) {
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_pair_smem_bytes(c)));
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_pair_smem_bytes(c)));
+        }
         h->rollout_ready = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (c.num_cylinders <= 5) hs_rollout_fused_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
-    else hs_rollout_fused_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    const bool small_c = c.num_cylinders <= 5;
+    if (pair) {
+        if (small_c) hs_rollout_pair_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+        else hs_rollout_pair_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    } else {
+        if (small_c) hs_rollout_fused_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+        else hs_rollout_fused_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     h->tp_frames += num_ticks;
@@ -1192,6 +1205,10 @@ int hs_set_option(hs_handle* h, int option, int value) {
         case HS_OPT_HOST_IO_GRAPH:
             if (value != 0 && value != 1) return set_err(HS_ERR_INVALID, "HS_OPT_HOST_IO_GRAPH must be 0 or 1%s");
             h->io_graph_mode = value;
+            return HS_OK;
+        case HS_OPT_ROLLOUT_VARIANT:
+            if (value < 0 || value > 1) return set_err(HS_ERR_INVALID, "HS_OPT_ROLLOUT_VARIANT must be 0 (auto: two ticks per predictor pass) or 1 (one tick per pass)%s");
+            h->rollout_variant = value;
             return HS_OK;
         case HS_OPT_TICK_MAPPING:
             if (value < 0 || value > 2) return set_err(HS_ERR_INVALID, "HS_OPT_TICK_MAPPING must be 0 (auto), 1 (4 lanes per env) or 2 (one lane per env)%s");

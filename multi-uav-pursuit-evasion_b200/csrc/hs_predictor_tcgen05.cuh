@@ -439,9 +439,16 @@ __device__ __forceinline__ TnLane tn_lane_consts(const TPParams& W, int row) {
 // x of all H steps of one 32-env tile -> B operand (tf32 hi/lo): lane = (env & 7) + 8 * (k & 3) per core
 // matrix, so the 32 stores of a warp cover 128 contiguous bytes; loads are issued ten at a time.
 template <int FD, int NTHREADS = TN_THREADS>
+__device__ __forceinline__ void tn_stage_x_ptr(const float* __restrict__ win, int64_t xstride, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo);
+template <int FD, int NTHREADS = TN_THREADS>
 __device__ __forceinline__ void tn_stage_x(const KParams& P, int64_t e0, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
     int64_t xstride;
-    const float* __restrict__ win = tp_window_base(P, e0, H * FD, FD, xstride);
+    const float* win = tp_window_base(P, e0, H * FD, FD, xstride);
+    tn_stage_x_ptr<FD, NTHREADS>(win, xstride, nenv, H, Xhi, Xlo);
+}
+// `win`: chronological window of the tile's first env, `xstride` floats between consecutive envs
+template <int FD, int NTHREADS>
+__device__ __forceinline__ void tn_stage_x_ptr(const float* __restrict__ win, int64_t xstride, int nenv, int H, uint8_t* Xhi, uint8_t* Xlo) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = lane & 7, kk = lane >> 3;
     constexpr int NW = NTHREADS / 32, BATCH = 10;

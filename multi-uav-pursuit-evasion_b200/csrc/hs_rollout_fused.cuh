@@ -29,6 +29,7 @@ struct XRingHook {
     static constexpr bool ACTIVE = true;
     uint8_t *xhi, *xlo;              // slot base + (tick warp) * TN_SBO; nullptr: leave the staging to the predictor warps
     int nenv_w;                      // valid envs of this warp
+    __device__ __forceinline__ void state(bool, bool, int, int, const V3&, const Q4&, const V3&, const V3&, float, bool) const {}
     template <int FD> __device__ __forceinline__ void frame(const float* tile, int per_env, int keep, int lane) const {
         if (xhi == nullptr) return;
         const int rr = lane & 7, kk = lane >> 3;

@@ -44,6 +44,7 @@ __device__ __noinline__ void tp_prefetch_slow(float* tp_tile, const float* src, 
 struct NoFrameHook {
     static constexpr bool ACTIVE = false;
     template <int FD> __device__ __forceinline__ void frame(const float*, int, int, int) const {}
+    __device__ __forceinline__ void state(bool, bool, int, int, const V3&, const Q4&, const V3&, const V3&, float, bool) const {}
 };
 template <int A, bool RESET, int CT, bool TP_IN_SMEM = false, class Hook = NoFrameHook>
 __device__ __forceinline__ void hs_tick_body(const KParams& P, const hs_buffers& B, const float* __restrict__ action,
@@ -338,6 +339,7 @@ __device__ __forceinline__ void hs_tick_body(const KParams& P, const hs_buffers&
         if (Hook::ACTIVE) {
             __syncwarp();
             hook.template frame<FD>(tp_tile, per_env, keep, lane);
+            hook.state(is_drone, is_ev, slot, lane >> 2, p, q, lv, tp, progress, bdetect);     // what the row kernels read back
         }
         {
             float* gdst = B.tp_input + e0 * per_env;

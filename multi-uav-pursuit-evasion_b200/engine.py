@@ -495,6 +495,10 @@ class HsEngine:
         check(lib.hs_set_option(self._h, _lib.HS_OPT_TICK_MAPPING, int(mapping)), "hs_set_option")
         self._graphs = None
 
+    def set_rollout_variant(self, variant: int):
+        """HS_OPT_ROLLOUT_VARIANT: 0 auto (hs_rollout_pair_kernel: two ticks per predictor pass), 1 hs_rollout_fused_kernel."""
+        check(lib.hs_set_option(self._h, _lib.HS_OPT_ROLLOUT_VARIANT, int(variant)), "hs_set_option")
+
     def set_exact_math(self, on: bool):
         """HS_OPT_EXACT_MATH: run the tick with the IEEE-arithmetic build of the kernel (parity evidence; ~2x slower)."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_EXACT_MATH, 1 if on else 0), "hs_set_option")
