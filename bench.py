@@ -517,16 +517,16 @@ def run_gpu_arm(args):
         if one_kernel:
             step_us = 1e3 * ms_total / args.steps
             ach = ab_all["total"] * E * ROLLOUT / (step_us * 1e-6) / 1e9
-            roof = {"bound": "hbm", "kernel": "hs_rollout_fused_kernel<3,5>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "hs_rollout_pair_kernel<3,5>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
                     "frac": ach / peak_hbm, "traffic": ROLLOUT_TRAFFIC, "traffic_source": ROLLOUT_TRAFFIC_SRC,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": ab_all["total"] * E * ROLLOUT, "launch_us": step_us,
                     "share_of_step": 1.0,
                     "note": "3077 algorithmic B/env-tick (SURVEY 8d) x 4096 envs x 64 ticks per launch over the launch period "
-                            "measured in the timed region.  A CTA keeps its 32-env tile for the whole rollout; per tick it is a "
-                            "dependent chain - 10 LSTM steps x ~1.3 us on the tensor pipe + staging + FC/rows, with the ~8 us "
-                            "control tick of the NEXT step hidden under it on dedicated warps - not a stream: the fraction states how "
-                            "far this latency-bound launch is from the bandwidth roof; the HBM-bound regime of the tick is "
-                            "roofline.at_scale"}
+                            "measured in the timed region.  A CTA keeps its 32-env tile for the whole rollout; per PAIR of ticks it is a "
+                            "dependent chain - 10 LSTM steps x 120 tcgen05.mma (two ticks ping-pong on the tensor pipe) + epilogues + "
+                            "FC/rows, with the control ticks of the next two steps running beside it on dedicated warps - not a "
+                            "stream: the fraction states how far this latency-bound launch is from the bandwidth roof; the HBM-bound "
+                            "regime of the tick is roofline.at_scale"}
         elif one_launch:
             ach = ab_all["total"] * E / (tick_us * 1e-6) / 1e9
             roof = {"bound": "hbm", "kernel": "hs_tick_tp_fused_kernel<3,5,true>", "achieved": ach, "peak": peak_hbm, "unit": "GB/s",
@@ -553,8 +553,9 @@ def run_gpu_arm(args):
             "l2": (f"outputs larger than L2: every rollout writes its 64 ticks into 512 MB of time-major rollout storage, and consecutive "
                    f"steps rotate over {ROLL_ROTATE} independent env batches per GPU" if one_kernel else
                    f"inputs larger than L2: the ticks of a rollout rotate over {ROTATE} independent env batches per GPU"),
-            "launch": ("ONE kernel launch per 64-tick rollout (hs_rollout_fused: the tick of step t+1 on dedicated warps beside "
-                       "the tcgen05 predictor of step t; a different device-resident action every tick)" if one_kernel else
+            "launch": ("ONE kernel launch per 64-tick rollout (hs_rollout_fused -> hs_rollout_pair_kernel: the control ticks run on "
+                       "dedicated warps two steps ahead of the tcgen05 predictor, which advances two ticks at a time; a different "
+                       "device-resident action every tick)" if one_kernel else
                        "one CUDA graph launch per 64-tick rollout (64 kernel nodes, one hs_tick_tp_fused_kernel per tick)"
                        if rollout_graph is not None else "one CUDA graph launch per tick (64 per step)"),
             "collective": (f"all_gather of the per-env episode returns after every rollout: {args.steps} inside the timed region"
@@ -746,8 +747,8 @@ def extra_measurements(torch, mupe_b200, engines, envs, tp_net, dev, args, varia
     return extra
 
 
-ROLLOUT_TRAFFIC = 516387072     # dram read + write of one 64-tick hs_rollout_fused launch at 4096 envs (ncu)
-ROLLOUT_TRAFFIC_SRC = ("profiles/r2_ncu_rollout_fused_4k.txt: dram read 17.5 MB + write 498.9 MB per 64-tick launch (the tile's state and "
+ROLLOUT_TRAFFIC = 508470784     # dram read + write of one 64-tick hs_rollout_fused launch at 4096 envs (ncu)
+ROLLOUT_TRAFFIC_SRC = ("profiles/r2_ncu_rollout_pair_4k.txt: dram read 17.6 MB + write 490.9 MB per 64-tick launch (the tile's state and "
                        "TP window never leave the SM between ticks; what reaches HBM is every tick's outputs)")
 RING_TRAFFIC_1M = 1728035512    # dram read + write of one 1 Mi-env launch in ring mode (ncu)
 RING_TRAFFIC_SRC = "profiles/r2_ncu_tick_wide_ring_v6_1M.txt (dram read 0.5707 GB + write 1.1573 GB per 1 Mi-env launch = 1648 B/env)"

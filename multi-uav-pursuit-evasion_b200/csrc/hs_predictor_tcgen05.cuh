@@ -707,7 +707,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t& phase) {
 // barrier `idx` of an array of mbarriers; `bits` holds one phase bit per barrier (no dynamically indexed registers)
 __device__ __forceinline__ void mbar_wait_idx(uint32_t bar0, uint32_t idx, uint32_t& bits) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 16)) __trap(); }
+    // (polling is 17 % of the rollout kernels' issued instructions, profiles/r2_ncu_rollout_pair_4k.txt, but it is not what
+    // bounds them: a __nanosleep(40) back-off here changed nothing - measured, 15.7 us per tick either way)
+    while (!mbar_try_wait(bar0 + 8u * idx, (bits >> idx) & 1u)) { if (++spins > (1u << 22)) __trap(); }
     bits ^= 1u << idx;
 }
 
