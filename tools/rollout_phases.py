@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Phase timeline of one tick (t = 8) inside hs_rollout_fused_kernel (CTA 0, %globaltimer).  Needs the timing build:
+"""Phase timeline of one tick (t = 8) inside hs_rollout_fused_kernel - the one-tick-per-pass variant - (CTA 0, %globaltimer).  Needs the timing build:
     python multi-uav-pursuit-evasion_b200/build.py --define HS_FUSED_TIMING --out multi-uav-pursuit-evasion_b200/libhs_b200_timing.so
     HS_B200_LIB=multi-uav-pursuit-evasion_b200/libhs_b200_timing.so python tools/rollout_phases.py"""
 import ctypes as C
@@ -21,6 +21,7 @@ def main():
     torch.manual_seed(0)
     tp = mupe_b200.TP_net(16, 15, 5).to(dev)
     eng = mupe_b200.HsEngine(mupe_b200.build_hs_config(E), dev, rollout_steps=T)
+    eng.set_rollout_variant(1)          # the stamps live in hs_rollout_fused_kernel (one tick per predictor pass)
     a = 0.9 / 2 ** 0.5
     dpos = torch.rand(E, 3, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([0.1, -a + 0.1, 0.5], device=dev)
     tpos = torch.rand(E, 3, device=dev) * torch.tensor([a - 0.2, 2 * a - 0.2, 0.2], device=dev) + torch.tensor([-a + 0.1, -a + 0.1, 0.5], device=dev)
