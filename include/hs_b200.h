@@ -349,9 +349,9 @@ int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, 
  * tests can separate rounding amplified by the task's discontinuities from defects. */
 enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4,
        HS_OPT_EXACT_MATH = 5, HS_OPT_TICK_MAPPING = 6, HS_OPT_ROLLOUT_VARIANT = 7 };
-/* HS_OPT_ROLLOUT_VARIANT: kernel behind hs_rollout_fused.  0 (default) = hs_rollout_pair_kernel: the predictor warps advance
- * two consecutive ticks at a time (full 32-env MMA tiles, half the tensor-pipe instructions); 1 = hs_rollout_fused_kernel:
- * one tick at a time as two 16-env halves.  Same results. */
+/* HS_OPT_ROLLOUT_VARIANT: kernel behind hs_rollout_fused = ticks the predictor warps advance per pass.  0 (default) = auto;
+ * 2, 3 = hs_rollout_pair_kernel (full 32-env MMA tiles of 2 or 3 consecutive ticks ping-pong on the tensor pipe: half the
+ * tensor-pipe instructions of) 1 = hs_rollout_fused_kernel (one tick at a time as two 16-env halves).  Same results. */
 /* HS_OPT_TICK_MAPPING: which work decomposition hs_step_pre / hs_reset use for the tick kernel.
  *   0 (default) = auto: 4 lanes per env (hs_tick_kernel, latency-bound small batches) below 32768 envs, one lane per
  *       env (hs_tick_wide_kernel: TMA tensor loads of the SoA state tile, bulk stores of the outputs; bandwidth-bound

@@ -44,6 +44,9 @@
 #include "hs_predictor_tcgen05.cuh"
 #include "hs_rollout_fused.cuh"
 #include "hs_rollout_pair.cuh"
+#ifndef HS_ROLLOUT_AUTO_STREAMS
+#define HS_ROLLOUT_AUTO_STREAMS 2     /* measured: 1 -> 17.96, 2 -> 15.35, 3 -> 15.35 us per tick at 4096 envs (the tick warps bound 2 and 3) */
+#endif
 #include "hs_reset.cuh"
 #include "hs_hover.cuh"
 #include "hs_samplers.cuh"
@@ -92,7 +95,7 @@ struct hs_handle {
     int io_zero_copy_action = 1; // HS_OPT_HOST_IO_ZERO_COPY_ACTION: pinned host actions are read in place by the tick kernel
     int exact_math = 0;          // HS_OPT_EXACT_MATH: the tick runs the IEEE-arithmetic build of hs_tick_kernel (parity evidence)
     bool rollout_ready = false;  // hs_rollout_fused_kernel's shared-memory attribute set
-    int rollout_variant = 0;     // HS_OPT_ROLLOUT_VARIANT: 0 auto (two ticks per predictor pass), 1 one tick per pass
+    int rollout_variant = 0;     // HS_OPT_ROLLOUT_VARIANT: 0 auto, else ticks per predictor pass (1, 2, 3)
     int tick_mapping = 0;        // HS_OPT_TICK_MAPPING: 0 auto, 1 four lanes per env, 2 one lane per env (hs_tick_wide_kernel)
     // TMA tensor maps of the one-lane mapping (state tile load / store, stats tile), valid for tm_arena / tm_stats
     CUtensorMap tm[3];
@@ -535,6 +538,7 @@ int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, 
     if (num_sets < 1 || first_set < 0 || first_set >= num_sets || num_ticks < 1)
         return set_err(HS_ERR_INVALID, "hs_rollout_fused: num_sets >= 1, 0 <= first_set < num_sets, num_ticks >= 1%s");
     const int64_t tiles32 = ((int64_t)c.num_envs + TN_E - 1) / TN_E;
+    static_assert(RP_H == 10, "hs_rollout_pair_kernel is built for history_step 10");
     if (!c.use_tp_net || c.num_agents != 3 || c.history_step != 10 || c.use_obstacles || h->exact_math || tp_ring_mode(h) ||
         rollout_fused_smem_bytes(c) > HS_MAX_DYN_SMEM)
         return set_err(HS_ERR_INVALID, "hs_rollout_fused covers the reference's shape (3 pursuers, history_step 10, use_tp_net, no use_obstacles, "
@@ -555,25 +559,36 @@ int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, 
     RP.first_tp_prev = first_tp_prev;
     RP.action = action; RP.action_tick_stride = action_tick_stride;
     RP.pred_out = tp_pred_out; RP.pred_tick_stride = pred_tick_stride;
-    const bool pair = h->rollout_variant != 1 && rollout_pair_smem_bytes(c) <= HS_MAX_DYN_SMEM;
-    const size_t smem = pair ? rollout_pair_smem_bytes(c) : rollout_fused_smem_bytes(c);
+    // streams per predictor pass: 1 = hs_rollout_fused_kernel; 2, 3 = hs_rollout_pair_kernel<NS>
+    int ns = (h->rollout_variant == 0) ? HS_ROLLOUT_AUTO_STREAMS : h->rollout_variant;
+    while (ns > 1 && rollout_pair_smem_bytes(c, ns) > HS_MAX_DYN_SMEM) --ns;
+    const size_t smem = ns > 1 ? rollout_pair_smem_bytes(c, ns) : rollout_fused_smem_bytes(c);
     if (!h->rollout_ready) {
-        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_fused_smem_bytes(c)));
-        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_fused_smem_bytes(c)));
-        if (rollout_pair_smem_bytes(c) <= HS_MAX_DYN_SMEM) {
-            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_pair_smem_bytes(c)));
-            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_pair_smem_bytes(c)));
+        const cudaFuncAttribute attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, 5>, attr, (int)rollout_fused_smem_bytes(c)));
+        CUDA_OK(cudaFuncSetAttribute(hs_rollout_fused_kernel<3, CMAX>, attr, (int)rollout_fused_smem_bytes(c)));
+        if (rollout_pair_smem_bytes(c, 2) <= HS_MAX_DYN_SMEM) {
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, 5, 2>, attr, (int)rollout_pair_smem_bytes(c, 2)));
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, CMAX, 2>, attr, (int)rollout_pair_smem_bytes(c, 2)));
+        }
+        if (rollout_pair_smem_bytes(c, 3) <= HS_MAX_DYN_SMEM) {
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, 5, 3>, attr, (int)rollout_pair_smem_bytes(c, 3)));
+            CUDA_OK(cudaFuncSetAttribute(hs_rollout_pair_kernel<3, CMAX, 3>, attr, (int)rollout_pair_smem_bytes(c, 3)));
         }
         h->rollout_ready = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
     const bool small_c = c.num_cylinders <= 5;
-    if (pair) {
-        if (small_c) hs_rollout_pair_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
-        else hs_rollout_pair_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+    const unsigned grid = (unsigned)tiles32;
+    if (ns == 3) {
+        if (small_c) hs_rollout_pair_kernel<3, 5, 3><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
+        else hs_rollout_pair_kernel<3, CMAX, 3><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
+    } else if (ns == 2) {
+        if (small_c) hs_rollout_pair_kernel<3, 5, 2><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
+        else hs_rollout_pair_kernel<3, CMAX, 2><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
     } else {
-        if (small_c) hs_rollout_fused_kernel<3, 5><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
-        else hs_rollout_fused_kernel<3, CMAX><<<(unsigned)tiles32, RF_THREADS, smem, s>>>(P, W, RP);
+        if (small_c) hs_rollout_fused_kernel<3, 5><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
+        else hs_rollout_fused_kernel<3, CMAX><<<grid, RF_THREADS, smem, s>>>(P, W, RP);
     }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
@@ -1207,7 +1222,7 @@ int hs_set_option(hs_handle* h, int option, int value) {
             h->io_graph_mode = value;
             return HS_OK;
         case HS_OPT_ROLLOUT_VARIANT:
-            if (value < 0 || value > 1) return set_err(HS_ERR_INVALID, "HS_OPT_ROLLOUT_VARIANT must be 0 (auto: two ticks per predictor pass) or 1 (one tick per pass)%s");
+            if (value < 0 || value > 3) return set_err(HS_ERR_INVALID, "HS_OPT_ROLLOUT_VARIANT must be 0 (auto) or the number of ticks per predictor pass: 1, 2, 3%s");
             h->rollout_variant = value;
             return HS_OK;
         case HS_OPT_TICK_MAPPING:

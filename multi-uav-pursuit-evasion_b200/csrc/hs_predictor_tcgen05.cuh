@@ -147,7 +147,8 @@ hs_tp_fill_tc_kernel(const __grid_constant__ KParams P, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) { cst[j] = 0.f; hreg[j] = 0.f; }
         int64_t xstride;
-        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride) + (e - e0) * xstride;
+        const float* xin = tp_window_base(P, e0, H * FD, FD, xstride);
+        xin += (e - e0) * xstride;
         float xf[16];
         auto load_x = [&](int s) {
 #pragma unroll

@@ -1,5 +1,5 @@
 // hs_rollout_pair.cuh -- hs_rollout_pair_kernel: the rollout kernel of hs_rollout_fused.cuh with the predictor advancing
-// TWO TICKS at a time.  Part of the single translation unit hs_kernels.cu.
+// a GROUP of NS = 2 or 3 consecutive ticks at a time.  Part of the single translation unit hs_kernels.cu.
 //
 // Why: the phase timeline of hs_rollout_fused_kernel (tools/rollout_phases.py) shows the recurrence bound by the tensor
 // pipe's INSTRUCTION rate - 120 tcgen05.mma of shape 128 x 16 x 8 per LSTM step (two 16-env halves x two M-tiles x 30) at
@@ -8,23 +8,39 @@
 // tick), so this kernel ping-pongs the full 32-env tiles of ticks 2p and 2p+1 instead: 128 x 32 x 8 MMAs, 60 per tick and
 // LSTM step - half the tensor-pipe instructions for the same arithmetic.
 //
+// NS = 3 (a third stream in the bubbles of the MMA -> commit -> epilogue -> h chain) is built too but buys nothing: with
+// two streams the predictor already keeps up with the tick warps, whose ~8 us tick body takes ~15 us next to the busy
+// epilogue warps and now bounds the kernel (1 / 2 / 3 ticks per pass: 17.96 / 15.35 / 15.35 us per tick at 4096 envs).
+//
 // What changes against hs_rollout_fused_kernel:
-//   * the tick warps run two ticks ahead; the B-operand ring has H + 2 step slots (frame f lives in slot f mod 12, so
-//     the windows of ticks t and t+1 share 9 slots and ticks t+2, t+3 write the two slots outside them - the second one
-//     after the predictor warps' "pair free", which they raise once the step-0 MMAs of the pair have completed);
+//   * the tick warps run one group ahead; the B-operand ring has H + 2 NS - 1 step slots (frame f lives in slot
+//     f mod S): the NS + 9 frames of a group's windows and the NS frames the tick warps write meanwhile never share a slot;
 //   * what FC + rows need from the state of a tick (pose, velocity, evader position, progress, detect flag) is stashed by
-//     the tick warps in shared memory (four-deep ring: the arena already holds a later tick when the rows are built);
-//   * buffer tables: four-deep ring; "tick done" uses one named barrier for even and one for odd ticks (two arrivals can
-//     be pending).
+//     the tick warps in shared memory (ring of two groups: the arena already holds a later tick when the rows are built);
+//   * buffer tables: ring of two groups; "tick done" uses one named barrier per position in the group (NS arrivals can be
+//     pending); "group free" is raised by the predictor warps at the top of a group, once the previous one is complete.
 // Results are bit-identical to hs_rollout_fused_kernel and to T calls of hs_step_fused.
 #pragma once
 #include "hs_rollout_fused.cuh"
 
 namespace {
 
-constexpr int RP_SLOTS = 12;                                   // operand ring: history_step (10) + 2
+constexpr int RP_H = 10;                                       // history_step this kernel is built for (checked by the host)
 constexpr int RP_STASH = 35;                                   // floats per env: 3 x (pos3, quat4, linvel3) + tpos3 + progress + detect
-constexpr int RP_BAR_MAIN = 1, RP_BAR_DONE_EVEN = 2, RP_BAR_PAIR_FREE = 3, RP_BAR_TICKW = 4, RP_BAR_DONE_ODD = 5;
+constexpr int RP_BAR_MAIN = 1, RP_BAR_GROUP_FREE = 3, RP_BAR_TICKW = 4;
+// "tick done" of the j-th tick of a group: one named barrier each (NS arrivals can be pending)
+__device__ __forceinline__ void rp_done_arrive(int j) {
+    if (j == 0) asm volatile("bar.arrive 2, %0;" :: "n"(RF_THREADS) : "memory");
+    else if (j == 1) asm volatile("bar.arrive 5, %0;" :: "n"(RF_THREADS) : "memory");
+    else asm volatile("bar.arrive 6, %0;" :: "n"(RF_THREADS) : "memory");
+}
+__device__ __forceinline__ void rp_done_sync(int j) {
+    if (j == 0) asm volatile("bar.sync 2, %0;" :: "n"(RF_THREADS) : "memory");
+    else if (j == 1) asm volatile("bar.sync 5, %0;" :: "n"(RF_THREADS) : "memory");
+    else asm volatile("bar.sync 6, %0;" :: "n"(RF_THREADS) : "memory");
+}
+// operand ring: the NS + 9 frames of a group's windows and the NS frames of the next group never share a slot
+__host__ __device__ constexpr int rp_slots(int NS) { return RP_H + 2 * NS - 1; }
 
 struct PairHook {
     static constexpr bool ACTIVE = true;
@@ -79,15 +95,17 @@ __device__ __forceinline__ TnRowIn tn_row_from_stash(const float* stash) {
     return R;
 }
 
-template <int A, int CT>
+template <int A, int CT, int NS>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant__ TPParams W, const __grid_constant__ RolloutParams RP) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ hs_buffers sB[4];                       // buffer table of tick t at sB[t & 3]
+    constexpr int RING = 2 * NS;                       // depth of the table / stash rings: two groups
+    constexpr int RP_SLOTS = rp_slots(NS);
+    __shared__ hs_buffers sB[RING];                    // buffer table of tick t at sB[t % RING]
     const hs_config& c = P.c;
     constexpr int FD = 7 + 3 * A;
     constexpr int NTH = RF_MAIN_THREADS;
-    const int H = c.history_step;                      // == RP_SLOTS - 2 (checked by the host)
+    const int H = c.history_step;                      // == RP_H (checked by the host)
     const int F3 = 3 * c.future_step;
     const int E = c.num_envs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,16 +114,20 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
     uint8_t* H0 = smem_raw;                                     // stream 0: hi, then lo
     float* fcw = reinterpret_cast<float*>(H0 + 2 * TN_H_BYTES);
     float* fcb = fcw + F3 * TP_HID;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // d_ready[2], h_ready[2] (index = stream)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
-    uint8_t* Xhi = reinterpret_cast<uint8_t*>(mbar + 6);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(fcb + 32);    // d_ready[4], h_ready[4] (index = stream)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
+    uint8_t* Xhi = reinterpret_cast<uint8_t*>(mbar + 10);
     uint8_t* Xlo = Xhi + (size_t)RP_SLOTS * TN_X_STEP;
     float* preds = reinterpret_cast<float*>(Xlo + (size_t)RP_SLOTS * TN_X_STEP);
     float* rowbuf = preds + TN_E * 3 * FMAX;
     float* wst = rowbuf + TN_E * A * (20 + 3 * FMAX);           // weight staging tile; after the prologue:
     float* rowbuf2 = wst;                                       //   second row tile
-    uint8_t* H1 = reinterpret_cast<uint8_t*>(rowbuf2 + TN_E * A * (20 + 3 * FMAX));      //   stream 1's h (hi, lo)
-    float* stash = reinterpret_cast<float*>(H1 + 2 * TN_H_BYTES);                        //   4 x [RP_STASH][32]
+    uint8_t* H1 = reinterpret_cast<uint8_t*>(rowbuf2 + TN_E * A * (20 + 3 * FMAX));      //   h (hi, lo) of streams 1 .. NS-1
+    float* stash = reinterpret_cast<float*>(H1 + (NS - 1) * 2 * TN_H_BYTES);             //   RING x [RP_STASH][32]
+    static_assert((size_t)TN_E * A * (20 + 3 * FMAX) * 4 + (size_t)(NS - 1) * 2 * TN_H_BYTES + (size_t)RING * RP_STASH * TN_E * 4
+                  <= (size_t)256 * TN_WPITCH * 4, "the rings must fit the dead weight staging tile");
+    auto Hbuf = [&](int k) -> uint8_t* { return k == 0 ? H0 : H1 + (size_t)(k - 1) * 2 * TN_H_BYTES; };
+    auto dcol = [](int k) -> uint32_t { return k < 2 ? (uint32_t)(k * 2 * TN_E) : (uint32_t)(TN_COL_A + 320); };   // 0, 64, 448
     float* tick_mem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wst + 256 * TN_WPITCH) + 127) & ~(uintptr_t)127);
     auto slot_of = [](int f) { return f % RP_SLOTS; };          // frame produced by tick t: f = H + t
 
@@ -130,12 +152,13 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
         };
         uint32_t tbl = table_word(0);
         // The stash / table rings and the weight-staging region they alias become free when the prologue is over: the
-        // predictor warps raise "pair free" once for that (pair index -1), then once per pair.
-        asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_PAIR_FREE), "n"(RF_THREADS) : "memory");
-        for (int t = 0; t < T; ++t) {
-            // ticks 2p+2, 2p+3 may start once pair p has released its oldest operand slot, stash and table entries
-            if (t >= 2 && (t & 1) == 0) asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_PAIR_FREE), "n"(RF_THREADS) : "memory");
-            if (ttid < TBL_WORDS) reinterpret_cast<uint32_t*>(&sB[t & 3])[ttid] = tbl;
+        // predictor warps raise "group free" once for that, then at the top of every group but the last.
+        asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_GROUP_FREE), "n"(RF_THREADS) : "memory");
+        for (int t = 0, j = 0; t < T; ++t, j = (j + 1 == NS) ? 0 : j + 1) {
+            // the ticks of group g+1 may start once the predictor warps have begun group g (= finished group g-1: its
+            // stash, table and operand slots are free)
+            if (t >= NS && j == 0) asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_GROUP_FREE), "n"(RF_THREADS) : "memory");
+            if (ttid < TBL_WORDS) reinterpret_cast<uint32_t*>(&sB[t % RING])[ttid] = tbl;
             tbl = table_word(t + 1);
             asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_TICKW), "n"(32 * FUSED_TICK_WARPS) : "memory");
             const float* act = RP.action + (int64_t)t * RP.action_tick_stride;
@@ -144,13 +167,12 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
             hook.nenv_w = (int)max((int64_t)0, min((int64_t)ENVS_PER_WARP, E - warp_g * ENVS_PER_WARP));
             hook.xhi = Xhi + (size_t)slot_of(H + t) * TN_X_STEP + (size_t)tw * TN_SBO;
             hook.xlo = Xlo + (size_t)slot_of(H + t) * TN_X_STEP + (size_t)tw * TN_SBO;
-            hook.stash = stash + (t & 3) * (RP_STASH * TN_E);
-            hs_tick_body<A, false, CT, true, PairHook>(P, sB[t & 3], act, warp_g, m, m + TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS,
+            hook.stash = stash + (t % RING) * (RP_STASH * TN_E);
+            hs_tick_body<A, false, CT, true, PairHook>(P, sB[t % RING], act, warp_g, m, m + TICK_STAGE_WORDS, m + 2 * TICK_STAGE_WORDS,
                                                        m + 2 * TICK_STAGE_WORDS + ENVS_PER_WARP * TP_ENV_WORDS_MAX, hook);
             fence_async_smem();                          // operand ring: generic-proxy stores -> the MMAs' async proxy
             __threadfence_block();
-            if (t & 1) asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_DONE_ODD), "n"(RF_THREADS) : "memory");
-            else asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_DONE_EVEN), "n"(RF_THREADS) : "memory");
+            rp_done_arrive(j);
         }
         return;
     }
@@ -159,10 +181,10 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
     const int row = (warp & 3) * 32 + lane;            // TMEM lane = gate row of both M-tiles
     const int cg = warp >> 2;                          // 0..3: epilogue column group; 4: issuing warps
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar)) : "memory");        // d_ready: one commit per M-tile
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar + 1)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 2)) : "memory");   // h_ready: 16 epilogue warps
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 3)) : "memory");
+        for (int k = 0; k < 4; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(smem_u32(mbar + k)) : "memory");        // d_ready: one commit per M-tile
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" :: "r"(smem_u32(mbar + 4 + k)) : "memory");   // h_ready: 16 epilogue warps
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -188,9 +210,9 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
     tn_sync<RP_BAR_MAIN, NTH>();
     tc_fence_after();
     // the weight staging tile is dead: the tick warps may use the stash that aliases it
-    asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_PAIR_FREE), "n"(RF_THREADS) : "memory");
+    asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_GROUP_FREE), "n"(RF_THREADS) : "memory");
 
-    const uint32_t d_ready = smem_u32(mbar), h_ready = smem_u32(mbar + 2);
+    const uint32_t d_ready = smem_u32(mbar), h_ready = smem_u32(mbar + 4);
     uint32_t ph_d = 0u, ph_h = 0u;
     const uint32_t warp_u = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -202,23 +224,24 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
     I.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN_E >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t d_mine = tmem_u + mytl * TN_E;              // stream k: + k * 2 * TN_E
 
-    for (int t0 = 0; t0 < T; t0 += 2) {
-        const int ns = (t0 + 1 < T) ? 2 : 1;                   // streams of this pair: ticks t0 (and t0 + 1)
-        asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_DONE_EVEN), "n"(RF_THREADS) : "memory");
-        if (ns == 2) asm volatile("bar.sync %0, %1;" :: "n"(RP_BAR_DONE_ODD), "n"(RF_THREADS) : "memory");
-        const bool more = t0 + 2 < T;                          // another pair follows: release the tick warps for it
+    for (int t0 = 0; t0 < T; t0 += NS) {
+        const int ns = min(NS, T - t0);                        // streams of this group: ticks t0 .. t0 + ns - 1
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (k < ns) rp_done_sync(k);
+        // the tick warps may start the next group: everything it overwrites belongs to groups that are complete (raised
+        // only now, with every "tick done" of this group consumed, so that no named barrier ever sees two pending phases)
+        if (t0 + NS < T) asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_GROUP_FREE), "n"(RF_THREADS) : "memory");
         tc_fence_before();
-        // (the issuing warps have nothing to protect; the epilogue warps arrive after the step-0 MMAs of the pair)
-        if (issuer && more) asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_PAIR_FREE), "n"(RF_THREADS) : "memory");
         if (issuer) {
             if (elect_one()) {
                 tc_fence_after();
                 auto xdesc = [&](int k, int s, bool lo) {      // step s of tick t0 + k: frame (t0 + k + 1 + s)
                     return tc_desc(smem_u32(lo ? Xlo : Xhi) + (uint32_t)slot_of(t0 + k + 1 + s) * TN_X_STEP, TN_X_LBO, TN_SBO);
                 };
-                auto hdesc = [&](int k, bool lo) { return tc_desc(smem_u32((k ? H1 : H0) + (lo ? TN_H_BYTES : 0)), TN_H_LBO, TN_SBO); };
+                auto hdesc = [&](int k, bool lo) { return tc_desc(smem_u32(Hbuf(k) + (lo ? TN_H_BYTES : 0)), TN_H_LBO, TN_SBO); };
                 for (int k = 0; k < ns; ++k) {
-                    I.x_part(d_mine + (uint32_t)(k * 2 * TN_E), xdesc(k, 0, false), xdesc(k, 0, true), 0u);
+                    I.x_part(d_mine + dcol(k), xdesc(k, 0, false), xdesc(k, 0, true), 0u);
                     tc_commit(d_ready + 8u * (uint32_t)k);
                 }
                 for (int s = 0; s < H; ++s)
@@ -226,7 +249,7 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
                         mbar_wait_idx(h_ready, (uint32_t)k, ph_h);
                         if (s + 1 < H) {
                             tc_fence_after();
-                            const uint32_t d = d_mine + (uint32_t)(k * 2 * TN_E);
+                            const uint32_t d = d_mine + dcol(k);
                             I.x_part(d, xdesc(k, s + 1, false), xdesc(k, s + 1, true), 0u);
                             I.h_part(d, hdesc(k, false), hdesc(k, true));
                             tc_commit(d_ready + 8u * (uint32_t)k);
@@ -235,26 +258,23 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
             }
             __syncwarp();
         } else {
-            float cst[2][8];
+            float cst[NS][8];
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+            for (int k = 0; k < NS; ++k)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cst[k][j] = 0.f;
             for (int s = 0; s < H; ++s) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < NS; ++k) {
                     if (k < ns) {
                         mbar_wait_idx(d_ready, (uint32_t)k, ph_d);
                         tc_fence_after();
-                        uint8_t* Hk = k ? H1 : H0;
-                        tn_epilogue(lane_base + (uint32_t)(k * 2 * TN_E), L, cg, cst[k], Hk, Hk + TN_H_BYTES);
+                        uint8_t* Hk = Hbuf(k);
+                        tn_epilogue(lane_base + dcol(k), L, cg, cst[k], Hk, Hk + TN_H_BYTES);
                         fence_async_smem();                      // h (generic proxy) -> async proxy of the next MMAs
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(h_ready + 8u * (uint32_t)k);
-                        __syncwarp();
-                        if (s == 0 && k == ns - 1 && more)       // the step-0 MMAs of the pair are complete
-                            asm volatile("bar.arrive %0, %1;" :: "n"(RP_BAR_PAIR_FREE), "n"(RF_THREADS) : "memory");
                     }
                 }
             }
@@ -262,13 +282,13 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
         tn_sync<RP_BAR_MAIN, NTH>();          // all h of the last step written; the issuing warps have consumed every arrival
         for (int k = 0; k < ns; ++k) {
             const int t = t0 + k;
-            const TnRowIn RI = tn_row_from_stash<A>(stash + (t & 3) * (RP_STASH * TN_E));
+            const TnRowIn RI = tn_row_from_stash<A>(stash + (t % RING) * (RP_STASH * TN_E));
             float* pred_out = (RP.pred_out != nullptr) ? RP.pred_out + (int64_t)t * RP.pred_tick_stride : nullptr;
-            uint8_t* Hk = k ? H1 : H0;
-            tn_fc_rows<A, NTH, RP_BAR_MAIN, true>(P, sB[t & 3].state_self, sB[t & 3].state_drones, pred_out, e0, nenv, Hk, Hk + TN_H_BYTES,
-                                                  fcw, fcb, preds, rowbuf, RI, rowbuf2);
+            uint8_t* Hk = Hbuf(k);
+            tn_fc_rows<A, NTH, RP_BAR_MAIN, true>(P, sB[t % RING].state_self, sB[t % RING].state_drones, pred_out, e0, nenv, Hk,
+                                                  Hk + TN_H_BYTES, fcw, fcb, preds, rowbuf, RI, rowbuf2);
         }
-        // FC of both streams has read h (barriers inside tn_fc_rows); the next pair's epilogue may overwrite it
+        // FC of every stream has read h (barriers inside tn_fc_rows); the next group's epilogue may overwrite it
     }
     if (tid == 0) bulk_wait_read<0>();        // the last tick's row tiles are still being read by the bulk engine
     tc_fence_before();
@@ -276,8 +296,8 @@ hs_rollout_pair_kernel(const __grid_constant__ KParams P, const __grid_constant_
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-static size_t rollout_pair_smem_bytes(const hs_config& c) {
-    return tp_fused_smem_bytes(c) + 2 * (size_t)(RP_SLOTS - c.history_step) * TN_X_STEP;
+static size_t rollout_pair_smem_bytes(const hs_config& c, int NS) {
+    return tp_fused_smem_bytes(c) + 2 * (size_t)(rp_slots(NS) - c.history_step) * TN_X_STEP + 32;
 }
 
 }  // namespace

@@ -496,7 +496,8 @@ class HsEngine:
         self._graphs = None
 
     def set_rollout_variant(self, variant: int):
-        """HS_OPT_ROLLOUT_VARIANT: 0 auto (hs_rollout_pair_kernel: two ticks per predictor pass), 1 hs_rollout_fused_kernel."""
+        """HS_OPT_ROLLOUT_VARIANT: 0 auto, else the number of ticks the predictor warps advance per pass (1: hs_rollout_fused_kernel;
+        2, 3: hs_rollout_pair_kernel)."""
         check(lib.hs_set_option(self._h, _lib.HS_OPT_ROLLOUT_VARIANT, int(variant)), "hs_set_option")
 
     def set_exact_math(self, on: bool):

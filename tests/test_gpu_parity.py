@@ -419,7 +419,7 @@ def test_fused_tick_predictor_kernel_equals_two_launches(E, C, A):
         e.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["pair", "single"])
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["one-tick", "two-ticks", "three-ticks"])
 @pytest.mark.parametrize("E,C,T,storage", [(300, 5, 7, False), (32, 5, 3, False), (4096, 5, 12, False), (1000, 8, 5, False),
                                            (200, 5, 6, True), (4100, 5, 9, True), (64, 5, 1, False), (96, 5, 2, True)])
 def test_rollout_fused_kernel_equals_per_tick_launches(E, C, T, storage, variant):
@@ -437,7 +437,7 @@ def test_rollout_fused_kernel_equals_per_tick_launches(E, C, T, storage, variant
     init = O.sample_reset(P, E, g)
     kw = dict(rollout_steps=T) if storage else {}
     one, ref = mupe_b200.HsEngine(cfg, dev, **kw), mupe_b200.HsEngine(cfg, dev, **kw)
-    one.set_rollout_variant(variant)      # 0: two ticks per predictor pass (hs_rollout_pair_kernel), 1: hs_rollout_fused_kernel
+    one.set_rollout_variant(variant)      # ticks per predictor pass: 1 hs_rollout_fused_kernel; 2, 3 hs_rollout_pair_kernel
     for e in (one, ref):
         e.reset(None, init["drone_pos"], init["drone_rot"], init["target_pos"], init["cyl_pos"])
         e.step_post_tp(e.tp_weights(tp))

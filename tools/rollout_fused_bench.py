@@ -47,6 +47,13 @@ def main():
         return 1e3 * e0.elapsed_time(e1) / reps
 
     out = {"E": E, "T": T, "rotating_batches": R}
+    for v in (1, 2, 3):
+        for e in engs:
+            e.set_rollout_variant(v)
+        us = timed(lambda i: engs[i % R].rollout_fused(acts, T, ws[i % R]), 4 * R)
+        out[f"rollout_fused_{v}_ticks_per_pass"] = {"us_per_tick": us / T, "env_steps_per_s": E * T / (us * 1e-6)}
+    for e in engs:
+        e.set_rollout_variant(0)
     us = timed(lambda i: engs[i % R].rollout_fused(acts, T, ws[i % R]), 4 * R)
     out["rollout_fused"] = {"us_per_rollout": us, "us_per_tick": us / T, "env_steps_per_s": E * T / (us * 1e-6)}
     us = timed(lambda i: engs[i % R].rollout_fused(acts[0], T, ws[i % R]), 4 * R)
