@@ -178,7 +178,7 @@ class HsEngine:
 
     def set_tp_ring(self, on: bool = True):
         """Ring form of the TP window (hs_buffers.tp_ring, include/hs_b200.h): the tick writes the new frame twice into
-        ``tp_ring`` [E, 2H, FD] instead of shifting a chronological [E,H,FD] tensor (1216 B/env/tick less HBM traffic for
+        ``tp_ring`` [E, 2H, FD] instead of shifting a chronological [E,H,FD] tensor (1088 B/env/tick less HBM traffic for
         the reference's shape).  The window is then :meth:`tp_window`, a strided view valid until the next tick, and
         ``out["tp_input"]`` is NOT written.  Lane-per-env tick mapping only (num_agents >= 3); call before the first
         reset / tick."""
