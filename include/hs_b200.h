@@ -310,6 +310,24 @@ int hs_state_get(hs_handle* h, int field, float* dst, void* stream);
 int hs_state_set(hs_handle* h, int field, const float* src, void* stream);
 /* Number of kernels this handle has launched so far (bench `gpu_launches`). */
 int64_t hs_launch_count(const hs_handle* h);
+/* PPO minibatch gather: make_dataset_naive (omni_drones/learning/mappo.py:493-513) yields, per minibatch,
+ * tensordict.reshape(-1)[indices] for every key of the [E, T] rollout batch, i.e. rows addressed by the flat sample id
+ * n = env * T + step.  hs_gather_rows produces those rows for up to HS_GATHER_MAX_TENSORS keys in ONE launch from tensors
+ * that are merely strided over (env, step) - the time-major [T, E, ...] rollout storage the ticks wrote, or the reference's
+ * own [E, T, ...] layout - so the flattened copy the reference makes first never exists.  Pure data movement: the result
+ * is bit-identical to the reference's indexing for the same `indices` (the caller draws the permutation, torch.randperm). */
+#define HS_GATHER_MAX_TENSORS 24
+typedef struct hs_gather_tensor {
+    const void* src;            /* element (env 0, step 0) */
+    void* dst;                  /* [num_rows][row_bytes] contiguous */
+    int64_t stride_env;         /* bytes between consecutive envs of src */
+    int64_t stride_step;        /* bytes between consecutive steps of src */
+    int32_t row_bytes;          /* bytes of one (env, step) row: contiguous in src */
+    int32_t reserved;
+} hs_gather_tensor;
+int hs_gather_rows(const hs_gather_tensor* tensors, int num_tensors, const int64_t* indices_device, int64_t num_rows,
+                   int num_steps, void* stream);
+
 /* A whole rollout of `num_ticks` control ticks (tick + predictor, as hs_step_fused) in ONE kernel launch: what the
  * collector's loop `for t in range(T): td = env.step(td)` (omni_drones/utils/torchrl/collector.py:34-66) does when the
  * actions of the T ticks are already on the device (open-loop action sequences, replayed rollouts, benchmarks) - with a
@@ -349,9 +367,9 @@ int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, 
  * tests can separate rounding amplified by the task's discontinuities from defects. */
 enum { HS_OPT_PREDICTOR_VARIANT = 1, HS_OPT_HOST_IO_GRAPH = 2, HS_OPT_HOST_IO_ZERO_COPY_ACTION = 3, HS_OPT_FUSED_TICK = 4,
        HS_OPT_EXACT_MATH = 5, HS_OPT_TICK_MAPPING = 6, HS_OPT_ROLLOUT_VARIANT = 7 };
-/* HS_OPT_ROLLOUT_VARIANT: kernel behind hs_rollout_fused = ticks the predictor warps advance per pass.  0 (default) = auto;
- * 2, 3 = hs_rollout_pair_kernel (full 32-env MMA tiles of 2 or 3 consecutive ticks ping-pong on the tensor pipe: half the
- * tensor-pipe instructions of) 1 = hs_rollout_fused_kernel (one tick at a time as two 16-env halves).  Same results. */
+/* HS_OPT_ROLLOUT_VARIANT: which kernel runs a fused rollout = how many ticks the predictor warps advance per pass.
+ * 0 (default) = auto; 2, 3 = the full 32-env MMA tiles of 2 or 3 consecutive ticks ping-pong on the tensor pipe (half
+ * the tensor-pipe instructions of variant 1); 1 = one tick at a time as two 16-env halves.  Same results. */
 /* HS_OPT_TICK_MAPPING: which work decomposition hs_step_pre / hs_reset use for the tick kernel.
  *   0 (default) = auto: 4 lanes per env (hs_tick_kernel, latency-bound small batches) below 32768 envs, one lane per
  *       env (hs_tick_wide_kernel: TMA tensor loads of the SoA state tile, bulk stores of the outputs; bandwidth-bound

@@ -10,7 +10,7 @@ from .compat import (Compose, InitTracker, SyncDataCollector, TensorDict, Transf
 from .config import Cfg, build_hs_config, compose, load_drone_params
 from .engine import HostIoLoop, HsEngine, RolloutStorage
 from . import rollout
-from .rollout import compute_gae
+from .rollout import compute_gae, gather_minibatch, make_dataset_naive
 from .policy import FusedPolicy, MAPPOActorCritic
 from . import parallel
 from .envs import AgentSpec, GenBuffer, HideAndSeek, HideAndSeek_envgen, Hover, IsaacEnv, PIDRateController, TP_net
@@ -68,6 +68,6 @@ def install_shim(force_standins: bool = False) -> dict:
     return bound
 
 
-__all__ = ["shim_path", "install_shim", "HostIoLoop", "parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "MAPPOActorCritic", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
+__all__ = ["gather_minibatch", "make_dataset_naive", "shim_path", "install_shim", "HostIoLoop", "parallel", "rollout", "compute_gae", "RolloutStorage", "FusedPolicy", "MAPPOActorCritic", "HsError", "HsEngine", "Cfg", "build_hs_config", "compose", "load_drone_params", "TensorDict",
            "TransformedEnv", "Compose", "InitTracker", "SyncDataCollector", "step_mdp", "AgentSpec",
            "HideAndSeek", "HideAndSeek_envgen", "GenBuffer", "Hover", "IsaacEnv", "PIDRateController", "TP_net"]

@@ -75,6 +75,14 @@ class hs_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _BUF_FIELDS]
 
 
+class hs_gather_tensor(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("stride_env", C.c_int64), ("stride_step", C.c_int64),
+                ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
+
+
+HS_GATHER_MAX_TENSORS = 24
+
+
 class hs_tp_weights(C.Structure):
     _fields_ = [("weight_ih", C.c_void_p), ("weight_hh", C.c_void_p), ("bias_ih", C.c_void_p),
                 ("bias_hh", C.c_void_p), ("fc_weight", C.c_void_p), ("fc_bias", C.c_void_p),
@@ -172,6 +180,7 @@ _EXPORTS = {
     "hs_step_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hs_step_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hs_step_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),
+    "hs_gather_rows": (C.c_int, [C.POINTER(hs_gather_tensor), C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "hs_rollout_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.POINTER(hs_tp_weights), C.c_void_p, C.c_int64, C.c_void_p]),
     "hs_step_post_tp": (C.c_int, [C.c_void_p, C.POINTER(hs_tp_weights), C.c_void_p, C.c_void_p]),

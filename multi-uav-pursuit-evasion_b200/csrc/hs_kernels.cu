@@ -527,6 +527,29 @@ int hs_step_fused(hs_handle* h, const float* action, int action_is_raw, const ui
     return HS_OK;
 }
 
+int hs_gather_rows(const hs_gather_tensor* tensors, int num_tensors, const int64_t* indices_device, int64_t num_rows,
+                   int num_steps, void* stream) {
+    if (!tensors || !indices_device) return set_err(HS_ERR_INVALID, "hs_gather_rows: null argument%s");
+    if (num_tensors < 1 || num_tensors > HS_GATHER_MAX_TENSORS || num_rows < 0 || num_steps < 1)
+        return set_err(HS_ERR_INVALID, "hs_gather_rows: 1 <= num_tensors <= HS_GATHER_MAX_TENSORS, num_rows >= 0, num_steps >= 1%s");
+    static_assert(GATHER_MAX_TENSORS == HS_GATHER_MAX_TENSORS, "header and kernel disagree");
+    if (num_rows == 0) return HS_OK;
+    GatherParams G;
+    memset(&G, 0, sizeof(G));
+    for (int k = 0; k < num_tensors; ++k) {
+        const hs_gather_tensor& t = tensors[k];
+        if (!t.src || !t.dst || t.row_bytes < 1) return set_err(HS_ERR_INVALID, "hs_gather_rows: a tensor has a null pointer or an empty row%s");
+        G.d[k].src = static_cast<const uint8_t*>(t.src); G.d[k].dst = static_cast<uint8_t*>(t.dst);
+        G.d[k].stride_env = t.stride_env; G.d[k].stride_step = t.stride_step; G.d[k].row_bytes = t.row_bytes;
+    }
+    G.indices = indices_device; G.num_rows = num_rows; G.T = num_steps; G.num_tensors = num_tensors;
+    const int64_t blocks = (num_rows + 7) / 8;                       // 8 warps per block, one row per warp and pass
+    dim3 grid((unsigned)(blocks < 4096 ? blocks : 4096), (unsigned)num_tensors);
+    hs_gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G);
+    CUDA_OK(cudaGetLastError());
+    return HS_OK;
+}
+
 // T control ticks (tick + predictor each) in ONE launch: hs_rollout_fused_kernel keeps a 32-env tile per CTA for the whole
 // rollout (csrc/hs_rollout_fused.cuh).  Same results as T calls of hs_step_fused.
 int hs_rollout_fused(hs_handle* h, const hs_buffers* sets_device, int num_sets, int first_set, const float* first_tp_prev,

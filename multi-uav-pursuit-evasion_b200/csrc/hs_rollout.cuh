@@ -91,4 +91,51 @@ hs_adv_normalize_kernel(float* __restrict__ adv, const double* __restrict__ mome
     if (stats_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { stats_out[0] = meanf; stats_out[1] = stdf; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PPO minibatches straight from the rollout: what make_dataset_naive
+// (omni_drones/learning/mappo.py:493-513) yields - `tensordict.reshape(-1)[indices]` for every key, with the flat
+// sample index n = env * T + step - gathered from tensors that are strided over (env, step): the engine's time-major
+// [T, E, ...] rollout storage or the reference's [E, T, ...] batch, without materialising the flattened copy first.
+// One launch gathers every key: blockIdx.y = tensor, a warp per output row; rows move as 16 / 4 / 1 byte words,
+// whichever the row size and the addresses allow.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GATHER_MAX_TENSORS = 24;
+struct GatherDesc {
+    const uint8_t* src;
+    uint8_t* dst;
+    int64_t stride_env, stride_step;     // bytes between consecutive envs / steps of the source
+    int32_t row_bytes, pad;
+};
+struct GatherParams {
+    GatherDesc d[GATHER_MAX_TENSORS];
+    const int64_t* indices;              // [num_rows] flat sample ids n = env * T + step
+    int64_t num_rows;
+    int32_t T, num_tensors;
+};
+
+__global__ void __launch_bounds__(256)
+hs_gather_rows_kernel(const __grid_constant__ GatherParams G) {
+    const GatherDesc& D = G.d[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int rb = D.row_bytes;
+    const bool v16 = (rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(D.src) | reinterpret_cast<uintptr_t>(D.dst) |
+                                          (uintptr_t)D.stride_env | (uintptr_t)D.stride_step) & 15) == 0;
+    const bool v4 = (rb & 3) == 0 && ((reinterpret_cast<uintptr_t>(D.src) | reinterpret_cast<uintptr_t>(D.dst) |
+                                        (uintptr_t)D.stride_env | (uintptr_t)D.stride_step) & 3) == 0;
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < G.num_rows; i += warps) {
+        const int64_t n = __ldg(G.indices + i);
+        const int64_t e = n / G.T, t = n - e * G.T;
+        const uint8_t* s = D.src + e * D.stride_env + t * D.stride_step;
+        uint8_t* d = D.dst + i * (int64_t)rb;
+        if (v16) {
+            for (int k = lane; k < (rb >> 4); k += 32) reinterpret_cast<uint4*>(d)[k] = __ldg(reinterpret_cast<const uint4*>(s) + k);
+        } else if (v4) {
+            for (int k = lane; k < (rb >> 2); k += 32) reinterpret_cast<uint32_t*>(d)[k] = __ldg(reinterpret_cast<const uint32_t*>(s) + k);
+        } else {
+            for (int k = lane; k < rb; k += 32) d[k] = __ldg(s + k);
+        }
+    }
+}
+
 }  // namespace

@@ -78,3 +78,77 @@ def compute_gae(reward: torch.Tensor, done: torch.Tensor, value: torch.Tensor, n
                          ret.data_ptr(), scratch.data_ptr(), stats.data_ptr() if stats is not None else None, stream),
               "hs_gae")
     return (adv, ret, stats) if return_stats else (adv, ret)
+
+
+def _flat_items(td, prefix=()):
+    """(key tuple, tensor) of every leaf of a (nested) dict / tensordict."""
+    keys = td.keys() if hasattr(td, "keys") else []
+    for k in keys:
+        v = td[k] if not hasattr(td, "get") else td.get(k)
+        kk = prefix + (k if isinstance(k, tuple) else (k,))
+        if torch.is_tensor(v):
+            yield kk, v
+        else:
+            yield from _flat_items(v, kk)
+
+
+def gather_minibatch(batch, indices: torch.Tensor, num_steps: Optional[int] = None) -> Dict[tuple, torch.Tensor]:
+    """``tensordict.reshape(-1)[indices]`` of make_dataset_naive (omni_drones/learning/mappo.py:493-513) for every leaf of
+    ``batch`` - tensors shaped ``[E, T, ...]`` in ANY memory layout whose (env, step) rows are contiguous, in particular
+    the ``[E, T]`` views of the engine's time-major rollout storage - in one kernel launch per 24 keys (hs_gather_rows);
+    the flattened copy the reference makes first never exists.  ``indices``: int64 flat sample ids n = env * T + step.
+    Returns {key tuple: [len(indices), ...] contiguous tensor}; bit-identical to the reference's indexing."""
+    items = list(_flat_items(batch))
+    if not items:
+        return {}
+    dev = items[0][1].device
+    if dev.type != "cuda":
+        raise _lib.HsError("gather_minibatch runs on the GPU only (hs_gather_rows); got tensors on " + str(dev))
+    idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+    n = idx.numel()
+    out, descs, keep = {}, [], []
+    for key, v in items:
+        if v.dim() < 2:
+            raise _lib.HsError(f"gather_minibatch: {key} must be shaped [E, T, ...]")
+        T = v.shape[1]
+        if num_steps is None:
+            num_steps = T
+        if T != num_steps:
+            raise _lib.HsError(f"gather_minibatch: {key} has {T} steps, expected {num_steps}")
+        row = v[0, 0]
+        if not row.is_contiguous():
+            v = v.contiguous()                       # rows themselves strided: rare (none of the engine's tensors)
+            row = v[0, 0]
+        keep.append(v)
+        src = v.view(torch.uint8) if v.dtype == torch.bool else v
+        dst = torch.empty((n,) + tuple(v.shape[2:]), dtype=v.dtype, device=dev)
+        out[key] = dst
+        d = _lib.hs_gather_tensor()
+        d.src, d.dst = src.data_ptr(), dst.data_ptr()
+        d.stride_env, d.stride_step = v.stride(0) * v.element_size(), v.stride(1) * v.element_size()
+        d.row_bytes = max(1, row.numel()) * v.element_size()
+        descs.append(d)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        for i in range(0, len(descs), _lib.HS_GATHER_MAX_TENSORS):
+            chunk = descs[i:i + _lib.HS_GATHER_MAX_TENSORS]
+            arr = (_lib.hs_gather_tensor * len(chunk))(*chunk)
+            check(lib.hs_gather_rows(arr, len(chunk), idx.data_ptr(), n, int(num_steps), stream), "hs_gather_rows")
+    return out
+
+
+def make_dataset_naive(batch, num_minibatches: int = 4, seq_len: int = 1, perm: Optional[torch.Tensor] = None):
+    """omni_drones/learning/mappo.py:493-513 for seq_len == 1 (the reference's default: MAPPOPolicy has no
+    ``minibatch_seq_len``): a random permutation of the first (E*T // M) * M flat samples, split into M minibatches, each
+    gathered with :func:`gather_minibatch`.  ``perm`` (optional) supplies the permutation, e.g. the reference's own
+    ``torch.randperm`` draw; yields {key tuple: tensor} per minibatch."""
+    if seq_len != 1:
+        raise _lib.HsError("make_dataset_naive: only seq_len == 1 (the reference's default) is built")
+    first = next(_flat_items(batch))[1]
+    E, T = first.shape[:2]
+    total = (E * T // num_minibatches) * num_minibatches
+    if perm is None:
+        perm = torch.randperm(total, device=first.device)
+    perm = perm.reshape(num_minibatches, -1)
+    for indices in perm:
+        yield gather_minibatch(batch, indices, T)
