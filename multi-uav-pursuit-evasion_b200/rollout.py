@@ -138,17 +138,26 @@ def gather_minibatch(batch, indices: torch.Tensor, num_steps: Optional[int] = No
 
 
 def make_dataset_naive(batch, num_minibatches: int = 4, seq_len: int = 1, perm: Optional[torch.Tensor] = None):
-    """omni_drones/learning/mappo.py:493-513 for seq_len == 1 (the reference's default: MAPPOPolicy has no
-    ``minibatch_seq_len``): a random permutation of the first (E*T // M) * M flat samples, split into M minibatches, each
-    gathered with :func:`gather_minibatch`.  ``perm`` (optional) supplies the permutation, e.g. the reference's own
-    ``torch.randperm`` draw; yields {key tuple: tensor} per minibatch."""
-    if seq_len != 1:
-        raise _lib.HsError("make_dataset_naive: only seq_len == 1 (the reference's default) is built")
+    """omni_drones/learning/mappo.py:493-513: a random permutation of the first (N // M) * M samples, split into M
+    minibatches, each gathered with :func:`gather_minibatch`.  seq_len == 1 (the reference's default: MAPPOPolicy has no
+    ``minibatch_seq_len``): N = E * T flat samples, minibatch tensors ``[N / M, ...]``.  seq_len = L > 1: the steps are cut
+    into T // L chunks, N = E * (T // L) samples of L consecutive steps, minibatch tensors ``[N / M, L, ...]``.  ``perm``
+    (optional) supplies the permutation, e.g. the reference's own ``torch.randperm`` draw; yields {key tuple: tensor}."""
     first = next(_flat_items(batch))[1]
     E, T = first.shape[:2]
-    total = (E * T // num_minibatches) * num_minibatches
+    L = int(seq_len)
+    chunks = T // L if L > 1 else T
+    total = (E * chunks // num_minibatches) * num_minibatches
     if perm is None:
         perm = torch.randperm(total, device=first.device)
-    perm = perm.reshape(num_minibatches, -1)
+    perm = perm.to(first.device).reshape(num_minibatches, -1)
+    steps = torch.arange(L, device=first.device) if L > 1 else None
     for indices in perm:
-        yield gather_minibatch(batch, indices, T)
+        if L == 1:
+            yield gather_minibatch(batch, indices, T)
+        else:
+            # sample s = env * chunks + chunk  ->  flat rows env * T + chunk * L + (0 .. L-1)
+            env, chunk = indices // chunks, indices % chunks
+            rows = ((env * T + chunk * L).unsqueeze(1) + steps).reshape(-1)
+            mb = gather_minibatch(batch, rows, T)
+            yield {k: v.view(indices.numel(), L, *v.shape[1:]) for k, v in mb.items()}

@@ -56,6 +56,16 @@ def main():
         # sanity: the recorded permutation reproduces the minibatch
         idx = perm.reshape(M, -1)[m]
         assert torch.equal(batch["reward"].reshape(E * T, A, 1)[idx], td.d["reward"])
+    # seq_len = 2: chunks of two consecutive steps (T = 5 -> the last step is dropped), 12 samples, 3 per minibatch
+    torch.manual_seed(6)
+    state = torch.get_rng_state()
+    outs2 = list(ns["make_dataset_naive"](MiniTD(batch, (E, T)), M, 2))
+    torch.set_rng_state(state)
+    perm2 = torch.randperm((E * (T // 2) // M) * M)
+    out["perm_seq2"] = perm2.numpy()
+    for m, td in enumerate(outs2):
+        for k, v in td.d.items():
+            out[f"seq2_mb{m}_{k}"] = v.numpy()
     path = os.path.join(REPO, "tests", "golden", "minibatch.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(outs), "minibatches of", outs[0].shape[0], "samples")

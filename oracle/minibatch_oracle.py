@@ -14,3 +14,17 @@ def minibatches(batch: dict, perm: np.ndarray, num_minibatches: int):
     """perm: the reference's randperm over the first (E*T // M) * M samples."""
     for indices in perm.reshape(num_minibatches, -1):
         yield {k: gather(v, indices) for k, v in batch.items()}
+
+
+def minibatches_seq(batch: dict, perm: np.ndarray, num_minibatches: int, seq_len: int):
+    """seq_len > 1 branch (mappo.py:496-505): samples = (env, chunk of seq_len consecutive steps)."""
+    out = []
+    for indices in perm.reshape(num_minibatches, -1):
+        mb = {}
+        for k, v in batch.items():
+            E, T = v.shape[:2]
+            Tc = (T // seq_len) * seq_len
+            flat = np.ascontiguousarray(v[:, :Tc]).reshape((E * (Tc // seq_len), seq_len) + v.shape[2:])
+            mb[k] = flat[indices]
+        out.append(mb)
+    return out

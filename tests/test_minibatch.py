@@ -25,6 +25,27 @@ def test_oracle_matches_the_reference_minibatches():
             assert np.array_equal(v, z[f"mb{m}_{k}"]), (m, k)
 
 
+def test_oracle_matches_the_reference_minibatches_of_step_chunks():
+    z, batch, E, T, M = _load()
+    for m, mb in enumerate(MO.minibatches_seq(batch, z["perm_seq2"], M, 2)):
+        for k, v in mb.items():
+            assert np.array_equal(v, z[f"seq2_mb{m}_{k}"]), (m, k)
+
+
+@pytest.mark.gpu
+def test_gather_matches_the_reference_minibatches_of_step_chunks():
+    """seq_len = 2 (mappo.py:496-505): samples of two consecutive steps, from time-major storage views."""
+    import mupe_b200
+    z, batch, E, T, M = _load()
+    dev = torch.device("cuda:0")
+    tb = {k: torch.from_numpy(v).to(dev).transpose(0, 1).contiguous().transpose(0, 1) for k, v in batch.items()}
+    got = list(mupe_b200.make_dataset_naive(tb, M, seq_len=2, perm=torch.from_numpy(z["perm_seq2"])))
+    assert len(got) == M
+    for m, mb in enumerate(got):
+        for k in batch:
+            assert np.array_equal(mb[(k,)].cpu().numpy(), z[f"seq2_mb{m}_{k}"]), (m, k)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout", ["env_major", "time_major"])
 def test_gather_matches_the_reference_minibatches(layout):
@@ -73,6 +94,6 @@ def test_gather_full_size_from_the_rollout_storage():
     a = next(iter(mupe_b200.make_dataset_naive(sel, M)))[("reward",)]
     c = next(iter(mupe_b200.make_dataset_naive(sel, M)))[("reward",)]
     assert not torch.equal(a, c)
-    with pytest.raises(mupe_b200.HsError):
-        list(mupe_b200.make_dataset_naive(sel, M, seq_len=8))
+    mb8 = next(iter(mupe_b200.make_dataset_naive(sel, M, seq_len=8)))
+    assert tuple(mb8[("reward",)].shape) == (E * (T // 8) // M, 8, 3, 1)
     eng.close()
