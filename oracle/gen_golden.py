@@ -46,6 +46,7 @@ CASES = {
 CASES["obstacles_tp"] = (dict(use_obstacles=True), 12, "random_cylinders", 4, 4, None)     # cylinders inside the TP frame
 # four pursuers: the reference's fixed scenarios carry four start rows (hideandseek.py:633-682); 19-float TP frame
 CASES["a4_narrow_gap_tp"] = (dict(num_agents=4, num_cylinders=5), 12, "narrow_gap", 4, 4, None)
+CASES["random6_tp"] = (dict(num_cylinders=6), 12, "random", 4, 4, None)      # the fifth fixed scenario (hideandseek.py:512-521, 663-672)
 CASES["a4_random_tp"] = (dict(num_agents=4, num_cylinders=5), 12, "random_cylinders", 4, 4, None)
 UPDATE_EPOCHS = {"deploy_epoch_tp": [0, 3, 3, 20]}        # -> 0.5, 1.7, 1.7, min(5, 8.5)
 
